@@ -1,0 +1,43 @@
+"""Synthetic inputs of the BASELINE.json configs, seeded and prefix-stable:
+the first M trajectories are the same for every ensemble size N >= M, so the golden fixtures
+(first 1024 / 512 trajectories) are literally a prefix of the 2^20 / 2^24 benchmark ensembles."""
+import numpy as np
+
+LORENZ = dict(sigma=10.0, rho=28.0, beta=8.0 / 3.0, t0=0.0, tf=2.0, dt0=1e-2, rtol=1e-9, atol=1e-9)
+VDP = dict(t0=0.0, tf=10.0, dt0=1e-2, rtol=1e-9, atol=1e-9)
+NBODY = dict(bodies=64, G=1.0, eps2=1e-4, t0=0.0, tf=0.1, dt=0.01)
+LINEAR = dict(t0=0.0, tf=1.0, dt0=1e-2, rtol=1e-9, atol=1e-9)
+
+
+def lorenz_ensemble(n, seed=0):
+    """y0 (3, n) ~ U([-20,20] x [-25,25] x [0,50])."""
+    rng = np.random.default_rng(seed)
+    y0 = rng.uniform([-20.0, -25.0, 0.0], [20.0, 25.0, 50.0], size=(n, 3))
+    return np.ascontiguousarray(y0.T)
+
+
+def vdp_ensemble(n, seed=0):
+    """(y0 (2, n) ~ U([-2,2]^2), mu (n,) with log10 mu ~ U(-1, 1))."""
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(size=(n, 3))
+    mu = 10.0 ** (2.0 * u[:, 0] - 1.0)
+    y0 = 4.0 * u[:, 1:] - 2.0
+    return np.ascontiguousarray(y0.T), np.ascontiguousarray(mu)
+
+
+def linear_system(n, columns, seed=0):
+    """(A (n, n) near-skew with -0.1 I damping, Y0 (n, columns) ~ N(0,1))."""
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((n, n))
+    a = (g - g.T) / np.sqrt(2.0 * n) - 0.1 * np.eye(n)
+    y0 = rng.standard_normal((n, columns))
+    return np.ascontiguousarray(a), np.ascontiguousarray(y0)
+
+
+def nbody_ensemble(systems, bodies=64, seed=0):
+    """state (2, systems, bodies, 3) = (q ~ N(0,1); v ~ 0.1 N(0,1)), masses (bodies,) = 1/bodies."""
+    rng = np.random.default_rng(seed)
+    qv = rng.standard_normal((systems, 2, bodies, 3))
+    qv[:, 1] *= 0.1
+    state = np.ascontiguousarray(np.moveaxis(qv, 1, 0))
+    return state, np.full(bodies, 1.0 / bodies)

@@ -1,0 +1,97 @@
+"""Built-in right-hand sides: plain Python callables TAGGED with a fused device plugin.
+
+Each function is an ordinary `rhs(t, y, **constants)` callable in the reference's RHS protocol
+(/root/reference/desolver/differential_system.py:338-344, 536-539): it works on numpy arrays and
+torch tensors alike, so the unmodified reference can integrate it (that is how the fixtures in
+tests/golden/ were produced).  The `device_plugin` attribute names the fused sm_100a
+implementation in desolver_b200/csrc/ that `OdeSystem(..., ensemble=True)` dispatches to, and
+`plugin_params` lists, in ABI order, the `constants` keys that the kernel reads per trajectory.
+`DiffRHS` forwards unknown attribute reads to the wrapped callable (reference :438-439), so the
+tag survives wrapping.
+"""
+
+# ids shared with include/desolver_b200.h (DSB_RHS_*) and oracle/desolver_oracle.h (ORC_RHS_*)
+RHS_LINEAR, RHS_LORENZ, RHS_VDP, RHS_NBODY, RHS_SHO = 0, 1, 2, 3, 4
+
+
+def _stack(parts, like):
+    if type(like).__module__.split(".")[0] == "torch":
+        import torch
+        return torch.stack(parts)
+    import numpy
+    return numpy.stack(parts)
+
+
+def lorenz(t, y, sigma=10.0, rho=28.0, beta=8.0 / 3.0):
+    """Lorenz-63.  y[0], y[1], y[2] = x, y, z (trailing axes broadcast over an ensemble)."""
+    x, v, z = y[0], y[1], y[2]
+    return _stack([sigma * (v - x), x * (rho - z) - v, x * v - beta * z], y)
+
+
+lorenz.device_plugin = "lorenz"
+lorenz.plugin_id = RHS_LORENZ
+lorenz.plugin_params = ("sigma", "rho", "beta")
+lorenz.plugin_defaults = dict(sigma=10.0, rho=28.0, beta=8.0 / 3.0)
+
+
+def van_der_pol(t, y, mu=1.0):
+    """Van der Pol oscillator, y = (x, v): x' = v, v' = mu (1 - x^2) v - x."""
+    x, v = y[0], y[1]
+    return _stack([v, mu * (1 - x * x) * v - x], y)
+
+
+van_der_pol.device_plugin = "van_der_pol"
+van_der_pol.plugin_id = RHS_VDP
+van_der_pol.plugin_params = ("mu",)
+van_der_pol.plugin_defaults = dict(mu=1.0)
+
+
+def harmonic_oscillator(t, y, k=1.0, m=1.0):
+    """README oscillator, y = (x, v): x' = v, v' = -(k/m) x.
+
+    Equal, bit for bit on finite inputs, to the reference README's `[[0,1],[-k/m,0]] @ y`
+    (/root/reference/docs/examples/getting_started.py:15-24): the products with 0 and 1 are exact.
+    """
+    return _stack([y[1], -(k / m) * y[0]], y)
+
+
+harmonic_oscillator.device_plugin = "harmonic_oscillator"
+harmonic_oscillator.plugin_id = RHS_SHO
+harmonic_oscillator.plugin_params = ("k", "m")
+harmonic_oscillator.plugin_defaults = dict(k=1.0, m=1.0)
+
+
+def linear(t, y, A=None):
+    """Dense linear system y' = A @ y (A shared by the whole ensemble; y is (n,) or (n, N))."""
+    return A @ y
+
+
+linear.device_plugin = "linear"
+linear.plugin_id = RHS_LINEAR
+linear.plugin_params = ()
+linear.plugin_shared = ("A",)
+
+
+def nbody(t, y, m=None, eps2=0.0, G=1.0):
+    """Softened gravitational N-body.  y = (2, [B,] nb, 3): y[0] positions, y[1] velocities."""
+    q, v = y[0], y[1]
+    d = q[..., None, :, :] - q[..., :, None, :]            # d[i, j] = q[j] - q[i]
+    r2 = (d * d).sum(-1) + eps2
+    w = m * r2 ** -1.5                                      # m broadcasts over j (last axis)
+    nb = q.shape[-2]
+    if type(y).__module__.split(".")[0] == "torch":
+        import torch
+        w = w * (1.0 - torch.eye(nb, dtype=w.dtype, device=w.device))
+    else:
+        import numpy
+        w = w * (1.0 - numpy.eye(nb))
+    acc = G * (d * w[..., None]).sum(-2)
+    return _stack([v, acc], y)
+
+
+nbody.device_plugin = "nbody"
+nbody.plugin_id = RHS_NBODY
+nbody.plugin_params = ()
+nbody.plugin_shared = ("G", "eps2", "m")
+
+BUILTIN = {f.device_plugin: f for f in (lorenz, van_der_pol, harmonic_oscillator, linear, nbody)}

@@ -1,0 +1,143 @@
+/*
+ * desolver_b200.h -- C ABI of libdesolver_b200.so: the B200 (sm_100a) ensemble-integration
+ * engine that sits behind desolver's Python API.
+ *
+ * The reference (Microno95/desolver v5.1.0, pure Python) has no FFI; its seams are Python
+ * protocols.  Each entry point below states which reference code it
+ * replaces (paths relative to /root/reference/desolver/).  Conventions:
+ *   - plain C, no C++ types or exceptions cross the boundary;
+ *   - every call returns a dsb_status (0 = OK); dsb_last_error() gives a thread-local message;
+ *   - all array arguments are BORROWED raw DEVICE pointers owned by the caller (torch tensors
+ *     on the Python side); the library never allocates, frees or resizes them;
+ *   - every launch goes to the explicit `stream` argument (a cudaStream_t passed as void*);
+ *     no call synchronises the device or the stream;
+ *   - ensemble state is SoA: y[dim][n] (trajectory index fastest), t[n], dt[n];
+ *   - tableaux are passed in from the Python class data (cls.tableau_intermediate /
+ *     tableau_final / __order__), so there is one source of truth for coefficients.
+ * One handle per (device, method, right-hand side); handles are not thread-safe.
+ */
+#ifndef DESOLVER_B200_H
+#define DESOLVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSB_ABI_VERSION 1
+
+typedef enum {
+    DSB_OK = 0,
+    DSB_ERR_BAD_ARGUMENT = 1,
+    DSB_ERR_CUDA = 2,
+    DSB_ERR_UNSUPPORTED = 3   /* no fused kernel for this (rhs, method, dim) combination */
+} dsb_status;
+
+/* Built-in fused right-hand sides (desolver_b200/rhs_plugins.py tags the Python callables). */
+typedef enum {
+    DSB_RHS_LINEAR = 0,  /* y' = A y            (stage-level path + dsb_linear_rhs)          */
+    DSB_RHS_LORENZ = 1,  /* params: sigma, rho, beta                                          */
+    DSB_RHS_VDP    = 2,  /* params: mu                                                        */
+    DSB_RHS_NBODY  = 3,  /* state (2, nb, 3) per system; shared: G, eps2, masses              */
+    DSB_RHS_SHO    = 4,  /* params: k, m                                                      */
+    DSB_RHS_EXTERNAL = 100 /* arbitrary torch callable evaluated between stage kernels       */
+} dsb_rhs_id;
+
+/* Per-trajectory status word written by the kernels.  The Python side maps
+ * DSB_TRAJ_TOL_FAIL to exception_types.FailedToMeetTolerances wrapped in FailedIntegration
+ * (differential_system.py:1089-1093, integrators/integrator_types.py:220-224). */
+typedef enum {
+    DSB_TRAJ_DONE = 0,      /* reached tf                                                     */
+    DSB_TRAJ_TOL_FAIL = 1,  /* 64 retries exhausted; state frozen at the failed step's start  */
+    DSB_TRAJ_RUNNING = 2    /* step budget of this call exhausted before tf (chunked runs)    */
+} dsb_traj_status;
+
+#define DSB_FLAG_STRICT 1u  /* reference operation order, no FMA contraction, libm pow/atan   */
+
+#define DSB_MAX_PARAMS 4
+#define DSB_MAX_FUSED_STAGES 17
+
+/* ---- library ------------------------------------------------------------------------- */
+int         dsb_abi_version(void);
+const char *dsb_build_info(void);      /* contains "sm_100a"                                 */
+const char *dsb_last_error(void);
+
+/* ---- fused explicit Runge-Kutta ensemble engine ----------------------------------------
+ * Replaces, for a built-in right-hand side, the whole of OdeSystem.integrate's while loop
+ * (differential_system.py:996-1084) together with RungeKuttaIntegrator.__call__/step/
+ * get_error_estimate (integrators/integrator_types.py:162-228, 267-323), compute_step
+ * (integrators/components/runge_kutta_methods.py:44-54) and update_timestep
+ * (integrators/integrator_template.py:46-93), once per trajectory, in ONE persistent launch. */
+typedef struct dsb_erk_plan *dsb_erk_handle;
+
+int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int stages,
+                   const double *tableau_intermediate, /* stages x (stages+1), host */
+                   const double *tableau_final,        /* final_rows x (stages+1), host */
+                   int final_rows, double order, unsigned flags);
+int dsb_erk_destroy(dsb_erk_handle h);
+
+typedef struct {
+    int64_t n;                 /* trajectories in this shard                                   */
+    double *y;                 /* [dim][n] in/out                                              */
+    double *t;                 /* [n] in/out                                                   */
+    double *dt;                /* [n] in/out: step size to try next (reference self.dt)        */
+    const double *params[DSB_MAX_PARAMS];   /* per-RHS parameter arrays (device)              */
+    int64_t param_stride[DSB_MAX_PARAMS];   /* 1 = per trajectory, 0 = one shared value        */
+    double tf, rtol, atol;
+    int32_t *accepted;         /* [n] += accepted steps                                        */
+    int32_t *rejected;         /* [n] += rejected attempts                                     */
+    int32_t *status;           /* [n] dsb_traj_status (TOL_FAIL entries are skipped on entry)  */
+    int64_t max_steps;         /* accepted-step budget per trajectory for this call, <0 = none */
+    int32_t first_call;        /* 1: apply integrate()'s entry logic (:956-957, :971-974)      */
+    /* dense output (NULL = off): per trajectory `node_capacity` records of (t, y[dim], f[dim]) */
+    double *nodes;             /* [n][node_capacity][1 + 2*dim]                                */
+    int32_t *node_count;       /* [n] in/out                                                   */
+    int32_t node_capacity;
+    uint64_t *counters;        /* device, >= 4 words, zeroed by the caller: [0] work queue     */
+} dsb_erk_run_args;
+
+int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);
+/* number of kernel launches dsb_erk_run issues per call (for bench accounting) */
+int dsb_erk_run_launches(dsb_erk_handle h);
+
+/* ---- stage-level explicit RK (arbitrary right-hand side between kernels) -----------------
+ * For a torch callable the Python side calls, per attempt and on one stream:
+ *   for s in stages: dsb_erk_stage_state(s) -> rhs(t_stage, y_stage) written into K[s]
+ *   dsb_erk_attempt_finish()  (dY, error estimate, per-trajectory L2 norm, controller,
+ *                              masked commit, counters, active count)
+ * K is [stages][dim][n]. */
+typedef struct {
+    int64_t n;
+    int32_t dim;               /* flattened state size of one trajectory                       */
+    double *y, *t, *dt;        /* committed state, as in dsb_erk_run_args                      */
+    double *h;                 /* [n] step size of the attempt in flight                       */
+    double *h0;                /* [n] first step size of the current retry chain               */
+    double *K;                 /* [stages][dim][n]                                             */
+    double *y_stage;           /* [dim][n] out of dsb_erk_stage_state                          */
+    double *t_stage;           /* [n]      out of dsb_erk_stage_state                          */
+    double *scale;             /* [dim][n] controller scale (EMA on retries)                   */
+    double *err_hist;          /* [2][n]  eps_last, eps_last_last                              */
+    int32_t *trial;            /* [n] attempt number inside the current step                   */
+    int32_t *flags;            /* [n] bit0 active, bit1 final-step                             */
+    double tf, rtol, atol;
+    int32_t *accepted, *rejected, *status;
+    uint64_t *counters;        /* [0] active trajectories after the attempt                    */
+} dsb_erk_stage_args;
+
+int dsb_erk_attempt_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);
+int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage, void *stream);
+int dsb_erk_attempt_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream);
+
+/* ---- dense output ------------------------------------------------------------------------
+ * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
+ * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written
+ * by dsb_erk_run: out[d][i] = Hermite interpolant of trajectory i at tq[i*tq_stride]. */
+int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
+                   int32_t node_capacity, const double *tq, int64_t tq_stride,
+                   double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESOLVER_B200_H */
