@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ensemble engine (BASELINE.json metric):
+trajectory-steps/s, RK45 (Cash-Karp) adaptive fp64, Lorenz-63, 2^20 trajectories per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over the batch: every trajectory of the ensemble is
+integrated from t=0 to t=2 (rtol=atol=1e-9, dt0=1e-2), ~254 step attempts each.  A
+"trajectory-step" is one step ATTEMPT of one trajectory (accepted or rejected: same work); the
+count comes from the per-trajectory device counters of the same run.
+
+ value     device-timed (CUDA events on the launch stream), inputs resident in HBM.
+ e2e       same metric through the public API (`OdeSystem(...).integrate()`) with HOST buffers:
+           pinned host y0 -> device, integrate, final state + counters -> host, all timed.
+ roofline  algorithmic bytes (80 B per Lorenz trajectory-step: read+write y(3), t, dt)
+           over the fused kernel's event-timed duration, against the measured HBM copy bandwidth.
+ cpu_baseline  the CPU oracle (port of the reference algorithm, C) on this box's host cores, on a
+           bounded sample of the same ensemble; `--impl reference` runs ONLY that.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1 << 20
+BYTES_PER_TRAJ_STEP = 80.0          # 2*8*(dim+2), SURVEY.md section 8d
+METRIC = "trajectory-steps/s (RK45 Cash-Karp adaptive fp64, Lorenz-63, 2^20 trajectories per GPU, t in [0,2], tol 1e-9)"
+UNIT = "trajectory-steps/s"
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_sample(seconds_budget, n_global, rank_stride=1):
+    """Times the CPU oracle (oracle/desolver_oracle.c) on a bounded prefix of the same ensemble,
+    all host threads, one contiguous shard per thread.  Returns (steps_per_s, cores, sample_desc)."""
+    from desolver_b200 import benchmarks as bm
+    from desolver_b200.integrators import tableaux as tb
+    from oracle import oracle as orc
+    cfg = bm.LORENZ
+    threads = host_threads()
+    tab = tb.rk_arrays("RK45CKSolver")
+    params = [cfg["sigma"], cfg["rho"], cfg["beta"]]
+    # calibrate on a small piece, then size the sample for ~seconds_budget of wall time
+    y_small = bm.lorenz_ensemble(256 * threads)
+    t0 = time.perf_counter()
+    r = orc.erk_ensemble(orc.RHS_LORENZ, y_small, cfg["t0"], cfg["tf"], cfg["dt0"], cfg["rtol"], cfg["atol"], *tab,
+                         params=params, threads=threads)
+    rate = float((r["accepted"] + r["rejected"]).sum()) / (time.perf_counter() - t0)
+    m = int(min(n_global, max(1024 * threads, rate * seconds_budget / 255.0)))
+    y0 = bm.lorenz_ensemble(m)
+    t0 = time.perf_counter()
+    r = orc.erk_ensemble(orc.RHS_LORENZ, y0, cfg["t0"], cfg["tf"], cfg["dt0"], cfg["rtol"], cfg["atol"], *tab,
+                         params=params, threads=threads)
+    wall = time.perf_counter() - t0
+    steps = float((r["accepted"] + r["rejected"]).sum())
+    return steps / wall, threads, "first %d trajectories of the Lorenz ensemble, %.1f s wall" % (m, wall), steps, wall
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 100 ms during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference algorithm's CPU implementation (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_global = N_PER_GPU * args.gpus
+    per_step = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        rate, cores, sample, steps, wall = cpu_reference_sample(args.cpu_seconds, n_global)
+        if i >= args.warmup:
+            per_step.append((steps, wall))
+            info = (cores, sample)
+    total_steps = sum(s for s, _ in per_step)
+    total_wall = sum(w for _, w in per_step)
+    value = total_steps / total_wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "lorenz63_rk45ck_2^20_per_gpu", "sample": info[1]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[0], "kind": "port", "sample": info[1]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the CPU baseline sample")
+    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import desolver_b200 as de
+    from desolver_b200.backend import cuda_backend as cb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; desolver_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = max(world, 1)
+    n_local = args.n_per_gpu
+    cfg = de.benchmarks.LORENZ
+
+    # global ensemble of n_gpus * 2^20 trajectories, dealt round-robin: trajectory i -> rank i mod G
+    y0_host = de.benchmarks.lorenz_ensemble(n_local * n_gpus)[:, rank::n_gpus]
+    y0_pinned = torch.from_numpy(np.ascontiguousarray(y0_host)).pin_memory()
+    y0_dev = y0_pinned.to(dev)
+
+    sys_ = de.OdeSystem(de.rhs_plugins.lorenz, y0_dev, t=(cfg["t0"], cfg["tf"]), dt=cfg["dt0"], rtol=cfg["rtol"],
+                        atol=cfg["atol"], constants=dict(sigma=cfg["sigma"], rho=cfg["rho"], beta=cfg["beta"]),
+                        ensemble=True)
+    sys_.method = "RK45"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(ev=None):
+        """device-resident step: reset state from y0 (device copy), integrate, reduce the counters"""
+        sys_.reset()
+        if ev:
+            ev[0].record()
+        sys_.integrate()
+        if ev:
+            ev[1].record()
+        att = (sys_.accepted.sum(dtype=torch.float64) + sys_.rejected.sum(dtype=torch.float64))
+        stats[0] = att
+        stats[1] = (sys_.status != 0).sum().to(torch.float64)
+        if world > 1:
+            dist.all_reduce(stats)            # termination / statistics all-reduce (NCCL)
+        return stats
+
+    for _ in range(args.warmup):
+        one_step()
+        flush.zero_()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = sys_._launches
+    total_attempts = 0.0
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        step_ev[i][0].record()
+        st = one_step(kern_ev[i])
+        step_ev[i][1].record()
+        flush.zero_()                          # L2 flush between timed iterations (outside the events)
+        total_attempts_dev = st.clone()
+        if i == args.steps - 1:
+            pass
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in step_ev]
+    kern_ms = [a.elapsed_time(b) for a, b in kern_ev]
+    launches = sys_._launches - launches0
+    attempts_global = float(total_attempts_dev[0].item())       # per step, all ranks (already all-reduced)
+    failed = float(total_attempts_dev[1].item())
+    attempts_local = float((sys_.accepted.sum() + sys_.rejected.sum()).item())
+    accepted_local = float(sys_.accepted.sum().item())
+    t_local = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    total_ms, total_kern_ms = float(t_local[0]), float(t_local[1])
+    value = attempts_global * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: public API with host buffers (pinned y0 -> device, integrate, results -> host) ----
+    e2e_steps = max(2, min(args.steps, 5))
+    out_y = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
+    out_c = torch.empty((3, n_local), dtype=torch.int32).pin_memory()
+    e2e_ms = []
+    for i in range(1 + e2e_steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        s2 = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned.to(dev, non_blocking=True), t=(cfg["t0"], cfg["tf"]),
+                          dt=cfg["dt0"], rtol=cfg["rtol"], atol=cfg["atol"], ensemble=True)
+        s2.integrate()
+        out_y.copy_(s2[-1].y, non_blocking=True)
+        out_c[0].copy_(s2.accepted, non_blocking=True)
+        out_c[1].copy_(s2.rejected, non_blocking=True)
+        out_c[2].copy_(s2.status, non_blocking=True)
+        b.record()
+        barrier()
+        if i > 0:
+            e2e_ms.append(a.elapsed_time(b))
+        flush.zero_()
+    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = attempts_global / (float(e2e_t[0]) * 1e-3)
+    h2d = int(y0_pinned.numel() * 8)
+    d2h = int(out_y.numel() * 8 + out_c.numel() * 4)
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        kern_s = (total_kern_ms / args.steps) * 1e-3
+        achieved = attempts_local * BYTES_PER_TRAJ_STEP / kern_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "erk_fused_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "lorenz63_rk45ck_2^20_per_gpu", "trajectories_per_gpu": n_local,
+                           "t_span": [cfg["t0"], cfg["tf"]], "rtol": cfg["rtol"], "atol": cfg["atol"], "dt0": cfg["dt0"],
+                           "method": "RK45CK", "l2": "flushed between timed iterations (256 MiB memset)",
+                           "sharding": "round-robin over ranks, no data-path collective",
+                           "attempts_per_step": attempts_global, "accepted_local": accepted_local,
+                           "failed_trajectories": failed, "wall_s_timed_region": wall},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": peak_kind, "kernel": "dsb::erk_fused_kernel<Lorenz,6>",
+                             "kernel_ms": total_kern_ms / args.steps,
+                             "algorithmic_bytes_per_launch": attempts_local * BYTES_PER_TRAJ_STEP,
+                             "trajectory_steps_per_s_kernel": attempts_local / kern_s},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": float(e2e_t[0])},
+                "gpu_launches": launches}
+        if not args.no_cpu_baseline:
+            rate, cores, sample, _, _ = cpu_reference_sample(args.cpu_seconds, n_local * n_gpus)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

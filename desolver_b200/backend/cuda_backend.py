@@ -1,0 +1,140 @@
+"""Loader of libdesolver_b200.so and the ctypes mirror of include/desolver_b200.h.
+
+The library is the product: if it is missing or cannot be loaded, every entry point of the
+package that needs it raises -- there is no eager/PyTorch/CPU fallback.  torch is used for
+device memory (`tensor.data_ptr()`), streams (`torch.cuda.current_stream().cuda_stream`) and
+`torch.distributed`; all arithmetic of the hot path happens in the library's kernels.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_PKG, "libdesolver_b200.so")
+
+DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED = 0, 1, 2, 3
+TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING = 0, 1, 2
+FLAG_STRICT = 1
+MAX_PARAMS = 4
+FUSED_STAGES = (1, 2, 4, 6, 7, 13, 17)
+
+_dp = C.POINTER(C.c_double)
+
+
+class ErkRunArgs(C.Structure):
+    """dsb_erk_run_args (include/desolver_b200.h).  Pointers are raw device addresses."""
+    _fields_ = [
+        ("n", C.c_int64),
+        ("y", C.c_void_p), ("t", C.c_void_p), ("dt", C.c_void_p),
+        ("params", C.c_void_p * MAX_PARAMS),
+        ("param_stride", C.c_int64 * MAX_PARAMS),
+        ("tf", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
+        ("accepted", C.c_void_p), ("rejected", C.c_void_p), ("status", C.c_void_p),
+        ("max_steps", C.c_int64),
+        ("first_call", C.c_int32),
+        ("nodes", C.c_void_p), ("node_count", C.c_void_p), ("node_capacity", C.c_int32),
+        ("counters", C.c_void_p),
+    ]
+
+
+class LibraryError(RuntimeError):
+    """A dsb_* call returned a non-zero status."""
+
+
+_lib = None
+
+
+def library_path():
+    return _SO
+
+
+def build(force=False, jobs=None):
+    """Compile the library in-tree with nvcc for sm_100a (needs no GPU)."""
+    cmd = ["make", "-C", os.path.join(_PKG, "csrc"), "-j%d" % (jobs or os.cpu_count() or 4)]
+    if force:
+        cmd.append("-B")
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def is_available():
+    return os.path.exists(_SO)
+
+
+def lib():
+    """The loaded library (ctypes.CDLL) with prototypes set.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise ImportError(
+            "libdesolver_b200.so not found at %s: build it with `python -c \"import __graft_entry__ as g; "
+            "g.build()\"` or `make -C desolver_b200/csrc`.  desolver_b200 has no CPU fallback." % _SO)
+    L = C.CDLL(_SO)
+    L.dsb_abi_version.restype = C.c_int
+    L.dsb_build_info.restype = C.c_char_p
+    L.dsb_last_error.restype = C.c_char_p
+    L.dsb_erk_create.restype = C.c_int
+    L.dsb_erk_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                 C.c_double, C.c_uint]
+    L.dsb_erk_destroy.restype = C.c_int
+    L.dsb_erk_destroy.argtypes = [C.c_void_p]
+    L.dsb_erk_run.restype = C.c_int
+    L.dsb_erk_run.argtypes = [C.c_void_p, C.POINTER(ErkRunArgs), C.c_void_p]
+    L.dsb_erk_run_launches.restype = C.c_int
+    L.dsb_erk_run_launches.argtypes = [C.c_void_p]
+    L.dsb_dense_eval.restype = C.c_int
+    L.dsb_dense_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p]
+    if L.dsb_abi_version() != 1:
+        raise ImportError("libdesolver_b200.so has ABI version %d, expected 1" % L.dsb_abi_version())
+    _lib = L
+    return L
+
+
+def check(status, what=""):
+    if status != DSB_OK:
+        msg = lib().dsb_last_error().decode("utf-8", "replace")
+        raise LibraryError("%s failed with status %d: %s" % (what or "libdesolver_b200 call", status, msg))
+
+
+def current_stream_ptr(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class ErkHandle:
+    """Owns one dsb_erk_handle: (device, right-hand side, method tableau)."""
+
+    def __init__(self, device_index, rhs_id, dim, tableau_intermediate, tableau_final, order, strict=False):
+        import numpy as np
+        inter = np.ascontiguousarray(tableau_intermediate, dtype=np.float64)
+        final = np.ascontiguousarray(np.atleast_2d(tableau_final), dtype=np.float64)
+        self._keep = (inter, final)
+        self.stages = inter.shape[0]
+        self.final_rows = final.shape[0]
+        self.dim = int(dim)
+        self.rhs_id = int(rhs_id)
+        self.device_index = int(device_index)
+        self._h = C.c_void_p()
+        check(lib().dsb_erk_create(C.byref(self._h), self.device_index, self.rhs_id, self.dim, self.stages,
+                                   inter.ctypes.data_as(_dp), final.ctypes.data_as(_dp), self.final_rows,
+                                   float(order), FLAG_STRICT if strict else 0), "dsb_erk_create")
+
+    @property
+    def has_fused_kernel(self):
+        return lib().dsb_erk_run_launches(self._h) > 0
+
+    def run(self, args, stream_ptr):
+        check(lib().dsb_erk_run(self._h, C.byref(args), stream_ptr), "dsb_erk_run")
+
+    def close(self):
+        if self._h:
+            lib().dsb_erk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,133 @@
+// abi.cu -- the extern "C" surface of libdesolver_b200.so (include/desolver_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "plan.h"
+
+namespace dsb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim, int32_t cap,
+                      const double *tq, int64_t tq_stride, double *out, cudaStream_t stream);
+
+}  // namespace dsb
+
+#define DSB_STR2(x) #x
+#define DSB_STR(x) DSB_STR2(x)
+
+using namespace dsb;
+
+extern "C" {
+
+int dsb_abi_version(void) { return DSB_ABI_VERSION; }
+
+const char *dsb_build_info(void)
+{
+    return "libdesolver_b200 abi=1 arch=sm_100a nvcc=" DSB_STR(__CUDACC_VER_MAJOR__) "." DSB_STR(__CUDACC_VER_MINOR__)
+           " fused_stages={1,2,4,6,7,13,17} rhs={lorenz,van_der_pol,harmonic_oscillator}";
+}
+
+const char *dsb_last_error(void) { return g_error; }
+
+int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int stages,
+                   const double *tableau_intermediate, const double *tableau_final, int final_rows,
+                   double order, unsigned flags)
+{
+    if (!out || !tableau_intermediate || !tableau_final || stages < 1 || (final_rows != 1 && final_rows != 2) ||
+        dim < 1 || !(order > 0.0)) {
+        set_error("dsb_erk_create: bad argument (stages=%d final_rows=%d dim=%d order=%g)", stages, final_rows, dim, order);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    // explicit methods only: a[s][j] must vanish for j >= s (integrator_types.py:135)
+    for (int s = 0; s < stages; ++s)
+        for (int j = s; j < stages; ++j)
+            if (tableau_intermediate[s * (stages + 1) + 1 + j] != 0.0) {
+                set_error("dsb_erk_create: tableau is implicit (a[%d][%d] != 0); only explicit RK is supported", s, j);
+                return DSB_ERR_UNSUPPORTED;
+            }
+    DSB_CUDA_CHECK(cudaSetDevice(device));
+    dsb_erk_plan *p = new (std::nothrow) dsb_erk_plan;
+    if (!p) { set_error("out of host memory"); return DSB_ERR_BAD_ARGUMENT; }
+    p->device = device; p->rhs_id = rhs_id; p->dim = dim; p->stages = stages; p->final_rows = final_rows;
+    p->order = order; p->flags = flags;
+    p->inter.assign(tableau_intermediate, tableau_intermediate + (size_t)stages * (stages + 1));
+    p->fin.assign(tableau_final, tableau_final + (size_t)final_rows * (stages + 1));
+    cudaDeviceProp prop;
+    DSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+
+    bool fused = false;
+    switch (rhs_id) {
+    case DSB_RHS_LORENZ: fused = dim == 3 && select_fused_lorenz(p); break;
+    case DSB_RHS_VDP:    fused = dim == 2 && select_fused_vdp(p); break;
+    case DSB_RHS_SHO:    fused = dim == 2 && select_fused_sho(p); break;
+    default: break;
+    }
+    if (!fused) p->fused_launch = nullptr;
+
+    double2 host_tab[fm::ATAN_TABLE_SIZE];
+    fm::build_atan_table(host_tab);
+    if (cudaMalloc(&p->d_atan, sizeof(host_tab)) != cudaSuccess ||
+        cudaMemcpy(p->d_atan, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("dsb_erk_create: device table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete p;
+        return DSB_ERR_CUDA;
+    }
+    *out = p;
+    return DSB_OK;
+}
+
+int dsb_erk_destroy(dsb_erk_handle h)
+{
+    if (!h) return DSB_OK;
+    if (h->d_atan) cudaFree(h->d_atan);
+    if (h->d_tab) cudaFree(h->d_tab);
+    delete h;
+    return DSB_OK;
+}
+
+int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
+{
+    if (!h || !a) { set_error("dsb_erk_run: null handle or args"); return DSB_ERR_BAD_ARGUMENT; }
+    if (!h->fused_launch) {
+        set_error("dsb_erk_run: no fused kernel for rhs_id=%d dim=%d stages=%d; use the stage-level entry points",
+                  h->rhs_id, h->dim, h->stages);
+        return DSB_ERR_UNSUPPORTED;
+    }
+    if (a->n < 0 || !a->y || !a->t || !a->dt || !a->counters) {
+        set_error("dsb_erk_run: y, t, dt and counters are required");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    if (a->nodes && (!a->node_count || a->node_capacity < 2)) {
+        set_error("dsb_erk_run: dense output needs node_count and node_capacity >= 2");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    if (a->n == 0) return DSB_OK;
+    return h->fused_launch(h, a, (cudaStream_t)stream);
+}
+
+int dsb_erk_run_launches(dsb_erk_handle h) { return (h && h->fused_launch) ? 1 : 0; }
+
+int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
+                   int32_t node_capacity, const double *tq, int64_t tq_stride, double *out, void *stream)
+{
+    if (!nodes || !node_count || !tq || !out || dim < 1 || node_capacity < 2 || n < 0) {
+        set_error("dsb_dense_eval: bad argument");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    return launch_dense_eval(nodes, node_count, n, dim, node_capacity, tq, tq_stride, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+// erk_fused.cuh -- K1: the fused, persistent, thread-per-trajectory explicit Runge-Kutta
+// ensemble kernel (sm_100a).
+//
+// One launch integrates every trajectory of the shard from its current (t, y, dt) to tf.  Each
+// lane owns ONE trajectory: state, all S stage derivatives, controller history and counters live
+// in registers; nothing but the initial load and the final store touches HBM.  A lane whose
+// trajectory finishes pulls the next one from a global work queue (warp-aggregated atomicAdd), so
+// the 189..286-attempt spread between trajectories costs no lock-step
+// idling and no host round trip.  One loop iteration = one step ATTEMPT of every live lane:
+//     stage accumulation   y + h * sum_j a_sj k_j      (runge_kutta_methods.py:44-54)
+//     propagated increment h * sum_j b_j k_j           (integrator_types.py:307)
+//     embedded error       h * sum_j (b-bhat)_j k_j    (integrator_types.py:190,321)
+//     weighted L2 norm + controller + accept/reject    (integrator_template.py:46-93)
+//     masked commit, final-step clamp, termination     (differential_system.py:996-1002,1015-1018,1070-1071)
+//     retry chain h <- min(new, h0), <= 64 retries     (integrator_types.py:201-224)
+// Per-trajectory semantics are those of the reference run on that trajectory alone.
+#pragma once
+
+#include "common.cuh"
+#include "fastmath.cuh"
+#include <math_constants.h>
+
+namespace dsb {
+
+constexpr int ERK_THREADS = 128;
+
+template <int S>
+struct ErkKernelArgs {
+    dsb_erk_run_args a;
+    TableauData<S> tab;
+    const double2 *atan_table;   // device copy of fm::build_atan_table
+};
+
+// numpy's add.reduce over a contiguous axis of length S (see oracle/desolver_oracle.c):
+// S < 8 left to right; else 8 accumulators, pairwise combine, sequential tail.  S <= 17 here.
+template <int S, bool STRICT>
+__device__ __forceinline__ double np_sum_terms(const double (&term)[S])
+{
+    using A = Ar<STRICT>;
+    if (S < 8) {
+        double s = term[0];
+#pragma unroll
+        for (int i = 1; i < S; ++i) s = A::add(s, term[i]);
+        return s;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = term[j < S ? j : 0];
+    constexpr int full = S - (S % 8);
+#pragma unroll
+    for (int i = 8; i < full; i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = A::add(r[j], term[(i + j) < S ? (i + j) : 0]);
+    double res = A::add(A::add(A::add(r[0], r[1]), A::add(r[2], r[3])), A::add(A::add(r[4], r[5]), A::add(r[6], r[7])));
+#pragma unroll
+    for (int i = (full < 8 ? 8 : full); i < S; ++i) res = A::add(res, term[i]);
+    return res;
+}
+
+// pow-with-guard of the reference's 3-term branch: where(k > 0, k, 1)
+__device__ __forceinline__ double guarded_pow(double base, double expo)
+{
+    double k = pow(base, expo);
+    return k > 0.0 ? k : 1.0;
+}
+
+// corr contribution of one squared error norm x = ||diff/tol||^2:
+//   where(eps > 0, eps ** (1/order), 1)  with eps = 1/sqrt(x)     (integrator_template.py:64,74)
+template <bool STRICT>
+__device__ __forceinline__ double corr_term(double x, double order, int order_p)
+{
+    if (STRICT) {
+        double eps = 1.0 / sqrt(x);
+        return eps > 0.0 ? pow(eps, 1.0 / order) : 1.0;
+    }
+    if (x > 1e-280 && x < 1e280 && order_p > 0) {
+        if (order_p == 10) return fm::inv_root<10>(x);
+        if (order_p == 16) return fm::inv_root<16>(x);
+        return fm::inv_root_rt(x, order_p);
+    }
+    if (x == 0.0) return CUDART_INF;
+    if (!(x < CUDART_INF)) return 1.0;                  // inf or nan: eps = 0 or nan -> 1
+    return pow(x, -0.5 / order);
+}
+
+// resident blocks per SM: 4 (<=128 registers) while the stage derivatives fit, else 2 (<=255)
+template <class Rhs, int S>
+constexpr int erk_min_blocks() { return (S * Rhs::DIM <= 21) ? 4 : 2; }
+
+template <class Rhs, int S, bool STRICT>
+__global__ void __launch_bounds__(ERK_THREADS, (erk_min_blocks<Rhs, S>()))
+erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
+{
+    using A = Ar<STRICT>;
+    constexpr int D = Rhs::DIM, NP = Rhs::NPARAM;
+    constexpr unsigned FULL = 0xffffffffu;
+    const TableauData<S> &tab = P.tab;
+    const long long n = P.a.n;
+    const double tf = P.a.tf, rtol = P.a.rtol, atol = P.a.atol;
+    const int lane = threadIdx.x & 31;
+
+    __shared__ double2 s_atan[fm::ATAN_TABLE_SIZE];
+    if (!STRICT) {
+        for (int i = threadIdx.x; i < fm::ATAN_TABLE_SIZE; i += blockDim.x) s_atan[i] = P.atan_table[i];
+        __syncthreads();
+    }
+
+    // ---- per-lane trajectory state (registers) ----
+    long long idx = 0;
+    bool live = false, exhausted = false, final_step = false;
+    double y[D], prm[NP > 0 ? NP : 1], k[S][D], scale[D];
+    double t = 0.0, dt = 0.0, h = 0.0, h0 = 0.0;
+    double corr_first = 1.0, x_last = 1.0, x_last_last = 1.0;
+    int trial = 0, acc = 0, rej = 0;
+    long long steps = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { y[d] = 0.0; scale[d] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int d = 0; d < D; ++d) k[s][d] = 0.0;
+
+    auto store = [&](int st) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) P.a.y[(long long)d * n + idx] = y[d];
+        P.a.t[idx] = t;
+        P.a.dt[idx] = dt;
+        if (P.a.accepted) P.a.accepted[idx] += acc;
+        if (P.a.rejected) P.a.rejected[idx] += rej;
+        if (P.a.status) P.a.status[idx] = st;
+    };
+    auto dense_node = [&](const double (&f)[D]) {
+        int c = P.a.node_count[idx];
+        if (c < P.a.node_capacity) {
+            double *rec = P.a.nodes + ((long long)idx * P.a.node_capacity + c) * (1 + 2 * D);
+            rec[0] = t;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { rec[1 + d] = y[d]; rec[1 + D + d] = f[d]; }
+        }
+        P.a.node_count[idx] = c + 1;
+    };
+
+    for (;;) {
+        // ------------------------------------------------------------ refill from the queue
+        unsigned need = __ballot_sync(FULL, !live);
+        if (need && !exhausted) {
+            int cnt = __popc(need);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd((unsigned long long *)P.a.counters, (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            exhausted = (long long)(base + cnt) >= n;
+            long long mine = (long long)base + __popc(need & ((1u << lane) - 1u));
+            if (!live && mine < n) {
+                idx = mine;
+#pragma unroll
+                for (int d = 0; d < D; ++d) y[d] = P.a.y[(long long)d * n + idx];
+                t = P.a.t[idx];
+                dt = P.a.dt[idx];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) prm[p] = P.a.params[p][idx * P.a.param_stride[p]];
+                Rhs::prepare(prm);
+                acc = 0; rej = 0; trial = 0; steps = 0;
+                int st0 = P.a.status ? P.a.status[idx] : (int)DSB_TRAJ_DONE;
+                bool go = st0 != (int)DSB_TRAJ_TOL_FAIL;
+                if (go && P.a.first_call) {
+                    // integrate() entry: differential_system.py:956-957, 971-974
+                    double span = tf - t;
+                    if (fabs(span) < DSB_EPS4) go = false;
+                    else {
+                        if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
+                        if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+                    }
+                }
+                go = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                if (go) {
+                    live = true;
+                    if (P.a.nodes && P.a.node_count[idx] == 0) {
+                        double f0[D];
+                        Rhs::eval(y, prm, f0);
+                        dense_node(f0);
+                    }
+                } else {
+                    store(st0 == (int)DSB_TRAJ_TOL_FAIL ? st0 : (int)DSB_TRAJ_DONE);
+                }
+            }
+        }
+        if (!__any_sync(FULL, live)) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ------------------------------------------------------------ start of a step
+        if (trial == 0) {
+            final_step = fabs(dt + t) > fabs(tf);                 // differential_system.py:997
+            h = final_step ? (tf - t) : dt;
+            h0 = h;
+        }
+
+        // ------------------------------------------------------------ stages
+        double dlast[D];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            double ys[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double sum = 0.0;
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if ((tab.nz_a[s] >> j) & 1u) sum = A::mad(k[j][d], tab.a[s][j], sum);
+                if (STRICT) {
+                    double inc = A::mul(h, sum);
+                    if (s == S - 1) dlast[d] = inc;
+                    ys[d] = A::add(y[d], inc);
+                } else {
+                    if (s == S - 1) dlast[d] = h * sum;
+                    ys[d] = fma(h, sum, y[d]);
+                }
+            }
+            Rhs::eval(ys, prm, k[s]);
+        }
+
+        // ------------------------------------------------------------ increment + error estimate
+        double dY[D], err[D], slope[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (STRICT) {
+                double tb[S], te[S];
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    tb[j] = ((tab.nz_b >> j) & 1u) ? A::mul(k[j][d], tab.b[j]) : 0.0;
+                    te[j] = ((tab.nz_db >> j) & 1u) ? A::mul(tab.db[j], k[j][d]) : 0.0;
+                }
+                double sb = np_sum_terms<S, STRICT>(tb);
+                dY[d] = tab.fsal ? dlast[d] : A::mul(h, sb);
+                err[d] = A::mul(h, np_sum_terms<S, STRICT>(te));
+                slope[d] = dY[d] / h;                                  // dState / timestep
+            } else {
+                double sb = 0.0, se = 0.0;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    if ((tab.nz_b >> j) & 1u) sb = fma(k[j][d], tab.b[j], sb);
+                    if ((tab.nz_db >> j) & 1u) se = fma(k[j][d], tab.db[j], se);
+                }
+                dY[d] = tab.fsal ? dlast[d] : h * sb;
+                err[d] = h * se;
+                slope[d] = sb;                                         // = dY/h to rounding
+            }
+        }
+
+        // ------------------------------------------------------------ controller
+        bool redo = false;
+        double new_dt = h;
+        if (tab.adaptive) {
+            double x = 0.0;                                            // ||diff / tol||_2^2
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fmax(fabs(y[d]), fabs(slope[d]));
+                if (trial > 0) sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
+                scale[d] = sc;
+                double tol = A::mad(rtol, sc, atol);                  // atol + rtol*sc
+                double q = STRICT ? err[d] / tol : fm::fast_div(err[d], tol);
+                x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
+            }
+            if (!STRICT && !live) x = 1.0;     // idle lanes stay on the fast path (no divergent libm calls)
+            double corr;
+            if (trial < 2) {
+                double c_cur = corr_term<STRICT>(x, tab.order, tab.order_p);
+                corr = (trial == 0) ? c_cur : A::mul(c_cur, corr_first);
+                if (trial == 0) corr_first = c_cur;
+            } else {
+                // 3-term product, exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
+                double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order);
+                double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order);
+                double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order);
+                corr = A::mul(A::mul(k1, k2), k3);
+            }
+            x_last_last = x_last;
+            x_last = x;
+            double u = A::sub(A::mul(0.8, corr), 1.0);
+            double f;
+            if (STRICT || !(u < 1e30)) f = A::add(1.0, atan(u));
+            else f = fm::one_plus_atan(u, s_atan);
+            new_dt = A::mul(f, h);
+            redo = f < DSB_REJECT_BELOW;
+        }
+
+        // ------------------------------------------------------------ commit / retry
+        if (live) {
+            if (!redo) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) y[d] = A::add(y[d], dY[d]);
+                t = A::add(t, h);
+                acc++; steps++; trial = 0;
+                if (!final_step) dt = new_dt;
+                if (P.a.nodes) {
+                    double f1[D];
+                    Rhs::eval(y, prm, f1);
+                    dense_node(f1);
+                }
+                bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                bool budget = P.a.max_steps >= 0 && steps >= P.a.max_steps;
+                if (!more || budget) {
+                    store(more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE);
+                    live = false;
+                }
+            } else {
+                rej++; trial++;
+                if (trial > DSB_MAX_RETRIES) {
+                    store((int)DSB_TRAJ_TOL_FAIL);                   // state frozen at the step start
+                    live = false;
+                    trial = 0;
+                } else {
+                    // integrator_types.py:206 min(new, h0); sign-aware so tf < t0 also works
+                    h = h0 >= 0.0 ? fmin(new_dt, h0) : -fmin(fabs(new_dt), fabs(h0));
+                }
+            }
+        }
+    }
+}
+
+// Host-side launcher, one per instantiation.
+template <class Rhs, int S, bool STRICT>
+int launch_erk_fused(const ErkKernelArgs<S> &args, int blocks, cudaStream_t stream)
+{
+    erk_fused_kernel<Rhs, S, STRICT><<<blocks, ERK_THREADS, 0, stream>>>(args);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+template <class Rhs, int S, bool STRICT>
+int occupancy_erk_fused(int *blocks_per_sm)
+{
+    DSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        blocks_per_sm, erk_fused_kernel<Rhs, S, STRICT>, ERK_THREADS, 0));
+    return DSB_OK;
+}
+
+}  // namespace dsb

@@ -1,0 +1,193 @@
+// fastmath.cuh -- double-precision building blocks of the fused step-size controller.
+//
+// The reference controller (integrators/integrator_template.py:62-93) needs, per attempt and
+// per trajectory: dim divisions, a sqrt, a reciprocal, pow(x, 1/order) and atan.  With libm
+// those are ~60 % of the FP64 instructions of a Lorenz RK45 attempt, and the FP64 pipe is the
+// co-limit of the kernel.  These replacements keep <= ~2 ulp accuracy (so the
+// committed dt differs from libm's by the same last-ulp amount that numpy-SIMD and glibc differ
+// from each other) at a fraction of the instruction count:
+//   fast_div      : MUFU.RCP64H seed + one Newton step + remainder correction     (5 DFMA)
+//   inv_root<P>   : x^(-1/P) = (||e||^2)^(-1/(2 order)) -- folds sqrt, reciprocal and pow into
+//                   an FP32 lg2/ex2 seed + two division-free Newton steps          (14 DFMA)
+//   one_plus_atan : table-driven argument reduction + 4-term series                (~15 DFMA)
+// Everything is __host__ __device__ so tests/test_fastmath.py can check the algorithms on the
+// CPU against libm (the MUFU seeds are replaced by deliberately truncated libm values there).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define DSB_HD __host__ __device__ __forceinline__
+#else
+#define DSB_HD inline
+struct double2 { double x, y; };
+#endif
+
+namespace dsb {
+namespace fm {
+
+constexpr int ATAN_TABLE_SIZE = 128;
+constexpr double ATAN_G_LO = -0.5;
+constexpr double ATAN_INV_DG = 128.0 / 1.5;   // table is uniform in g = u / (1 + |u|), g in [-0.5, 1)
+
+DSB_HD uint64_t as_bits(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t b; memcpy(&b, &x, 8); return b;
+#endif
+}
+
+DSB_HD float bits_as_float(uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+// ~2^-20-accurate reciprocal seed (device: one MUFU.RCP64H; host: libm truncated to match)
+DSB_HD double rcp_seed(double d)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+#else
+    uint64_t b = as_bits(1.0 / d) & 0xffffffff00000000ull;
+    double r; memcpy(&r, &b, 8); return r;
+#endif
+}
+
+DSB_HD float lg2_seed(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return log2f(x) * (1.0f + 3e-7f);
+#endif
+}
+
+DSB_HD float ex2_seed(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return exp2f(x) * (1.0f - 3e-7f);
+#endif
+}
+
+DSB_HD float rcpf_seed(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// n / d to ~1 ulp for normal d; d = 0, inf, nan give inf/nan like IEEE division does.
+DSB_HD double fast_div(double n, double d)
+{
+    double r = rcp_seed(d);
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);               // 2^-40
+    double q = n * r;
+    double rem = fma(-d, q, n);
+    return fma(rem, r, q);
+}
+
+template <int P>
+DSB_HD double ipow(double c)
+{
+    if (P == 1) return c;
+    double h = ipow<(P / 2 > 0 ? P / 2 : 1)>(c);
+    double sq = h * h;
+    return (P & 1) ? sq * c : sq;
+}
+
+DSB_HD double ipow_rt(double c, int p)
+{
+    double r = 1.0;
+    while (p > 0) {
+        if (p & 1) r *= c;
+        c *= c;
+        p >>= 1;
+    }
+    return r;
+}
+
+// FP32 seed of x^(-1/P) for normal positive x, via exponent/mantissa split so any double
+// magnitude is safe (the seed itself always fits a float: |log2 x| / P <= 1074 / 2).
+DSB_HD double inv_root_seed(double x, float inv_p)
+{
+    uint64_t b = as_bits(x);
+    uint32_t hi = (uint32_t)(b >> 32);
+    int e = (int)((hi >> 20) & 0x7ffu) - 1023;
+    uint32_t mant23 = ((hi & 0xfffffu) << 3) | ((uint32_t)(b >> 29) & 7u);
+    float m = bits_as_float(0x3f800000u | mant23);         // [1, 2)
+    float lg = (float)e + lg2_seed(m);
+    return (double)ex2_seed(-lg * inv_p);
+}
+
+// x^(-1/P) for x in [1e-280, 1e280]; two Newton steps c <- c + c (1 - x c^P) / P.
+template <int P>
+DSB_HD double inv_root(double x)
+{
+    double c = inv_root_seed(x, 1.0f / (float)P);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        double e = fma(-x, ipow<P>(c), 1.0);
+        c = fma(c, e * (1.0 / P), c);
+    }
+    return c;
+}
+
+DSB_HD double inv_root_rt(double x, int p)
+{
+    double c = inv_root_seed(x, 1.0f / (float)p);
+    double ip = 1.0 / (double)p;
+    for (int it = 0; it < 2; ++it) {
+        double e = fma(-x, ipow_rt(c, p), 1.0);
+        c = fma(c, e * ip, c);
+    }
+    return c;
+}
+
+// Host-side table builder: entry k = { u_k, 1 + atan(u_k) } with g_k = -0.5 + 1.5 k / 128.
+inline void build_atan_table(double2 *tab)
+{
+    for (int k = 0; k < ATAN_TABLE_SIZE; ++k) {
+        double g = ATAN_G_LO + (double)k / ATAN_INV_DG;
+        double u = g / (1.0 - fabs(g));
+        tab[k].x = u;
+        tab[k].y = 1.0 + atan(u);
+    }
+}
+
+// 1 + atan(u) for u in [-1, 1e30): atan(u) = atan(u_k) + atan((u - u_k) / (1 + u u_k)).
+DSB_HD double one_plus_atan(double u, const double2 *tab)
+{
+    float uf = (float)u;
+    float g = uf * rcpf_seed(1.0f + fabsf(uf));
+    int k = (int)rintf((g - (float)ATAN_G_LO) * (float)ATAN_INV_DG);
+    k = k < 0 ? 0 : (k > ATAN_TABLE_SIZE - 1 ? ATAN_TABLE_SIZE - 1 : k);
+    double2 e = tab[k];
+    double r = fast_div(u - e.x, fma(u, e.x, 1.0));
+    double r2 = r * r;
+    double p = fma(r2, fma(r2, -1.0 / 7.0, 1.0 / 5.0), -1.0 / 3.0);   // |r| < 0.012: r^9/9 < 6e-19
+    return e.y + fma(r * r2, p, r);
+}
+
+}  // namespace fm
+}  // namespace dsb

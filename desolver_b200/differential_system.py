@@ -1,0 +1,528 @@
+"""`OdeSystem` of the drop-in: the reference's constructor and `integrate()` surface
+(/root/reference/desolver/differential_system.py:457-1199) in front of the B200 ensemble engine.
+
+What stays source-compatible: `OdeSystem(equ_rhs, y0, t=(0, 1), dense_output=False, dt=1.0,
+rtol=None, atol=None, constants=dict())`, `.integrate(t=None, callback=None, eta=False,
+events=None)`, `.method` / `.set_method`, `.y .t .dt .t0 .tf .rtol .atol .constants .nfev .njev
+.sol .success .integration_status`, `len(a)`, `a[i]`, `a[t]`, `reset()`.
+
+What is new (the reference has no ensemble concept): `ensemble=True` declares
+the LAST axis of `y0` to enumerate independent trajectories.  Each column then evolves exactly as
+the reference would evolve it alone -- own t, own dt, own error norm, own accept/reject chain --
+and `constants` entries of trailing length N are per-trajectory.  `ensemble=False` (default)
+keeps the reference meaning: the whole of `y0` is one system with one dt (an ensemble of N = 1).
+
+History model: the reference stores every accepted step (`:1015-1016`), which is impossible for
+2^20 trajectories with ragged step counts.  Here `a.y` / `a.t` hold one row per `integrate()`
+call (row 0 = initial condition), `a[-1]` is the final ensemble state, per-step history is
+available through `dense_output=True` (`a.sol(t)`), and the per-trajectory integer tensors
+`accepted`, `rejected`, `status` replace what the reference leaves implicit in `len(a)`.
+"""
+import collections
+import ctypes as C
+
+import numpy as np
+
+from . import backend as D
+from . import exception_types as etypes
+from . import integrators
+from .backend import cuda_backend as cb
+
+__all__ = ["DiffRHS", "rhs_prettifier", "OdeSystem", "DenseOutput", "StateTuple"]
+
+StateTuple = collections.namedtuple("StateTuple", ["t", "y", "event"])
+
+# a stuck trajectory (dt underflow) loops forever in the reference; the kernels stop after this
+# many accepted steps per integrate() call and report DSB_TRAJ_RUNNING instead
+DEFAULT_STEP_CAP = 50_000_000
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DiffRHS(object):
+    """Right-hand-side wrapper, same call protocol and counters as the reference's
+    (`differential_system.py:293-447`): `rhs(t, y, **constants)`, `nfev`, attribute forwarding to
+    the wrapped callable (which is how the `device_plugin` tag of rhs_plugins survives wrapping)."""
+
+    def __init__(self, rhs, equ_repr=None, md_repr=None):
+        self.__dict__["rhs"] = rhs
+        self.__dict__["equ_repr"] = str(equ_repr) if equ_repr is not None else str(rhs)
+        self.__dict__["md_repr"] = md_repr if md_repr is not None else self.__dict__["equ_repr"]
+        self.__dict__["nfev"] = 0
+        self.__dict__["njev"] = 0
+
+    def __call__(self, t, y, *args, **kwargs):
+        val = self.rhs(t, y, *args, **kwargs)
+        self.__dict__["nfev"] += 1
+        return val
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["rhs"], name)
+
+    def __setattr__(self, name, val):
+        if name in ("rhs", "equ_repr", "md_repr", "nfev", "njev"):
+            self.__dict__[name] = val
+        else:
+            setattr(self.__dict__["rhs"], name, val)
+
+    def __str__(self):
+        return self.equ_repr
+
+    def _repr_markdown_(self):
+        return self.md_repr
+
+    def __repr__(self):
+        return "<DiffRHS({},{},{})>".format(repr(self.rhs), self.equ_repr, self.md_repr)
+
+
+def rhs_prettifier(equ_repr=None, md_repr=None):
+    def rhs_wrapper(rhs):
+        return DiffRHS(rhs, equ_repr, md_repr)
+    return rhs_wrapper
+
+
+class DenseOutput(object):
+    """Dense output over the per-trajectory node store (t_k, y_k, f_k) written by the step kernels.
+
+    `sol(t)` evaluates, for every trajectory, the cubic Hermite interpolant of the accepted step
+    that contains `t` -- the lookup and formula of the reference's DenseOutput / CubicHermiteInterp
+    (`differential_system.py:205-227`, `utilities/interpolation.py:41-61`) as one kernel launch.
+    `t` may be a scalar or a tensor of one time per trajectory.
+    """
+
+    def __init__(self, system):
+        self._sys = system
+
+    def __len__(self):
+        cnt = self._sys._node_count
+        return 0 if cnt is None else int(cnt.max().item())
+
+    @property
+    def node_count(self):
+        return self._sys._node_count
+
+    def __call__(self, t):
+        torch = _torch()
+        s = self._sys
+        if s._nodes is None:
+            raise ValueError("No interpolant has been added and time interval is not defined!")
+        if int(s._node_count.max().item()) > s._node_capacity:
+            raise MemoryError("dense-output node store overflowed (capacity %d nodes per trajectory); "
+                              "construct the system with a larger dense_capacity" % s._node_capacity)
+        tq = torch.as_tensor(t, dtype=torch.float64, device=s.device)
+        if tq.ndim == 0:
+            tq = tq.reshape(1)
+            stride = 0
+        else:
+            if tq.shape != (s.n_traj,):
+                raise ValueError("expected a scalar or one query time per trajectory, shape (%d,)" % s.n_traj)
+            tq = tq.contiguous()
+            stride = 1
+        out = torch.empty((s.numel, s.n_traj), dtype=torch.float64, device=s.device)
+        cb.check(cb.lib().dsb_dense_eval(s._nodes.data_ptr(), s._node_count.data_ptr(), s.n_traj, s.numel,
+                                         s._node_capacity, tq.data_ptr(), stride, out.data_ptr(),
+                                         cb.current_stream_ptr(s.device)), "dsb_dense_eval")
+        return s._user_shape(out)
+
+
+class OdeSystem(object):
+    """Ordinary differential equation system integrated on a B200 by libdesolver_b200.so."""
+
+    def __init__(self, equ_rhs, y0, t=(0, 1), dense_output=False, dt=1.0, rtol=None, atol=None, constants=dict(),
+                 ensemble=False, device=None, dense_capacity=None, strict=False):
+        torch = _torch()
+        if len(t) != 2:
+            raise ValueError("Two time bounds are required, only {} were given.".format(len(t)))
+        if not callable(equ_rhs):
+            raise TypeError("equ_rhs is not callable, please pass a callable object for the right hand side.")
+        cb.lib()                                   # fail loudly if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("desolver_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.equ_rhs = equ_rhs if isinstance(equ_rhs, DiffRHS) else DiffRHS(equ_rhs)
+
+        if isinstance(y0, torch.Tensor) and y0.is_cuda and device is None:
+            device = y0.device
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        y0 = torch.as_tensor(y0, dtype=torch.float64).to(self.device)
+        self.ensemble = bool(ensemble)
+        if self.ensemble:
+            if y0.ndim < 2:
+                raise ValueError("ensemble=True needs y0 of shape (*dim, N) with the trajectories on the last axis")
+            self.dim = tuple(y0.shape[:-1])
+            self.n_traj = int(y0.shape[-1])
+        else:
+            self.dim = tuple(y0.shape)
+            self.n_traj = 1
+        self.numel = int(np.prod(self.dim)) if len(self.dim) else 1
+        self.dtype = torch.float64
+        self.strict = bool(strict)
+
+        self.__rtol = rtol
+        self.__atol = atol
+        self.__consts = dict(constants) if constants is not None else dict()
+        self.__t0 = float(t[0])
+        self.__tf = float(t[1])
+        self.__dt0 = float(dt)
+        self.__dense_output = bool(dense_output)
+        self._node_capacity = int(dense_capacity) if dense_capacity is not None else 1024
+        self.__method = integrators.RK45CKSolver
+        self.__int_status = 0
+        self.__events = []
+        self._step_cap = DEFAULT_STEP_CAP
+        self._handles = {}
+        self.callback_every = 1
+
+        self._y0 = y0.reshape(self.numel, self.n_traj).contiguous().clone()
+        # one RHS evaluation as a shape check, like the reference (:536-539)
+        probe = self.equ_rhs(self._user_time(torch.full((self.n_traj,), self.__t0, dtype=torch.float64,
+                                                        device=self.device)),
+                             self._user_shape(self._y0), **self.__consts)
+        if tuple(probe.shape) != tuple(self._user_shape(self._y0).shape):
+            raise ValueError("Expected rhs to return a shape that is compatible with y0, got shapes "
+                             "Shape[y0]={} and Shape[dy]={}".format(tuple(self._user_shape(self._y0).shape),
+                                                                    tuple(probe.shape)))
+        self._reset_state()
+        self.initialise_integrator()
+
+    # ------------------------------------------------------------------ state helpers
+    def _user_shape(self, flat):
+        """(numel, N) storage -> the caller's (*dim[, N]) view."""
+        return flat.reshape(*self.dim, self.n_traj) if self.ensemble else flat.reshape(self.dim)
+
+    def _user_time(self, tvec):
+        return tvec if self.ensemble else tvec.reshape(())
+
+    def _reset_state(self):
+        torch = _torch()
+        n, dev = self.n_traj, self.device
+        self._y = self._y0.clone()
+        self._t = torch.full((n,), self.__t0, dtype=torch.float64, device=dev)
+        self._dt = torch.full((n,), self.__dt0, dtype=torch.float64, device=dev)
+        self.accepted = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.rejected = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        self._hist_y = [self._y.clone()]
+        self._hist_t = [self._t.clone()]
+        self._nodes = None
+        self._node_count = None
+        self._launches = 0
+        self._fix_dt_dir(self.__tf, self.__t0)
+
+    def _fix_dt_dir(self, t1, t0):
+        torch = _torch()
+        flip = torch.sign(self._dt) != float(np.sign(t1 - t0))
+        self._dt = torch.where(flip, -self._dt, self._dt)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def sol(self):
+        return DenseOutput(self) if self.__dense_output else None
+
+    @property
+    def success(self):
+        return self.__int_status == 1 or self.__int_status == 2
+
+    @property
+    def events(self):
+        return self.__events
+
+    @property
+    def y(self):
+        """History of states: one row per integrate() call (row 0 = y0), shape (rows, *dim[, N])."""
+        torch = _torch()
+        return torch.stack([self._user_shape(r) for r in self._hist_y])
+
+    @property
+    def t(self):
+        torch = _torch()
+        return torch.stack([self._user_time(r) for r in self._hist_t])
+
+    @property
+    def nfev(self):
+        """Right-hand-side evaluations in the reference's accounting, summed over the ensemble:
+        per trajectory 1 (constructor) + 1 (first initial_rhs) + (S+1) per attempt
+        (S per attempt for FSAL schemes); SURVEY.md fact 5."""
+        att = int((self.accepted.sum() + self.rejected.sum()).item())
+        if att == 0:
+            return self.n_traj
+        integ = self.integrator
+        per_attempt = integ.stages + (0 if getattr(integ, "is_fsal", False) or integ.symplectic else 1)
+        return self.n_traj * 2 + per_attempt * att
+
+    @property
+    def njev(self):
+        return 0
+
+    @property
+    def constants(self):
+        return self.__consts
+
+    @constants.setter
+    def constants(self, new_constants):
+        self.__consts = new_constants
+
+    @constants.deleter
+    def constants(self):
+        self.__consts = dict()
+
+    @property
+    def rtol(self):
+        return self.__rtol
+
+    @rtol.setter
+    def rtol(self, new_rtol):
+        self.__rtol = float(new_rtol)
+        self.initialise_integrator()
+
+    @property
+    def atol(self):
+        return self.__atol
+
+    @atol.setter
+    def atol(self, new_atol):
+        self.__atol = float(new_atol)
+        self.initialise_integrator()
+
+    @property
+    def dt(self):
+        """Current step size(s): a 0-d tensor for a single system, shape (N,) for an ensemble."""
+        return self._user_time(self._dt)
+
+    @dt.setter
+    def dt(self, new_dt):
+        torch = _torch()
+        self._dt = torch.as_tensor(new_dt, dtype=torch.float64, device=self.device).expand(self.n_traj).clone()
+        self._fix_dt_dir(self.__tf, self.__t0)
+
+    @property
+    def t0(self):
+        return self.__t0
+
+    @t0.setter
+    def t0(self, new_t0):
+        if abs(self.__tf - float(new_t0)) <= D.epsilon("float64"):
+            raise ValueError("The start time of the integration cannot be greater than or equal to {}!".format(self.__tf))
+        self.__t0 = float(new_t0)
+        self._fix_dt_dir(self.__tf, self.__t0)
+
+    @property
+    def tf(self):
+        return self.__tf
+
+    @tf.setter
+    def tf(self, new_tf):
+        if abs(self.__t0 - float(new_tf)) <= D.epsilon("float64"):
+            raise ValueError("The end time of the integration cannot be equal to the start time: {}!".format(self.__t0))
+        self.__tf = float(new_tf)
+        self._fix_dt_dir(self.__tf, self.__t0)
+
+    def get_current_time(self):
+        return self._user_time(self._t)
+
+    # ------------------------------------------------------------------ method handling
+    def initialise_integrator(self, preserve_states=False):
+        kwargs = dict(dtype=self.dtype, device=self.device, atol=self.atol, rtol=self.rtol)
+        self.integrator = self.__method(self.dim, **kwargs)
+
+    @property
+    def method(self):
+        return self.__method
+
+    @method.setter
+    def method(self, new_method):
+        self.set_method(new_method, None)
+
+    def set_method(self, new_method, staggered_mask=None, preserve_states=True):
+        if staggered_mask is not None:
+            raise NotImplementedError("custom staggered_mask is not supported (dead code in the reference)")
+        if isinstance(new_method, str) and new_method in integrators.available_methods():
+            self.__method = integrators.available_methods(False)[new_method]
+        elif isinstance(new_method, type) and issubclass(new_method, integrators.IntegratorTemplate):
+            self.__method = new_method
+        else:
+            raise ValueError("The method you selected does not exist in the list of available methods, "
+                             "call desolver_b200.available_methods() to see what these are")
+        self.initialise_integrator(preserve_states=preserve_states)
+
+    @property
+    def integration_status(self):
+        if self.__int_status == 0:
+            return "Integration has not been run."
+        if isinstance(self.__int_status, KeyboardInterrupt):
+            return "A KeyboardInterrupt exception was raised during integration."
+        if isinstance(self.__int_status, etypes.FailedIntegration):
+            if self.__int_status.__cause__ is not None:
+                return "The integration failed with the following exception: {}\n\tCaused by {}".format(
+                    self.__int_status, self.__int_status.__cause__)
+            return "The integration failed with the following exception: {}".format(self.__int_status)
+        if self.__int_status == 1:
+            return "Integration completed successfully."
+        if self.__int_status == 2:
+            return "Integration terminated upon finding a triggered event."
+        return "It should not be possible to initialise the system with this status"
+
+    def reset(self):
+        """Resets the system to the initial time (reference :900-910)."""
+        self.__int_status = 0
+        self.__events = []
+        self._reset_state()
+        self.initialise_integrator()
+
+    # ------------------------------------------------------------------ the hot path
+    def _fused_plugin(self):
+        """(plugin id, parameter names) if the RHS is tagged with a fused device plugin that the
+        library has a thread-per-trajectory kernel for; else None."""
+        rhs = self.equ_rhs
+        pid = getattr(rhs, "plugin_id", None)
+        if pid is None or getattr(rhs, "device_plugin", None) not in ("lorenz", "van_der_pol", "harmonic_oscillator"):
+            return None
+        if not isinstance(self.integrator, integrators.RungeKuttaIntegrator):
+            return None
+        if self.integrator.stages not in cb.FUSED_STAGES or len(self.dim) != 1:
+            return None
+        return pid, tuple(rhs.plugin_params), dict(rhs.plugin_defaults)
+
+    def _param_tensors(self, names, defaults):
+        """Per-plugin parameter arrays: a (N,) tensor is per-trajectory (stride 1), anything else
+        is one shared value (stride 0)."""
+        torch = _torch()
+        tensors, strides = [], []
+        for name in names:
+            v = self.__consts.get(name, defaults.get(name))
+            v = torch.as_tensor(v, dtype=torch.float64, device=self.device)
+            if v.ndim == 0:
+                tensors.append(v.reshape(1).contiguous())
+                strides.append(0)
+            elif tuple(v.shape) == (self.n_traj,):
+                tensors.append(v.contiguous())
+                strides.append(1)
+            else:
+                raise ValueError("constant %r must be a scalar or have shape (%d,)" % (name, self.n_traj))
+        return tensors, strides
+
+    def _ensure_dense_store(self):
+        torch = _torch()
+        if self.__dense_output and self._nodes is None:
+            rec = 1 + 2 * self.numel
+            self._nodes = torch.empty((self.n_traj, self._node_capacity, rec), dtype=torch.float64, device=self.device)
+            self._node_count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
+
+    def _run_fused(self, tf, plugin, max_steps, first_call):
+        integ = self.integrator
+        pid, names, defaults = plugin
+        key = (type(integ).__name__, pid, self.strict)
+        if key not in self._handles:       # handles survive reset(): one per (method, rhs, flavour)
+            self._handles[key] = cb.ErkHandle(self.device.index or 0, pid, self.numel, integ.tableau_intermediate,
+                                              integ.tableau_final, integ.order, strict=self.strict)
+        handle = self._handles[key]
+        params, strides = self._param_tensors(names, defaults)
+        self._ensure_dense_store()
+        self._counters.zero_()
+        a = cb.ErkRunArgs()
+        a.n = self.n_traj
+        a.y, a.t, a.dt = self._y.data_ptr(), self._t.data_ptr(), self._dt.data_ptr()
+        for i, (p, s) in enumerate(zip(params, strides)):
+            a.params[i] = p.data_ptr()
+            a.param_stride[i] = s
+        a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+        a.accepted, a.rejected, a.status = self.accepted.data_ptr(), self.rejected.data_ptr(), self.status.data_ptr()
+        a.max_steps = int(max_steps)
+        a.first_call = 1 if first_call else 0
+        if self._nodes is not None:
+            a.nodes, a.node_count, a.node_capacity = self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity
+        a.counters = self._counters.data_ptr()
+        handle.run(a, cb.current_stream_ptr(self.device))
+        self._launches += 1
+        self._keepalive = params
+
+    def integrate(self, t=None, callback=None, eta=False, events=None):
+        """Integrates every trajectory to time `t` (default: `self.tf`), reference `:912-1101`.
+
+        The whole loop runs on the device without host synchronisation per step.  `callback`
+        forces chunked execution: the kernels return every `self.callback_every` accepted steps per
+        trajectory and `callback(self)` is invoked in between.  `events` are not supported by the
+        ensemble engine and raise.
+        """
+        torch = _torch()
+        if events is not None:
+            raise NotImplementedError("event detection is not supported by the ensemble engine")
+        tf = float(t) if t is not None else self.__tf
+        if callback is None:
+            callbacks = []
+        elif isinstance(callback, (tuple, list)):
+            callbacks = list(callback)
+        else:
+            callbacks = [callback]
+        plugin = self._fused_plugin()
+        if plugin is None:
+            raise NotImplementedError(
+                "no fused device kernel for this right-hand side / method; the stage-level path is not built yet")
+        try:
+            if not callbacks and not eta:
+                self._run_fused(tf, plugin, self._step_cap, first_call=True)
+            else:
+                first = True
+                bar = None
+                if eta:
+                    from tqdm.auto import tqdm
+                    bar = tqdm(total=None)
+                while True:
+                    self._run_fused(tf, plugin, self.callback_every, first_call=first)
+                    first = False
+                    for cbk in callbacks:
+                        cbk(self)
+                    if bar is not None:
+                        bar.update()
+                    if not bool((self.status == cb.TRAJ_RUNNING).any().item()):
+                        break
+                if bar is not None:
+                    bar.close()
+            self._hist_y.append(self._y.clone())
+            self._hist_t.append(self._t.clone())
+            # error policy: run everything to completion, then raise like the reference does
+            # (:1089-1093 wraps integrator_types.py:220-224) if any trajectory failed
+            n_fail = int((self.status == cb.TRAJ_TOL_FAIL).sum().item())
+            if n_fail:
+                cause = etypes.FailedToMeetTolerances(
+                    "Failed to integrate {} of {} trajectories to the tolerances required: rtol={}, atol={}".format(
+                        n_fail, self.n_traj, self.integrator.rtol, self.integrator.atol))
+                raise cause
+        except KeyboardInterrupt as e:
+            self.__int_status = e
+            raise e
+        except Exception as e:
+            new_e = etypes.FailedIntegration("Failed to integrate system")
+            new_e.__cause__ = e
+            self.__int_status = new_e
+            raise new_e
+        else:
+            self.__int_status = 1
+
+    # ------------------------------------------------------------------ container protocol
+    def __len__(self):
+        return len(self._hist_y)
+
+    def __getitem__(self, index):
+        torch = _torch()
+        if isinstance(index, int):
+            if index >= len(self._hist_y) or index < -len(self._hist_y):
+                raise IndexError("index {} out of bounds for integrations with {} steps".format(index, len(self._hist_y)))
+            return StateTuple(t=self._user_time(self._hist_t[index]), y=self._user_shape(self._hist_y[index]), event=None)
+        if isinstance(index, slice):
+            return StateTuple(t=self.t[index], y=self.y[index], event=None)
+        if self.__dense_output and self._nodes is not None:
+            return StateTuple(t=index, y=self.sol(index), event=None)
+        raise KeyError("time indexing needs dense_output=True in the ensemble engine")
+
+    def __str__(self):
+        return "y({t0}) = {y0}\ndy = {eq}\ny({t}) = {y}\n".format(t0=self.__t0, y0=self[0].y, eq=str(self.equ_rhs),
+                                                                 t=self[-1].t, y=self[-1].y)
+
+    def __repr__(self):
+        return "\n".join(["{:>10}: {}".format(k, v) for k, v in (
+            ("message", self.integration_status), ("nfev", self.nfev), ("njev", self.njev), ("t0", self.__t0),
+            ("tf", self.__tf), ("trajectories", self.n_traj), ("method", self.__method.__name__))])

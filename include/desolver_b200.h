@@ -27,6 +27,12 @@ extern "C" {
 
 #define DSB_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define DSB_API __attribute__((visibility("default")))
+#else
+#define DSB_API
+#endif
+
 typedef enum {
     DSB_OK = 0,
     DSB_ERR_BAD_ARGUMENT = 1,
@@ -59,9 +65,9 @@ typedef enum {
 #define DSB_MAX_FUSED_STAGES 17
 
 /* ---- library ------------------------------------------------------------------------- */
-int         dsb_abi_version(void);
-const char *dsb_build_info(void);      /* contains "sm_100a"                                 */
-const char *dsb_last_error(void);
+DSB_API int         dsb_abi_version(void);
+DSB_API const char *dsb_build_info(void);      /* contains "sm_100a"                                 */
+DSB_API const char *dsb_last_error(void);
 
 /* ---- fused explicit Runge-Kutta ensemble engine ----------------------------------------
  * Replaces, for a built-in right-hand side, the whole of OdeSystem.integrate's while loop
@@ -71,11 +77,11 @@ const char *dsb_last_error(void);
  * (integrators/integrator_template.py:46-93), once per trajectory, in ONE persistent launch. */
 typedef struct dsb_erk_plan *dsb_erk_handle;
 
-int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int stages,
+DSB_API int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int stages,
                    const double *tableau_intermediate, /* stages x (stages+1), host */
                    const double *tableau_final,        /* final_rows x (stages+1), host */
                    int final_rows, double order, unsigned flags);
-int dsb_erk_destroy(dsb_erk_handle h);
+DSB_API int dsb_erk_destroy(dsb_erk_handle h);
 
 typedef struct {
     int64_t n;                 /* trajectories in this shard                                   */
@@ -97,43 +103,15 @@ typedef struct {
     uint64_t *counters;        /* device, >= 4 words, zeroed by the caller: [0] work queue     */
 } dsb_erk_run_args;
 
-int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);
+DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);
 /* number of kernel launches dsb_erk_run issues per call (for bench accounting) */
-int dsb_erk_run_launches(dsb_erk_handle h);
-
-/* ---- stage-level explicit RK (arbitrary right-hand side between kernels) -----------------
- * For a torch callable the Python side calls, per attempt and on one stream:
- *   for s in stages: dsb_erk_stage_state(s) -> rhs(t_stage, y_stage) written into K[s]
- *   dsb_erk_attempt_finish()  (dY, error estimate, per-trajectory L2 norm, controller,
- *                              masked commit, counters, active count)
- * K is [stages][dim][n]. */
-typedef struct {
-    int64_t n;
-    int32_t dim;               /* flattened state size of one trajectory                       */
-    double *y, *t, *dt;        /* committed state, as in dsb_erk_run_args                      */
-    double *h;                 /* [n] step size of the attempt in flight                       */
-    double *h0;                /* [n] first step size of the current retry chain               */
-    double *K;                 /* [stages][dim][n]                                             */
-    double *y_stage;           /* [dim][n] out of dsb_erk_stage_state                          */
-    double *t_stage;           /* [n]      out of dsb_erk_stage_state                          */
-    double *scale;             /* [dim][n] controller scale (EMA on retries)                   */
-    double *err_hist;          /* [2][n]  eps_last, eps_last_last                              */
-    int32_t *trial;            /* [n] attempt number inside the current step                   */
-    int32_t *flags;            /* [n] bit0 active, bit1 final-step                             */
-    double tf, rtol, atol;
-    int32_t *accepted, *rejected, *status;
-    uint64_t *counters;        /* [0] active trajectories after the attempt                    */
-} dsb_erk_stage_args;
-
-int dsb_erk_attempt_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);
-int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage, void *stream);
-int dsb_erk_attempt_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream);
+DSB_API int dsb_erk_run_launches(dsb_erk_handle h);
 
 /* ---- dense output ------------------------------------------------------------------------
  * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
  * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written
  * by dsb_erk_run: out[d][i] = Hermite interpolant of trajectory i at tq[i*tq_stride]. */
-int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
+DSB_API int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
                    int32_t node_capacity, const double *tq, int64_t tq_stride,
                    double *out, void *stream);
 
