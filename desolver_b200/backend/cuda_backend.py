@@ -138,3 +138,19 @@ class ErkHandle:
             self.close()
         except Exception:
             pass
+
+
+_handle_cache = {}
+
+
+def erk_handle(device_index, rhs_id, dim, tableau_intermediate, tableau_final, order, strict=False):
+    """Process-wide cache: one dsb_erk_handle per (device, rhs, dim, tableau, flavour).  Creating a
+    handle costs a cudaMalloc + synchronous copy, so systems share them."""
+    import numpy as np
+    key = (int(device_index), int(rhs_id), int(dim), np.asarray(tableau_intermediate).tobytes(),
+           np.asarray(tableau_final).tobytes(), float(order), bool(strict))
+    h = _handle_cache.get(key)
+    if h is None:
+        h = _handle_cache[key] = ErkHandle(device_index, rhs_id, dim, tableau_intermediate, tableau_final, order,
+                                           strict=strict)
+    return h

