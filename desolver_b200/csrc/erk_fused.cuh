@@ -24,7 +24,10 @@
 
 namespace dsb {
 
-constexpr int ERK_THREADS = 128;
+#ifndef DSB_ERK_THREADS
+#define DSB_ERK_THREADS 128
+#endif
+constexpr int ERK_THREADS = DSB_ERK_THREADS;
 
 template <int S>
 struct ErkKernelArgs {
@@ -142,7 +145,14 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
 
 // resident blocks per SM: 4 (<=128 registers) while the stage derivatives fit, else 2 (<=255)
 template <class Rhs, int S>
-constexpr int erk_min_blocks() { return (S * Rhs::DIM <= 21) ? 4 : 2; }
+constexpr int erk_min_blocks()
+{
+#ifdef DSB_ERK_MIN_BLOCKS
+    return DSB_ERK_MIN_BLOCKS;
+#else
+    return (S * Rhs::DIM <= 18) ? 5 : ((S * Rhs::DIM <= 21) ? 4 : 2);
+#endif
+}
 
 template <class Rhs, class Tab, bool STRICT>
 __global__ void __launch_bounds__(ERK_THREADS, (erk_min_blocks<Rhs, Tab::S>()))
@@ -309,25 +319,24 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         // ------------------------------------------------------------ controller
         bool redo = false;
         double new_dt = h;
+        double x = 0.0;                                                // ||diff / tol||_2^2
+        double corr = 1.0, sc_cur[D];
         if (tab.adaptive()) {
             const bool any_retry = __any_sync(FULL, trial > 0);       // warp-uniform: rare paths are skipped
-            double x = 0.0;                                            // ||diff / tol||_2^2
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fmax(fabs(y[d]), fabs(slope[d]));
-                if (any_retry && trial > 0) sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
-                scale[d] = sc;
+                double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fm::abs_max(y[d], slope[d]);
+                if (any_retry && trial > 0)                            // EMA on retries (:58-59); warp-uniform skip
+                    sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
+                sc_cur[d] = sc;
                 double tol = A::mad(rtol, sc, atol);                  // atol + rtol*sc
                 double q = STRICT ? err[d] / tol : fm::fast_div(err[d], tol);
                 x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
             }
             if (!STRICT && !live) x = 1.0;     // idle lanes stay on the fast path (no divergent libm calls)
-            double corr;
             if (!any_retry || trial < 2) {
-                double c_cur = corr_term<STRICT>(x, tab.order(), tab.order_p());
-                corr = c_cur;
-                if (any_retry && trial == 1) corr = A::mul(c_cur, corr_first);
-                if (trial == 0) corr_first = c_cur;
+                corr = corr_term<STRICT>(x, tab.order(), tab.order_p());
+                if (any_retry && trial == 1) corr = A::mul(corr, corr_first);
             } else {
                 // 3-term product, exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
                 double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
@@ -335,8 +344,6 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
                 corr = A::mul(A::mul(k1, k2), k3);
             }
-            x_last_last = x_last;
-            x_last = x;
             double u = A::sub(A::mul(0.8, corr), 1.0);
             double f;
             if (STRICT || !(u < 1e30)) f = A::add(1.0, atan(u));
@@ -366,6 +373,12 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 }
             } else {
                 rej++; trial++;
+                // retry-chain history (integrator_template.py:58-61,75,79,90), only needed when retrying
+                if (trial == 1) corr_first = corr;
+                x_last_last = x_last;
+                x_last = x;
+#pragma unroll
+                for (int d = 0; d < D; ++d) scale[d] = sc_cur[d];
                 if (trial > DSB_MAX_RETRIES) {
                     store((int)DSB_TRAJ_TOL_FAIL);                   // state frozen at the step start
                     live = false;

@@ -96,6 +96,20 @@ DSB_HD float rcpf_seed(float x)
 #endif
 }
 
+// max(|a|, |b|) through the integer pipe: for non-negative IEEE doubles the bit patterns order like
+// the values (a NaN, having the largest exponent, wins -- np.maximum semantics).  Saves the FP64
+// pipe a DSETP plus the select/NaN-quieting sequence fmax() expands to on sm_100.
+DSB_HD double abs_max(double a, double b)
+{
+    uint64_t ia = as_bits(a) & 0x7fffffffffffffffull, ib = as_bits(b) & 0x7fffffffffffffffull;
+    uint64_t m = ia > ib ? ia : ib;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)m);
+#else
+    double r; memcpy(&r, &m, 8); return r;
+#endif
+}
+
 // n / d to ~1 ulp for normal d; d = 0, inf, nan give inf/nan like IEEE division does.
 DSB_HD double fast_div(double n, double d)
 {
@@ -140,28 +154,25 @@ DSB_HD double inv_root_seed(double x, float inv_p)
     return (double)ex2_seed(-lg * inv_p);
 }
 
-// x^(-1/P) for x in [1e-280, 1e280]; two Newton steps c <- c + c (1 - x c^P) / P.
+// x^(-1/P) for x in [1e-280, 1e280]: ONE third-order (Halley-type) correction of the FP32 seed,
+//   e = 1 - x c^P,   c <- c + c * (e/P) * (1 + (P+1)/(2P) e),
+// whose error is O(e^3): a 3e-7 seed lands below 1e-17 relative before rounding.
 template <int P>
 DSB_HD double inv_root(double x)
 {
     double c = inv_root_seed(x, 1.0f / (float)P);
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        double e = fma(-x, ipow<P>(c), 1.0);
-        c = fma(c, e * (1.0 / P), c);
-    }
-    return c;
+    double e = fma(-x, ipow<P>(c), 1.0);
+    double g = fma(e, (P + 1.0) / (2.0 * P), 1.0) * (e * (1.0 / P));
+    return fma(c, g, c);
 }
 
 DSB_HD double inv_root_rt(double x, int p)
 {
     double c = inv_root_seed(x, 1.0f / (float)p);
     double ip = 1.0 / (double)p;
-    for (int it = 0; it < 2; ++it) {
-        double e = fma(-x, ipow_rt(c, p), 1.0);
-        c = fma(c, e * ip, c);
-    }
-    return c;
+    double e = fma(-x, ipow_rt(c, p), 1.0);
+    double g = fma(e, 0.5 * (p + 1.0) * ip, 1.0) * (e * ip);
+    return fma(c, g, c);
 }
 
 // Host-side table builder: entry k = { u_k, 1 + atan(u_k) } with g_k = -0.5 + 1.5 k / 128.
