@@ -37,6 +37,26 @@ class ErkRunArgs(C.Structure):
     ]
 
 
+MAX_STAGES = 40
+
+
+class ErkStageArgs(C.Structure):
+    """dsb_erk_stage_args (include/desolver_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64),
+        ("dim", C.c_int32), ("chunks", C.c_int32),
+        ("y", C.c_void_p), ("t", C.c_void_p), ("dt", C.c_void_p),
+        ("h", C.c_void_p), ("h0", C.c_void_p),
+        ("K", C.c_void_p * MAX_STAGES),
+        ("y_stage", C.c_void_p), ("t_stage", C.c_void_p), ("dY", C.c_void_p), ("scale", C.c_void_p),
+        ("hist", C.c_void_p), ("partial", C.c_void_p),
+        ("trial", C.c_void_p), ("flags", C.c_void_p),
+        ("tf", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
+        ("accepted", C.c_void_p), ("rejected", C.c_void_p), ("status", C.c_void_p),
+        ("counters", C.c_void_p),
+    ]
+
+
 class LibraryError(RuntimeError):
     """A dsb_* call returned a non-zero status."""
 
@@ -86,6 +106,13 @@ def lib():
     L.dsb_dense_eval.restype = C.c_int
     L.dsb_dense_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p]
+    for name in ("dsb_erk_stage_begin", "dsb_erk_stage_state"):
+        getattr(L, name).restype = C.c_int
+        getattr(L, name).argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_int, C.c_void_p]
+    L.dsb_erk_stage_finish.restype = C.c_int
+    L.dsb_erk_stage_finish.argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_void_p]
+    L.dsb_erk_stage_launches.restype = C.c_int
+    L.dsb_erk_stage_launches.argtypes = [C.c_void_p]
     if L.dsb_abi_version() != 1:
         raise ImportError("libdesolver_b200.so has ABI version %d, expected 1" % L.dsb_abi_version())
     _lib = L
@@ -127,6 +154,19 @@ class ErkHandle:
 
     def run(self, args, stream_ptr):
         check(lib().dsb_erk_run(self._h, C.byref(args), stream_ptr), "dsb_erk_run")
+
+    def stage_begin(self, args, first_call, stream_ptr):
+        check(lib().dsb_erk_stage_begin(self._h, C.byref(args), 1 if first_call else 0, stream_ptr), "dsb_erk_stage_begin")
+
+    def stage_state(self, args, stage, stream_ptr):
+        check(lib().dsb_erk_stage_state(self._h, C.byref(args), int(stage), stream_ptr), "dsb_erk_stage_state")
+
+    def stage_finish(self, args, stream_ptr):
+        check(lib().dsb_erk_stage_finish(self._h, C.byref(args), stream_ptr), "dsb_erk_stage_finish")
+
+    @property
+    def stage_launches(self):
+        return lib().dsb_erk_stage_launches(self._h)
 
     def close(self):
         if self._h:

@@ -21,6 +21,9 @@ void set_error(const char *fmt, ...)
 
 int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim, int32_t cap,
                       const double *tq, int64_t tq_stride, double *out, cudaStream_t stream);
+int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
+int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream);
+int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream);
 
 }  // namespace dsb
 
@@ -119,6 +122,23 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
 }
 
 int dsb_erk_run_launches(dsb_erk_handle h) { return (h && h->fused_launch) ? 1 : 0; }
+
+int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream)
+{
+    return stage_begin(h, a, first_call, (cudaStream_t)stream);
+}
+
+int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage, void *stream)
+{
+    return stage_state(h, a, stage, (cudaStream_t)stream);
+}
+
+int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream)
+{
+    return stage_finish(h, a, (cudaStream_t)stream);
+}
+
+int dsb_erk_stage_launches(dsb_erk_handle h) { return h ? 1 + h->stages + 3 : 0; }
 
 int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
                    int32_t node_capacity, const double *tq, int64_t tq_stride, double *out, void *stream)

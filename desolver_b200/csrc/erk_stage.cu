@@ -1,0 +1,364 @@
+// erk_stage.cu -- K2: stage-level explicit Runge-Kutta kernels for right-hand sides that are NOT fused
+// (an arbitrary torch callable, or the dense linear RHS evaluated by a GEMM).  Per attempt the host side
+// issues, on one stream and without synchronising:
+//     dsb_erk_stage_begin                      step start: final-step clamp, h, h0 (differential_system.py:997-1002)
+//     for s in stages: dsb_erk_stage_state(s)  y_stage = y + h * sum_j a_sj K_j, t_stage = t + c_s h
+//                      K[s] = rhs(t_stage, y_stage)            <- the user's code, between our kernels
+//     dsb_erk_stage_finish                     dY, error estimate, per-trajectory L2 norm, controller,
+//                                              masked commit, counters, active count
+// Any explicit tableau with up to DSB_MAX_STAGES stages (RK14(12) has 35).  Layout: [dim][n], trajectory index
+// fastest, every array; K[s] are separate [dim][n] tensors (the tensors the user's RHS returned).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "fastmath.cuh"
+#include "plan.h"
+
+namespace dsb {
+
+constexpr int FLAG_ACTIVE = 1, FLAG_FINAL = 2, FLAG_ACCEPTED = 4;
+
+struct StageRow {
+    int nterms;
+    int idx[DSB_MAX_STAGES];
+    double coef[DSB_MAX_STAGES];
+    double c;
+};
+
+struct FinalRows {
+    int stages, adaptive, fsal, order_p;
+    double order;
+    double b[DSB_MAX_STAGES], db[DSB_MAX_STAGES];
+};
+
+struct KPtrs {
+    const double *k[DSB_MAX_STAGES];
+};
+
+// ---- begin: integrate()-entry logic on the first call, step-start logic on every attempt -------------------
+__global__ void stage_begin_kernel(dsb_erk_stage_args a, int first_call)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    int fl = a.flags[i];
+    double t = a.t[i], dt = a.dt[i];
+    if (first_call) {
+        int st0 = a.status ? a.status[i] : (int)DSB_TRAJ_DONE;
+        bool go = st0 != (int)DSB_TRAJ_TOL_FAIL;
+        double span = a.tf - t;
+        if (go) {
+            if (fabs(span) < DSB_EPS4) go = false;                                  // differential_system.py:956
+            else {
+                if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;            // :971
+                if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);   // :973-974
+            }
+        }
+        go = go && (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);                    // :996
+        fl = go ? FLAG_ACTIVE : 0;
+        a.trial[i] = 0;
+        a.dt[i] = dt;
+        if (a.status) a.status[i] = go ? (int)DSB_TRAJ_RUNNING : (st0 == (int)DSB_TRAJ_TOL_FAIL ? st0 : (int)DSB_TRAJ_DONE);
+    }
+    if (i == 0) a.counters[1] = 0;                 // active count, re-accumulated by the controller kernel
+    fl &= ~FLAG_ACCEPTED;
+    if ((fl & FLAG_ACTIVE) && a.trial[i] == 0) {
+        bool final_step = fabs(dt + t) > fabs(a.tf);                                // :997
+        double h = final_step ? (a.tf - t) : dt;
+        a.h[i] = h;
+        a.h0[i] = h;
+        fl = final_step ? (fl | FLAG_FINAL) : (fl & ~FLAG_FINAL);
+    }
+    a.flags[i] = fl;
+}
+
+// ---- stage state: non-zero coefficients only, left to right (runge_kutta_methods.py:45-48) -----------------
+template <bool STRICT>
+__global__ void stage_state_kernel(dsb_erk_stage_args a, KPtrs K, StageRow row, int keep_increment)
+{
+    using A = Ar<STRICT>;
+    const long long total = (long long)a.dim * a.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % a.n;
+        const double h = a.h[i];
+        double sum = 0.0;
+        for (int q = 0; q < row.nterms; ++q) sum = A::mad(K.k[row.idx[q]][e], row.coef[q], sum);
+        const double inc = A::mul(h, sum);
+        a.y_stage[e] = STRICT ? A::add(a.y[e], inc) : fma(h, sum, a.y[e]);
+        if (keep_increment) a.dY[e] = inc;       // FSAL: dState = last stage's increment (integrator_types.py:303-305)
+        if (e < a.n) a.t_stage[i] = A::add(a.t[i], A::mul(h, row.c));
+    }
+}
+
+// ---- finish 1/3: increment, error estimate, scale, partial squared norms -----------------------------------
+// grid.x tiles trajectories, grid.y tiles the state dimension into `chunks`; thread (i, chunk) walks its d-range.
+template <bool STRICT>
+__global__ void stage_increment_kernel(dsb_erk_stage_args a, KPtrs K, FinalRows fr, int d_per_chunk)
+{
+    using A = Ar<STRICT>;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int chunk = blockIdx.y;
+    const int d0 = chunk * d_per_chunk, d1 = min(a.dim, d0 + d_per_chunk);
+    const double h = a.h[i];
+    const int trial = a.trial[i];
+    const int S = fr.stages;
+    double x = 0.0;
+    bool first = true;
+    for (int d = d0; d < d1; ++d) {
+        const long long e = (long long)d * a.n + i;
+        double sb, se;
+        if (STRICT) {
+            // numpy contiguous reduce over ALL stages: < 8 left to right, else 8 accumulators + tail
+            double r[8], rb = 0.0, re = 0.0;
+            double q[8];
+            if (S < 8) {
+                for (int j = 0; j < S; ++j) {
+                    double kv = K.k[j][e];
+                    double tb = __dmul_rn(kv, fr.b[j]), te = __dmul_rn(fr.db[j], kv);
+                    rb = j == 0 ? tb : __dadd_rn(rb, tb);
+                    re = j == 0 ? te : __dadd_rn(re, te);
+                }
+            } else {
+                const int full = S - (S % 8);
+                for (int j = 0; j < 8; ++j) { double kv = K.k[j][e]; r[j] = __dmul_rn(kv, fr.b[j]); q[j] = __dmul_rn(fr.db[j], kv); }
+                for (int j0 = 8; j0 < full; j0 += 8)
+                    for (int j = 0; j < 8; ++j) {
+                        double kv = K.k[j0 + j][e];
+                        r[j] = __dadd_rn(r[j], __dmul_rn(kv, fr.b[j0 + j]));
+                        q[j] = __dadd_rn(q[j], __dmul_rn(fr.db[j0 + j], kv));
+                    }
+                rb = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                re = __dadd_rn(__dadd_rn(__dadd_rn(q[0], q[1]), __dadd_rn(q[2], q[3])), __dadd_rn(__dadd_rn(q[4], q[5]), __dadd_rn(q[6], q[7])));
+                for (int j = full; j < S; ++j) {
+                    double kv = K.k[j][e];
+                    rb = __dadd_rn(rb, __dmul_rn(kv, fr.b[j]));
+                    re = __dadd_rn(re, __dmul_rn(fr.db[j], kv));
+                }
+            }
+            sb = rb; se = re;
+        } else {
+            sb = 0.0; se = 0.0;
+            for (int j = 0; j < S; ++j) {
+                double kv = K.k[j][e];
+                sb = fma(kv, fr.b[j], sb);
+                se = fma(kv, fr.db[j], se);
+            }
+        }
+        // FSAL: dState is the last stage's increment, kept by the state kernel (integrator_types.py:303-305)
+        double dY = fr.fsal ? a.dY[e] : A::mul(h, sb);
+        double err = A::mul(h, se);
+        a.dY[e] = dY;
+        if (fr.adaptive) {
+            double slope = STRICT ? dY / h : (fr.fsal ? fm::fast_div(dY, h) : sb);
+            double sc = np_maximum(fabs(a.y[e]), fabs(slope));
+            if (trial > 0) sc = A::add(A::mul(0.8, a.scale[e]), A::mul(0.2, sc));
+            a.scale[e] = sc;
+            double tol = A::mad(a.rtol, sc, a.atol);
+            double qv = STRICT ? err / tol : fm::fast_div(err, tol);
+            x = first ? __dmul_rn(qv, qv) : fma(qv, qv, x);
+            first = false;
+        }
+    }
+    a.partial[(long long)chunk * a.n + i] = x;
+}
+
+__device__ __forceinline__ double guarded_pow2(double base, double expo)
+{
+    double k = pow(base, expo);
+    return k > 0.0 ? k : 1.0;
+}
+
+// ---- finish 2/3: per-trajectory controller + bookkeeping (integrator_template.py:46-93, types :188-224) ----
+template <bool STRICT>
+__global__ void stage_controller_kernel(dsb_erk_stage_args a, FinalRows fr, int chunks)
+{
+    using A = Ar<STRICT>;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int still_active = 0;
+    if (i < a.n) {
+        int fl = a.flags[i];
+        if (fl & FLAG_ACTIVE) {
+            const double h = a.h[i], h0 = a.h0[i];
+            int trial = a.trial[i];
+            bool redo = false;
+            double new_dt = h;
+            if (fr.adaptive) {
+                double x = a.partial[i];
+                for (int c = 1; c < chunks; ++c) x = __dadd_rn(x, a.partial[(long long)c * a.n + i]);
+                double *hist = a.hist;                                  // [0] x_last [1] x_last_last [2] corr_first
+                const double x_last = hist[i], x_ll = hist[a.n + i], corr_first = hist[2 * a.n + i];
+                double corr;
+                if (trial < 2) {
+                    double c_cur;
+                    if (STRICT) { double eps = 1.0 / sqrt(x); c_cur = eps > 0.0 ? pow(eps, 1.0 / fr.order) : 1.0; }
+                    else if (x > 1e-280 && x < 1e280 && fr.order_p > 0) c_cur = fm::inv_root_rt(x, fr.order_p);
+                    else if (x == 0.0) c_cur = CUDART_INF;
+                    else if (!(x < CUDART_INF)) c_cur = 1.0;
+                    else c_cur = pow(x, -0.5 / fr.order);
+                    corr = trial == 0 ? c_cur : A::mul(c_cur, corr_first);
+                    if (trial == 0) hist[2 * a.n + i] = c_cur;
+                } else {
+                    double k1 = guarded_pow2(1.0 / sqrt(x), 0.55 / fr.order);
+                    double k2 = guarded_pow2(1.0 / sqrt(x_last), -0.27 / fr.order);
+                    double k3 = guarded_pow2(1.0 / sqrt(x_ll), 0.05 / fr.order);
+                    corr = A::mul(A::mul(k1, k2), k3);
+                }
+                hist[a.n + i] = x_last;
+                hist[i] = x;
+                double f = A::add(1.0, atan(A::sub(A::mul(0.8, corr), 1.0)));
+                new_dt = A::mul(f, h);
+                redo = f < DSB_REJECT_BELOW;
+            }
+            if (!redo) {
+                double t = A::add(a.t[i], h);
+                a.t[i] = t;
+                double dt = a.dt[i];
+                if (!(fl & FLAG_FINAL)) { dt = new_dt; a.dt[i] = dt; }
+                a.trial[i] = 0;
+                if (a.accepted) a.accepted[i] += 1;
+                fl |= FLAG_ACCEPTED;
+                bool more = (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
+                if (!more) { fl &= ~FLAG_ACTIVE; if (a.status) a.status[i] = (int)DSB_TRAJ_DONE; }
+            } else {
+                if (a.rejected) a.rejected[i] += 1;
+                trial += 1;
+                if (trial > DSB_MAX_RETRIES) {
+                    fl &= ~FLAG_ACTIVE;
+                    a.trial[i] = 0;
+                    if (a.status) a.status[i] = (int)DSB_TRAJ_TOL_FAIL;
+                } else {
+                    a.trial[i] = trial;
+                    a.h[i] = h0 >= 0.0 ? fmin(new_dt, h0) : -fmin(fabs(new_dt), fabs(h0));
+                }
+            }
+            a.flags[i] = fl;
+            still_active = (fl & FLAG_ACTIVE) ? 1 : 0;
+        }
+    }
+    // block-reduced count of trajectories that still need attempts -> counters[1]
+    int cnt = __syncthreads_count(still_active);
+    if (threadIdx.x == 0 && cnt) atomicAdd((unsigned long long *)&a.counters[1], (unsigned long long)cnt);
+}
+
+// ---- finish 3/3: masked commit y += dY where the attempt was accepted (differential_system.py:1015) --------
+template <bool STRICT>
+__global__ void stage_commit_kernel(dsb_erk_stage_args a)
+{
+    using A = Ar<STRICT>;
+    const long long total = (long long)a.dim * a.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % a.n;
+        if (a.flags[i] & FLAG_ACCEPTED) a.y[e] = A::add(a.y[e], a.dY[e]);
+    }
+}
+
+static void build_final(const dsb_erk_plan *p, FinalRows &fr);
+
+static void build_rows(const dsb_erk_plan *p, int s, StageRow &row)
+{
+    const int S = p->stages, W = S + 1;
+    row.nterms = 0;
+    row.c = p->inter[s * W];
+    for (int j = 0; j < S; ++j) {
+        double v = p->inter[s * W + 1 + j];
+        if (v != 0.0) { row.idx[row.nterms] = j; row.coef[row.nterms] = v; row.nterms++; }
+    }
+}
+
+static void build_final(const dsb_erk_plan *p, FinalRows &fr)
+{
+    const int S = p->stages, W = S + 1;
+    fr.stages = S;
+    fr.adaptive = p->final_rows == 2;
+    fr.order = p->order;
+    double p2 = 2.0 * p->order;
+    fr.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
+    fr.fsal = 1;
+    for (int j = 0; j < S; ++j) {
+        fr.b[j] = p->fin[1 + j];
+        fr.db[j] = fr.adaptive ? p->fin[1 + j] - p->fin[W + 1 + j] : 0.0;
+        if (p->inter[(S - 1) * W + 1 + j] != fr.b[j]) fr.fsal = 0;
+    }
+}
+
+static int grid_for(long long total, int threads, int sms)
+{
+    long long blocks = (total + threads - 1) / threads;
+    long long cap = (long long)sms * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+static int check_args(const dsb_erk_plan *h, const dsb_erk_stage_args *a, const char *who)
+{
+    if (!h || !a) { set_error("%s: null handle or args", who); return DSB_ERR_BAD_ARGUMENT; }
+    if (h->stages > DSB_MAX_STAGES) { set_error("%s: %d stages exceed DSB_MAX_STAGES", who, h->stages); return DSB_ERR_UNSUPPORTED; }
+    if (a->n < 0 || a->dim < 1 || !a->y || !a->t || !a->dt || !a->h || !a->h0 || !a->y_stage || !a->t_stage || !a->dY ||
+        !a->scale || !a->hist || !a->partial || !a->trial || !a->flags || !a->counters || a->chunks < 1) {
+        set_error("%s: missing buffer", who);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    return DSB_OK;
+}
+
+int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream)
+{
+    int rc = check_args(h, a, "dsb_erk_stage_begin");
+    if (rc != DSB_OK || a->n == 0) return rc;
+    stage_begin_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, stream>>>(*a, first_call);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream)
+{
+    int rc = check_args(h, a, "dsb_erk_stage_state");
+    if (rc != DSB_OK || a->n == 0) return rc;
+    if (stage < 0 || stage >= h->stages) { set_error("dsb_erk_stage_state: stage %d out of range", stage); return DSB_ERR_BAD_ARGUMENT; }
+    StageRow row;
+    build_rows(h, stage, row);
+    KPtrs K;
+    for (int j = 0; j < DSB_MAX_STAGES; ++j) K.k[j] = j < h->stages ? a->K[j] : nullptr;
+    for (int q = 0; q < row.nterms; ++q)
+        if (!K.k[row.idx[q]]) { set_error("dsb_erk_stage_state: K[%d] is null", row.idx[q]); return DSB_ERR_BAD_ARGUMENT; }
+    const long long total = (long long)a->dim * a->n;
+    const int grid = grid_for(total, 256, h->sm_count);
+    FinalRows fr;
+    build_final(h, fr);
+    const int keep = (fr.fsal && stage == h->stages - 1) ? 1 : 0;
+    if (h->flags & DSB_FLAG_STRICT) stage_state_kernel<true><<<grid, 256, 0, stream>>>(*a, K, row, keep);
+    else stage_state_kernel<false><<<grid, 256, 0, stream>>>(*a, K, row, keep);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream)
+{
+    int rc = check_args(h, a, "dsb_erk_stage_finish");
+    if (rc != DSB_OK || a->n == 0) return rc;
+    FinalRows fr;
+    build_final(h, fr);
+    KPtrs K;
+    for (int j = 0; j < DSB_MAX_STAGES; ++j) {
+        K.k[j] = j < h->stages ? a->K[j] : nullptr;
+        if (j < h->stages && !K.k[j]) { set_error("dsb_erk_stage_finish: K[%d] is null", j); return DSB_ERR_BAD_ARGUMENT; }
+    }
+    const bool strict = h->flags & DSB_FLAG_STRICT;
+    const int chunks = a->chunks;
+    const int d_per_chunk = (a->dim + chunks - 1) / chunks;
+    dim3 g1((unsigned)((a->n + 127) / 128), (unsigned)chunks);
+    const unsigned g2 = (unsigned)((a->n + 127) / 128);
+    const int g3 = grid_for((long long)a->dim * a->n, 256, h->sm_count);
+    if (strict) {
+        stage_increment_kernel<true><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
+        stage_controller_kernel<true><<<g2, 128, 0, stream>>>(*a, fr, chunks);
+        stage_commit_kernel<true><<<g3, 256, 0, stream>>>(*a);
+    } else {
+        stage_increment_kernel<false><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
+        stage_controller_kernel<false><<<g2, 128, 0, stream>>>(*a, fr, chunks);
+        stage_commit_kernel<false><<<g3, 256, 0, stream>>>(*a);
+    }
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+}  // namespace dsb

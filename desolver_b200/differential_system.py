@@ -173,6 +173,8 @@ class OdeSystem(object):
         self.__events = []
         self._step_cap = DEFAULT_STEP_CAP
         self._launches = 0
+        self.sync_every = 8          # stage-level path: host checks the active count every N attempts
+        self.use_fused = True        # False forces the stage-level path even for a tagged right-hand side
         self.callback_every = 1
 
         self._y0 = y0.reshape(self.numel, self.n_traj).contiguous().clone()
@@ -448,6 +450,60 @@ class OdeSystem(object):
         self._launches += 1
         self._keepalive = params
 
+    def _run_stagewise(self, tf, callbacks, bar):
+        """Generic right-hand side: the user's torch callable is evaluated between the fused stage
+        kernels of libdesolver_b200.so (dsb_erk_stage_*), all on the current stream.  The host looks at
+        the active-trajectory count only every `self.sync_every` attempts."""
+        torch = _torch()
+        integ = self.integrator
+        if not isinstance(integ, integrators.RungeKuttaIntegrator):
+            raise NotImplementedError("stage-level path supports explicit Runge-Kutta methods")
+        if self.__dense_output:
+            raise NotImplementedError("dense_output needs a fused device right-hand side in this version")
+        n, D, S, dev = self.n_traj, self.numel, integ.stages, self.device
+        handle = cb.erk_handle(dev.index or 0, 100, D, integ.tableau_intermediate, integ.tableau_final, integ.order,
+                               strict=self.strict)
+        chunks = max(1, min(4096, (D + 127) // 128))
+        f64 = dict(dtype=torch.float64, device=dev)
+        buf = dict(h=torch.zeros(n, **f64), h0=torch.zeros(n, **f64), y_stage=torch.empty((D, n), **f64),
+                   t_stage=torch.zeros(n, **f64), dY=torch.zeros((D, n), **f64), scale=torch.zeros((D, n), **f64),
+                   hist=torch.ones((3, n), **f64), partial=torch.zeros((chunks, n), **f64),
+                   trial=torch.zeros(n, dtype=torch.int32, device=dev), flags=torch.zeros(n, dtype=torch.int32, device=dev))
+        a = cb.ErkStageArgs()
+        a.n, a.dim, a.chunks = n, D, chunks
+        a.y, a.t, a.dt = self._y.data_ptr(), self._t.data_ptr(), self._dt.data_ptr()
+        for k, v in buf.items():
+            setattr(a, k, v.data_ptr())
+        a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+        a.accepted, a.rejected, a.status = self.accepted.data_ptr(), self.rejected.data_ptr(), self.status.data_ptr()
+        a.counters = self._counters.data_ptr()
+        stream = cb.current_stream_ptr(dev)
+        y_view = self._user_shape(buf["y_stage"])
+        t_view = self._user_time(buf["t_stage"])
+        K = [None] * S
+        first, attempts = True, 0
+        while True:
+            handle.stage_begin(a, first, stream)
+            first = False
+            for s in range(S):
+                handle.stage_state(a, s, stream)
+                k = self.equ_rhs(t_view, y_view, **self.__consts)
+                k = k.to(torch.float64).reshape(D, n)
+                K[s] = k if k.is_contiguous() else k.contiguous()      # keep alive until the attempt finishes
+                a.K[s] = K[s].data_ptr()
+            handle.stage_finish(a, stream)
+            self._launches += handle.stage_launches
+            attempts += 1
+            for cbk in callbacks:
+                cbk(self)
+            if bar is not None:
+                bar.update()
+            if callbacks or attempts % self.sync_every == 0:
+                if int(self._counters[1].item()) == 0:
+                    break
+            if attempts > self._step_cap:
+                break
+
     def integrate(self, t=None, callback=None, eta=False, events=None):
         """Integrates every trajectory to time `t` (default: `self.tf`), reference `:912-1101`.
 
@@ -466,12 +522,17 @@ class OdeSystem(object):
             callbacks = list(callback)
         else:
             callbacks = [callback]
-        plugin = self._fused_plugin()
-        if plugin is None:
-            raise NotImplementedError(
-                "no fused device kernel for this right-hand side / method; the stage-level path is not built yet")
+        plugin = self._fused_plugin() if self.use_fused else None
         try:
-            if not callbacks and not eta:
+            if plugin is None:
+                bar = None
+                if eta:
+                    from tqdm.auto import tqdm
+                    bar = tqdm(total=None)
+                self._run_stagewise(tf, callbacks, bar)
+                if bar is not None:
+                    bar.close()
+            elif not callbacks and not eta:
                 self._run_fused(tf, plugin, self._step_cap, first_call=True)
             else:
                 first = True

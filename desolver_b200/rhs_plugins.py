@@ -94,4 +94,12 @@ nbody.plugin_id = RHS_NBODY
 nbody.plugin_params = ()
 nbody.plugin_shared = ("G", "eps2", "m")
 
+def forced_oscillator(t, y):
+    """y'' + y = t written as a first-order system (the reference's own test fixture,
+    /root/reference/desolver/tests/common.py:27-72).  NOT tagged: it is time dependent and has no fused
+    kernel, so it exercises the stage-level path (user callable between fused stage kernels)."""
+    return _stack([y[1], -y[0] + t], y)
+
+
 BUILTIN = {f.device_plugin: f for f in (lorenz, van_der_pol, harmonic_oscillator, linear, nbody)}
+BUILTIN["forced_oscillator"] = forced_oscillator

@@ -107,6 +107,50 @@ DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *st
 /* number of kernel launches dsb_erk_run issues per call (for bench accounting) */
 DSB_API int dsb_erk_run_launches(dsb_erk_handle h);
 
+/* ---- stage-level explicit RK (arbitrary right-hand side between kernels) -----------------
+ * For a right-hand side without a fused kernel (any torch callable; the dense linear RHS evaluated by
+ * a GEMM) the host issues per attempt, on one stream and without synchronising:
+ *   dsb_erk_stage_begin                       step start: final-step clamp, h, h0 (differential_system.py:997-1002;
+ *                                             with first_call=1 also integrate()'s entry logic :956-957,:971-974)
+ *   for s in stages: dsb_erk_stage_state(s)   y_stage = y + h*sum_j a_sj K_j, t_stage = t + c_s*h
+ *                                             (integrators/components/runge_kutta_methods.py:44-54)
+ *                    K[s] = rhs(t_stage, y_stage)          <- caller's code, same stream
+ *   dsb_erk_stage_finish                      dY = h*sum b_j K_j, error estimate, per-trajectory L2 norm,
+ *                                             controller, masked commit, counters
+ *                                             (integrators/integrator_types.py:188-228,302-323,
+ *                                              integrators/integrator_template.py:46-93,
+ *                                              differential_system.py:1015-1018,1070-1071)
+ * counters[1] holds the number of trajectories that still need attempts after dsb_erk_stage_finish.
+ * Any explicit tableau with up to DSB_MAX_STAGES stages; every array is [dim][n], trajectory index fastest. */
+#define DSB_MAX_STAGES 40
+
+typedef struct {
+    int64_t n;
+    int32_t dim;               /* flattened state size of one trajectory                       */
+    int32_t chunks;            /* partial-norm tiles over dim (>= 1)                           */
+    double *y, *t, *dt;        /* committed state, as in dsb_erk_run_args                      */
+    double *h;                 /* [n] step size of the attempt in flight                       */
+    double *h0;                /* [n] first step size of the current retry chain               */
+    const double *K[DSB_MAX_STAGES]; /* stage derivatives, each [dim][n]                       */
+    double *y_stage;           /* [dim][n] out of dsb_erk_stage_state                          */
+    double *t_stage;           /* [n]      out of dsb_erk_stage_state                          */
+    double *dY;                /* [dim][n] scratch: increment of the attempt in flight         */
+    double *scale;             /* [dim][n] controller scale (EMA on retries)                   */
+    double *hist;              /* [3][n]  retry-chain history                                  */
+    double *partial;           /* [chunks][n] partial squared error norms                      */
+    int32_t *trial;            /* [n] attempt number inside the current step                   */
+    int32_t *flags;            /* [n] bit0 active, bit1 final step, bit2 last attempt accepted */
+    double tf, rtol, atol;
+    int32_t *accepted, *rejected, *status;
+    uint64_t *counters;        /* >= 4 words; [1] = active trajectories after finish           */
+} dsb_erk_stage_args;
+
+DSB_API int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);
+DSB_API int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage, void *stream);
+DSB_API int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream);
+/* kernel launches issued by one begin + S x state + finish sequence (bench accounting) */
+DSB_API int dsb_erk_stage_launches(dsb_erk_handle h);
+
 /* ---- dense output ------------------------------------------------------------------------
  * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
  * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written

@@ -86,8 +86,8 @@ static void rhs_nbody(const orc_problem *p, const double *y, double *dy)
 
 void orc_rhs(const orc_problem *p, const double *prm, double t, const double *y, double *dy)
 {
-    (void)t; /* every built-in is autonomous */
     switch (p->rhs_id) {
+    case ORC_RHS_FORCED: dy[0] = y[1]; dy[1] = -y[0] + t; break;
     case ORC_RHS_LINEAR: rhs_linear(p, y, dy); break;
     case ORC_RHS_LORENZ: rhs_lorenz(prm, y, dy); break;
     case ORC_RHS_VDP:    rhs_vdp(prm, y, dy); break;

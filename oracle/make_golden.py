@@ -181,6 +181,17 @@ def main():
             np.savez_compressed(os.path.join(GOLD, "linear_rk87.npz"),
                                 **pack(res, dict(A=A, y0=Y0, tf=1.0, dt0=1e-2, rtol=1e-9, atol=1e-9)))
             print("linear_rk87 done")
+        if want("forced"):
+            # time-dependent RHS, the reference's own test fixture (tests/common.py:27-72)
+            rng = np.random.default_rng(21)
+            n = 64
+            y0 = np.ascontiguousarray(rng.uniform(-2, 2, size=(n, 2)).T)
+            for method, key in (("RK45", "rk45"), ("RK87", "rk87")):
+                jobs = [("forced_oscillator", method, y0[:, i], 0.0, 5.0, 1e-2, 1e-10, 1e-10, {}, None) for i in range(n)]
+                res = run_many(pool, jobs)
+                np.savez_compressed(os.path.join(GOLD, "forced_%s.npz" % key),
+                                    **pack(res, dict(y0=y0, tf=5.0, dt0=1e-2, rtol=1e-10, atol=1e-10)))
+            print("forced done")
         if want("dense"):
             tq = np.sort(np.random.default_rng(3).uniform(0.0, 2.0, size=24))
             y0 = bm.lorenz_ensemble(8)
