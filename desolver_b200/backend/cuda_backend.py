@@ -57,6 +57,33 @@ class ErkStageArgs(C.Structure):
     ]
 
 
+class SympRunArgs(C.Structure):
+    """dsb_symp_run_args (include/desolver_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64),
+        ("y", C.c_void_p), ("t", C.c_void_p), ("dt", C.c_void_p),
+        ("tf", C.c_double),
+        ("steps", C.c_void_p), ("status", C.c_void_p),
+        ("max_steps", C.c_int64),
+        ("first_call", C.c_int32), ("bodies", C.c_int32),
+        ("masses", C.c_void_p),
+        ("G", C.c_double), ("eps2", C.c_double),
+    ]
+
+
+class SympStageArgs(C.Structure):
+    """dsb_symp_stage_args (include/desolver_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64),
+        ("dim", C.c_int32),
+        ("y", C.c_void_p), ("t", C.c_void_p), ("dt", C.c_void_p),
+        ("h", C.c_void_p), ("dS", C.c_void_p), ("y_stage", C.c_void_p), ("t_stage", C.c_void_p),
+        ("flags", C.c_void_p), ("steps", C.c_void_p), ("status", C.c_void_p),
+        ("tf", C.c_double),
+        ("counters", C.c_void_p),
+    ]
+
+
 class LibraryError(RuntimeError):
     """A dsb_* call returned a non-zero status."""
 
@@ -113,6 +140,18 @@ def lib():
     L.dsb_erk_stage_finish.argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_void_p]
     L.dsb_erk_stage_launches.restype = C.c_int
     L.dsb_erk_stage_launches.argtypes = [C.c_void_p]
+    L.dsb_symp_create.restype = C.c_int
+    L.dsb_symp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_uint]
+    L.dsb_symp_destroy.restype = C.c_int
+    L.dsb_symp_destroy.argtypes = [C.c_void_p]
+    L.dsb_symp_run.restype = C.c_int
+    L.dsb_symp_run.argtypes = [C.c_void_p, C.POINTER(SympRunArgs), C.c_void_p]
+    L.dsb_symp_stage_begin.restype = C.c_int
+    L.dsb_symp_stage_begin.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p]
+    L.dsb_symp_stage_accumulate.restype = C.c_int
+    L.dsb_symp_stage_accumulate.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p]
+    L.dsb_symp_stage_commit.restype = C.c_int
+    L.dsb_symp_stage_commit.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_void_p]
     if L.dsb_abi_version() != 1:
         raise ImportError("libdesolver_b200.so has ABI version %d, expected 1" % L.dsb_abi_version())
     _lib = L
@@ -193,4 +232,46 @@ def erk_handle(device_index, rhs_id, dim, tableau_intermediate, tableau_final, o
     if h is None:
         h = _handle_cache[key] = ErkHandle(device_index, rhs_id, dim, tableau_intermediate, tableau_final, order,
                                            strict=strict)
+    return h
+
+
+class SympHandle:
+    """Owns one dsb_symp_handle: (device, right-hand side, splitting tableau)."""
+
+    def __init__(self, device_index, rhs_id, dim, tableau, strict=False):
+        import numpy as np
+        tab = np.ascontiguousarray(tableau, dtype=np.float64)
+        self.stages = tab.shape[0]
+        self._h = C.c_void_p()
+        check(lib().dsb_symp_create(C.byref(self._h), int(device_index), int(rhs_id), int(dim), self.stages,
+                                    tab.ctypes.data_as(_dp), FLAG_STRICT if strict else 0), "dsb_symp_create")
+
+    def run(self, args, stream_ptr):
+        check(lib().dsb_symp_run(self._h, C.byref(args), stream_ptr), "dsb_symp_run")
+
+    def stage_begin(self, args, first_call, stream_ptr):
+        check(lib().dsb_symp_stage_begin(self._h, C.byref(args), 1 if first_call else 0, stream_ptr), "dsb_symp_stage_begin")
+
+    def stage_accumulate(self, args, stage, f_ptr, stream_ptr):
+        check(lib().dsb_symp_stage_accumulate(self._h, C.byref(args), int(stage), f_ptr, stream_ptr),
+              "dsb_symp_stage_accumulate")
+
+    def stage_commit(self, args, stream_ptr):
+        check(lib().dsb_symp_stage_commit(self._h, C.byref(args), stream_ptr), "dsb_symp_stage_commit")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().dsb_symp_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def symp_handle(device_index, rhs_id, dim, tableau, strict=False):
+    import numpy as np
+    key = ("symp", int(device_index), int(rhs_id), int(dim), np.asarray(tableau).tobytes(), bool(strict))
+    h = _handle_cache.get(key)
+    if h is None:
+        h = _handle_cache[key] = SympHandle(device_index, rhs_id, dim, tableau, strict=strict)
     return h

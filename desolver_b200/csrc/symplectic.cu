@@ -1,0 +1,326 @@
+// symplectic.cu -- K4: explicit symplectic splitting integrators (BABs9o7H, ABAs5o6H, symplectic Euler).
+//
+//  (A) nbody_symplectic_kernel: fused, one launch per integrate(): the whole fixed-step loop of
+//      OdeSystem.integrate (differential_system.py:996-1002,1015-1018: last step truncated to land on tf)
+//      around ExplicitSymplecticIntegrator.step (integrators/integrator_types.py:402-417) with the softened
+//      gravitational N-body right-hand side (desolver_b200/rhs_plugins.py:nbody) evaluated in shared memory.
+//      One thread per body, `SPB` systems per CTA; all-pairs forces, j summed left to right like the
+//      reference's sum over axis -2.  The reference evaluates the full RHS at all S stages and multiplies the
+//      unused half by a 0 mask; here a force evaluation happens only at stages whose kick
+//      coefficient is non-zero (10 of 19 for BABs9o7H) -- identical results for finite states.
+//  (B) stage-level kernels for any other right-hand side (user torch callable between them).
+// Kick (momentum) variables = second half of axis 0 of the state, drift (position) = first half
+// (integrator_types.py:359-362).  Time advances by tableau column 1 (:412).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace dsb {
+
+struct SympTableau {
+    int stages;
+    double drift[DSB_MAX_STAGES];   // column 1
+    double kick[DSB_MAX_STAGES];    // column 2
+};
+
+}  // namespace dsb
+
+struct dsb_symp_plan {
+    int device = 0, rhs_id = 0, dim = 0, sm_count = 0;
+    unsigned flags = 0;
+    dsb::SympTableau tab;
+};
+
+namespace dsb {
+
+// ------------------------------------------------------------------------------------------ (A) fused N-body
+template <bool STRICT>
+__global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
+{
+    using A = Ar<STRICT>;
+    extern __shared__ double smem[];
+    const int nb = a.bodies;
+    const int spb = blockDim.y;
+    double *sq = smem + (size_t)threadIdx.y * nb * 3;       // this system's stage positions
+    double *sm = smem + (size_t)spb * nb * 3;                // masses (shared by all systems)
+    const long long sys = (long long)blockIdx.x * spb + threadIdx.y;
+    const int i = threadIdx.x;
+    const bool valid = sys < a.n;
+    for (int j = threadIdx.y * nb + i; j < nb; j += nb * spb) sm[j] = a.masses[j];
+    const long long n = a.n;
+    const long long s_ = valid ? sys : 0;
+
+    double q0[3], v0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        q0[k] = a.y[(long long)(i * 3 + k) * n + s_];
+        v0[k] = a.y[(long long)(nb * 3 + i * 3 + k) * n + s_];
+    }
+    double t = a.t[s_], dt = a.dt[s_];
+    const double tf = a.tf;
+    int steps = 0;
+    bool go = valid;
+    if (a.first_call) {                                                     // differential_system.py:956-957,971-974
+        double span = tf - t;
+        if (fabs(span) < DSB_EPS4) go = false;
+        else {
+            if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
+            if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+        }
+    }
+    __syncthreads();
+
+    // the loop condition is uniform within a system (same t, dt in all its threads); systems of one CTA may
+    // stop at different steps, so every thread keeps hitting the barriers until the whole CTA is done
+    for (;;) {
+        bool more = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32) && (a.max_steps < 0 || steps < a.max_steps);
+        if (!__syncthreads_or(more)) break;
+        const bool final_step = fabs(dt + t) > fabs(tf);                    // :997
+        const double h = final_step ? (tf - t) : dt;
+        double dq[3] = {0.0, 0.0, 0.0}, dv[3] = {0.0, 0.0, 0.0};
+        for (int s = 0; s < T.stages; ++s) {
+            const double c1 = T.drift[s], c2 = T.kick[s];
+            double vcur[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vcur[k] = A::add(v0[k], dv[k]);
+            if (c2 != 0.0) {                                                // kick stage: forces at q + dS_q
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sq[i * 3 + k] = A::add(q0[k], dq[k]);
+                __syncthreads();
+                const double qx = sq[i * 3], qy = sq[i * 3 + 1], qz = sq[i * 3 + 2];
+                double ax = 0.0, ay = 0.0, az = 0.0;
+                for (int j = 0; j < nb; ++j) {
+                    const double dx = A::sub(sq[j * 3], qx), dy = A::sub(sq[j * 3 + 1], qy), dz = A::sub(sq[j * 3 + 2], qz);
+                    double w;
+                    if (STRICT) {
+                        double r2 = A::add(A::add(A::add(A::mul(dx, dx), A::mul(dy, dy)), A::mul(dz, dz)), a.eps2);
+                        w = A::mul(sm[j], pow(r2, -1.5));
+                    } else {
+                        double r2 = fma(dz, dz, fma(dy, dy, dx * dx)) + a.eps2;
+                        double rinv = rsqrt(r2);
+                        w = sm[j] * (rinv * rinv * rinv);
+                    }
+                    w = (j == i) ? 0.0 : w;
+                    ax = A::mad(dx, w, ax);
+                    ay = A::mad(dy, w, ay);
+                    az = A::mad(dz, w, az);
+                }
+                __syncthreads();
+                dv[0] = A::add(dv[0], A::mul(A::mul(h, A::mul(a.G, ax)), c2));     // dS += (h*f) * coef  (:409-413)
+                dv[1] = A::add(dv[1], A::mul(A::mul(h, A::mul(a.G, ay)), c2));
+                dv[2] = A::add(dv[2], A::mul(A::mul(h, A::mul(a.G, az)), c2));
+            }
+            if (c1 != 0.0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dq[k] = A::add(dq[k], A::mul(A::mul(h, vcur[k]), c1));
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { q0[k] = A::add(q0[k], dq[k]); v0[k] = A::add(v0[k], dv[k]); }
+            t = A::add(t, h);
+            steps++;
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            a.y[(long long)(i * 3 + k) * n + sys] = q0[k];
+            a.y[(long long)(nb * 3 + i * 3 + k) * n + sys] = v0[k];
+        }
+        if (i == 0) {
+            a.t[sys] = t;
+            a.dt[sys] = dt;
+            if (a.steps) a.steps[sys] += steps;
+            bool more = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+            if (a.status) a.status[sys] = more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- (B) stage-level kernels
+constexpr int SFLAG_ACTIVE = 1;
+
+__global__ void symp_begin_kernel(dsb_symp_stage_args a, int first_call)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double t = a.t[i], dt = a.dt[i];
+    int fl = a.flags[i];
+    if (first_call) {
+        bool go = true;
+        double span = a.tf - t;
+        if (fabs(span) < DSB_EPS4) go = false;
+        else {
+            if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
+            if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+        }
+        a.dt[i] = dt;
+        fl = go ? SFLAG_ACTIVE : 0;
+    }
+    bool more = (fl & SFLAG_ACTIVE) && (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
+    fl = more ? SFLAG_ACTIVE : 0;
+    a.flags[i] = fl;
+    if (a.status) a.status[i] = more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE;
+    bool final_step = fabs(dt + t) > fabs(a.tf);
+    a.h[i] = more ? (final_step ? (a.tf - t) : dt) : 0.0;
+    a.t_stage[i] = t;
+    if (i == 0) a.counters[1] = 0;
+}
+
+// dS = 0 and y_stage = y at the start of a step
+__global__ void symp_reset_kernel(dsb_symp_stage_args a)
+{
+    const long long total = (long long)a.dim * a.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        a.dS[e] = 0.0;
+        a.y_stage[e] = a.y[e];
+    }
+}
+
+// dS += (h * f) * (drift or kick coefficient); y_stage = y + dS; t_stage += h * drift   (:407-413)
+template <bool STRICT>
+__global__ void symp_accumulate_kernel(dsb_symp_stage_args a, const double *f, double c_drift, double c_kick)
+{
+    using A = Ar<STRICT>;
+    const long long total = (long long)a.dim * a.n;
+    const long long half = (long long)(a.dim / 2) * a.n;       // first half of axis 0 = drift variables
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % a.n;
+        const double h = a.h[i];
+        const double coef = e < half ? c_drift : c_kick;
+        double ds = a.dS[e];
+        if (coef != 0.0) ds = A::add(ds, A::mul(A::mul(h, f[e]), coef));
+        a.dS[e] = ds;
+        a.y_stage[e] = A::add(a.y[e], ds);
+        if (e < a.n) a.t_stage[i] = A::add(a.t_stage[i], A::mul(h, c_drift));
+    }
+}
+
+template <bool STRICT>
+__global__ void symp_commit_kernel(dsb_symp_stage_args a)
+{
+    using A = Ar<STRICT>;
+    const long long total = (long long)a.dim * a.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e % a.n;
+        if (a.flags[i] & SFLAG_ACTIVE) a.y[e] = A::add(a.y[e], a.dS[e]);
+    }
+}
+
+__global__ void symp_advance_kernel(dsb_symp_stage_args a)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int still = 0;
+    if (i < a.n && (a.flags[i] & SFLAG_ACTIVE)) {
+        double t = __dadd_rn(a.t[i], a.h[i]);
+        a.t[i] = t;
+        if (a.steps) a.steps[i] += 1;
+        double dt = a.dt[i];
+        still = (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
+        if (!still) { a.flags[i] = 0; if (a.status) a.status[i] = (int)DSB_TRAJ_DONE; }
+    }
+    int cnt = __syncthreads_count(still);
+    if (threadIdx.x == 0 && cnt) atomicAdd((unsigned long long *)&a.counters[1], (unsigned long long)cnt);
+}
+
+static int grid_for(long long total, int threads, int sms)
+{
+    long long blocks = (total + threads - 1) / threads;
+    long long cap = (long long)sms * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" {
+
+int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int stages, const double *tableau, unsigned flags)
+{
+    if (!out || !tableau || stages < 1 || stages > DSB_MAX_STAGES || dim < 2 || (dim & 1)) {
+        set_error("dsb_symp_create: bad argument (stages=%d dim=%d; dim must be even, stages <= %d)", stages, dim, DSB_MAX_STAGES);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    DSB_CUDA_CHECK(cudaSetDevice(device));
+    dsb_symp_plan *p = new dsb_symp_plan;
+    p->device = device; p->rhs_id = rhs_id; p->dim = dim; p->flags = flags;
+    p->tab.stages = stages;
+    for (int s = 0; s < stages; ++s) { p->tab.drift[s] = tableau[3 * s + 1]; p->tab.kick[s] = tableau[3 * s + 2]; }
+    cudaDeviceProp prop;
+    DSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    *out = p;
+    return DSB_OK;
+}
+
+int dsb_symp_destroy(dsb_symp_handle h) { delete h; return DSB_OK; }
+
+int dsb_symp_run(dsb_symp_handle h, const dsb_symp_run_args *a, void *stream)
+{
+    if (!h || !a || !a->y || !a->t || !a->dt) { set_error("dsb_symp_run: null argument"); return DSB_ERR_BAD_ARGUMENT; }
+    if (h->rhs_id != DSB_RHS_NBODY) { set_error("dsb_symp_run: fused symplectic kernel exists for the N-body right-hand side only"); return DSB_ERR_UNSUPPORTED; }
+    if (a->bodies < 1 || a->bodies > 1024 || h->dim != 6 * a->bodies || !a->masses) {
+        set_error("dsb_symp_run: state dim %d does not match 2*bodies*3 with bodies=%d", h->dim, a->bodies);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    if (a->n == 0) return DSB_OK;
+    int spb = 128 / a->bodies;
+    if (spb < 1) spb = 1;
+    dim3 block((unsigned)a->bodies, (unsigned)spb);
+    unsigned grid = (unsigned)((a->n + spb - 1) / spb);
+    size_t smem = sizeof(double) * ((size_t)spb * a->bodies * 3 + a->bodies);
+    if (h->flags & DSB_FLAG_STRICT) nbody_symplectic_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(*a, h->tab);
+    else nbody_symplectic_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(*a, h->tab);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+static int symp_check(dsb_symp_handle h, const dsb_symp_stage_args *a, const char *who)
+{
+    if (!h || !a || !a->y || !a->t || !a->dt || !a->h || !a->dS || !a->y_stage || !a->t_stage || !a->flags || !a->counters ||
+        a->dim != h->dim || a->n < 0) {
+        set_error("%s: bad argument", who);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    return DSB_OK;
+}
+
+int dsb_symp_stage_begin(dsb_symp_handle h, const dsb_symp_stage_args *a, int first_call, void *stream)
+{
+    int rc = symp_check(h, a, "dsb_symp_stage_begin");
+    if (rc != DSB_OK || a->n == 0) return rc;
+    symp_begin_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a, first_call);
+    symp_reset_kernel<<<grid_for((long long)a->dim * a->n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(*a);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+int dsb_symp_stage_accumulate(dsb_symp_handle h, const dsb_symp_stage_args *a, int stage, const double *f, void *stream)
+{
+    int rc = symp_check(h, a, "dsb_symp_stage_accumulate");
+    if (rc != DSB_OK || a->n == 0) return rc;
+    if (stage < 0 || stage >= h->tab.stages || !f) { set_error("dsb_symp_stage_accumulate: bad stage or null f"); return DSB_ERR_BAD_ARGUMENT; }
+    const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
+    if (h->flags & DSB_FLAG_STRICT)
+        symp_accumulate_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, f, h->tab.drift[stage], h->tab.kick[stage]);
+    else
+        symp_accumulate_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, f, h->tab.drift[stage], h->tab.kick[stage]);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void *stream)
+{
+    int rc = symp_check(h, a, "dsb_symp_stage_commit");
+    if (rc != DSB_OK || a->n == 0) return rc;
+    const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
+    if (h->flags & DSB_FLAG_STRICT) symp_commit_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+    else symp_commit_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+    symp_advance_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+}  // extern "C"

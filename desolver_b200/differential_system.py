@@ -504,6 +504,85 @@ class OdeSystem(object):
             if attempts > self._step_cap:
                 break
 
+    def _run_symplectic(self, tf, callbacks, bar):
+        """Explicit symplectic splitting (fixed dt).  Fused kernel for the tagged N-body right-hand side,
+        stage-level kernels around the user's callable otherwise."""
+        torch = _torch()
+        integ = self.integrator
+        n, D, dev = self.n_traj, self.numel, self.device
+        stream = cb.current_stream_ptr(dev)
+        rhs = self.equ_rhs
+        fused = (self.use_fused and getattr(rhs, "device_plugin", None) == "nbody" and len(self.dim) == 3
+                 and self.dim[0] == 2 and self.dim[2] == 3 and not self.__dense_output)
+        if self.__dense_output:
+            raise NotImplementedError("dense_output is not available for symplectic methods in this version")
+        if fused:
+            nb = self.dim[1]
+            handle = cb.symp_handle(dev.index or 0, rhs.plugin_id, D, integ.tableau_intermediate, strict=self.strict)
+            m = torch.as_tensor(self.__consts["m"], dtype=torch.float64, device=dev).contiguous()
+            if tuple(m.shape) != (nb,):
+                raise ValueError("fused N-body kernel needs masses of shape (%d,) shared by all systems" % nb)
+            a = cb.SympRunArgs()
+            a.n, a.y, a.t, a.dt = n, self._y.data_ptr(), self._t.data_ptr(), self._dt.data_ptr()
+            a.tf = float(tf)
+            a.steps, a.status = self.accepted.data_ptr(), self.status.data_ptr()
+            a.bodies, a.masses = nb, m.data_ptr()
+            a.G, a.eps2 = float(self.__consts.get("G", 1.0)), float(self.__consts.get("eps2", 0.0))
+            if not callbacks and bar is None:
+                a.max_steps, a.first_call = -1, 1
+                handle.run(a, stream)
+                self._launches += 1
+            else:
+                first = True
+                while True:
+                    a.max_steps, a.first_call = self.callback_every, 1 if first else 0
+                    first = False
+                    handle.run(a, stream)
+                    self._launches += 1
+                    for cbk in callbacks:
+                        cbk(self)
+                    if bar is not None:
+                        bar.update()
+                    if not bool((self.status == cb.TRAJ_RUNNING).any().item()):
+                        break
+            self._keepalive = m
+            return
+        handle = cb.symp_handle(dev.index or 0, 100, D, integ.tableau_intermediate, strict=self.strict)
+        S = integ.stages
+        f64 = dict(dtype=torch.float64, device=dev)
+        buf = dict(h=torch.zeros(n, **f64), dS=torch.zeros((D, n), **f64), y_stage=torch.empty((D, n), **f64),
+                   t_stage=torch.zeros(n, **f64), flags=torch.zeros(n, dtype=torch.int32, device=dev))
+        a = cb.SympStageArgs()
+        a.n, a.dim = n, D
+        a.y, a.t, a.dt = self._y.data_ptr(), self._t.data_ptr(), self._dt.data_ptr()
+        for k, v in buf.items():
+            setattr(a, k, v.data_ptr())
+        a.steps, a.status = self.accepted.data_ptr(), self.status.data_ptr()
+        a.tf = float(tf)
+        a.counters = self._counters.data_ptr()
+        y_view = self._user_shape(buf["y_stage"])
+        t_view = self._user_time(buf["t_stage"])
+        first, steps = True, 0
+        while True:
+            handle.stage_begin(a, first, stream)
+            first = False
+            for s in range(S):
+                f = self.equ_rhs(t_view, y_view, **self.__consts).to(torch.float64).reshape(D, n)
+                f = f if f.is_contiguous() else f.contiguous()
+                handle.stage_accumulate(a, s, f.data_ptr(), stream)
+            handle.stage_commit(a, stream)
+            self._launches += 4 + S
+            steps += 1
+            for cbk in callbacks:
+                cbk(self)
+            if bar is not None:
+                bar.update()
+            if callbacks or steps % self.sync_every == 0:
+                if int(self._counters[1].item()) == 0:
+                    break
+            if steps > self._step_cap:
+                break
+
     def integrate(self, t=None, callback=None, eta=False, events=None):
         """Integrates every trajectory to time `t` (default: `self.tf`), reference `:912-1101`.
 
@@ -524,7 +603,15 @@ class OdeSystem(object):
             callbacks = [callback]
         plugin = self._fused_plugin() if self.use_fused else None
         try:
-            if plugin is None:
+            if self.integrator.symplectic:
+                bar = None
+                if eta:
+                    from tqdm.auto import tqdm
+                    bar = tqdm(total=None)
+                self._run_symplectic(tf, callbacks, bar)
+                if bar is not None:
+                    bar.close()
+            elif plugin is None:
                 bar = None
                 if eta:
                     from tqdm.auto import tqdm

@@ -73,19 +73,25 @@ linear.plugin_shared = ("A",)
 
 
 def nbody(t, y, m=None, eps2=0.0, G=1.0):
-    """Softened gravitational N-body.  y = (2, [B,] nb, 3): y[0] positions, y[1] velocities."""
-    q, v = y[0], y[1]
-    d = q[..., None, :, :] - q[..., :, None, :]            # d[i, j] = q[j] - q[i]
-    r2 = (d * d).sum(-1) + eps2
-    w = m * r2 ** -1.5                                      # m broadcasts over j (last axis)
-    nb = q.shape[-2]
+    """Softened gravitational N-body.  y = (2, nb, 3[, N]): y[0] positions, y[1] velocities; a trailing
+    axis enumerates independent systems (the ensemble axis of `OdeSystem(..., ensemble=True)`).
+    Masses m (nb,) are shared by all systems."""
+    q, v = y[0], y[1]                                       # (nb, 3, ...)
+    extra = (1,) * (q.ndim - 2)
+    d = q[None] - q[:, None]                                # d[i, j] = q[j] - q[i]   (nb, nb, 3, ...)
+    r2 = (d * d).sum(2) + eps2                              # (nb, nb, ...)
+    nb = q.shape[0]
     if type(y).__module__.split(".")[0] == "torch":
         import torch
-        w = w * (1.0 - torch.eye(nb, dtype=w.dtype, device=w.device))
+        off = 1.0 - torch.eye(nb, dtype=q.dtype, device=q.device)
+        mm = torch.as_tensor(m, dtype=q.dtype, device=q.device)
     else:
         import numpy
-        w = w * (1.0 - numpy.eye(nb))
-    acc = G * (d * w[..., None]).sum(-2)
+        off = 1.0 - numpy.eye(nb)
+        mm = numpy.asarray(m)
+    w = mm.reshape((1, nb) + extra) * r2 ** -1.5
+    w = w * off.reshape((nb, nb) + extra)                   # no self-interaction
+    acc = G * (d * w[:, :, None]).sum(1)                    # sum over j   (nb, 3, ...)
     return _stack([v, acc], y)
 
 

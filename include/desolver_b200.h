@@ -151,6 +151,54 @@ DSB_API int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, 
 /* kernel launches issued by one begin + S x state + finish sequence (bench accounting) */
 DSB_API int dsb_erk_stage_launches(dsb_erk_handle h);
 
+/* ---- explicit symplectic splitting integrators -------------------------------------------
+ * Replace ExplicitSymplecticIntegrator.__call__/step (integrators/integrator_types.py:375-417) and the
+ * fixed-step loop of OdeSystem.integrate around it (differential_system.py:996-1002,1015-1018).
+ * `tableau` is the class data: stages x 3, column 1 = drift weight (also the time advance), column 2 = kick
+ * weight (integrators/explicit_integration_schemes.py:340-425).  Kick variables are the second half of
+ * axis 0 of the state (integrator_types.py:359-362); dim must be even. */
+typedef struct dsb_symp_plan *dsb_symp_handle;
+
+DSB_API int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int stages,
+                            const double *tableau /* stages x 3, host */, unsigned flags);
+DSB_API int dsb_symp_destroy(dsb_symp_handle h);
+
+/* fused: gravitational N-body, state per system (2, bodies, 3) = (q; v), one launch per integrate() */
+typedef struct {
+    int64_t n;                 /* systems                                                       */
+    double *y;                 /* [2*bodies*3][n] in/out                                        */
+    double *t, *dt;            /* [n] in/out                                                    */
+    double tf;
+    int32_t *steps;            /* [n] += steps taken                                            */
+    int32_t *status;           /* [n] dsb_traj_status                                           */
+    int64_t max_steps;         /* step budget per system for this call, < 0 = none              */
+    int32_t first_call;
+    int32_t bodies;
+    const double *masses;      /* [bodies] device, shared by all systems                        */
+    double G, eps2;            /* gravitational constant, Plummer softening squared             */
+} dsb_symp_run_args;
+
+DSB_API int dsb_symp_run(dsb_symp_handle h, const dsb_symp_run_args *args, void *stream);
+
+/* stage-level, any right-hand side: per step  begin; for s in stages: f = rhs(t_stage, y_stage),
+ * accumulate(s, f);  commit.  counters[1] = systems still short of tf after commit. */
+typedef struct {
+    int64_t n;
+    int32_t dim;
+    double *y, *t, *dt;
+    double *h;                 /* [n] step size of the step in flight                           */
+    double *dS;                /* [dim][n] accumulated increment                                */
+    double *y_stage;           /* [dim][n] y + dS                                               */
+    double *t_stage;           /* [n]                                                           */
+    int32_t *flags, *steps, *status;
+    double tf;
+    uint64_t *counters;
+} dsb_symp_stage_args;
+
+DSB_API int dsb_symp_stage_begin(dsb_symp_handle h, const dsb_symp_stage_args *a, int first_call, void *stream);
+DSB_API int dsb_symp_stage_accumulate(dsb_symp_handle h, const dsb_symp_stage_args *a, int stage, const double *f, void *stream);
+DSB_API int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void *stream);
+
 /* ---- dense output ------------------------------------------------------------------------
  * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
  * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written

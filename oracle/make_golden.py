@@ -206,13 +206,14 @@ def main():
     # ---- symplectic N-body: the batched reference call IS the per-system semantics ----
     if want("nbody"):
         from desolver_b200 import rhs_plugins
-        state, m = bm.nbody_ensemble(6, bodies=8, seed=1)
+        state, m = bm.nbody_ensemble(6, bodies=8, seed=1)                  # (2, B, nb, 3)
+        ens = np.ascontiguousarray(np.moveaxis(state, 1, -1))               # (2, nb, 3, B): ensemble axis last
         blob = dict(state0=state, m=m, eps2=1e-4, G=1.0, dt=0.01, tf=0.105)
         for method in ("BABS9O7H", "ABAS5O6H"):
-            a = de.OdeSystem(rhs_plugins.nbody, y0=state, t=(0.0, 0.105), dt=0.01, constants=dict(m=m, eps2=1e-4, G=1.0))
+            a = de.OdeSystem(rhs_plugins.nbody, y0=ens, t=(0.0, 0.105), dt=0.01, constants=dict(m=m, eps2=1e-4, G=1.0))
             a.method = method
             a.integrate()
-            blob[method + ".y"] = np.asarray(a.y[-1])
+            blob[method + ".y"] = np.ascontiguousarray(np.moveaxis(np.asarray(a.y[-1]), -1, 1))   # back to (2, B, nb, 3)
             blob[method + ".t"] = np.asarray(a.t)
             # per-system runs must coincide bit for bit with the batched run (fixed dt, no controller)
             for b in range(2):
@@ -220,7 +221,7 @@ def main():
                                  constants=dict(m=m, eps2=1e-4, G=1.0))
                 s.method = method
                 s.integrate()
-                assert np.array_equal(s.y[-1], a.y[-1][:, b]), "batched != per-system"
+                assert np.array_equal(s.y[-1], blob[method + ".y"][:, b]), "batched != per-system"
         np.savez_compressed(os.path.join(GOLD, "nbody_symplectic.npz"), **blob)
         print("nbody done: steps", len(blob["BABS9O7H.t"]) - 1)
 

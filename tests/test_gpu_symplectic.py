@@ -1,0 +1,98 @@
+"""GPU parity tests of the explicit symplectic splitting integrators (K4): the fused N-body kernel and the
+stage-level kernels, against the reference fixtures and the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, rel_inf
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _de():
+    import desolver_b200 as de
+    return de
+
+
+def _nbody_system(state, m, tf, dt, method, strict=False, use_fused=True, eps2=1e-4):
+    """state (2, B, nb, 3) reference layout -> ensemble layout (2, nb, 3, B)."""
+    de = _de()
+    y0 = torch.as_tensor(np.ascontiguousarray(np.moveaxis(state, 1, -1)))
+    a = de.OdeSystem(de.rhs_plugins.nbody, y0, t=(0.0, tf), dt=dt, constants=dict(m=torch.as_tensor(m), eps2=eps2, G=1.0),
+                     ensemble=True, strict=strict)
+    a.method = method
+    a.use_fused = use_fused
+    a.integrate()
+    return a, np.moveaxis(a[-1].y.cpu().numpy(), -1, 1)
+
+
+@pytest.mark.parametrize("method", ["BABS9O7H", "ABAS5O6H"])
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("use_fused", [True, False])
+def test_nbody_golden(method, strict, use_fused):
+    g = load_golden("nbody_symplectic.npz")
+    a, y = _nbody_system(g["state0"], g["m"], float(g["tf"]), float(g["dt"]), method, strict, use_fused)
+    ref = g[method + ".y"]
+    steps = len(g[method + ".t"]) - 1
+    assert np.all(a.accepted.cpu().numpy() == steps) and np.all(a.status.cpu().numpy() == 0)
+    assert np.all(a[-1].t.cpu().numpy() == g[method + ".t"][-1])          # truncated last step lands on tf
+    B = ref.shape[1]
+    err = max(rel_inf(y[:, b].reshape(-1), ref[:, b].reshape(-1), axis=0) for b in range(B))
+    assert err <= (1e-13 if strict else 1e-11), err
+    assert a.nfev == B * (2 + a.integrator.stages * steps)                  # reference: 1 + S*steps + 1 per system
+
+
+def test_nbody_against_oracle_64_bodies():
+    from desolver_b200.integrators import tableaux as tb
+    from oracle import oracle as orc
+    de = _de()
+    state, m = de.benchmarks.nbody_ensemble(48, bodies=64, seed=4)
+    a, y = _nbody_system(state, m, 0.1, 0.01, "BABS9O7H")
+    B = state.shape[1]
+    y0 = np.ascontiguousarray(np.moveaxis(state, 1, -1).reshape(-1, B))
+    shared = np.concatenate([[1.0, 1e-4], m])
+    ref = orc.symplectic_ensemble(orc.RHS_NBODY, y0, 0.0, 0.1, 0.01, tb.symplectic_array("BABs9o7HSolver")[0],
+                                  shared=shared, threads=os.cpu_count())
+    got = a[-1].y.reshape(-1, B).cpu().numpy()
+    assert np.all(a.accepted.cpu().numpy() == ref["steps"]) and np.all(ref["steps"] == 10)
+    assert rel_inf(got, ref["y"]).max() <= 1e-11
+    # size-independent properties: total momentum is conserved, and the scheme is time-reversible
+    mom0 = (m[None, :, None] * state[1]).sum(1)
+    mom1 = (m[None, :, None] * y[1]).sum(1)
+    assert np.max(np.abs(mom1 - mom0)) < 1e-14
+    # reversibility needs the SAME step partition both ways: dyadic dt, tf = 8 dt exactly (no truncated step)
+    dt = 2.0 ** -7
+    f, _ = _nbody_system(state, m, 8 * dt, dt, "BABS9O7H")
+    assert np.all(f.accepted.cpu().numpy() == 8)
+    b = de.OdeSystem(de.rhs_plugins.nbody, f[-1].y.clone(), t=(8 * dt, 0.0), dt=dt,
+                     constants=dict(m=torch.as_tensor(m), eps2=1e-4, G=1.0), ensemble=True)
+    b.method = "BABS9O7H"
+    b.integrate()
+    assert np.all(b.accepted.cpu().numpy() == 8) and bool((b[-1].t == 0.0).all())
+    back = np.moveaxis(b[-1].y.cpu().numpy(), -1, 1)
+    diff = np.abs(back - state)
+    assert np.median(diff) < 1e-13 and np.max(diff) < 1e-8       # roundoff, amplified only by close encounters
+
+
+def test_known_answers_sho_symplectic():
+    """KA4 / KA5: README oscillator, dt = 0.05, 126 steps, last one truncated."""
+    de = _de()
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+    for key, method in (("KA4", "BABS9O7H"), ("KA5", "ABAS5O6H")):
+        two_pi = float.fromhex(ka[key]["t"][0])
+        want = np.array([float.fromhex(s) for s in ka[key]["y"]])
+        for strict in (True, False):
+            a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, np.array([1.0, 0.0]), t=(0, two_pi), dt=0.05, strict=strict)
+            a.method = method
+            a.integrate()
+            assert int(a.accepted[0]) == ka[key]["steps"] == 126
+            assert float(a[-1].t) == two_pi
+            assert a.nfev == ka[key]["nfev"]
+            y = a[-1].y.cpu().numpy()
+            if strict:
+                assert np.array_equal(y, want)                                  # +,* only: bit-exact
+            else:
+                assert np.max(np.abs(y - want)) < 1e-14
