@@ -14,9 +14,10 @@ from . import exception_types
 from . import integrators
 from . import rhs_plugins
 from . import benchmarks
+from . import distributed
 from .differential_system import DiffRHS, OdeSystem, DenseOutput, StateTuple, rhs_prettifier
 from .integrators import available_methods
 
 __version__ = "0.1.0"
-__all__ = ["backend", "exception_types", "integrators", "rhs_plugins", "benchmarks", "DiffRHS", "OdeSystem",
+__all__ = ["backend", "exception_types", "integrators", "rhs_plugins", "benchmarks", "distributed", "DiffRHS", "OdeSystem",
            "DenseOutput", "StateTuple", "rhs_prettifier", "available_methods"]

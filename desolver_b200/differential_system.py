@@ -482,6 +482,9 @@ class OdeSystem(object):
         t_view = self._user_time(buf["t_stage"])
         K = [None] * S
         first, attempts = True, 0
+        # heavy attempts (large state x ensemble): one host look per attempt costs nothing next to the
+        # attempt itself and saves up to sync_every-1 wasted lock-step rounds at the end
+        sync_every = 1 if D * n * S >= (1 << 24) else self.sync_every
         while True:
             handle.stage_begin(a, first, stream)
             first = False
@@ -498,7 +501,7 @@ class OdeSystem(object):
                 cbk(self)
             if bar is not None:
                 bar.update()
-            if callbacks or attempts % self.sync_every == 0:
+            if callbacks or attempts % sync_every == 0:
                 if int(self._counters[1].item()) == 0:
                     break
             if attempts > self._step_cap:
