@@ -77,7 +77,7 @@ def cpu_reference_sample(seconds_budget, n_global, rank_stride=1):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 100 ms during the timed region."""
+    """Samples SM clock and throttle reasons of one GPU every 5 ms during the timed region."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -109,7 +109,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()

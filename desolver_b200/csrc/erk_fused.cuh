@@ -326,8 +326,10 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fm::abs_max(y[d], slope[d]);
-                if (any_retry && trial > 0)                            // EMA on retries (:58-59); warp-uniform skip
-                    sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
+                if (any_retry) {                                       // EMA on retries (:58-59); warp-uniform branch
+                    asm volatile("" ::: "memory");                     // keep it a branch: no speculation of the EMA
+                    if (trial > 0) sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
+                }
                 sc_cur[d] = sc;
                 double tol = A::mad(rtol, sc, atol);                  // atol + rtol*sc
                 double q = STRICT ? err[d] / tol : fm::fast_div(err[d], tol);
@@ -339,10 +341,17 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 if (any_retry && trial == 1) corr = A::mul(corr, corr_first);
             } else {
                 // 3-term product, exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
-                double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
-                double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
-                double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
-                corr = A::mul(A::mul(k1, k2), k3);
+                asm volatile("" ::: "memory");
+                const double lo = 1e-250, hi = 1e250;
+                const bool tame = x > lo && x < hi && x_last > lo && x_last < hi && x_last_last > lo && x_last_last < hi;
+                if (!STRICT && tame && tab.order_p() > 0 && (tab.order_p() % 2) == 0) {
+                    corr = fm::corr_three_term(x, x_last, x_last_last, 20 * tab.order_p());
+                } else {
+                    double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
+                    double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
+                    double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
+                    corr = A::mul(A::mul(k1, k2), k3);
+                }
             }
             double u = A::sub(A::mul(0.8, corr), 1.0);
             double f;

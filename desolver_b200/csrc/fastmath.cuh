@@ -101,11 +101,15 @@ DSB_HD float rcpf_seed(float x)
 // pipe a DSETP plus the select/NaN-quieting sequence fmax() expands to on sm_100.
 DSB_HD double abs_max(double a, double b)
 {
+#if defined(__CUDA_ARCH__)
+    // explicit 32-bit halves: written as a 64-bit mask the compiler materialises |x| with a DADD (FP64 pipe)
+    unsigned ha = (unsigned)__double2hiint(a) & 0x7fffffffu, hb = (unsigned)__double2hiint(b) & 0x7fffffffu;
+    unsigned la = (unsigned)__double2loint(a), lb = (unsigned)__double2loint(b);
+    bool a_wins = (ha > hb) || (ha == hb && la > lb);
+    return __hiloint2double((int)(a_wins ? ha : hb), (int)(a_wins ? la : lb));
+#else
     uint64_t ia = as_bits(a) & 0x7fffffffffffffffull, ib = as_bits(b) & 0x7fffffffffffffffull;
     uint64_t m = ia > ib ? ia : ib;
-#if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)m);
-#else
     double r; memcpy(&r, &m, 8); return r;
 #endif
 }
@@ -173,6 +177,26 @@ DSB_HD double inv_root_rt(double x, int p)
     double e = fma(-x, ipow_rt(c, p), 1.0);
     double g = fma(e, 0.5 * (p + 1.0) * ip, 1.0) * (e * ip);
     return fma(c, g, c);
+}
+
+// The reference's 3-term controller product for the 3rd and later attempt of a step
+// (integrators/integrator_template.py:80-90), for finite positive squared norms x = ||e/tol||^2 (eps = x^-1/2):
+//   eps_cur^(0.55/order) * eps_last^(-0.27/order) * eps_last_last^(0.05/order)
+//     = x_cur^(-11/(40 order)) * x_last^(27/(200 order)) * x_ll^(-1/(40 order))
+// written with integer inverse roots (q = 40*order, 5q = 200*order must be integers) so that no libm pow is
+// needed.  The 200*order-th root is refined twice (its third-order constant is ~P^2/3).
+DSB_HD double corr_three_term(double x_cur, double x_last, double x_ll, int q)
+{
+    double r1 = inv_root_rt(x_cur, q);
+    double r3 = inv_root_rt(x_ll, q);
+    const int p2 = 5 * q;
+    double c = inv_root_seed(x_last, 1.0f / (float)p2);
+    const double ip = 1.0 / (double)p2;
+    for (int it = 0; it < 2; ++it) {
+        double e = fma(-x_last, ipow_rt(c, p2), 1.0);
+        c = fma(c, fma(e, 0.5 * (p2 + 1.0) * ip, 1.0) * (e * ip), c);
+    }
+    return (ipow_rt(r1, 11) * fast_div(1.0, ipow_rt(c, 27))) * r3;
 }
 
 // Host-side table builder: entry k = { u_k, 1 + atan(u_k) } with g_k = -0.5 + 1.5 k / 128.

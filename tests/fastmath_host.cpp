@@ -32,7 +32,16 @@ int main()
         double x = pow(10.0, -280 + 560 * U(rng));
         wext = fmax(wext, fabs(inv_root<16>(x) - pow(x, -1.0 / 16)) / pow(x, -1.0 / 16));
     }
-    printf("%.3e %.3e %.3e %.3e %.3e %.3e %.3e\n", w10, w16, wrt, wat, wdiv, wmax, wext);
+    // 3-term controller product against libm pow, orders 5 and 8
+    double w3 = 0;
+    for (int i = 0; i < 300000; i++) {
+        double a = pow(10.0, -6 + 12 * U(rng)), b = pow(10.0, -6 + 12 * U(rng)), c = pow(10.0, -6 + 12 * U(rng));
+        for (int order = 5; order <= 8; order += 3) {
+            double ref = pow(1 / sqrt(a), 0.55 / order) * pow(1 / sqrt(b), -0.27 / order) * pow(1 / sqrt(c), 0.05 / order);
+            w3 = fmax(w3, fabs(corr_three_term(a, b, c, 40 * order) - ref) / ref);
+        }
+    }
+    printf("%.3e %.3e %.3e %.3e %.3e %.3e %.3e %.3e\n", w10, w16, wrt, wat, wdiv, wmax, wext, w3);
     printf("%.17g %.17g\n", one_plus_atan(-1.0, tab), one_plus_atan(1e29, tab));
     return 0;
 }
