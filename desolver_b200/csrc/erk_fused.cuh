@@ -133,11 +133,12 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
         double eps = 1.0 / sqrt(x);
         return eps > 0.0 ? pow(eps, 1.0 / order) : 1.0;
     }
-    if (x > 1e-280 && x < 1e280 && order_p > 0) {
-        if (order_p == 10) return fm::inv_root<10>(x);
-        if (order_p == 16) return fm::inv_root<16>(x);
+    if (x > DSB_KC(xlo, 1e-36) && x < DSB_KC(xhi, 1e36) && order_p > 0) {
+        if (order_p == 10) return fm::inv_root_narrow<10>(x);
+        if (order_p == 16) return fm::inv_root_narrow<16>(x);
         return fm::inv_root_rt(x, order_p);
     }
+    if (x > 1e-280 && x < 1e280 && order_p > 0) return fm::inv_root_rt(x, order_p);
     if (x == 0.0) return CUDART_INF;
     if (!(x < CUDART_INF)) return 1.0;                  // inf or nan: eps = 0 or nan -> 1
     return pow(x, -0.5 / order);
@@ -310,7 +311,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     if constexpr (Tab::template use_b<j>()) sb = fma(k[j][d], tab.template b<j>(), sb);
                     if constexpr (Tab::template use_db<j>()) se = fma(k[j][d], tab.template db<j>(), se);
                 });
-                dY[d] = tab.fsal() ? dlast[d] : h * sb;
+                dY[d] = tab.fsal() ? dlast[d] : sb;                    // non-FSAL: the commit does y = fma(h, sb, y)
                 err[d] = h * se;
                 slope[d] = sb;                                         // = dY/h to rounding
             }
@@ -328,11 +329,11 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fm::abs_max(y[d], slope[d]);
                 if (any_retry) {                                       // EMA on retries (:58-59); warp-uniform branch
                     asm volatile("" ::: "memory");                     // keep it a branch: no speculation of the EMA
-                    if (trial > 0) sc = A::add(A::mul(0.8, scale[d]), A::mul(0.2, sc));
+                    if (trial > 0) sc = A::add(A::mul(DSB_KC(c08, 0.8), scale[d]), A::mul(DSB_KC(c02, 0.2), sc));
                 }
                 sc_cur[d] = sc;
                 double tol = A::mad(rtol, sc, atol);                  // atol + rtol*sc
-                double q = STRICT ? err[d] / tol : fm::fast_div(err[d], tol);
+                double q = STRICT ? err[d] / tol : fm::quick_div(err[d], tol);
                 x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
             }
             if (!STRICT && !live) x = 1.0;     // idle lanes stay on the fast path (no divergent libm calls)
@@ -353,19 +354,20 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     corr = A::mul(A::mul(k1, k2), k3);
                 }
             }
-            double u = A::sub(A::mul(0.8, corr), 1.0);
+            double u = A::sub(A::mul(DSB_KC(c08, 0.8), corr), 1.0);
             double f;
-            if (STRICT || !(u < 1e30)) f = A::add(1.0, atan(u));
+            if (STRICT || !(u < DSB_KC(ubig, 1e30))) f = A::add(1.0, atan(u));
             else f = fm::one_plus_atan(u, s_atan);
             new_dt = A::mul(f, h);
-            redo = f < DSB_REJECT_BELOW;
+            redo = f < DSB_KC(reject_below, DSB_REJECT_BELOW);
         }
 
         // ------------------------------------------------------------ commit / retry
         if (live) {
             if (!redo) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) y[d] = A::add(y[d], dY[d]);
+                for (int d = 0; d < D; ++d)
+                    y[d] = (STRICT || tab.fsal()) ? A::add(y[d], dY[d]) : fma(h, dY[d], y[d]);
                 t = A::add(t, h);
                 acc++; steps++; trial = 0;
                 if (!final_step) dt = new_dt;
@@ -374,7 +376,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     Rhs::eval(y, prm, f1);
                     dense_node(f1);
                 }
-                bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_KC(eps32, DSB_EPS32));
                 bool budget = P.a.max_steps >= 0 && steps >= P.a.max_steps;
                 if (!more || budget) {
                     store(more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE);

@@ -28,6 +28,22 @@ struct double2 { double x, y; };
 namespace dsb {
 namespace fm {
 
+// Double literals of the hot loop live in the user constant bank: a constant-bank operand is free, while a
+// 64-bit immediate that does not fit the 32-bit immediate field costs two UMOVs every time it is used.
+// (A __constant__ object may be rewritten by the host, so the compiler cannot fold it back into immediates.)
+struct HotConstants {
+    double c08, c02, ip10, hp10, ip16, hp16, am7, a5, am3, reject_below, eps32, xlo, xhi, ubig;
+};
+#if defined(__CUDACC__)
+static __constant__ HotConstants kc = {0.8, 0.2, 1.0 / 10, 11.0 / 20, 1.0 / 16, 17.0 / 32, -1.0 / 7.0, 1.0 / 5.0, -1.0 / 3.0,
+                                       0.9 * 0.9, 32.0 * 2.220446049250313e-16, 1e-36, 1e36, 1e30};
+#endif
+#if defined(__CUDA_ARCH__)
+#define DSB_KC(name, literal) (::dsb::fm::kc.name)
+#else
+#define DSB_KC(name, literal) (literal)
+#endif
+
 constexpr int ATAN_TABLE_SIZE = 128;
 constexpr double ATAN_G_LO = -0.5;
 constexpr double ATAN_INV_DG = 128.0 / 1.5;   // table is uniform in g = u / (1 + |u|), g in [-0.5, 1)
@@ -125,6 +141,16 @@ DSB_HD double fast_div(double n, double d)
     return fma(rem, r, q);
 }
 
+// n / d to ~2^-40 relative (seed + one Newton step, no remainder correction).  Used ONLY for the error-norm
+// quotients err/tol: the norm feeds nothing but the step-size factor, where 1e-12 relative is far below the
+// conditioning of dt itself (a last-ulp state change already moves dt by ~1e-9 relative).
+DSB_HD double quick_div(double n, double d)
+{
+    double r = rcp_seed(d);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return n * r;
+}
+
 template <int P>
 DSB_HD double ipow(double c)
 {
@@ -166,7 +192,22 @@ DSB_HD double inv_root(double x)
 {
     double c = inv_root_seed(x, 1.0f / (float)P);
     double e = fma(-x, ipow<P>(c), 1.0);
-    double g = fma(e, (P + 1.0) / (2.0 * P), 1.0) * (e * (1.0 / P));
+    const double ip = P == 10 ? DSB_KC(ip10, 0.1) : (P == 16 ? DSB_KC(ip16, 1.0 / 16) : 1.0 / P);
+    const double hp = P == 10 ? DSB_KC(hp10, 11.0 / 20) : (P == 16 ? DSB_KC(hp16, 17.0 / 32) : (P + 1.0) / (2.0 * P));
+    double g = fma(e, hp, 1.0) * (e * ip);
+    return fma(c, g, c);
+}
+
+// Same, for x in [1e-36, 1e36] (|err/tol| in [1e-18, 1e18]): the seed is taken from (float)x directly
+// (one F2F instead of the exponent/mantissa split).
+template <int P>
+DSB_HD double inv_root_narrow(double x)
+{
+    double c = (double)ex2_seed(lg2_seed((float)x) * (-1.0f / (float)P));
+    double e = fma(-x, ipow<P>(c), 1.0);
+    const double ip = P == 10 ? DSB_KC(ip10, 0.1) : (P == 16 ? DSB_KC(ip16, 1.0 / 16) : 1.0 / P);
+    const double hp = P == 10 ? DSB_KC(hp10, 11.0 / 20) : (P == 16 ? DSB_KC(hp16, 17.0 / 32) : (P + 1.0) / (2.0 * P));
+    double g = fma(e, hp, 1.0) * (e * ip);
     return fma(c, g, c);
 }
 
@@ -220,7 +261,7 @@ DSB_HD double one_plus_atan(double u, const double2 *tab)
     double2 e = tab[k];
     double r = fast_div(u - e.x, fma(u, e.x, 1.0));
     double r2 = r * r;
-    double p = fma(r2, fma(r2, -1.0 / 7.0, 1.0 / 5.0), -1.0 / 3.0);   // |r| < 0.012: r^9/9 < 6e-19
+    double p = fma(r2, fma(r2, DSB_KC(am7, -1.0 / 7.0), DSB_KC(a5, 1.0 / 5.0)), DSB_KC(am3, -1.0 / 3.0));   // |r| < 0.012: r^9/9 < 6e-19
     return e.y + fma(r * r2, p, r);
 }
 

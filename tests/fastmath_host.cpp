@@ -16,6 +16,7 @@ int main()
         double r10 = pow(x, -0.1), r16 = pow(x, -1.0 / 16);
         w10 = fmax(w10, fabs(inv_root<10>(x) - r10) / r10);
         w16 = fmax(w16, fabs(inv_root<16>(x) - r16) / r16);
+        w10 = fmax(w10, fabs(inv_root_narrow<10>(x) - r10) / r10);
         wrt = fmax(wrt, fabs(inv_root_rt(x, 10) - r10) / r10);
         double u = (i % 3 == 0) ? -1 + 4 * U(rng) : ((i % 3 == 1) ? -1 + pow(10.0, -8 + 36 * U(rng)) : 0.8 * pow(10.0, -1 + 2 * U(rng)) - 1);
         if (u < -1) u = -1;
