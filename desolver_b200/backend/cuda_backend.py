@@ -133,6 +133,9 @@ def lib():
     L.dsb_dense_eval.restype = C.c_int
     L.dsb_dense_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p]
+    L.dsb_dense_append.restype = C.c_int
+    L.dsb_dense_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     for name in ("dsb_erk_stage_begin", "dsb_erk_stage_state"):
         getattr(L, name).restype = C.c_int
         getattr(L, name).argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_int, C.c_void_p]

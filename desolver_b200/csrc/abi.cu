@@ -21,6 +21,8 @@ void set_error(const char *fmt, ...)
 
 int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim, int32_t cap,
                       const double *tq, int64_t tq_stride, double *out, cudaStream_t stream);
+int launch_dense_append(double *nodes, int32_t *node_count, int32_t cap, int64_t n, int32_t dim, const double *t,
+                        const double *y, const double *f, const int32_t *flags, int32_t mask, cudaStream_t stream);
 int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
 int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream);
 int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream);
@@ -139,6 +141,16 @@ int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *st
 }
 
 int dsb_erk_stage_launches(dsb_erk_handle h) { return h ? 1 + h->stages + 3 : 0; }
+
+int dsb_dense_append(double *nodes, int32_t *node_count, int32_t node_capacity, int64_t n, int32_t dim, const double *t,
+                     const double *y, const double *f, const int32_t *flags, int32_t mask, void *stream)
+{
+    if (!nodes || !node_count || !t || !y || !f || dim < 1 || node_capacity < 2 || n < 0) {
+        set_error("dsb_dense_append: bad argument");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    return launch_dense_append(nodes, node_count, node_capacity, n, dim, t, y, f, flags, mask, (cudaStream_t)stream);
+}
 
 int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
                    int32_t node_capacity, const double *tq, int64_t tq_stride, double *out, void *stream)

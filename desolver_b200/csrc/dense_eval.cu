@@ -53,6 +53,37 @@ __global__ void dense_eval_kernel(const double *__restrict__ nodes, const int32_
     }
 }
 
+// Appends one node (t, y, f) to the store of every trajectory whose flag word has `mask` set (all trajectories
+// when flags == nullptr): the dense-output writer of the stage-level path (the fused kernel writes its nodes
+// itself).  One thread per trajectory; reads are coalesced over the ensemble axis.
+__global__ void dense_append_kernel(double *__restrict__ nodes, int32_t *__restrict__ node_count, int cap, long long n,
+                                    int dim, const double *__restrict__ t, const double *__restrict__ y,
+                                    const double *__restrict__ f, const int32_t *__restrict__ flags, int mask)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags && !(flags[i] & mask)) return;
+    const int c = node_count[i];
+    if (c < cap) {
+        double *rec = nodes + (i * (long long)cap + c) * (1 + 2 * dim);
+        rec[0] = t[i];
+        for (int d = 0; d < dim; ++d) {
+            rec[1 + d] = y[(long long)d * n + i];
+            rec[1 + dim + d] = f[(long long)d * n + i];
+        }
+    }
+    node_count[i] = c + 1;
+}
+
+int launch_dense_append(double *nodes, int32_t *node_count, int32_t cap, int64_t n, int32_t dim, const double *t,
+                        const double *y, const double *f, const int32_t *flags, int32_t mask, cudaStream_t stream)
+{
+    if (n <= 0) return DSB_OK;
+    dense_append_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(nodes, node_count, cap, n, dim, t, y, f, flags, mask);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
 int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim, int32_t cap,
                       const double *tq, int64_t tq_stride, double *out, cudaStream_t stream)
 {

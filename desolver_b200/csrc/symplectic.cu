@@ -38,17 +38,17 @@ template <bool STRICT>
 __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
 {
     using A = Ar<STRICT>;
-    extern __shared__ double smem[];
+    extern __shared__ double4 smem4[];
     const int nb = a.bodies;
     const int spb = blockDim.y;
-    double *sq = smem + (size_t)threadIdx.y * nb * 3;       // this system's stage positions
-    double *sm = smem + (size_t)spb * nb * 3;                // masses (shared by all systems)
+    // stage positions and masses of this CTA's systems as (x, y, z, m): two LDS.128 per partner body
+    double4 *sq = smem4 + (size_t)threadIdx.y * nb;
     const long long sys = (long long)blockIdx.x * spb + threadIdx.y;
     const int i = threadIdx.x;
     const bool valid = sys < a.n;
-    for (int j = threadIdx.y * nb + i; j < nb; j += nb * spb) sm[j] = a.masses[j];
     const long long n = a.n;
     const long long s_ = valid ? sys : 0;
+    const double my_mass = a.masses[i];
 
     double q0[3], v0[3];
 #pragma unroll
@@ -68,7 +68,6 @@ __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
             if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
         }
     }
-    __syncthreads();
 
     // the loop condition is uniform within a system (same t, dt in all its threads); systems of one CTA may
     // stop at different steps, so every thread keeps hitting the barriers until the whole CTA is done
@@ -84,23 +83,26 @@ __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
 #pragma unroll
             for (int k = 0; k < 3; ++k) vcur[k] = A::add(v0[k], dv[k]);
             if (c2 != 0.0) {                                                // kick stage: forces at q + dS_q
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sq[i * 3 + k] = A::add(q0[k], dq[k]);
+                const double qx = A::add(q0[0], dq[0]), qy = A::add(q0[1], dq[1]), qz = A::add(q0[2], dq[2]);
+                sq[i] = make_double4(qx, qy, qz, my_mass);
                 __syncthreads();
-                const double qx = sq[i * 3], qy = sq[i * 3 + 1], qz = sq[i * 3 + 2];
                 double ax = 0.0, ay = 0.0, az = 0.0;
+                // The partner loop includes j == i: there d = 0 and the term is 0 * (m r2^-1.5) = +0 for any
+                // softening eps2 > 0 -- exactly what the reference's w * (1 - eye) yields (for eps2 = 0 both give NaN).
+#pragma unroll 4
                 for (int j = 0; j < nb; ++j) {
-                    const double dx = A::sub(sq[j * 3], qx), dy = A::sub(sq[j * 3 + 1], qy), dz = A::sub(sq[j * 3 + 2], qz);
+                    const double4 pj = sq[j];
+                    const double dx = A::sub(pj.x, qx), dy = A::sub(pj.y, qy), dz = A::sub(pj.z, qz);
                     double w;
                     if (STRICT) {
                         double r2 = A::add(A::add(A::add(A::mul(dx, dx), A::mul(dy, dy)), A::mul(dz, dz)), a.eps2);
-                        w = A::mul(sm[j], pow(r2, -1.5));
+                        w = A::mul(pj.w, pow(r2, -1.5));
+                        if (j == i) w = A::mul(w, 0.0);
                     } else {
                         double r2 = fma(dz, dz, fma(dy, dy, dx * dx)) + a.eps2;
                         double rinv = rsqrt(r2);
-                        w = sm[j] * (rinv * rinv * rinv);
+                        w = pj.w * (rinv * rinv * rinv);
                     }
-                    w = (j == i) ? 0.0 : w;
                     ax = A::mad(dx, w, ax);
                     ay = A::mad(dy, w, ay);
                     az = A::mad(dz, w, az);
@@ -270,7 +272,7 @@ int dsb_symp_run(dsb_symp_handle h, const dsb_symp_run_args *a, void *stream)
     if (spb < 1) spb = 1;
     dim3 block((unsigned)a->bodies, (unsigned)spb);
     unsigned grid = (unsigned)((a->n + spb - 1) / spb);
-    size_t smem = sizeof(double) * ((size_t)spb * a->bodies * 3 + a->bodies);
+    size_t smem = sizeof(double4) * (size_t)spb * a->bodies;
     if (h->flags & DSB_FLAG_STRICT) nbody_symplectic_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(*a, h->tab);
     else nbody_symplectic_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(*a, h->tab);
     DSB_CUDA_CHECK(cudaGetLastError());

@@ -458,8 +458,6 @@ class OdeSystem(object):
         integ = self.integrator
         if not isinstance(integ, integrators.RungeKuttaIntegrator):
             raise NotImplementedError("stage-level path supports explicit Runge-Kutta methods")
-        if self.__dense_output:
-            raise NotImplementedError("dense_output needs a fused device right-hand side in this version")
         n, D, S, dev = self.n_traj, self.numel, integ.stages, self.device
         handle = cb.erk_handle(dev.index or 0, 100, D, integ.tableau_intermediate, integ.tableau_final, integ.order,
                                strict=self.strict)
@@ -481,6 +479,22 @@ class OdeSystem(object):
         y_view = self._user_shape(buf["y_stage"])
         t_view = self._user_time(buf["t_stage"])
         K = [None] * S
+        self._ensure_dense_store()
+        dense = self._nodes is not None
+        y_committed = self._user_shape(self._y)
+        t_committed = self._user_time(self._t)
+
+        def record_nodes(flags_ptr):
+            """node (t, y, f = rhs(t, y)) for the trajectories flagged as just accepted (all if flags_ptr is None)"""
+            f = self.equ_rhs(t_committed, y_committed, **self.__consts).to(torch.float64).reshape(D, n)
+            f = f if f.is_contiguous() else f.contiguous()
+            cb.check(cb.lib().dsb_dense_append(self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity,
+                                               n, D, self._t.data_ptr(), self._y.data_ptr(), f.data_ptr(), flags_ptr, 4,
+                                               stream), "dsb_dense_append")
+            self._launches += 1
+
+        if dense and int(self._node_count.max().item()) == 0:
+            record_nodes(None)                                   # node 0 = initial condition
         first, attempts = True, 0
         # heavy attempts (large state x ensemble): one host look per attempt costs nothing next to the
         # attempt itself and saves up to sync_every-1 wasted lock-step rounds at the end
@@ -497,6 +511,8 @@ class OdeSystem(object):
             handle.stage_finish(a, stream)
             self._launches += handle.stage_launches
             attempts += 1
+            if dense:
+                record_nodes(buf["flags"].data_ptr())
             for cbk in callbacks:
                 cbk(self)
             if bar is not None:

@@ -203,6 +203,14 @@ DSB_API int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *
  * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
  * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written
  * by dsb_erk_run: out[d][i] = Hermite interpolant of trajectory i at tq[i*tq_stride]. */
+/* Writer for the stage-level path: append the node (t[i], y[:, i], f[:, i]) for every trajectory i whose
+ * flags[i] has `mask` set (flags == NULL: all).  With the flag word of dsb_erk_stage_args and mask = 4 this
+ * records exactly the steps the last dsb_erk_stage_finish accepted; f is rhs(t, y) evaluated by the caller
+ * (the reference's final_rhs, integrators/integrator_types.py:308, dense_output :109-119). */
+DSB_API int dsb_dense_append(double *nodes, int32_t *node_count, int32_t node_capacity, int64_t n, int32_t dim,
+                             const double *t, const double *y, const double *f, const int32_t *flags, int32_t mask,
+                             void *stream);
+
 DSB_API int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
                    int32_t node_capacity, const double *tq, int64_t tq_stride,
                    double *out, void *stream);

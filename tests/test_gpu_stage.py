@@ -129,3 +129,31 @@ def test_stage_path_callbacks_and_failure():
     with pytest.raises(de.exception_types.FailedIntegration):
         b.integrate()
     assert int(b.status[2]) == 1 and int(b.rejected[2]) == 65 and int((b.status != 0).sum()) == 1
+
+
+def test_stage_path_dense_output():
+    """Dense output written by the stage-level path (dsb_dense_append) == the fused kernel's node store."""
+    de = _de()
+    g = load_golden("lorenz_dense.npz")
+
+    def run(use_fused):
+        a = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(g["y0"]), t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9,
+                         ensemble=True, dense_output=True, dense_capacity=512, strict=True)
+        a.use_fused = use_fused
+        a.integrate()
+        return a
+    a, b = run(False), run(True)
+    assert torch.equal(a.sol.node_count, b.sol.node_count)
+    assert np.array_equal((a.sol.node_count - 1).cpu().numpy(), g["n_interp"])
+    for q, tq in enumerate(g["tq"]):
+        got = a.sol(float(tq)).cpu().numpy()
+        assert np.max(rel_inf(got, g["dense"][q])) < 1e-10
+        assert np.max(rel_inf(got, b.sol(float(tq)).cpu().numpy())) < 1e-11
+    # time-dependent untagged RHS with dense output, against the analytic solution between the nodes
+    f = load_golden("forced_rk45.npz")
+    c = de.OdeSystem(de.rhs_plugins.forced_oscillator, torch.as_tensor(f["y0"]), t=(0.0, 5.0), dt=1e-2, rtol=1e-10, atol=1e-10,
+                     ensemble=True, dense_output=True, dense_capacity=2048)
+    c.integrate()
+    for tq in (0.37, 2.5, 4.99):
+        exact = tq + f["y0"][0] * np.cos(tq) + (f["y0"][1] - 1.0) * np.sin(tq)
+        assert np.max(np.abs(c.sol(tq)[0].cpu().numpy() - exact)) < 1e-7
