@@ -144,14 +144,15 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
     return pow(x, -0.5 / order);
 }
 
-// resident blocks per SM: 4 (<=128 registers) while the stage derivatives fit, else 2 (<=255)
+// resident blocks per SM: 6 (<=80 registers; measured best for Cash-Karp x dim<=3), 4 (<=128) while the stage
+// derivatives fit, else 2 (<=255)
 template <class Rhs, int S>
 constexpr int erk_min_blocks()
 {
 #ifdef DSB_ERK_MIN_BLOCKS
     return DSB_ERK_MIN_BLOCKS;
 #else
-    return (S * Rhs::DIM <= 18) ? 5 : ((S * Rhs::DIM <= 21) ? 4 : 2);
+    return (S * Rhs::DIM <= 18) ? 6 : ((S * Rhs::DIM <= 21) ? 4 : 2);
 #endif
 }
 
@@ -180,7 +181,6 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     double t = 0.0, dt = 0.0, h = 0.0, h0 = 0.0;
     double corr_first = 1.0, x_last = 1.0, x_last_last = 1.0;
     int trial = 0, acc = 0, rej = 0;
-    long long steps = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) { y[d] = 0.0; scale[d] = 0.0; }
 #pragma unroll
@@ -208,10 +208,44 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         P.a.node_count[idx] = c + 1;
     };
 
-    for (;;) {
-        // ------------------------------------------------------------ refill from the queue
-        unsigned need = __ballot_sync(FULL, !live);
-        if (need && !exhausted) {
+    // Start of a step: final-step clamp (differential_system.py:997-1002).  Called when a trajectory is loaded
+    // and after every accepted step, so the loop top has no per-attempt bookkeeping.
+    auto start_step = [&]() {
+        final_step = fabs(dt + t) > fabs(tf);
+        h = final_step ? (tf - t) : dt;
+    };
+
+    // Rare path, entered by the whole warp when ANY lane rejected, finished, failed or is idle:
+    // retry bookkeeping, result stores, refill from the global queue.  Returns false when the warp is out of work.
+    bool redo = false, done = false;
+    double new_dt = 0.0, x = 0.0, corr = 1.0, sc_cur[D];
+    auto event_path = [&]() -> bool {
+        if (live && redo) {
+            // integrator_types.py:201-224: retry with min(new, h0); history for the 2- and 3-term controller
+            rej++;
+            if (trial == 0) { h0 = h; corr_first = corr; }
+            trial++;
+            x_last_last = x_last;
+            x_last = x;
+#pragma unroll
+            for (int d = 0; d < D; ++d) scale[d] = sc_cur[d];
+            if (trial > DSB_MAX_RETRIES) {
+                store((int)DSB_TRAJ_TOL_FAIL);                       // state frozen at the step start
+                live = false;
+                trial = 0;
+            } else {
+                h = h0 >= 0.0 ? fmin(new_dt, h0) : -fmin(fabs(new_dt), fabs(h0));
+            }
+        } else if (live && done) {
+            bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+            store(more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE);
+            live = false;
+        }
+        // refill idle lanes from the queue (warp-aggregated atomicAdd); a loaded trajectory that has nothing to
+        // do (already at tf, failed earlier) is stored at once and the lane asks again
+        for (;;) {
+            unsigned need = __ballot_sync(FULL, !live);
+            if (!need || exhausted) break;
             int cnt = __popc(need);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd((unsigned long long *)P.a.counters, (unsigned long long)cnt);
@@ -227,7 +261,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 #pragma unroll
                 for (int p = 0; p < NP; ++p) prm[p] = P.a.params[p][idx * P.a.param_stride[p]];
                 Rhs::prepare(prm);
-                acc = 0; rej = 0; trial = 0; steps = 0;
+                acc = 0; rej = 0; trial = 0;
                 int st0 = P.a.status ? P.a.status[idx] : (int)DSB_TRAJ_DONE;
                 bool go = st0 != (int)DSB_TRAJ_TOL_FAIL;
                 if (go && P.a.first_call) {
@@ -239,31 +273,28 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                         if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
                     }
                 }
-                go = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                go = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);         // :996
+                if (go && P.a.max_steps == 0) go = false;
                 if (go) {
                     live = true;
+                    start_step();
                     if (P.a.nodes && P.a.node_count[idx] == 0) {
                         double f0[D];
                         Rhs::eval(y, prm, f0);
                         dense_node(f0);
                     }
                 } else {
-                    store(st0 == (int)DSB_TRAJ_TOL_FAIL ? st0 : (int)DSB_TRAJ_DONE);
+                    bool more = st0 != (int)DSB_TRAJ_TOL_FAIL && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                    store(st0 == (int)DSB_TRAJ_TOL_FAIL ? st0 : (more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE));
                 }
             }
         }
-        if (!__any_sync(FULL, live)) {
-            if (exhausted) break;
-            continue;
-        }
+        return __any_sync(FULL, live);
+    };
 
-        // ------------------------------------------------------------ start of a step
-        if (trial == 0) {
-            final_step = fabs(dt + t) > fabs(tf);                 // differential_system.py:997
-            h = final_step ? (tf - t) : dt;
-            h0 = h;
-        }
+    if (!event_path()) return;
 
+    for (;;) {
         // ------------------------------------------------------------ stages
         double dlast[D];
         static_for<0, S>([&](auto s_) {
@@ -318,10 +349,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         }
 
         // ------------------------------------------------------------ controller
-        bool redo = false;
-        double new_dt = h;
-        double x = 0.0;                                                // ||diff / tol||_2^2
-        double corr = 1.0, sc_cur[D];
+        redo = false;
+        new_dt = h;
         if (tab.adaptive()) {
             const bool any_retry = __any_sync(FULL, trial > 0);       // warp-uniform: rare paths are skipped
 #pragma unroll
@@ -362,43 +391,28 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             redo = f < DSB_KC(reject_below, DSB_REJECT_BELOW);
         }
 
-        // ------------------------------------------------------------ commit / retry
-        if (live) {
-            if (!redo) {
+        // ------------------------------------------------------------ accept: commit and start the next step
+        done = false;
+        if (live && !redo) {
 #pragma unroll
-                for (int d = 0; d < D; ++d)
-                    y[d] = (STRICT || tab.fsal()) ? A::add(y[d], dY[d]) : fma(h, dY[d], y[d]);
-                t = A::add(t, h);
-                acc++; steps++; trial = 0;
-                if (!final_step) dt = new_dt;
-                if (P.a.nodes) {
-                    double f1[D];
-                    Rhs::eval(y, prm, f1);
-                    dense_node(f1);
-                }
-                bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_KC(eps32, DSB_EPS32));
-                bool budget = P.a.max_steps >= 0 && steps >= P.a.max_steps;
-                if (!more || budget) {
-                    store(more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE);
-                    live = false;
-                }
-            } else {
-                rej++; trial++;
-                // retry-chain history (integrator_template.py:58-61,75,79,90), only needed when retrying
-                if (trial == 1) corr_first = corr;
-                x_last_last = x_last;
-                x_last = x;
-#pragma unroll
-                for (int d = 0; d < D; ++d) scale[d] = sc_cur[d];
-                if (trial > DSB_MAX_RETRIES) {
-                    store((int)DSB_TRAJ_TOL_FAIL);                   // state frozen at the step start
-                    live = false;
-                    trial = 0;
-                } else {
-                    // integrator_types.py:206 min(new, h0); sign-aware so tf < t0 also works
-                    h = h0 >= 0.0 ? fmin(new_dt, h0) : -fmin(fabs(new_dt), fabs(h0));
-                }
+            for (int d = 0; d < D; ++d)
+                y[d] = (STRICT || tab.fsal()) ? A::add(y[d], dY[d]) : fma(h, dY[d], y[d]);   // :1015
+            t = A::add(t, h);                                                                 // :1016
+            acc++;
+            trial = 0;
+            if (!final_step) dt = new_dt;                                                     // :1070-1071
+            if (P.a.nodes) {
+                double f1[D];
+                Rhs::eval(y, prm, f1);
+                dense_node(f1);
             }
+            start_step();
+            done = !((dt != 0.0) && (fabs(tf - t) >= DSB_KC(eps32, DSB_EPS32)))               // :996
+                   || (P.a.max_steps >= 0 && acc >= P.a.max_steps);
+        }
+        // ------------------------------------------------------------ rare events: reject, finish, refill
+        if (__any_sync(FULL, live ? (redo || done) : !exhausted)) {
+            if (!event_path()) break;
         }
     }
 }
