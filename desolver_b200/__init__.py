@@ -15,9 +15,9 @@ from . import integrators
 from . import rhs_plugins
 from . import benchmarks
 from . import distributed
-from .differential_system import DiffRHS, OdeSystem, DenseOutput, StateTuple, rhs_prettifier
+from .differential_system import DiffRHS, OdeSystem, DenseOutput, StateTuple, rhs_prettifier, solve_ivp
 from .integrators import available_methods
 
 __version__ = "0.1.0"
 __all__ = ["backend", "exception_types", "integrators", "rhs_plugins", "benchmarks", "distributed", "DiffRHS", "OdeSystem",
-           "DenseOutput", "StateTuple", "rhs_prettifier", "available_methods"]
+           "DenseOutput", "StateTuple", "rhs_prettifier", "solve_ivp", "available_methods"]

@@ -54,6 +54,7 @@ class ErkStageArgs(C.Structure):
         ("tf", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
         ("accepted", C.c_void_p), ("rejected", C.c_void_p), ("status", C.c_void_p),
         ("counters", C.c_void_p),
+        ("one_step", C.c_int32),
     ]
 
 

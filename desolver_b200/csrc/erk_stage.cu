@@ -219,6 +219,7 @@ __global__ void stage_controller_kernel(dsb_erk_stage_args a, FinalRows fr, int 
                 fl |= FLAG_ACCEPTED;
                 bool more = (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
                 if (!more) { fl &= ~FLAG_ACTIVE; if (a.status) a.status[i] = (int)DSB_TRAJ_DONE; }
+                else if (a.one_step) { fl &= ~FLAG_ACTIVE; if (a.status) a.status[i] = (int)DSB_TRAJ_RUNNING; }
             } else {
                 if (a.rejected) a.rejected[i] += 1;
                 trial += 1;

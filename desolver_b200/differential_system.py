@@ -28,7 +28,7 @@ from . import exception_types as etypes
 from . import integrators
 from .backend import cuda_backend as cb
 
-__all__ = ["DiffRHS", "rhs_prettifier", "OdeSystem", "DenseOutput", "StateTuple"]
+__all__ = ["DiffRHS", "rhs_prettifier", "OdeSystem", "DenseOutput", "StateTuple", "solve_ivp"]
 
 StateTuple = collections.namedtuple("StateTuple", ["t", "y", "event"])
 
@@ -702,3 +702,55 @@ class OdeSystem(object):
         return "\n".join(["{:>10}: {}".format(k, v) for k, v in (
             ("message", self.integration_status), ("nfev", self.nfev), ("njev", self.njev), ("t0", self.__t0),
             ("tf", self.__tf), ("trajectories", self.n_traj), ("method", self.__method.__name__))])
+
+
+def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, events=None, vectorized=False, args=None,
+              **options):
+    """Functional wrapper with the signature of the reference's `solve_ivp`
+    (`differential_system.py:1202-1255`, itself modelled on scipy's).  `t_eval` is served by repeated
+    `integrate(t)` calls exactly like the reference (`:1245-1248`).  Extra options: `ensemble`, `device`, `strict`.
+    Returns a `scipy.optimize.OptimizeResult`-style object with `t`, `y`, `sol`, `nfev`, `status`, `success`,
+    `ode_system`; for an ensemble `y` has shape (*dim, N, n_times) and `t` (n_times,) or (N, n_times)."""
+    import inspect
+    torch = _torch()
+    from scipy.optimize import OptimizeResult
+    if events is not None:
+        raise NotImplementedError("event detection is not supported by the ensemble engine")
+    constants = None
+    if args is not None:
+        fn = fun
+        while isinstance(fn, DiffRHS):
+            fn = fn.rhs
+        names = inspect.getfullargspec(fn)[0][2:]
+        constants = {k: v for k, v in zip(names, args)}
+    max_step = options.get("max_step", np.inf)
+    min_step = options.get("min_step", 0.0)
+    first = min(max(options.get("first_step", 1.0), min_step), max_step)
+    system = OdeSystem(fun, y0, t=t_span, dense_output=dense_output, dt=first, atol=options.get("atol"),
+                       rtol=options.get("rtol"), constants=constants or {}, ensemble=options.get("ensemble", False),
+                       device=options.get("device"), strict=options.get("strict", False))
+    system.method = method
+    callbacks = list(options.get("callbacks", []))
+    if "max_step" in options or "min_step" in options:
+        def clip_step(ode_sys):                       # reference :1229-1232
+            ode_sys.dt = torch.clamp(ode_sys._dt, min=min_step, max=max_step)
+        callbacks.append(clip_step)
+    kw = dict(callback=callbacks or None, eta=options.get("show_prog_bar", False))
+    if t_eval is None:
+        system.integrate(**kw)
+        t_res = system.t
+        y_res = torch.movedim(system.y, 0, -1)
+    else:
+        t_eval = np.sort(np.asarray(t_eval, dtype=np.float64))
+        if t_eval[0] < min(t_span) or t_eval[-1] > max(t_span):
+            raise ValueError(f"Expected `t_eval` to be in the range [{t_span[0]}, {t_span[1]}]")
+        ts, ys = [], []
+        for tq in t_eval:
+            system.integrate(t=float(tq), **kw)
+            ts.append(system[-1].t)
+            ys.append(system[-1].y)
+        t_res = torch.stack(ts, dim=-1)
+        y_res = torch.stack(ys, dim=-1)
+    return OptimizeResult(t=t_res, y=y_res, sol=system.sol, t_events=None, y_events=None, nfev=system.nfev,
+                          njev=system.njev, status=system.integration_status, message=system.integration_status,
+                          success=system.success, ode_system=system)

@@ -94,6 +94,75 @@ class RungeKuttaIntegrator(TableauIntegrator, abc.ABC):
                                 redo_count=0, num_step_retries=64)
 
 
+    def __call__(self, rhs, initial_time, initial_state, constants, timestep):
+        """The reference's integrator protocol (`integrators/integrator_template.py:38-40`, called from
+        `differential_system.py:1003-1004`): ONE accepted step, with the retry chain of
+        `integrator_types.py:162-228`, for every trajectory of `initial_state` (*dim[, N]).
+
+        Returns `(new_timestep, (dTime, dState))`; times and step sizes are 0-d tensors for a single system and
+        (N,) tensors for an ensemble (`initial_state.ndim == len(dim) + 1`).  Runs on the stage-level kernels of
+        libdesolver_b200.so with the callable `rhs` evaluated between them; raises `FailedToMeetTolerances` if
+        any trajectory exhausts its 64 retries."""
+        import torch
+        from .. import exception_types as etypes
+        from ..backend import cuda_backend as cb
+        y0 = torch.as_tensor(initial_state, dtype=torch.float64)
+        if not y0.is_cuda:
+            y0 = y0.to(self.device if self.device is not None else "cuda")
+        dev = y0.device
+        ensemble = y0.ndim == len(self.dim) + 1
+        n = int(y0.shape[-1]) if ensemble else 1
+        D = self.numel
+        y = y0.reshape(D, n).contiguous().clone()
+        f64 = dict(dtype=torch.float64, device=dev)
+        t = torch.as_tensor(initial_time, **f64).expand(n).contiguous().clone()
+        dt = torch.as_tensor(timestep, **f64).expand(n).contiguous().clone()
+        handle = cb.erk_handle(dev.index or 0, 100, D, self.tableau_intermediate, self.tableau_final, self.order)
+        S = self.stages
+        chunks = max(1, min(4096, (D + 127) // 128))
+        i32 = dict(dtype=torch.int32, device=dev)
+        buf = dict(h=torch.zeros(n, **f64), h0=torch.zeros(n, **f64), y_stage=torch.empty((D, n), **f64),
+                   t_stage=torch.zeros(n, **f64), dY=torch.zeros((D, n), **f64), scale=torch.zeros((D, n), **f64),
+                   hist=torch.ones((3, n), **f64), partial=torch.zeros((chunks, n), **f64),
+                   trial=torch.zeros(n, **i32), flags=torch.zeros(n, **i32))
+        status = torch.zeros(n, **i32)
+        counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        a = cb.ErkStageArgs()
+        a.n, a.dim, a.chunks = n, D, chunks
+        a.y, a.t, a.dt = y.data_ptr(), t.data_ptr(), dt.data_ptr()
+        for k, v in buf.items():
+            setattr(a, k, v.data_ptr())
+        # tf = +/-inf in the direction of the step: the final-step clamp belongs to the caller's loop (:997-1002)
+        direction = float(torch.sign(dt[0]).item()) or 1.0
+        a.tf, a.rtol, a.atol = direction * float("inf"), float(self.rtol), float(self.atol)
+        a.status, a.counters, a.one_step = status.data_ptr(), counters.data_ptr(), 1
+        stream = cb.current_stream_ptr(dev)
+        shape = tuple(self.dim) + ((n,) if ensemble else ())
+        y_view = buf["y_stage"].reshape(shape)
+        t_view = buf["t_stage"] if ensemble else buf["t_stage"].reshape(())
+        keep = [None] * S
+        first = True
+        for _ in range(66):
+            handle.stage_begin(a, first, stream)
+            first = False
+            for s in range(S):
+                handle.stage_state(a, s, stream)
+                k = rhs(t_view, y_view, **constants).to(torch.float64).reshape(D, n)
+                keep[s] = k if k.is_contiguous() else k.contiguous()
+                a.K[s] = keep[s].data_ptr()
+            handle.stage_finish(a, stream)
+            if int(counters[1].item()) == 0:
+                break
+        if bool((status == cb.TRAJ_TOL_FAIL).any().item()):
+            raise etypes.FailedToMeetTolerances(
+                "Failed to integrate system to the tolerances required: rtol={}, atol={}".format(self.rtol, self.atol))
+        t0 = torch.as_tensor(initial_time, **f64).expand(n)
+        self.dState = (y - y0.reshape(D, n)).reshape(shape)
+        self.dTime = (t - t0) if ensemble else (t - t0).reshape(())
+        new_dt = dt if ensemble else dt.reshape(())
+        return new_dt, (self.dTime, self.dState)
+
+
 class ExplicitSymplecticIntegrator(TableauIntegrator):
     symplectic = True
 

@@ -143,6 +143,9 @@ typedef struct {
     double tf, rtol, atol;
     int32_t *accepted, *rejected, *status;
     uint64_t *counters;        /* >= 4 words; [1] = active trajectories after finish           */
+    int32_t one_step;          /* != 0: a trajectory goes inactive as soon as it accepts a step -- the
+                                  integrator protocol `integrator(rhs, t, y, constants, timestep)`
+                                  (integrators/integrator_template.py:38-40, differential_system.py:1003-1004) */
 } dsb_erk_stage_args;
 
 DSB_API int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);

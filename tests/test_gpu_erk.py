@@ -232,3 +232,23 @@ def test_bad_arguments():
     a = de.OdeSystem(de.rhs_plugins.lorenz, np.ones(3))
     with pytest.raises(ValueError):
         a.method = "no such method"
+
+
+def test_solve_ivp_wrapper():
+    """Functional interface (reference differential_system.py:1202-1255): args -> constants, t_eval by repeated
+    integrate(t), and scipy parity at the reference's own bar of 1e-6 (test_differential_system.py:791-868)."""
+    from scipy.integrate import solve_ivp as scipy_solve_ivp
+    de = _de()
+    y0 = np.array([1.0, 1.0, 20.0])
+    t_eval = np.linspace(0.1, 1.5, 8)
+    res = de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.5), y0, method="RK45", t_eval=t_eval, args=(10.0, 28.0, 8.0 / 3.0),
+                       rtol=1e-10, atol=1e-10, first_step=1e-2)
+    assert res.success and tuple(res.y.shape) == (3, 8) and np.allclose(res.t.cpu().numpy(), t_eval, rtol=0, atol=1e-14)
+    ref = scipy_solve_ivp(lambda t, y: [10.0 * (y[1] - y[0]), y[0] * (28.0 - y[2]) - y[1], y[0] * y[1] - 8.0 / 3.0 * y[2]],
+                          (0.0, 1.5), y0, method="DOP853", t_eval=t_eval, rtol=1e-12, atol=1e-12)
+    assert np.max(np.abs(res.y.cpu().numpy() - ref.y)) < 1e-6
+    ens = de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 0.5), de.benchmarks.lorenz_ensemble(64), t_eval=[0.25, 0.5], ensemble=True,
+                       rtol=1e-9, atol=1e-9, first_step=1e-2)
+    assert tuple(ens.y.shape) == (3, 64, 2) and tuple(ens.t.shape) == (64, 2)
+    with pytest.raises(ValueError):
+        de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.0), y0, t_eval=[2.0])

@@ -157,3 +157,36 @@ def test_stage_path_dense_output():
     for tq in (0.37, 2.5, 4.99):
         exact = tq + f["y0"][0] * np.cos(tq) + (f["y0"][1] - 1.0) * np.sin(tq)
         assert np.max(np.abs(c.sol(tq)[0].cpu().numpy() - exact)) < 1e-7
+
+
+def test_integrator_protocol_drives_the_reference_loop():
+    """Seam 1 of the reference (integrator protocol): the while loop of OdeSystem.integrate
+    (differential_system.py:996-1071) written out in the test, around `integrator(rhs, t, y, constants, timestep)`."""
+    de = _de()
+    g = load_golden("lorenz_rk45.npz")
+    n = 32
+    y = torch.as_tensor(g["y0"][:, :n].copy()).cuda()
+    integ = de.integrators.RK45CKSolver((3,), torch.float64, rtol=1e-9, atol=1e-9, device=y.device)
+    rhs = de.rhs_plugins.lorenz
+    t = torch.zeros(n, dtype=torch.float64, device=y.device)
+    dt = torch.full((n,), 1e-2, dtype=torch.float64, device=y.device)
+    tf = 2.0
+    steps = torch.zeros(n, dtype=torch.int64, device=y.device)
+    for _ in range(400):
+        active = (dt != 0) & ((tf - t).abs() >= 32 * 2.220446049250313e-16)
+        if not bool(active.any()):
+            break
+        final = (dt + t).abs() > abs(tf)
+        h = torch.where(final, tf - t, dt)
+        new_dt, (dT, dY) = integ(rhs, t, y, {}, timestep=h)
+        y = torch.where(active, y + dY, y)
+        t = torch.where(active, t + dT, t)
+        dt = torch.where(active & ~final, new_dt, dt)
+        steps += active.to(torch.int64)
+    assert bool((t == tf).all())
+    assert np.array_equal(steps.cpu().numpy(), g["accepted"][:n])
+    assert rel_inf(y.cpu().numpy(), g["y_final"][:, :n]).max() <= 1e-10
+    # single system: 0-d time and step, reference return convention
+    one = de.integrators.RK45CKSolver((3,), torch.float64, rtol=1e-9, atol=1e-9)
+    nd, (dT, dY) = one(rhs, torch.tensor(0.0), torch.as_tensor(g["y0"][:, 0].copy()).cuda(), {}, timestep=torch.tensor(1e-2))
+    assert nd.ndim == 0 and dT.ndim == 0 and tuple(dY.shape) == (3,)
