@@ -175,6 +175,8 @@ class OdeSystem(object):
         self._launches = 0
         self.sync_every = 8          # stage-level path: host checks the active count every N attempts
         self.use_fused = True        # False forces the stage-level path even for a tagged right-hand side
+        self.compaction = True       # stage-level path: gather the active trajectories when < 50 % remain
+        self._compactions = 0
         self.callback_every = 1
 
         self._y0 = y0.reshape(self.numel, self.n_traj).contiguous().clone()
@@ -453,7 +455,10 @@ class OdeSystem(object):
     def _run_stagewise(self, tf, callbacks, bar):
         """Generic right-hand side: the user's torch callable is evaluated between the fused stage
         kernels of libdesolver_b200.so (dsb_erk_stage_*), all on the current stream.  The host looks at
-        the active-trajectory count only every `self.sync_every` attempts."""
+        the active-trajectory count only every `self.sync_every` attempts.  When fewer than half of the
+        working columns are still active (trajectories need very different numbers of attempts, e.g. Van der
+        Pol with mu in [0.1, 10]) the working set is compacted to the active trajectories, so the lock-step
+        rounds near the end no longer pay for the finished ones."""
         torch = _torch()
         integ = self.integrator
         if not isinstance(integ, integrators.RungeKuttaIntegrator):
@@ -463,24 +468,35 @@ class OdeSystem(object):
                                strict=self.strict)
         chunks = max(1, min(4096, (D + 127) // 128))
         f64 = dict(dtype=torch.float64, device=dev)
-        buf = dict(h=torch.zeros(n, **f64), h0=torch.zeros(n, **f64), y_stage=torch.empty((D, n), **f64),
-                   t_stage=torch.zeros(n, **f64), dY=torch.zeros((D, n), **f64), scale=torch.zeros((D, n), **f64),
-                   hist=torch.ones((3, n), **f64), partial=torch.zeros((chunks, n), **f64),
-                   trial=torch.zeros(n, dtype=torch.int32, device=dev), flags=torch.zeros(n, dtype=torch.int32, device=dev))
-        a = cb.ErkStageArgs()
-        a.n, a.dim, a.chunks = n, D, chunks
-        a.y, a.t, a.dt = self._y.data_ptr(), self._t.data_ptr(), self._dt.data_ptr()
-        for k, v in buf.items():
-            setattr(a, k, v.data_ptr())
-        a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
-        a.accepted, a.rejected, a.status = self.accepted.data_ptr(), self.rejected.data_ptr(), self.status.data_ptr()
-        a.counters = self._counters.data_ptr()
+        i32 = dict(dtype=torch.int32, device=dev)
         stream = cb.current_stream_ptr(dev)
-        y_view = self._user_shape(buf["y_stage"])
-        t_view = self._user_time(buf["t_stage"])
-        K = [None] * S
         self._ensure_dense_store()
         dense = self._nodes is not None
+        full = dict(y=self._y, t=self._t, dt=self._dt, accepted=self.accepted, rejected=self.rejected, status=self.status)
+        persistent = ("h", "h0", "trial", "flags", "scale", "hist")     # per-trajectory state that outlives an attempt
+
+        def alloc(m):
+            return dict(h=torch.zeros(m, **f64), h0=torch.zeros(m, **f64), y_stage=torch.empty((D, m), **f64),
+                        t_stage=torch.zeros(m, **f64), dY=torch.zeros((D, m), **f64), scale=torch.zeros((D, m), **f64),
+                        hist=torch.ones((3, m), **f64), partial=torch.zeros((chunks, m), **f64),
+                        trial=torch.zeros(m, **i32), flags=torch.zeros(m, **i32))
+
+        def bind(work, buf, m):
+            a = cb.ErkStageArgs()
+            a.n, a.dim, a.chunks = m, D, chunks
+            a.y, a.t, a.dt = work["y"].data_ptr(), work["t"].data_ptr(), work["dt"].data_ptr()
+            for k, v in buf.items():
+                setattr(a, k, v.data_ptr())
+            a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+            a.accepted, a.rejected, a.status = work["accepted"].data_ptr(), work["rejected"].data_ptr(), work["status"].data_ptr()
+            a.counters = self._counters.data_ptr()
+            shape = tuple(self.dim) + ((m,) if self.ensemble else ())
+            return a, buf["y_stage"].reshape(shape), (buf["t_stage"] if self.ensemble else buf["t_stage"].reshape(()))
+
+        work, buf, m, index, consts = full, alloc(n), n, None, self.__consts
+        a, y_view, t_view = bind(work, buf, m)
+        can_compact = self.ensemble and self.compaction and not callbacks and not dense
+        K = [None] * S
         y_committed = self._user_shape(self._y)
         t_committed = self._user_time(self._t)
 
@@ -493,6 +509,10 @@ class OdeSystem(object):
                                                stream), "dsb_dense_append")
             self._launches += 1
 
+        def scatter_back():
+            for k, v in work.items():
+                full[k].index_copy_(full[k].ndim - 1, index, v)
+
         if dense and int(self._node_count.max().item()) == 0:
             record_nodes(None)                                   # node 0 = initial condition
         first, attempts = True, 0
@@ -504,8 +524,8 @@ class OdeSystem(object):
             first = False
             for s in range(S):
                 handle.stage_state(a, s, stream)
-                k = self.equ_rhs(t_view, y_view, **self.__consts)
-                k = k.to(torch.float64).reshape(D, n)
+                k = self.equ_rhs(t_view, y_view, **consts)
+                k = k.to(torch.float64).reshape(D, m)
                 K[s] = k if k.is_contiguous() else k.contiguous()      # keep alive until the attempt finishes
                 a.K[s] = K[s].data_ptr()
             handle.stage_finish(a, stream)
@@ -518,10 +538,27 @@ class OdeSystem(object):
             if bar is not None:
                 bar.update()
             if callbacks or attempts % sync_every == 0:
-                if int(self._counters[1].item()) == 0:
+                active = int(self._counters[1].item())
+                if active == 0:
                     break
+                if can_compact and m >= 2048 and 2 * active < m:
+                    sel = (buf["flags"] & 1).nonzero().squeeze(1)
+                    if index is not None:
+                        scatter_back()
+                    index = sel if index is None else index[sel]
+                    work = {k: v.index_select(v.ndim - 1, index).contiguous() for k, v in full.items()}
+                    new_buf = alloc(int(sel.numel()))
+                    for k in persistent:
+                        new_buf[k] = buf[k].index_select(buf[k].ndim - 1, sel).contiguous()
+                    buf, m = new_buf, int(sel.numel())
+                    consts = {k: (v.index_select(v.ndim - 1, index) if isinstance(v, torch.Tensor) and v.ndim >= 1
+                                  and v.shape[-1] == n else v) for k, v in self.__consts.items()}
+                    a, y_view, t_view = bind(work, buf, m)
+                    self._compactions += 1
             if attempts > self._step_cap:
                 break
+        if index is not None:
+            scatter_back()
 
     def _run_symplectic(self, tf, callbacks, bar):
         """Explicit symplectic splitting (fixed dt).  Fused kernel for the tagged N-body right-hand side,

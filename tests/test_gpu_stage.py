@@ -190,3 +190,28 @@ def test_integrator_protocol_drives_the_reference_loop():
     one = de.integrators.RK45CKSolver((3,), torch.float64, rtol=1e-9, atol=1e-9)
     nd, (dT, dY) = one(rhs, torch.tensor(0.0), torch.as_tensor(g["y0"][:, 0].copy()).cuda(), {}, timestep=torch.tensor(1e-2))
     assert nd.ndim == 0 and dT.ndim == 0 and tuple(dY.shape) == (3,)
+
+
+def test_stage_path_compaction_is_transparent():
+    """Van der Pol with mu in [0.1, 10] needs 118..470 attempts per trajectory: the stage-level path compacts
+    its working set to the active trajectories; results must be bitwise those of the uncompacted run."""
+    de = _de()
+    y0, mu = de.benchmarks.vdp_ensemble(8192, seed=3)
+
+    def run(compaction):
+        a = de.OdeSystem(de.rhs_plugins.van_der_pol, torch.as_tensor(y0), t=(0.0, 10.0), dt=1e-2, rtol=1e-9, atol=1e-9,
+                         constants=dict(mu=torch.as_tensor(mu)), ensemble=True)
+        a.use_fused = False
+        a.compaction = compaction
+        a.integrate()
+        return a
+    a, b = run(True), run(False)
+    assert a._compactions >= 1 and b._compactions == 0
+    assert torch.equal(a[-1].y, b[-1].y) and torch.equal(a[-1].t, b[-1].t)
+    assert torch.equal(a.accepted, b.accepted) and torch.equal(a.rejected, b.rejected) and bool((a.status == 0).all())
+    assert a.equ_rhs.nfev == b.equ_rhs.nfev                     # same number of lock-step rounds, on fewer columns
+    fused = de.OdeSystem(de.rhs_plugins.van_der_pol, torch.as_tensor(y0), t=(0.0, 10.0), dt=1e-2, rtol=1e-9, atol=1e-9,
+                         constants=dict(mu=torch.as_tensor(mu)), ensemble=True)
+    fused.integrate()
+    assert torch.equal(fused.accepted, a.accepted)
+    assert rel_inf(a[-1].y.cpu().numpy(), fused[-1].y.cpu().numpy()).max() < 1e-10
