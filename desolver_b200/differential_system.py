@@ -217,16 +217,18 @@ class OdeSystem(object):
         n, dev = self.n_traj, self.device
         self._y = self._y0.clone()
         self._t = torch.full((n,), self.__t0, dtype=torch.float64, device=dev)
-        self._dt = torch.full((n,), self.__dt0, dtype=torch.float64, device=dev)
+        dt0 = self.__dt0                                  # sign follows the direction of integration (reference :728-732)
+        if np.sign(dt0) != np.sign(self.__tf - self.__t0):
+            dt0 = -dt0
+        self._dt = torch.full((n,), dt0, dtype=torch.float64, device=dev)
         self.accepted = torch.zeros(n, dtype=torch.int32, device=dev)
         self.rejected = torch.zeros(n, dtype=torch.int32, device=dev)
         self.status = torch.zeros(n, dtype=torch.int32, device=dev)
         self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
-        self._hist_y = [self._y.clone()]
+        self._hist_y = [self._y0]                         # row 0 = initial condition (never written to)
         self._hist_t = [self._t.clone()]
         self._nodes = None
         self._node_count = None
-        self._fix_dt_dir(self.__tf, self.__t0)
 
     def _fix_dt_dir(self, t1, t0):
         torch = _torch()
