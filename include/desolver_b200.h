@@ -42,7 +42,7 @@ typedef enum {
 
 /* Built-in fused right-hand sides (desolver_b200/rhs_plugins.py tags the Python callables). */
 typedef enum {
-    DSB_RHS_LINEAR = 0,  /* y' = A y            (stage-level path + dsb_linear_rhs)          */
+    DSB_RHS_LINEAR = 0,  /* y' = A y: stage-level entry points, A @ Y_stage as one FP64 GEMM */
     DSB_RHS_LORENZ = 1,  /* params: sigma, rho, beta                                          */
     DSB_RHS_VDP    = 2,  /* params: mu                                                        */
     DSB_RHS_NBODY  = 3,  /* state (2, nb, 3) per system; shared: G, eps2, masses              */
