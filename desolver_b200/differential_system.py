@@ -176,6 +176,7 @@ class OdeSystem(object):
         self.sync_every = 8          # stage-level path: host checks the active count every N attempts
         self.use_fused = True        # False forces the stage-level path even for a tagged right-hand side
         self.compaction = True       # stage-level path: gather the active trajectories when < 50 % remain
+        self.use_graphs = True       # stage-level path: replay one attempt as a CUDA graph
         self._compactions = 0
         self.callback_every = 1
 
@@ -508,7 +509,7 @@ class OdeSystem(object):
             f = f if f.is_contiguous() else f.contiguous()
             cb.check(cb.lib().dsb_dense_append(self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity,
                                                n, D, self._t.data_ptr(), self._y.data_ptr(), f.data_ptr(), flags_ptr, 4,
-                                               stream), "dsb_dense_append")
+                                               cb.current_stream_ptr(dev)), "dsb_dense_append")
             self._launches += 1
 
         def scatter_back():
@@ -521,20 +522,51 @@ class OdeSystem(object):
         # heavy attempts (large state x ensemble): one host look per attempt costs nothing next to the
         # attempt itself and saves up to sync_every-1 wasted lock-step rounds at the end
         sync_every = 1 if D * n * S >= (1 << 24) else self.sync_every
-        while True:
-            handle.stage_begin(a, first, stream)
-            first = False
+
+        def one_attempt(first_call):
+            """begin, S x (stage state -> user RHS), finish[, dense nodes]: ~S*(1 + RHS kernels) + 4 launches"""
+            st = cb.current_stream_ptr(dev)
+            handle.stage_begin(a, first_call, st)
             for s in range(S):
-                handle.stage_state(a, s, stream)
+                handle.stage_state(a, s, st)
                 k = self.equ_rhs(t_view, y_view, **consts)
                 k = k.to(torch.float64).reshape(D, m)
                 K[s] = k if k.is_contiguous() else k.contiguous()      # keep alive until the attempt finishes
                 a.K[s] = K[s].data_ptr()
-            handle.stage_finish(a, stream)
-            self._launches += handle.stage_launches
-            attempts += 1
+            handle.stage_finish(a, st)
             if dense:
                 record_nodes(buf["flags"].data_ptr())
+
+        def capture():
+            """One attempt as a CUDA graph: replaying it costs one launch instead of ~S*(1 + RHS kernels) + 4, which
+            is what bounds small and medium ensembles.  A right-hand side that is not capture-safe (host
+            synchronisation, CPU work) keeps the eager loop."""
+            if not self.use_graphs or callbacks:     # callbacks may rebind the system's tensors (e.g. ode_sys.dt = ...)
+                return None
+            try:
+                g = torch.cuda.CUDAGraph()
+                nfev0 = self.equ_rhs.nfev
+                with torch.cuda.graph(g):
+                    one_attempt(False)
+                self.equ_rhs.nfev = nfev0            # the capture pass recorded the calls, it did not execute them
+                return g
+            except Exception:
+                torch.cuda.synchronize(dev)
+                return None
+
+        graph, rhs_calls_per_attempt = None, S + (1 if dense else 0)
+        while True:
+            if first:
+                one_attempt(True)                    # eager: integrate()-entry logic, allocator warm-up
+                first = False
+                graph = capture()
+            elif graph is not None:
+                graph.replay()
+                self.equ_rhs.nfev += rhs_calls_per_attempt
+            else:
+                one_attempt(False)
+            self._launches += handle.stage_launches if graph is None else 1
+            attempts += 1
             for cbk in callbacks:
                 cbk(self)
             if bar is not None:
@@ -557,6 +589,7 @@ class OdeSystem(object):
                                   and v.shape[-1] == n else v) for k, v in self.__consts.items()}
                     a, y_view, t_view = bind(work, buf, m)
                     self._compactions += 1
+                    graph = capture()                # new working set, new addresses: re-capture
             if attempts > self._step_cap:
                 break
         if index is not None:
