@@ -388,6 +388,7 @@ class OdeSystem(object):
         """Resets the system to the initial time (reference :900-910)."""
         self.__int_status = 0
         self.__events = []
+        self.equ_rhs.nfev = 0                              # reference :906
         self._reset_state()
         self.initialise_integrator()
 
