@@ -162,6 +162,53 @@ __global__ void stage_increment_kernel(dsb_erk_stage_args a, KPtrs K, FinalRows 
     a.partial[(long long)chunk * a.n + i] = x;
 }
 
+// Same as stage_increment_kernel for FEW trajectories with a LARGE state (the reference's plain use: one big
+// system, one dt): a CTA owns one (chunk, trajectory) pair, its threads stride over the chunk's state elements and
+// the partial squared norm is reduced in a fixed order (warp shuffles, then warp 0 over the warp sums), so the
+// result is deterministic.  The summation order differs from the FMA chain of the narrow kernel at rounding level.
+template <bool STRICT>
+__global__ void stage_increment_wide_kernel(dsb_erk_stage_args a, KPtrs K, FinalRows fr, int d_per_chunk)
+{
+    using A = Ar<STRICT>;
+    const long long i = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const int d0 = chunk * d_per_chunk, d1 = min(a.dim, d0 + d_per_chunk);
+    const double h = a.h[i];
+    const int trial = a.trial[i];
+    const int S = fr.stages;
+    double x = 0.0;
+    for (int d = d0 + threadIdx.x; d < d1; d += blockDim.x) {
+        const long long e = (long long)d * a.n + i;
+        double sb = 0.0, se = 0.0;
+        for (int j = 0; j < S; ++j) {
+            const double kv = K.k[j][e];
+            sb = A::mad(kv, fr.b[j], sb);
+            se = A::mad(kv, fr.db[j], se);
+        }
+        const double dY = fr.fsal ? a.dY[e] : A::mul(h, sb);
+        const double err = A::mul(h, se);
+        a.dY[e] = dY;
+        if (fr.adaptive) {
+            double sc = np_maximum(fabs(a.y[e]), fabs(dY / h));
+            if (trial > 0) sc = A::add(A::mul(0.8, a.scale[e]), A::mul(0.2, sc));
+            a.scale[e] = sc;
+            const double qv = err / A::mad(a.rtol, sc, a.atol);
+            x = fma(qv, qv, x);
+        }
+    }
+    __shared__ double warp_sum[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) a.partial[(long long)chunk * a.n + i] = v;
+    }
+}
+
 __device__ __forceinline__ double guarded_pow2(double base, double expo)
 {
     double k = pow(base, expo);
@@ -349,12 +396,19 @@ int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_
     dim3 g1((unsigned)((a->n + 127) / 128), (unsigned)chunks);
     const unsigned g2 = (unsigned)((a->n + 127) / 128);
     const int g3 = grid_for((long long)a->dim * a->n, 256, h->sm_count);
+    // few trajectories, large state (e.g. ensemble=False with a big system): parallelise over the state instead
+    const bool wide = a->n < 32 && a->dim >= 8192;
+    if (wide) {
+        dim3 gw((unsigned)chunks, (unsigned)a->n);
+        if (strict) stage_increment_wide_kernel<true><<<gw, 256, 0, stream>>>(*a, K, fr, d_per_chunk);
+        else stage_increment_wide_kernel<false><<<gw, 256, 0, stream>>>(*a, K, fr, d_per_chunk);
+    }
     if (strict) {
-        stage_increment_kernel<true><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
+        if (!wide) stage_increment_kernel<true><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
         stage_controller_kernel<true><<<g2, 128, 0, stream>>>(*a, fr, chunks);
         stage_commit_kernel<true><<<g3, 256, 0, stream>>>(*a);
     } else {
-        stage_increment_kernel<false><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
+        if (!wide) stage_increment_kernel<false><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
         stage_controller_kernel<false><<<g2, 128, 0, stream>>>(*a, fr, chunks);
         stage_commit_kernel<false><<<g3, 256, 0, stream>>>(*a);
     }

@@ -249,3 +249,56 @@ def test_stage_path_cuda_graph_replay_is_transparent():
     c = de.OdeSystem(host_sync_rhs, torch.as_tensor(g["y0"]), t=(0.0, 5.0), dt=1e-2, rtol=1e-10, atol=1e-10, ensemble=True)
     c.integrate()
     assert np.array_equal(c.accepted.cpu().numpy(), g["accepted"])
+
+
+def test_single_large_system_reference_semantics():
+    """ensemble=False with a big state: ONE dt and ONE L2 norm over the whole state (what the reference does when
+    it is handed a (3, N) array) -- the wide increment kernel.  Checked against a numpy
+    transcription of the reference algorithm on the same 12288-dimensional system."""
+    from desolver_b200.integrators import tableaux as tb
+    de = _de()
+    rng = np.random.default_rng(5)
+    blocks, nb = 4096, 3                                  # state dim 12288 >= 8192 -> wide kernel
+    Ab = rng.standard_normal((nb, nb)) * 0.5 - np.eye(nb)
+    y0 = rng.standard_normal((nb, blocks))
+
+    def rhs(t, y):                                        # y (3, blocks): the same 3x3 system for every column
+        return torch.as_tensor(Ab, device=y.device) @ y
+    a = de.OdeSystem(rhs, torch.as_tensor(y0), t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9)       # ensemble=False
+    a.method = "RK45"
+    a.integrate()
+    assert a.n_traj == 1 and tuple(a[-1].y.shape) == (nb, blocks) and a.dt.ndim == 0
+    inter, fin, _ = tb.rk_arrays("RK45CKSolver")
+    y, t, dt, acc, att = y0.copy(), 0.0, 1e-2, 0, 0
+    while dt != 0 and abs(1.0 - t) >= 32 * 2.220446049250313e-16:
+        final = abs(dt + t) > 1.0
+        h = (1.0 - t) if final else dt
+        h0, hist = h, []
+        for trial in range(65):
+            att += 1
+            Ks = []
+            for s_ in range(6):
+                inc = sum((Ks[j] * inter[s_, 1 + j] for j in range(s_) if inter[s_, 1 + j] != 0.0), np.zeros_like(y))
+                Ks.append(Ab @ (y + h * inc))
+            dS = h * sum(Ks[j] * fin[0, 1 + j] for j in range(6))
+            diff = h * sum((fin[0, 1 + j] - fin[1, 1 + j]) * Ks[j] for j in range(6))
+            sc_new = np.maximum(np.abs(y), np.abs(dS / h))
+            sc = sc_new if trial == 0 else 0.8 * sc + 0.2 * sc_new
+            eps = 1.0 / np.linalg.norm((diff / (1e-9 + 1e-9 * sc)).ravel())
+            hist.append(eps)
+            if trial == 0:
+                corr = eps ** 0.2
+            elif trial == 1:
+                corr = eps ** 0.2 * hist[-2] ** 0.2
+            else:
+                corr = eps ** 0.11 * hist[-2] ** -0.054 * hist[-3] ** 0.01
+            f = 1 + np.arctan(0.8 * corr - 1)
+            new = f * h
+            if not f < 0.81:
+                break
+            h = min(new, h0)
+        y, t, acc = y + dS, t + h, acc + 1
+        if not final:
+            dt = new
+    assert int(a.accepted[0]) == acc and int(a.accepted[0] + a.rejected[0]) == att
+    assert rel_inf(a[-1].y.cpu().numpy().ravel(), y.ravel(), axis=0) <= 1e-10
