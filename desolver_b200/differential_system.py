@@ -655,15 +655,39 @@ class OdeSystem(object):
         y_view = self._user_shape(buf["y_stage"])
         t_view = self._user_time(buf["t_stage"])
         first, steps = True, 0
-        while True:
-            handle.stage_begin(a, first, stream)
-            first = False
+
+        def one_step(first_call):
+            st = cb.current_stream_ptr(dev)
+            handle.stage_begin(a, first_call, st)
             for s in range(S):
                 f = self.equ_rhs(t_view, y_view, **self.__consts).to(torch.float64).reshape(D, n)
                 f = f if f.is_contiguous() else f.contiguous()
-                handle.stage_accumulate(a, s, f.data_ptr(), stream)
-            handle.stage_commit(a, stream)
-            self._launches += 4 + S
+                keep[s] = f
+                handle.stage_accumulate(a, s, f.data_ptr(), st)
+            handle.stage_commit(a, st)
+
+        keep = [None] * S
+        graph = None
+        while True:
+            if first:
+                one_step(True)
+                first = False
+                if self.use_graphs and not callbacks:        # same CUDA-graph replay as the explicit-RK stage path
+                    try:
+                        graph = torch.cuda.CUDAGraph()
+                        nfev0 = self.equ_rhs.nfev
+                        with torch.cuda.graph(graph):
+                            one_step(False)
+                        self.equ_rhs.nfev = nfev0
+                    except Exception:
+                        torch.cuda.synchronize(dev)
+                        graph = None
+            elif graph is not None:
+                graph.replay()
+                self.equ_rhs.nfev += S
+            else:
+                one_step(False)
+            self._launches += (4 + S) if graph is None else 1
             steps += 1
             for cbk in callbacks:
                 cbk(self)

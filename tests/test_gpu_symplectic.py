@@ -85,3 +85,27 @@ def test_backward_time_mirrors_reference_single_step():
     a.method = "BABS9O7H"
     a.integrate()
     assert int(a.accepted[0]) == 1 and float(a[-1].t) == 0.5 and float(a.dt) == -0.05
+
+
+def test_known_answers_sho_symplectic():
+    """KA4 / KA5: README oscillator, dt = 0.05, 126 steps, last one truncated; stage-level
+    kernels around the Python callable (eager first step, then CUDA-graph replay)."""
+    de = _de()
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+    for key, method in (("KA4", "BABS9O7H"), ("KA5", "ABAS5O6H")):
+        two_pi = float.fromhex(ka[key]["t"][0])
+        want = np.array([float.fromhex(s) for s in ka[key]["y"]])
+        for strict in (True, False):
+            for graphs in (True, False):
+                a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, np.array([1.0, 0.0]), t=(0, two_pi), dt=0.05, strict=strict)
+                a.method = method
+                a.use_graphs = graphs
+                a.integrate()
+                assert int(a.accepted[0]) == ka[key]["steps"] == 126
+                assert float(a[-1].t) == two_pi
+                assert a.nfev == ka[key]["nfev"]
+                y = a[-1].y.cpu().numpy()
+                if strict:
+                    assert np.array_equal(y, want)                              # +,* only: bit-exact
+                else:
+                    assert np.max(np.abs(y - want)) < 1e-14
