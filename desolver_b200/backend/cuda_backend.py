@@ -145,7 +145,7 @@ def lib():
     L.dsb_erk_stage_launches.restype = C.c_int
     L.dsb_erk_stage_launches.argtypes = [C.c_void_p]
     L.dsb_symp_create.restype = C.c_int
-    L.dsb_symp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_uint]
+    L.dsb_symp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_uint]
     L.dsb_symp_destroy.restype = C.c_int
     L.dsb_symp_destroy.argtypes = [C.c_void_p]
     L.dsb_symp_run.restype = C.c_int
@@ -242,12 +242,12 @@ def erk_handle(device_index, rhs_id, dim, tableau_intermediate, tableau_final, o
 class SympHandle:
     """Owns one dsb_symp_handle: (device, right-hand side, splitting tableau)."""
 
-    def __init__(self, device_index, rhs_id, dim, tableau, strict=False):
+    def __init__(self, device_index, rhs_id, dim, drift_count, tableau, strict=False):
         import numpy as np
         tab = np.ascontiguousarray(tableau, dtype=np.float64)
         self.stages = tab.shape[0]
         self._h = C.c_void_p()
-        check(lib().dsb_symp_create(C.byref(self._h), int(device_index), int(rhs_id), int(dim), self.stages,
+        check(lib().dsb_symp_create(C.byref(self._h), int(device_index), int(rhs_id), int(dim), int(drift_count), self.stages,
                                     tab.ctypes.data_as(_dp), FLAG_STRICT if strict else 0), "dsb_symp_create")
 
     def run(self, args, stream_ptr):
@@ -272,10 +272,10 @@ class SympHandle:
             pass
 
 
-def symp_handle(device_index, rhs_id, dim, tableau, strict=False):
+def symp_handle(device_index, rhs_id, dim, drift_count, tableau, strict=False):
     import numpy as np
-    key = ("symp", int(device_index), int(rhs_id), int(dim), np.asarray(tableau).tobytes(), bool(strict))
+    key = ("symp", int(device_index), int(rhs_id), int(dim), int(drift_count), np.asarray(tableau).tobytes(), bool(strict))
     h = _handle_cache.get(key)
     if h is None:
-        h = _handle_cache[key] = SympHandle(device_index, rhs_id, dim, tableau, strict=strict)
+        h = _handle_cache[key] = SympHandle(device_index, rhs_id, dim, drift_count, tableau, strict=strict)
     return h

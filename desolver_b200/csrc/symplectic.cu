@@ -26,7 +26,7 @@ struct SympTableau {
 }  // namespace dsb
 
 struct dsb_symp_plan {
-    int device = 0, rhs_id = 0, dim = 0, sm_count = 0;
+    int device = 0, rhs_id = 0, dim = 0, drift_count = 0, sm_count = 0;
     unsigned flags = 0;
     dsb::SympTableau tab;
 };
@@ -182,11 +182,11 @@ __global__ void symp_reset_kernel(dsb_symp_stage_args a)
 
 // dS += (h * f) * (drift or kick coefficient); y_stage = y + dS; t_stage += h * drift   (:407-413)
 template <bool STRICT>
-__global__ void symp_accumulate_kernel(dsb_symp_stage_args a, const double *f, double c_drift, double c_kick)
+__global__ void symp_accumulate_kernel(dsb_symp_stage_args a, const double *f, double c_drift, double c_kick, int drift_count)
 {
     using A = Ar<STRICT>;
     const long long total = (long long)a.dim * a.n;
-    const long long half = (long long)(a.dim / 2) * a.n;       // first half of axis 0 = drift variables
+    const long long half = (long long)drift_count * a.n;       // leading part of axis 0 = drift variables
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e % a.n;
         const double h = a.h[i];
@@ -239,15 +239,17 @@ using namespace dsb;
 
 extern "C" {
 
-int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int stages, const double *tableau, unsigned flags)
+int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int drift_count, int stages,
+                    const double *tableau, unsigned flags)
 {
-    if (!out || !tableau || stages < 1 || stages > DSB_MAX_STAGES || dim < 2 || (dim & 1)) {
-        set_error("dsb_symp_create: bad argument (stages=%d dim=%d; dim must be even, stages <= %d)", stages, dim, DSB_MAX_STAGES);
+    if (!out || !tableau || stages < 1 || stages > DSB_MAX_STAGES || dim < 2 || drift_count < 0 || drift_count > dim) {
+        set_error("dsb_symp_create: bad argument (stages=%d dim=%d drift_count=%d; stages <= %d)", stages, dim, drift_count,
+                  DSB_MAX_STAGES);
         return DSB_ERR_BAD_ARGUMENT;
     }
     DSB_CUDA_CHECK(cudaSetDevice(device));
     dsb_symp_plan *p = new dsb_symp_plan;
-    p->device = device; p->rhs_id = rhs_id; p->dim = dim; p->flags = flags;
+    p->device = device; p->rhs_id = rhs_id; p->dim = dim; p->drift_count = drift_count; p->flags = flags;
     p->tab.stages = stages;
     for (int s = 0; s < stages; ++s) { p->tab.drift[s] = tableau[3 * s + 1]; p->tab.kick[s] = tableau[3 * s + 2]; }
     cudaDeviceProp prop;
@@ -263,7 +265,7 @@ int dsb_symp_run(dsb_symp_handle h, const dsb_symp_run_args *a, void *stream)
 {
     if (!h || !a || !a->y || !a->t || !a->dt) { set_error("dsb_symp_run: null argument"); return DSB_ERR_BAD_ARGUMENT; }
     if (h->rhs_id != DSB_RHS_NBODY) { set_error("dsb_symp_run: fused symplectic kernel exists for the N-body right-hand side only"); return DSB_ERR_UNSUPPORTED; }
-    if (a->bodies < 1 || a->bodies > 1024 || h->dim != 6 * a->bodies || !a->masses) {
+    if (a->bodies < 1 || a->bodies > 1024 || h->dim != 6 * a->bodies || h->drift_count != 3 * a->bodies || !a->masses) {
         set_error("dsb_symp_run: state dim %d does not match 2*bodies*3 with bodies=%d", h->dim, a->bodies);
         return DSB_ERR_BAD_ARGUMENT;
     }
@@ -306,9 +308,9 @@ int dsb_symp_stage_accumulate(dsb_symp_handle h, const dsb_symp_stage_args *a, i
     if (stage < 0 || stage >= h->tab.stages || !f) { set_error("dsb_symp_stage_accumulate: bad stage or null f"); return DSB_ERR_BAD_ARGUMENT; }
     const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
     if (h->flags & DSB_FLAG_STRICT)
-        symp_accumulate_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, f, h->tab.drift[stage], h->tab.kick[stage]);
+        symp_accumulate_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, f, h->tab.drift[stage], h->tab.kick[stage], h->drift_count);
     else
-        symp_accumulate_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, f, h->tab.drift[stage], h->tab.kick[stage]);
+        symp_accumulate_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, f, h->tab.drift[stage], h->tab.kick[stage], h->drift_count);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }

@@ -604,13 +604,15 @@ class OdeSystem(object):
         n, D, dev = self.n_traj, self.numel, self.device
         stream = cb.current_stream_ptr(dev)
         rhs = self.equ_rhs
+        # drift (position) variables = rows [0, dim0 // 2) of axis 0, kick = the rest (reference integrator_types.py:359-362)
+        drift_count = (self.dim[0] // 2) * (D // self.dim[0]) if len(self.dim) else 0
         fused = (self.use_fused and getattr(rhs, "device_plugin", None) == "nbody" and len(self.dim) == 3
                  and self.dim[0] == 2 and self.dim[2] == 3 and not self.__dense_output)
         if self.__dense_output:
             raise NotImplementedError("dense_output is not available for symplectic methods in this version")
         if fused:
             nb = self.dim[1]
-            handle = cb.symp_handle(dev.index or 0, rhs.plugin_id, D, integ.tableau_intermediate, strict=self.strict)
+            handle = cb.symp_handle(dev.index or 0, rhs.plugin_id, D, drift_count, integ.tableau_intermediate, strict=self.strict)
             m = torch.as_tensor(self.__consts["m"], dtype=torch.float64, device=dev).contiguous()
             if tuple(m.shape) != (nb,):
                 raise ValueError("fused N-body kernel needs masses of shape (%d,) shared by all systems" % nb)
@@ -639,7 +641,7 @@ class OdeSystem(object):
                         break
             self._keepalive = m
             return
-        handle = cb.symp_handle(dev.index or 0, 100, D, integ.tableau_intermediate, strict=self.strict)
+        handle = cb.symp_handle(dev.index or 0, 100, D, drift_count, integ.tableau_intermediate, strict=self.strict)
         S = integ.stages
         f64 = dict(dtype=torch.float64, device=dev)
         buf = dict(h=torch.zeros(n, **f64), dS=torch.zeros((D, n), **f64), y_stage=torch.empty((D, n), **f64),

@@ -158,11 +158,12 @@ DSB_API int dsb_erk_stage_launches(dsb_erk_handle h);
  * Replace ExplicitSymplecticIntegrator.__call__/step (integrators/integrator_types.py:375-417) and the
  * fixed-step loop of OdeSystem.integrate around it (differential_system.py:996-1002,1015-1018).
  * `tableau` is the class data: stages x 3, column 1 = drift weight (also the time advance), column 2 = kick
- * weight (integrators/explicit_integration_schemes.py:340-425).  Kick variables are the second half of
- * axis 0 of the state (integrator_types.py:359-362); dim must be even. */
+ * weight (integrators/explicit_integration_schemes.py:340-425).  Kick variables are rows dim0//2.. of axis 0 of
+ * the state (integrator_types.py:359-362): `drift_count` = (dim0 // 2) * prod(dim[1:]) leading elements of the
+ * flattened state are drift (position) variables, the rest kick (momentum) variables. */
 typedef struct dsb_symp_plan *dsb_symp_handle;
 
-DSB_API int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int stages,
+DSB_API int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int drift_count, int stages,
                             const double *tableau /* stages x 3, host */, unsigned flags);
 DSB_API int dsb_symp_destroy(dsb_symp_handle h);
 

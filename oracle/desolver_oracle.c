@@ -339,7 +339,7 @@ int orc_symplectic_trajectory(const orc_problem *prob, int S, const double *T, c
                               double *y, double *t_io, double *dt_io, double tf,
                               int64_t max_steps, int64_t *steps_out)
 {
-    const int dim = prob->dim, half = dim / 2;
+    const int dim = prob->dim, half = prob->drift_count >= 0 ? prob->drift_count : dim / 2;
     double t = *t_io, dt = *dt_io;
     int64_t steps = 0;
     int status = ORC_STATUS_OK;

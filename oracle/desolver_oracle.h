@@ -51,6 +51,8 @@ typedef struct {
     int n_params;          /* number of per-trajectory scalar parameters             */
     const double *shared;  /* shared block (see enum above), may be NULL             */
     int n_shared;
+    int drift_count;       /* symplectic only: leading state elements that are drift  */
+                           /* variables = (dim0 // 2) * prod(dim[1:]); < 0: dim / 2   */
 } orc_problem;
 
 typedef struct {

@@ -28,7 +28,7 @@ _lp = C.POINTER(C.c_int64)
 
 class _Problem(C.Structure):
     _fields_ = [("rhs_id", C.c_int), ("dim", C.c_int), ("n_params", C.c_int),
-                ("shared", _dp), ("n_shared", C.c_int)]
+                ("shared", _dp), ("n_shared", C.c_int), ("drift_count", C.c_int)]
 
 
 class _Tableau(C.Structure):
@@ -90,7 +90,7 @@ def _ptr(a):
 
 def _problem(rhs_id, dim, n_params, shared):
     sh = _f64(shared) if shared is not None else None
-    prob = _Problem(rhs_id, dim, n_params, _ptr(sh), 0 if sh is None else sh.size)
+    prob = _Problem(rhs_id, dim, n_params, _ptr(sh), 0 if sh is None else sh.size, -1)
     return prob, sh
 
 
@@ -153,8 +153,9 @@ def erk_ensemble(rhs_id, y0, t0, tf, dt0, rtol, atol, inter, final, order, param
     return dict(y=y, t=t, dt=dt, accepted=acc, rejected=rej, status=st)
 
 
-def symplectic_ensemble(rhs_id, y0, t0, tf, dt0, tab3, params=None, shared=None, threads=1):
-    """Fixed-step symplectic splitting over every column of y0 (dim, N)."""
+def symplectic_ensemble(rhs_id, y0, t0, tf, dt0, tab3, params=None, shared=None, threads=1, drift_count=-1):
+    """Fixed-step symplectic splitting over every column of y0 (dim, N).  `drift_count` leading state elements
+    are drift variables (default dim // 2; (dim0 // 2) * prod(dim[1:]) for a state whose axis 0 is odd)."""
     lib = load()
     y = _f64(np.array(y0, dtype=np.float64, copy=True))
     squeeze = y.ndim == 1
@@ -170,6 +171,7 @@ def symplectic_ensemble(rhs_id, y0, t0, tf, dt0, tab3, params=None, shared=None,
     steps = np.zeros(n, np.int32)
     st = np.zeros(n, np.int32)
     prob, _sh = _problem(rhs_id, dim, prm.shape[0], shared)
+    prob.drift_count = int(drift_count)
     tab3 = _f64(tab3)
 
     def work(first, count):

@@ -109,3 +109,26 @@ def test_known_answers_sho_symplectic():
                     assert np.array_equal(y, want)                              # +,* only: bit-exact
                 else:
                     assert np.max(np.abs(y - want)) < 1e-14
+
+
+def test_odd_leading_axis_kick_mask():
+    """Kick variables are rows dim0 // 2 .. of axis 0 (reference integrator_types.py:359-362): for a 3-row state that is
+    1 drift row and 2 kick rows.  Engine (stage-level kernels) vs oracle with the same split; the reference
+    semantics (rhs evaluated on the whole state, unused half masked by 0) make this well defined for any RHS."""
+    from desolver_b200.integrators import tableaux as tb
+    from oracle import oracle as orc
+    de = _de()
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((3, 3)) * 0.3
+    y0 = rng.standard_normal((3, 16))
+    a = de.OdeSystem(de.rhs_plugins.linear, torch.as_tensor(y0), t=(0.0, 0.32), dt=0.05, constants=dict(A=torch.as_tensor(A).cuda()),
+                     ensemble=True, strict=True)
+    a.method = "ABAS5O6H"
+    a.integrate()
+    ref = orc.symplectic_ensemble(orc.RHS_LINEAR, y0, 0.0, 0.32, 0.05, tb.symplectic_array("ABAs5o6HSolver")[0], shared=A,
+                                  drift_count=1)
+    assert np.array_equal(a.accepted.cpu().numpy(), ref["steps"])
+    assert rel_inf(a[-1].y.cpu().numpy(), ref["y"]).max() < 1e-13
+    wrong = orc.symplectic_ensemble(orc.RHS_LINEAR, y0, 0.0, 0.32, 0.05, tb.symplectic_array("ABAs5o6HSolver")[0], shared=A,
+                                    drift_count=2)
+    assert rel_inf(a[-1].y.cpu().numpy(), wrong["y"]).max() > 1e-6
