@@ -248,6 +248,29 @@ def main():
     total_ms, total_kern_ms = float(t_local[0]), float(t_local[1])
     value = attempts_global * args.steps / (total_ms * 1e-3)
 
+    # ---- parity gate, printed with the throughput: the first trajectories of this rank's
+    # shard against the CPU oracle in the same run; run-to-run bitwise determinism of the GPU path ----
+    parity = None
+    if rank == 0:
+        from desolver_b200.integrators import tableaux as tb
+        from oracle import oracle as orc
+        m = min(4096, n_local)
+        ref = orc.erk_ensemble(orc.RHS_LORENZ, np.ascontiguousarray(y0_host[:, :m]), cfg["t0"], cfg["tf"], cfg["dt0"], cfg["rtol"],
+                               cfg["atol"], *tb.rk_arrays("RK45CKSolver"), params=[cfg["sigma"], cfg["rho"], cfg["beta"]],
+                               threads=host_threads())
+        y_a = sys_[-1].y.clone()
+        acc_a, rej_a = sys_.accepted.clone(), sys_.rejected.clone()
+        one_step()
+        deterministic = bool(torch.equal(y_a, sys_[-1].y) and torch.equal(acc_a, sys_.accepted) and torch.equal(rej_a, sys_.rejected))
+        got = y_a[:, :m].cpu().numpy()
+        err = np.max(np.abs(got - ref["y"]), axis=0) / np.max(np.abs(ref["y"]), axis=0)
+        same = (acc_a[:m].cpu().numpy() == ref["accepted"]) & (rej_a[:m].cpu().numpy() == ref["rejected"])
+        parity = {"checked_trajectories": int(m), "counts_identical_frac": float(same.mean()), "max_rel_err": float(err.max()),
+                  "p99_rel_err": float(np.percentile(err, 99)), "bitwise_deterministic": deterministic,
+                  "bar": "counts identical >= 0.999, rel err <= 1e-10 (BASELINE.json north_star)"}
+    elif world > 1:
+        one_step()                                        # keep the collective inside one_step matched across ranks
+
     # ---- e2e: public API with host buffers (pinned y0 -> device, integrate, results -> host) ----
     e2e_steps = max(2, min(args.steps, 5))
     out_y = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
@@ -304,6 +327,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": float(e2e_t[0]), "ms_all_rank0": e2e_ms},
                 "gpu_launches": launches}
+        line["parity"] = parity
         if not args.no_cpu_baseline:
             rate, cores, sample, _, _ = cpu_reference_sample(args.cpu_seconds, n_local * n_gpus)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
