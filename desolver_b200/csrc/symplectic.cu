@@ -33,6 +33,16 @@ struct dsb_symp_plan {
 
 namespace dsb {
 
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed + one third-order correction (the arithmetic of CUDA's rsqrt()
+// without its denormal/inf side branch, which costs five extra issue slots per pair interaction).
+__device__ __forceinline__ double rsqrt_pos(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(x, -(r * r), 1.0);
+    return fma(fma(e, 0.375, 0.5), r * e, r);
+}
+
 // ------------------------------------------------------------------------------------------ (A) fused N-body
 template <bool STRICT>
 __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
@@ -99,8 +109,8 @@ __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
                         w = A::mul(pj.w, pow(r2, -1.5));
                         if (j == i) w = A::mul(w, 0.0);
                     } else {
-                        double r2 = fma(dz, dz, fma(dy, dy, dx * dx)) + a.eps2;
-                        double rinv = rsqrt(r2);
+                        double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, a.eps2)));
+                        double rinv = rsqrt_pos(r2);
                         w = pj.w * (rinv * rinv * rinv);
                     }
                     ax = A::mad(dx, w, ax);
