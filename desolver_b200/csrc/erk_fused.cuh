@@ -133,13 +133,18 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
         double eps = 1.0 / sqrt(x);
         return eps > 0.0 ? pow(eps, 1.0 / order) : 1.0;
     }
-    if (x > DSB_KC(xlo, 1e-36) && x < DSB_KC(xhi, 1e36) && order_p > 0) {
+    // 2^-120 <= x < 2^120 (|err/tol| in [7.5e-19, 1.2e18]) tested on the exponent bits: two integer instructions
+    // instead of two DSETP plus their constants; zero, denormal, inf and nan all fall outside
+    const unsigned hi = (unsigned)__double2hiint(x);
+    if (hi - 0x38700000u < 0x0f000000u && order_p > 0) {
         if (order_p == 10) return fm::inv_root_narrow<10>(x);
         if (order_p == 16) return fm::inv_root_narrow<16>(x);
         return fm::inv_root_rt(x, order_p);
     }
     if (x > 1e-280 && x < 1e280 && order_p > 0) return fm::inv_root_rt(x, order_p);
-    if (x == 0.0) return CUDART_INF;
+    // eps = inf: the reference gets corr = inf and factor 1 + atan(inf) = 1 + pi/2; 1e300 gives the same double
+    // (atan(0.8e300 - 1) rounds to pi/2) and keeps the table-driven atan in range without a guard
+    if (x == 0.0) return 1e300;
     if (!(x < CUDART_INF)) return 1.0;                  // inf or nan: eps = 0 or nan -> 1
     return pow(x, -0.5 / order);
 }
@@ -167,6 +172,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     const long long n = P.a.n;
     const double tf = P.a.tf, rtol = P.a.rtol, atol = P.a.atol;
     const int lane = threadIdx.x & 31;
+    const int step_budget = P.a.max_steps < 0 ? 0x7fffffff : (P.a.max_steps > 0x7fffffff ? 0x7fffffff : (int)P.a.max_steps);
 
     __shared__ double2 s_atan[fm::ATAN_TABLE_SIZE];
     if (!STRICT) {
@@ -357,7 +363,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             for (int d = 0; d < D; ++d) {
                 double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fm::abs_max(y[d], slope[d]);
                 if (any_retry) {                                       // EMA on retries (:58-59); warp-uniform branch
-                    asm volatile("" ::: "memory");                     // keep it a branch: no speculation of the EMA
+                    __syncwarp();                                      // keeps it a branch (no if-conversion of the EMA)
                     if (trial > 0) sc = A::add(A::mul(DSB_KC(c08, 0.8), scale[d]), A::mul(DSB_KC(c02, 0.2), sc));
                 }
                 sc_cur[d] = sc;
@@ -385,8 +391,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             }
             double u = A::sub(A::mul(DSB_KC(c08, 0.8), corr), 1.0);
             double f;
-            if (STRICT || !(u < DSB_KC(ubig, 1e30))) f = A::add(1.0, atan(u));
-            else f = fm::one_plus_atan(u, s_atan);
+            if (STRICT) f = A::add(1.0, atan(u));
+            else f = fm::one_plus_atan(u, s_atan);                     // corr <= 1e300 by construction
             new_dt = A::mul(f, h);
             redo = f < DSB_KC(reject_below, DSB_REJECT_BELOW);
         }
@@ -408,7 +414,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             }
             start_step();
             done = !((dt != 0.0) && (fabs(tf - t) >= DSB_KC(eps32, DSB_EPS32)))               // :996
-                   || (P.a.max_steps >= 0 && acc >= P.a.max_steps);
+                   || acc >= step_budget;
         }
         // ------------------------------------------------------------ rare events: reject, finish, refill
         if (__any_sync(FULL, live ? (redo || done) : !exhausted)) {

@@ -254,7 +254,7 @@ inline void build_atan_table(double2 *tab)
 // 1 + atan(u) for u in [-1, 1e30): atan(u) = atan(u_k) + atan((u - u_k) / (1 + u u_k)).
 DSB_HD double one_plus_atan(double u, const double2 *tab)
 {
-    float uf = (float)u;
+    float uf = fminf((float)u, 1e18f);           // u up to 1e300 (corr cap): (float)u = inf would make g NaN
     float g = uf * rcpf_seed(1.0f + fabsf(uf));
     int k = (int)rintf((g - (float)ATAN_G_LO) * (float)ATAN_INV_DG);
     k = k < 0 ? 0 : (k > ATAN_TABLE_SIZE - 1 ? ATAN_TABLE_SIZE - 1 : k);

@@ -43,6 +43,6 @@ int main()
         }
     }
     printf("%.3e %.3e %.3e %.3e %.3e %.3e %.3e %.3e\n", w10, w16, wrt, wat, wdiv, wmax, wext, w3);
-    printf("%.17g %.17g\n", one_plus_atan(-1.0, tab), one_plus_atan(1e29, tab));
+    printf("%.17g %.17g\n", one_plus_atan(-1.0, tab), one_plus_atan(0.8e300, tab));
     return 0;
 }

@@ -20,4 +20,4 @@ def test_fastmath_accuracy(tmp_path):
     assert wext <= 4 * eps
     assert w3 <= 1e-13          # rare >=3rd-attempt branch: 11th/27th powers of integer roots amplify rounding
     assert float(out[8]) == 1.0 + math.atan(-1.0)
-    assert abs(float(out[9]) - (1.0 + math.atan(1e29))) <= 2 * eps * 2.57
+    assert abs(float(out[9]) - (1.0 + math.atan(0.8e300))) <= 2 * eps * 2.57
