@@ -372,21 +372,23 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
             }
             if (!STRICT && !live) x = 1.0;     // idle lanes stay on the fast path (no divergent libm calls)
-            if (!any_retry || trial < 2) {
-                corr = corr_term<STRICT>(x, tab.order(), tab.order_p());
-                if (any_retry && trial == 1) corr = A::mul(corr, corr_first);
-            } else {
-                // 3-term product, exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
-                asm volatile("" ::: "memory");
-                const double lo = 1e-250, hi = 1e250;
-                const bool tame = x > lo && x < hi && x_last > lo && x_last < hi && x_last_last > lo && x_last_last < hi;
-                if (!STRICT && tame && tab.order_p() > 0 && (tab.order_p() % 2) == 0) {
-                    corr = fm::corr_three_term(x, x_last, x_last_last, 20 * tab.order_p());
-                } else {
-                    double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
-                    double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
-                    double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
-                    corr = A::mul(A::mul(k1, k2), k3);
+            corr = corr_term<STRICT>(x, tab.order(), tab.order_p());   // first attempt of a step (:73-75)
+            if (any_retry) {                                           // retry chains only; warp-uniform branch
+                __syncwarp();
+                if (trial == 1) {
+                    corr = A::mul(corr, corr_first);                   // 2nd attempt: two-term product (:76-79)
+                } else if (trial >= 2) {
+                    // 3rd+ attempt: exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
+                    const double lo = 1e-250, hi = 1e250;
+                    const bool tame = x > lo && x < hi && x_last > lo && x_last < hi && x_last_last > lo && x_last_last < hi;
+                    if (!STRICT && tame && tab.order_p() > 0 && (tab.order_p() % 2) == 0) {
+                        corr = fm::corr_three_term(x, x_last, x_last_last, 20 * tab.order_p());
+                    } else {
+                        double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
+                        double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
+                        double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
+                        corr = A::mul(A::mul(k1, k2), k3);
+                    }
                 }
             }
             double u = A::sub(A::mul(DSB_KC(c08, 0.8), corr), 1.0);
