@@ -149,7 +149,7 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
     return pow(x, -0.5 / order);
 }
 
-// resident blocks per SM: 6 (<=80 registers; measured best for Cash-Karp x dim<=3), 4 (<=128) while the stage
+// resident blocks per SM: 7 (<=72 registers; measured best for Cash-Karp x dim 3; 8 for dim 2), 4 (<=128) while the stage
 // derivatives fit, else 2 (<=255)
 template <class Rhs, int S>
 constexpr int erk_min_blocks()
@@ -157,7 +157,7 @@ constexpr int erk_min_blocks()
 #ifdef DSB_ERK_MIN_BLOCKS
     return DSB_ERK_MIN_BLOCKS;
 #else
-    return (S * Rhs::DIM <= 18) ? 6 : ((S * Rhs::DIM <= 21) ? 4 : 2);
+    return (S * Rhs::DIM <= 12) ? 8 : ((S * Rhs::DIM <= 18) ? 7 : ((S * Rhs::DIM <= 21) ? 4 : 2));
 #endif
 }
 
@@ -295,6 +295,13 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 }
             }
         }
+        if (!live) {
+            // permanently idle lane (queue exhausted): park it on a benign state so that its (discarded)
+            // arithmetic keeps taking the same branches as the live lanes of the warp
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = 1.0;
+            t = 0.0; dt = 1e-3; h = 1e-3; final_step = false; trial = 0;
+        }
         return __any_sync(FULL, live);
     };
 
@@ -371,7 +378,6 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 double q = STRICT ? err[d] / tol : fm::quick_div(err[d], tol);
                 x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
             }
-            if (!STRICT && !live) x = 1.0;     // idle lanes stay on the fast path (no divergent libm calls)
             corr = corr_term<STRICT>(x, tab.order(), tab.order_p());   // first attempt of a step (:73-75)
             if (any_retry) {                                           // retry chains only; warp-uniform branch
                 __syncwarp();

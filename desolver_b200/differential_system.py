@@ -173,6 +173,7 @@ class OdeSystem(object):
         self.__events = []
         self._step_cap = DEFAULT_STEP_CAP
         self._launches = 0
+        self._scalar_cache = {}
         self.sync_every = 8          # stage-level path: host checks the active count every N attempts
         self.use_fused = True        # False forces the stage-level path even for a tagged right-hand side
         self.compaction = True       # stage-level path: gather the active trajectories when < 50 % remain
@@ -408,12 +409,21 @@ class OdeSystem(object):
 
     def _param_tensors(self, names, defaults):
         """Per-plugin parameter arrays: a (N,) tensor is per-trajectory (stride 1), anything else
-        is one shared value (stride 0)."""
+        is one shared value (stride 0).  Scalars are uploaded once and cached (a fresh `torch.as_tensor`
+        per integrate() call costs a host-to-device copy each)."""
         torch = _torch()
         tensors, strides = [], []
         for name in names:
             v = self.__consts.get(name, defaults.get(name))
-            v = torch.as_tensor(v, dtype=torch.float64, device=self.device)
+            if not isinstance(v, torch.Tensor):
+                key = (name, float(v))
+                cached = self._scalar_cache.get(key)
+                if cached is None:
+                    cached = self._scalar_cache[key] = torch.full((1,), float(v), dtype=torch.float64, device=self.device)
+                tensors.append(cached)
+                strides.append(0)
+                continue
+            v = v.to(device=self.device, dtype=torch.float64)
             if v.ndim == 0:
                 tensors.append(v.reshape(1).contiguous())
                 strides.append(0)
