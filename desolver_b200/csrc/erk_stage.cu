@@ -89,6 +89,70 @@ __global__ void stage_state_kernel(dsb_erk_stage_args a, KPtrs K, StageRow row, 
     }
 }
 
+// Ensemble-shaped variant (n >= 64): thread = VEC adjacent trajectories (128-bit accesses for VEC = 2), grid.y
+// walks the state rows; no integer division per element, h is loaded once per thread.
+template <int VEC> struct Pack;
+template <> struct Pack<1> { double v[1]; };
+template <> struct __align__(16) Pack<2> { double v[2]; };
+
+template <bool STRICT, int VEC>
+__global__ void stage_state_rows_kernel(dsb_erk_stage_args a, KPtrs K, StageRow row, int keep_increment)
+{
+    using A = Ar<STRICT>;
+    using P = Pack<VEC>;
+    const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (col >= a.n) return;
+    const P h = *reinterpret_cast<const P *>(a.h + col);
+    if (blockIdx.y == 0) {
+        const P t = *reinterpret_cast<const P *>(a.t + col);
+        P ts;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ts.v[v] = A::add(t.v[v], A::mul(h.v[v], row.c));
+        *reinterpret_cast<P *>(a.t_stage + col) = ts;
+    }
+    for (int d = blockIdx.y; d < a.dim; d += gridDim.y) {
+        const long long e = (long long)d * a.n + col;
+        P sum;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sum.v[v] = 0.0;
+        for (int q = 0; q < row.nterms; ++q) {
+            const P kv = *reinterpret_cast<const P *>(K.k[row.idx[q]] + e);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sum.v[v] = A::mad(kv.v[v], row.coef[q], sum.v[v]);
+        }
+        const P y = *reinterpret_cast<const P *>(a.y + e);
+        P ys, inc;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            inc.v[v] = A::mul(h.v[v], sum.v[v]);
+            ys.v[v] = STRICT ? A::add(y.v[v], inc.v[v]) : fma(h.v[v], sum.v[v], y.v[v]);
+        }
+        *reinterpret_cast<P *>(a.y_stage + e) = ys;
+        if (keep_increment) *reinterpret_cast<P *>(a.dY + e) = inc;
+    }
+}
+
+template <bool STRICT, int VEC>
+__global__ void stage_commit_rows_kernel(dsb_erk_stage_args a)
+{
+    using A = Ar<STRICT>;
+    using P = Pack<VEC>;
+    const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (col >= a.n) return;
+    bool acc[VEC], any = false;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { acc[v] = a.flags[col + v] & FLAG_ACCEPTED; any |= acc[v]; }
+    if (!any) return;
+    for (int d = blockIdx.y; d < a.dim; d += gridDim.y) {
+        const long long e = (long long)d * a.n + col;
+        P y = *reinterpret_cast<const P *>(a.y + e);
+        const P dy = *reinterpret_cast<const P *>(a.dY + e);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) if (acc[v]) y.v[v] = A::add(y.v[v], dy.v[v]);
+        *reinterpret_cast<P *>(a.y + e) = y;
+    }
+}
+
 // ---- finish 1/3: increment, error estimate, scale, partial squared norms -----------------------------------
 // grid.x tiles trajectories, grid.y tiles the state dimension into `chunks`; thread (i, chunk) walks its d-range.
 template <bool STRICT>
@@ -336,6 +400,15 @@ static int grid_for(long long total, int threads, int sms)
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// rows of the state per grid.y slot: enough CTAs to fill the machine (~16 per SM), each walking many rows so that
+// the per-CTA setup (parameter structs, h) is amortised
+static unsigned rows_grid_y(unsigned gx, int dim, int sms)
+{
+    unsigned want = ((unsigned)sms * 16u + gx - 1) / gx;
+    if (want < 1) want = 1;
+    return want < (unsigned)dim ? want : (unsigned)dim;
+}
+
 static int check_args(const dsb_erk_plan *h, const dsb_erk_stage_args *a, const char *who)
 {
     if (!h || !a) { set_error("%s: null handle or args", who); return DSB_ERR_BAD_ARGUMENT; }
@@ -373,7 +446,19 @@ int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, c
     FinalRows fr;
     build_final(h, fr);
     const int keep = (fr.fsal && stage == h->stages - 1) ? 1 : 0;
-    if (h->flags & DSB_FLAG_STRICT) stage_state_kernel<true><<<grid, 256, 0, stream>>>(*a, K, row, keep);
+    const bool strict = h->flags & DSB_FLAG_STRICT;
+    if (a->n >= 64) {
+        const int vec = (a->n % 2 == 0) ? 2 : 1;
+        const unsigned gx = (unsigned)((a->n / vec + 127) / 128);
+        dim3 g(gx, rows_grid_y(gx, a->dim, h->sm_count));
+        if (vec == 2) {
+            if (strict) stage_state_rows_kernel<true, 2><<<g, 128, 0, stream>>>(*a, K, row, keep);
+            else stage_state_rows_kernel<false, 2><<<g, 128, 0, stream>>>(*a, K, row, keep);
+        } else {
+            if (strict) stage_state_rows_kernel<true, 1><<<g, 128, 0, stream>>>(*a, K, row, keep);
+            else stage_state_rows_kernel<false, 1><<<g, 128, 0, stream>>>(*a, K, row, keep);
+        }
+    } else if (strict) stage_state_kernel<true><<<grid, 256, 0, stream>>>(*a, K, row, keep);
     else stage_state_kernel<false><<<grid, 256, 0, stream>>>(*a, K, row, keep);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
@@ -396,6 +481,10 @@ int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_
     dim3 g1((unsigned)((a->n + 127) / 128), (unsigned)chunks);
     const unsigned g2 = (unsigned)((a->n + 127) / 128);
     const int g3 = grid_for((long long)a->dim * a->n, 256, h->sm_count);
+    const bool rows = a->n >= 64;
+    const int vec = (a->n % 2 == 0) ? 2 : 1;
+    const unsigned grx = (unsigned)((a->n / vec + 127) / 128);
+    dim3 gr(grx, rows_grid_y(grx, a->dim, h->sm_count));
     // few trajectories, large state (e.g. ensemble=False with a big system): parallelise over the state instead
     const bool wide = a->n < 32 && a->dim >= 8192;
     if (wide) {
@@ -406,11 +495,15 @@ int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_
     if (strict) {
         if (!wide) stage_increment_kernel<true><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
         stage_controller_kernel<true><<<g2, 128, 0, stream>>>(*a, fr, chunks);
-        stage_commit_kernel<true><<<g3, 256, 0, stream>>>(*a);
+        if (rows && vec == 2) stage_commit_rows_kernel<true, 2><<<gr, 128, 0, stream>>>(*a);
+        else if (rows) stage_commit_rows_kernel<true, 1><<<gr, 128, 0, stream>>>(*a);
+        else stage_commit_kernel<true><<<g3, 256, 0, stream>>>(*a);
     } else {
         if (!wide) stage_increment_kernel<false><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
         stage_controller_kernel<false><<<g2, 128, 0, stream>>>(*a, fr, chunks);
-        stage_commit_kernel<false><<<g3, 256, 0, stream>>>(*a);
+        if (rows && vec == 2) stage_commit_rows_kernel<false, 2><<<gr, 128, 0, stream>>>(*a);
+        else if (rows) stage_commit_rows_kernel<false, 1><<<gr, 128, 0, stream>>>(*a);
+        else stage_commit_kernel<false><<<g3, 256, 0, stream>>>(*a);
     }
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
