@@ -199,17 +199,15 @@ def main():
     def one_step(ev=None):
         """device-resident step: reset state from y0 (device copy), integrate, reduce the counters"""
         sys_.reset()
-        if ev:
-            ev[0].record()
+        sys_._kernel_events = ev              # CUDA events recorded around the dsb_erk_run launch itself
         sys_.integrate()
-        if ev:
-            ev[1].record()
-        att = (sys_.accepted.sum(dtype=torch.float64) + sys_.rejected.sum(dtype=torch.float64))
-        stats[0] = att
-        stats[1] = (sys_.status != 0).sum().to(torch.float64)
+        sys_._kernel_events = None
+        st = sys_.stats                       # totals accumulated by the kernel itself (one 64-byte D2H in integrate())
         if world > 1:
+            stats[0], stats[1] = float(st["attempts"]), float(st["failed"] + st["running"])
             dist.all_reduce(stats)            # termination / statistics all-reduce (NCCL)
-        return stats
+            return stats.clone()
+        return torch.tensor([float(st["attempts"]), float(st["failed"] + st["running"])], dtype=torch.float64)
 
     for _ in range(args.warmup):
         one_step()
@@ -229,9 +227,7 @@ def main():
         st = one_step(kern_ev[i])
         step_ev[i][1].record()
         flush.zero_()                          # L2 flush between timed iterations (outside the events)
-        total_attempts_dev = st.clone()
-        if i == args.steps - 1:
-            pass
+        total_attempts_dev = st
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -240,8 +236,8 @@ def main():
     launches = sys_._launches - launches0
     attempts_global = float(total_attempts_dev[0].item())       # per step, all ranks (already all-reduced)
     failed = float(total_attempts_dev[1].item())
-    attempts_local = float((sys_.accepted.sum() + sys_.rejected.sum()).item())
-    accepted_local = float(sys_.accepted.sum().item())
+    attempts_local = float(sys_.stats["attempts"])
+    accepted_local = float(sys_.stats["accepted"])
     t_local = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -271,34 +267,36 @@ def main():
     elif world > 1:
         one_step()                                        # keep the collective inside one_step matched across ranks
 
-    # ---- e2e: public API with host buffers (pinned y0 -> device, integrate, results -> host) ----
+    # ---- e2e: public API with host buffers.  `host_io=True`: pinned host y0 in, pinned host results out; the
+    # upload, the kernels and the download of the chunks overlap inside integrate() (OdeSystem._run_host_pipeline).
+    # The timed region covers construction, every host<->device copy, the integration and the final synchronisation.
     e2e_steps = max(2, min(args.steps, 5))
-    out_y = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
-    out_c = torch.empty((3, n_local), dtype=torch.int32).pin_memory()
+    host_out = dict(y=torch.empty((3, n_local), dtype=torch.float64).pin_memory(),
+                    accepted=torch.empty(n_local, dtype=torch.int32).pin_memory(),
+                    rejected=torch.empty(n_local, dtype=torch.int32).pin_memory(),
+                    status=torch.empty(n_local, dtype=torch.int32).pin_memory())
     e2e_ms = []
-    E2E_WARMUP = 2                      # allocator / pinned-copy warm-up iterations, untimed
+    E2E_WARMUP = 2                      # allocator / stream-creation warm-up iterations, untimed
     for i in range(E2E_WARMUP + e2e_steps):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        s2 = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned.to(dev, non_blocking=True), t=(cfg["t0"], cfg["tf"]),
-                          dt=cfg["dt0"], rtol=cfg["rtol"], atol=cfg["atol"], ensemble=True)
-        s2.integrate()
-        out_y.copy_(s2[-1].y, non_blocking=True)
-        out_c[0].copy_(s2.accepted, non_blocking=True)
-        out_c[1].copy_(s2.rejected, non_blocking=True)
-        out_c[2].copy_(s2.status, non_blocking=True)
+        s2 = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned, t=(cfg["t0"], cfg["tf"]), dt=cfg["dt0"], rtol=cfg["rtol"],
+                          atol=cfg["atol"], ensemble=True, device=dev, host_io=True, host_out=host_out)
+        s2.integrate()                  # returns after the last download has landed in host_out
         b.record()
         barrier()
         if i >= E2E_WARMUP:
             e2e_ms.append(a.elapsed_time(b))
+        if i == 0 and rank == 0:        # the host results are the device-resident results, bit for bit
+            assert torch.equal(s2[-1].y, sys_[-1].y.cpu()) and torch.equal(s2.accepted, sys_.accepted.cpu())
         flush.zero_()
     e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = attempts_global / (float(e2e_t[0]) * 1e-3)
     h2d = int(y0_pinned.numel() * 8)
-    d2h = int(out_y.numel() * 8 + out_c.numel() * 4)
+    d2h = int(sum(v.numel() * v.element_size() for v in host_out.values()))
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
@@ -319,7 +317,7 @@ def main():
                            "attempts_per_step": attempts_global, "accepted_local": accepted_local,
                            "failed_trajectories": failed, "wall_s_timed_region": wall},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_kind, "kernel": "dsb::erk_fused_kernel<Lorenz,6>",
+                             "traffic": traffic, "peak_source": peak_kind, "kernel": "dsb::erk_fused_kernel<LorenzRhs, StaticTab<CashKarp45>>",
                              "kernel_ms": total_kern_ms / args.steps,
                              "algorithmic_bytes_per_launch": attempts_local * BYTES_PER_TRAJ_STEP,
                              "trajectory_steps_per_s_kernel": attempts_local / kern_s},

@@ -12,6 +12,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_PKG, "libdesolver_b200.so")
 
+ABI_VERSION = 2
 DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED = 0, 1, 2, 3
 TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING = 0, 1, 2
 FLAG_STRICT = 1
@@ -34,6 +35,11 @@ class ErkRunArgs(C.Structure):
         ("first_call", C.c_int32),
         ("nodes", C.c_void_p), ("node_count", C.c_void_p), ("node_capacity", C.c_int32),
         ("counters", C.c_void_p),
+        # ABI 2
+        ("stride", C.c_int64),
+        ("y_init", C.c_void_p),
+        ("t_init", C.c_double), ("dt_init", C.c_double),
+        ("fresh", C.c_int32),
     ]
 
 
@@ -156,8 +162,8 @@ def lib():
     L.dsb_symp_stage_accumulate.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p]
     L.dsb_symp_stage_commit.restype = C.c_int
     L.dsb_symp_stage_commit.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_void_p]
-    if L.dsb_abi_version() != 1:
-        raise ImportError("libdesolver_b200.so has ABI version %d, expected 1" % L.dsb_abi_version())
+    if L.dsb_abi_version() != ABI_VERSION:
+        raise ImportError("libdesolver_b200.so has ABI version %d, expected %d" % (L.dsb_abi_version(), ABI_VERSION))
     _lib = L
     return L
 

@@ -40,7 +40,7 @@ int dsb_abi_version(void) { return DSB_ABI_VERSION; }
 
 const char *dsb_build_info(void)
 {
-    return "libdesolver_b200 abi=1 arch=sm_100a nvcc=" DSB_STR(__CUDACC_VER_MAJOR__) "." DSB_STR(__CUDACC_VER_MINOR__)
+    return "libdesolver_b200 abi=2 arch=sm_100a nvcc=" DSB_STR(__CUDACC_VER_MAJOR__) "." DSB_STR(__CUDACC_VER_MINOR__)
            " fused_stages={1,2,4,6,7,13,17} rhs={lorenz,van_der_pol,harmonic_oscillator}";
 }
 
@@ -90,6 +90,18 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
         delete p;
         return DSB_ERR_CUDA;
     }
+    if (final_rows == 2) {
+        // step-size factor of a step's first attempt, tabulated for this method's order (factor_table.h)
+        std::vector<ft::Entry> host_ft(ft::ENTRIES);
+        ft::build_table(order, 0.8, host_ft.data());
+        if (cudaMalloc(&p->d_factor, sizeof(ft::Entry) * ft::ENTRIES) != cudaSuccess ||
+            cudaMemcpy(p->d_factor, host_ft.data(), sizeof(ft::Entry) * ft::ENTRIES, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("dsb_erk_create: device table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(p->d_atan);
+            delete p;
+            return DSB_ERR_CUDA;
+        }
+    }
     *out = p;
     return DSB_OK;
 }
@@ -99,6 +111,7 @@ int dsb_erk_destroy(dsb_erk_handle h)
     if (!h) return DSB_OK;
     if (h->d_atan) cudaFree(h->d_atan);
     if (h->d_tab) cudaFree(h->d_tab);
+    if (h->d_factor) cudaFree(h->d_factor);
     delete h;
     return DSB_OK;
 }
@@ -117,6 +130,10 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
     }
     if (a->nodes && (!a->node_count || a->node_capacity < 2)) {
         set_error("dsb_erk_run: dense output needs node_count and node_capacity >= 2");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    if (a->stride != 0 && a->stride < a->n) {
+        set_error("dsb_erk_run: stride (%lld) must be 0 or >= n (%lld)", (long long)a->stride, (long long)a->n);
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "fastmath.cuh"
+#include "factor_table.h"
 #include <math_constants.h>
 #include <type_traits>
 #include "tableau_static.cuh"
@@ -34,6 +35,7 @@ struct ErkKernelArgs {
     dsb_erk_run_args a;
     TableauData<S> tab;
     const double2 *atan_table;   // device copy of fm::build_atan_table
+    const ft::Entry *factor_table;   // device copy of ft::build_table for this method's order (adaptive, fast flavour)
 };
 
 // compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
@@ -175,10 +177,30 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     const int step_budget = P.a.max_steps < 0 ? 0x7fffffff : (P.a.max_steps > 0x7fffffff ? 0x7fffffff : (int)P.a.max_steps);
 
     __shared__ double2 s_atan[fm::ATAN_TABLE_SIZE];
+    // double2 slots per shared-memory entry: 4 used + 1 pad, so that the 128-bit loads of 32 lanes reading 32
+    // different entries spread over all bank groups (80-byte stride: 4 wavefronts instead of 16; measured 3.81 ->
+    // 3.77 ms).  With 8 resident blocks per SM the padded table would not fit, so those kernels stay unpadded.
+#ifdef DSB_FT_SLOTS
+    constexpr int FT_SLOTS = DSB_FT_SLOTS;
+#else
+    constexpr int FT_SLOTS = erk_min_blocks<Rhs, Tab::S>() >= 8 ? 4 : 5;
+#endif
+    __shared__ double2 s_ft[(STRICT ? 1 : ft::HOT_ENTRIES) * FT_SLOTS];   // hot octaves of the step-size factor table
+    // per-thread statistics slots (no atomics): attempts, accepted steps, failed / unfinished trajectories
+    __shared__ unsigned long long s_att[ERK_THREADS], s_acc[ERK_THREADS];
+    __shared__ unsigned s_fail[ERK_THREADS], s_run[ERK_THREADS];
+    s_att[threadIdx.x] = 0; s_acc[threadIdx.x] = 0; s_fail[threadIdx.x] = 0; s_run[threadIdx.x] = 0;
     if (!STRICT) {
         for (int i = threadIdx.x; i < fm::ATAN_TABLE_SIZE; i += blockDim.x) s_atan[i] = P.atan_table[i];
+        if (tab.adaptive()) {
+            const double2 *src = reinterpret_cast<const double2 *>(P.factor_table + ft::HOT_OFFSET);
+            for (int i = threadIdx.x; i < ft::HOT_ENTRIES * 4; i += blockDim.x) s_ft[(i >> 2) * FT_SLOTS + (i & 3)] = src[i];
+        }
         __syncthreads();
     }
+    const long long ld = P.a.stride > 0 ? P.a.stride : n;          // leading dimension of y (and y_init)
+    const double *y_src = P.a.y_init ? P.a.y_init : P.a.y;
+    const bool fresh = P.a.fresh != 0;
 
     // ---- per-lane trajectory state (registers) ----
     long long idx = 0;
@@ -196,12 +218,36 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 
     auto store = [&](int st) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) P.a.y[(long long)d * n + idx] = y[d];
+        for (int d = 0; d < D; ++d) P.a.y[(long long)d * ld + idx] = y[d];
         P.a.t[idx] = t;
         P.a.dt[idx] = dt;
-        if (P.a.accepted) P.a.accepted[idx] += acc;
-        if (P.a.rejected) P.a.rejected[idx] += rej;
+        if (P.a.accepted) P.a.accepted[idx] = fresh ? acc : P.a.accepted[idx] + acc;
+        if (P.a.rejected) P.a.rejected[idx] = fresh ? rej : P.a.rejected[idx] + rej;
         if (P.a.status) P.a.status[idx] = st;
+        s_att[threadIdx.x] += (unsigned long long)(acc + rej);
+        s_acc[threadIdx.x] += (unsigned long long)acc;
+        s_fail[threadIdx.x] += st == (int)DSB_TRAJ_TOL_FAIL;
+        s_run[threadIdx.x] += st == (int)DSB_TRAJ_RUNNING;
+    };
+    // per-warp totals -> counters[2..5] (one atomic per statistic per warp, at warp exit)
+    auto flush_stats = [&]() {
+        __syncwarp();
+        unsigned long long a = s_att[threadIdx.x], c = s_acc[threadIdx.x];
+        unsigned f = s_fail[threadIdx.x], r = s_run[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(FULL, a, o);
+            c += __shfl_xor_sync(FULL, c, o);
+        }
+        f = __reduce_add_sync(FULL, f);
+        r = __reduce_add_sync(FULL, r);
+        if (lane == 0) {
+            unsigned long long *ctr = (unsigned long long *)P.a.counters;
+            if (a) atomicAdd(ctr + 2, a);
+            if (c) atomicAdd(ctr + 3, c);
+            if (f) atomicAdd(ctr + 4, (unsigned long long)f);
+            if (r) atomicAdd(ctr + 5, (unsigned long long)r);
+        }
     };
     auto dense_node = [&](const double (&f)[D]) {
         int c = P.a.node_count[idx];
@@ -229,7 +275,11 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         if (live && redo) {
             // integrator_types.py:201-224: retry with min(new, h0); history for the 2- and 3-term controller
             rej++;
-            if (trial == 0) { h0 = h; corr_first = corr; }
+            if (trial == 0) {
+                h0 = h;
+                // (the fast flavour forms the two-term product of the next attempt from x_last, see the controller)
+                if (STRICT) corr_first = corr;
+            }
             trial++;
             x_last_last = x_last;
             x_last = x;
@@ -261,14 +311,14 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             if (!live && mine < n) {
                 idx = mine;
 #pragma unroll
-                for (int d = 0; d < D; ++d) y[d] = P.a.y[(long long)d * n + idx];
-                t = P.a.t[idx];
-                dt = P.a.dt[idx];
+                for (int d = 0; d < D; ++d) y[d] = y_src[(long long)d * ld + idx];
+                t = fresh ? P.a.t_init : P.a.t[idx];
+                dt = fresh ? P.a.dt_init : P.a.dt[idx];
 #pragma unroll
                 for (int p = 0; p < NP; ++p) prm[p] = P.a.params[p][idx * P.a.param_stride[p]];
                 Rhs::prepare(prm);
                 acc = 0; rej = 0; trial = 0;
-                int st0 = P.a.status ? P.a.status[idx] : (int)DSB_TRAJ_DONE;
+                int st0 = (P.a.status && !fresh) ? P.a.status[idx] : (int)DSB_TRAJ_DONE;
                 bool go = st0 != (int)DSB_TRAJ_TOL_FAIL;
                 if (go && P.a.first_call) {
                     // integrate() entry: differential_system.py:956-957, 971-974
@@ -305,7 +355,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         return __any_sync(FULL, live);
     };
 
-    if (!event_path()) return;
+    if (!event_path()) { flush_stats(); return; }
 
     for (;;) {
         // ------------------------------------------------------------ stages
@@ -368,7 +418,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             const bool any_retry = __any_sync(FULL, trial > 0);       // warp-uniform: rare paths are skipped
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fm::abs_max(y[d], slope[d]);
+                double sc = STRICT ? np_maximum(fabs(y[d]), fabs(slope[d])) : fm::abs_max_setp(y[d], slope[d]);
                 if (any_retry) {                                       // EMA on retries (:58-59); warp-uniform branch
                     __syncwarp();                                      // keeps it a branch (no if-conversion of the EMA)
                     if (trial > 0) sc = A::add(A::mul(DSB_KC(c08, 0.8), scale[d]), A::mul(DSB_KC(c02, 0.2), sc));
@@ -378,29 +428,74 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 double q = STRICT ? err[d] / tol : fm::quick_div(err[d], tol);
                 x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
             }
-            corr = corr_term<STRICT>(x, tab.order(), tab.order_p());   // first attempt of a step (:73-75)
-            if (any_retry) {                                           // retry chains only; warp-uniform branch
-                __syncwarp();
-                if (trial == 1) {
-                    corr = A::mul(corr, corr_first);                   // 2nd attempt: two-term product (:76-79)
-                } else if (trial >= 2) {
-                    // 3rd+ attempt: exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
-                    const double lo = 1e-250, hi = 1e250;
-                    const bool tame = x > lo && x < hi && x_last > lo && x_last < hi && x_last_last > lo && x_last_last < hi;
-                    if (!STRICT && tame && tab.order_p() > 0 && (tab.order_p() % 2) == 0) {
-                        corr = fm::corr_three_term(x, x_last, x_last_last, 20 * tab.order_p());
-                    } else {
-                        double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
-                        double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
-                        double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
-                        corr = A::mul(A::mul(k1, k2), k3);
+            // retry chains (:76-90): corr of this attempt times the history; lanes on a first attempt skip it
+            auto retry_corr = [&](double c_cur) -> double {
+                if (trial == 1) return A::mul(c_cur, corr_first);      // 2nd attempt: two-term product (:76-79)
+                // 3rd+ attempt: exponents 0.55/-0.27/0.05 over order (integrator_template.py:80-90)
+                const double lo = 1e-250, hi = 1e250;
+                const bool tame = x > lo && x < hi && x_last > lo && x_last < hi && x_last_last > lo && x_last_last < hi;
+                if (!STRICT && tame && tab.order_p() > 0 && (tab.order_p() % 2) == 0)
+                    return fm::corr_three_term(x, x_last, x_last_last, 20 * tab.order_p());
+                double k1 = guarded_pow(1.0 / sqrt(x), 0.55 / tab.order());
+                double k2 = guarded_pow(1.0 / sqrt(x_last), -0.27 / tab.order());
+                double k3 = guarded_pow(1.0 / sqrt(x_last_last), 0.05 / tab.order());
+                return A::mul(A::mul(k1, k2), k3);
+            };
+            double f;
+            if constexpr (STRICT) {
+                corr = corr_term<STRICT>(x, tab.order(), tab.order_p());   // first attempt of a step (:73-75)
+                if (any_retry) {                                           // retry chains only; warp-uniform branch
+                    __syncwarp();
+                    if (trial >= 1) corr = retry_corr(corr);
+                }
+                double u = A::sub(A::mul(DSB_KC(c08, 0.8), corr), 1.0);
+                f = A::add(1.0, atan(u));
+            } else {
+                // First attempt of a step: f = F(x) = 1 + atan(0.8 x^(-1/(2 order)) - 1) from the factor table
+                // (factor_table.h), a pure function of the bits of its argument.  Second attempt (:76-79):
+                // corr = eps_cur^(1/order) * eps_last^(1/order) = (x * x_last)^(-1/(2 order)), i.e. the SAME function
+                // of the product of the two squared norms.  Third and later attempts (three-term product with
+                // non-integer exponents, :80-90) are rare and go through fastmath.cuh.  Idle lanes read entry 0.
+                double xe = x;
+                if (any_retry) {                                           // warp-uniform branch
+                    __syncwarp();
+                    if (trial == 1) xe = x * x_last;
+                }
+                const bool deep = trial >= 2;
+                const unsigned xhi = (unsigned)__double2hiint(xe);
+                const int kt = ft::index_of_hi(xhi);
+                const unsigned kh = (live && !deep) ? (unsigned)(kt - ft::HOT_OFFSET) : 0u;
+                const double dx = xe - __hiloint2double((int)ft::midpoint_hi(xhi), 0);     // exact
+                double cf[ft::DEG + 1];
+                if (__all_sync(FULL, kh < (unsigned)ft::HOT_ENTRIES)) {
+                    const double2 *e = &s_ft[kh * FT_SLOTS];
+#pragma unroll
+                    for (int i = 0; i < (ft::DEG + 1) / 2; ++i) { double2 v = e[i]; cf[2 * i] = v.x; cf[2 * i + 1] = v.y; }
+                    f = ft::horner(cf, dx);
+                } else {
+                    // some lane left the hot octaves (first steps, truncated last step): global copy of the table,
+                    // same coefficients, same Horner chain -> same bits; beyond the table: fastmath.cuh
+                    const bool in_tab = (unsigned)kt < (unsigned)ft::ENTRIES;
+                    const double2 *e = reinterpret_cast<const double2 *>(P.factor_table + (in_tab ? kt : 0));
+#pragma unroll
+                    for (int i = 0; i < (ft::DEG + 1) / 2; ++i) { double2 v = __ldg(e + i); cf[2 * i] = v.x; cf[2 * i + 1] = v.y; }
+                    f = ft::horner(cf, dx);
+                    if (!in_tab && !deep) {
+                        // xe outside [2^-100, 2^28), zero, inf or nan.  For trial == 1 the two-term product is formed
+                        // from the factors so that an overflowing / underflowing xe cannot change the result class.
+                        corr = corr_term<STRICT>(x, tab.order(), tab.order_p());
+                        if (trial == 1) corr = corr * corr_term<STRICT>(x_last, tab.order(), tab.order_p());
+                        f = fm::one_plus_atan(fma(DSB_KC(c08, 0.8), fmin(corr, 1e300), -1.0), s_atan);
+                    }
+                }
+                if (any_retry) {                                           // retry chains only; warp-uniform branch
+                    __syncwarp();
+                    if (deep) {
+                        corr = retry_corr(1.0);
+                        f = fm::one_plus_atan(fma(DSB_KC(c08, 0.8), fmin(corr, 1e300), -1.0), s_atan);
                     }
                 }
             }
-            double u = A::sub(A::mul(DSB_KC(c08, 0.8), corr), 1.0);
-            double f;
-            if (STRICT) f = A::add(1.0, atan(u));
-            else f = fm::one_plus_atan(u, s_atan);                     // corr <= 1e300 by construction
             new_dt = A::mul(f, h);
             redo = f < DSB_KC(reject_below, DSB_REJECT_BELOW);
         }
@@ -429,6 +524,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             if (!event_path()) break;
         }
     }
+    flush_stats();
 }
 
 // Host-side launcher, one per instantiation.

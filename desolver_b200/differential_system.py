@@ -128,11 +128,36 @@ class DenseOutput(object):
         return s._user_shape(out)
 
 
+def _state_property(name):
+    """Per-trajectory state tensor that is filled on first use: `reset()` only marks the state as pristine, and a
+    fused run from a pristine state lets the kernel initialise everything itself (dsb_erk_run_args.fresh), so
+    re-running an ensemble costs no fill / copy launches.  Any other reader triggers `_materialize()` first."""
+    raw = "_raw_" + name
+
+    def getter(self):
+        self._materialize()
+        return getattr(self, raw)
+
+    def setter(self, value):
+        self._materialize()
+        setattr(self, raw, value)
+
+    return property(getter, setter)
+
+
 class OdeSystem(object):
     """Ordinary differential equation system integrated on a B200 by libdesolver_b200.so."""
 
+    _y = _state_property("y")
+    _t = _state_property("t")
+    _dt = _state_property("dt")
+    accepted = _state_property("accepted")
+    rejected = _state_property("rejected")
+    status = _state_property("status")
+
     def __init__(self, equ_rhs, y0, t=(0, 1), dense_output=False, dt=1.0, rtol=None, atol=None, constants=dict(),
-                 ensemble=False, device=None, dense_capacity=None, strict=False):
+                 ensemble=False, device=None, dense_capacity=None, strict=False, host_io=False, host_chunks=4,
+                 host_out=None):
         torch = _torch()
         if len(t) != 2:
             raise ValueError("Two time bounds are required, only {} were given.".format(len(t)))
@@ -146,7 +171,18 @@ class OdeSystem(object):
         if isinstance(y0, torch.Tensor) and y0.is_cuda and device is None:
             device = y0.device
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        y0 = torch.as_tensor(y0, dtype=torch.float64).to(self.device)
+        # host_io=True: y0 stays in (pinned) host memory and the results come back to host memory -- like the
+        # reference, where the state lives wherever y0 lives (differential_system.py:507-515).  integrate() then
+        # streams the ensemble through the device in `host_chunks` pieces: the upload of piece c+1 and the
+        # download of piece c-1 overlap the kernel of piece c (see _run_host_pipeline).
+        self.host_io = bool(host_io)
+        self.host_chunks = int(host_chunks)
+        y0 = torch.as_tensor(y0, dtype=torch.float64)
+        if self.host_io:
+            if y0.is_cuda or not ensemble:
+                raise ValueError("host_io=True needs ensemble=True and a host (CPU, ideally pinned) y0")
+        else:
+            y0 = y0.to(self.device)
         self.ensemble = bool(ensemble)
         if self.ensemble:
             if y0.ndim < 2:
@@ -181,6 +217,11 @@ class OdeSystem(object):
         self._compactions = 0
         self.callback_every = 1
 
+        if self.host_io:
+            self._init_host_io(y0, host_out)
+            self._reset_state()
+            self.initialise_integrator()
+            return
         self._y0 = y0.reshape(self.numel, self.n_traj).contiguous().clone()
         # one RHS evaluation as a shape check, like the reference (:536-539)
         probe = self.equ_rhs(self._user_time(torch.full((self.n_traj,), self.__t0, dtype=torch.float64,
@@ -214,23 +255,90 @@ class OdeSystem(object):
     def _user_time(self, tvec):
         return tvec if self.ensemble else tvec.reshape(())
 
-    def _reset_state(self):
+    def _init_host_io(self, y0, host_out):
+        """host_io=True: host-side state (y0 as given, pinned result buffers) and device staging buffers."""
         torch = _torch()
         n, dev = self.n_traj, self.device
-        self._y = self._y0.clone()
-        self._t = torch.full((n,), self.__t0, dtype=torch.float64, device=dev)
+        self._y0 = y0.reshape(self.numel, n)                      # host view, never copied
+        if not self._y0.is_contiguous():
+            self._y0 = self._y0.contiguous()
+        if self._fused_plugin_tag() is None:
+            raise NotImplementedError("host_io=True is implemented for right-hand sides with a fused device plugin "
+                                      "(rhs_plugins.lorenz / van_der_pol / harmonic_oscillator)")
+        host_out = host_out or {}
+
+        def host_buffer(name, shape, dtype):
+            buf = host_out.get(name)
+            if buf is None:
+                buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+            if tuple(buf.shape) != tuple(shape) or buf.dtype != dtype or buf.is_cuda or not buf.is_contiguous():
+                raise ValueError("host_out[%r] must be a contiguous host tensor of shape %r, dtype %s" % (name, shape, dtype))
+            return buf
+
+        self._raw_y = host_buffer("y", (self.numel, n), torch.float64)
+        self._raw_accepted = host_buffer("accepted", (n,), torch.int32)
+        self._raw_rejected = host_buffer("rejected", (n,), torch.int32)
+        self._raw_status = host_buffer("status", (n,), torch.int32)
+        self._dev_y = torch.empty((self.numel, n), dtype=torch.float64, device=dev)
+        self._raw_t = torch.empty((n,), dtype=torch.float64, device=dev)      # t and dt stay on the device
+        self._raw_dt = torch.empty((n,), dtype=torch.float64, device=dev)
+        self._dev_accepted = torch.empty(n, dtype=torch.int32, device=dev)
+        self._dev_rejected = torch.empty(n, dtype=torch.int32, device=dev)
+        self._dev_status = torch.empty(n, dtype=torch.int32, device=dev)
+        self._counters = torch.zeros(8 * max(1, self.host_chunks), dtype=torch.int64, device=dev)
+        self._pipe_streams = None
+
+    def _fused_plugin_tag(self):
+        rhs = self.equ_rhs
+        if getattr(rhs, "plugin_id", None) is None:
+            return None
+        if getattr(rhs, "device_plugin", None) not in ("lorenz", "van_der_pol", "harmonic_oscillator"):
+            return None
+        return rhs.plugin_id
+
+    def _initial_dt(self):
         dt0 = self.__dt0                                  # sign follows the direction of integration (reference :728-732)
         if np.sign(dt0) != np.sign(self.__tf - self.__t0):
             dt0 = -dt0
-        self._dt = torch.full((n,), dt0, dtype=torch.float64, device=dev)
-        self.accepted = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.rejected = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.status = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        return dt0
+
+    def _reset_state(self):
+        """Back to (t0, y0, dt0) with zero counters.  Only allocates; the fills happen in `_materialize()` or, for
+        a fused run, inside the kernel."""
+        torch = _torch()
+        n, dev = self.n_traj, self.device
+        if getattr(self, "_raw_y", None) is None:
+            self._raw_y = torch.empty_like(self._y0)
+            self._raw_t = torch.empty((n,), dtype=torch.float64, device=dev)
+            self._raw_dt = torch.empty((n,), dtype=torch.float64, device=dev)
+            self._raw_accepted = torch.empty(n, dtype=torch.int32, device=dev)
+            self._raw_rejected = torch.empty(n, dtype=torch.int32, device=dev)
+            self._raw_status = torch.empty(n, dtype=torch.int32, device=dev)
+            self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        self._pristine = True
+        self._stats = None
         self._hist_y = [self._y0]                         # row 0 = initial condition (never written to)
-        self._hist_t = [self._t.clone()]
+        self._hist_t = [self.__t0]                        # scalars stand for "every trajectory at this time"
         self._nodes = None
         self._node_count = None
+
+    def _materialize(self):
+        if self.__dict__.get("_pristine"):
+            self._pristine = False
+            if self.host_io:
+                self._host_done = False
+            self._raw_y.copy_(self._y0)
+            self._raw_t.fill_(self.__t0)
+            self._raw_dt.fill_(self._initial_dt())
+            self._raw_accepted.zero_()
+            self._raw_rejected.zero_()
+            self._raw_status.zero_()
+
+    def _hist_time(self, row):
+        torch = _torch()
+        if isinstance(row, float):
+            row = torch.full((self.n_traj,), row, dtype=torch.float64, device="cpu" if self.host_io else self.device)
+        return row
 
     def _fix_dt_dir(self, t1, t0):
         torch = _torch()
@@ -259,13 +367,15 @@ class OdeSystem(object):
     @property
     def t(self):
         torch = _torch()
-        return torch.stack([self._user_time(r) for r in self._hist_t])
+        return torch.stack([self._user_time(self._hist_time(r)) for r in self._hist_t])
 
     @property
     def nfev(self):
         """Right-hand-side evaluations in the reference's accounting, summed over the ensemble:
         per trajectory 1 (constructor) + 1 (first initial_rhs) + (S+1) per attempt
         (S per attempt for FSAL schemes); SURVEY.md fact 5."""
+        if self.__dict__.get("_pristine"):
+            return self.n_traj
         att = int((self.accepted.sum() + self.rejected.sum()).item())
         if att == 0:
             return self.n_traj
@@ -276,6 +386,20 @@ class OdeSystem(object):
     @property
     def njev(self):
         return 0
+
+    @property
+    def stats(self):
+        """Ensemble totals since the last reset: step attempts, accepted steps, trajectories that failed the
+        tolerances, trajectories still short of tf.  After a fused run they come from the kernel's own counters
+        (no reduction launches); otherwise from the per-trajectory tensors."""
+        if self.__dict__.get("_pristine"):
+            return dict(attempts=0, accepted=0, failed=0, running=0)
+        if self._stats is not None:
+            return dict(self._stats)
+        acc = int(self.accepted.sum().item())
+        return dict(attempts=acc + int(self.rejected.sum().item()), accepted=acc,
+                    failed=int((self.status == cb.TRAJ_TOL_FAIL).sum().item()),
+                    running=int((self.status == cb.TRAJ_RUNNING).sum().item()))
 
     @property
     def constants(self):
@@ -451,20 +575,103 @@ class OdeSystem(object):
         self._counters.zero_()
         a = cb.ErkRunArgs()
         a.n = self.n_traj
-        a.y, a.t, a.dt = self._y.data_ptr(), self._t.data_ptr(), self._dt.data_ptr()
+        if self._pristine and first_call:
+            # pristine state (constructor / reset()): the kernel reads y0 directly, starts every trajectory at
+            # (t0, dt0) with zero counters and overwrites t, dt, accepted, rejected, status -- no fill launches
+            self._pristine = False
+            a.fresh, a.t_init, a.dt_init = 1, self.__t0, self._initial_dt()
+            a.y_init = self._y0.data_ptr()
+        a.y, a.t, a.dt = self._raw_y.data_ptr(), self._raw_t.data_ptr(), self._raw_dt.data_ptr()
         for i, (p, s) in enumerate(zip(params, strides)):
             a.params[i] = p.data_ptr()
             a.param_stride[i] = s
         a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
-        a.accepted, a.rejected, a.status = self.accepted.data_ptr(), self.rejected.data_ptr(), self.status.data_ptr()
+        a.accepted, a.rejected, a.status = (self._raw_accepted.data_ptr(), self._raw_rejected.data_ptr(),
+                                            self._raw_status.data_ptr())
         a.max_steps = int(max_steps)
         a.first_call = 1 if first_call else 0
         if self._nodes is not None:
             a.nodes, a.node_count, a.node_capacity = self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity
         a.counters = self._counters.data_ptr()
+        ev = self.__dict__.get("_kernel_events")          # optional (start, end) CUDA events bracketing the launch
+        if ev:
+            ev[0].record()
         handle.run(a, cb.current_stream_ptr(self.device))
+        if ev:
+            ev[1].record()
         self._launches += 1
         self._keepalive = params
+
+    def _run_host_pipeline(self, tf, plugin):
+        """host_io=True: the ensemble is cut into `host_chunks` contiguous pieces; piece c is uploaded on a copy
+        stream, integrated by its own dsb_erk_run launch (pointers offset into the [dim][N] staging buffers,
+        `stride` = N, `fresh` = 1 so there is no fill launch) on one of two compute streams, and downloaded on a third
+        stream.  Upload of piece c+1, kernel of piece c and download of piece c-1 overlap; two compute streams
+        let the next kernel's blocks move in while the previous kernel's last trajectories drain."""
+        torch = _torch()
+        integ = self.integrator
+        pid, names, defaults = plugin
+        n, dev = self.n_traj, self.device
+        handle = cb.erk_handle(dev.index or 0, pid, self.numel, integ.tableau_intermediate, integ.tableau_final,
+                               integ.order, strict=self.strict)
+        params, strides = self._param_tensors(names, defaults)
+        chunks = max(1, min(self.host_chunks, n // 1024 if n >= 1024 else 1))
+        bounds = [((n * c // chunks) // 32) * 32 for c in range(chunks)] + [n]
+        if self._pipe_streams is None:
+            self._pipe_streams = tuple(torch.cuda.Stream(device=dev) for _ in range(4))
+        up, down, comp0, comp1 = self._pipe_streams
+        cur = torch.cuda.current_stream(dev)
+        self._counters.zero_()
+        for st in (up, comp0, comp1):
+            st.wait_stream(cur)
+        t0, dt0 = self.t0, self._initial_dt()
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi <= lo:
+                continue
+            with torch.cuda.stream(up):
+                for d in range(self.numel):
+                    self._dev_y[d, lo:hi].copy_(self._y0[d, lo:hi], non_blocking=True)
+                uploaded = up.record_event()
+            comp = comp0 if c % 2 == 0 else comp1
+            comp.wait_event(uploaded)
+            a = cb.ErkRunArgs()
+            a.n, a.stride = hi - lo, n
+            a.y = self._dev_y.data_ptr() + 8 * lo
+            a.t, a.dt = self._raw_t.data_ptr() + 8 * lo, self._raw_dt.data_ptr() + 8 * lo
+            for i, (p, sp) in enumerate(zip(params, strides)):
+                a.params[i] = p.data_ptr() + 8 * lo * sp
+                a.param_stride[i] = sp
+            a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+            a.accepted = self._dev_accepted.data_ptr() + 4 * lo
+            a.rejected = self._dev_rejected.data_ptr() + 4 * lo
+            a.status = self._dev_status.data_ptr() + 4 * lo
+            a.max_steps, a.first_call = int(self._step_cap), 1
+            a.fresh, a.t_init, a.dt_init = 1, t0, dt0
+            a.counters = self._counters.data_ptr() + 64 * c
+            handle.run(a, C.c_void_p(comp.cuda_stream))
+            self._launches += 1
+            integrated = comp.record_event()
+            down.wait_event(integrated)
+            with torch.cuda.stream(down):
+                for d in range(self.numel):
+                    self._raw_y[d, lo:hi].copy_(self._dev_y[d, lo:hi], non_blocking=True)
+                self._raw_accepted[lo:hi].copy_(self._dev_accepted[lo:hi], non_blocking=True)
+                self._raw_rejected[lo:hi].copy_(self._dev_rejected[lo:hi], non_blocking=True)
+                self._raw_status[lo:hi].copy_(self._dev_status[lo:hi], non_blocking=True)
+        for st in (down, comp0, comp1):
+            cur.wait_stream(st)
+        self._keepalive = params
+        self._pristine = False
+        self._host_done = True
+        c = self._counters.cpu().reshape(-1, 8)[:chunks]          # synchronises: every copy above has landed
+        return int(c[:, 2].sum()), int(c[:, 3].sum()), int(c[:, 4].sum()), int(c[:, 5].sum())
+
+    def _fused_stats(self):
+        """(attempts, accepted, failed, running) of the last dsb_erk_run, from the kernel's own counters: ONE
+        64-byte device-to-host copy instead of reductions over the per-trajectory arrays."""
+        c = self._counters.cpu()
+        return int(c[2]), int(c[3]), int(c[4]), int(c[5])
 
     def _run_stagewise(self, tf, callbacks, bar):
         """Generic right-hand side: the user's torch callable is evaluated between the fused stage
@@ -730,7 +937,12 @@ class OdeSystem(object):
         else:
             callbacks = [callback]
         plugin = self._fused_plugin() if self.use_fused else None
+        fused_stats = None
         try:
+            if self.host_io and (plugin is None or self.integrator.symplectic):
+                raise NotImplementedError("host_io=True needs an explicit Runge-Kutta method with a fused kernel")
+            if self.integrator.symplectic or plugin is None:
+                self._stats = None
             if self.integrator.symplectic:
                 bar = None
                 if eta:
@@ -747,30 +959,49 @@ class OdeSystem(object):
                 self._run_stagewise(tf, callbacks, bar)
                 if bar is not None:
                     bar.close()
+            elif self.host_io:
+                if callbacks or eta or self.__dense_output or not self.__dict__.get("_pristine"):
+                    raise NotImplementedError("host_io=True systems integrate once per reset(), without callbacks, "
+                                              "progress bar or dense output")
+                fused_stats = self._run_host_pipeline(tf, plugin)
             elif not callbacks and not eta:
                 self._run_fused(tf, plugin, self._step_cap, first_call=True)
+                fused_stats = self._fused_stats()
             else:
                 first = True
                 bar = None
                 if eta:
                     from tqdm.auto import tqdm
                     bar = tqdm(total=None)
+                fused_stats = (0, 0, 0, 0)
                 while True:
                     self._run_fused(tf, plugin, self.callback_every, first_call=first)
                     first = False
+                    st = self._fused_stats()
+                    fused_stats = (fused_stats[0] + st[0], fused_stats[1] + st[1], st[2], st[3])
                     for cbk in callbacks:
                         cbk(self)
                     if bar is not None:
                         bar.update()
-                    if not bool((self.status == cb.TRAJ_RUNNING).any().item()):
+                    if st[3] == 0:
                         break
                 if bar is not None:
                     bar.close()
-            self._hist_y.append(self._y.clone())
-            self._hist_t.append(self._t.clone())
+            if self.host_io:
+                self._hist_y.append(self._raw_y)              # the pinned result buffer itself (no 25 MB host copy)
+                self._hist_t.append(float(tf) if fused_stats[2] + fused_stats[3] == 0 else self._raw_t.cpu())
+            else:
+                self._hist_y.append(self._y.clone())
+                self._hist_t.append(self._t.clone())
             # error policy: run everything to completion, then raise like the reference does
             # (:1089-1093 wraps integrator_types.py:220-224) if any trajectory failed
-            n_fail = int((self.status == cb.TRAJ_TOL_FAIL).sum().item())
+            if fused_stats is not None:
+                prev = self._stats or dict(attempts=0, accepted=0)
+                self._stats = dict(attempts=prev["attempts"] + fused_stats[0], accepted=prev["accepted"] + fused_stats[1],
+                                   failed=fused_stats[2], running=fused_stats[3])
+                n_fail = fused_stats[2]
+            else:
+                n_fail = int((self.status == cb.TRAJ_TOL_FAIL).sum().item())
             if n_fail:
                 cause = etypes.FailedToMeetTolerances(
                     "Failed to integrate {} of {} trajectories to the tolerances required: rtol={}, atol={}".format(
@@ -796,7 +1027,8 @@ class OdeSystem(object):
         if isinstance(index, int):
             if index >= len(self._hist_y) or index < -len(self._hist_y):
                 raise IndexError("index {} out of bounds for integrations with {} steps".format(index, len(self._hist_y)))
-            return StateTuple(t=self._user_time(self._hist_t[index]), y=self._user_shape(self._hist_y[index]), event=None)
+            return StateTuple(t=self._user_time(self._hist_time(self._hist_t[index])),
+                              y=self._user_shape(self._hist_y[index]), event=None)
         if isinstance(index, slice):
             return StateTuple(t=self.t[index], y=self.y[index], event=None)
         if self.__dense_output and self._nodes is not None:

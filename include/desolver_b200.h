@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSB_ABI_VERSION 1
+#define DSB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DSB_API __attribute__((visibility("default")))
@@ -100,7 +100,19 @@ typedef struct {
     double *nodes;             /* [n][node_capacity][1 + 2*dim]                                */
     int32_t *node_count;       /* [n] in/out                                                   */
     int32_t node_capacity;
-    uint64_t *counters;        /* device, >= 4 words, zeroed by the caller: [0] work queue     */
+    uint64_t *counters;        /* device, >= 8 words, zeroed by the caller: [0] work queue; on return
+                                  [2] += step attempts of this call, [3] += accepted steps,
+                                  [4] += trajectories left in DSB_TRAJ_TOL_FAIL, [5] += in DSB_TRAJ_RUNNING  */
+    /* ---- ABI 2 ---- */
+    int64_t stride;            /* leading dimension of y / y_init in elements (0: n).  A caller that streams
+                                  an ensemble through the device in chunks passes pointers offset into one
+                                  [dim][stride] allocation and n = the chunk length                          */
+    const double *y_init;      /* [dim][stride] initial state read INSTEAD of y (NULL: y is in/out); y is
+                                  then write-only, so re-running from the same y0 needs no reset copy      */
+    double t_init, dt_init;    /* with fresh != 0: every trajectory starts at (t_init, dt_init)            */
+    int32_t fresh;             /* != 0: t, dt, accepted, rejected, status are uninitialised outputs: the
+                                  kernel starts from (t_init, dt_init) with zero counts and overwrites them
+                                  (reference: OdeSystem.__init__/reset, differential_system.py:520-528,900-910) */
 } dsb_erk_run_args;
 
 DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);

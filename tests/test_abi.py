@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in syms:
         assert hasattr(lib, name), "missing export %s" % name
     info = cb.lib().dsb_build_info().decode()
-    assert "sm_100a" in info and cb.lib().dsb_abi_version() == 1
+    assert "sm_100a" in info and cb.lib().dsb_abi_version() == cb.ABI_VERSION == 2
 
 
 def test_ctypes_struct_matches_header_layout():
@@ -37,7 +37,33 @@ def test_ctypes_struct_matches_header_layout():
     assert a.n.offset == 0 and a.y.offset == 8 and a.params.offset == 32
     assert a.param_stride.offset == 32 + 8 * cb.MAX_PARAMS
     assert a.tf.offset == 32 + 16 * cb.MAX_PARAMS
-    assert a.counters.offset + 8 == ctypes.sizeof(a)
+    assert a.stride.offset == a.counters.offset + 8
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """Every ctypes mirror has the size and field offsets gcc gives the struct in include/desolver_b200.h."""
+    import subprocess
+    from desolver_b200.backend import cuda_backend as cb
+    pairs = {"dsb_erk_run_args": cb.ErkRunArgs, "dsb_erk_stage_args": cb.ErkStageArgs,
+             "dsb_symp_run_args": cb.SympRunArgs, "dsb_symp_stage_args": cb.SympStageArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "desolver_b200.h"', 'int main(void){']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line in filter(None, out):
+        cname, fname, val = line.split()
+        cls = pairs[cname]
+        if fname == "sizeof":
+            assert ctypes.sizeof(cls) == int(val), line
+        else:
+            assert getattr(cls, fname).offset == int(val), line
 
 
 def test_bad_arguments_are_reported_without_a_gpu():
