@@ -151,15 +151,17 @@ __device__ __forceinline__ double corr_term(double x, double order, int order_p)
     return pow(x, -0.5 / order);
 }
 
-// resident blocks per SM: 7 (<=72 registers; measured best for Cash-Karp x dim 3; 8 for dim 2), 4 (<=128) while the stage
-// derivatives fit, else 2 (<=255)
+// resident blocks per SM: 6 (<=80 registers, no spill in the hot loop; measured best for Cash-Karp x dim 3 since the
+// factor table shortened the controller: 3.68 ms against 3.79 ms at 7 blocks / 72 registers), 7 for dim 2 (Van der Pol 2^24: 40.7 ms against 43.9 ms at 8 and
+// 42.1 ms at 6), 4 (<=128)
+// while the stage derivatives fit, else 2 (<=255)
 template <class Rhs, int S>
 constexpr int erk_min_blocks()
 {
 #ifdef DSB_ERK_MIN_BLOCKS
     return DSB_ERK_MIN_BLOCKS;
 #else
-    return (S * Rhs::DIM <= 12) ? 8 : ((S * Rhs::DIM <= 18) ? 7 : ((S * Rhs::DIM <= 21) ? 4 : 2));
+    return (S * Rhs::DIM <= 12) ? 7 : ((S * Rhs::DIM <= 18) ? 6 : ((S * Rhs::DIM <= 21) ? 4 : 2));
 #endif
 }
 
