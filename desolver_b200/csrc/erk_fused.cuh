@@ -28,7 +28,11 @@ namespace dsb {
 #ifndef DSB_ERK_THREADS
 #define DSB_ERK_THREADS 128
 #endif
+#ifndef DSB_ERK_REFILL_BATCH
+#define DSB_ERK_REFILL_BATCH 4
+#endif
 constexpr int ERK_THREADS = DSB_ERK_THREADS;
+constexpr int REFILL_BATCH = DSB_ERK_REFILL_BATCH;   // lanes of a warp that must be waiting before the warp stores + refills
 
 template <int S>
 struct ErkKernelArgs {
@@ -294,10 +298,11 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             } else {
                 h = h0 >= 0.0 ? fmin(new_dt, h0) : -fmin(fabs(new_dt), fabs(h0));
             }
-        } else if (live && done) {
+        }
+        if (!live && done) {                                             // finished earlier, result still in registers
             bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
             store(more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE);
-            live = false;
+            done = false;
         }
         // refill idle lanes from the queue (warp-aggregated atomicAdd); a loaded trajectory that has nothing to
         // do (already at tf, failed earlier) is stored at once and the lane asks again
@@ -408,7 +413,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     if constexpr (Tab::template use_db<j>()) se = fma(k[j][d], tab.template db<j>(), se);
                 });
                 dY[d] = tab.fsal() ? dlast[d] : sb;                    // non-FSAL: the commit does y = fma(h, sb, y)
-                err[d] = h * se;
+                err[d] = se;                                           // the factor h enters the norm once: x = h^2 * sum(..)
                 slope[d] = sb;                                         // = dY/h to rounding
             }
         }
@@ -430,6 +435,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 double q = STRICT ? err[d] / tol : fm::quick_div(err[d], tol);
                 x = (d == 0) ? __dmul_rn(q, q) : fma(q, q, x);        // OpenBLAS ddot: FMA chain
             }
+            if (!STRICT) x *= h * h;                                   // fast flavour: err[d] above is the estimate / h
             // retry chains (:76-90): corr of this attempt times the history; lanes on a first attempt skip it
             auto retry_corr = [&](double c_cur) -> double {
                 if (trial == 1) return A::mul(c_cur, corr_first);      // 2nd attempt: two-term product (:76-79)
@@ -482,7 +488,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 #pragma unroll
                     for (int i = 0; i < (ft::DEG + 1) / 2; ++i) { double2 v = __ldg(e + i); cf[2 * i] = v.x; cf[2 * i + 1] = v.y; }
                     f = ft::horner(cf, dx);
-                    if (!in_tab && !deep) {
+                    if (!in_tab && !deep && live) {
                         // xe outside [2^-100, 2^28), zero, inf or nan.  For trial == 1 the two-term product is formed
                         // from the factors so that an overflowing / underflowing xe cannot change the result class.
                         corr = corr_term<STRICT>(x, tab.order(), tab.order_p());
@@ -503,7 +509,6 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         }
 
         // ------------------------------------------------------------ accept: commit and start the next step
-        done = false;
         if (live && !redo) {
 #pragma unroll
             for (int d = 0; d < D; ++d)
@@ -520,9 +525,15 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             start_step();
             done = !((dt != 0.0) && (fabs(tf - t) >= DSB_KC(eps32, DSB_EPS32)))               // :996
                    || acc >= step_budget;
+            live = !done;
         }
         // ------------------------------------------------------------ rare events: reject, finish, refill
-        if (__any_sync(FULL, live ? (redo || done) : !exhausted)) {
+        // A finished lane keeps its result in registers (its further arithmetic is discarded) until REFILL_BATCH
+        // lanes of the warp need service, a lane rejected, or the queue is empty: the store + refill pass costs the
+        // whole warp ~250 instructions, and trajectories that start together take their first-step retry chain
+        // (dt0 is usually too large: two rejections, i.e. the expensive three-term branch) in the same iterations.
+        const unsigned svc = __ballot_sync(FULL, !live && (done || !exhausted));
+        if (__any_sync(FULL, live && redo) || __popc(svc) >= REFILL_BATCH || (exhausted && svc != 0u)) {
             if (!event_path()) break;
         }
     }
