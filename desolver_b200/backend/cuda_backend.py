@@ -40,6 +40,22 @@ class ErkRunArgs(C.Structure):
         ("y_init", C.c_void_p),
         ("t_init", C.c_double), ("dt_init", C.c_double),
         ("fresh", C.c_int32),
+        ("done_shift", C.c_int32),
+        ("avail", C.c_void_p),
+        ("done", C.c_void_p),
+    ]
+
+
+class ErkHostArgs(C.Structure):
+    """dsb_erk_host_args (include/desolver_b200.h)."""
+    _fields_ = [
+        ("run", ErkRunArgs),
+        ("host_y0", C.c_void_p), ("host_y", C.c_void_p),
+        ("host_accepted", C.c_void_p), ("host_rejected", C.c_void_p), ("host_status", C.c_void_p),
+        ("host_stride", C.c_int64),
+        ("chunk_shift", C.c_int32),
+        ("flags", C.c_void_p),
+        ("stream_up", C.c_void_p), ("stream_down", C.c_void_p),
     ]
 
 
@@ -135,6 +151,8 @@ def lib():
     L.dsb_erk_destroy.argtypes = [C.c_void_p]
     L.dsb_erk_run.restype = C.c_int
     L.dsb_erk_run.argtypes = [C.c_void_p, C.POINTER(ErkRunArgs), C.c_void_p]
+    L.dsb_erk_run_host.restype = C.c_int
+    L.dsb_erk_run_host.argtypes = [C.c_void_p, C.POINTER(ErkHostArgs), C.c_void_p]
     L.dsb_erk_run_launches.restype = C.c_int
     L.dsb_erk_run_launches.argtypes = [C.c_void_p]
     L.dsb_dense_eval.restype = C.c_int
@@ -203,6 +221,14 @@ class ErkHandle:
 
     def run(self, args, stream_ptr):
         check(lib().dsb_erk_run(self._h, C.byref(args), stream_ptr), "dsb_erk_run")
+
+    def run_host(self, args, stream_ptr):
+        """dsb_erk_run_host; returns False when the driver lacks stream memory operations (caller falls back)."""
+        status = lib().dsb_erk_run_host(self._h, C.byref(args), stream_ptr)
+        if status == DSB_ERR_UNSUPPORTED:
+            return False
+        check(status, "dsb_erk_run_host")
+        return True
 
     def stage_begin(self, args, first_call, stream_ptr):
         check(lib().dsb_erk_stage_begin(self._h, C.byref(args), 1 if first_call else 0, stream_ptr), "dsb_erk_stage_begin")

@@ -23,6 +23,7 @@ int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n,
                       const double *tq, int64_t tq_stride, double *out, cudaStream_t stream);
 int launch_dense_append(double *nodes, int32_t *node_count, int32_t cap, int64_t n, int32_t dim, const double *t,
                         const double *y, const double *f, const int32_t *flags, int32_t mask, cudaStream_t stream);
+int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream);
 int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
 int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream);
 int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream);
@@ -112,6 +113,8 @@ int dsb_erk_destroy(dsb_erk_handle h)
     if (h->d_atan) cudaFree(h->d_atan);
     if (h->d_tab) cudaFree(h->d_tab);
     if (h->d_factor) cudaFree(h->d_factor);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     delete h;
     return DSB_OK;
 }
@@ -138,6 +141,12 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
     }
     if (a->n == 0) return DSB_OK;
     return h->fused_launch(h, a, (cudaStream_t)stream);
+}
+
+int dsb_erk_run_host(dsb_erk_handle h, const dsb_erk_host_args *a, void *stream)
+{
+    if (!h || !a) { set_error("dsb_erk_run_host: null handle or args"); return DSB_ERR_BAD_ARGUMENT; }
+    return run_host(h, a, (cudaStream_t)stream);
 }
 
 int dsb_erk_run_launches(dsb_erk_handle h) { return (h && h->fused_launch) ? 1 : 0; }

@@ -210,7 +210,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 
     // ---- per-lane trajectory state (registers) ----
     long long idx = 0;
-    bool live = false, exhausted = false, final_step = false;
+    bool live = false, exhausted = false, final_step = false, gave_up = false;
     double y[D], prm[NP > 0 ? NP : 1], k[S][D], scale[D];
     double t = 0.0, dt = 0.0, h = 0.0, h0 = 0.0;
     double corr_first = 1.0, x_last = 1.0, x_last_last = 1.0;
@@ -234,6 +234,15 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         s_acc[threadIdx.x] += (unsigned long long)acc;
         s_fail[threadIdx.x] += st == (int)DSB_TRAJ_TOL_FAIL;
         s_run[threadIdx.x] += st == (int)DSB_TRAJ_RUNNING;
+        if (P.a.done) {
+            // dsb_erk_run_host: a download stream waits for "every trajectory of this chunk is stored"
+#ifdef DSB_DONE_FENCE_SYSTEM
+            __threadfence_system();
+#else
+            __threadfence();          // results and counter both live in device memory: L2 is the coherence point of
+#endif                                // the SMs, the stream wait and the copy engine
+            atomicAdd(P.a.done + (idx >> P.a.done_shift), 1u);
+        }
     };
     // per-warp totals -> counters[2..5] (one atomic per statistic per warp, at warp exit)
     auto flush_stats = [&]() {
@@ -314,7 +323,32 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             if (lane == 0) base = atomicAdd((unsigned long long *)P.a.counters, (unsigned long long)cnt);
             base = __shfl_sync(FULL, base, 0);
             exhausted = (long long)(base + cnt) >= n;
+            bool abandon = false;
+            if (P.a.avail && (long long)base < n) {
+                // dsb_erk_run_host: the initial states arrive chunk by chunk while this kernel runs; wait (bounded:
+                // ~2 s) until everything this warp just claimed is resident.  After a time-out the warp keeps
+                // claiming and counts the abandoned trajectories as done, so that no download stream waits forever;
+                // counters[6] tells the host.
+                const unsigned want = (unsigned)((long long)(base + cnt) < n ? (long long)(base + cnt) : n);
+                if (lane == 0 && !gave_up) {
+                    unsigned have;
+                    long long spins = 0;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(P.a.avail) : "memory");
+                        if (have >= want) break;
+                        if (++spins > 4000000) { gave_up = true; break; }
+                        __nanosleep(500);
+                    }
+                    if (gave_up) atomicExch((unsigned long long *)P.a.counters + 6, 1ull);
+                }
+                gave_up = __shfl_sync(FULL, gave_up ? 1 : 0, 0) != 0;
+                abandon = gave_up;
+            }
             long long mine = (long long)base + __popc(need & ((1u << lane) - 1u));
+            if (abandon) {
+                if (!live && mine < n && P.a.done) atomicAdd(P.a.done + (mine >> P.a.done_shift), 1u);
+                continue;
+            }
             if (!live && mine < n) {
                 idx = mine;
 #pragma unroll

@@ -17,6 +17,7 @@ struct dsb_erk_plan {
     bool fused_static = false;           // compile-time tableau variant selected
     double2 *d_atan = nullptr;           // device copy of the atan reduction table
     double *d_tab = nullptr;             // device copy of the flat tableau for the stage-level kernels
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;   // dsb_erk_run_host: fork / join of the copy streams
     dsb::ft::Entry *d_factor = nullptr;  // device copy of the step-size factor table (factor_table.h), adaptive only
     // type-erased fused launcher (nullptr: no fused kernel for this rhs/method)
     int (*fused_launch)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;

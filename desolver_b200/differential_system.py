@@ -156,7 +156,7 @@ class OdeSystem(object):
     status = _state_property("status")
 
     def __init__(self, equ_rhs, y0, t=(0, 1), dense_output=False, dt=1.0, rtol=None, atol=None, constants=dict(),
-                 ensemble=False, device=None, dense_capacity=None, strict=False, host_io=False, host_chunks=4,
+                 ensemble=False, device=None, dense_capacity=None, strict=False, host_io=False, host_chunks=16,
                  host_out=None):
         torch = _torch()
         if len(t) != 2:
@@ -286,7 +286,9 @@ class OdeSystem(object):
         self._dev_rejected = torch.empty(n, dtype=torch.int32, device=dev)
         self._dev_status = torch.empty(n, dtype=torch.int32, device=dev)
         self._counters = torch.zeros(8 * max(1, self.host_chunks), dtype=torch.int64, device=dev)
+        self._pipe_flags = torch.zeros(2 + max(1, self.host_chunks) * 2, dtype=torch.int32, device=dev)
         self._pipe_streams = None
+        self.host_pipeline = "streamed"      # "chunked": one dsb_erk_run launch per chunk (fallback without stream mem-ops)
 
     def _fused_plugin_tag(self):
         rhs = self.equ_rhs
@@ -622,6 +624,40 @@ class OdeSystem(object):
         up, down, comp0, comp1 = self._pipe_streams
         cur = torch.cuda.current_stream(dev)
         self._counters.zero_()
+        if self.host_pipeline == "streamed":
+            # ONE persistent launch; the library overlaps the chunked uploads / downloads with it through stream
+            # memory operations (dsb_erk_run_host)
+            shift = max(10, int(np.ceil(np.log2(max(1, -(-n // max(1, self.host_chunks)))))))
+            if self._pipe_flags.numel() < 2 + (-(-n // (1 << shift))):
+                self._pipe_flags = torch.zeros(2 + (-(-n // (1 << shift))), dtype=torch.int32, device=dev)
+            ha = cb.ErkHostArgs()
+            a = ha.run
+            a.n, a.stride = n, n
+            a.y, a.t, a.dt = self._dev_y.data_ptr(), self._raw_t.data_ptr(), self._raw_dt.data_ptr()
+            for i, (p, sp) in enumerate(zip(params, strides)):
+                a.params[i], a.param_stride[i] = p.data_ptr(), sp
+            a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+            a.accepted, a.rejected, a.status = (self._dev_accepted.data_ptr(), self._dev_rejected.data_ptr(),
+                                                self._dev_status.data_ptr())
+            a.max_steps, a.first_call = int(self._step_cap), 1
+            a.fresh, a.t_init, a.dt_init = 1, self.t0, self._initial_dt()
+            a.counters = self._counters.data_ptr()
+            ha.host_y0, ha.host_y = self._y0.data_ptr(), self._raw_y.data_ptr()
+            ha.host_accepted, ha.host_rejected, ha.host_status = (self._raw_accepted.data_ptr(), self._raw_rejected.data_ptr(),
+                                                                  self._raw_status.data_ptr())
+            ha.host_stride, ha.chunk_shift = n, shift
+            ha.flags = self._pipe_flags.data_ptr()
+            ha.stream_up, ha.stream_down = up.cuda_stream, down.cuda_stream
+            if handle.run_host(ha, C.c_void_p(cur.cuda_stream)):
+                self._launches += 1
+                self._keepalive = params
+                self._pristine = False
+                self._host_done = True
+                c = self._counters.cpu()                      # synchronises `cur`, which waited for the download stream
+                if int(c[6]):
+                    raise RuntimeError("dsb_erk_run_host: the kernel timed out waiting for its initial states")
+                return int(c[2]), int(c[3]), int(c[4]), int(c[5])
+            self.host_pipeline = "chunked"                    # driver without stream memory operations
         for st in (up, comp0, comp1):
             st.wait_stream(cur)
         t0, dt0 = self.t0, self._initial_dt()

@@ -113,9 +113,41 @@ typedef struct {
     int32_t fresh;             /* != 0: t, dt, accepted, rejected, status are uninitialised outputs: the
                                   kernel starts from (t_init, dt_init) with zero counts and overwrites them
                                   (reference: OdeSystem.__init__/reset, differential_system.py:520-528,900-910) */
+    /* flow control of a launch that overlaps its own uploads / downloads (set by dsb_erk_run_host) */
+    int32_t done_shift;        /* done[i >> done_shift] counts the stored trajectories of block i >> done_shift */
+    const uint32_t *avail;     /* device word (NULL: off): the initial state of trajectories [0, *avail) is resident;
+                                  the kernel waits, bounded, before it loads a trajectory beyond it; a wait that
+                                  times out sets counters[6] = 1 and abandons the remaining trajectories       */
+    uint32_t *done;            /* device words (NULL: off), zeroed by the caller, see done_shift                  */
 } dsb_erk_run_args;
 
 DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);
+
+/* The same integration for an ensemble that lives in HOST memory (the reference keeps the state wherever y0
+ * lives, differential_system.py:507-515): ONE persistent launch whose uploads and downloads overlap it.
+ *   stream_up  : per chunk of 2^chunk_shift trajectories, cudaMemcpy2DAsync(host_y0 -> run.y) followed by a
+ *                stream memory operation that publishes the resident count in flags[0];
+ *   stream     : the kernel (run.avail = flags, run.done = flags + 1): a lane takes the next trajectory of the
+ *                queue as soon as its initial state is resident, and counts stored results per chunk;
+ *   stream_down: per chunk, a stream wait on flags[1 + c] == chunk length, then the device-to-host copies of the
+ *                chunk's final state and counters.
+ * `stream` finally waits for stream_down, so synchronising it means every result has landed.  No host
+ * synchronisation inside.  `run` must describe device staging buffers with fresh = 1 and y_init = NULL; host
+ * buffers should be pinned (pageable memory works but serialises).  Needs stream memory operations
+ * (cuStreamWriteValue32 / cuStreamWaitValue32): DSB_ERR_UNSUPPORTED if the driver does not provide them -- the
+ * caller then falls back to chunked dsb_erk_run launches. */
+typedef struct {
+    dsb_erk_run_args run;
+    const double *host_y0;     /* [dim][host_stride]                                            */
+    double *host_y;            /* [dim][host_stride] out                                        */
+    int32_t *host_accepted, *host_rejected, *host_status;   /* [n] out                          */
+    int64_t host_stride;       /* leading dimension of host_y0 / host_y in elements (0: n)      */
+    int32_t chunk_shift;       /* chunk = 2^chunk_shift trajectories                            */
+    uint32_t *flags;           /* device, >= 1 + ceil(n / 2^chunk_shift) words (zeroed here)    */
+    void *stream_up, *stream_down;
+} dsb_erk_host_args;
+
+DSB_API int dsb_erk_run_host(dsb_erk_handle h, const dsb_erk_host_args *args, void *stream);
 /* number of kernel launches dsb_erk_run issues per call (for bench accounting) */
 DSB_API int dsb_erk_run_launches(dsb_erk_handle h);
 

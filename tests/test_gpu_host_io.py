@@ -52,8 +52,9 @@ def test_reset_and_rerun_is_bitwise_and_stats_match_counters():
     assert torch.equal(a[-1].y, c[-1].y) and torch.equal(a.accepted, c.accepted)
 
 
-@pytest.mark.parametrize("n,chunks", [(20000, 4), (4099, 3), (1000, 4), (65536, 8)])
-def test_host_io_pipeline_matches_device_run_bitwise(n, chunks):
+@pytest.mark.parametrize("mode", ["streamed", "chunked"])
+@pytest.mark.parametrize("n,chunks", [(20000, 4), (4099, 3), (1000, 4), (65536, 8), (300000, 16)])
+def test_host_io_pipeline_matches_device_run_bitwise(n, chunks, mode):
     de = _de()
     y0 = de.benchmarks.lorenz_ensemble(n, seed=7)
     a = _device_run(y0)
@@ -61,8 +62,10 @@ def test_host_io_pipeline_matches_device_run_bitwise(n, chunks):
     h = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned, t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True,
                      host_io=True, host_chunks=chunks)
     h.method = "RK45"
+    h.host_pipeline = mode         # "streamed": one launch + stream memory operations; "chunked": one launch per chunk
     for rep in range(2):                             # second pass: reset() + integrate() reuses every buffer
         h.integrate()
+        assert h.host_pipeline == mode
         assert not h[-1].y.is_cuda and h[-1].y.is_pinned()
         assert np.array_equal(h[-1].y.numpy(), a[-1].y.cpu().numpy())
         assert np.array_equal(h.accepted.numpy(), a.accepted.cpu().numpy())
