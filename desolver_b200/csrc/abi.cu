@@ -81,7 +81,7 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     case DSB_RHS_SHO:    fused = dim == 2 && select_fused_sho(p); break;
     default: break;
     }
-    if (!fused) p->fused_launch = nullptr;
+    if (!fused) p->fused_launch = p->fused_launch_flow = nullptr;
 
     double2 host_tab[fm::ATAN_TABLE_SIZE];
     fm::build_atan_table(host_tab);

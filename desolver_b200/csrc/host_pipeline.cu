@@ -43,8 +43,9 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
 {
     const dsb_erk_run_args &r = a->run;
     const int64_t n = r.n;
-    if (!h->fused_launch) {
-        set_error("dsb_erk_run_host: no fused kernel for rhs_id=%d dim=%d stages=%d", h->rhs_id, h->dim, h->stages);
+    if (!h->fused_launch_flow) {
+        set_error("dsb_erk_run_host: no flow-controlled fused kernel for rhs_id=%d dim=%d stages=%d flags=%u (fast "
+                  "flavour, <= 7 stages); use chunked dsb_erk_run launches", h->rhs_id, h->dim, h->stages, h->flags);
         return DSB_ERR_UNSUPPORTED;
     }
     if (n < 0 || n > 0x7fffffffLL || !r.y || !r.t || !r.dt || !r.counters || !r.accepted || !r.rejected || !r.status ||
@@ -91,7 +92,7 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
             run.avail = a->flags;
             run.done = a->flags + 1;
             run.done_shift = a->chunk_shift;
-            status = h->fused_launch(h, &run, stream);
+            status = h->fused_launch_flow(h, &run, stream);
             if (status != DSB_OK) return status;
         }
     }

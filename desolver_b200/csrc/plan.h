@@ -21,6 +21,8 @@ struct dsb_erk_plan {
     dsb::ft::Entry *d_factor = nullptr;  // device copy of the step-size factor table (factor_table.h), adaptive only
     // type-erased fused launcher (nullptr: no fused kernel for this rhs/method)
     int (*fused_launch)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
+    // same kernel with the upload / download flow control of dsb_erk_run_host compiled in (fast flavour only)
+    int (*fused_launch_flow)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
 };
 
 namespace dsb {
@@ -52,7 +54,7 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
-template <class Rhs, class Tab, bool STRICT>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
 {
     ErkKernelArgs<Tab::S> args;
@@ -60,7 +62,7 @@ int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStrea
     fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
     args.factor_table = p->d_factor;
-    return launch_erk_fused<Rhs, Tab, STRICT>(args, p->fused_blocks, stream);
+    return launch_erk_fused<Rhs, Tab, STRICT, FLOW>(args, p->fused_blocks, stream);
 }
 
 // true iff the caller's tableau equals the compile-time one bit for bit
@@ -83,6 +85,7 @@ template <class Rhs, class Tab, bool STRICT>
 void bind_fused(dsb_erk_plan *p, int *per_sm)
 {
     p->fused_launch = fused_trampoline<Rhs, Tab, STRICT>;
+    if constexpr (!STRICT && Tab::S <= 7) p->fused_launch_flow = fused_trampoline<Rhs, Tab, STRICT, true>;
     occupancy_erk_fused<Rhs, Tab, STRICT>(per_sm);
 }
 

@@ -56,7 +56,7 @@ del s, y0
 torch.cuda.empty_cache()
 
 # ---- configs 4 and 2 through their drivers
-for cmd in (["tools/vdp_sharded.py", "--check", "1024", "--reps", "3"], ["tools/linear_timing.py", "--check", "8", "--reps", "2"]):
+for cmd in (["tools/vdp_sharded.py", "--check", "1024", "--reps", "3"], ["tools/linear_timing.py", "--check", "8", "--reps", "3"]):
     out = subprocess.run([sys.executable] + cmd, cwd=ROOT, capture_output=True, text=True)
     line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:]
     print(line)
