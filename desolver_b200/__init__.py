@@ -15,9 +15,10 @@ from . import integrators
 from . import rhs_plugins
 from . import benchmarks
 from . import distributed
+from . import events
 from .differential_system import DiffRHS, OdeSystem, DenseOutput, StateTuple, rhs_prettifier, solve_ivp
 from .integrators import available_methods
 
 __version__ = "0.1.0"
-__all__ = ["backend", "exception_types", "integrators", "rhs_plugins", "benchmarks", "distributed", "DiffRHS", "OdeSystem",
+__all__ = ["backend", "exception_types", "integrators", "rhs_plugins", "benchmarks", "distributed", "events", "DiffRHS", "OdeSystem",
            "DenseOutput", "StateTuple", "rhs_prettifier", "solve_ivp", "available_methods"]

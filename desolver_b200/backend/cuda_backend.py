@@ -14,7 +14,8 @@ _SO = os.path.join(_PKG, "libdesolver_b200.so")
 
 ABI_VERSION = 2
 DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED = 0, 1, 2, 3
-TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING = 0, 1, 2
+TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING, TRAJ_EVENT = 0, 1, 2, 3
+MAX_EVENTS = 4
 FLAG_STRICT = 1
 MAX_PARAMS = 4
 FUSED_STAGES = (1, 2, 4, 6, 7, 13, 17)
@@ -43,6 +44,9 @@ class ErkRunArgs(C.Structure):
         ("done_shift", C.c_int32),
         ("avail", C.c_void_p),
         ("done", C.c_void_p),
+        ("n_events", C.c_int32), ("ev_capacity", C.c_int32),
+        ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
+        ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
     ]
 
 

@@ -81,7 +81,7 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     case DSB_RHS_SHO:    fused = dim == 2 && select_fused_sho(p); break;
     default: break;
     }
-    if (!fused) p->fused_launch = p->fused_launch_flow = nullptr;
+    if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = nullptr;
 
     double2 host_tab[fm::ATAN_TABLE_SIZE];
     fm::build_atan_table(host_tab);
@@ -140,6 +140,19 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;
+    if (a->n_events > 0) {
+        if (a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
+            a->ev_capacity < 1 || a->nodes) {
+            set_error("dsb_erk_run: events need ev_coef, ev_flags, ev_records, ev_count, ev_capacity >= 1, at most %d "
+                      "events, and no dense-output store in the same call", DSB_MAX_EVENTS);
+            return DSB_ERR_BAD_ARGUMENT;
+        }
+        if (!h->fused_launch_events) {
+            set_error("dsb_erk_run: no event-detecting kernel for rhs_id=%d stages=%d (<= 7 stages)", h->rhs_id, h->stages);
+            return DSB_ERR_UNSUPPORTED;
+        }
+        return h->fused_launch_events(h, a, (cudaStream_t)stream);
+    }
     return h->fused_launch(h, a, (cudaStream_t)stream);
 }
 

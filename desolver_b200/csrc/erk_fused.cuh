@@ -172,8 +172,10 @@ constexpr int erk_min_blocks()
 // FLOW: the launch overlaps its own uploads / downloads (dsb_erk_run_host): it waits for `avail` before loading a
 // trajectory and counts stored results in `done`.  A separate instantiation, because even untaken the hooks cost the
 // device-resident kernel 3.6 % (3.53 -> 3.66 ms: different register allocation in the hot loop).
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false>
-__global__ void __launch_bounds__(ERK_THREADS, (erk_min_blocks<Rhs, Tab::S>()))
+// EV: event detection after every accepted step (dsb_erk_run_args.n_events > 0), see the event block below.
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
+__global__ void __launch_bounds__(ERK_THREADS, (EV ? (erk_min_blocks<Rhs, Tab::S>() > 4 ? 4 : erk_min_blocks<Rhs, Tab::S>())
+                                                   : erk_min_blocks<Rhs, Tab::S>()))
 erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 {
     using A = Ar<STRICT>;
@@ -199,6 +201,22 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     __shared__ unsigned long long s_att[ERK_THREADS], s_acc[ERK_THREADS];
     __shared__ unsigned s_fail[ERK_THREADS], s_run[ERK_THREADS];
     s_att[threadIdx.x] = 0; s_acc[threadIdx.x] = 0; s_fail[threadIdx.x] = 0; s_run[threadIdx.x] = 0;
+    // event detection state (EV only): coefficients of the hyperplane events, and per thread the state before the
+    // last commit (the step's interpolant and the roll-back of a terminal event need it), g at the step start and the
+    // time of each event's last recorded occurrence
+    constexpr int NE = DSB_MAX_EVENTS, EVW = Rhs::DIM + 2;
+    __shared__ double s_evc[EV ? NE * EVW : 1];
+    __shared__ int s_evf[EV ? NE : 1];
+    __shared__ double s_yprev[EV ? Rhs::DIM : 1][EV ? ERK_THREADS : 1];
+    __shared__ double s_tprev[EV ? 2 : 1][EV ? ERK_THREADS : 1];
+    __shared__ double s_gprev[EV ? NE : 1][EV ? ERK_THREADS : 1];
+    __shared__ double s_evlast[EV ? NE : 1][EV ? ERK_THREADS : 1];
+    const int ne = EV ? (P.a.n_events < NE ? P.a.n_events : NE) : 0;
+    if (EV) {
+        for (int i = threadIdx.x; i < ne * EVW; i += blockDim.x) s_evc[i] = P.a.ev_coef[i];
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) s_evf[i] = P.a.ev_flags[i];
+        __syncthreads();
+    }
     if (!STRICT) {
         for (int i = threadIdx.x; i < fm::ATAN_TABLE_SIZE; i += blockDim.x) s_atan[i] = P.atan_table[i];
         if (tab.adaptive()) {
@@ -280,9 +298,19 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 
     // Start of a step: final-step clamp (differential_system.py:997-1002).  Called when a trajectory is loaded
     // and after every accepted step, so the loop top has no per-attempt bookkeeping.
+    double tf_lane = tf;               // EV: a terminal event re-targets the trajectory to the event time
+    bool final_leg = false;            // EV: re-integration to a terminal root in progress (events are off, :1054)
     auto start_step = [&]() {
-        final_step = fabs(dt + t) > fabs(tf);
-        h = final_step ? (tf - t) : dt;
+        const double tfc = EV ? tf_lane : tf;
+        final_step = fabs(dt + t) > fabs(tfc);
+        h = final_step ? (tfc - t) : dt;
+    };
+    // g_e(t, y) of the hyperplane events
+    auto ev_g = [&](int e, double tt, const double (&yy)[D]) -> double {
+        double g = s_evc[e * EVW + D] * tt - s_evc[e * EVW + D + 1];
+#pragma unroll
+        for (int d = 0; d < D; ++d) g = fma(s_evc[e * EVW + d], yy[d], g);
+        return g;
     };
 
     // Rare path, entered by the whole warp when ANY lane rejected, finished, failed or is idle:
@@ -312,8 +340,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             }
         }
         if (!live && done) {                                             // finished earlier, result still in registers
-            bool more = (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
-            store(more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE);
+            bool more = (dt != 0.0) && (fabs((EV ? tf_lane : tf) - t) >= DSB_EPS32);
+            store(more ? (int)DSB_TRAJ_RUNNING : ((EV && final_leg) ? (int)DSB_TRAJ_EVENT : (int)DSB_TRAJ_DONE));
             done = false;
         }
         // refill idle lanes from the queue (warp-aggregated atomicAdd); a loaded trajectory that has nothing to
@@ -363,7 +391,16 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 Rhs::prepare(prm);
                 acc = 0; rej = 0; trial = 0;
                 int st0 = (P.a.status && !fresh) ? P.a.status[idx] : (int)DSB_TRAJ_DONE;
-                bool go = st0 != (int)DSB_TRAJ_TOL_FAIL;
+                bool go = st0 != (int)DSB_TRAJ_TOL_FAIL && st0 != (int)DSB_TRAJ_EVENT;
+                if (EV) {
+                    tf_lane = tf;
+                    final_leg = false;
+                    for (int e = 0; e < ne; ++e) {
+                        s_gprev[e][threadIdx.x] = ev_g(e, t, y);
+                        s_evlast[e][threadIdx.x] = CUDART_NAN;
+                    }
+                    if (fresh) P.a.ev_count[idx] = 0;
+                }
                 if (go && P.a.first_call) {
                     // integrate() entry: differential_system.py:956-957, 971-974
                     double span = tf - t;
@@ -384,8 +421,9 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                         dense_node(f0);
                     }
                 } else {
-                    bool more = st0 != (int)DSB_TRAJ_TOL_FAIL && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
-                    store(st0 == (int)DSB_TRAJ_TOL_FAIL ? st0 : (more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE));
+                    const bool frozen = st0 == (int)DSB_TRAJ_TOL_FAIL || st0 == (int)DSB_TRAJ_EVENT;
+                    bool more = !frozen && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                    store(frozen ? st0 : (more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE));
                 }
             }
         }
@@ -546,7 +584,14 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         }
 
         // ------------------------------------------------------------ accept: commit and start the next step
+        unsigned ev_mask = 0;
         if (live && !redo) {
+            if (EV) {                                                   // state before the commit (interpolant, roll-back)
+#pragma unroll
+                for (int d = 0; d < D; ++d) s_yprev[d][threadIdx.x] = y[d];
+                s_tprev[0][threadIdx.x] = t;
+                s_tprev[1][threadIdx.x] = dt;
+            }
 #pragma unroll
             for (int d = 0; d < D; ++d)
                 y[d] = (STRICT || tab.fsal()) ? A::add(y[d], dY[d]) : fma(h, dY[d], y[d]);   // :1015
@@ -559,10 +604,127 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 Rhs::eval(y, prm, f1);
                 dense_node(f1);
             }
+            if (EV && !final_leg) {
+                // an event is searched for iff g changes sign over the step (utilities/optimizer.py:252)
+                for (int e = 0; e < ne; ++e) {
+                    const double g1 = ev_g(e, t, y), g0 = s_gprev[e][threadIdx.x];
+                    s_gprev[e][threadIdx.x] = g1;
+                    const int dir = s_evf[e] & 3;
+                    const bool rising = g0 < 0.0;
+                    if (g0 * g1 < 0.0 && (dir == 0 || (dir == 1) == rising)) ev_mask |= 1u << e;
+                }
+            }
             start_step();
-            done = !((dt != 0.0) && (fabs(tf - t) >= DSB_KC(eps32, DSB_EPS32)))               // :996
+            done = !((dt != 0.0) && (fabs((EV ? tf_lane : tf) - t) >= DSB_KC(eps32, DSB_EPS32)))   // :996
                    || acc >= step_budget;
             live = !done;
+        }
+        // ------------------------------------------------------------ events (EV): locate, record, terminal roll-back
+        if (EV) {
+            if (__any_sync(FULL, ev_mask != 0u) && ev_mask != 0u) {
+                const int tid = threadIdx.x;
+                // the accepted step [t0, t1] and its cubic Hermite interpolant (integrator_types.py:109-119,
+                // utilities/interpolation.py:41-61): p0, p1 = states, m0 = the step's first stage, m1 = rhs(t1, y1)
+                const double t0 = s_tprev[0][tid], t1 = t, trange = t1 - t0;
+                double y0[D], f1[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) y0[d] = s_yprev[d][tid];
+                Rhs::eval(y, prm, f1);
+                double root[NE];
+                int which[NE], cnt = 0;
+                for (int e = 0; e < ne; ++e) {
+                    if (!(ev_mask >> e & 1u)) continue;
+                    // along the interpolant a linear g is itself the Hermite cubic of (g0, g1, dg0, dg1):
+                    //   G(tau) = g0 + a tau + c2 tau^2 + c3 tau^3,  a = trange*dg0, b = trange*dg1
+                    const double g0 = ev_g(e, t0, y0), g1 = ev_g(e, t1, y);
+                    double dg0 = s_evc[e * EVW + D], dg1 = dg0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        dg0 = fma(s_evc[e * EVW + d], k[0][d], dg0);
+                        dg1 = fma(s_evc[e * EVW + d], f1[d], dg1);
+                    }
+                    const double a = trange * dg0, b = trange * dg1;
+                    const double c2 = 3.0 * (g1 - g0) - 2.0 * a - b, c3 = 2.0 * (g0 - g1) + a + b;
+                    // bracketed Newton on [0, 1] (the reference runs Brent's method on the same function)
+                    double lo = 0.0, hi = 1.0, tau = g0 / (g0 - g1);
+                    for (int it = 0; it < 100; ++it) {
+                        const double G = fma(fma(fma(c3, tau, c2), tau, a), tau, g0);
+                        if (G == 0.0) break;
+                        if ((G < 0.0) == (g0 < 0.0)) lo = tau; else hi = tau;
+                        const double dG = fma(fma(3.0 * c3, tau, 2.0 * c2), tau, a);
+                        double nxt = tau - G / dG;
+                        if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
+                        const bool conv = fabs(nxt - tau) <= 4.0e-16 || hi - lo <= 4.0e-16;
+                        tau = nxt;
+                        if (conv) break;
+                    }
+                    root[cnt] = fma(tau, trange, t0);
+                    which[cnt] = e;
+                    cnt++;
+                }
+                // in the order of time (:152-155); stop after the first terminal event (:157-162)
+                for (int i = 1; i < cnt; ++i)
+                    for (int j = i; j > 0 && (trange >= 0.0 ? root[j] < root[j - 1] : root[j] > root[j - 1]); --j) {
+                        double tr = root[j]; root[j] = root[j - 1]; root[j - 1] = tr;
+                        int tw = which[j]; which[j] = which[j - 1]; which[j - 1] = tw;
+                    }
+                bool term = false;
+                double term_root = 0.0;
+                for (int i = 0; i < cnt && !term; ++i) {
+                    const int e = which[i];
+                    const double rt = root[i], last = s_evlast[e][tid];
+                    // a repeat of the same occurrence is dropped (:1043-1048: |t - t_last| <= epsilon^0.7)
+                    if (!(last == last) || fabs(rt - last) > 2.9e-11) {
+                        s_evlast[e][tid] = rt;
+                        const int c = P.a.ev_count[idx];
+                        if (c < P.a.ev_capacity) {
+                            double *rec = P.a.ev_records + ((long long)idx * P.a.ev_capacity + c) * EVW;
+                            const double ta = (rt - t0) / trange;                  // interpolation.py:38-39
+                            rec[0] = rt;
+                            rec[1 + D] = (double)e;
+                            if (ta == 0.0 || ta == 1.0) {
+#pragma unroll
+                                for (int d = 0; d < D; ++d) rec[1 + d] = ta == 0.0 ? y0[d] : y[d];
+                            } else {
+                                const double t2 = __dmul_rn(ta, ta), t3 = __dmul_rn(t2, ta);
+                                const double h00 = __dadd_rn(__dsub_rn(__dmul_rn(2.0, t3), __dmul_rn(3.0, t2)), 1.0);
+                                const double h10 = __dadd_rn(__dsub_rn(t3, __dmul_rn(2.0, t2)), ta);
+                                const double h01 = __dadd_rn(__dmul_rn(-2.0, t3), __dmul_rn(3.0, t2));
+                                const double h11 = __dsub_rn(t3, t2);
+#pragma unroll
+                                for (int d = 0; d < D; ++d)
+                                    rec[1 + d] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h00, y0[d]),
+                                                                               __dmul_rn(__dmul_rn(h10, trange), k[0][d])),
+                                                                     __dmul_rn(h01, y[d])),
+                                                           __dmul_rn(__dmul_rn(h11, trange), f1[d]));
+                            }
+                        }
+                        P.a.ev_count[idx] = c + 1;
+                    }
+                    if (s_evf[e] & 4) { term = true; term_root = rt; }
+                }
+                if (term) {
+                    // terminal event: drop the step and integrate to the root like the nested
+                    // self.integrate(roots[-1]) of differential_system.py:1051-1055 (counter -= 1; entry clamp
+                    // dt = |t_root - t| / 2 of :973-974; final-step clamp; no event detection on that leg)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) y[d] = y0[d];
+                    t = t0;
+                    dt = s_tprev[1][tid];
+                    acc--;
+                    tf_lane = term_root;
+                    final_leg = true;
+                    const double span = tf_lane - t;
+                    if (fabs(span) < DSB_EPS4) {                         // integrate() returns at once (:956-957)
+                        done = true;
+                    } else {
+                        if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+                        start_step();
+                        done = !((dt != 0.0) && (fabs(tf_lane - t) >= DSB_EPS32)) || acc >= step_budget;
+                    }
+                    live = !done;
+                }
+            }
         }
         // ------------------------------------------------------------ rare events: reject, finish, refill
         // A finished lane keeps its result in registers (its further arithmetic is discarded) until REFILL_BATCH
@@ -578,19 +740,19 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 }
 
 // Host-side launcher, one per instantiation.
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
 int launch_erk_fused(const ErkKernelArgs<Tab::S> &args, int blocks, cudaStream_t stream)
 {
-    erk_fused_kernel<Rhs, Tab, STRICT, FLOW><<<blocks, ERK_THREADS, 0, stream>>>(args);
+    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EV><<<blocks, ERK_THREADS, 0, stream>>>(args);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
 
-template <class Rhs, class Tab, bool STRICT>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
 int occupancy_erk_fused(int *blocks_per_sm)
 {
     DSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT>, ERK_THREADS, 0));
+        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EV>, ERK_THREADS, 0));
     return DSB_OK;
 }
 

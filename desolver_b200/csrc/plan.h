@@ -23,6 +23,9 @@ struct dsb_erk_plan {
     int (*fused_launch)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
     // same kernel with the upload / download flow control of dsb_erk_run_host compiled in (fast flavour only)
     int (*fused_launch_flow)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
+    // same kernel with event detection compiled in (<= 7 stages); its own persistent grid size
+    int (*fused_launch_events)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
+    int events_blocks = 0;
 };
 
 namespace dsb {
@@ -54,7 +57,7 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
 {
     ErkKernelArgs<Tab::S> args;
@@ -62,7 +65,7 @@ int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStrea
     fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
     args.factor_table = p->d_factor;
-    return launch_erk_fused<Rhs, Tab, STRICT, FLOW>(args, p->fused_blocks, stream);
+    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EV>(args, EV ? p->events_blocks : p->fused_blocks, stream);
 }
 
 // true iff the caller's tableau equals the compile-time one bit for bit
@@ -86,6 +89,12 @@ void bind_fused(dsb_erk_plan *p, int *per_sm)
 {
     p->fused_launch = fused_trampoline<Rhs, Tab, STRICT>;
     if constexpr (!STRICT && Tab::S <= 7) p->fused_launch_flow = fused_trampoline<Rhs, Tab, STRICT, true>;
+    if constexpr (Tab::S <= 7) {
+        p->fused_launch_events = fused_trampoline<Rhs, Tab, STRICT, false, true>;
+        int ev_per_sm = 0;
+        occupancy_erk_fused<Rhs, Tab, STRICT, false, true>(&ev_per_sm);
+        p->events_blocks = p->sm_count * (ev_per_sm < 1 ? 1 : ev_per_sm);
+    }
     occupancy_erk_fused<Rhs, Tab, STRICT>(per_sm);
 }
 

@@ -216,6 +216,8 @@ class OdeSystem(object):
         self.use_graphs = True       # stage-level path: replay one attempt as a CUDA graph
         self._compactions = 0
         self.callback_every = 1
+        self.event_capacity = 64     # event records kept per trajectory (device event detection)
+        self._event_log = None
 
         if self.host_io:
             self._init_host_io(y0, host_out)
@@ -319,6 +321,7 @@ class OdeSystem(object):
             self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
         self._pristine = True
         self._stats = None
+        self._event_log = None
         self._hist_y = [self._y0]                         # row 0 = initial condition (never written to)
         self._hist_t = [self.__t0]                        # scalars stand for "every trajectory at this time"
         self._nodes = None
@@ -358,7 +361,12 @@ class OdeSystem(object):
 
     @property
     def events(self):
-        return self.__events
+        """Events found so far.  A single system gives the reference's list of `StateTuple(t, y, event)`
+        (`differential_system.py:557-560`); an ensemble gives an `events.EventLog` (per-trajectory counts, times,
+        states and event indices as device tensors; `log.for_trajectory(i)` is the reference's list)."""
+        if self._event_log is None:
+            return self.__events
+        return self._event_log if self.ensemble else self._event_log.for_trajectory(0)
 
     @property
     def y(self):
@@ -567,7 +575,19 @@ class OdeSystem(object):
             self._nodes = torch.empty((self.n_traj, self._node_capacity, rec), dtype=torch.float64, device=self.device)
             self._node_count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
 
-    def _run_fused(self, tf, plugin, max_steps, first_call):
+    def _event_tensors(self, events):
+        """Device-side description of the events (dsb_erk_run_args.ev_*): coefficient rows, flag words, record store."""
+        torch = _torch()
+        from .events import EventLog
+        coef = torch.as_tensor(np.stack([ev.coefficients(self.numel) for ev in events]), dtype=torch.float64).to(self.device)
+        flags = torch.as_tensor([ev.flags for ev in events], dtype=torch.int32).to(self.device)
+        if self._event_log is None or self._event_log.events != list(events):
+            records = torch.zeros((self.n_traj, int(self.event_capacity), self.numel + 2), dtype=torch.float64, device=self.device)
+            count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
+            self._event_log = EventLog(events, records, count, self.dim)
+        return coef, flags
+
+    def _run_fused(self, tf, plugin, max_steps, first_call, events=None):
         integ = self.integrator
         pid, names, defaults = plugin
         handle = cb.erk_handle(self.device.index or 0, pid, self.numel, integ.tableau_intermediate,
@@ -595,6 +615,12 @@ class OdeSystem(object):
         if self._nodes is not None:
             a.nodes, a.node_count, a.node_capacity = self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity
         a.counters = self._counters.data_ptr()
+        if events:
+            coef, flags = self._event_tensors(events)
+            a.n_events, a.ev_capacity = len(events), self._event_log.capacity
+            a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
+            a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
+            params = list(params) + [coef, flags]             # keep alive until the launch has run
         ev = self.__dict__.get("_kernel_events")          # optional (start, end) CUDA events bracketing the launch
         if ev:
             ev[0].record()
@@ -964,7 +990,16 @@ class OdeSystem(object):
         """
         torch = _torch()
         if events is not None:
-            raise NotImplementedError("event detection is not supported by the ensemble engine")
+            from .events import HyperplaneEvent
+            events = [events] if callable(events) and not isinstance(events, (list, tuple)) else list(events)
+            if not all(isinstance(ev, HyperplaneEvent) for ev in events):
+                raise NotImplementedError("the device detects events of type desolver_b200.events.HyperplaneEvent "
+                                          "(g(t, y) = w.y + wt*t - c: component crossings, Poincare sections, time "
+                                          "marks); arbitrary Python event callables are not supported")
+            if len(events) > cb.MAX_EVENTS:
+                raise NotImplementedError("at most %d events per integrate() call" % cb.MAX_EVENTS)
+            if not events:
+                events = None
         tf = float(t) if t is not None else self.__tf
         if callback is None:
             callbacks = []
@@ -977,6 +1012,11 @@ class OdeSystem(object):
         try:
             if self.host_io and (plugin is None or self.integrator.symplectic):
                 raise NotImplementedError("host_io=True needs an explicit Runge-Kutta method with a fused kernel")
+            if events and (plugin is None or self.integrator.symplectic or self.host_io or callbacks or eta
+                           or self.__dense_output or self.integrator.stages > 7):
+                raise NotImplementedError("device event detection needs a right-hand side with a fused plugin, an explicit "
+                                          "Runge-Kutta method with at most 7 stages, device-resident state, and no "
+                                          "callbacks / progress bar / dense output in the same call")
             if self.integrator.symplectic or plugin is None:
                 self._stats = None
             if self.integrator.symplectic:
@@ -1001,7 +1041,7 @@ class OdeSystem(object):
                                               "progress bar or dense output")
                 fused_stats = self._run_host_pipeline(tf, plugin)
             elif not callbacks and not eta:
-                self._run_fused(tf, plugin, self._step_cap, first_call=True)
+                self._run_fused(tf, plugin, self._step_cap, first_call=True, events=events)
                 fused_stats = self._fused_stats()
             else:
                 first = True
@@ -1052,7 +1092,10 @@ class OdeSystem(object):
             self.__int_status = new_e
             raise new_e
         else:
-            self.__int_status = 1
+            # "Integration terminated upon finding a triggered event." (reference :1055) if a terminal event fired
+            terminated = bool(events) and any(ev.is_terminal for ev in events) and \
+                bool((self.status == cb.TRAJ_EVENT).any().item())
+            self.__int_status = 2 if terminated else 1
 
     # ------------------------------------------------------------------ container protocol
     def __len__(self):
@@ -1091,8 +1134,6 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
     import inspect
     torch = _torch()
     from scipy.optimize import OptimizeResult
-    if events is not None:
-        raise NotImplementedError("event detection is not supported by the ensemble engine")
     constants = None
     if args is not None:
         fn = fun
@@ -1112,7 +1153,7 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
         def clip_step(ode_sys):                       # reference :1229-1232
             ode_sys.dt = torch.clamp(ode_sys._dt, min=min_step, max=max_step)
         callbacks.append(clip_step)
-    kw = dict(callback=callbacks or None, eta=options.get("show_prog_bar", False))
+    kw = dict(callback=callbacks or None, eta=options.get("show_prog_bar", False), events=events)
     if t_eval is None:
         system.integrate(**kw)
         t_res = system.t
@@ -1128,6 +1169,17 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
             ys.append(system[-1].y)
         t_res = torch.stack(ts, dim=-1)
         y_res = torch.stack(ys, dim=-1)
-    return OptimizeResult(t=t_res, y=y_res, sol=system.sol, t_events=None, y_events=None, nfev=system.nfev,
+    t_events = y_events = None
+    if events is not None and not system.ensemble:
+        # scipy layout, like the reference (:1251-1253): one array of times / states per event function
+        evl = [events] if callable(events) and not isinstance(events, (list, tuple)) else list(events)
+        found = system.events
+        t_events = [torch.stack([st.t for st in found if st.event is ev]) if any(st.event is ev for st in found)
+                    else torch.empty(0, dtype=torch.float64) for ev in evl]
+        y_events = [torch.stack([st.y for st in found if st.event is ev]) if any(st.event is ev for st in found)
+                    else torch.empty(0, dtype=torch.float64) for ev in evl]
+    elif events is not None:
+        t_events = y_events = system.events                # ensemble: the EventLog
+    return OptimizeResult(t=t_res, y=y_res, sol=system.sol, t_events=t_events, y_events=y_events, nfev=system.nfev,
                           njev=system.njev, status=system.integration_status, message=system.integration_status,
                           success=system.success, ode_system=system)

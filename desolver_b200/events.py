@@ -1,0 +1,113 @@
+"""Event functions with a device implementation.
+
+The reference detects events after every accepted step by root-finding `event(t, sol(t), **constants)` on the
+step's dense-output interpolant (/root/reference/desolver/differential_system.py:29-57, 60-167, 1020-1066), with the
+scipy-style protocol: an event is any callable `event(t, y, **constants) -> float` carrying the optional
+attributes `is_terminal` (stop at the event) and `direction` (> 0: only rising zero crossings, < 0: only falling,
+0: both).
+
+`HyperplaneEvent` is such a callable -- it can be handed to the unmodified reference as it is, which is how
+tests/golden/events_*.npz were produced -- whose function is affine,
+
+    g(t, y) = sum_d w[d] * y[d] + wt * t - c,
+
+so that the fused kernels can evaluate it per trajectory in registers, bracket sign changes over each accepted
+step and locate the root on the step's cubic Hermite interpolant without leaving the device
+(include/desolver_b200.h, dsb_erk_run_args.n_events).  Component crossings (Poincare sections, thresholds,
+time marks) are all of this form.
+"""
+import numpy as np
+
+__all__ = ["HyperplaneEvent", "component_crossing", "EventLog"]
+
+
+class HyperplaneEvent(object):
+    """g(t, y) = w . y + wt * t - c, with the reference's event attributes `is_terminal` and `direction`."""
+
+    def __init__(self, w, c=0.0, wt=0.0, direction=0, is_terminal=False, name=None):
+        self.w = np.asarray(w, dtype=np.float64).reshape(-1)
+        self.c = float(c)
+        self.wt = float(wt)
+        self.direction = int(np.sign(direction))
+        self.is_terminal = bool(is_terminal)
+        self.name = name or "hyperplane(w=%s, wt=%g, c=%g)" % (self.w.tolist(), self.wt, self.c)
+
+    def __call__(self, t, y, *args, **constants):
+        # y is (dim,) for one system, (dim, N) for an ensemble; a multi-axis state (*dim[, N]) is flattened first
+        n = self.w.shape[0]
+        if y.shape[0] != n:
+            lead = 1
+            k = 0
+            while lead < n:
+                lead *= y.shape[k]
+                k += 1
+            y = y.reshape((n,) + tuple(y.shape[k:]))
+        g = self.wt * t - self.c
+        for d in range(n):
+            if self.w[d] != 0.0:
+                g = g + self.w[d] * y[d]
+        return g
+
+    def coefficients(self, dim):
+        if self.w.shape[0] != dim:
+            raise ValueError("event %s has %d weights, the state has %d components" % (self.name, self.w.shape[0], dim))
+        return np.concatenate([self.w, [self.wt, self.c]])
+
+    @property
+    def flags(self):
+        return (1 if self.direction > 0 else (2 if self.direction < 0 else 0)) | (4 if self.is_terminal else 0)
+
+    def __repr__(self):
+        return "<HyperplaneEvent %s direction=%d terminal=%s>" % (self.name, self.direction, self.is_terminal)
+
+
+def component_crossing(index, value=0.0, dim=None, direction=0, is_terminal=False):
+    """Event `y[index] == value` for a state of `dim` components (flattened index)."""
+    if dim is None:
+        raise ValueError("component_crossing needs dim= (the number of state components)")
+    w = np.zeros(int(dim))
+    w[int(index)] = 1.0
+    return HyperplaneEvent(w, c=value, direction=direction, is_terminal=is_terminal,
+                           name="y[%d] == %g" % (int(index), float(value)))
+
+
+class EventLog(object):
+    """Events found by the device, per trajectory: `count[i]` events (at most `capacity` are kept), event k of
+    trajectory i happened at `t[i, k]` in state `y[:, i, k]` and belongs to `events[index[i, k]]`."""
+
+    def __init__(self, events, records, count, dim_shape):
+        self.events = list(events)
+        self.count = count
+        self.capacity = int(records.shape[1])
+        self._records = records
+        self._dim = tuple(dim_shape)
+
+    @property
+    def t(self):
+        return self._records[:, :, 0]
+
+    @property
+    def y(self):
+        import torch
+        d = self._records.shape[2] - 2
+        return torch.movedim(self._records[:, :, 1:1 + d], 2, 0)
+
+    @property
+    def index(self):
+        return self._records[:, :, -1].long()
+
+    @property
+    def overflowed(self):
+        return bool((self.count > self.capacity).any().item())
+
+    def for_trajectory(self, i):
+        """The reference's `OdeSystem.events` for trajectory i: a list of StateTuple(t, y, event)."""
+        from .differential_system import StateTuple
+        k = min(int(self.count[i].item()), self.capacity)
+        rec = self._records[i, :k].cpu()
+        d = rec.shape[1] - 2
+        return [StateTuple(t=rec[j, 0], y=rec[j, 1:1 + d].reshape(self._dim), event=self.events[int(rec[j, -1])])
+                for j in range(k)]
+
+    def __len__(self):
+        return int(self.count.clamp(max=self.capacity).sum().item())

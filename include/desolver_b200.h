@@ -56,12 +56,15 @@ typedef enum {
 typedef enum {
     DSB_TRAJ_DONE = 0,      /* reached tf                                                     */
     DSB_TRAJ_TOL_FAIL = 1,  /* 64 retries exhausted; state frozen at the failed step's start  */
-    DSB_TRAJ_RUNNING = 2    /* step budget of this call exhausted before tf (chunked runs)    */
+    DSB_TRAJ_RUNNING = 2,   /* step budget of this call exhausted before tf (chunked runs)    */
+    DSB_TRAJ_EVENT = 3      /* stopped at the root of a terminal event (reference: integration_status 2,
+                               differential_system.py:1053-1055)                               */
 } dsb_traj_status;
 
 #define DSB_FLAG_STRICT 1u  /* reference operation order, no FMA contraction, libm pow/atan   */
 
 #define DSB_MAX_PARAMS 4
+#define DSB_MAX_EVENTS 4
 #define DSB_MAX_FUSED_STAGES 17
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -119,6 +122,22 @@ typedef struct {
                                   the kernel waits, bounded, before it loads a trajectory beyond it; a wait that
                                   times out sets counters[6] = 1 and abandons the remaining trajectories       */
     uint32_t *done;            /* device words (NULL: off), zeroed by the caller, see done_shift                  */
+    /* ---- event detection on the device (n_events = 0: off) --------------------------------------------------
+     * Replaces, per trajectory, prepare_events / handle_events and the event hooks of the integrate loop
+     * (differential_system.py:29-57, 60-167, 1020-1066) for hyperplane event functions
+     *     g_e(t, y) = sum_d w[e][d] * y[d] + wt[e] * t - c[e].
+     * After every accepted step an event whose g changes sign over the step (fa * fb < 0, the bracketing test of
+     * utilities/optimizer.py:252) is located as the root of g along the step's cubic Hermite interpolant
+     * (utilities/interpolation.py:41-61; for a linear g that is a cubic in the step fraction), filtered by
+     * direction, de-duplicated like :1043-1048, and recorded as (t_root, y(t_root), e).  A terminal event rolls the
+     * step back and re-integrates to t_root exactly like the nested self.integrate(roots[-1]) of :1053-1054 (entry
+     * clamp dt = |t_root - t| / 2, final-step clamp), then stops the trajectory with DSB_TRAJ_EVENT.            */
+    int32_t n_events;          /* <= DSB_MAX_EVENTS                                                               */
+    int32_t ev_capacity;       /* records per trajectory                                                          */
+    const double *ev_coef;     /* device [n_events][dim + 2]: w[dim], wt, c                                       */
+    const int32_t *ev_flags;   /* device [n_events]: bits 0-1 direction (0 either, 1 rising, 2 falling), bit 2 terminal */
+    double *ev_records;        /* device [n][ev_capacity][dim + 2]: t, y[dim], event index                        */
+    int32_t *ev_count;         /* device [n] in/out: events found (records beyond ev_capacity are dropped)        */
 } dsb_erk_run_args;
 
 DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);

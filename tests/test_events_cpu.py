@@ -1,0 +1,40 @@
+"""CPU tests of the event objects (no GPU): HyperplaneEvent is a valid event callable of the reference's protocol
+on numpy arrays and torch tensors, and the committed event fixtures are well formed."""
+import numpy as np
+
+from conftest import load_golden
+
+
+def test_hyperplane_event_protocol():
+    import torch
+    from desolver_b200.events import HyperplaneEvent, component_crossing
+    ev = HyperplaneEvent([1.0, 0.0, -2.0], c=0.5, wt=0.25, direction=-3, is_terminal=True)
+    y = np.array([1.0, 7.0, 0.125])
+    assert ev(2.0, y) == 1.0 - 0.25 + 0.25 * 2.0 - 0.5
+    assert ev.direction == -1 and ev.is_terminal and ev.flags == (2 | 4)
+    assert np.array_equal(ev.coefficients(3), [1.0, 0.0, -2.0, 0.25, 0.5])
+    ens = np.stack([y, 2 * y], axis=-1)
+    assert np.array_equal(ev(2.0, ens), [ev(2.0, y), ev(2.0, 2 * y)])
+    assert torch.equal(ev(2.0, torch.as_tensor(ens)), torch.as_tensor(ev(2.0, ens)))
+    c = component_crossing(1, 3.0, dim=2, direction=1)
+    assert c(0.0, np.array([9.0, 4.0])) == 1.0 and c.flags == 1 and not c.is_terminal
+    # multi-axis state (2, 2) flattened to 4 components
+    m = component_crossing(3, 0.0, dim=4)
+    assert m(0.0, np.arange(4.0).reshape(2, 2)) == 3.0
+
+
+def test_event_fixtures_are_well_formed():
+    for name in ("lorenz_sections", "lorenz_terminal", "vdp_sections", "vdp_terminal"):
+        g = load_golden("events_%s.npz" % name)
+        n = g["y0"].shape[1]
+        assert g["records"].shape[0] == n and g["count"].shape == (n,)
+        for i in range(n):
+            k = int(g["count"][i])
+            t = g["records"][i, :k, 0]
+            assert np.all(np.isfinite(t)) and np.all(np.diff(t) >= 0)
+        if name.endswith("terminal"):
+            term = g["status"] == 2
+            assert term.any()
+            # a terminated trajectory ends at its last event
+            last = np.array([g["records"][i, g["count"][i] - 1, 0] for i in np.nonzero(term)[0]])
+            assert np.max(np.abs(last - g["t_final"][term])) <= 1e-9
