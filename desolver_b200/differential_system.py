@@ -1169,17 +1169,9 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
             ys.append(system[-1].y)
         t_res = torch.stack(ts, dim=-1)
         y_res = torch.stack(ys, dim=-1)
-    t_events = y_events = None
-    if events is not None and not system.ensemble:
-        # scipy layout, like the reference (:1251-1253): one array of times / states per event function
-        evl = [events] if callable(events) and not isinstance(events, (list, tuple)) else list(events)
-        found = system.events
-        t_events = [torch.stack([st.t for st in found if st.event is ev]) if any(st.event is ev for st in found)
-                    else torch.empty(0, dtype=torch.float64) for ev in evl]
-        y_events = [torch.stack([st.y for st in found if st.event is ev]) if any(st.event is ev for st in found)
-                    else torch.empty(0, dtype=torch.float64) for ev in evl]
-    elif events is not None:
-        t_events = y_events = system.events                # ensemble: the EventLog
+    # like the reference (:1252-1253) both keys carry `ode_system.events`: the list of StateTuple(t, y, event) for a
+    # single system, the EventLog for an ensemble
+    t_events = y_events = system.events if events is not None else None
     return OptimizeResult(t=t_res, y=y_res, sol=system.sol, t_events=t_events, y_events=y_events, nfev=system.nfev,
                           njev=system.njev, status=system.integration_status, message=system.integration_status,
                           success=system.success, ode_system=system)
