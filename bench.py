@@ -204,9 +204,12 @@ def main():
         sys_._kernel_events = None
         st = sys_.stats                       # totals accumulated by the kernel itself (one 64-byte D2H in integrate())
         if world > 1:
-            stats[0], stats[1] = float(st["attempts"]), float(st["failed"] + st["running"])
-            dist.all_reduce(stats)            # termination / statistics all-reduce (NCCL)
-            return stats.clone()
+            # termination / statistics all-reduce (NCCL) straight from the kernel's device counters
+            # ([2] attempts, [4] failed, [5] unfinished): no host round trip in front of the collective
+            c = sys_._counters.to(torch.float64)
+            red = torch.stack([c[2], c[4] + c[5]])
+            dist.all_reduce(red)
+            return red
         return torch.tensor([float(st["attempts"]), float(st["failed"] + st["running"])], dtype=torch.float64)
 
     for _ in range(args.warmup):
