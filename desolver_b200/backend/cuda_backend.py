@@ -17,7 +17,7 @@ DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED = 0, 1, 2, 3
 TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING, TRAJ_EVENT = 0, 1, 2, 3
 MAX_EVENTS = 4
 FLAG_STRICT = 1
-MAX_PARAMS = 4
+MAX_PARAMS = 6
 FUSED_STAGES = (1, 2, 4, 6, 7, 13, 17)
 
 _dp = C.POINTER(C.c_double)

@@ -42,7 +42,7 @@ int dsb_abi_version(void) { return DSB_ABI_VERSION; }
 const char *dsb_build_info(void)
 {
     return "libdesolver_b200 abi=2 arch=sm_100a nvcc=" DSB_STR(__CUDACC_VER_MAJOR__) "." DSB_STR(__CUDACC_VER_MINOR__)
-           " fused_stages={1,2,4,6,7,13,17} rhs={lorenz,van_der_pol,harmonic_oscillator}";
+           " fused_stages={1,2,4,6,7,13,17} rhs={lorenz,van_der_pol,harmonic_oscillator,forced,duffing}";
 }
 
 const char *dsb_last_error(void) { return g_error; }
@@ -79,6 +79,8 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     case DSB_RHS_LORENZ: fused = dim == 3 && select_fused_lorenz(p); break;
     case DSB_RHS_VDP:    fused = dim == 2 && select_fused_vdp(p); break;
     case DSB_RHS_SHO:    fused = dim == 2 && select_fused_sho(p); break;
+    case DSB_RHS_FORCED: fused = dim == 2 && select_fused_forced(p); break;
+    case DSB_RHS_DUFFING: fused = dim == 2 && select_fused_duffing(p); break;
     default: break;
     }
     if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = nullptr;

@@ -22,6 +22,7 @@
 #include <math_constants.h>
 #include <type_traits>
 #include "tableau_static.cuh"
+#include "rhs_builtin.cuh"
 
 namespace dsb {
 
@@ -65,6 +66,7 @@ struct StaticTab {
     const TableauData<T::S> &d;
     template <int s, int j> static constexpr bool use_a() { return T::A[s][j] != 0.0; }
     template <int s, int j> __device__ __forceinline__ double a() const { return d.a[s][j]; }
+    template <int s> __device__ __forceinline__ double c() const { return d.c[s]; }
     template <int j> static constexpr bool use_b() { return T::B[j] != 0.0; }
     template <int j> __device__ __forceinline__ double b() const { return d.b[j]; }
     template <int j> static constexpr bool use_db() { return (T::B[j] - T::BH[j]) != 0.0; }
@@ -85,6 +87,7 @@ struct RuntimeTab {
     const TableauData<S_> &d;
     template <int s, int j> static constexpr bool use_a() { return j < s; }
     template <int s, int j> __device__ __forceinline__ double a() const { return d.a[s][j]; }
+    template <int s> __device__ __forceinline__ double c() const { return d.c[s]; }
     template <int j> static constexpr bool use_b() { return true; }
     template <int j> __device__ __forceinline__ double b() const { return d.b[j]; }
     template <int j> static constexpr bool use_db() { return true; }
@@ -417,7 +420,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     start_step();
                     if (P.a.nodes && P.a.node_count[idx] == 0) {
                         double f0[D];
-                        Rhs::eval(y, prm, f0);
+                        eval_rhs<Rhs>(t, y, prm, f0);
                         dense_node(f0);
                     }
                 } else {
@@ -461,7 +464,10 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     ys[d] = (s == 0) ? y[d] : fma(h, sum, y[d]);      // stage 0: y + h*0
                 }
             }
-            Rhs::eval(ys, prm, k[s]);
+            // stage time t + c_s h (runge_kutta_methods.py:50); dead code for an autonomous right-hand side
+            double ts = t;
+            if constexpr (Rhs::TIME) ts = STRICT ? A::add(t, A::mul(h, tab.template c<s>())) : fma(h, tab.template c<s>(), t);
+            eval_rhs<Rhs>(ts, ys, prm, k[s]);
         });
 
         // ------------------------------------------------------------ increment + error estimate
@@ -601,7 +607,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             if (!final_step) dt = new_dt;                                                     // :1070-1071
             if (P.a.nodes) {
                 double f1[D];
-                Rhs::eval(y, prm, f1);
+                eval_rhs<Rhs>(t, y, prm, f1);
                 dense_node(f1);
             }
             if (EV && !final_leg) {
@@ -629,7 +635,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 double y0[D], f1[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) y0[d] = s_yprev[d][tid];
-                Rhs::eval(y, prm, f1);
+                eval_rhs<Rhs>(t1, y, prm, f1);
                 double root[NE];
                 int which[NE], cnt = 0;
                 for (int e = 0; e < ne; ++e) {

@@ -135,5 +135,7 @@ bool select_fused(dsb_erk_plan *p)
 bool select_fused_lorenz(dsb_erk_plan *p);
 bool select_fused_vdp(dsb_erk_plan *p);
 bool select_fused_sho(dsb_erk_plan *p);
+bool select_fused_forced(dsb_erk_plan *p);
+bool select_fused_duffing(dsb_erk_plan *p);
 
 }  // namespace dsb

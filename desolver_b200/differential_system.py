@@ -26,6 +26,7 @@ import numpy as np
 from . import backend as D
 from . import exception_types as etypes
 from . import integrators
+from . import rhs_plugins
 from .backend import cuda_backend as cb
 
 __all__ = ["DiffRHS", "rhs_prettifier", "OdeSystem", "DenseOutput", "StateTuple", "solve_ivp"]
@@ -266,7 +267,7 @@ class OdeSystem(object):
             self._y0 = self._y0.contiguous()
         if self._fused_plugin_tag() is None:
             raise NotImplementedError("host_io=True is implemented for right-hand sides with a fused device plugin "
-                                      "(rhs_plugins.lorenz / van_der_pol / harmonic_oscillator)")
+                                      "(rhs_plugins.FUSED)")
         host_out = host_out or {}
 
         def host_buffer(name, shape, dtype):
@@ -296,7 +297,7 @@ class OdeSystem(object):
         rhs = self.equ_rhs
         if getattr(rhs, "plugin_id", None) is None:
             return None
-        if getattr(rhs, "device_plugin", None) not in ("lorenz", "van_der_pol", "harmonic_oscillator"):
+        if getattr(rhs, "device_plugin", None) not in rhs_plugins.FUSED:
             return None
         return rhs.plugin_id
 
@@ -533,7 +534,7 @@ class OdeSystem(object):
         library has a thread-per-trajectory kernel for; else None."""
         rhs = self.equ_rhs
         pid = getattr(rhs, "plugin_id", None)
-        if pid is None or getattr(rhs, "device_plugin", None) not in ("lorenz", "van_der_pol", "harmonic_oscillator"):
+        if pid is None or getattr(rhs, "device_plugin", None) not in rhs_plugins.FUSED:
             return None
         if not isinstance(self.integrator, integrators.RungeKuttaIntegrator):
             return None

@@ -11,7 +11,7 @@ tag survives wrapping.
 """
 
 # ids shared with include/desolver_b200.h (DSB_RHS_*) and oracle/desolver_oracle.h (ORC_RHS_*)
-RHS_LINEAR, RHS_LORENZ, RHS_VDP, RHS_NBODY, RHS_SHO = 0, 1, 2, 3, 4
+RHS_LINEAR, RHS_LORENZ, RHS_VDP, RHS_NBODY, RHS_SHO, RHS_FORCED, RHS_DUFFING = 0, 1, 2, 3, 4, 5, 6
 
 
 def _stack(parts, like):
@@ -107,5 +107,41 @@ def forced_oscillator(t, y):
     return _stack([y[1], -y[0] + t], y)
 
 
-BUILTIN = {f.device_plugin: f for f in (lorenz, van_der_pol, harmonic_oscillator, linear, nbody)}
+def forced(t, y):
+    """The same system as `forced_oscillator`, TAGGED: time-dependent right-hand sides run in the fused kernel too
+    (the stage time t + c_s h is formed per lane, /root/reference/desolver/integrators/components/
+    runge_kutta_methods.py:49-50)."""
+    return _stack([y[1], -y[0] + t], y)
+
+
+forced.device_plugin = "forced"
+forced.plugin_id = RHS_FORCED
+forced.plugin_params = ()
+forced.plugin_defaults = dict()
+
+
+def _cos(x):
+    if type(x).__module__.split(".")[0] == "torch":
+        import torch
+        return torch.cos(x)
+    import numpy
+    return numpy.cos(x)
+
+
+def duffing(t, y, delta=0.2, alpha=-1.0, beta=1.0, gamma=0.3, omega=1.2):
+    """Duffing oscillator x'' + delta x' + alpha x + beta x^3 = gamma cos(omega t), y = (x, v) -- the system of the
+    reference's example notebooks (/root/reference/docs/examples).  Any parameter may be per-trajectory."""
+    x, v = y[0], y[1]
+    return _stack([v, gamma * _cos(omega * t) - delta * v - alpha * x - beta * x * x * x], y)
+
+
+duffing.device_plugin = "duffing"
+duffing.plugin_id = RHS_DUFFING
+duffing.plugin_params = ("delta", "alpha", "beta", "gamma", "omega")
+duffing.plugin_defaults = dict(delta=0.2, alpha=-1.0, beta=1.0, gamma=0.3, omega=1.2)
+
+# right-hand sides with a thread-per-trajectory fused kernel (csrc/rhs_builtin.cuh)
+FUSED = ("lorenz", "van_der_pol", "harmonic_oscillator", "forced", "duffing")
+
+BUILTIN = {f.device_plugin: f for f in (lorenz, van_der_pol, harmonic_oscillator, linear, nbody, forced, duffing)}
 BUILTIN["forced_oscillator"] = forced_oscillator

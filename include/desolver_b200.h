@@ -47,6 +47,8 @@ typedef enum {
     DSB_RHS_VDP    = 2,  /* params: mu                                                        */
     DSB_RHS_NBODY  = 3,  /* state (2, nb, 3) per system; shared: G, eps2, masses              */
     DSB_RHS_SHO    = 4,  /* params: k, m                                                      */
+    DSB_RHS_FORCED = 5,  /* y'' + y = t (time dependent; the reference's test fixture), no params */
+    DSB_RHS_DUFFING = 6, /* x'' + delta x' + alpha x + beta x^3 = gamma cos(omega t); params in that order */
     DSB_RHS_EXTERNAL = 100 /* arbitrary torch callable evaluated between stage kernels       */
 } dsb_rhs_id;
 
@@ -63,7 +65,7 @@ typedef enum {
 
 #define DSB_FLAG_STRICT 1u  /* reference operation order, no FMA contraction, libm pow/atan   */
 
-#define DSB_MAX_PARAMS 4
+#define DSB_MAX_PARAMS 6
 #define DSB_MAX_EVENTS 4
 #define DSB_MAX_FUSED_STAGES 17
 

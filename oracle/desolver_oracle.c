@@ -88,6 +88,10 @@ void orc_rhs(const orc_problem *p, const double *prm, double t, const double *y,
 {
     switch (p->rhs_id) {
     case ORC_RHS_FORCED: dy[0] = y[1]; dy[1] = -y[0] + t; break;
+    case ORC_RHS_DUFFING:   /* desolver_b200/rhs_plugins.py: duffing, left to right */
+        dy[0] = y[1];
+        dy[1] = ((prm[3] * cos(prm[4] * t) - prm[0] * y[1]) - prm[1] * y[0]) - ((prm[2] * y[0]) * y[0]) * y[0];
+        break;
     case ORC_RHS_LINEAR: rhs_linear(p, y, dy); break;
     case ORC_RHS_LORENZ: rhs_lorenz(prm, y, dy); break;
     case ORC_RHS_VDP:    rhs_vdp(prm, y, dy); break;

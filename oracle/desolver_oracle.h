@@ -36,7 +36,9 @@ enum {
     ORC_RHS_VDP    = 2, /* traj params: mu ; dy = [v, mu*(1-x*x)*v - x]               */
     ORC_RHS_NBODY  = 3, /* state (2, nb, 3) = (q; v); shared = [G, eps2, m_0..m_nb-1] */
     ORC_RHS_SHO    = 4, /* traj params: k, m ; dy = [y1, -(k/m)*y0]                   */
-    ORC_RHS_FORCED = 5  /* dy = [y1, -y0 + t]   (time dependent; reference test fixture)*/
+    ORC_RHS_FORCED = 5, /* dy = [y1, -y0 + t]   (time dependent; reference test fixture)*/
+    ORC_RHS_DUFFING = 6 /* traj params: delta, alpha, beta, gamma, omega;
+                           dy = [v, gamma*cos(omega*t) - delta*v - alpha*x - beta*x*x*x]   */
 };
 
 enum {

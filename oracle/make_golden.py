@@ -158,6 +158,20 @@ def main():
                                 **pack(res, dict(y0=y0, mu=mu, tf=V["tf"], dt0=V["dt0"], rtol=V["rtol"], atol=V["atol"])))
             att = np.array([r["attempts"] for r in res])
             print("vdp_rk45: attempts mean %.1f min %d max %d" % (att.mean(), att.min(), att.max()))
+        if want("duffing_rk45"):
+            # Duffing oscillator of the reference's example notebooks, per-trajectory forcing amplitude and frequency
+            rng = np.random.default_rng(11)
+            n = 128
+            y0 = np.ascontiguousarray(rng.uniform(-1.5, 1.5, size=(2, n)))
+            gamma = rng.uniform(0.1, 0.5, size=n)
+            omega = rng.uniform(0.8, 1.6, size=n)
+            jobs = [("duffing", "RK45", y0[:, i], 0.0, 10.0, 1e-2, 1e-9, 1e-9,
+                     dict(delta=0.2, alpha=-1.0, beta=1.0, gamma=float(gamma[i]), omega=float(omega[i])), None) for i in range(n)]
+            res = run_many(pool, jobs)
+            np.savez_compressed(os.path.join(GOLD, "duffing_rk45.npz"),
+                                **pack(res, dict(y0=y0, gamma=gamma, omega=omega, tf=10.0, dt0=1e-2, rtol=1e-9, atol=1e-9)))
+            att = np.array([r["attempts"] for r in res])
+            print("duffing_rk45: attempts mean %.1f min %d max %d" % (att.mean(), att.min(), att.max()))
         if want("edge"):
             # oversized first steps (2 consecutive rejections -> 3-term controller), loose/tight
             # tolerances, dt0 > tf - t0 (the |tf-t|/2 clamp), very short spans

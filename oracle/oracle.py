@@ -18,7 +18,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libdesolver_oracle.so")
 
-RHS_LINEAR, RHS_LORENZ, RHS_VDP, RHS_NBODY, RHS_SHO, RHS_FORCED = 0, 1, 2, 3, 4, 5
+RHS_LINEAR, RHS_LORENZ, RHS_VDP, RHS_NBODY, RHS_SHO, RHS_FORCED, RHS_DUFFING = 0, 1, 2, 3, 4, 5, 6
 STATUS_OK, STATUS_TOL_FAIL, STATUS_RUNNING = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)

@@ -252,3 +252,28 @@ def test_solve_ivp_wrapper():
     assert tuple(ens.y.shape) == (3, 64, 2) and tuple(ens.t.shape) == (64, 2)
     with pytest.raises(ValueError):
         de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.0), y0, t_eval=[2.0])
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_time_dependent_plugins_run_in_the_fused_kernel(strict):
+    """Non-autonomous right-hand sides in the persistent kernel: the stage time t + c_s h is formed per lane.
+    `forced` is the reference's own test fixture (golden: forced_rk45 / forced_rk87), `duffing` the system of its
+    example notebooks with per-trajectory forcing amplitude and frequency (golden: duffing_rk45)."""
+    de = _de()
+    for key, method in (("rk45", "RK45"), ("rk87", "RK87")):
+        g = load_golden("forced_%s.npz" % key)
+        a = _run(de.rhs_plugins.forced, g["y0"], 5.0, 1e-2, 1e-10, method, strict=strict)
+        assert a._launches == 1                                   # one persistent launch, not the stage-level path
+        _compare(a, g["y_final"], g["accepted"], g["attempts"], count_fraction=1.0 if key == "rk45" else 0.95)
+    g = load_golden("duffing_rk45.npz")
+    consts = dict(gamma=torch.as_tensor(g["gamma"]), omega=torch.as_tensor(g["omega"]))
+    a = _run(de.rhs_plugins.duffing, g["y0"], 10.0, 1e-2, 1e-9, "RK45", constants=consts, strict=strict)
+    assert a._launches == 1
+    frac, err = _compare(a, g["y_final"], g["accepted"], g["attempts"])
+    print("duffing strict=%s: counts identical %.4f, max rel err %.3g" % (strict, frac, err))
+    # the same callable through the stage-level path (torch cos between the stage kernels) agrees
+    b = de.OdeSystem(de.rhs_plugins.duffing, torch.as_tensor(g["y0"]), t=(0.0, 10.0), dt=1e-2, rtol=1e-9, atol=1e-9,
+                     constants={k: v.cuda() for k, v in consts.items()}, ensemble=True, strict=strict)
+    b.use_fused = False
+    b.integrate()
+    _compare(b, g["y_final"], g["accepted"], g["attempts"])

@@ -77,6 +77,17 @@ def test_other_tableaux_match_reference(name, cls):
     _check(g, r, state_tol=5e-12)
 
 
+def test_duffing_rk45_matches_reference():
+    """Time-dependent right-hand side with per-trajectory forcing (cos through libm vs numpy)."""
+    g = load_golden("duffing_rk45.npz")
+    n = g["y0"].shape[1]
+    prm = np.stack([np.full(n, 0.2), np.full(n, -1.0), np.full(n, 1.0), g["gamma"], g["omega"]])
+    r = orc.erk_ensemble(orc.RHS_DUFFING, g["y0"], 0.0, 10.0, 1e-2, 1e-9, 1e-9, *tb.rk_arrays("RK45CKSolver"), params=prm,
+                         threads=4)
+    assert np.array_equal(r["accepted"], g["accepted"]) and np.array_equal(r["accepted"] + r["rejected"], g["attempts"])
+    assert rel_inf(r["y"], g["y_final"]).max() <= 1e-12
+
+
 def test_edge_cases_match_reference():
     # oversized dt0 (double rejections -> 3-term controller), dt0 > span clamp, tiny spans
     g, r = _erk("edge_rk45.npz", "RK45CKSolver", orc.RHS_LORENZ, params=LORENZ_P)
