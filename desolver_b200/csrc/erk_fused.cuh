@@ -177,7 +177,11 @@ constexpr int erk_min_blocks()
 // device-resident kernel 3.6 % (3.53 -> 3.66 ms: different register allocation in the hot loop).
 // EV: event detection after every accepted step (dsb_erk_run_args.n_events > 0), see the event block below.
 template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
-__global__ void __launch_bounds__(ERK_THREADS, (EV ? (erk_min_blocks<Rhs, Tab::S>() > 4 ? 4 : erk_min_blocks<Rhs, Tab::S>())
+#ifndef DSB_EV_MAX_BLOCKS
+#define DSB_EV_MAX_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(ERK_THREADS, (EV ? (erk_min_blocks<Rhs, Tab::S>() > DSB_EV_MAX_BLOCKS ? DSB_EV_MAX_BLOCKS
+                                                                                                         : erk_min_blocks<Rhs, Tab::S>())
                                                    : erk_min_blocks<Rhs, Tab::S>()))
 erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 {
@@ -197,21 +201,18 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 #ifdef DSB_FT_SLOTS
     constexpr int FT_SLOTS = DSB_FT_SLOTS;
 #else
-    constexpr int FT_SLOTS = erk_min_blocks<Rhs, Tab::S>() >= 8 ? 4 : 5;
+    constexpr int FT_SLOTS = (EV || erk_min_blocks<Rhs, Tab::S>() >= 8) ? 4 : 5;   // EV: its own arrays need the room
 #endif
     __shared__ double2 s_ft[(STRICT ? 1 : ft::HOT_ENTRIES) * FT_SLOTS];   // hot octaves of the step-size factor table
     // per-thread statistics slots (no atomics): attempts, accepted steps, failed / unfinished trajectories
     __shared__ unsigned long long s_att[ERK_THREADS], s_acc[ERK_THREADS];
     __shared__ unsigned s_fail[ERK_THREADS], s_run[ERK_THREADS];
     s_att[threadIdx.x] = 0; s_acc[threadIdx.x] = 0; s_fail[threadIdx.x] = 0; s_run[threadIdx.x] = 0;
-    // event detection state (EV only): coefficients of the hyperplane events, and per thread the state before the
-    // last commit (the step's interpolant and the roll-back of a terminal event need it), g at the step start and the
-    // time of each event's last recorded occurrence
+    // event detection state (EV only): coefficients of the hyperplane events, and per thread g at the step start
+    // and the time of each event's last recorded occurrence
     constexpr int NE = DSB_MAX_EVENTS, EVW = Rhs::DIM + 2;
     __shared__ double s_evc[EV ? NE * EVW : 1];
     __shared__ int s_evf[EV ? NE : 1];
-    __shared__ double s_yprev[EV ? Rhs::DIM : 1][EV ? ERK_THREADS : 1];
-    __shared__ double s_tprev[EV ? 2 : 1][EV ? ERK_THREADS : 1];
     __shared__ double s_gprev[EV ? NE : 1][EV ? ERK_THREADS : 1];
     __shared__ double s_evlast[EV ? NE : 1][EV ? ERK_THREADS : 1];
     const int ne = EV ? (P.a.n_events < NE ? P.a.n_events : NE) : 0;
@@ -591,13 +592,10 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 
         // ------------------------------------------------------------ accept: commit and start the next step
         unsigned ev_mask = 0;
+        double yprev[D], tprev = t, dtprev = dt;                        // EV: the state before the commit (interpolant,
+#pragma unroll                                                          // roll-back); dead right after the event block
+        for (int d = 0; d < D; ++d) yprev[d] = y[d];
         if (live && !redo) {
-            if (EV) {                                                   // state before the commit (interpolant, roll-back)
-#pragma unroll
-                for (int d = 0; d < D; ++d) s_yprev[d][threadIdx.x] = y[d];
-                s_tprev[0][threadIdx.x] = t;
-                s_tprev[1][threadIdx.x] = dt;
-            }
 #pragma unroll
             for (int d = 0; d < D; ++d)
                 y[d] = (STRICT || tab.fsal()) ? A::add(y[d], dY[d]) : fma(h, dY[d], y[d]);   // :1015
@@ -612,12 +610,15 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             }
             if (EV && !final_leg) {
                 // an event is searched for iff g changes sign over the step (utilities/optimizer.py:252)
-                for (int e = 0; e < ne; ++e) {
-                    const double g1 = ev_g(e, t, y), g0 = s_gprev[e][threadIdx.x];
-                    s_gprev[e][threadIdx.x] = g1;
-                    const int dir = s_evf[e] & 3;
-                    const bool rising = g0 < 0.0;
-                    if (g0 * g1 < 0.0 && (dir == 0 || (dir == 1) == rising)) ev_mask |= 1u << e;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    if (e < ne) {
+                        const double g1 = ev_g(e, t, y), g0 = s_gprev[e][threadIdx.x];
+                        s_gprev[e][threadIdx.x] = g1;
+                        const int dir = s_evf[e] & 3;
+                        const bool rising = g0 < 0.0;
+                        if (g0 * g1 < 0.0 && (dir == 0 || (dir == 1) == rising)) ev_mask |= 1u << e;
+                    }
                 }
             }
             start_step();
@@ -631,10 +632,10 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 const int tid = threadIdx.x;
                 // the accepted step [t0, t1] and its cubic Hermite interpolant (integrator_types.py:109-119,
                 // utilities/interpolation.py:41-61): p0, p1 = states, m0 = the step's first stage, m1 = rhs(t1, y1)
-                const double t0 = s_tprev[0][tid], t1 = t, trange = t1 - t0;
+                const double t0 = tprev, t1 = t, trange = t1 - t0;
                 double y0[D], f1[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) y0[d] = s_yprev[d][tid];
+                for (int d = 0; d < D; ++d) y0[d] = yprev[d];
                 eval_rhs<Rhs>(t1, y, prm, f1);
                 double root[NE];
                 int which[NE], cnt = 0;
@@ -653,16 +654,19 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     const double c2 = 3.0 * (g1 - g0) - 2.0 * a - b, c3 = 2.0 * (g0 - g1) + a + b;
                     // bracketed Newton on [0, 1] (the reference runs Brent's method on the same function)
                     double lo = 0.0, hi = 1.0, tau = g0 / (g0 - g1);
-                    for (int it = 0; it < 100; ++it) {
+                    for (int it = 0; it < 64; ++it) {
                         const double G = fma(fma(fma(c3, tau, c2), tau, a), tau, g0);
                         if (G == 0.0) break;
                         if ((G < 0.0) == (g0 < 0.0)) lo = tau; else hi = tau;
                         const double dG = fma(fma(3.0 * c3, tau, 2.0 * c2), tau, a);
-                        double nxt = tau - G / dG;
+                        const double step = G / dG;
+                        // converged: the Newton correction is below the spacing of tau.  (Testing the bracket first
+                        // would bisect a still-wide bracket whenever rounding puts the last iterate on its edge.)
+                        if (fabs(step) <= 2.3e-16) break;
+                        double nxt = tau - step;
                         if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
-                        const bool conv = fabs(nxt - tau) <= 4.0e-16 || hi - lo <= 4.0e-16;
                         tau = nxt;
-                        if (conv) break;
+                        if (hi - lo <= 4.0e-16) break;
                     }
                     root[cnt] = fma(tau, trange, t0);
                     which[cnt] = e;
@@ -716,7 +720,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 #pragma unroll
                     for (int d = 0; d < D; ++d) y[d] = y0[d];
                     t = t0;
-                    dt = s_tprev[1][tid];
+                    dt = dtprev;
                     acc--;
                     tf_lane = term_root;
                     final_leg = true;

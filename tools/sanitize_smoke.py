@@ -39,6 +39,26 @@ for fused in (True, False):
     a.method = "BABS9O7H"
     a.use_fused = fused
     a.integrate()
+# second-session paths: kernel-side init (reset + rerun), host-resident ensembles (flow-controlled launch and the
+# chunked fallback), device event detection (recorded + terminal), time-dependent plugins
+a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0, 0.3), dt=1e-2, rtol=1e-8, atol=1e-8, ensemble=True)
+a.integrate()
+a.reset()
+a.integrate()
+yh = torch.as_tensor(de.benchmarks.lorenz_ensemble(2500)).pin_memory()
+for mode in ("streamed", "chunked"):
+    h = de.OdeSystem(de.rhs_plugins.lorenz, yh, t=(0, 0.3), dt=1e-2, rtol=1e-8, atol=1e-8, ensemble=True, host_io=True, host_chunks=3)
+    h.host_pipeline = mode
+    h.integrate()
+    assert h.host_pipeline == mode and bool((h.status == 0).all())
+cc = de.events.component_crossing
+a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0, 1.0), dt=1e-2, rtol=1e-8, atol=1e-8, ensemble=True)
+a.event_capacity = 4
+a.integrate(events=[cc(0, 0.0, dim=3), cc(1, 0.0, dim=3, direction=1, is_terminal=True), cc(2, 25.0, dim=3)])
+assert int(a.events.count.sum()) > 0
+for rhs in (de.rhs_plugins.forced, de.rhs_plugins.duffing):
+    a = de.OdeSystem(rhs, torch.as_tensor(y2), t=(0, 1.0), dt=1e-2, rtol=1e-8, atol=1e-8, ensemble=True)
+    a.integrate()
 a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, np.array([1.0, 0.0]), t=(0, 1.0), dt=0.05)
 a.method = "ABAS5O6H"
 a.integrate()
