@@ -157,6 +157,8 @@ def lib():
     L.dsb_erk_run.argtypes = [C.c_void_p, C.POINTER(ErkRunArgs), C.c_void_p]
     L.dsb_erk_run_host.restype = C.c_int
     L.dsb_erk_run_host.argtypes = [C.c_void_p, C.POINTER(ErkHostArgs), C.c_void_p]
+    L.dsb_dgemm.restype = C.c_int
+    L.dsb_dgemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     L.dsb_erk_run_launches.restype = C.c_int
     L.dsb_erk_run_launches.argtypes = [C.c_void_p]
     L.dsb_dense_eval.restype = C.c_int
@@ -194,6 +196,25 @@ def check(status, what=""):
     if status != DSB_OK:
         msg = lib().dsb_last_error().decode("utf-8", "replace")
         raise LibraryError("%s failed with status %d: %s" % (what or "libdesolver_b200 call", status, msg))
+
+
+def dgemm(A, B, out=None):
+    """C = A @ B for contiguous float64 CUDA matrices through the library's FP64 tensor-core kernel (dsb_dgemm).
+    Returns None when the shape is outside the kernel's tiling (the caller then uses a library GEMM)."""
+    import torch
+    M, K = A.shape
+    K2, N = B.shape
+    if (K != K2 or M % 64 or N % 128 or K % 16 or A.dtype != torch.float64 or B.dtype != torch.float64
+            or not (A.is_cuda and B.is_cuda and A.is_contiguous() and B.is_contiguous())
+            or A.data_ptr() % 16 or B.data_ptr() % 16):
+        return None
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    status = lib().dsb_dgemm(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, current_stream_ptr(A.device))
+    if status == DSB_ERR_UNSUPPORTED:
+        return None
+    check(status, "dsb_dgemm")
+    return out
 
 
 def current_stream_ptr(device):

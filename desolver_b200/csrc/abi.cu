@@ -23,6 +23,7 @@ int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n,
                       const double *tq, int64_t tq_stride, double *out, cudaStream_t stream);
 int launch_dense_append(double *nodes, int32_t *node_count, int32_t cap, int64_t n, int32_t dim, const double *t,
                         const double *y, const double *f, const int32_t *flags, int32_t mask, cudaStream_t stream);
+int launch_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, int sm_count, cudaStream_t stream);
 int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream);
 int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
 int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream);
@@ -182,6 +183,15 @@ int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *st
 }
 
 int dsb_erk_stage_launches(dsb_erk_handle h) { return h ? 1 + h->stages + 3 : 0; }
+
+int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, void *stream)
+{
+    if (!A || !B || !C) { set_error("dsb_dgemm: null pointer"); return DSB_ERR_BAD_ARGUMENT; }
+    int dev = 0, sms = 0;
+    DSB_CUDA_CHECK(cudaGetDevice(&dev));
+    DSB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_dgemm(A, B, C, M, N, K, sms, (cudaStream_t)stream);
+}
 
 int dsb_dense_append(double *nodes, int32_t *node_count, int32_t node_capacity, int64_t n, int32_t dim, const double *t,
                      const double *y, const double *f, const int32_t *flags, int32_t mask, void *stream)

@@ -835,11 +835,17 @@ class OdeSystem(object):
                 torch.cuda.synchronize(dev)
                 return None
 
-        graph, rhs_calls_per_attempt = None, S + (1 if dense else 0)
+        graph, rhs_calls_per_attempt, rewarm = None, S + (1 if dense else 0), False
         while True:
             if first:
                 one_attempt(True)                    # eager: integrate()-entry logic, allocator warm-up
                 first = False
+                graph = capture()
+            elif rewarm:
+                # after a compaction the right-hand side sees new shapes (e.g. the linear plugin leaves its tiled GEMM
+                # for the library one, whose first call creates handles and workspaces): never inside a capture
+                one_attempt(False)
+                rewarm = False
                 graph = capture()
             elif graph is not None:
                 graph.replay()
@@ -870,7 +876,7 @@ class OdeSystem(object):
                                   and v.shape[-1] == n else v) for k, v in self.__consts.items()}
                     a, y_view, t_view = bind(work, buf, m)
                     self._compactions += 1
-                    graph = capture()                # new working set, new addresses: re-capture
+                    graph, rewarm = None, True       # new working set, new addresses: one eager attempt, then re-capture
             if attempts > self._step_cap:
                 break
         if index is not None:

@@ -62,8 +62,21 @@ harmonic_oscillator.plugin_defaults = dict(k=1.0, m=1.0)
 
 
 def linear(t, y, A=None):
-    """Dense linear system y' = A @ y (A shared by the whole ensemble; y is (n,) or (n, N))."""
+    """Dense linear system y' = A @ y (A shared by the whole ensemble; y is (n,) or (n, N)).
+
+    For an ensemble of CUDA float64 columns whose shape fits its tiling, the product is the library's own FP64
+    tensor-core kernel (dsb_dgemm, csrc/dgemm.cu); otherwise -- numpy arrays, the reference, odd shapes -- the
+    array library's matmul.  `linear.use_library_gemm = True` forces the latter."""
+    if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2
+            and getattr(A, "is_cuda", False)):
+        from .backend import cuda_backend as cb
+        out = cb.dgemm(A, y)
+        if out is not None:
+            return out
     return A @ y
+
+
+linear.use_library_gemm = False
 
 
 linear.device_plugin = "linear"

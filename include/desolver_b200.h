@@ -268,6 +268,14 @@ DSB_API int dsb_symp_stage_begin(dsb_symp_handle h, const dsb_symp_stage_args *a
 DSB_API int dsb_symp_stage_accumulate(dsb_symp_handle h, const dsb_symp_stage_args *a, int stage, const double *f, void *stream);
 DSB_API int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void *stream);
 
+/* ---- dense linear right-hand side ---------------------------------------------------------
+ * K = A @ Y for the linear benchmark system y' = A y over an ensemble stored as Y[n][columns]
+ * (rhs_plugins.linear; the reference evaluates the user's `A @ y` inside compute_step,
+ * integrators/components/runge_kutta_methods.py:49-54): C[M][N] = A[M][K] * B[K][N], row-major fp64, as a
+ * hand-written FP64 tensor-core kernel (mma.sync.m8n8k4.f64, csrc/dgemm.cu).  Needs M % 64 == 0, N % 128 == 0,
+ * K % 16 == 0 and 16-byte aligned pointers, else DSB_ERR_UNSUPPORTED (the caller then uses a library GEMM). */
+DSB_API int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, void *stream);
+
 /* ---- dense output ------------------------------------------------------------------------
  * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
  * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written
