@@ -312,6 +312,11 @@ class OdeSystem(object):
         a fused run, inside the kernel."""
         torch = _torch()
         n, dev = self.n_traj, self.device
+        if self.__dict__.get("_hist_alias") and not self.host_io:
+            # a history row handed out earlier (a[-1]) still refers to the state buffers: leave them to their
+            # holders and continue on fresh ones (an allocation, not a copy)
+            self._raw_y = torch.empty_like(self._y0)
+            self._raw_t = torch.empty((n,), dtype=torch.float64, device=dev)
         if getattr(self, "_raw_y", None) is None:
             self._raw_y = torch.empty_like(self._y0)
             self._raw_t = torch.empty((n,), dtype=torch.float64, device=dev)
@@ -323,6 +328,7 @@ class OdeSystem(object):
         self._pristine = True
         self._stats = None
         self._event_log = None
+        self._hist_alias = False
         self._hist_y = [self._y0]                         # row 0 = initial condition (never written to)
         self._hist_t = [self.__t0]                        # scalars stand for "every trajectory at this time"
         self._nodes = None
@@ -339,6 +345,14 @@ class OdeSystem(object):
             self._raw_accepted.zero_()
             self._raw_rejected.zero_()
             self._raw_status.zero_()
+
+    def _detach_history(self):
+        if self.__dict__.get("_hist_alias"):
+            self._hist_alias = False
+            if not self.host_io and self._hist_y and self._hist_y[-1] is self._raw_y:
+                # the history row (and whoever was handed a[-1]) keeps the old buffers; the state moves to copies
+                self._raw_y = self._raw_y.clone()
+                self._raw_t = self._raw_t.clone()
 
     def _hist_time(self, row):
         torch = _torch()
@@ -1008,6 +1022,7 @@ class OdeSystem(object):
             if not events:
                 events = None
         tf = float(t) if t is not None else self.__tf
+        self._detach_history()
         if callback is None:
             callbacks = []
         elif isinstance(callback, (tuple, list)):
@@ -1074,8 +1089,11 @@ class OdeSystem(object):
                 self._hist_y.append(self._raw_y)              # the pinned result buffer itself (no 25 MB host copy)
                 self._hist_t.append(float(tf) if fused_stats[2] + fused_stats[3] == 0 else self._raw_t.cpu())
             else:
-                self._hist_y.append(self._y.clone())
-                self._hist_t.append(self._t.clone())
+                # the newest history row aliases the live state; it is copied only if a later integrate() call is
+                # about to advance that state (_detach_history) -- reset() + integrate() loops never pay for it
+                self._hist_y.append(self._raw_y)
+                self._hist_t.append(self._raw_t)
+                self._hist_alias = True
             # error policy: run everything to completion, then raise like the reference does
             # (:1089-1093 wraps integrator_types.py:220-224) if any trajectory failed
             if fused_stats is not None:

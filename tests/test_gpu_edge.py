@@ -144,3 +144,22 @@ def test_dense_store_overflow_and_continuation():
     with pytest.raises(MemoryError):                # ... but evaluating it is refused
         c.sol(0.5)
     assert a.sol is not None and de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(y0), ensemble=True).sol is None
+
+
+def test_history_rows_survive_later_integrations_and_resets():
+    """`a[-1]` aliases the live state until the state moves on: rows handed out earlier must keep their values when
+    integrate() continues or the system is reset and run again."""
+    import desolver_b200 as de
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(512, seed=9))
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    a.integrate(0.5)
+    row1_y, row1_t = a[-1].y, a[-1].t
+    keep_y, keep_t = row1_y.clone(), row1_t.clone()
+    a.integrate(1.0)
+    assert torch.equal(row1_y, keep_y) and torch.equal(row1_t, keep_t) and torch.equal(a[1].y, keep_y)
+    assert float(a[-1].t.min()) == 1.0 and not torch.equal(a[-1].y, keep_y)
+    end_y = a[-1].y
+    keep_end = end_y.clone()
+    a.reset()
+    a.integrate(0.25)
+    assert torch.equal(end_y, keep_end) and float(a[-1].t.max()) == 0.25 and len(a) == 2
