@@ -172,6 +172,27 @@ constexpr int erk_min_blocks()
 #endif
 }
 
+// Flow-control hooks of dsb_erk_run_host, kept out of line so that their registers do not enter the allocation of the
+// hot loop.  flow_wait: spin (bounded, ~2 s) until `*avail >= want`; returns false after a time-out.
+static __device__ __noinline__ bool flow_wait(const uint32_t *avail, unsigned want)
+{
+    unsigned have;
+    for (long long spins = 0; spins <= 4000000; ++spins) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(avail) : "memory");
+        if (have >= want) return true;
+        __nanosleep(500);
+    }
+    return false;
+}
+// flow_done: results of one trajectory are stored -> bump its chunk's completion counter.  Results and counter both live
+// in device memory: L2 is the coherence point of the SMs, the stream wait and the copy engine, so a device-scope fence
+// orders them (a system-scope fence here cost 0.6 ms per 2^20 trajectories).
+static __device__ __noinline__ void flow_done(uint32_t *counter)
+{
+    __threadfence();
+    atomicAdd(counter, 1u);
+}
+
 // FLOW: the launch overlaps its own uploads / downloads (dsb_erk_run_host): it waits for `avail` before loading a
 // trajectory and counts stored results in `done`.  A separate instantiation, because even untaken the hooks cost the
 // device-resident kernel 3.6 % (3.53 -> 3.66 ms: different register allocation in the hot loop).
@@ -208,6 +229,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     __shared__ unsigned long long s_att[ERK_THREADS], s_acc[ERK_THREADS];
     __shared__ unsigned s_fail[ERK_THREADS], s_run[ERK_THREADS];
     s_att[threadIdx.x] = 0; s_acc[threadIdx.x] = 0; s_fail[threadIdx.x] = 0; s_run[threadIdx.x] = 0;
+    __shared__ int s_gave_up[ERK_THREADS / 32];          // FLOW: this warp's wait for its initial states timed out
+    if (FLOW && lane == 0) s_gave_up[threadIdx.x >> 5] = 0;
     // event detection state (EV only): coefficients of the hyperplane events, and per thread g at the step start
     // and the time of each event's last recorded occurrence
     constexpr int NE = DSB_MAX_EVENTS, EVW = Rhs::DIM + 2;
@@ -235,7 +258,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 
     // ---- per-lane trajectory state (registers) ----
     long long idx = 0;
-    bool live = false, exhausted = false, final_step = false, gave_up = false;
+    bool live = false, exhausted = false, final_step = false;
     double y[D], prm[NP > 0 ? NP : 1], k[S][D], scale[D];
     double t = 0.0, dt = 0.0, h = 0.0, h0 = 0.0;
     double corr_first = 1.0, x_last = 1.0, x_last_last = 1.0;
@@ -259,15 +282,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         s_acc[threadIdx.x] += (unsigned long long)acc;
         s_fail[threadIdx.x] += st == (int)DSB_TRAJ_TOL_FAIL;
         s_run[threadIdx.x] += st == (int)DSB_TRAJ_RUNNING;
-        if (FLOW && P.a.done) {
-            // dsb_erk_run_host: a download stream waits for "every trajectory of this chunk is stored"
-#ifdef DSB_DONE_FENCE_SYSTEM
-            __threadfence_system();
-#else
-            __threadfence();          // results and counter both live in device memory: L2 is the coherence point of
-#endif                                // the SMs, the stream wait and the copy engine
-            atomicAdd(P.a.done + (idx >> P.a.done_shift), 1u);
-        }
+        // dsb_erk_run_host: a download stream waits for "every trajectory of this chunk is stored"
+        if (FLOW && P.a.done) flow_done(P.a.done + (idx >> P.a.done_shift));
     };
     // per-warp totals -> counters[2..5] (one atomic per statistic per warp, at warp exit)
     auto flush_stats = [&]() {
@@ -365,19 +381,14 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 // claiming and counts the abandoned trajectories as done, so that no download stream waits forever;
                 // counters[6] tells the host.
                 const unsigned want = (unsigned)((long long)(base + cnt) < n ? (long long)(base + cnt) : n);
-                if (lane == 0 && !gave_up) {
-                    unsigned have;
-                    long long spins = 0;
-                    for (;;) {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(P.a.avail) : "memory");
-                        if (have >= want) break;
-                        if (++spins > 4000000) { gave_up = true; break; }
-                        __nanosleep(500);
-                    }
-                    if (gave_up) atomicExch((unsigned long long *)P.a.counters + 6, 1ull);
+                int bad = s_gave_up[threadIdx.x >> 5];
+                if (lane == 0 && !bad && !flow_wait(P.a.avail, want)) {
+                    bad = 1;
+                    s_gave_up[threadIdx.x >> 5] = 1;
+                    atomicExch((unsigned long long *)P.a.counters + 6, 1ull);
                 }
-                gave_up = __shfl_sync(FULL, gave_up ? 1 : 0, 0) != 0;
-                abandon = gave_up;
+                abandon = __shfl_sync(FULL, bad, 0) != 0;
+                if (abandon) s_gave_up[threadIdx.x >> 5] = 1;
             }
             long long mine = (long long)base + __popc(need & ((1u << lane) - 1u));
             if (FLOW && abandon) {

@@ -288,8 +288,9 @@ class OdeSystem(object):
         self._dev_accepted = torch.empty(n, dtype=torch.int32, device=dev)
         self._dev_rejected = torch.empty(n, dtype=torch.int32, device=dev)
         self._dev_status = torch.empty(n, dtype=torch.int32, device=dev)
-        self._counters = torch.zeros(8 * max(1, self.host_chunks), dtype=torch.int64, device=dev)
-        self._pipe_flags = torch.zeros(2 + max(1, self.host_chunks) * 2, dtype=torch.int32, device=dev)
+        # both are cleared by every run (counters.zero_() / the library's memset of the flags)
+        self._counters = torch.empty(8 * max(1, self.host_chunks), dtype=torch.int64, device=dev)
+        self._pipe_flags = torch.empty(2 + max(1, self.host_chunks) * 2, dtype=torch.int32, device=dev)
         self._pipe_streams = None
         self.host_pipeline = "streamed"      # "chunked": one dsb_erk_run launch per chunk (fallback without stream mem-ops)
 

@@ -63,7 +63,11 @@ int main(int argc, char **argv)
         cudaMemcpy(dt, dt0.data(), 8 * n, cudaMemcpyHostToDevice);
         cudaMemset(acc, 0, 4 * n); cudaMemset(rej, 0, 4 * n); cudaMemset(ctr, 0, 64);
         cudaEventRecord(e0);
+        #ifdef BENCH_FLOW
+        launch_erk_fused<Rhs, Tab, false, true>(args, sms * per_sm, 0);     // flow-controlled instantiation, hooks idle
+#else
         launch_erk_fused<Rhs, Tab, false>(args, sms * per_sm, 0);
+#endif
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (r > 0 && ms < best) best = ms;
