@@ -792,6 +792,15 @@ class OdeSystem(object):
             shape = tuple(self.dim) + ((m,) if self.ensemble else ())
             return a, buf["y_stage"].reshape(shape), (buf["t_stage"] if self.ensemble else buf["t_stage"].reshape(()))
 
+        # persistent stage arrays for right-hand sides with an `out=` argument (the linear plugin: 13 x 268 MB for the
+        # benchmark configuration, which would otherwise be allocated by every eager attempt AND inside every graph's
+        # private pool, and released again at the end of every integrate() call)
+        k_out = None
+        if getattr(self.equ_rhs, "supports_out", False) and self.ensemble:
+            cache = self.__dict__.get("_stage_k_cache")
+            if cache is None or len(cache) != S or tuple(cache[0].shape) != (D, n):
+                cache = self._stage_k_cache = [torch.empty((D, n), **f64) for _ in range(S)]
+            k_out = cache
         work, buf, m, index, consts = full, alloc(n), n, None, self.__consts
         a, y_view, t_view = bind(work, buf, m)
         can_compact = self.ensemble and self.compaction and not callbacks and not dense
@@ -825,7 +834,12 @@ class OdeSystem(object):
             handle.stage_begin(a, first_call, st)
             for s in range(S):
                 handle.stage_state(a, s, st)
-                k = self.equ_rhs(t_view, y_view, **consts)
+                if k_out is not None:
+                    # right-hand side that writes into a caller-owned array (rhs.supports_out): the S stage arrays are
+                    # owned by the system and reused by every attempt, graph and integrate() call -- no allocation
+                    k = self.equ_rhs(t_view, y_view, out=k_out[s].reshape(-1)[:D * m].reshape(D, m), **consts)
+                else:
+                    k = self.equ_rhs(t_view, y_view, **consts)
                 k = k.to(torch.float64).reshape(D, m)
                 K[s] = k if k.is_contiguous() else k.contiguous()      # keep alive until the attempt finishes
                 a.K[s] = K[s].data_ptr()

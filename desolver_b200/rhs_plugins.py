@@ -61,7 +61,7 @@ harmonic_oscillator.plugin_params = ("k", "m")
 harmonic_oscillator.plugin_defaults = dict(k=1.0, m=1.0)
 
 
-def linear(t, y, A=None):
+def linear(t, y, A=None, out=None):
     """Dense linear system y' = A @ y (A shared by the whole ensemble; y is (n,) or (n, N)).
 
     For an ensemble of CUDA float64 columns whose shape fits its tiling, the product is the library's own FP64
@@ -70,13 +70,17 @@ def linear(t, y, A=None):
     if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2
             and getattr(A, "is_cuda", False)):
         from .backend import cuda_backend as cb
-        out = cb.dgemm(A, y)
-        if out is not None:
-            return out
+        res = cb.dgemm(A, y, out=out if (out is not None and out.is_contiguous()) else None)
+        if res is not None:
+            return res
+    if out is not None and type(y).__module__.split(".")[0] == "torch" and out.is_contiguous():
+        import torch
+        return torch.matmul(A, y, out=out)
     return A @ y
 
 
 linear.use_library_gemm = False
+linear.supports_out = True        # rhs(t, y, out=array, **constants) writes the derivative into a caller-owned array
 
 
 linear.device_plugin = "linear"
