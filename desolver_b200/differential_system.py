@@ -597,10 +597,11 @@ class OdeSystem(object):
         from .events import EventLog
         coef = torch.as_tensor(np.stack([ev.coefficients(self.numel) for ev in events]), dtype=torch.float64).to(self.device)
         flags = torch.as_tensor([ev.flags for ev in events], dtype=torch.int32).to(self.device)
-        if self._event_log is None or self._event_log.events != list(events):
+        if self._event_log is None or self._event_log.compiled != list(events):
             records = torch.zeros((self.n_traj, int(self.event_capacity), self.numel + 2), dtype=torch.float64, device=self.device)
             count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
             self._event_log = EventLog(events, records, count, self.dim)
+            self._event_log.compiled = list(events)
         return coef, flags
 
     def _run_fused(self, tf, plugin, max_steps, first_call, events=None):
@@ -1025,17 +1026,17 @@ class OdeSystem(object):
         ensemble engine and raise.
         """
         torch = _torch()
+        user_events = None
         if events is not None:
-            from .events import HyperplaneEvent
-            events = [events] if callable(events) and not isinstance(events, (list, tuple)) else list(events)
-            if not all(isinstance(ev, HyperplaneEvent) for ev in events):
-                raise NotImplementedError("the device detects events of type desolver_b200.events.HyperplaneEvent "
-                                          "(g(t, y) = w.y + wt*t - c: component crossings, Poincare sections, time "
-                                          "marks); arbitrary Python event callables are not supported")
-            if len(events) > cb.MAX_EVENTS:
+            from .events import as_hyperplane
+            user_events = [events] if callable(events) and not isinstance(events, (list, tuple)) else list(events)
+            if len(user_events) > cb.MAX_EVENTS:
                 raise NotImplementedError("at most %d events per integrate() call" % cb.MAX_EVENTS)
+            # the device detects affine event functions g(t, y) = w.y + wt*t - c; an ordinary Python callable of that
+            # form (t - t_mark, y[0] - level, ...) is recognised by probing it, anything else raises
+            events = [as_hyperplane(ev, self.numel, self.__consts) for ev in user_events]
             if not events:
-                events = None
+                events = user_events = None
         tf = float(t) if t is not None else self.__tf
         self._detach_history()
         if callback is None:
@@ -1079,6 +1080,8 @@ class OdeSystem(object):
                 fused_stats = self._run_host_pipeline(tf, plugin)
             elif not callbacks and not eta:
                 self._run_fused(tf, plugin, self._step_cap, first_call=True, events=events)
+                if events:
+                    self._event_log.events = list(user_events)     # StateTuple.event is the caller's own object
                 fused_stats = self._fused_stats()
             else:
                 first = True

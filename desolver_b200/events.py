@@ -18,7 +18,7 @@ time marks) are all of this form.
 """
 import numpy as np
 
-__all__ = ["HyperplaneEvent", "component_crossing", "EventLog"]
+__all__ = ["HyperplaneEvent", "as_hyperplane", "component_crossing", "EventLog"]
 
 
 class HyperplaneEvent(object):
@@ -59,6 +59,59 @@ class HyperplaneEvent(object):
 
     def __repr__(self):
         return "<HyperplaneEvent %s direction=%d terminal=%s>" % (self.name, self.direction, self.is_terminal)
+
+
+def as_hyperplane(event, dim, constants=None):
+    """A `HyperplaneEvent` equal to `event` if that callable is an affine function of (t, y) -- which is checked, not
+    assumed: the coefficients are read off by probing `event` at the origin and the unit vectors (numpy arrays first,
+    CPU torch tensors if the callable insists on torch), and the fit is verified at random points.  Typical scipy-style
+    events -- `t - t_mark`, `y[0] - level`, `y[1] + 2*y[0]` -- qualify and then run on the device unchanged; anything
+    else (products, `requires_dstate` events, per-trajectory constants) raises NotImplementedError."""
+    if isinstance(event, HyperplaneEvent):
+        return event
+    if getattr(event, "requires_dstate", False):
+        raise NotImplementedError("events with requires_dstate=True are not supported on the device")
+    consts = {k: v for k, v in (constants or {}).items()}
+    for v in consts.values():
+        if getattr(v, "ndim", 0) >= 1 and type(v).__module__.split(".")[0] == "torch" and v.is_cuda:
+            consts = {k: (c.cpu() if hasattr(c, "cpu") else c) for k, c in consts.items()}
+            break
+
+    def probe(make):
+        def g(t, y):
+            return float(np.asarray(event(make(t, scalar=True), make(y), **consts)).reshape(-1)[0])
+        return g
+    makers = [lambda v, scalar=False: np.float64(v) if scalar else np.asarray(v, dtype=np.float64)]
+    try:
+        import torch
+        makers.append(lambda v, scalar=False: torch.as_tensor(v, dtype=torch.float64))
+    except ImportError:
+        pass
+    last = None
+    for make in makers:
+        try:
+            g = probe(make)
+            zero = np.zeros(dim)
+            g0 = g(0.0, zero)
+            wt = g(1.0, zero) - g0
+            w = np.array([g(0.0, np.eye(dim)[d]) - g0 for d in range(dim)])
+            rng = np.random.default_rng(12345)
+            for _ in range(4):
+                tt, yy = float(rng.uniform(-3, 3)), rng.uniform(-3, 3, size=dim)
+                want = g(tt, yy)
+                fit = float(w @ yy) + wt * tt + g0
+                if not abs(want - fit) <= 1e-9 * (1.0 + abs(want)):
+                    raise NotImplementedError("event %r is not an affine function of (t, y): the device detects hyperplane "
+                                              "events only (desolver_b200.events.HyperplaneEvent)" % (event,))
+            hp = HyperplaneEvent(w, c=-g0, wt=wt, direction=getattr(event, "direction", 0),
+                                 is_terminal=getattr(event, "is_terminal", False), name=getattr(event, "__name__", repr(event)))
+            hp.source = event
+            return hp
+        except NotImplementedError:
+            raise
+        except Exception as exc:                      # the callable could not digest this array type: try the next one
+            last = exc
+    raise NotImplementedError("event %r could not be probed for an affine form (%r)" % (event, last))
 
 
 def component_crossing(index, value=0.0, dim=None, direction=0, is_terminal=False):

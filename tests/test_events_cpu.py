@@ -38,3 +38,26 @@ def test_event_fixtures_are_well_formed():
             # a terminated trajectory ends at its last event
             last = np.array([g["records"][i, g["count"][i] - 1, 0] for i in np.nonzero(term)[0]])
             assert np.max(np.abs(last - g["t_final"][term])) <= 1e-9
+
+
+def test_affine_callables_are_recognised_and_others_refused():
+    import pytest
+    import torch
+    from desolver_b200.events import as_hyperplane
+
+    def time_event(t, y, **kwargs):
+        return np.asarray(t - np.pi / 8)
+    time_event.is_terminal = True
+    h = as_hyperplane(time_event, 2)
+    assert h.source is time_event and h.is_terminal and h.wt == 1.0 and abs(h.c - np.pi / 8) < 1e-16 and not h.w.any()
+    h = as_hyperplane(lambda t, y, k=2.0: y[1] + k * y[0] - 0.5, 2, dict(k=3.0))
+    assert np.allclose(h.w, [3.0, 1.0]) and h.wt == 0.0 and h.c == 0.5
+    h = as_hyperplane(lambda t, y: torch.as_tensor(y[0]).to(torch.float64) - 1.0, 3)      # torch-only callable
+    assert np.array_equal(h.w, [1.0, 0.0, 0.0]) and h.c == 1.0
+    for bad in (lambda t, y: (t - 1.0) * (t - 2.0), lambda t, y: y[0] * y[1], lambda t, y: np.sin(y[0])):
+        with pytest.raises(NotImplementedError):
+            as_hyperplane(bad, 2)
+    ev = lambda t, y, dy: dy[0]
+    ev.requires_dstate = True
+    with pytest.raises(NotImplementedError):
+        as_hyperplane(ev, 2)

@@ -135,6 +135,24 @@ def test_single_system_event_list_has_the_reference_shape():
     lst = a.events
     assert isinstance(lst, list) and len(lst) == 1 and lst[0].event is ev
     assert abs(float(lst[0].t) - np.pi / 2) <= 1e-8 and abs(float(lst[0].y[0])) <= 1e-12
-    with pytest.raises(NotImplementedError):
+    # plain Python callables of affine form are recognised by probing and run on the device (the reference's own
+    # event tests use exactly these: a time mark and a level of one component, tests/test_event_detection.py:22-29,83-91)
+    def time_event(t, y, **kwargs):
+        return np.asarray(t - np.pi / 8)
+    time_event.is_terminal = True
+    time_event.direction = 0
+
+    def first_y_event(t, y, **kwargs):
+        return y[0] - np.cos(np.pi / 16)
+    a.reset()
+    a.integrate(events=[time_event, first_y_event])
+    assert a.integration_status == "Integration terminated upon finding a triggered event."
+    assert abs(float(a[-1].t) - np.pi / 8) <= 1e-12
+    lst = a.events
+    assert [st.event for st in lst] == [first_y_event, time_event]
+    assert abs(float(lst[0].t) - np.pi / 16) <= 1e-5 and abs(float(lst[1].t) - np.pi / 8) <= 1e-12
+    # non-affine events are refused, not silently mis-detected
+    for bad in (lambda t, y: (t - 1.0) * (t - 2.0), lambda t, y: y[0] * y[1]):
         a.reset()
-        a.integrate(events=lambda t, y: y[0])
+        with pytest.raises(NotImplementedError):
+            a.integrate(events=bad)
