@@ -81,6 +81,10 @@ class ErkStageArgs(C.Structure):
         ("accepted", C.c_void_p), ("rejected", C.c_void_p), ("status", C.c_void_p),
         ("counters", C.c_void_p),
         ("one_step", C.c_int32),
+        ("n_events", C.c_int32), ("ev_capacity", C.c_int32),
+        ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
+        ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
+        ("ev_state", C.c_void_p), ("tf_per", C.c_void_p),
     ]
 
 
@@ -172,6 +176,8 @@ def lib():
         getattr(L, name).argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_int, C.c_void_p]
     L.dsb_erk_stage_finish.restype = C.c_int
     L.dsb_erk_stage_finish.argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_void_p]
+    L.dsb_erk_stage_finish_events.restype = C.c_int
+    L.dsb_erk_stage_finish_events.argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_int, C.c_void_p, C.c_void_p]
     L.dsb_erk_stage_launches.restype = C.c_int
     L.dsb_erk_stage_launches.argtypes = [C.c_void_p]
     L.dsb_symp_create.restype = C.c_int
@@ -263,6 +269,10 @@ class ErkHandle:
 
     def stage_finish(self, args, stream_ptr):
         check(lib().dsb_erk_stage_finish(self._h, C.byref(args), stream_ptr), "dsb_erk_stage_finish")
+
+    def stage_finish_events(self, args, phase, f1_ptr, stream_ptr):
+        check(lib().dsb_erk_stage_finish_events(self._h, C.byref(args), int(phase), f1_ptr, stream_ptr),
+              "dsb_erk_stage_finish_events")
 
     @property
     def stage_launches(self):

@@ -28,6 +28,7 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream);
 int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
 int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream);
 int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream);
+int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int phase, const double *f1, cudaStream_t stream);
 
 }  // namespace dsb
 
@@ -180,6 +181,11 @@ int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage
 int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream)
 {
     return stage_finish(h, a, (cudaStream_t)stream);
+}
+
+int dsb_erk_stage_finish_events(dsb_erk_handle h, const dsb_erk_stage_args *a, int phase, const double *f1, void *stream)
+{
+    return stage_finish_events(h, a, phase, f1, (cudaStream_t)stream);
 }
 
 int dsb_erk_stage_launches(dsb_erk_handle h) { return h ? 1 + h->stages + 3 : 0; }

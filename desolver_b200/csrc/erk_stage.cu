@@ -17,6 +17,24 @@
 namespace dsb {
 
 constexpr int FLAG_ACTIVE = 1, FLAG_FINAL = 2, FLAG_ACCEPTED = 4;
+constexpr int FLAG_FINAL_LEG = 8;      // re-integration to the root of a terminal event in progress (events are off)
+constexpr int EV_NE = DSB_MAX_EVENTS;  // ev_state rows: 0 t_prev, 1 dt_prev, 2.. last occurrence per event, 2+NE.. g per event
+
+__device__ __forceinline__ double tf_of(const dsb_erk_stage_args &a, long long i) { return a.tf_per ? a.tf_per[i] : a.tf; }
+
+// g_e(t, y + dy) of a hyperplane event for trajectory i (dy = nullptr: g_e(t, y))
+__device__ __forceinline__ double stage_ev_g(const dsb_erk_stage_args &a, int e, long long i, double t, const double *dy)
+{
+    const double *w = a.ev_coef + (long long)e * (a.dim + 2);
+    double g = w[a.dim] * t - w[a.dim + 1];
+    for (int d = 0; d < a.dim; ++d) {
+        if (w[d] != 0.0) {
+            const long long q = (long long)d * a.n + i;
+            g = fma(w[d], dy ? a.y[q] + dy[q] : a.y[q], g);
+        }
+    }
+    return g;
+}
 
 struct StageRow {
     int nterms;
@@ -44,8 +62,8 @@ __global__ void stage_begin_kernel(dsb_erk_stage_args a, int first_call)
     double t = a.t[i], dt = a.dt[i];
     if (first_call) {
         int st0 = a.status ? a.status[i] : (int)DSB_TRAJ_DONE;
-        bool go = st0 != (int)DSB_TRAJ_TOL_FAIL;
-        double span = a.tf - t;
+        bool go = st0 != (int)DSB_TRAJ_TOL_FAIL && st0 != (int)DSB_TRAJ_EVENT;
+        double span = tf_of(a, i) - t;
         if (go) {
             if (fabs(span) < DSB_EPS4) go = false;                                  // differential_system.py:956
             else {
@@ -53,17 +71,25 @@ __global__ void stage_begin_kernel(dsb_erk_stage_args a, int first_call)
                 if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);   // :973-974
             }
         }
-        go = go && (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);                    // :996
+        go = go && (dt != 0.0) && (fabs(tf_of(a, i) - t) >= DSB_EPS32);             // :996
         fl = go ? FLAG_ACTIVE : 0;
         a.trial[i] = 0;
         a.dt[i] = dt;
-        if (a.status) a.status[i] = go ? (int)DSB_TRAJ_RUNNING : (st0 == (int)DSB_TRAJ_TOL_FAIL ? st0 : (int)DSB_TRAJ_DONE);
+        const bool frozen = st0 == (int)DSB_TRAJ_TOL_FAIL || st0 == (int)DSB_TRAJ_EVENT;
+        if (a.status) a.status[i] = go ? (int)DSB_TRAJ_RUNNING : (frozen ? st0 : (int)DSB_TRAJ_DONE);
+        if (a.n_events > 0) {
+            for (int e = 0; e < a.n_events; ++e) {
+                a.ev_state[(long long)(2 + e) * a.n + i] = CUDART_NAN;
+                a.ev_state[(long long)(2 + EV_NE + e) * a.n + i] = stage_ev_g(a, e, i, t, nullptr);
+            }
+        }
     }
     if (i == 0) a.counters[1] = 0;                 // active count, re-accumulated by the controller kernel
     fl &= ~FLAG_ACCEPTED;
     if ((fl & FLAG_ACTIVE) && a.trial[i] == 0) {
-        bool final_step = fabs(dt + t) > fabs(a.tf);                                // :997
-        double h = final_step ? (a.tf - t) : dt;
+        const double tfi = tf_of(a, i);
+        bool final_step = fabs(dt + t) > fabs(tfi);                                 // :997
+        double h = final_step ? (tfi - t) : dt;
         a.h[i] = h;
         a.h0[i] = h;
         fl = final_step ? (fl | FLAG_FINAL) : (fl & ~FLAG_FINAL);
@@ -321,15 +347,22 @@ __global__ void stage_controller_kernel(dsb_erk_stage_args a, FinalRows fr, int 
                 redo = f < DSB_REJECT_BELOW;
             }
             if (!redo) {
+                double dt = a.dt[i];
+                if (a.n_events > 0) {                                   // the roll-back of a terminal event needs these
+                    a.ev_state[i] = a.t[i];
+                    a.ev_state[a.n + i] = dt;
+                }
                 double t = A::add(a.t[i], h);
                 a.t[i] = t;
-                double dt = a.dt[i];
                 if (!(fl & FLAG_FINAL)) { dt = new_dt; a.dt[i] = dt; }
                 a.trial[i] = 0;
                 if (a.accepted) a.accepted[i] += 1;
                 fl |= FLAG_ACCEPTED;
-                bool more = (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
-                if (!more) { fl &= ~FLAG_ACTIVE; if (a.status) a.status[i] = (int)DSB_TRAJ_DONE; }
+                bool more = (dt != 0.0) && (fabs(tf_of(a, i) - t) >= DSB_EPS32);
+                if (!more) {
+                    fl &= ~FLAG_ACTIVE;
+                    if (a.status) a.status[i] = (fl & FLAG_FINAL_LEG) ? (int)DSB_TRAJ_EVENT : (int)DSB_TRAJ_DONE;
+                }
                 else if (a.one_step) { fl &= ~FLAG_ACTIVE; if (a.status) a.status[i] = (int)DSB_TRAJ_RUNNING; }
             } else {
                 if (a.rejected) a.rejected[i] += 1;
@@ -361,6 +394,127 @@ __global__ void stage_commit_kernel(dsb_erk_stage_args a)
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e % a.n;
         if (a.flags[i] & FLAG_ACCEPTED) a.y[e] = A::add(a.y[e], a.dY[e]);
+    }
+}
+
+// ---- events, phase 0 tail: y_stage = y + dY, t_stage = t (already advanced where the attempt was accepted) ----
+__global__ void stage_y1_kernel(dsb_erk_stage_args a)
+{
+    const long long total = (long long)a.dim * a.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        a.y_stage[e] = a.y[e] + a.dY[e];
+        if (e < a.n) a.t_stage[e] = a.t[e];
+    }
+}
+
+// ---- events, phase 1: locate / record / terminal roll-back, one thread per trajectory.  The same algorithm as the
+// event block of the fused kernel (erk_fused.cuh): differential_system.py:29-57, 60-167, 1020-1066. -------------------
+__global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restrict__ k0, const double *__restrict__ f1)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    int fl = a.flags[i];
+    if (!(fl & FLAG_ACCEPTED) || (fl & FLAG_FINAL_LEG)) return;
+    const long long n = a.n;
+    const int D = a.dim, W = a.dim + 2, ne = a.n_events;
+    const double t1 = a.t[i], t0 = a.ev_state[i], dt_prev = a.ev_state[n + i], trange = t1 - t0;
+    double g0s[EV_NE], g1s[EV_NE];
+    unsigned mask = 0;
+    for (int e = 0; e < ne; ++e) {
+        const double g1 = stage_ev_g(a, e, i, t1, a.dY), g0 = a.ev_state[(long long)(2 + EV_NE + e) * n + i];
+        a.ev_state[(long long)(2 + EV_NE + e) * n + i] = g1;
+        g0s[e] = g0; g1s[e] = g1;
+        const int dir = a.ev_flags[e] & 3;
+        const bool rising = g0 < 0.0;
+        if (g0 * g1 < 0.0 && (dir == 0 || (dir == 1) == rising)) mask |= 1u << e;
+    }
+    if (!mask) return;
+    double root[EV_NE];
+    int which[EV_NE], cnt = 0;
+    for (int e = 0; e < ne; ++e) {
+        if (!(mask >> e & 1u)) continue;
+        const double *w = a.ev_coef + (long long)e * W;
+        double dg0 = w[D], dg1 = w[D];
+        for (int d = 0; d < D; ++d)
+            if (w[d] != 0.0) { dg0 = fma(w[d], k0[(long long)d * n + i], dg0); dg1 = fma(w[d], f1[(long long)d * n + i], dg1); }
+        const double g0 = g0s[e], g1 = g1s[e], ca = trange * dg0, cb = trange * dg1;
+        const double c2 = 3.0 * (g1 - g0) - 2.0 * ca - cb, c3 = 2.0 * (g0 - g1) + ca + cb;
+        double lo = 0.0, hi = 1.0, tau = g0 / (g0 - g1);
+        for (int it = 0; it < 64; ++it) {
+            const double G = fma(fma(fma(c3, tau, c2), tau, ca), tau, g0);
+            if (G == 0.0) break;
+            if ((G < 0.0) == (g0 < 0.0)) lo = tau; else hi = tau;
+            const double dG = fma(fma(3.0 * c3, tau, 2.0 * c2), tau, ca);
+            const double step = G / dG;
+            if (fabs(step) <= 2.3e-16) break;
+            double nxt = tau - step;
+            if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
+            tau = nxt;
+            if (hi - lo <= 4.0e-16) break;
+        }
+        root[cnt] = fma(tau, trange, t0);
+        which[cnt] = e;
+        cnt++;
+    }
+    for (int p = 1; p < cnt; ++p)
+        for (int q = p; q > 0 && (trange >= 0.0 ? root[q] < root[q - 1] : root[q] > root[q - 1]); --q) {
+            double tr = root[q]; root[q] = root[q - 1]; root[q - 1] = tr;
+            int tw = which[q]; which[q] = which[q - 1]; which[q - 1] = tw;
+        }
+    bool term = false;
+    double term_root = 0.0;
+    for (int p = 0; p < cnt && !term; ++p) {
+        const int e = which[p];
+        const double rt = root[p], last = a.ev_state[(long long)(2 + e) * n + i];
+        if (!(last == last) || fabs(rt - last) > 2.9e-11) {
+            a.ev_state[(long long)(2 + e) * n + i] = rt;
+            const int c = a.ev_count[i];
+            if (c < a.ev_capacity) {
+                double *rec = a.ev_records + ((long long)i * a.ev_capacity + c) * W;
+                const double ta = (rt - t0) / trange;
+                rec[0] = rt;
+                rec[1 + D] = (double)e;
+                const double t2 = __dmul_rn(ta, ta), t3 = __dmul_rn(t2, ta);
+                const double h00 = __dadd_rn(__dsub_rn(__dmul_rn(2.0, t3), __dmul_rn(3.0, t2)), 1.0);
+                const double h10 = __dadd_rn(__dsub_rn(t3, __dmul_rn(2.0, t2)), ta);
+                const double h01 = __dadd_rn(__dmul_rn(-2.0, t3), __dmul_rn(3.0, t2));
+                const double h11 = __dsub_rn(t3, t2);
+                for (int d = 0; d < D; ++d) {
+                    const long long q = (long long)d * n + i;
+                    const double p0 = a.y[q], p1 = a.y[q] + a.dY[q];
+                    rec[1 + d] = ta == 0.0 ? p0 : (ta == 1.0 ? p1 :
+                        __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h00, p0), __dmul_rn(__dmul_rn(h10, trange), k0[q])),
+                                            __dmul_rn(h01, p1)), __dmul_rn(__dmul_rn(h11, trange), f1[q])));
+                }
+            }
+            a.ev_count[i] = c + 1;
+        }
+        if (a.ev_flags[e] & 4) { term = true; term_root = rt; }
+    }
+    if (term) {
+        // drop the step and integrate to the root (differential_system.py:1051-1055, entry clamp :973-974)
+        const bool was_active = fl & FLAG_ACTIVE;
+        a.t[i] = t0;
+        if (a.accepted) a.accepted[i] -= 1;
+        a.tf_per[i] = term_root;
+        fl &= ~(FLAG_ACCEPTED | FLAG_FINAL);
+        const double span = term_root - t0;
+        double dt = dt_prev;
+        bool active;
+        if (fabs(span) < DSB_EPS4) {
+            active = false;
+            if (a.status) a.status[i] = (int)DSB_TRAJ_EVENT;
+        } else {
+            if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+            active = (dt != 0.0) && (fabs(span) >= DSB_EPS32);
+            if (a.status) a.status[i] = active ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_EVENT;
+        }
+        a.dt[i] = dt;
+        a.trial[i] = 0;
+        fl = active ? (fl | FLAG_ACTIVE | FLAG_FINAL_LEG) : ((fl & ~FLAG_ACTIVE) | FLAG_FINAL_LEG);
+        a.flags[i] = fl;
+        if (active && !was_active) atomicAdd((unsigned long long *)&a.counters[1], 1ull);
+        if (!active && was_active) atomicAdd((unsigned long long *)&a.counters[1], ~0ull);      // -1
     }
 }
 
@@ -464,7 +618,8 @@ int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, c
     return DSB_OK;
 }
 
-int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream)
+// parts: 1 = increment + error norm + controller, 2 = masked commit, 3 = both
+static int stage_finish_parts(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int parts, cudaStream_t stream)
 {
     int rc = check_args(h, a, "dsb_erk_stage_finish");
     if (rc != DSB_OK || a->n == 0) return rc;
@@ -487,23 +642,64 @@ int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_
     dim3 gr(grx, rows_grid_y(grx, a->dim, h->sm_count));
     // few trajectories, large state (e.g. ensemble=False with a big system): parallelise over the state instead
     const bool wide = a->n < 32 && a->dim >= 8192;
-    if (wide) {
+    if (wide && (parts & 1)) {
         dim3 gw((unsigned)chunks, (unsigned)a->n);
         if (strict) stage_increment_wide_kernel<true><<<gw, 256, 0, stream>>>(*a, K, fr, d_per_chunk);
         else stage_increment_wide_kernel<false><<<gw, 256, 0, stream>>>(*a, K, fr, d_per_chunk);
     }
     if (strict) {
-        if (!wide) stage_increment_kernel<true><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
-        stage_controller_kernel<true><<<g2, 128, 0, stream>>>(*a, fr, chunks);
-        if (rows && vec == 2) stage_commit_rows_kernel<true, 2><<<gr, 128, 0, stream>>>(*a);
-        else if (rows) stage_commit_rows_kernel<true, 1><<<gr, 128, 0, stream>>>(*a);
-        else stage_commit_kernel<true><<<g3, 256, 0, stream>>>(*a);
+        if (parts & 1) {
+            if (!wide) stage_increment_kernel<true><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
+            stage_controller_kernel<true><<<g2, 128, 0, stream>>>(*a, fr, chunks);
+        }
+        if (parts & 2) {
+            if (rows && vec == 2) stage_commit_rows_kernel<true, 2><<<gr, 128, 0, stream>>>(*a);
+            else if (rows) stage_commit_rows_kernel<true, 1><<<gr, 128, 0, stream>>>(*a);
+            else stage_commit_kernel<true><<<g3, 256, 0, stream>>>(*a);
+        }
     } else {
-        if (!wide) stage_increment_kernel<false><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
-        stage_controller_kernel<false><<<g2, 128, 0, stream>>>(*a, fr, chunks);
-        if (rows && vec == 2) stage_commit_rows_kernel<false, 2><<<gr, 128, 0, stream>>>(*a);
-        else if (rows) stage_commit_rows_kernel<false, 1><<<gr, 128, 0, stream>>>(*a);
-        else stage_commit_kernel<false><<<g3, 256, 0, stream>>>(*a);
+        if (parts & 1) {
+            if (!wide) stage_increment_kernel<false><<<g1, 128, 0, stream>>>(*a, K, fr, d_per_chunk);
+            stage_controller_kernel<false><<<g2, 128, 0, stream>>>(*a, fr, chunks);
+        }
+        if (parts & 2) {
+            if (rows && vec == 2) stage_commit_rows_kernel<false, 2><<<gr, 128, 0, stream>>>(*a);
+            else if (rows) stage_commit_rows_kernel<false, 1><<<gr, 128, 0, stream>>>(*a);
+            else stage_commit_kernel<false><<<g3, 256, 0, stream>>>(*a);
+        }
+    }
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream)
+{
+    if (a && a->n_events > 0) {
+        set_error("dsb_erk_stage_finish: with events the attempt ends with dsb_erk_stage_finish_events (phases 0 and 1)");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    return stage_finish_parts(h, a, 3, stream);
+}
+
+int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int phase, const double *f1, cudaStream_t stream)
+{
+    int rc = check_args(h, a, "dsb_erk_stage_finish_events");
+    if (rc != DSB_OK) return rc;
+    if (a->n_events < 1 || a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
+        !a->ev_state || !a->tf_per || a->ev_capacity < 1 || (phase != 0 && phase != 1) || (phase == 1 && !f1) || !a->K[0]) {
+        set_error("dsb_erk_stage_finish_events: needs 1..%d events with ev_coef, ev_flags, ev_records, ev_count, ev_state, "
+                  "tf_per, ev_capacity >= 1, K[0], phase 0 or 1, and f1 in phase 1", DSB_MAX_EVENTS);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    if (a->n == 0) return DSB_OK;
+    if (phase == 0) {
+        rc = stage_finish_parts(h, a, 1, stream);
+        if (rc != DSB_OK) return rc;
+        stage_y1_kernel<<<grid_for((long long)a->dim * a->n, 256, h->sm_count), 256, 0, stream>>>(*a);
+    } else {
+        stage_events_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, stream>>>(*a, a->K[0], f1);
+        DSB_CUDA_CHECK(cudaGetLastError());
+        return stage_finish_parts(h, a, 2, stream);
     }
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;

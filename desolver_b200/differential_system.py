@@ -752,7 +752,7 @@ class OdeSystem(object):
         c = self._counters.cpu()
         return int(c[2]), int(c[3]), int(c[4]), int(c[5])
 
-    def _run_stagewise(self, tf, callbacks, bar):
+    def _run_stagewise(self, tf, callbacks, bar, events=None):
         """Generic right-hand side: the user's torch callable is evaluated between the fused stage
         kernels of libdesolver_b200.so (dsb_erk_stage_*), all on the current stream.  The host looks at
         the active-trajectory count only every `self.sync_every` attempts.  When fewer than half of the
@@ -804,7 +804,19 @@ class OdeSystem(object):
             k_out = cache
         work, buf, m, index, consts = full, alloc(n), n, None, self.__consts
         a, y_view, t_view = bind(work, buf, m)
-        can_compact = self.ensemble and self.compaction and not callbacks and not dense
+        ev_keep = None
+        if events:
+            # device event detection around any right-hand side (dsb_erk_stage_finish_events): per-trajectory final
+            # times (a terminal event re-targets its trajectory), scratch state, and the record store of the log
+            coef, flags = self._event_tensors(events)
+            ev_state = torch.zeros((2 + 2 * cb.MAX_EVENTS, n), **f64)
+            tf_per = torch.full((n,), float(tf), **f64)
+            a.n_events, a.ev_capacity = len(events), self._event_log.capacity
+            a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
+            a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
+            a.ev_state, a.tf_per = ev_state.data_ptr(), tf_per.data_ptr()
+            ev_keep = (coef, flags, ev_state, tf_per)
+        can_compact = self.ensemble and self.compaction and not callbacks and not dense and not events
         K = [None] * S
         y_committed = self._user_shape(self._y)
         t_committed = self._user_time(self._t)
@@ -844,7 +856,17 @@ class OdeSystem(object):
                 k = k.to(torch.float64).reshape(D, m)
                 K[s] = k if k.is_contiguous() else k.contiguous()      # keep alive until the attempt finishes
                 a.K[s] = K[s].data_ptr()
-            handle.stage_finish(a, st)
+            if events:
+                # phase 0: controller + (t_stage, y_stage) = the state after the attempt; f1 = rhs there (the reference's
+                # final_rhs, integrator_types.py:308); phase 1: locate / record / roll back, then the masked commit
+                handle.stage_finish_events(a, 0, None, st)
+                f1 = self.equ_rhs(t_view, y_view, **consts).to(torch.float64).reshape(D, m)
+                f1 = f1 if f1.is_contiguous() else f1.contiguous()
+                K.append(f1)                                           # keep alive until the attempt finishes
+                del K[S:-1]
+                handle.stage_finish_events(a, 1, f1.data_ptr(), st)
+            else:
+                handle.stage_finish(a, st)
             if dense:
                 record_nodes(buf["flags"].data_ptr())
 
@@ -865,7 +887,7 @@ class OdeSystem(object):
                 torch.cuda.synchronize(dev)
                 return None
 
-        graph, rhs_calls_per_attempt, rewarm = None, S + (1 if dense else 0), False
+        graph, rhs_calls_per_attempt, rewarm = None, S + (1 if dense else 0) + (1 if events else 0), False
         while True:
             if first:
                 one_attempt(True)                    # eager: integrate()-entry logic, allocator warm-up
@@ -1050,11 +1072,11 @@ class OdeSystem(object):
         try:
             if self.host_io and (plugin is None or self.integrator.symplectic):
                 raise NotImplementedError("host_io=True needs an explicit Runge-Kutta method with a fused kernel")
-            if events and (plugin is None or self.integrator.symplectic or self.host_io or callbacks or eta
-                           or self.__dense_output or self.integrator.stages > 7):
-                raise NotImplementedError("device event detection needs a right-hand side with a fused plugin, an explicit "
-                                          "Runge-Kutta method with at most 7 stages, device-resident state, and no "
-                                          "callbacks / progress bar / dense output in the same call")
+            if events and (self.integrator.symplectic or self.host_io or callbacks or eta or self.__dense_output):
+                raise NotImplementedError("device event detection needs an explicit Runge-Kutta method, device-resident "
+                                          "state, and no callbacks / progress bar / dense output in the same call")
+            if events and plugin is not None and self.integrator.stages > 7:
+                plugin = None            # the event-detecting fused kernels stop at 7 stages: stage-level path
             if self.integrator.symplectic or plugin is None:
                 self._stats = None
             if self.integrator.symplectic:
@@ -1070,7 +1092,9 @@ class OdeSystem(object):
                 if eta:
                     from tqdm.auto import tqdm
                     bar = tqdm(total=None)
-                self._run_stagewise(tf, callbacks, bar)
+                self._run_stagewise(tf, callbacks, bar, events=events)
+                if events:
+                    self._event_log.events = list(user_events)
                 if bar is not None:
                     bar.close()
             elif self.host_io:

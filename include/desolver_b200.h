@@ -211,11 +211,27 @@ typedef struct {
     int32_t one_step;          /* != 0: a trajectory goes inactive as soon as it accepts a step -- the
                                   integrator protocol `integrator(rhs, t, y, constants, timestep)`
                                   (integrators/integrator_template.py:38-40, differential_system.py:1003-1004) */
+    /* event detection (n_events = 0: off): the hyperplane events of dsb_erk_run_args, for any right-hand side.
+     * With events the attempt ends with dsb_erk_stage_finish_events(phase 0) -> f1 = rhs(t_stage, y_stage)
+     * (the reference's final_rhs, integrators/integrator_types.py:308) -> dsb_erk_stage_finish_events(phase 1). */
+    int32_t n_events, ev_capacity;
+    const double *ev_coef;     /* [n_events][dim + 2]                                              */
+    const int32_t *ev_flags;   /* [n_events]                                                       */
+    double *ev_records;        /* [n][ev_capacity][dim + 2]                                        */
+    int32_t *ev_count;         /* [n] in/out                                                       */
+    double *ev_state;          /* [2 + 2*DSB_MAX_EVENTS][n] scratch: t and dt before the last accepted step,
+                                  last occurrence time per event, g at the step start per event     */
+    double *tf_per;            /* [n] per-trajectory final time, initialised to tf by the caller; a terminal
+                                  event re-targets it to the event time (NULL: tf for everyone)     */
 } dsb_erk_stage_args;
 
 DSB_API int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);
 DSB_API int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage, void *stream);
 DSB_API int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream);
+/* finish with event detection: phase 0 = increment, error norm, controller, and y_stage = y + dY, t_stage = t_new
+ * for the caller's f1 = rhs(t_stage, y_stage); phase 1 = locate / record events over the accepted steps (Hermite
+ * interpolant from K[0] and f1), roll back and re-target trajectories stopped by a terminal event, masked commit. */
+DSB_API int dsb_erk_stage_finish_events(dsb_erk_handle h, const dsb_erk_stage_args *a, int phase, const double *f1, void *stream);
 /* kernel launches issued by one begin + S x state + finish sequence (bench accounting) */
 DSB_API int dsb_erk_stage_launches(dsb_erk_handle h);
 

@@ -29,7 +29,7 @@ def _event_set(name):
     return mod.event_set(name)
 
 
-def _run(name, events=True):
+def _run(name, events=True, use_fused=True):
     import desolver_b200 as de
     g = load_golden("events_%s.npz" % name)
     lorenz = name.startswith("lorenz")
@@ -38,6 +38,7 @@ def _run(name, events=True):
     a = de.OdeSystem(rhs, torch.as_tensor(np.ascontiguousarray(g["y0"])), t=(0.0, 2.0 if lorenz else 10.0), dt=1e-2, rtol=1e-9,
                      atol=1e-9, constants=consts, ensemble=True)
     a.method = "RK45"
+    a.use_fused = use_fused        # False: the stage-level path (user RHS between the stage kernels) with its event kernels
     evs = _event_set(name)
     a.integrate(events=evs if events else None)
     torch.cuda.synchronize()
@@ -72,9 +73,10 @@ def _check_events(a, g):
     return cnt, idx
 
 
+@pytest.mark.parametrize("use_fused", [True, False])
 @pytest.mark.parametrize("name", ["lorenz_sections", "vdp_sections"])
-def test_non_terminal_events_match_reference_and_do_not_perturb_the_integration(name):
-    a, g, evs = _run(name)
+def test_non_terminal_events_match_reference_and_do_not_perturb_the_integration(name, use_fused):
+    a, g, evs = _run(name, use_fused=use_fused)
     cnt, idx = _check_events(a, g)
     assert cnt.sum() > 0 and a.success and "completed" in a.integration_status
     # one event per sign change of g over an accepted step, per event function
@@ -89,17 +91,18 @@ def test_non_terminal_events_match_reference_and_do_not_perturb_the_integration(
         for st in log.for_trajectory(i):
             assert abs(float(st.event(float(st.t), st.y.numpy()))) <= 1e-9
     # events are observers: the integration itself is bit-identical to a run without them
-    b, _, _ = _run(name, events=False)
+    b, _, _ = _run(name, events=False, use_fused=use_fused)
     assert torch.equal(a[-1].y, b[-1].y) and torch.equal(a.accepted, b.accepted) and torch.equal(a.rejected, b.rejected)
     assert rel_inf(a[-1].y.cpu().numpy(), g["y_final"]).max() <= 1e-9
     assert np.mean(a.accepted.cpu().numpy() == g["accepted"]) >= 0.97
 
 
+@pytest.mark.parametrize("use_fused", [True, False])
 @pytest.mark.parametrize("name", ["lorenz_terminal", "vdp_terminal"])
-def test_terminal_events_stop_the_trajectory_at_the_root(name):
+def test_terminal_events_stop_the_trajectory_at_the_root(name, use_fused):
     import desolver_b200 as de
     from desolver_b200.backend import cuda_backend as cb
-    a, g, evs = _run(name)
+    a, g, evs = _run(name, use_fused=use_fused)
     _check_events(a, g)
     st = a.status.cpu().numpy()
     tfin = a[-1].t.cpu().numpy()
@@ -156,3 +159,38 @@ def test_single_system_event_list_has_the_reference_shape():
         a.reset()
         with pytest.raises(NotImplementedError):
             a.integrate(events=bad)
+
+
+def test_events_with_an_untagged_callable_and_a_13_stage_method():
+    """Stage-level path: a user torch callable (no plugin) with RK8(7), one recorded and one terminal event, against the
+    closed-form solution of the forced oscillator y'' + y = t: y = t + (y0 - 0) cos t + (v0 - 1) sin t."""
+    import desolver_b200 as de
+    rng = np.random.default_rng(5)
+    y0 = rng.uniform(0.5, 1.5, size=(2, 300))
+    a = de.OdeSystem(lambda t, y: torch.stack([y[1], -y[0] + t]), torch.as_tensor(y0), t=(0.0, 6.0), dt=1e-2, rtol=1e-10,
+                     atol=1e-10, ensemble=True)
+    a.method = "RK87"
+    level = de.events.HyperplaneEvent([1.0, 0.0], c=0.0, wt=-1.0, direction=0)         # y - t = 0: a cos t + b sin t = 0
+    stop = de.events.component_crossing(1, 1.0, dim=2, direction=-1, is_terminal=True)  # v falls through 1: -a sin t + b cos t = 0
+    a.integrate(events=[level, stop])
+    log = a.events
+    A, B = y0[0], y0[1] - 1.0
+    t_level = np.mod(np.arctan2(-A, B), np.pi)                   # first root of A cos t + B sin t
+    t_stop_all = np.mod(np.arctan2(B, A), np.pi)                 # roots of -A sin t + B cos t (every pi)
+    tfin = a[-1].t.cpu().numpy()
+    st = a.status.cpu().numpy()
+    # a falling crossing of v = 1 comes once per period 2 pi > 6: most, not all, trajectories meet one
+    assert set(np.unique(st)) <= {0, 3} and (st == 3).mean() > 0.5 and np.all(np.abs(tfin[st == 0] - 6.0) <= 1e-12)
+    for i in np.nonzero(st == 3)[0][::7]:
+        lst = log.for_trajectory(int(i))
+        assert lst[-1].event is stop and abs(float(lst[-1].t) - tfin[i]) <= 1e-12
+        # the terminal root is one of the stationary points of v with v' < 0 there
+        k = np.round((tfin[i] - t_stop_all[i]) / np.pi)
+        assert abs(tfin[i] - (t_stop_all[i] + k * np.pi)) <= 2e-5      # cubic Hermite interpolation over RK8(7)-sized steps
+        levels = [float(st.t) for st in lst if st.event is level]
+        for tl in levels:
+            kk = np.round((tl - t_level[i]) / np.pi)
+            assert abs(tl - (t_level[i] + kk * np.pi)) <= 2e-5
+    # final state = exact solution at the stopping time, to the integration tolerance
+    exact = tfin + A * np.cos(tfin) + B * np.sin(tfin)
+    assert np.max(np.abs(a[-1].y[0].cpu().numpy() - exact)) <= 1e-7
