@@ -152,6 +152,7 @@ __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
 
 // ------------------------------------------------------------------------------------- (B) stage-level kernels
 constexpr int SFLAG_ACTIVE = 1;
+constexpr int SFLAG_STEPPED = 4;       // took a step in the commit just done (mask of dsb_dense_append); cleared by begin
 
 __global__ void symp_begin_kernel(dsb_symp_stage_args a, int first_call)
 {
@@ -230,7 +231,8 @@ __global__ void symp_advance_kernel(dsb_symp_stage_args a)
         if (a.steps) a.steps[i] += 1;
         double dt = a.dt[i];
         still = (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
-        if (!still) { a.flags[i] = 0; if (a.status) a.status[i] = (int)DSB_TRAJ_DONE; }
+        a.flags[i] = (still ? SFLAG_ACTIVE : 0) | SFLAG_STEPPED;
+        if (!still && a.status) a.status[i] = (int)DSB_TRAJ_DONE;
     }
     int cnt = __syncthreads_count(still);
     if (threadIdx.x == 0 && cnt) atomicAdd((unsigned long long *)&a.counters[1], (unsigned long long)cnt);

@@ -946,8 +946,6 @@ class OdeSystem(object):
         drift_count = (self.dim[0] // 2) * (D // self.dim[0]) if len(self.dim) else 0
         fused = (self.use_fused and getattr(rhs, "device_plugin", None) == "nbody" and len(self.dim) == 3
                  and self.dim[0] == 2 and self.dim[2] == 3 and not self.__dense_output)
-        if self.__dense_output:
-            raise NotImplementedError("dense_output is not available for symplectic methods in this version")
         if fused:
             nb = self.dim[1]
             handle = cb.symp_handle(dev.index or 0, rhs.plugin_id, D, drift_count, integ.tableau_intermediate, strict=self.strict)
@@ -996,6 +994,27 @@ class OdeSystem(object):
         t_view = self._user_time(buf["t_stage"])
         first, steps = True, 0
 
+        self._ensure_dense_store()
+        dense = self._nodes is not None
+        y_committed, t_committed = self._user_shape(self._y), self._user_time(self._t)
+
+        def record_nodes(flags_ptr):
+            """Dense-output node (t, y, rhs(t, y)) of the systems that just stepped (all if flags_ptr is None).  The
+            reference's symplectic integrator never refreshes `final_rhs` after the first step
+            (integrators/integrator_types.py:385-386), so its later interpolants carry a stale end slope; the nodes
+            here hold the slope at their own time."""
+            f = self.equ_rhs(t_committed, y_committed, **self.__consts).to(torch.float64).reshape(D, n)
+            f = f if f.is_contiguous() else f.contiguous()
+            cb.check(cb.lib().dsb_dense_append(self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity,
+                                               n, D, self._t.data_ptr(), self._y.data_ptr(), f.data_ptr(), flags_ptr, 4,
+                                               cb.current_stream_ptr(dev)), "dsb_dense_append")
+            keep_f[0] = f
+            self._launches += 1
+
+        keep_f = [None]
+        if dense and int(self._node_count.max().item()) == 0:
+            record_nodes(None)                                   # node 0 = initial condition
+
         def one_step(first_call):
             st = cb.current_stream_ptr(dev)
             handle.stage_begin(a, first_call, st)
@@ -1005,6 +1024,8 @@ class OdeSystem(object):
                 keep[s] = f
                 handle.stage_accumulate(a, s, f.data_ptr(), st)
             handle.stage_commit(a, st)
+            if dense:
+                record_nodes(buf["flags"].data_ptr())
 
         keep = [None] * S
         graph = None
@@ -1024,7 +1045,7 @@ class OdeSystem(object):
                         graph = None
             elif graph is not None:
                 graph.replay()
-                self.equ_rhs.nfev += S
+                self.equ_rhs.nfev += S + (1 if dense else 0)
             else:
                 one_step(False)
             self._launches += (4 + S) if graph is None else 1
