@@ -112,6 +112,10 @@ class SympStageArgs(C.Structure):
         ("flags", C.c_void_p), ("steps", C.c_void_p), ("status", C.c_void_p),
         ("tf", C.c_double),
         ("counters", C.c_void_p),
+        ("n_events", C.c_int32), ("ev_capacity", C.c_int32),
+        ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
+        ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
+        ("ev_state", C.c_void_p), ("tf_per", C.c_void_p), ("ev_scratch", C.c_void_p),
     ]
 
 
@@ -190,6 +194,8 @@ def lib():
     L.dsb_symp_stage_begin.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p]
     L.dsb_symp_stage_accumulate.restype = C.c_int
     L.dsb_symp_stage_accumulate.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p]
+    L.dsb_symp_stage_commit_events.restype = C.c_int
+    L.dsb_symp_stage_commit_events.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dsb_symp_stage_commit.restype = C.c_int
     L.dsb_symp_stage_commit.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_void_p]
     if L.dsb_abi_version() != ABI_VERSION:
@@ -329,6 +335,10 @@ class SympHandle:
 
     def stage_commit(self, args, stream_ptr):
         check(lib().dsb_symp_stage_commit(self._h, C.byref(args), stream_ptr), "dsb_symp_stage_commit")
+
+    def stage_commit_events(self, args, phase, f0_ptr, f1_ptr, stream_ptr):
+        check(lib().dsb_symp_stage_commit_events(self._h, C.byref(args), int(phase), f0_ptr, f1_ptr, stream_ptr),
+              "dsb_symp_stage_commit_events")
 
     def __del__(self):
         try:

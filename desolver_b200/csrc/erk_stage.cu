@@ -520,6 +520,14 @@ __global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restri
 
 static void build_final(const dsb_erk_plan *p, FinalRows &fr);
 
+// the event kernel over any buffers that follow the dsb_erk_stage_args conventions (used by symplectic.cu as well)
+int launch_stage_events(const dsb_erk_stage_args &view, const double *k0, const double *f1, cudaStream_t stream)
+{
+    stage_events_kernel<<<(unsigned)((view.n + 127) / 128), 128, 0, stream>>>(view, k0, f1);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
 static void build_rows(const dsb_erk_plan *p, int s, StageRow &row)
 {
     const int S = p->stages, W = S + 1;

@@ -12,6 +12,7 @@
 // Kick (momentum) variables = second half of axis 0 of the state, drift (position) = first half
 // (integrator_types.py:359-362).  Time advances by tableau column 1 (:412).
 #include <math_constants.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -153,6 +154,11 @@ __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
 // ------------------------------------------------------------------------------------- (B) stage-level kernels
 constexpr int SFLAG_ACTIVE = 1;
 constexpr int SFLAG_STEPPED = 4;       // took a step in the commit just done (mask of dsb_dense_append); cleared by begin
+constexpr int SFLAG_FINAL_LEG = 8;     // re-integration to the root of a terminal event (same bit as in erk_stage.cu)
+
+int launch_stage_events(const dsb_erk_stage_args &view, const double *k0, const double *f1, cudaStream_t stream);
+
+__device__ __forceinline__ double symp_tf(const dsb_symp_stage_args &a, long long i) { return a.tf_per ? a.tf_per[i] : a.tf; }
 
 __global__ void symp_begin_kernel(dsb_symp_stage_args a, int first_call)
 {
@@ -160,23 +166,35 @@ __global__ void symp_begin_kernel(dsb_symp_stage_args a, int first_call)
     if (i >= a.n) return;
     double t = a.t[i], dt = a.dt[i];
     int fl = a.flags[i];
+    const double tfi = symp_tf(a, i);
     if (first_call) {
         bool go = true;
-        double span = a.tf - t;
+        double span = tfi - t;
+        if (a.n_events > 0) {
+            fl &= ~SFLAG_FINAL_LEG;
+            for (int e = 0; e < a.n_events; ++e) {
+                const double *w = a.ev_coef + (long long)e * (a.dim + 2);
+                double g = w[a.dim] * t - w[a.dim + 1];
+                for (int d = 0; d < a.dim; ++d)
+                    if (w[d] != 0.0) g = fma(w[d], a.y[(long long)d * a.n + i], g);
+                a.ev_state[(long long)(2 + e) * a.n + i] = CUDART_NAN;
+                a.ev_state[(long long)(2 + DSB_MAX_EVENTS + e) * a.n + i] = g;
+            }
+        }
         if (fabs(span) < DSB_EPS4) go = false;
         else {
             if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
             if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
         }
         a.dt[i] = dt;
-        fl = go ? SFLAG_ACTIVE : 0;
+        fl = (fl & SFLAG_FINAL_LEG) | (go ? SFLAG_ACTIVE : 0);
     }
-    bool more = (fl & SFLAG_ACTIVE) && (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
-    fl = more ? SFLAG_ACTIVE : 0;
+    bool more = (fl & SFLAG_ACTIVE) && (dt != 0.0) && (fabs(tfi - t) >= DSB_EPS32);
+    fl = (fl & SFLAG_FINAL_LEG) | (more ? SFLAG_ACTIVE : 0);
     a.flags[i] = fl;
-    if (a.status) a.status[i] = more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE;
-    bool final_step = fabs(dt + t) > fabs(a.tf);
-    a.h[i] = more ? (final_step ? (a.tf - t) : dt) : 0.0;
+    if (a.status) a.status[i] = more ? (int)DSB_TRAJ_RUNNING : ((fl & SFLAG_FINAL_LEG) ? (int)DSB_TRAJ_EVENT : (int)DSB_TRAJ_DONE);
+    bool final_step = fabs(dt + t) > fabs(tfi);
+    a.h[i] = more ? (final_step ? (tfi - t) : dt) : 0.0;
     a.t_stage[i] = t;
     if (i == 0) a.counters[1] = 0;
 }
@@ -210,14 +228,14 @@ __global__ void symp_accumulate_kernel(dsb_symp_stage_args a, const double *f, d
     }
 }
 
-template <bool STRICT>
+template <bool STRICT, int MASK = SFLAG_ACTIVE>
 __global__ void symp_commit_kernel(dsb_symp_stage_args a)
 {
     using A = Ar<STRICT>;
     const long long total = (long long)a.dim * a.n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e % a.n;
-        if (a.flags[i] & SFLAG_ACTIVE) a.y[e] = A::add(a.y[e], a.dS[e]);
+        if (a.flags[i] & MASK) a.y[e] = A::add(a.y[e], a.dS[e]);
     }
 }
 
@@ -226,13 +244,18 @@ __global__ void symp_advance_kernel(dsb_symp_stage_args a)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int still = 0;
     if (i < a.n && (a.flags[i] & SFLAG_ACTIVE)) {
+        const int leg = a.flags[i] & SFLAG_FINAL_LEG;
+        double dt = a.dt[i];
+        if (a.n_events > 0) {                                        // the roll-back of a terminal event needs these
+            a.ev_state[i] = a.t[i];
+            a.ev_state[a.n + i] = dt;
+        }
         double t = __dadd_rn(a.t[i], a.h[i]);
         a.t[i] = t;
         if (a.steps) a.steps[i] += 1;
-        double dt = a.dt[i];
-        still = (dt != 0.0) && (fabs(a.tf - t) >= DSB_EPS32);
-        a.flags[i] = (still ? SFLAG_ACTIVE : 0) | SFLAG_STEPPED;
-        if (!still && a.status) a.status[i] = (int)DSB_TRAJ_DONE;
+        still = (dt != 0.0) && (fabs(symp_tf(a, i) - t) >= DSB_EPS32);
+        a.flags[i] = (still ? SFLAG_ACTIVE : 0) | SFLAG_STEPPED | leg;
+        if (!still && a.status) a.status[i] = leg ? (int)DSB_TRAJ_EVENT : (int)DSB_TRAJ_DONE;
     }
     int cnt = __syncthreads_count(still);
     if (threadIdx.x == 0 && cnt) atomicAdd((unsigned long long *)&a.counters[1], (unsigned long long)cnt);
@@ -335,6 +358,43 @@ int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void 
     if (h->flags & DSB_FLAG_STRICT) symp_commit_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     else symp_commit_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     symp_advance_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a, int phase, const double *f0,
+                                 const double *f1, void *stream)
+{
+    int rc = symp_check(h, a, "dsb_symp_stage_commit_events");
+    if (rc != DSB_OK) return rc;
+    if (a->n_events < 1 || a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
+        !a->ev_state || !a->tf_per || !a->ev_scratch || a->ev_capacity < 1 || (phase != 0 && phase != 1) ||
+        (phase == 1 && (!f0 || !f1))) {
+        set_error("dsb_symp_stage_commit_events: needs 1..%d events with all ev_* buffers, tf_per, phase 0 or 1, and f0, f1 in "
+                  "phase 1", DSB_MAX_EVENTS);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    if (a->n == 0) return DSB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 0) {
+        symp_advance_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, st>>>(*a);
+        DSB_CUDA_CHECK(cudaGetLastError());
+        return DSB_OK;
+    }
+    // the event kernel of erk_stage.cu over a view of the symplectic buffers: dY = dS, accepted = steps, the
+    // "accepted" bit of that kernel is this file's "stepped" bit
+    dsb_erk_stage_args v;
+    memset(&v, 0, sizeof(v));
+    v.n = a->n; v.dim = a->dim; v.chunks = 1;
+    v.y = a->y; v.t = a->t; v.dt = a->dt; v.dY = a->dS; v.flags = a->flags; v.trial = a->ev_scratch;
+    v.accepted = a->steps; v.status = a->status; v.counters = a->counters; v.tf = a->tf;
+    v.n_events = a->n_events; v.ev_capacity = a->ev_capacity; v.ev_coef = a->ev_coef; v.ev_flags = a->ev_flags;
+    v.ev_records = a->ev_records; v.ev_count = a->ev_count; v.ev_state = a->ev_state; v.tf_per = a->tf_per;
+    rc = launch_stage_events(v, f0, f1, st);
+    if (rc != DSB_OK) return rc;
+    const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
+    if (h->flags & DSB_FLAG_STRICT) symp_commit_kernel<true, SFLAG_STEPPED><<<grid, 256, 0, st>>>(*a);
+    else symp_commit_kernel<false, SFLAG_STEPPED><<<grid, 256, 0, st>>>(*a);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }

@@ -934,7 +934,7 @@ class OdeSystem(object):
         if index is not None:
             scatter_back()
 
-    def _run_symplectic(self, tf, callbacks, bar):
+    def _run_symplectic(self, tf, callbacks, bar, events=None):
         """Explicit symplectic splitting (fixed dt).  Fused kernel for the tagged N-body right-hand side,
         stage-level kernels around the user's callable otherwise."""
         torch = _torch()
@@ -945,7 +945,7 @@ class OdeSystem(object):
         # drift (position) variables = rows [0, dim0 // 2) of axis 0, kick = the rest (reference integrator_types.py:359-362)
         drift_count = (self.dim[0] // 2) * (D // self.dim[0]) if len(self.dim) else 0
         fused = (self.use_fused and getattr(rhs, "device_plugin", None) == "nbody" and len(self.dim) == 3
-                 and self.dim[0] == 2 and self.dim[2] == 3 and not self.__dense_output)
+                 and self.dim[0] == 2 and self.dim[2] == 3 and not self.__dense_output and not events)
         if fused:
             nb = self.dim[1]
             handle = cb.symp_handle(dev.index or 0, rhs.plugin_id, D, drift_count, integ.tableau_intermediate, strict=self.strict)
@@ -993,6 +993,17 @@ class OdeSystem(object):
         y_view = self._user_shape(buf["y_stage"])
         t_view = self._user_time(buf["t_stage"])
         first, steps = True, 0
+        ev_keep = None
+        if events:
+            coef, flags = self._event_tensors(events)
+            ev_state = torch.zeros((2 + 2 * cb.MAX_EVENTS, n), **f64)
+            tf_per = torch.full((n,), float(tf), **f64)
+            scratch = torch.zeros(n, dtype=torch.int32, device=dev)
+            a.n_events, a.ev_capacity = len(events), self._event_log.capacity
+            a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
+            a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
+            a.ev_state, a.tf_per, a.ev_scratch = ev_state.data_ptr(), tf_per.data_ptr(), scratch.data_ptr()
+            ev_keep = (coef, flags, ev_state, tf_per, scratch)
 
         self._ensure_dense_store()
         dense = self._nodes is not None
@@ -1023,7 +1034,14 @@ class OdeSystem(object):
                 f = f if f.is_contiguous() else f.contiguous()
                 keep[s] = f
                 handle.stage_accumulate(a, s, f.data_ptr(), st)
-            handle.stage_commit(a, st)
+            if events:
+                # the first stage's right-hand side is rhs at the step start (dS = 0 there); f1 = rhs after the step
+                handle.stage_commit_events(a, 0, None, None, st)
+                f1 = self.equ_rhs(t_view, y_view, **self.__consts).to(torch.float64).reshape(D, n)
+                keep_f[0] = f1 if f1.is_contiguous() else f1.contiguous()
+                handle.stage_commit_events(a, 1, keep[0].data_ptr(), keep_f[0].data_ptr(), st)
+            else:
+                handle.stage_commit(a, st)
             if dense:
                 record_nodes(buf["flags"].data_ptr())
 
@@ -1045,7 +1063,7 @@ class OdeSystem(object):
                         graph = None
             elif graph is not None:
                 graph.replay()
-                self.equ_rhs.nfev += S + (1 if dense else 0)
+                self.equ_rhs.nfev += S + (1 if dense or events else 0)
             else:
                 one_step(False)
             self._launches += (4 + S) if graph is None else 1
@@ -1093,9 +1111,9 @@ class OdeSystem(object):
         try:
             if self.host_io and (plugin is None or self.integrator.symplectic):
                 raise NotImplementedError("host_io=True needs an explicit Runge-Kutta method with a fused kernel")
-            if events and (self.integrator.symplectic or self.host_io or callbacks or eta or self.__dense_output):
-                raise NotImplementedError("device event detection needs an explicit Runge-Kutta method, device-resident "
-                                          "state, and no callbacks / progress bar / dense output in the same call")
+            if events and (self.host_io or callbacks or eta or self.__dense_output):
+                raise NotImplementedError("device event detection needs device-resident state and no callbacks / progress "
+                                          "bar / dense output in the same call")
             if events and plugin is not None and self.integrator.stages > 7:
                 plugin = None            # the event-detecting fused kernels stop at 7 stages: stage-level path
             if self.integrator.symplectic or plugin is None:
@@ -1105,7 +1123,9 @@ class OdeSystem(object):
                 if eta:
                     from tqdm.auto import tqdm
                     bar = tqdm(total=None)
-                self._run_symplectic(tf, callbacks, bar)
+                self._run_symplectic(tf, callbacks, bar, events=events)
+                if events:
+                    self._event_log.events = list(user_events)
                 if bar is not None:
                     bar.close()
             elif plugin is None:

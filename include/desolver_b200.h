@@ -278,11 +278,27 @@ typedef struct {
     int32_t *flags, *steps, *status;
     double tf;
     uint64_t *counters;
+    /* event detection (n_events = 0: off), as in dsb_erk_stage_args; the step then ends with
+     * dsb_symp_stage_commit_events(phase 0) -> f1 = rhs(t_stage, y_stage) -> dsb_symp_stage_commit_events(phase 1) */
+    int32_t n_events, ev_capacity;
+    const double *ev_coef;
+    const int32_t *ev_flags;
+    double *ev_records;
+    int32_t *ev_count;
+    double *ev_state;          /* [2 + 2*DSB_MAX_EVENTS][n] scratch                              */
+    double *tf_per;            /* [n] per-system final time, initialised to tf by the caller     */
+    int32_t *ev_scratch;       /* [n] scratch                                                    */
 } dsb_symp_stage_args;
 
 DSB_API int dsb_symp_stage_begin(dsb_symp_handle h, const dsb_symp_stage_args *a, int first_call, void *stream);
 DSB_API int dsb_symp_stage_accumulate(dsb_symp_handle h, const dsb_symp_stage_args *a, int stage, const double *f, void *stream);
 DSB_API int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void *stream);
+/* commit with event detection: phase 0 advances the time (y_stage / t_stage already hold the state after the step, for
+ * the caller's f1 = rhs(t_stage, y_stage)); phase 1 locates / records events on the step's Hermite interpolant
+ * (f0 = the first stage's right-hand side = rhs at the step start), rolls back systems stopped by a terminal event
+ * and commits the others. */
+DSB_API int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a, int phase, const double *f0,
+                                         const double *f1, void *stream);
 
 /* ---- dense linear right-hand side ---------------------------------------------------------
  * K = A @ Y for the linear benchmark system y' = A y over an ensemble stored as Y[n][columns]

@@ -194,3 +194,29 @@ def test_events_with_an_untagged_callable_and_a_13_stage_method():
     # final state = exact solution at the stopping time, to the integration tolerance
     exact = tfin + A * np.cos(tfin) + B * np.sin(tfin)
     assert np.max(np.abs(a[-1].y[0].cpu().numpy() - exact)) <= 1e-7
+
+
+def test_events_with_a_symplectic_method():
+    """Splitting scheme + events (the reference's event tests run ABAs5o6H too, tests/test_event_detection.py): harmonic
+    oscillators q'' = -q with different amplitudes, a recorded section q = 0 and a terminal time mark."""
+    import desolver_b200 as de
+    amp = np.linspace(0.5, 2.0, 64)
+    y0 = np.stack([amp, np.zeros(64)])
+    a = de.OdeSystem(lambda t, y: torch.stack([y[1], -y[0]]), torch.as_tensor(y0), t=(0.0, 10.0), dt=0.01, ensemble=True)
+    a.method = "ABAS5O6H"
+    section = de.events.component_crossing(0, 0.0, dim=2, direction=0)
+
+    def time_mark(t, y, **kwargs):              # a plain Python callable of affine form, terminal
+        return t - 7.3
+    time_mark.is_terminal = True
+    a.integrate(events=[section, time_mark])
+    assert a.integration_status == "Integration terminated upon finding a triggered event."
+    assert np.all(a.status.cpu().numpy() == 3) and np.max(np.abs(a[-1].t.cpu().numpy() - 7.3)) <= 1e-12
+    log = a.events
+    for i in range(0, 64, 9):
+        lst = log.for_trajectory(i)
+        zeros = [float(st.t) for st in lst if st.event is section]
+        assert lst[-1].event is time_mark and abs(float(lst[-1].t) - 7.3) <= 1e-12
+        assert np.allclose(zeros, [np.pi / 2, 3 * np.pi / 2], rtol=0, atol=1e-8) and len(zeros) == 2
+    yf = a[-1].y.cpu().numpy()
+    assert np.max(np.abs(yf[0] - amp * np.cos(7.3))) <= 1e-9 and np.max(np.abs(yf[1] + amp * np.sin(7.3))) <= 1e-9
