@@ -338,8 +338,6 @@ class OdeSystem(object):
     def _materialize(self):
         if self.__dict__.get("_pristine"):
             self._pristine = False
-            if self.host_io:
-                self._host_done = False
             self._raw_y.copy_(self._y0)
             self._raw_t.fill_(self.__t0)
             self._raw_dt.fill_(self._initial_dt())
@@ -695,7 +693,6 @@ class OdeSystem(object):
                 self._launches += 1
                 self._keepalive = params
                 self._pristine = False
-                self._host_done = True
                 c = self._counters.cpu()                      # synchronises `cur`, which waited for the download stream
                 if int(c[6]):
                     raise RuntimeError("dsb_erk_run_host: the kernel timed out waiting for its initial states")
@@ -742,7 +739,6 @@ class OdeSystem(object):
             cur.wait_stream(st)
         self._keepalive = params
         self._pristine = False
-        self._host_done = True
         c = self._counters.cpu().reshape(-1, 8)[:chunks]          # synchronises: every copy above has landed
         return int(c[:, 2].sum()), int(c[:, 3].sum()), int(c[:, 4].sum()), int(c[:, 5].sum())
 
@@ -804,7 +800,6 @@ class OdeSystem(object):
             k_out = cache
         work, buf, m, index, consts = full, alloc(n), n, None, self.__consts
         a, y_view, t_view = bind(work, buf, m)
-        ev_keep = None
         if events:
             # device event detection around any right-hand side (dsb_erk_stage_finish_events): per-trajectory final
             # times (a terminal event re-targets its trajectory), scratch state, and the record store of the log
@@ -815,7 +810,7 @@ class OdeSystem(object):
             a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
             a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
             a.ev_state, a.tf_per = ev_state.data_ptr(), tf_per.data_ptr()
-            ev_keep = (coef, flags, ev_state, tf_per)
+            self._keepalive = (coef, flags, ev_state, tf_per)      # referenced by raw pointer until the run has finished
         can_compact = self.ensemble and self.compaction and not callbacks and not dense and not events
         K = [None] * S
         y_committed = self._user_shape(self._y)
@@ -993,7 +988,6 @@ class OdeSystem(object):
         y_view = self._user_shape(buf["y_stage"])
         t_view = self._user_time(buf["t_stage"])
         first, steps = True, 0
-        ev_keep = None
         if events:
             coef, flags = self._event_tensors(events)
             ev_state = torch.zeros((2 + 2 * cb.MAX_EVENTS, n), **f64)
@@ -1003,7 +997,7 @@ class OdeSystem(object):
             a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
             a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
             a.ev_state, a.tf_per, a.ev_scratch = ev_state.data_ptr(), tf_per.data_ptr(), scratch.data_ptr()
-            ev_keep = (coef, flags, ev_state, tf_per, scratch)
+            self._keepalive = (coef, flags, ev_state, tf_per, scratch)   # referenced by raw pointer until the run has finished
 
         self._ensure_dense_store()
         dense = self._nodes is not None
