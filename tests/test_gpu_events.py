@@ -220,3 +220,36 @@ def test_events_with_a_symplectic_method():
         assert np.allclose(zeros, [np.pi / 2, 3 * np.pi / 2], rtol=0, atol=1e-8) and len(zeros) == 2
     yf = a[-1].y.cpu().numpy()
     assert np.max(np.abs(yf[0] - amp * np.cos(7.3))) <= 1e-9 and np.max(np.abs(yf[1] + amp * np.sin(7.3))) <= 1e-9
+
+
+def test_event_edge_cases():
+    """Record-store overflow, strict fused vs stage-level path (bit-equal event lists), a terminal event inside the very
+    first step of a single system, and events on the second leg of a continued integration."""
+    import desolver_b200 as de
+    cc = de.events.component_crossing
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(500, seed=4)).cuda()
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0, 5.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    a.event_capacity = 2
+    a.integrate(events=[cc(0, 0.0, dim=3), cc(1, 0.0, dim=3)])
+    log = a.events
+    assert log.overflowed and int(log.count.max()) > 2 and len(log.for_trajectory(int(log.count.argmax()))) == 2
+    res = []
+    for fused in (True, False):
+        b = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, strict=True)
+        b.use_fused = fused
+        b.integrate(events=[cc(0, 0.0, dim=3)])
+        res.append((b.events.count.clone(), b.events.t.clone(), b[-1].y.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][2], res[1][2])
+    valid = torch.arange(res[0][1].shape[1], device="cuda")[None, :] < res[0][0][:, None]
+    assert float((res[0][1] - res[1][1])[valid].abs().max()) <= 1e-15
+    s = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, np.array([1.0, 0.0]), t=(0, 1.0), dt=0.5, rtol=1e-9, atol=1e-9)
+    s.integrate(events=cc(0, 0.99999, dim=2, direction=-1, is_terminal=True))
+    assert "terminated" in s.integration_status and abs(float(s[-1].t) - np.arccos(0.99999)) <= 1e-5      # root of the cubic interpolant of a large first step
+    assert len(s.events) == 1 and float(s.events[0].t) == float(s[-1].t)
+    c = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    c.integrate(1.0)
+    c.integrate(2.0, events=[cc(0, 0.0, dim=3)])
+    d = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    d.integrate(1.0)
+    d.integrate(2.0)
+    assert torch.equal(c[-1].y, d[-1].y) and float(c.events.t[c.events.count > 0][:, 0].min()) >= 1.0

@@ -143,3 +143,18 @@ def test_abi_chunked_launch_with_stride_and_y_init():
     bad.n, bad.stride = 10, 5
     bad.y, bad.t, bad.dt, bad.counters = y.data_ptr(), t.data_ptr(), dt.data_ptr(), ctr.data_ptr()
     assert cb.lib().dsb_erk_run(handle._h, C.byref(bad), None) == cb.DSB_ERR_BAD_ARGUMENT
+
+
+@pytest.mark.parametrize("mode", ["streamed", "chunked"])
+@pytest.mark.parametrize("n", [1, 31, 33, 1000])
+def test_host_io_tiny_ensembles_and_pageable_memory(n, mode):
+    """Sizes below one warp / one chunk, and y0 in ordinary (pageable) host memory: same bits as the device run."""
+    de = _de()
+    y0 = de.benchmarks.lorenz_ensemble(n, seed=3)
+    ref = _device_run(y0, tf=0.5)
+    h = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(y0), t=(0.0, 0.5), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True,
+                     host_io=True)
+    h.method = "RK45"
+    h.host_pipeline = mode
+    h.integrate()
+    assert torch.equal(h[-1].y, ref[-1].y.cpu()) and torch.equal(h.accepted, ref.accepted.cpu())
