@@ -79,7 +79,12 @@ def as_hyperplane(event, dim, constants=None):
 
     def probe(make):
         def g(t, y):
-            return float(np.asarray(event(make(t, scalar=True), make(y), **consts)).reshape(-1)[0])
+            out = event(make(t, scalar=True), make(y), **consts)
+            out = np.asarray(out.detach().cpu() if hasattr(out, "detach") else out)
+            if out.size != 1:
+                raise NotImplementedError("event %r returns %d values for one state: events that depend on per-trajectory "
+                                          "constants are not supported on the device" % (event, out.size))
+            return float(out.reshape(-1)[0])
         return g
     makers = [lambda v, scalar=False: np.float64(v) if scalar else np.asarray(v, dtype=np.float64)]
     try:

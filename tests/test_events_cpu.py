@@ -57,6 +57,8 @@ def test_affine_callables_are_recognised_and_others_refused():
     for bad in (lambda t, y: (t - 1.0) * (t - 2.0), lambda t, y: y[0] * y[1], lambda t, y: np.sin(y[0])):
         with pytest.raises(NotImplementedError):
             as_hyperplane(bad, 2)
+    with pytest.raises(NotImplementedError):                  # depends on a per-trajectory constant
+        as_hyperplane(lambda t, y, mu=None: y[0] - mu, 2, dict(mu=np.linspace(0.0, 1.0, 5)))
     ev = lambda t, y, dy: dy[0]
     ev.requires_dstate = True
     with pytest.raises(NotImplementedError):
