@@ -38,8 +38,11 @@ namespace gemm {
 #ifndef DSB_GEMM_CTAS
 #define DSB_GEMM_CTAS 2        // resident CTAs per SM
 #endif
-constexpr int WM = DSB_GEMM_WM, CTAS = DSB_GEMM_CTAS;
-constexpr int BM = 32 * WM, BN = 128, BK = DSB_GEMM_BK, STAGES = DSB_GEMM_STAGES, THREADS = 64 * WM;
+#ifndef DSB_GEMM_WTN
+#define DSB_GEMM_WTN 64        // warp tile width (columns): 64 -> 2 warps along N, 32 -> 4 warps along N
+#endif
+constexpr int WM = DSB_GEMM_WM, CTAS = DSB_GEMM_CTAS, WTN = DSB_GEMM_WTN, NT = WTN / 8;
+constexpr int BM = 32 * WM, BN = 128, BK = DSB_GEMM_BK, STAGES = DSB_GEMM_STAGES, THREADS = 32 * WM * (BN / WTN);
 constexpr int LDA = BK + 4;        // doubles: 2 * LDA words == 8 (mod 32) -> rows g = 0..3 fill one wavefront
 constexpr int LDB = BN + 8;        // doubles: 272 words == 16 (mod 32) -> k rows t = 0, 1 fill one wavefront
 constexpr int A_STAGE = BM * LDA, B_STAGE = BK * LDB;
@@ -102,11 +105,11 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
     if (tile < mb * nb) prologue(tile);
     for (; tile < mb * nb; tile += gridDim.x) {
         const int m0 = (tile % mb) * BM, n0 = (tile / mb) * BN;
-        double acc[4][8][2];
+        double acc[4][NT][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         for (int k = 0; k < kt; ++k) {
             cp_async_wait<STAGES - 2>();
@@ -114,18 +117,18 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
             if (k + STAGES - 1 < kt) load_stage((k + STAGES - 1) % STAGES, (k + STAGES - 1) * BK);
             cp_async_commit();
             const double *a = sA + (k % STAGES) * A_STAGE + (wm * 32 + g) * LDA + t;
-            const double *b = sB + (k % STAGES) * B_STAGE + t * LDB + wn * 64 + g;
+            const double *b = sB + (k % STAGES) * B_STAGE + t * LDB + wn * WTN + g;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
-                double af[4], bf[8];
+                double af[4], bf[NT];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) af[i] = a[i * 8 * LDA + kk * 4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bf[j] = b[kk * 4 * LDB + j * 8];
+                for (int j = 0; j < NT; ++j) bf[j] = b[kk * 4 * LDB + j * 8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dmma(acc[i][j], af[i], bf[j]);
+                    for (int j = 0; j < NT; ++j) dmma(acc[i][j], af[i], bf[j]);
             }
         }
         cp_async_wait<0>();
@@ -136,11 +139,11 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
         if (tile + (int)gridDim.x < mb * nb) prologue(tile + gridDim.x);
 
         // epilogue: lane (g, t) owns C[8 i + g][8 j + 2 t .. + 1] of each 8 x 8 tile: 16-byte stores
-        double *Cg = C + (size_t)(m0 + wm * 32 + g) * N + n0 + wn * 64 + 2 * t;
+        double *Cg = C + (size_t)(m0 + wm * 32 + g) * N + n0 + wn * WTN + 2 * t;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < NT; ++j)
                 *reinterpret_cast<double2 *>(Cg + (size_t)i * 8 * N + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
 }
