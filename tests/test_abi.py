@@ -75,6 +75,16 @@ def test_bad_arguments_are_reported_without_a_gpu():
     assert lib.dsb_erk_create(ctypes.byref(h), 0, 1, 3, 0, None, None, 2, 5.0, 0) == cb.DSB_ERR_BAD_ARGUMENT
 
 
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    from desolver_b200.backend import cuda_backend as cb
+    lib = cb.lib()
+    assert lib.dsb_dgemm(None, None, None, 64, 128, 16, None) == cb.DSB_ERR_BAD_ARGUMENT
+    assert lib.dsb_erk_run_host(None, None, None) == cb.DSB_ERR_BAD_ARGUMENT
+    assert lib.dsb_erk_stage_finish_events(None, None, 0, None, None) == cb.DSB_ERR_BAD_ARGUMENT
+    assert lib.dsb_symp_stage_commit_events(None, None, 0, None, None, None) == cb.DSB_ERR_BAD_ARGUMENT
+    assert b"bad argument" in lib.dsb_last_error() or b"null" in lib.dsb_last_error()
+
+
 def test_package_has_no_cpu_fallback():
     import torch
     import desolver_b200 as de
