@@ -206,10 +206,9 @@ def main():
         if world > 1:
             # termination / statistics all-reduce (NCCL) straight from the kernel's device counters
             # ([2] attempts, [4] failed, [5] unfinished): no host round trip in front of the collective
-            c = sys_._counters.to(torch.float64)
-            red = torch.stack([c[2], c[4] + c[5]])
+            red = sys_._counters[2:6].clone()          # [attempts, accepted, failed, unfinished], int64
             dist.all_reduce(red)
-            return red
+            return torch.stack([red[0], red[2] + red[3]]).to(torch.float64)
         return torch.tensor([float(st["attempts"]), float(st["failed"] + st["running"])], dtype=torch.float64)
 
     for _ in range(args.warmup):
