@@ -85,6 +85,7 @@ class ErkStageArgs(C.Structure):
         ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
         ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
         ("ev_state", C.c_void_p), ("tf_per", C.c_void_p),
+        ("ev_coef_dy", C.c_void_p),
     ]
 
 
@@ -116,6 +117,7 @@ class SympStageArgs(C.Structure):
         ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
         ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
         ("ev_state", C.c_void_p), ("tf_per", C.c_void_p), ("ev_scratch", C.c_void_p),
+        ("ev_coef_dy", C.c_void_p),
     ]
 
 

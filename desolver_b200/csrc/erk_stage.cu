@@ -418,12 +418,43 @@ __global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restri
     const long long n = a.n;
     const int D = a.dim, W = a.dim + 2, ne = a.n_events;
     const double t1 = a.t[i], t0 = a.ev_state[i], dt_prev = a.ev_state[n + i], trange = t1 - t0;
-    double g0s[EV_NE], g1s[EV_NE];
+    // Along the step's interpolant an affine event g(t, y, dy) = wy.y + wdy.dy + wt t - c is the polynomial
+    //   G(tau) = [Hermite cubic of (gy0, gy1, a, b)](tau) + wdy . grad(tau),
+    // with gy = wy.y + wt t - c at the ends, a = trange (wy.m0 + wt), b = trange (wy.m1 + wt), and
+    //   wdy . grad(tau) = M0 + tau (-6 (P - Q)/trange - 4 M0 - 2 M1) + tau^2 (6 (P - Q)/trange + 3 M0 + 3 M1)
+    // (utilities/interpolation.py:63-78; P, Q = wdy.p0, wdy.p1; M0, M1 = wdy.m0, wdy.m1).  g at the step start is
+    // formed from the step's own data (p0, m0 = K[0]) -- what the reference's root finder evaluates at t_prev.
+    double pc[EV_NE][4];                      // G(tau) = pc0 + pc1 tau + pc2 tau^2 + pc3 tau^3
     unsigned mask = 0;
     for (int e = 0; e < ne; ++e) {
-        const double g1 = stage_ev_g(a, e, i, t1, a.dY), g0 = a.ev_state[(long long)(2 + EV_NE + e) * n + i];
+        const double *w = a.ev_coef + (long long)e * W;
+        const double *wd = a.ev_coef_dy ? a.ev_coef_dy + (long long)e * D : nullptr;
+        double gy0 = w[D] * t0 - w[D + 1], gy1 = w[D] * t1 - w[D + 1], dg0 = w[D], dg1 = w[D];
+        double P = 0.0, Q = 0.0, M0 = 0.0, M1 = 0.0;
+        bool has_dy = false;
+        for (int d = 0; d < D; ++d) {
+            const long long q = (long long)d * n + i;
+            const bool uy = w[d] != 0.0, ud = wd && wd[d] != 0.0;
+            if (!uy && !ud) continue;
+            const double p0 = a.y[q], p1 = a.y[q] + a.dY[q], m0 = k0[q], m1 = f1[q];
+            if (uy) { gy0 = fma(w[d], p0, gy0); gy1 = fma(w[d], p1, gy1); dg0 = fma(w[d], m0, dg0); dg1 = fma(w[d], m1, dg1); }
+            if (ud) { P = fma(wd[d], p0, P); Q = fma(wd[d], p1, Q); M0 = fma(wd[d], m0, M0); M1 = fma(wd[d], m1, M1); has_dy = true; }
+        }
+        const double ca = trange * dg0, cb = trange * dg1;
+        pc[e][0] = gy0;
+        pc[e][1] = ca;
+        pc[e][2] = 3.0 * (gy1 - gy0) - 2.0 * ca - cb;
+        pc[e][3] = 2.0 * (gy0 - gy1) + ca + cb;
+        double g0 = gy0, g1 = gy1;
+        if (has_dy) {
+            const double s6 = 6.0 * (P - Q) / trange;
+            pc[e][0] += M0;
+            pc[e][1] += -s6 - 4.0 * M0 - 2.0 * M1;
+            pc[e][2] += s6 + 3.0 * M0 + 3.0 * M1;
+            g0 += M0;
+            g1 += M1;
+        }
         a.ev_state[(long long)(2 + EV_NE + e) * n + i] = g1;
-        g0s[e] = g0; g1s[e] = g1;
         const int dir = a.ev_flags[e] & 3;
         const bool rising = g0 < 0.0;
         if (g0 * g1 < 0.0 && (dir == 0 || (dir == 1) == rising)) mask |= 1u << e;
@@ -433,18 +464,14 @@ __global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restri
     int which[EV_NE], cnt = 0;
     for (int e = 0; e < ne; ++e) {
         if (!(mask >> e & 1u)) continue;
-        const double *w = a.ev_coef + (long long)e * W;
-        double dg0 = w[D], dg1 = w[D];
-        for (int d = 0; d < D; ++d)
-            if (w[d] != 0.0) { dg0 = fma(w[d], k0[(long long)d * n + i], dg0); dg1 = fma(w[d], f1[(long long)d * n + i], dg1); }
-        const double g0 = g0s[e], g1 = g1s[e], ca = trange * dg0, cb = trange * dg1;
-        const double c2 = 3.0 * (g1 - g0) - 2.0 * ca - cb, c3 = 2.0 * (g0 - g1) + ca + cb;
+        const double c0 = pc[e][0], c1 = pc[e][1], c2 = pc[e][2], c3 = pc[e][3];
+        const double g0 = c0, g1 = ((c3 + c2) + c1) + c0;
         double lo = 0.0, hi = 1.0, tau = g0 / (g0 - g1);
         for (int it = 0; it < 64; ++it) {
-            const double G = fma(fma(fma(c3, tau, c2), tau, ca), tau, g0);
+            const double G = fma(fma(fma(c3, tau, c2), tau, c1), tau, c0);
             if (G == 0.0) break;
             if ((G < 0.0) == (g0 < 0.0)) lo = tau; else hi = tau;
-            const double dG = fma(fma(3.0 * c3, tau, 2.0 * c2), tau, ca);
+            const double dG = fma(fma(3.0 * c3, tau, 2.0 * c2), tau, c1);
             const double step = G / dG;
             if (fabs(step) <= 2.3e-16) break;
             double nxt = tau - step;

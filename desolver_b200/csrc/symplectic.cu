@@ -390,6 +390,7 @@ int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a
     v.accepted = a->steps; v.status = a->status; v.counters = a->counters; v.tf = a->tf;
     v.n_events = a->n_events; v.ev_capacity = a->ev_capacity; v.ev_coef = a->ev_coef; v.ev_flags = a->ev_flags;
     v.ev_records = a->ev_records; v.ev_count = a->ev_count; v.ev_state = a->ev_state; v.tf_per = a->tf_per;
+    v.ev_coef_dy = a->ev_coef_dy;
     rc = launch_stage_events(v, f0, f1, st);
     if (rc != DSB_OK) return rc;
     const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);

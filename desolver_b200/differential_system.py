@@ -595,6 +595,10 @@ class OdeSystem(object):
         from .events import EventLog
         coef = torch.as_tensor(np.stack([ev.coefficients(self.numel) for ev in events]), dtype=torch.float64).to(self.device)
         flags = torch.as_tensor([ev.flags for ev in events], dtype=torch.int32).to(self.device)
+        self._event_coef_dy = None
+        if any(ev.requires_dstate for ev in events):          # weights on dState/dt (stage-level kernels only)
+            self._event_coef_dy = torch.as_tensor(np.stack([ev.dy_coefficients(self.numel) for ev in events]),
+                                                  dtype=torch.float64).to(self.device)
         if self._event_log is None or self._event_log.compiled != list(events):
             records = torch.zeros((self.n_traj, int(self.event_capacity), self.numel + 2), dtype=torch.float64, device=self.device)
             count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
@@ -810,6 +814,8 @@ class OdeSystem(object):
             a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
             a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
             a.ev_state, a.tf_per = ev_state.data_ptr(), tf_per.data_ptr()
+            if self._event_coef_dy is not None:
+                a.ev_coef_dy = self._event_coef_dy.data_ptr()
             self._keepalive = (coef, flags, ev_state, tf_per)      # referenced by raw pointer until the run has finished
         can_compact = self.ensemble and self.compaction and not callbacks and not dense and not events
         K = [None] * S
@@ -997,6 +1003,8 @@ class OdeSystem(object):
             a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
             a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
             a.ev_state, a.tf_per, a.ev_scratch = ev_state.data_ptr(), tf_per.data_ptr(), scratch.data_ptr()
+            if self._event_coef_dy is not None:
+                a.ev_coef_dy = self._event_coef_dy.data_ptr()
             self._keepalive = (coef, flags, ev_state, tf_per, scratch)   # referenced by raw pointer until the run has finished
 
         self._ensure_dense_store()
@@ -1108,8 +1116,9 @@ class OdeSystem(object):
             if events and (self.host_io or callbacks or eta or self.__dense_output):
                 raise NotImplementedError("device event detection needs device-resident state and no callbacks / progress "
                                           "bar / dense output in the same call")
-            if events and plugin is not None and self.integrator.stages > 7:
-                plugin = None            # the event-detecting fused kernels stop at 7 stages: stage-level path
+            if events and plugin is not None and (self.integrator.stages > 7 or any(ev.requires_dstate for ev in events)):
+                # the event-detecting fused kernels stop at 7 stages and see g(t, y) only: stage-level path
+                plugin = None
             if self.integrator.symplectic or plugin is None:
                 self._stats = None
             if self.integrator.symplectic:

@@ -18,21 +18,56 @@ time marks) are all of this form.
 """
 import numpy as np
 
-__all__ = ["HyperplaneEvent", "as_hyperplane", "component_crossing", "EventLog"]
+__all__ = ["HyperplaneEvent", "as_hyperplane", "component_crossing", "component_extremum", "EventLog"]
 
 
 class HyperplaneEvent(object):
-    """g(t, y) = w . y + wt * t - c, with the reference's event attributes `is_terminal` and `direction`."""
+    """g(t, y[, dy]) = w . y + w_dy . dy + wt * t - c, with the reference's event attributes `is_terminal`, `direction`
+    and -- when `w_dy` is given -- `requires_dstate` (the event then also sees dy = the derivative of the dense-output
+    interpolant, /root/reference/desolver/differential_system.py:92-96: extrema of a component, e.g. the successive
+    maxima of z of the Lorenz map, are `w_dy = e_z, direction = -1`)."""
 
-    def __init__(self, w, c=0.0, wt=0.0, direction=0, is_terminal=False, name=None):
+    def __init__(self, w, c=0.0, wt=0.0, direction=0, is_terminal=False, name=None, w_dy=None):
         self.w = np.asarray(w, dtype=np.float64).reshape(-1)
+        self.w_dy = None
+        if w_dy is not None:
+            w_dy = np.asarray(w_dy, dtype=np.float64).reshape(-1)
+            if w_dy.shape != self.w.shape:
+                raise ValueError("w_dy must have as many entries as w")
+            if w_dy.any():
+                self.w_dy = w_dy
+        self.requires_dstate = self.w_dy is not None
         self.c = float(c)
         self.wt = float(wt)
         self.direction = int(np.sign(direction))
         self.is_terminal = bool(is_terminal)
-        self.name = name or "hyperplane(w=%s, wt=%g, c=%g)" % (self.w.tolist(), self.wt, self.c)
+        self.name = name or "hyperplane(w=%s, w_dy=%s, wt=%g, c=%g)" % (
+            self.w.tolist(), None if self.w_dy is None else self.w_dy.tolist(), self.wt, self.c)
 
     def __call__(self, t, y, *args, **constants):
+        if self.w_dy is not None:
+            dy = args[0]
+            return self._affine(t, y) + self._dot(self.w_dy, dy, 0.0)
+        return self._affine(t, y)
+
+    def _dot(self, w, y, g):
+        n = w.shape[0]
+        if y.shape[0] != n:
+            lead = 1
+            k = 0
+            while lead < n:
+                lead *= y.shape[k]
+                k += 1
+            y = y.reshape((n,) + tuple(y.shape[k:]))
+        for d in range(n):
+            if w[d] != 0.0:
+                g = g + w[d] * y[d]
+        return g
+
+    def dy_coefficients(self, dim):
+        return np.zeros(dim) if self.w_dy is None else self.w_dy
+
+    def _affine(self, t, y, *args, **constants):
         # y is (dim,) for one system, (dim, N) for an ensemble; a multi-axis state (*dim[, N]) is flattened first
         n = self.w.shape[0]
         if y.shape[0] != n:
@@ -66,11 +101,11 @@ def as_hyperplane(event, dim, constants=None):
     assumed: the coefficients are read off by probing `event` at the origin and the unit vectors (numpy arrays first,
     CPU torch tensors if the callable insists on torch), and the fit is verified at random points.  Typical scipy-style
     events -- `t - t_mark`, `y[0] - level`, `y[1] + 2*y[0]` -- qualify and then run on the device unchanged; anything
-    else (products, `requires_dstate` events, per-trajectory constants) raises NotImplementedError."""
+    else (products, per-trajectory constants) raises NotImplementedError.  `requires_dstate` events
+    `event(t, y, dy)` are probed in dy as well."""
     if isinstance(event, HyperplaneEvent):
         return event
-    if getattr(event, "requires_dstate", False):
-        raise NotImplementedError("events with requires_dstate=True are not supported on the device")
+    with_dy = bool(getattr(event, "requires_dstate", False))
     consts = {k: v for k, v in (constants or {}).items()}
     for v in consts.values():
         if getattr(v, "ndim", 0) >= 1 and type(v).__module__.split(".")[0] == "torch" and v.is_cuda:
@@ -78,8 +113,11 @@ def as_hyperplane(event, dim, constants=None):
             break
 
     def probe(make):
-        def g(t, y):
-            out = event(make(t, scalar=True), make(y), **consts)
+        def g(t, y, dy=None):
+            if with_dy:
+                out = event(make(t, scalar=True), make(y), make(np.zeros(dim) if dy is None else dy), **consts)
+            else:
+                out = event(make(t, scalar=True), make(y), **consts)
             out = np.asarray(out.detach().cpu() if hasattr(out, "detach") else out)
             if out.size != 1:
                 raise NotImplementedError("event %r returns %d values for one state: events that depend on per-trajectory "
@@ -100,15 +138,16 @@ def as_hyperplane(event, dim, constants=None):
             g0 = g(0.0, zero)
             wt = g(1.0, zero) - g0
             w = np.array([g(0.0, np.eye(dim)[d]) - g0 for d in range(dim)])
+            w_dy = np.array([g(0.0, zero, np.eye(dim)[d]) - g0 for d in range(dim)]) if with_dy else None
             rng = np.random.default_rng(12345)
             for _ in range(4):
-                tt, yy = float(rng.uniform(-3, 3)), rng.uniform(-3, 3, size=dim)
-                want = g(tt, yy)
-                fit = float(w @ yy) + wt * tt + g0
+                tt, yy, dd = float(rng.uniform(-3, 3)), rng.uniform(-3, 3, size=dim), rng.uniform(-3, 3, size=dim)
+                want = g(tt, yy, dd)
+                fit = float(w @ yy) + wt * tt + g0 + (float(w_dy @ dd) if with_dy else 0.0)
                 if not abs(want - fit) <= 1e-9 * (1.0 + abs(want)):
                     raise NotImplementedError("event %r is not an affine function of (t, y): the device detects hyperplane "
                                               "events only (desolver_b200.events.HyperplaneEvent)" % (event,))
-            hp = HyperplaneEvent(w, c=-g0, wt=wt, direction=getattr(event, "direction", 0),
+            hp = HyperplaneEvent(w, c=-g0, wt=wt, direction=getattr(event, "direction", 0), w_dy=w_dy,
                                  is_terminal=getattr(event, "is_terminal", False), name=getattr(event, "__name__", repr(event)))
             hp.source = event
             return hp
@@ -117,6 +156,16 @@ def as_hyperplane(event, dim, constants=None):
         except Exception as exc:                      # the callable could not digest this array type: try the next one
             last = exc
     raise NotImplementedError("event %r could not be probed for an affine form (%r)" % (event, last))
+
+
+def component_extremum(index, dim=None, direction=0, is_terminal=False):
+    """Event `d y[index] / dt == 0`: an extremum of that component (direction -1: maxima, +1: minima)."""
+    if dim is None:
+        raise ValueError("component_extremum needs dim= (the number of state components)")
+    w = np.zeros(int(dim))
+    w[int(index)] = 1.0
+    return HyperplaneEvent(np.zeros(int(dim)), w_dy=w, direction=direction, is_terminal=is_terminal,
+                           name="dy[%d]/dt == 0" % int(index))
 
 
 def component_crossing(index, value=0.0, dim=None, direction=0, is_terminal=False):

@@ -223,6 +223,9 @@ typedef struct {
                                   last occurrence time per event, g at the step start per event     */
     double *tf_per;            /* [n] per-trajectory final time, initialised to tf by the caller; a terminal
                                   event re-targets it to the event time (NULL: tf for everyone)     */
+    const double *ev_coef_dy;  /* [n_events][dim] weights on dState/dt (NULL: none): events of the reference's
+                                  `requires_dstate` kind, g(t, y, dy) with dy = the interpolant's derivative
+                                  (differential_system.py:92-96, utilities/interpolation.py:63-78)  */
 } dsb_erk_stage_args;
 
 DSB_API int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);
@@ -288,6 +291,7 @@ typedef struct {
     double *ev_state;          /* [2 + 2*DSB_MAX_EVENTS][n] scratch                              */
     double *tf_per;            /* [n] per-system final time, initialised to tf by the caller     */
     int32_t *ev_scratch;       /* [n] scratch                                                    */
+    const double *ev_coef_dy;  /* [n_events][dim] weights on dState/dt (NULL: none)              */
 } dsb_symp_stage_args;
 
 DSB_API int dsb_symp_stage_begin(dsb_symp_handle h, const dsb_symp_stage_args *a, int first_call, void *stream);

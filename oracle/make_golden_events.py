@@ -33,7 +33,9 @@ MAX_EV = 48
 
 
 def event_set(name):
-    from desolver_b200.events import component_crossing
+    from desolver_b200.events import component_crossing, component_extremum
+    if name == "lorenz_zmax":          # successive maxima of z (the Lorenz map): dz/dt falls through 0 -- requires_dstate
+        return [component_extremum(2, dim=3, direction=-1), component_crossing(0, 0.0, dim=3, direction=0)]
     if name == "lorenz_sections":      # lobe switches (x = 0, both directions) and falling crossings of y = 0
         return [component_crossing(0, 0.0, dim=3, direction=0), component_crossing(1, 0.0, dim=3, direction=-1)]
     if name == "lorenz_terminal":      # stop at the first rising crossing of x = 0; y = 0 crossings are recorded until then
@@ -66,7 +68,10 @@ def run_one(job):
     ys, ts = np.asarray(a.y), np.asarray(a.t)
     crossings = np.zeros(len(evs), dtype=np.int32)
     for e, ev in enumerate(evs):
-        gv = np.array([ev(ts[k], ys[k]) for k in range(len(ts))])
+        if getattr(ev, "requires_dstate", False):
+            gv = np.array([ev(ts[k], ys[k], rhs_plugins.BUILTIN[rhs_name](ts[k], ys[k], **dict(consts))) for k in range(len(ts))])
+        else:
+            gv = np.array([ev(ts[k], ys[k]) for k in range(len(ts))])
         chg = gv[:-1] * gv[1:] < 0
         if ev.direction > 0:
             chg &= gv[:-1] < 0
@@ -80,6 +85,7 @@ def run_one(job):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
     from desolver_b200 import benchmarks as bm
     L = bm.LORENZ
@@ -88,6 +94,7 @@ def main():
     yl = bm.lorenz_ensemble(n, seed=21)
     yv, mu = bm.vdp_ensemble(n, seed=22)
     cases = {
+        "lorenz_zmax": [("lorenz", "lorenz_zmax", yl[:, i], 2.0, 1e-2, 1e-9, lconst) for i in range(n)],
         "lorenz_sections": [("lorenz", "lorenz_sections", yl[:, i], 2.0, 1e-2, 1e-9, lconst) for i in range(n)],
         "lorenz_terminal": [("lorenz", "lorenz_terminal", yl[:, i], 2.0, 1e-2, 1e-9, lconst) for i in range(n)],
         "vdp_sections": [("van_der_pol", "vdp_sections", yv[:, i], 10.0, 1e-2, 1e-9, dict(mu=float(mu[i]))) for i in range(n)],
@@ -95,6 +102,8 @@ def main():
     }
     with ProcessPoolExecutor(args.procs) as pool:
         for name, jobs in cases.items():
+            if args.only and name not in args.only.split(","):
+                continue
             res = list(pool.map(run_one, jobs, chunksize=4))
             y0 = yl if name.startswith("lorenz") else yv
             blob = dict(y0=y0, records=np.stack([r["rec"] for r in res]), count=np.array([r["count"] for r in res], dtype=np.int32),

@@ -59,7 +59,13 @@ def test_affine_callables_are_recognised_and_others_refused():
             as_hyperplane(bad, 2)
     with pytest.raises(NotImplementedError):                  # depends on a per-trajectory constant
         as_hyperplane(lambda t, y, mu=None: y[0] - mu, 2, dict(mu=np.linspace(0.0, 1.0, 5)))
-    ev = lambda t, y, dy: dy[0]
+    ev = lambda t, y, dy: 2.0 * dy[1] - y[0] + 0.5 * t - 3.0      # the reference's requires_dstate protocol
     ev.requires_dstate = True
+    h = as_hyperplane(ev, 2)
+    assert h.requires_dstate and np.array_equal(h.w_dy, [0.0, 2.0]) and np.array_equal(h.w, [-1.0, 0.0])
+    assert h.wt == 0.5 and h.c == 3.0
+    assert h(1.0, np.array([1.0, 0.0]), np.array([0.0, 4.0])) == ev(1.0, np.array([1.0, 0.0]), np.array([0.0, 4.0]))
+    bad = lambda t, y, dy: dy[0] * y[0]
+    bad.requires_dstate = True
     with pytest.raises(NotImplementedError):
-        as_hyperplane(ev, 2)
+        as_hyperplane(bad, 2)

@@ -74,7 +74,7 @@ def _check_events(a, g):
 
 
 @pytest.mark.parametrize("use_fused", [True, False])
-@pytest.mark.parametrize("name", ["lorenz_sections", "vdp_sections"])
+@pytest.mark.parametrize("name", ["lorenz_sections", "vdp_sections", "lorenz_zmax"])
 def test_non_terminal_events_match_reference_and_do_not_perturb_the_integration(name, use_fused):
     a, g, evs = _run(name, use_fused=use_fused)
     cnt, idx = _check_events(a, g)
@@ -87,11 +87,18 @@ def test_non_terminal_events_match_reference_and_do_not_perturb_the_integration(
     assert np.all(a.status.cpu().numpy() == 0)
     # recorded states lie on their hyperplanes
     log = a.events
+    import desolver_b200 as de
     for i in range(0, cnt.shape[0], 7):
         for st in log.for_trajectory(i):
-            assert abs(float(st.event(float(st.t), st.y.numpy()))) <= 1e-9
+            if st.event.requires_dstate:
+                # extremum of z along the INTERPOLANT; the true derivative there vanishes to the interpolation error
+                dy = de.rhs_plugins.lorenz(float(st.t), st.y.numpy())
+                assert abs(float(st.event(float(st.t), st.y.numpy(), dy))) <= 1e-2
+            else:
+                assert abs(float(st.event(float(st.t), st.y.numpy()))) <= 1e-9
     # events are observers: the integration itself is bit-identical to a run without them
-    b, _, _ = _run(name, events=False, use_fused=use_fused)
+    # (requires_dstate events always run on the stage-level path, so that is the path to compare with)
+    b, _, _ = _run(name, events=False, use_fused=use_fused and not any(e.requires_dstate for e in evs))
     assert torch.equal(a[-1].y, b[-1].y) and torch.equal(a.accepted, b.accepted) and torch.equal(a.rejected, b.rejected)
     assert rel_inf(a[-1].y.cpu().numpy(), g["y_final"]).max() <= 1e-9
     assert np.mean(a.accepted.cpu().numpy() == g["accepted"]) >= 0.97
