@@ -47,6 +47,7 @@ class ErkRunArgs(C.Structure):
         ("n_events", C.c_int32), ("ev_capacity", C.c_int32),
         ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
         ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
+        ("ev_coef_dy", C.c_void_p),
     ]
 
 

@@ -85,7 +85,7 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     case DSB_RHS_DUFFING: fused = dim == 2 && select_fused_duffing(p); break;
     default: break;
     }
-    if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = nullptr;
+    if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = p->fused_launch_events_dy = nullptr;
 
     double2 host_tab[fm::ATAN_TABLE_SIZE];
     fm::build_atan_table(host_tab);
@@ -155,7 +155,7 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
             set_error("dsb_erk_run: no event-detecting kernel for rhs_id=%d stages=%d (<= 7 stages)", h->rhs_id, h->stages);
             return DSB_ERR_UNSUPPORTED;
         }
-        return h->fused_launch_events(h, a, (cudaStream_t)stream);
+        return (a->ev_coef_dy ? h->fused_launch_events_dy : h->fused_launch_events)(h, a, (cudaStream_t)stream);
     }
     return h->fused_launch(h, a, (cudaStream_t)stream);
 }

@@ -197,16 +197,19 @@ static __device__ __noinline__ void flow_done(uint32_t *counter)
 // trajectory and counts stored results in `done`.  A separate instantiation, because even untaken the hooks cost the
 // device-resident kernel 3.6 % (3.53 -> 3.66 ms: different register allocation in the hot loop).
 // EV: event detection after every accepted step (dsb_erk_run_args.n_events > 0), see the event block below.
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
+// (EVK: 0 none, 1 events g(t, y), 2 events that may also depend on dState/dt -- a separate instantiation, because the
+// extra live values cost the plain event kernel 15 %: 6.0 -> 6.9 ms)
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
 #ifndef DSB_EV_MAX_BLOCKS
 #define DSB_EV_MAX_BLOCKS 5
 #endif
-__global__ void __launch_bounds__(ERK_THREADS, (EV ? (erk_min_blocks<Rhs, Tab::S>() > DSB_EV_MAX_BLOCKS ? DSB_EV_MAX_BLOCKS
+__global__ void __launch_bounds__(ERK_THREADS, (EVK ? (erk_min_blocks<Rhs, Tab::S>() > DSB_EV_MAX_BLOCKS ? DSB_EV_MAX_BLOCKS
                                                                                                          : erk_min_blocks<Rhs, Tab::S>())
                                                    : erk_min_blocks<Rhs, Tab::S>()))
 erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 {
     using A = Ar<STRICT>;
+    constexpr bool EV = EVK != 0;
     constexpr int S = Tab::S, D = Rhs::DIM, NP = Rhs::NPARAM;
     constexpr unsigned FULL = 0xffffffffu;
     const Tab tab(P.tab);
@@ -235,11 +238,14 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     // and the time of each event's last recorded occurrence
     constexpr int NE = DSB_MAX_EVENTS, EVW = Rhs::DIM + 2;
     __shared__ double s_evc[EV ? NE * EVW : 1];
+    __shared__ double s_evd[EV ? NE * Rhs::DIM : 1];         // weights on dState/dt (requires_dstate events)
     __shared__ int s_evf[EV ? NE : 1];
     __shared__ double s_gprev[EV ? NE : 1][EV ? ERK_THREADS : 1];
     __shared__ double s_evlast[EV ? NE : 1][EV ? ERK_THREADS : 1];
     const int ne = EV ? (P.a.n_events < NE ? P.a.n_events : NE) : 0;
+    const bool ev_dy = EVK == 2 && P.a.ev_coef_dy != nullptr;  // some event also depends on dState/dt
     if (EV) {
+        for (int i = threadIdx.x; i < ne * Rhs::DIM; i += blockDim.x) s_evd[i] = ev_dy ? P.a.ev_coef_dy[i] : 0.0;
         for (int i = threadIdx.x; i < ne * EVW; i += blockDim.x) s_evc[i] = P.a.ev_coef[i];
         for (int i = threadIdx.x; i < ne; i += blockDim.x) s_evf[i] = P.a.ev_flags[i];
         __syncthreads();
@@ -332,6 +338,14 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         for (int d = 0; d < D; ++d) g = fma(s_evc[e * EVW + d], yy[d], g);
         return g;
     };
+    // wdy_e . v: the part of a requires_dstate event that sees dState/dt (v = a right-hand side, or a state for the
+    // P, Q terms of the interpolant's derivative)
+    auto ev_d = [&](int e, const double (&v)[D]) -> double {
+        double g = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) g = fma(s_evd[e * D + d], v[d], g);
+        return g;
+    };
 
     // Rare path, entered by the whole warp when ANY lane rejected, finished, failed or is idle:
     // retry bookkeeping, result stores, refill from the global queue.  Returns false when the warp is out of work.
@@ -410,8 +424,10 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 if (EV) {
                     tf_lane = tf;
                     final_leg = false;
+                    double fl0[D];
+                    if (ev_dy) eval_rhs<Rhs>(t, y, prm, fl0);
                     for (int e = 0; e < ne; ++e) {
-                        s_gprev[e][threadIdx.x] = ev_g(e, t, y);
+                        s_gprev[e][threadIdx.x] = ev_g(e, t, y) + (ev_dy ? ev_d(e, fl0) : 0.0);
                         s_evlast[e][threadIdx.x] = CUDART_NAN;
                     }
                     if (fresh) P.a.ev_count[idx] = 0;
@@ -621,10 +637,12 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             }
             if (EV && !final_leg) {
                 // an event is searched for iff g changes sign over the step (utilities/optimizer.py:252)
+                double fc[D];
+                if (ev_dy) eval_rhs<Rhs>(t, y, prm, fc);                 // requires_dstate events see rhs at the step end
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     if (e < ne) {
-                        const double g1 = ev_g(e, t, y), g0 = s_gprev[e][threadIdx.x];
+                        const double g1 = ev_g(e, t, y) + (ev_dy ? ev_d(e, fc) : 0.0), g0 = s_gprev[e][threadIdx.x];
                         s_gprev[e][threadIdx.x] = g1;
                         const int dir = s_evf[e] & 3;
                         const bool rising = g0 < 0.0;
@@ -654,15 +672,27 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     if (!(ev_mask >> e & 1u)) continue;
                     // along the interpolant a linear g is itself the Hermite cubic of (g0, g1, dg0, dg1):
                     //   G(tau) = g0 + a tau + c2 tau^2 + c3 tau^3,  a = trange*dg0, b = trange*dg1
-                    const double g0 = ev_g(e, t0, y0), g1 = ev_g(e, t1, y);
+                    const double gy0 = ev_g(e, t0, y0), gy1 = ev_g(e, t1, y);
                     double dg0 = s_evc[e * EVW + D], dg1 = dg0;
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         dg0 = fma(s_evc[e * EVW + d], k[0][d], dg0);
                         dg1 = fma(s_evc[e * EVW + d], f1[d], dg1);
                     }
-                    const double a = trange * dg0, b = trange * dg1;
-                    const double c2 = 3.0 * (g1 - g0) - 2.0 * a - b, c3 = 2.0 * (g0 - g1) + a + b;
+                    double g0 = gy0, a = trange * dg0;
+                    const double b = trange * dg1;
+                    double c2 = 3.0 * (gy1 - gy0) - 2.0 * a - b;
+                    const double c3 = 2.0 * (gy0 - gy1) + a + b;
+                    double g1 = gy1;
+                    if (ev_dy) {
+                        // + wdy . grad(tau) = M0 + tau (-6 (P - Q)/trange - 4 M0 - 2 M1) + tau^2 (6 (P - Q)/trange + 3 M0 + 3 M1)
+                        // (utilities/interpolation.py:63-78)
+                        const double M0 = ev_d(e, k[0]), M1 = ev_d(e, f1), s6 = 6.0 * (ev_d(e, y0) - ev_d(e, y)) / trange;
+                        g0 += M0;
+                        g1 += M1;
+                        a += -s6 - 4.0 * M0 - 2.0 * M1;
+                        c2 += s6 + 3.0 * M0 + 3.0 * M1;
+                    }
                     // bracketed Newton on [0, 1] (the reference runs Brent's method on the same function)
                     double lo = 0.0, hi = 1.0, tau = g0 / (g0 - g1);
                     for (int it = 0; it < 64; ++it) {
@@ -761,19 +791,19 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 }
 
 // Host-side launcher, one per instantiation.
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
 int launch_erk_fused(const ErkKernelArgs<Tab::S> &args, int blocks, cudaStream_t stream)
 {
-    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EV><<<blocks, ERK_THREADS, 0, stream>>>(args);
+    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK><<<blocks, ERK_THREADS, 0, stream>>>(args);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
 int occupancy_erk_fused(int *blocks_per_sm)
 {
     DSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EV>, ERK_THREADS, 0));
+        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK>, ERK_THREADS, 0));
     return DSB_OK;
 }
 

@@ -25,7 +25,8 @@ struct dsb_erk_plan {
     int (*fused_launch_flow)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
     // same kernel with event detection compiled in (<= 7 stages); its own persistent grid size
     int (*fused_launch_events)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
-    int events_blocks = 0;
+    int (*fused_launch_events_dy)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;   // + dState/dt events
+    int events_blocks = 0, events_dy_blocks = 0;
 };
 
 namespace dsb {
@@ -57,7 +58,7 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, bool EV = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
 {
     ErkKernelArgs<Tab::S> args;
@@ -65,7 +66,8 @@ int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStrea
     fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
     args.factor_table = p->d_factor;
-    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EV>(args, EV ? p->events_blocks : p->fused_blocks, stream);
+    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK>(
+        args, EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks), stream);
 }
 
 // true iff the caller's tableau equals the compile-time one bit for bit
@@ -90,10 +92,13 @@ void bind_fused(dsb_erk_plan *p, int *per_sm)
     p->fused_launch = fused_trampoline<Rhs, Tab, STRICT>;
     if constexpr (!STRICT && Tab::S <= 7) p->fused_launch_flow = fused_trampoline<Rhs, Tab, STRICT, true>;
     if constexpr (Tab::S <= 7) {
-        p->fused_launch_events = fused_trampoline<Rhs, Tab, STRICT, false, true>;
+        p->fused_launch_events = fused_trampoline<Rhs, Tab, STRICT, false, 1>;
+        p->fused_launch_events_dy = fused_trampoline<Rhs, Tab, STRICT, false, 2>;
         int ev_per_sm = 0;
-        occupancy_erk_fused<Rhs, Tab, STRICT, false, true>(&ev_per_sm);
+        occupancy_erk_fused<Rhs, Tab, STRICT, false, 1>(&ev_per_sm);
         p->events_blocks = p->sm_count * (ev_per_sm < 1 ? 1 : ev_per_sm);
+        occupancy_erk_fused<Rhs, Tab, STRICT, false, 2>(&ev_per_sm);
+        p->events_dy_blocks = p->sm_count * (ev_per_sm < 1 ? 1 : ev_per_sm);
     }
     occupancy_erk_fused<Rhs, Tab, STRICT>(per_sm);
 }

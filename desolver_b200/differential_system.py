@@ -639,6 +639,8 @@ class OdeSystem(object):
             a.n_events, a.ev_capacity = len(events), self._event_log.capacity
             a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
             a.ev_records, a.ev_count = self._event_log._records.data_ptr(), self._event_log.count.data_ptr()
+            if self._event_coef_dy is not None:
+                a.ev_coef_dy = self._event_coef_dy.data_ptr()
             params = list(params) + [coef, flags]             # keep alive until the launch has run
         ev = self.__dict__.get("_kernel_events")          # optional (start, end) CUDA events bracketing the launch
         if ev:
@@ -1116,9 +1118,8 @@ class OdeSystem(object):
             if events and (self.host_io or callbacks or eta or self.__dense_output):
                 raise NotImplementedError("device event detection needs device-resident state and no callbacks / progress "
                                           "bar / dense output in the same call")
-            if events and plugin is not None and (self.integrator.stages > 7 or any(ev.requires_dstate for ev in events)):
-                # the event-detecting fused kernels stop at 7 stages and see g(t, y) only: stage-level path
-                plugin = None
+            if events and plugin is not None and self.integrator.stages > 7:
+                plugin = None            # the event-detecting fused kernels stop at 7 stages: stage-level path
             if self.integrator.symplectic or plugin is None:
                 self._stats = None
             if self.integrator.symplectic:

@@ -140,6 +140,9 @@ typedef struct {
     const int32_t *ev_flags;   /* device [n_events]: bits 0-1 direction (0 either, 1 rising, 2 falling), bit 2 terminal */
     double *ev_records;        /* device [n][ev_capacity][dim + 2]: t, y[dim], event index                        */
     int32_t *ev_count;         /* device [n] in/out: events found (records beyond ev_capacity are dropped)        */
+    const double *ev_coef_dy;  /* device [n_events][dim] weights on dState/dt (NULL: none): `requires_dstate` events,
+                                  g(t, y, dy) = w.y + w_dy.dy + wt t - c with dy the interpolant's derivative
+                                  (differential_system.py:92-96, utilities/interpolation.py:63-78)                */
 } dsb_erk_run_args;
 
 DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);

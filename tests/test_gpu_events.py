@@ -97,8 +97,7 @@ def test_non_terminal_events_match_reference_and_do_not_perturb_the_integration(
             else:
                 assert abs(float(st.event(float(st.t), st.y.numpy()))) <= 1e-9
     # events are observers: the integration itself is bit-identical to a run without them
-    # (requires_dstate events always run on the stage-level path, so that is the path to compare with)
-    b, _, _ = _run(name, events=False, use_fused=use_fused and not any(e.requires_dstate for e in evs))
+    b, _, _ = _run(name, events=False, use_fused=use_fused)
     assert torch.equal(a[-1].y, b[-1].y) and torch.equal(a.accepted, b.accepted) and torch.equal(a.rejected, b.rejected)
     assert rel_inf(a[-1].y.cpu().numpy(), g["y_final"]).max() <= 1e-9
     assert np.mean(a.accepted.cpu().numpy() == g["accepted"]) >= 0.97

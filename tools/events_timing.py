@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Cost of device event detection on the headline ensemble: 2^20 Lorenz trajectories, RK45CK, t in [0, 2], with
-(a) no events, (b) two recorded sections (x = 0 both ways, y = 0 falling), (c) a terminal event (first rising x = 0)."""
+(a) no events, (b) two recorded sections (x = 0 both ways, y = 0 falling), (c) a terminal event (first rising x = 0),
+(d) the successive maxima of z (an event on dState/dt)."""
 import json
 import os
 import sys
@@ -15,7 +16,8 @@ y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(n)).cuda()
 cc = de.events.component_crossing
 cases = {"none": None,
          "two sections": [cc(0, 0.0, dim=3), cc(1, 0.0, dim=3, direction=-1)],
-         "terminal x=0 rising + y=0 section": [cc(0, 0.0, dim=3, direction=1, is_terminal=True), cc(1, 0.0, dim=3)]}
+         "terminal x=0 rising + y=0 section": [cc(0, 0.0, dim=3, direction=1, is_terminal=True), cc(1, 0.0, dim=3)],
+         "Lorenz map: maxima of z (requires_dstate)": [de.events.component_extremum(2, dim=3, direction=-1)]}
 for name, evs in cases.items():
     a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, cfg["tf"]), dt=cfg["dt0"], rtol=1e-9, atol=1e-9, ensemble=True)
     a.event_capacity = 16
