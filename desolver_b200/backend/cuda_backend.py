@@ -12,8 +12,9 @@ import subprocess
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_PKG, "libdesolver_b200.so")
 
-ABI_VERSION = 2
-DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED = 0, 1, 2, 3
+ABI_VERSION = 3
+DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED, DSB_ERR_NCCL = 0, 1, 2, 3, 4
+COMM_ID_BYTES, IPC_HANDLE_BYTES = 128, 64
 TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING, TRAJ_EVENT = 0, 1, 2, 3
 MAX_EVENTS = 4
 FLAG_STRICT = 1
@@ -21,6 +22,16 @@ MAX_PARAMS = 6
 FUSED_STAGES = (1, 2, 4, 6, 7, 13, 17)
 
 _dp = C.POINTER(C.c_double)
+
+
+class NodeStoreStruct(C.Structure):
+    """dsb_node_store (include/desolver_b200.h)."""
+    _fields_ = [
+        ("pool", C.c_void_p),
+        ("capacity", C.c_int64),
+        ("width", C.c_int32), ("page_entries", C.c_int32), ("dim", C.c_int32),
+        ("cursor", C.c_void_p), ("page_fill", C.c_void_p), ("node_count", C.c_void_p),
+    ]
 
 
 class ErkRunArgs(C.Structure):
@@ -34,7 +45,7 @@ class ErkRunArgs(C.Structure):
         ("accepted", C.c_void_p), ("rejected", C.c_void_p), ("status", C.c_void_p),
         ("max_steps", C.c_int64),
         ("first_call", C.c_int32),
-        ("nodes", C.c_void_p), ("node_count", C.c_void_p), ("node_capacity", C.c_int32),
+        ("store", NodeStoreStruct),
         ("counters", C.c_void_p),
         # ABI 2
         ("stride", C.c_int64),
@@ -48,6 +59,10 @@ class ErkRunArgs(C.Structure):
         ("ev_coef", C.c_void_p), ("ev_flags", C.c_void_p),
         ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
         ("ev_coef_dy", C.c_void_p),
+        # ABI 3: scatter-store
+        ("out_y", C.c_void_p), ("out_t", C.c_void_p), ("out_dt", C.c_void_p),
+        ("out_accepted", C.c_void_p), ("out_rejected", C.c_void_p), ("out_status", C.c_void_p),
+        ("out_stride", C.c_int64), ("out_index_mul", C.c_int64), ("out_index_add", C.c_int64),
     ]
 
 
@@ -172,12 +187,24 @@ def lib():
     L.dsb_dgemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     L.dsb_erk_run_launches.restype = C.c_int
     L.dsb_erk_run_launches.argtypes = [C.c_void_p]
-    L.dsb_dense_eval.restype = C.c_int
-    L.dsb_dense_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
-                                 C.c_void_p, C.c_void_p]
-    L.dsb_dense_append.restype = C.c_int
-    L.dsb_dense_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    ns = C.POINTER(NodeStoreStruct)
+    L.dsb_node_offsets_scratch.restype = C.c_int64
+    L.dsb_node_offsets_scratch.argtypes = [C.c_int64]
+    L.dsb_node_offsets.restype = C.c_int
+    L.dsb_node_offsets.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dsb_node_locate.restype = C.c_int
+    L.dsb_node_locate.argtypes = [ns, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dsb_node_append_rows.restype = C.c_int
+    L.dsb_node_append_rows.argtypes = [ns, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.dsb_node_eval.restype = C.c_int
+    L.dsb_node_eval.argtypes = [ns, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                C.c_void_p, C.c_int32, C.c_void_p]
+    L.dsb_node_gather.restype = C.c_int
+    L.dsb_node_gather.argtypes = [ns, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    L.dsb_hermite_eval.restype = C.c_int
+    L.dsb_hermite_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
     for name in ("dsb_erk_stage_begin", "dsb_erk_stage_state"):
         getattr(L, name).restype = C.c_int
         getattr(L, name).argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_int, C.c_void_p]
@@ -201,6 +228,34 @@ def lib():
     L.dsb_symp_stage_commit_events.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dsb_symp_stage_commit.restype = C.c_int
     L.dsb_symp_stage_commit.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_void_p]
+    # collectives and peer buffers (ABI 3)
+    L.dsb_comm_available.restype = C.c_int
+    L.dsb_comm_nccl_version.restype = C.c_int
+    L.dsb_comm_get_unique_id.restype = C.c_int
+    L.dsb_comm_get_unique_id.argtypes = [C.c_void_p]
+    L.dsb_comm_init_rank.restype = C.c_int
+    L.dsb_comm_init_rank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.dsb_comm_from_nccl.restype = C.c_int
+    L.dsb_comm_from_nccl.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]
+    L.dsb_comm_destroy.restype = C.c_int
+    L.dsb_comm_destroy.argtypes = [C.c_void_p]
+    L.dsb_comm_size.restype = C.c_int
+    L.dsb_comm_size.argtypes = [C.c_void_p]
+    L.dsb_comm_rank.restype = C.c_int
+    L.dsb_comm_rank.argtypes = [C.c_void_p]
+    L.dsb_comm_allreduce_counters.restype = C.c_int
+    L.dsb_comm_allreduce_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.dsb_comm_gather.restype = C.c_int
+    L.dsb_comm_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                  C.c_void_p]
+    L.dsb_peer_alloc.restype = C.c_int
+    L.dsb_peer_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_int]
+    L.dsb_peer_free.restype = C.c_int
+    L.dsb_peer_free.argtypes = [C.c_void_p, C.c_int]
+    L.dsb_peer_open.restype = C.c_int
+    L.dsb_peer_open.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]
+    L.dsb_peer_close.restype = C.c_int
+    L.dsb_peer_close.argtypes = [C.c_void_p, C.c_int]
     if L.dsb_abi_version() != ABI_VERSION:
         raise ImportError("libdesolver_b200.so has ABI version %d, expected %d" % (L.dsb_abi_version(), ABI_VERSION))
     _lib = L
@@ -359,3 +414,104 @@ def symp_handle(device_index, rhs_id, dim, drift_count, tableau, strict=False):
     if h is None:
         h = _handle_cache[key] = SympHandle(device_index, rhs_id, dim, drift_count, tableau, strict=strict)
     return h
+
+
+class Comm:
+    """Owns one dsb_comm_handle: an NCCL communicator over the ranks of a sharded ensemble, created from a
+    ncclUniqueId that the host side distributes (include/desolver_b200.h, "collectives").  All calls are enqueued on
+    the given stream; none synchronises."""
+
+    def __init__(self, device_index, nranks, rank, unique_id):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique_id must be %d bytes" % COMM_ID_BYTES)
+        self.device_index, self.nranks, self.rank = int(device_index), int(nranks), int(rank)
+        self._id = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._h = C.c_void_p()
+        check(lib().dsb_comm_init_rank(C.byref(self._h), self.device_index, self.nranks, self.rank, self._id),
+              "dsb_comm_init_rank")
+
+    @staticmethod
+    def available():
+        return bool(lib().dsb_comm_available())
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        check(lib().dsb_comm_get_unique_id(buf), "dsb_comm_get_unique_id")
+        return bytes(buf.raw)
+
+    def allreduce_counters(self, send_ptr, recv_ptr, count, stream_ptr):
+        check(lib().dsb_comm_allreduce_counters(self._h, send_ptr, recv_ptr, int(count), stream_ptr),
+              "dsb_comm_allreduce_counters")
+
+    def gather(self, shard, staging, full, n_global, stream_ptr):
+        """full[r, j * W + w] = shard_w[r, j]: `shard` is this rank's contiguous (rows, n_local) or (n_local,) tensor of
+        4- or 8-byte elements, `full` the (rows, n_global) result, `staging` a byte buffer (see staging_bytes)."""
+        rows = 1 if shard.ndim == 1 else int(shard.shape[0])
+        check(lib().dsb_comm_gather(self._h, shard.data_ptr(), staging.data_ptr(), full.data_ptr(), rows,
+                                    shard.element_size(), int(shard.shape[-1]), int(n_global), stream_ptr), "dsb_comm_gather")
+
+    def staging_bytes(self, rows, elem_bytes, n_global):
+        return self.nranks * rows * ((n_global + self.nranks - 1) // self.nranks) * elem_bytes
+
+    def close(self):
+        if self._h:
+            lib().dsb_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PeerBuffer:
+    """A device allocation that other processes of the box can map (CUDA IPC): the destination of the fused kernel's
+    scatter-store (dsb_erk_run_args.out_*).  The owner calls `PeerBuffer.allocate`, ships `.handle` (64 bytes) to its
+    peers, and they call `PeerBuffer.open(handle)`.  `.tensor(dtype, shape, offset)` views the memory as a torch tensor."""
+
+    def __init__(self, ptr, nbytes, device_index, owner, handle=None):
+        self.ptr, self.nbytes, self.device_index, self.owner, self.handle = ptr, int(nbytes), int(device_index), owner, handle
+
+    @classmethod
+    def allocate(cls, nbytes, device_index):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(IPC_HANDLE_BYTES)
+        check(lib().dsb_peer_alloc(C.byref(ptr), int(nbytes), handle, int(device_index)), "dsb_peer_alloc")
+        return cls(ptr.value, nbytes, device_index, True, bytes(handle.raw))
+
+    @classmethod
+    def open(cls, handle, nbytes, device_index):
+        ptr = C.c_void_p()
+        buf = C.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES)
+        check(lib().dsb_peer_open(C.byref(ptr), buf, int(device_index)), "dsb_peer_open")
+        return cls(ptr.value, nbytes, device_index, False)
+
+    def tensor(self, dtype, shape, offset=0):
+        """torch view of [offset, offset + prod(shape) * itemsize) of the buffer (through __cuda_array_interface__)."""
+        import torch
+        typestr = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = dict(shape=tuple(int(x) for x in shape), typestr=typestr,
+                                          data=(self.ptr + int(offset), False), version=2)
+        t = torch.as_tensor(v, device="cuda:%d" % self.device_index)
+        t._dsb_keepalive = self
+        return t
+
+    def close(self):
+        if self.ptr:
+            if self.owner:
+                lib().dsb_peer_free(C.c_void_p(self.ptr), self.device_index)
+            else:
+                lib().dsb_peer_close(C.c_void_p(self.ptr), self.device_index)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -19,10 +19,6 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-int launch_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim, int32_t cap,
-                      const double *tq, int64_t tq_stride, double *out, cudaStream_t stream);
-int launch_dense_append(double *nodes, int32_t *node_count, int32_t cap, int64_t n, int32_t dim, const double *t,
-                        const double *y, const double *f, const int32_t *flags, int32_t mask, cudaStream_t stream);
 int launch_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, int sm_count, cudaStream_t stream);
 int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream);
 int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
@@ -43,7 +39,7 @@ int dsb_abi_version(void) { return DSB_ABI_VERSION; }
 
 const char *dsb_build_info(void)
 {
-    return "libdesolver_b200 abi=2 arch=sm_100a nvcc=" DSB_STR(__CUDACC_VER_MAJOR__) "." DSB_STR(__CUDACC_VER_MINOR__)
+    return "libdesolver_b200 abi=3 arch=sm_100a nvcc=" DSB_STR(__CUDACC_VER_MAJOR__) "." DSB_STR(__CUDACC_VER_MINOR__)
            " fused_stages={1,2,4,6,7,13,17} rhs={lorenz,van_der_pol,harmonic_oscillator,forced,duffing}";
 }
 
@@ -65,16 +61,16 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
                 set_error("dsb_erk_create: tableau is implicit (a[%d][%d] != 0); only explicit RK is supported", s, j);
                 return DSB_ERR_UNSUPPORTED;
             }
-    DSB_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);                 // the caller's current device is restored on return
+    int sm_count = 0;
+    DSB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     dsb_erk_plan *p = new (std::nothrow) dsb_erk_plan;
     if (!p) { set_error("out of host memory"); return DSB_ERR_BAD_ARGUMENT; }
     p->device = device; p->rhs_id = rhs_id; p->dim = dim; p->stages = stages; p->final_rows = final_rows;
     p->order = order; p->flags = flags;
     p->inter.assign(tableau_intermediate, tableau_intermediate + (size_t)stages * (stages + 1));
     p->fin.assign(tableau_final, tableau_final + (size_t)final_rows * (stages + 1));
-    cudaDeviceProp prop;
-    DSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    p->sm_count = prop.multiProcessorCount;
+    p->sm_count = sm_count;
 
     bool fused = false;
     switch (rhs_id) {
@@ -85,7 +81,8 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     case DSB_RHS_DUFFING: fused = dim == 2 && select_fused_duffing(p); break;
     default: break;
     }
-    if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = p->fused_launch_events_dy = nullptr;
+    if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = p->fused_launch_events_dy =
+        p->fused_launch_scatter = p->fused_launch_dense = nullptr;
 
     double2 host_tab[fm::ATAN_TABLE_SIZE];
     fm::build_atan_table(host_tab);
@@ -114,6 +111,7 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
 int dsb_erk_destroy(dsb_erk_handle h)
 {
     if (!h) return DSB_OK;
+    DeviceGuard guard(h->device);
     if (h->d_atan) cudaFree(h->d_atan);
     if (h->d_tab) cudaFree(h->d_tab);
     if (h->d_factor) cudaFree(h->d_factor);
@@ -135,8 +133,13 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
         set_error("dsb_erk_run: y, t, dt and counters are required");
         return DSB_ERR_BAD_ARGUMENT;
     }
-    if (a->nodes && (!a->node_count || a->node_capacity < 2)) {
-        set_error("dsb_erk_run: dense output needs node_count and node_capacity >= 2");
+    const dsb_node_store &ns = a->store;
+    if (ns.pool && (!ns.cursor || !ns.page_fill || !ns.node_count || ns.width != 32 || ns.page_entries < 32 ||
+                    ns.page_entries % 32 != 0 || ns.capacity < ns.page_entries || ns.capacity % ns.page_entries != 0 ||
+                    ns.dim != h->dim || a->out_y || a->n_events > 0)) {
+        set_error("dsb_erk_run: the node store of a fused run needs cursor, page_fill, node_count, width = 32, page_entries a "
+                  "multiple of 32, capacity a multiple of page_entries, dim = %d, and neither events nor a scatter-store in "
+                  "the same call", h->dim);
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->stride != 0 && a->stride < a->n) {
@@ -144,9 +147,10 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;
+    DeviceGuard guard(h->device);
     if (a->n_events > 0) {
         if (a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
-            a->ev_capacity < 1 || a->nodes) {
+            a->ev_capacity < 1 || a->store.pool) {
             set_error("dsb_erk_run: events need ev_coef, ev_flags, ev_records, ev_count, ev_capacity >= 1, at most %d "
                       "events, and no dense-output store in the same call", DSB_MAX_EVENTS);
             return DSB_ERR_BAD_ARGUMENT;
@@ -157,12 +161,31 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
         }
         return (a->ev_coef_dy ? h->fused_launch_events_dy : h->fused_launch_events)(h, a, (cudaStream_t)stream);
     }
+    if (a->out_y) {
+        if (!a->out_t || !a->out_dt || !a->out_accepted || !a->out_rejected || !a->out_status || !a->fresh || !a->y_init ||
+            a->out_index_mul < 1 || a->out_index_add < 0 || a->out_stride < 1 || a->store.pool) {
+            set_error("dsb_erk_run: the scatter-store needs every out_* pointer, out_stride >= 1, out_index_mul >= 1, "
+                      "out_index_add >= 0, fresh != 0, y_init, and no dense-output store");
+            return DSB_ERR_BAD_ARGUMENT;
+        }
+        if (!h->fused_launch_scatter) {
+            set_error("dsb_erk_run: no scatter-store kernel for rhs_id=%d stages=%d flags=%u (fast flavour, <= 7 stages)",
+                      h->rhs_id, h->stages, h->flags);
+            return DSB_ERR_UNSUPPORTED;
+        }
+        return h->fused_launch_scatter(h, a, (cudaStream_t)stream);
+    }
+    if (a->store.pool) {
+        if (!h->fused_launch_dense) { set_error("dsb_erk_run: no dense-output kernel for this handle"); return DSB_ERR_UNSUPPORTED; }
+        return h->fused_launch_dense(h, a, (cudaStream_t)stream);
+    }
     return h->fused_launch(h, a, (cudaStream_t)stream);
 }
 
 int dsb_erk_run_host(dsb_erk_handle h, const dsb_erk_host_args *a, void *stream)
 {
     if (!h || !a) { set_error("dsb_erk_run_host: null handle or args"); return DSB_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
     return run_host(h, a, (cudaStream_t)stream);
 }
 
@@ -170,21 +193,29 @@ int dsb_erk_run_launches(dsb_erk_handle h) { return (h && h->fused_launch) ? 1 :
 
 int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream)
 {
+    if (!h) { set_error("dsb_erk_stage_begin: null handle"); return DSB_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
     return stage_begin(h, a, first_call, (cudaStream_t)stream);
 }
 
 int dsb_erk_stage_state(dsb_erk_handle h, const dsb_erk_stage_args *a, int stage, void *stream)
 {
+    if (!h) { set_error("dsb_erk_stage_state: null handle"); return DSB_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
     return stage_state(h, a, stage, (cudaStream_t)stream);
 }
 
 int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, void *stream)
 {
+    if (!h) { set_error("dsb_erk_stage_finish: null handle"); return DSB_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
     return stage_finish(h, a, (cudaStream_t)stream);
 }
 
 int dsb_erk_stage_finish_events(dsb_erk_handle h, const dsb_erk_stage_args *a, int phase, const double *f1, void *stream)
 {
+    if (!h) { set_error("dsb_erk_stage_finish_events: null handle"); return DSB_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
     return stage_finish_events(h, a, phase, f1, (cudaStream_t)stream);
 }
 
@@ -197,26 +228,6 @@ int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N,
     DSB_CUDA_CHECK(cudaGetDevice(&dev));
     DSB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     return launch_dgemm(A, B, C, M, N, K, sms, (cudaStream_t)stream);
-}
-
-int dsb_dense_append(double *nodes, int32_t *node_count, int32_t node_capacity, int64_t n, int32_t dim, const double *t,
-                     const double *y, const double *f, const int32_t *flags, int32_t mask, void *stream)
-{
-    if (!nodes || !node_count || !t || !y || !f || dim < 1 || node_capacity < 2 || n < 0) {
-        set_error("dsb_dense_append: bad argument");
-        return DSB_ERR_BAD_ARGUMENT;
-    }
-    return launch_dense_append(nodes, node_count, node_capacity, n, dim, t, y, f, flags, mask, (cudaStream_t)stream);
-}
-
-int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
-                   int32_t node_capacity, const double *tq, int64_t tq_stride, double *out, void *stream)
-{
-    if (!nodes || !node_count || !tq || !out || dim < 1 || node_capacity < 2 || n < 0) {
-        set_error("dsb_dense_eval: bad argument");
-        return DSB_ERR_BAD_ARGUMENT;
-    }
-    return launch_dense_eval(nodes, node_count, n, dim, node_capacity, tq, tq_stride, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -27,6 +27,21 @@ void set_error(const char *fmt, ...);
         }                                                                                 \
     } while (0)
 
+// Makes `device` current for the duration of an entry point and restores the caller's device afterwards: handles are
+// cached per device on the Python side, and a launch on a stream of device 1 while device 0 is current fails with
+// cudaErrorInvalidResourceHandle.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // Arithmetic policy.  STRICT: every + and * rounds separately (numpy's separate ufunc calls;
 // nvcc never contracts the __d*_rn intrinsics).  Fast: plain operators, which nvcc contracts
 // into DFMA (-fmad=true), halving the FP64 issue count.

@@ -199,17 +199,25 @@ static __device__ __noinline__ void flow_done(uint32_t *counter)
 // EV: event detection after every accepted step (dsb_erk_run_args.n_events > 0), see the event block below.
 // (EVK: 0 none, 1 events g(t, y), 2 events that may also depend on dState/dt -- a separate instantiation, because the
 // extra live values cost the plain event kernel 15 %: 6.0 -> 6.9 ms)
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
+// SCATTER: results are stored through the out_* pointers at index idx * out_index_mul + out_index_add instead of
+// y / t / dt / accepted / rejected / status at idx: the sharded ensemble's gather fused into the result store (the
+// destination is the root rank's buffer, mapped through CUDA IPC; remote stores travel over NVLink while the rest
+// of the shard is still integrating).  Needs fresh != 0 and y_init (the launch then reads nothing it writes).
+// DENSE: one node (t, y, f = rhs(t, y)) per accepted step goes to the paged node store (dsb_node_store, node_store.cu):
+// dense output and the per-step history of single systems.  Its own instantiation: the node's right-hand side and the
+// page cursor would otherwise live in the hot loop of the plain kernel.
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
 #ifndef DSB_EV_MAX_BLOCKS
 #define DSB_EV_MAX_BLOCKS 5
 #endif
-__global__ void __launch_bounds__(ERK_THREADS, (EVK ? (erk_min_blocks<Rhs, Tab::S>() > DSB_EV_MAX_BLOCKS ? DSB_EV_MAX_BLOCKS
+__global__ void __launch_bounds__(ERK_THREADS, ((EVK || DENSE) ? (erk_min_blocks<Rhs, Tab::S>() > DSB_EV_MAX_BLOCKS ? DSB_EV_MAX_BLOCKS
                                                                                                          : erk_min_blocks<Rhs, Tab::S>())
                                                    : erk_min_blocks<Rhs, Tab::S>()))
 erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 {
     using A = Ar<STRICT>;
     constexpr bool EV = EVK != 0;
+    static_assert(!(DENSE && (FLOW || SCATTER || EVK != 0)), "the dense-output kernel is device-resident and event-free");
     constexpr int S = Tab::S, D = Rhs::DIM, NP = Rhs::NPARAM;
     constexpr unsigned FULL = 0xffffffffu;
     const Tab tab(P.tab);
@@ -269,6 +277,9 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     double t = 0.0, dt = 0.0, h = 0.0, h0 = 0.0;
     double corr_first = 1.0, x_last = 1.0, x_last_last = 1.0;
     int trial = 0, acc = 0, rej = 0;
+    int nk = 0;                                   // DENSE: nodes this trajectory has recorded so far (ordinal of the next)
+    long long pg_base = -1;                       // DENSE: first entry of the page this warp is filling (-1: none)
+    int pg_used = 0;                              //        entries of it already used (both warp-uniform)
 #pragma unroll
     for (int d = 0; d < D; ++d) { y[d] = 0.0; scale[d] = 0.0; }
 #pragma unroll
@@ -277,13 +288,25 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         for (int d = 0; d < D; ++d) k[s][d] = 0.0;
 
     auto store = [&](int st) {
+        if constexpr (SCATTER) {
+            const long long o = idx * P.a.out_index_mul + P.a.out_index_add;
 #pragma unroll
-        for (int d = 0; d < D; ++d) P.a.y[(long long)d * ld + idx] = y[d];
-        P.a.t[idx] = t;
-        P.a.dt[idx] = dt;
-        if (P.a.accepted) P.a.accepted[idx] = fresh ? acc : P.a.accepted[idx] + acc;
-        if (P.a.rejected) P.a.rejected[idx] = fresh ? rej : P.a.rejected[idx] + rej;
-        if (P.a.status) P.a.status[idx] = st;
+            for (int d = 0; d < D; ++d) P.a.out_y[(long long)d * P.a.out_stride + o] = y[d];
+            P.a.out_t[o] = t;
+            P.a.out_dt[o] = dt;
+            P.a.out_accepted[o] = acc;
+            P.a.out_rejected[o] = rej;
+            P.a.out_status[o] = st;
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) P.a.y[(long long)d * ld + idx] = y[d];
+            P.a.t[idx] = t;
+            P.a.dt[idx] = dt;
+            if (P.a.accepted) P.a.accepted[idx] = fresh ? acc : P.a.accepted[idx] + acc;
+            if (P.a.rejected) P.a.rejected[idx] = fresh ? rej : P.a.rejected[idx] + rej;
+            if (P.a.status) P.a.status[idx] = st;
+        }
+        if constexpr (DENSE) P.a.store.node_count[idx] = nk;
         s_att[threadIdx.x] += (unsigned long long)(acc + rej);
         s_acc[threadIdx.x] += (unsigned long long)acc;
         s_fail[threadIdx.x] += st == (int)DSB_TRAJ_TOL_FAIL;
@@ -311,15 +334,47 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             if (r) atomicAdd(ctr + 5, (unsigned long long)r);
         }
     };
-    auto dense_node = [&](const double (&f)[D]) {
-        int c = P.a.node_count[idx];
-        if (c < P.a.node_capacity) {
-            double *rec = P.a.nodes + ((long long)idx * P.a.node_capacity + c) * (1 + 2 * D);
-            rec[0] = t;
-#pragma unroll
-            for (int d = 0; d < D; ++d) { rec[1 + d] = y[d]; rec[1 + D + d] = f[d]; }
+    // DENSE, warp-collective: the lanes with `want` append the node (idx, nk, t, y, f) to the warp's page of the node
+    // store, packed into consecutive entries -- each field row of a 32-entry group is written as one or two contiguous
+    // segments, whatever trajectories the lanes hold.  A new page costs the warp one atomicAdd per page_entries nodes.
+    auto dense_append = [&](bool want, const double (&f)[D]) {
+        const unsigned m = __ballot_sync(FULL, want);
+        if (!m) return;
+        const dsb_node_store &st = P.a.store;
+        const int cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+        const int room = pg_base >= 0 ? st.page_entries - pg_used : 0;
+        long long e;
+        if (cnt <= room) {
+            e = pg_base + pg_used + rank;
+            pg_used += cnt;
+        } else {
+            unsigned long long nb = 0;
+            if (lane == 0) {
+                if (pg_base >= 0) st.page_fill[pg_base / st.page_entries] = st.page_entries;   // full after this append
+                nb = atomicAdd((unsigned long long *)st.cursor, (unsigned long long)st.page_entries);
+            }
+            nb = __shfl_sync(FULL, nb, 0);
+            const bool ok = (long long)(nb + st.page_entries) <= st.capacity;
+            e = rank < room ? pg_base + pg_used + rank : (ok ? (long long)nb + (rank - room) : -1);
+            pg_base = ok ? (long long)nb : -1;
+            pg_used = ok ? cnt - room : 0;
         }
-        P.a.node_count[idx] = c + 1;
+        if (want) {
+            if (e >= 0) {
+                const long long g = e >> 5;
+                double *rec = st.pool + g * ((2 + 2 * D) * 32) + (e & 31);
+                *reinterpret_cast<int2 *>(rec) = make_int2((int)idx, nk);
+                rec[32] = t;
+#pragma unroll
+                for (int d = 0; d < D; ++d) { rec[(2 + d) * 32] = y[d]; rec[(2 + D + d) * 32] = f[d]; }
+            } else {
+                atomicAdd((unsigned long long *)st.cursor + 1, 1ull);          // pool full: dropped, but counted
+            }
+            nk++;
+        }
+    };
+    auto dense_flush = [&]() {                    // at warp exit: the page in progress keeps its fill level
+        if (DENSE && lane == 0 && pg_base >= 0) P.a.store.page_fill[pg_base / P.a.store.page_entries] = pg_used;
     };
 
     // Start of a step: final-step clamp (differential_system.py:997-1002).  Called when a trajectory is loaded
@@ -409,16 +464,20 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 if (!live && mine < n && P.a.done) atomicAdd(P.a.done + (mine >> P.a.done_shift), 1u);
                 continue;
             }
+            bool want0 = false;                   // DENSE: this lane just loaded a trajectory without nodes
+            double f0[DENSE ? D : 1];
             if (!live && mine < n) {
                 idx = mine;
 #pragma unroll
-                for (int d = 0; d < D; ++d) y[d] = y_src[(long long)d * ld + idx];
+                for (int d = 0; d < D; ++d)   // FLOW: the copy engine writes this buffer while the kernel runs -> bypass L1
+                    y[d] = FLOW ? __ldcg(y_src + (long long)d * ld + idx) : y_src[(long long)d * ld + idx];
                 t = fresh ? P.a.t_init : P.a.t[idx];
                 dt = fresh ? P.a.dt_init : P.a.dt[idx];
 #pragma unroll
                 for (int p = 0; p < NP; ++p) prm[p] = P.a.params[p][idx * P.a.param_stride[p]];
                 Rhs::prepare(prm);
                 acc = 0; rej = 0; trial = 0;
+                if constexpr (DENSE) nk = fresh ? 0 : P.a.store.node_count[idx];
                 int st0 = (P.a.status && !fresh) ? P.a.status[idx] : (int)DSB_TRAJ_DONE;
                 bool go = st0 != (int)DSB_TRAJ_TOL_FAIL && st0 != (int)DSB_TRAJ_EVENT;
                 if (EV) {
@@ -446,10 +505,11 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 if (go) {
                     live = true;
                     start_step();
-                    if (P.a.nodes && P.a.node_count[idx] == 0) {
-                        double f0[D];
-                        eval_rhs<Rhs>(t, y, prm, f0);
-                        dense_node(f0);
+                    if constexpr (DENSE) {
+                        if (nk == 0) {            // node 0 = the initial condition
+                            eval_rhs<Rhs>(t, y, prm, f0);
+                            want0 = true;
+                        }
                     }
                 } else {
                     const bool frozen = st0 == (int)DSB_TRAJ_TOL_FAIL || st0 == (int)DSB_TRAJ_EVENT;
@@ -457,6 +517,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     store(frozen ? st0 : (more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE));
                 }
             }
+            if constexpr (DENSE) dense_append(want0, f0);
         }
         if (!live) {
             // permanently idle lane (queue exhausted): park it on a benign state so that its (discarded)
@@ -468,7 +529,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
         return __any_sync(FULL, live);
     };
 
-    if (!event_path()) { flush_stats(); return; }
+    if (!event_path()) { dense_flush(); flush_stats(); return; }
 
     for (;;) {
         // ------------------------------------------------------------ stages
@@ -619,6 +680,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 
         // ------------------------------------------------------------ accept: commit and start the next step
         unsigned ev_mask = 0;
+        bool node_now = false;                                          // DENSE: this lane accepted a step in this iteration
+        double fnode[DENSE ? D : 1];
         double yprev[D], tprev = t, dtprev = dt;                        // EV: the state before the commit (interpolant,
 #pragma unroll                                                          // roll-back); dead right after the event block
         for (int d = 0; d < D; ++d) yprev[d] = y[d];
@@ -630,10 +693,9 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             acc++;
             trial = 0;
             if (!final_step) dt = new_dt;                                                     // :1070-1071
-            if (P.a.nodes) {
-                double f1[D];
-                eval_rhs<Rhs>(t, y, prm, f1);
-                dense_node(f1);
+            if constexpr (DENSE) {
+                eval_rhs<Rhs>(t, y, prm, fnode);                                              // the reference's final_rhs
+                node_now = true;
             }
             if (EV && !final_leg) {
                 // an event is searched for iff g changes sign over the step (utilities/optimizer.py:252)
@@ -654,6 +716,10 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             done = !((dt != 0.0) && (fabs((EV ? tf_lane : tf) - t) >= DSB_KC(eps32, DSB_EPS32)))   // :996
                    || acc >= step_budget;
             live = !done;
+        }
+        if constexpr (DENSE) {
+            // the node carries the state AFTER the commit, but `t`/`y` of a lane that just finished are still those values
+            dense_append(node_now, fnode);
         }
         // ------------------------------------------------------------ events (EV): locate, record, terminal roll-back
         if (EV) {
@@ -787,23 +853,24 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             if (!event_path()) break;
         }
     }
+    dense_flush();
     flush_stats();
 }
 
 // Host-side launcher, one per instantiation.
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
 int launch_erk_fused(const ErkKernelArgs<Tab::S> &args, int blocks, cudaStream_t stream)
 {
-    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK><<<blocks, ERK_THREADS, 0, stream>>>(args);
+    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE><<<blocks, ERK_THREADS, 0, stream>>>(args);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
 int occupancy_erk_fused(int *blocks_per_sm)
 {
     DSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK>, ERK_THREADS, 0));
+        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE>, ERK_THREADS, 0));
     return DSB_OK;
 }
 

@@ -619,6 +619,18 @@ int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_ca
     return DSB_OK;
 }
 
+// 128-bit accesses (VEC = 2) need every array 16-byte aligned: torch allocations are, but a right-hand side may return
+// a view at an odd 8-byte offset.
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static int pick_vec(const dsb_erk_plan *h, const dsb_erk_stage_args *a)
+{
+    if (a->n % 2 != 0) return 1;
+    bool ok = aligned16(a->y) && aligned16(a->t) && aligned16(a->h) && aligned16(a->dY) && aligned16(a->y_stage) &&
+              aligned16(a->t_stage) && aligned16(a->flags);
+    for (int j = 0; j < h->stages && ok; ++j) ok = !a->K[j] || aligned16(a->K[j]);
+    return ok ? 2 : 1;
+}
+
 int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream)
 {
     int rc = check_args(h, a, "dsb_erk_stage_state");
@@ -637,7 +649,7 @@ int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, c
     const int keep = (fr.fsal && stage == h->stages - 1) ? 1 : 0;
     const bool strict = h->flags & DSB_FLAG_STRICT;
     if (a->n >= 64) {
-        const int vec = (a->n % 2 == 0) ? 2 : 1;
+        const int vec = pick_vec(h, a);
         const unsigned gx = (unsigned)((a->n / vec + 127) / 128);
         dim3 g(gx, rows_grid_y(gx, a->dim, h->sm_count));
         if (vec == 2) {
@@ -672,7 +684,7 @@ static int stage_finish_parts(const dsb_erk_plan *h, const dsb_erk_stage_args *a
     const unsigned g2 = (unsigned)((a->n + 127) / 128);
     const int g3 = grid_for((long long)a->dim * a->n, 256, h->sm_count);
     const bool rows = a->n >= 64;
-    const int vec = (a->n % 2 == 0) ? 2 : 1;
+    const int vec = pick_vec(h, a);
     const unsigned grx = (unsigned)((a->n / vec + 127) / 128);
     dim3 gr(grx, rows_grid_y(grx, a->dim, h->sm_count));
     // few trajectories, large state (e.g. ensemble=False with a big system): parallelise over the state instead

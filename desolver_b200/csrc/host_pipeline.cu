@@ -51,7 +51,7 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
     if (n < 0 || n > 0x7fffffffLL || !r.y || !r.t || !r.dt || !r.counters || !r.accepted || !r.rejected || !r.status ||
         !a->host_y0 || !a->host_y || !a->host_accepted || !a->host_rejected || !a->host_status || !a->flags ||
         !a->stream_up || !a->stream_down || a->chunk_shift < 5 || a->chunk_shift > 30 || !r.fresh || r.y_init ||
-        r.nodes) {
+        r.store.pool) {
         set_error("dsb_erk_run_host: bad argument (device staging buffers with fresh = 1, no y_init, no dense output; "
                   "host buffers, flags and two extra streams are required; 5 <= chunk_shift <= 30)");
         return DSB_ERR_BAD_ARGUMENT;

@@ -27,6 +27,11 @@ struct dsb_erk_plan {
     int (*fused_launch_events)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
     int (*fused_launch_events_dy)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;   // + dState/dt events
     int events_blocks = 0, events_dy_blocks = 0;
+    // same kernel storing its results through the out_* scatter pointers (fast flavour only)
+    int (*fused_launch_scatter)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
+    // same kernel writing one node per accepted step to the paged node store (dense output / step history)
+    int (*fused_launch_dense)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
+    int dense_blocks = 0;
 };
 
 namespace dsb {
@@ -58,7 +63,7 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
 {
     ErkKernelArgs<Tab::S> args;
@@ -66,8 +71,8 @@ int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStrea
     fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
     args.factor_table = p->d_factor;
-    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK>(
-        args, EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks), stream);
+    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE>(
+        args, DENSE ? p->dense_blocks : (EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks)), stream);
 }
 
 // true iff the caller's tableau equals the compile-time one bit for bit
@@ -91,6 +96,7 @@ void bind_fused(dsb_erk_plan *p, int *per_sm)
 {
     p->fused_launch = fused_trampoline<Rhs, Tab, STRICT>;
     if constexpr (!STRICT && Tab::S <= 7) p->fused_launch_flow = fused_trampoline<Rhs, Tab, STRICT, true>;
+    if constexpr (!STRICT && Tab::S <= 7) p->fused_launch_scatter = fused_trampoline<Rhs, Tab, STRICT, false, 0, true>;
     if constexpr (Tab::S <= 7) {
         p->fused_launch_events = fused_trampoline<Rhs, Tab, STRICT, false, 1>;
         p->fused_launch_events_dy = fused_trampoline<Rhs, Tab, STRICT, false, 2>;
@@ -99,6 +105,12 @@ void bind_fused(dsb_erk_plan *p, int *per_sm)
         p->events_blocks = p->sm_count * (ev_per_sm < 1 ? 1 : ev_per_sm);
         occupancy_erk_fused<Rhs, Tab, STRICT, false, 2>(&ev_per_sm);
         p->events_dy_blocks = p->sm_count * (ev_per_sm < 1 ? 1 : ev_per_sm);
+    }
+    {
+        p->fused_launch_dense = fused_trampoline<Rhs, Tab, STRICT, false, 0, false, true>;
+        int d_per_sm = 0;
+        occupancy_erk_fused<Rhs, Tab, STRICT, false, 0, false, true>(&d_per_sm);
+        p->dense_blocks = p->sm_count * (d_per_sm < 1 ? 1 : d_per_sm);
     }
     occupancy_erk_fused<Rhs, Tab, STRICT>(per_sm);
 }

@@ -284,14 +284,14 @@ int dsb_symp_create(dsb_symp_handle *out, int device, int rhs_id, int dim, int d
                   DSB_MAX_STAGES);
         return DSB_ERR_BAD_ARGUMENT;
     }
-    DSB_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);                 // the caller's current device is restored on return
+    int sm_count = 0;
+    DSB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     dsb_symp_plan *p = new dsb_symp_plan;
     p->device = device; p->rhs_id = rhs_id; p->dim = dim; p->drift_count = drift_count; p->flags = flags;
     p->tab.stages = stages;
     for (int s = 0; s < stages; ++s) { p->tab.drift[s] = tableau[3 * s + 1]; p->tab.kick[s] = tableau[3 * s + 2]; }
-    cudaDeviceProp prop;
-    DSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    p->sm_count = prop.multiProcessorCount;
+    p->sm_count = sm_count;
     *out = p;
     return DSB_OK;
 }
@@ -307,6 +307,7 @@ int dsb_symp_run(dsb_symp_handle h, const dsb_symp_run_args *a, void *stream)
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;
+    DeviceGuard guard(h->device);
     int spb = 128 / a->bodies;
     if (spb < 1) spb = 1;
     dim3 block((unsigned)a->bodies, (unsigned)spb);
@@ -332,6 +333,7 @@ int dsb_symp_stage_begin(dsb_symp_handle h, const dsb_symp_stage_args *a, int fi
 {
     int rc = symp_check(h, a, "dsb_symp_stage_begin");
     if (rc != DSB_OK || a->n == 0) return rc;
+    DeviceGuard guard(h->device);
     symp_begin_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a, first_call);
     symp_reset_kernel<<<grid_for((long long)a->dim * a->n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(*a);
     DSB_CUDA_CHECK(cudaGetLastError());
@@ -342,6 +344,7 @@ int dsb_symp_stage_accumulate(dsb_symp_handle h, const dsb_symp_stage_args *a, i
 {
     int rc = symp_check(h, a, "dsb_symp_stage_accumulate");
     if (rc != DSB_OK || a->n == 0) return rc;
+    DeviceGuard guard(h->device);
     if (stage < 0 || stage >= h->tab.stages || !f) { set_error("dsb_symp_stage_accumulate: bad stage or null f"); return DSB_ERR_BAD_ARGUMENT; }
     const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
     if (h->flags & DSB_FLAG_STRICT)
@@ -356,6 +359,7 @@ int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void 
 {
     int rc = symp_check(h, a, "dsb_symp_stage_commit");
     if (rc != DSB_OK || a->n == 0) return rc;
+    DeviceGuard guard(h->device);
     const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
     if (h->flags & DSB_FLAG_STRICT) symp_commit_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     else symp_commit_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
@@ -377,6 +381,7 @@ int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;
+    DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (phase == 0) {
         symp_advance_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, st>>>(*a);

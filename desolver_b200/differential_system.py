@@ -86,47 +86,80 @@ def rhs_prettifier(equ_repr=None, md_repr=None):
 
 
 class DenseOutput(object):
-    """Dense output over the per-trajectory node store (t_k, y_k, f_k) written by the step kernels.
+    """Dense output over the node store (t_k, y_k, f_k) written by the step kernels (`node_store.NodeStore`).
 
-    `sol(t)` evaluates, for every trajectory, the cubic Hermite interpolant of the accepted step
-    that contains `t` -- the lookup and formula of the reference's DenseOutput / CubicHermiteInterp
-    (`differential_system.py:205-227`, `utilities/interpolation.py:41-61`) as one kernel launch.
-    `t` may be a scalar or a tensor of one time per trajectory.
+    `sol(t)` evaluates, for every trajectory, the cubic Hermite interpolant of the accepted step that contains `t` --
+    the lookup and formula of the reference's DenseOutput / CubicHermiteInterp
+    (`differential_system.py:205-227`, `utilities/interpolation.py:41-61`) -- as one kernel launch for ALL query times:
+
+      single system   `sol(0.3)` -> (*dim);  `sol(t_array)` -> t_array.shape + (*dim)   (the reference's shapes)
+      ensemble        `sol(0.3)` -> (*dim, N);  `sol(t)` with t of shape (N,) -> one time per trajectory, (*dim, N);
+                      `sol.grid(times)` with times of shape (T,) -> (T, *dim, N), every trajectory at every time;
+                      `sol(t)` with t of shape (T, N) -> (T, *dim, N)
+    `sol.grad(t)` is the interpolant's time derivative (`utilities/interpolation.py:63-78`), same shapes.
     """
 
     def __init__(self, system):
         self._sys = system
 
     def __len__(self):
-        cnt = self._sys._node_count
-        return 0 if cnt is None else int(cnt.max().item())
+        st = self._sys._node_store
+        return 0 if st is None else int(st.node_count.max().item())
 
     @property
     def node_count(self):
-        return self._sys._node_count
+        st = self._sys._node_store
+        return None if st is None else st.node_count
 
-    def __call__(self, t):
+    @property
+    def t_min(self):
+        return self._sys.t0
+
+    def _store(self):
+        st = self._sys._node_store
+        if st is None or not st.with_f:
+            raise ValueError("No interpolant has been added and time interval is not defined!")
+        return st
+
+    def _eval(self, t, derivative, grid=False):
         torch = _torch()
         s = self._sys
-        if s._nodes is None:
-            raise ValueError("No interpolant has been added and time interval is not defined!")
-        if int(s._node_count.max().item()) > s._node_capacity:
-            raise MemoryError("dense-output node store overflowed (capacity %d nodes per trajectory); "
-                              "construct the system with a larger dense_capacity" % s._node_capacity)
-        tq = torch.as_tensor(t, dtype=torch.float64, device=s.device)
+        st = self._store()
+        tq = torch.as_tensor(t, dtype=torch.float64).to(s.device)
+        n = s.n_traj
+        if not s.ensemble:
+            # reference shapes: scalar -> (*dim), array -> t.shape + (*dim)
+            flat = tq.reshape(-1).contiguous()
+            out = st.evaluate(flat, 0, 1, flat.numel(), derivative)             # (T, D, 1)
+            return out.reshape(tuple(tq.shape) + tuple(s.dim))
+        if grid:
+            flat = tq.reshape(-1).contiguous()
+            out = st.evaluate(flat, 0, 1, flat.numel(), derivative)             # (T, D, N)
+            return out.reshape((flat.numel(),) + tuple(s.dim) + (n,))
         if tq.ndim == 0:
-            tq = tq.reshape(1)
-            stride = 0
-        else:
-            if tq.shape != (s.n_traj,):
-                raise ValueError("expected a scalar or one query time per trajectory, shape (%d,)" % s.n_traj)
+            out = st.evaluate(tq.reshape(1), 0, 0, 1, derivative)
+            return s._user_shape(out[0])
+        if tq.ndim == 1:
+            if tq.shape[0] != n:
+                raise ValueError("expected a scalar, one query time per trajectory (shape (%d,)), or a (T, %d) array; "
+                                 "use sol.grid(times) for a time grid shared by all trajectories" % (n, n))
+            out = st.evaluate(tq.contiguous(), 1, 0, 1, derivative)
+            return s._user_shape(out[0])
+        if tq.ndim == 2 and tq.shape[1] == n:
             tq = tq.contiguous()
-            stride = 1
-        out = torch.empty((s.numel, s.n_traj), dtype=torch.float64, device=s.device)
-        cb.check(cb.lib().dsb_dense_eval(s._nodes.data_ptr(), s._node_count.data_ptr(), s.n_traj, s.numel,
-                                         s._node_capacity, tq.data_ptr(), stride, out.data_ptr(),
-                                         cb.current_stream_ptr(s.device)), "dsb_dense_eval")
-        return s._user_shape(out)
+            out = st.evaluate(tq, 1, n, tq.shape[0], derivative)
+            return out.reshape((tq.shape[0],) + tuple(s.dim) + (n,))
+        raise ValueError("unsupported query shape %r" % (tuple(tq.shape),))
+
+    def __call__(self, t):
+        return self._eval(t, False)
+
+    def grad(self, t):
+        return self._eval(t, True)
+
+    def grid(self, times, derivative=False):
+        """Every trajectory at every time of `times` (T,): (T, *dim, N) -- ONE launch of the T x N evaluation kernel."""
+        return self._eval(times, derivative, grid=True)
 
 
 def _state_property(name):
@@ -158,7 +191,7 @@ class OdeSystem(object):
 
     def __init__(self, equ_rhs, y0, t=(0, 1), dense_output=False, dt=1.0, rtol=None, atol=None, constants=dict(),
                  ensemble=False, device=None, dense_capacity=None, strict=False, host_io=False, host_chunks=16,
-                 host_out=None):
+                 host_out=None, history=None):
         torch = _torch()
         if len(t) != 2:
             raise ValueError("Two time bounds are required, only {} were given.".format(len(t)))
@@ -204,7 +237,18 @@ class OdeSystem(object):
         self.__tf = float(t[1])
         self.__dt0 = float(dt)
         self.__dense_output = bool(dense_output)
-        self._node_capacity = int(dense_capacity) if dense_capacity is not None else 1024
+        # history="steps": `a.t`, `a.y`, `len(a)`, `a[i]` hold EVERY accepted step like the reference's
+        # (differential_system.py:1015-1018, 1163-1196) -- the default for a single system; history="calls": one row
+        # per integrate() call (row 0 = y0) -- the default for an ensemble, whose per-step history is ragged (use
+        # dense_output=True and `a.sol` / `a.steps(i)` there)
+        history = history or ("calls" if ensemble else "steps")
+        if history not in ("steps", "calls"):
+            raise ValueError("history must be 'steps' or 'calls'")
+        if history == "steps" and ensemble:
+            raise ValueError("history='steps' is the single-system history; an ensemble's per-step history is ragged: "
+                             "use dense_output=True and a.sol(t) / a.steps(i)")
+        self._record_steps = history == "steps" and not host_io
+        self._dense_capacity = int(dense_capacity) if dense_capacity is not None else None
         self.__method = integrators.RK45CKSolver
         self.__int_status = 0
         self.__events = []
@@ -219,6 +263,12 @@ class OdeSystem(object):
         self.callback_every = 1
         self.event_capacity = 64     # event records kept per trajectory (device event detection)
         self._event_log = None
+        # lazy_status=True: integrate() on the fused path returns as soon as the launch is enqueued -- no read-back of
+        # the kernel's counters, hence no host synchronisation; tolerance failures are raised (and `stats`,
+        # `success`, `integration_status` resolved) when one of them is first consulted
+        self.lazy_status = False
+        self._pending = False
+        self._scatter_store = None   # set by distributed.ShardedEnsemble(scatter_store=True)
 
         if self.host_io:
             self._init_host_io(y0, host_out)
@@ -328,12 +378,14 @@ class OdeSystem(object):
             self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
         self._pristine = True
         self._stats = None
+        self._pending = False
         self._event_log = None
         self._hist_alias = False
         self._hist_y = [self._y0]                         # row 0 = initial condition (never written to)
         self._hist_t = [self.__t0]                        # scalars stand for "every trajectory at this time"
-        self._nodes = None
-        self._node_count = None
+        self._node_store = None
+        self._steps_cache = None
+        self._rows_used = 0
 
     def _materialize(self):
         if self.__dict__.get("_pristine"):
@@ -360,9 +412,11 @@ class OdeSystem(object):
         return row
 
     def _fix_dt_dir(self, t1, t0):
+        # in place: the stage-level kernels keep raw pointers to the dt buffer for the whole of integrate()
         torch = _torch()
-        flip = torch.sign(self._dt) != float(np.sign(t1 - t0))
-        self._dt = torch.where(flip, -self._dt, self._dt)
+        dt = self._dt
+        flip = torch.sign(dt) != float(np.sign(t1 - t0))
+        dt.copy_(torch.where(flip, -dt, dt))
 
     # ------------------------------------------------------------------ properties
     @property
@@ -371,7 +425,37 @@ class OdeSystem(object):
 
     @property
     def success(self):
+        self._resolve_pending()
         return self.__int_status == 1 or self.__int_status == 2
+
+    def _pending_counters(self):
+        """Device int64[4] = the fused kernel's [attempts, accepted, failed, unfinished] of the last lazy integrate()
+        call (None if there is none): what a sharded run all-reduces without a host round trip."""
+        return self._counters[2:6] if self._pending else None
+
+    def _resolve_pending(self):
+        """lazy_status: read the counters of the last launch now (one 64-byte device-to-host copy = the first host
+        synchronisation since integrate() was called) and settle `stats` / `integration_status`."""
+        if not self.__dict__.get("_pending"):
+            return
+        self._pending = False
+        st = self._fused_stats()
+        prev = self._stats or dict(attempts=0, accepted=0)
+        self._stats = dict(attempts=prev["attempts"] + st[0], accepted=prev["accepted"] + st[1], failed=st[2], running=st[3])
+        if st[2]:
+            new_e = etypes.FailedIntegration("Failed to integrate system")
+            new_e.__cause__ = etypes.FailedToMeetTolerances(
+                "Failed to integrate {} of {} trajectories to the tolerances required: rtol={}, atol={}".format(
+                    st[2], self.n_traj, self.integrator.rtol, self.integrator.atol))
+            self.__int_status = new_e
+        else:
+            self.__int_status = 1
+
+    def check(self):
+        """Raises the `FailedIntegration` a lazy integrate() call could not raise itself (lazy_status=True)."""
+        self._resolve_pending()
+        if isinstance(self.__int_status, etypes.FailedIntegration):
+            raise self.__int_status
 
     @property
     def events(self):
@@ -382,15 +466,42 @@ class OdeSystem(object):
             return self.__events
         return self._event_log if self.ensemble else self._event_log.for_trajectory(0)
 
+    def _step_history(self):
+        """(t[steps + 1], y[steps + 1, *dim]) of a single system: every accepted step, row 0 = the initial condition --
+        gathered from the node store by one kernel (dsb_node_gather) and cached until the next integrate() call."""
+        torch = _torch()
+        if self._steps_cache is None:
+            st = self._node_store
+            if st is None or int(st.node_count[0].item()) == 0:
+                self._materialize()
+                self._steps_cache = (self._raw_t.reshape(1).clone(), self._raw_y.reshape((1,) + tuple(self.dim)).clone())
+            else:
+                t_rows, y_rows = st.gather(0)
+                self._steps_cache = (t_rows, y_rows.reshape((t_rows.shape[0],) + tuple(self.dim)))
+        return self._steps_cache
+
+    def steps(self, trajectory=0):
+        """(t, y) of every accepted step of ONE trajectory (row 0 = its initial condition): the reference's `a.t`,
+        `a.y` for that trajectory.  Needs the node store (dense_output=True, or a single system)."""
+        if self._node_store is None:
+            raise ValueError("no step history: construct the system with dense_output=True (ensembles) and integrate first")
+        t_rows, y_rows = self._node_store.gather(int(trajectory))
+        return t_rows, y_rows.reshape((t_rows.shape[0],) + tuple(self.dim))
+
     @property
     def y(self):
-        """History of states: one row per integrate() call (row 0 = y0), shape (rows, *dim[, N])."""
+        """History of states.  Single system: one row per accepted step like the reference (`:1015`), shape
+        (steps + 1, *dim).  Ensemble (or history="calls"): one row per integrate() call (row 0 = y0), (rows, *dim[, N])."""
         torch = _torch()
+        if self._record_steps:
+            return self._step_history()[1]
         return torch.stack([self._user_shape(r) for r in self._hist_y])
 
     @property
     def t(self):
         torch = _torch()
+        if self._record_steps:
+            return self._step_history()[0]
         return torch.stack([self._user_time(self._hist_time(r)) for r in self._hist_t])
 
     @property
@@ -418,6 +529,7 @@ class OdeSystem(object):
         (no reduction launches); otherwise from the per-trajectory tensors."""
         if self.__dict__.get("_pristine"):
             return dict(attempts=0, accepted=0, failed=0, running=0)
+        self._resolve_pending()
         if self._stats is not None:
             return dict(self._stats)
         acc = int(self.accepted.sum().item())
@@ -462,8 +574,13 @@ class OdeSystem(object):
 
     @dt.setter
     def dt(self, new_dt):
+        # written IN PLACE: a callback that assigns `ode_sys.dt` (e.g. solve_ivp's max_step / min_step clamp,
+        # reference :1229-1232) must reach kernels that hold a raw pointer to this buffer
         torch = _torch()
-        self._dt = torch.as_tensor(new_dt, dtype=torch.float64, device=self.device).expand(self.n_traj).clone()
+        new_dt = torch.as_tensor(new_dt, dtype=torch.float64, device=self._dt.device)
+        if new_dt.ndim > 1 or (new_dt.ndim == 1 and new_dt.shape[0] not in (1, self.n_traj)):
+            raise ValueError("dt must be a scalar or have shape (%d,)" % self.n_traj)
+        self._dt.copy_(new_dt.reshape(-1).expand(self.n_traj) if new_dt.ndim else new_dt.expand(self.n_traj))
         self._fix_dt_dir(self.__tf, self.__t0)
 
     @property
@@ -512,12 +629,17 @@ class OdeSystem(object):
         elif isinstance(new_method, type) and issubclass(new_method, integrators.IntegratorTemplate):
             self.__method = new_method
         else:
+            if isinstance(new_method, str) and (new_method in integrators.REFERENCE_ONLY_METHODS or "Richardson" in new_method):
+                raise NotImplementedError(
+                    "{!r} is an implicit scheme of the reference; desolver_b200 replaces the explicit Runge-Kutta and "
+                    "symplectic hot path only (implicit_methods() is empty) -- use desolver itself for it".format(new_method))
             raise ValueError("The method you selected does not exist in the list of available methods, "
                              "call desolver_b200.available_methods() to see what these are")
         self.initialise_integrator(preserve_states=preserve_states)
 
     @property
     def integration_status(self):
+        self._resolve_pending()
         if self.__int_status == 0:
             return "Integration has not been run."
         if isinstance(self.__int_status, KeyboardInterrupt):
@@ -582,12 +704,44 @@ class OdeSystem(object):
                 raise ValueError("constant %r must be a scalar or have shape (%d,)" % (name, self.n_traj))
         return tensors, strides
 
-    def _ensure_dense_store(self):
+    @property
+    def _want_nodes(self):
+        return self.__dense_output or self._record_steps
+
+    def _ensure_node_store(self, kind, need=0, chunked=False):
+        """The node store of this system (dense output and/or single-system step history), created on first use.
+        kind "fused": written by the fused kernel (32-entry groups, pages claimed per warp); kind "rows": written by
+        dsb_node_append_rows between stage kernels (one row-group of all n trajectories per attempt).  `need` = entries
+        (fused) / row-groups (rows) that must still be free."""
         torch = _torch()
-        if self.__dense_output and self._nodes is None:
-            rec = 1 + 2 * self.numel
-            self._nodes = torch.empty((self.n_traj, self._node_capacity, rec), dtype=torch.float64, device=self.device)
-            self._node_count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
+        from .node_store import NodeStore
+        if not self._want_nodes:
+            return None
+        n, st = self.n_traj, self._node_store
+        if st is not None and st.kind != kind:
+            raise NotImplementedError("this system's node store was started by the %s kernels; reset() before switching "
+                                      "between the fused and the stage-level path" % ("fused" if kind == "rows" else "stage-level"))
+        if st is None:
+            if kind == "fused":
+                page = 32 if (chunked or n <= 4096) else 256
+                per_traj = self._dense_capacity if self._dense_capacity is not None else (5001 if n == 1 else 288)
+                want = n * per_traj + min(4736, (n + 31) // 32) * page
+                free = torch.cuda.mem_get_info(self.device)[0]
+                cap = min(want, int(0.6 * free) // (8 * (2 + 2 * self.numel)))
+                cap = max(cap, int(need), 2 * page)
+                st = NodeStore(self.device, self.numel, n, "fused", cap, page_entries=page, with_f=True)
+            else:
+                rows = self._dense_capacity if self._dense_capacity is not None else 64
+                st = NodeStore(self.device, self.numel, n, "rows", max(rows, int(need), 2) * n, with_f=self.__dense_output)
+            self._node_store = st
+        if kind == "rows" and need:
+            if (self._rows_used + need) * n > st.capacity:
+                st.grow(max(2 * st.capacity, (self._rows_used + need) * n))
+        elif kind == "fused" and need:
+            claimed = st.usage()[0]
+            if claimed + need > st.capacity:
+                st.grow(claimed + need)
+        return st
 
     def _event_tensors(self, events):
         """Device-side description of the events (dsb_erk_run_args.ev_*): coefficient rows, flag words, record store."""
@@ -599,20 +753,67 @@ class OdeSystem(object):
         if any(ev.requires_dstate for ev in events):          # weights on dState/dt (stage-level kernels only)
             self._event_coef_dy = torch.as_tensor(np.stack([ev.dy_coefficients(self.numel) for ev in events]),
                                                   dtype=torch.float64).to(self.device)
-        if self._event_log is None or self._event_log.compiled != list(events):
+        # the log accumulates over integrate() calls like the reference's `self.__events` (:1043-1048); it is only
+        # re-created when the SET of events changes -- compared by value (coefficients, flags), because a plain
+        # callable is converted to a new HyperplaneEvent object on every call
+        signature = tuple((tuple(ev.coefficients(self.numel).tolist()), tuple(ev.dy_coefficients(self.numel).tolist()),
+                           int(ev.flags)) for ev in events)
+        if self._event_log is None or self._event_log.compiled != signature:
             records = torch.zeros((self.n_traj, int(self.event_capacity), self.numel + 2), dtype=torch.float64, device=self.device)
             count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
             self._event_log = EventLog(events, records, count, self.dim)
-            self._event_log.compiled = list(events)
+            self._event_log.compiled = signature
         return coef, flags
 
     def _run_fused(self, tf, plugin, max_steps, first_call, events=None):
+        """One dsb_erk_run launch.  With a node store (dense output / step history) the pool is sized before the launch:
+        exactly for a chunked call (a trajectory records at most max_steps + 1 nodes), by estimate for a one-shot call --
+        and if the estimate was too small, the kernel has still COUNTED every node, so the state is put back, the pool
+        grown to the size that is now known, and the (bitwise reproducible) launch repeated."""
+        torch = _torch()
+        store = None
+        if self._want_nodes and not events:
+            n = self.n_traj
+            chunked = int(max_steps) < self._step_cap
+            store = self._ensure_node_store("fused", chunked=chunked)
+            slack = min(4736, (n + 31) // 32) * store.page_entries         # one page in progress per warp
+            if chunked:
+                store = self._ensure_node_store("fused", need=n * (int(max_steps) + 1) + slack)
+        if store is None or int(max_steps) < self._step_cap:
+            self._launch_fused(tf, plugin, max_steps, first_call, events, store)
+            if store is not None:
+                self._steps_cache = None
+            return
+        pristine = bool(self._pristine and first_call)
+        snap_store = store.snapshot()
+        snap_state = None if pristine else tuple(x.clone() for x in (self._raw_y, self._raw_t, self._raw_dt, self._raw_accepted,
+                                                                     self._raw_rejected, self._raw_status))
+        nodes_before = int(snap_store[1].sum().item())
+        for attempt in range(3):
+            self._launch_fused(tf, plugin, max_steps, first_call, events, store)
+            claimed, dropped = store.usage()
+            if not dropped:
+                break
+            wanted = int(store.node_count.sum().item()) - nodes_before           # nodes this call records
+            store.restore(snap_store)
+            if pristine:
+                self._pristine = True
+            else:
+                for dst, src in zip((self._raw_y, self._raw_t, self._raw_dt, self._raw_accepted, self._raw_rejected,
+                                     self._raw_status), snap_state):
+                    dst.copy_(src)
+            store.grow(int(snap_store[0][0].item()) + wanted + wanted // 64 + slack)
+        else:
+            raise MemoryError("dense-output node store could not be sized")
+        self._steps_cache = None
+
+    def _launch_fused(self, tf, plugin, max_steps, first_call, events, store):
         integ = self.integrator
         pid, names, defaults = plugin
         handle = cb.erk_handle(self.device.index or 0, pid, self.numel, integ.tableau_intermediate,
                                integ.tableau_final, integ.order, strict=self.strict)
         params, strides = self._param_tensors(names, defaults)
-        self._ensure_dense_store()
+        self._resolve_pending()                   # a continued integration accumulates the previous call's totals
         self._counters.zero_()
         a = cb.ErkRunArgs()
         a.n = self.n_traj
@@ -622,6 +823,15 @@ class OdeSystem(object):
             self._pristine = False
             a.fresh, a.t_init, a.dt_init = 1, self.__t0, self._initial_dt()
             a.y_init = self._y0.data_ptr()
+            sc = self._scatter_store
+            if sc is not None and not events and store is None and int(max_steps) >= self._step_cap:
+                # sharded ensemble: results go straight to slot i * W + rank of the root's gather buffer (peer memory);
+                # the local y / t / dt / counter arrays are NOT written by this launch
+                a.out_y, a.out_t, a.out_dt = sc["y"], sc["t"], sc["dt"]
+                a.out_accepted, a.out_rejected, a.out_status = sc["accepted"], sc["rejected"], sc["status"]
+                a.out_stride, a.out_index_mul, a.out_index_add = sc["stride"], sc["index_mul"], sc["index_add"]
+        elif self._scatter_store is not None:
+            raise RuntimeError("scatter_store systems integrate once per reset() (the local state is not kept)")
         a.y, a.t, a.dt = self._raw_y.data_ptr(), self._raw_t.data_ptr(), self._raw_dt.data_ptr()
         for i, (p, s) in enumerate(zip(params, strides)):
             a.params[i] = p.data_ptr()
@@ -631,8 +841,9 @@ class OdeSystem(object):
                                             self._raw_status.data_ptr())
         a.max_steps = int(max_steps)
         a.first_call = 1 if first_call else 0
-        if self._nodes is not None:
-            a.nodes, a.node_count, a.node_capacity = self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity
+        if store is not None:
+            a.store = store.struct()
+            store.invalidate()
         a.counters = self._counters.data_ptr()
         if events:
             coef, flags = self._event_tensors(events)
@@ -772,8 +983,8 @@ class OdeSystem(object):
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         stream = cb.current_stream_ptr(dev)
-        self._ensure_dense_store()
-        dense = self._nodes is not None
+        store = self._ensure_node_store("rows", need=2) if self._want_nodes else None
+        dense = store is not None
         full = dict(y=self._y, t=self._t, dt=self._dt, accepted=self.accepted, rejected=self.rejected, status=self.status)
         persistent = ("h", "h0", "trial", "flags", "scale", "hist")     # per-trajectory state that outlives an attempt
 
@@ -825,19 +1036,24 @@ class OdeSystem(object):
         t_committed = self._user_time(self._t)
 
         def record_nodes(flags_ptr):
-            """node (t, y, f = rhs(t, y)) for the trajectories flagged as just accepted (all if flags_ptr is None)"""
-            f = self.equ_rhs(t_committed, y_committed, **self.__consts).to(torch.float64).reshape(D, n)
-            f = f if f.is_contiguous() else f.contiguous()
-            cb.check(cb.lib().dsb_dense_append(self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity,
-                                               n, D, self._t.data_ptr(), self._y.data_ptr(), f.data_ptr(), flags_ptr, 4,
-                                               cb.current_stream_ptr(dev)), "dsb_dense_append")
-            self._launches += 1
+            """node (t, y[, f = rhs(t, y)]) for the trajectories flagged as just accepted (all if flags_ptr is None); f only
+            with dense output -- the step history of a single system needs (t, y) alone and costs no evaluation"""
+            f = None
+            if store.with_f:
+                f = self.equ_rhs(t_committed, y_committed, **self.__consts).to(torch.float64).reshape(D, n)
+                f = f if f.is_contiguous() else f.contiguous()
+                keep_node_f[0] = f
+            store.append_rows(self._t, self._y, f, flags_ptr, 4)
+            self._rows_used += 1
+            self._launches += 2
+
+        keep_node_f = [None]
 
         def scatter_back():
             for k, v in work.items():
                 full[k].index_copy_(full[k].ndim - 1, index, v)
 
-        if dense and int(self._node_count.max().item()) == 0:
+        if dense and int(store.node_count.max().item()) == 0:
             record_nodes(None)                                   # node 0 = initial condition
         first, attempts = True, 0
         # heavy attempts (large state x ensemble): one host look per attempt costs nothing next to the
@@ -881,17 +1097,25 @@ class OdeSystem(object):
                 return None
             try:
                 g = torch.cuda.CUDAGraph()
-                nfev0 = self.equ_rhs.nfev
+                nfev0, rows0 = self.equ_rhs.nfev, self._rows_used
                 with torch.cuda.graph(g):
                     one_attempt(False)
                 self.equ_rhs.nfev = nfev0            # the capture pass recorded the calls, it did not execute them
+                self._rows_used = rows0
                 return g
             except Exception:
                 torch.cuda.synchronize(dev)
                 return None
 
-        graph, rhs_calls_per_attempt, rewarm = None, S + (1 if dense else 0) + (1 if events else 0), False
+        graph, rewarm = None, False
+        rhs_calls_per_attempt = S + (1 if dense and store.with_f else 0) + (1 if events else 0)
         while True:
+            if dense and (self._rows_used + 2) * n > store.capacity:
+                # the host knows an upper bound of the row-groups in use (one per attempt) without asking the device;
+                # a grown pool has a new address, so the captured attempt is rebuilt
+                store.grow(max(2 * store.capacity, (self._rows_used + 2) * n))
+                if not first:
+                    graph, rewarm = None, True
             if first:
                 one_attempt(True)                    # eager: integrate()-entry logic, allocator warm-up
                 first = False
@@ -905,6 +1129,9 @@ class OdeSystem(object):
             elif graph is not None:
                 graph.replay()
                 self.equ_rhs.nfev += rhs_calls_per_attempt
+                if dense:
+                    self._rows_used += 1
+                    store.invalidate()
             else:
                 one_attempt(False)
             self._launches += handle.stage_launches if graph is None else 1
@@ -936,6 +1163,7 @@ class OdeSystem(object):
                 break
         if index is not None:
             scatter_back()
+        self._steps_cache = None
 
     def _run_symplectic(self, tf, callbacks, bar, events=None):
         """Explicit symplectic splitting (fixed dt).  Fused kernel for the tagged N-body right-hand side,
@@ -948,7 +1176,7 @@ class OdeSystem(object):
         # drift (position) variables = rows [0, dim0 // 2) of axis 0, kick = the rest (reference integrator_types.py:359-362)
         drift_count = (self.dim[0] // 2) * (D // self.dim[0]) if len(self.dim) else 0
         fused = (self.use_fused and getattr(rhs, "device_plugin", None) == "nbody" and len(self.dim) == 3
-                 and self.dim[0] == 2 and self.dim[2] == 3 and not self.__dense_output and not events)
+                 and self.dim[0] == 2 and self.dim[2] == 3 and not self._want_nodes and not events)
         if fused:
             nb = self.dim[1]
             handle = cb.symp_handle(dev.index or 0, rhs.plugin_id, D, drift_count, integ.tableau_intermediate, strict=self.strict)
@@ -1009,25 +1237,26 @@ class OdeSystem(object):
                 a.ev_coef_dy = self._event_coef_dy.data_ptr()
             self._keepalive = (coef, flags, ev_state, tf_per, scratch)   # referenced by raw pointer until the run has finished
 
-        self._ensure_dense_store()
-        dense = self._nodes is not None
+        store = self._ensure_node_store("rows", need=2) if self._want_nodes else None
+        dense = store is not None
         y_committed, t_committed = self._user_shape(self._y), self._user_time(self._t)
 
         def record_nodes(flags_ptr):
-            """Dense-output node (t, y, rhs(t, y)) of the systems that just stepped (all if flags_ptr is None).  The
+            """Node (t, y[, rhs(t, y)]) of the systems that just stepped (all if flags_ptr is None).  The
             reference's symplectic integrator never refreshes `final_rhs` after the first step
             (integrators/integrator_types.py:385-386), so its later interpolants carry a stale end slope; the nodes
             here hold the slope at their own time."""
-            f = self.equ_rhs(t_committed, y_committed, **self.__consts).to(torch.float64).reshape(D, n)
-            f = f if f.is_contiguous() else f.contiguous()
-            cb.check(cb.lib().dsb_dense_append(self._nodes.data_ptr(), self._node_count.data_ptr(), self._node_capacity,
-                                               n, D, self._t.data_ptr(), self._y.data_ptr(), f.data_ptr(), flags_ptr, 4,
-                                               cb.current_stream_ptr(dev)), "dsb_dense_append")
-            keep_f[0] = f
-            self._launches += 1
+            f = None
+            if store.with_f:
+                f = self.equ_rhs(t_committed, y_committed, **self.__consts).to(torch.float64).reshape(D, n)
+                f = f if f.is_contiguous() else f.contiguous()
+                keep_f[0] = f
+            store.append_rows(self._t, self._y, f, flags_ptr, 4)
+            self._rows_used += 1
+            self._launches += 2
 
         keep_f = [None]
-        if dense and int(self._node_count.max().item()) == 0:
+        if dense and int(store.node_count.max().item()) == 0:
             record_nodes(None)                                   # node 0 = initial condition
 
         def one_step(first_call):
@@ -1050,24 +1279,41 @@ class OdeSystem(object):
                 record_nodes(buf["flags"].data_ptr())
 
         keep = [None] * S
-        graph = None
+        graph, regraph = None, False
+
+        def capture_step():
+            if not self.use_graphs or callbacks:             # same CUDA-graph replay as the explicit-RK stage path
+                return None
+            try:
+                g = torch.cuda.CUDAGraph()
+                nfev0, rows0 = self.equ_rhs.nfev, self._rows_used
+                with torch.cuda.graph(g):
+                    one_step(False)
+                self.equ_rhs.nfev, self._rows_used = nfev0, rows0
+                return g
+            except Exception:
+                torch.cuda.synchronize(dev)
+                return None
+
         while True:
+            if dense and (self._rows_used + 2) * n > store.capacity:
+                store.grow(max(2 * store.capacity, (self._rows_used + 2) * n))     # new pool address: rebuild the graph
+                if not first:
+                    graph, regraph = None, True
             if first:
                 one_step(True)
                 first = False
-                if self.use_graphs and not callbacks:        # same CUDA-graph replay as the explicit-RK stage path
-                    try:
-                        graph = torch.cuda.CUDAGraph()
-                        nfev0 = self.equ_rhs.nfev
-                        with torch.cuda.graph(graph):
-                            one_step(False)
-                        self.equ_rhs.nfev = nfev0
-                    except Exception:
-                        torch.cuda.synchronize(dev)
-                        graph = None
+                graph = capture_step()
+            elif regraph:
+                one_step(False)
+                regraph = False
+                graph = capture_step()
             elif graph is not None:
                 graph.replay()
-                self.equ_rhs.nfev += S + (1 if dense or events else 0)
+                self.equ_rhs.nfev += S + (1 if (dense and store.with_f) or events else 0)
+                if dense:
+                    self._rows_used += 1
+                    store.invalidate()
             else:
                 one_step(False)
             self._launches += (4 + S) if graph is None else 1
@@ -1081,15 +1327,20 @@ class OdeSystem(object):
                     break
             if steps > self._step_cap:
                 break
+        self._steps_cache = None
 
     def integrate(self, t=None, callback=None, eta=False, events=None):
         """Integrates every trajectory to time `t` (default: `self.tf`), reference `:912-1101`.
 
         The whole loop runs on the device without host synchronisation per step.  `callback`
         forces chunked execution: the kernels return every `self.callback_every` accepted steps per
-        trajectory and `callback(self)` is invoked in between.  `events` are not supported by the
-        ensemble engine and raise.
+        trajectory and `callback(self)` is invoked in between.  `events`: see `desolver_b200.events`.
         """
+        torch = _torch()
+        with torch.cuda.device(self.device):       # launches, streams and temporaries all belong to the system's device
+            return self._integrate(t, callback, eta, events)
+
+    def _integrate(self, t, callback, eta, events):
         torch = _torch()
         user_events = None
         if events is not None:
@@ -1112,14 +1363,17 @@ class OdeSystem(object):
             callbacks = [callback]
         plugin = self._fused_plugin() if self.use_fused else None
         fused_stats = None
+        lazy = False
         try:
             if self.host_io and (plugin is None or self.integrator.symplectic):
                 raise NotImplementedError("host_io=True needs an explicit Runge-Kutta method with a fused kernel")
-            if events and (self.host_io or callbacks or eta or self.__dense_output):
+            if events and (self.host_io or callbacks or eta):
                 raise NotImplementedError("device event detection needs device-resident state and no callbacks / progress "
-                                          "bar / dense output in the same call")
-            if events and plugin is not None and self.integrator.stages > 7:
-                plugin = None            # the event-detecting fused kernels stop at 7 stages: stage-level path
+                                          "bar in the same call")
+            if events and plugin is not None and (self.integrator.stages > 7 or self._want_nodes):
+                # the event-detecting fused kernels stop at 7 stages and write no nodes: a system that records dense
+                # output or its step history next to events runs on the stage-level kernels
+                plugin = None
             if self.integrator.symplectic or plugin is None:
                 self._stats = None
             if self.integrator.symplectic:
@@ -1151,7 +1405,9 @@ class OdeSystem(object):
                 self._run_fused(tf, plugin, self._step_cap, first_call=True, events=events)
                 if events:
                     self._event_log.events = list(user_events)     # StateTuple.event is the caller's own object
-                fused_stats = self._fused_stats()
+                lazy = self.lazy_status and not events
+                if not lazy:
+                    fused_stats = self._fused_stats()
             else:
                 first = True
                 bar = None
@@ -1183,7 +1439,10 @@ class OdeSystem(object):
                 self._hist_alias = True
             # error policy: run everything to completion, then raise like the reference does
             # (:1089-1093 wraps integrator_types.py:220-224) if any trajectory failed
-            if fused_stats is not None:
+            if lazy:
+                self._pending = True              # counters are read (and failures raised) on first use
+                n_fail = 0
+            elif fused_stats is not None:
                 prev = self._stats or dict(attempts=0, accepted=0)
                 self._stats = dict(attempts=prev["attempts"] + fused_stats[0], accepted=prev["accepted"] + fused_stats[1],
                                    failed=fused_stats[2], running=fused_stats[3])
@@ -1207,14 +1466,44 @@ class OdeSystem(object):
             # "Integration terminated upon finding a triggered event." (reference :1055) if a terminal event fired
             terminated = bool(events) and any(ev.is_terminal for ev in events) and \
                 bool((self.status == cb.TRAJ_EVENT).any().item())
-            self.__int_status = 2 if terminated else 1
+            if not lazy:
+                self.__int_status = 2 if terminated else 1
 
     # ------------------------------------------------------------------ container protocol
     def __len__(self):
+        if self._record_steps:
+            return int(self._step_history()[0].shape[0])          # counter + 1, reference :1198-1199
         return len(self._hist_y)
 
     def __getitem__(self, index):
         torch = _torch()
+        if self._record_steps:
+            t_rows, y_rows = self._step_history()
+            rows = int(t_rows.shape[0])
+            if isinstance(index, int):
+                if index == -1:                                  # the live state: no gather needed
+                    self._materialize()
+                    return StateTuple(t=self._user_time(self._raw_t), y=self._user_shape(self._raw_y), event=None)
+                if index >= rows or index < -rows:
+                    raise IndexError("index {} out of bounds for integrations with {} steps".format(index, rows))
+                return StateTuple(t=t_rows[index], y=y_rows[index], event=None)
+            if isinstance(index, slice):
+                # the reference slices by TIME (:1170-1183): start / stop are times, located by bisection
+                t_host = t_rows.cpu().numpy()
+                asc = rows < 2 or t_host[-1] >= t_host[0]
+
+                def locate(tv):
+                    arr = t_host if asc else -t_host
+                    return int(min(max(np.searchsorted(arr, float(tv) if asc else -float(tv), side="right") - 1, 0), rows - 1))
+                lo = locate(index.start) if index.start is not None else 0
+                hi = locate(index.stop) + 1 if index.stop is not None else rows
+                step = index.step if index.step is not None else 1
+                return StateTuple(t=t_rows[lo:hi:step], y=y_rows[lo:hi:step], event=None)
+            if self.__dense_output and self._node_store is not None:
+                return StateTuple(t=index, y=self.sol(index), event=None)
+            # nearest stored step (:1187-1196)
+            k = int(torch.argmin(torch.abs(t_rows - float(index))).item())
+            return StateTuple(t=t_rows[k], y=y_rows[k], event=None)
         if isinstance(index, int):
             if index >= len(self._hist_y) or index < -len(self._hist_y):
                 raise IndexError("index {} out of bounds for integrations with {} steps".format(index, len(self._hist_y)))
@@ -1222,7 +1511,7 @@ class OdeSystem(object):
                               y=self._user_shape(self._hist_y[index]), event=None)
         if isinstance(index, slice):
             return StateTuple(t=self.t[index], y=self.y[index], event=None)
-        if self.__dense_output and self._nodes is not None:
+        if self.__dense_output and self._node_store is not None:
             return StateTuple(t=index, y=self.sol(index), event=None)
         raise KeyError("time indexing needs dense_output=True in the ensemble engine")
 
@@ -1256,9 +1545,16 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
     max_step = options.get("max_step", np.inf)
     min_step = options.get("min_step", 0.0)
     first = min(max(options.get("first_step", 1.0), min_step), max_step)
-    system = OdeSystem(fun, y0, t=t_span, dense_output=dense_output, dt=first, atol=options.get("atol"),
-                       rtol=options.get("rtol"), constants=constants or {}, ensemble=options.get("ensemble", False),
-                       device=options.get("device"), strict=options.get("strict", False))
+    # t_eval_mode="steps" (default): repeated integrate(t) like the reference -- every t_eval[k] is an exact stop of the
+    # integration; "dense": ONE integration over t_span with the node store, then ONE launch of the T x N Hermite
+    # evaluation kernel (scipy's semantics: values at t_eval are interpolated, the steps are those of the free run)
+    mode = options.get("t_eval_mode", "steps")
+    if mode not in ("steps", "dense"):
+        raise ValueError("t_eval_mode must be 'steps' or 'dense'")
+    system = OdeSystem(fun, y0, t=t_span, dense_output=dense_output or (t_eval is not None and mode == "dense"), dt=first,
+                       atol=options.get("atol"), rtol=options.get("rtol"), constants=constants or {},
+                       ensemble=options.get("ensemble", False), device=options.get("device"),
+                       strict=options.get("strict", False), dense_capacity=options.get("dense_capacity"))
     system.method = method
     callbacks = list(options.get("callbacks", []))
     if "max_step" in options or "min_step" in options:
@@ -1274,13 +1570,22 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
         t_eval = np.sort(np.asarray(t_eval, dtype=np.float64))
         if t_eval[0] < min(t_span) or t_eval[-1] > max(t_span):
             raise ValueError(f"Expected `t_eval` to be in the range [{t_span[0]}, {t_span[1]}]")
-        ts, ys = [], []
-        for tq in t_eval:
-            system.integrate(t=float(tq), **kw)
-            ts.append(system[-1].t)
-            ys.append(system[-1].y)
-        t_res = torch.stack(ts, dim=-1)
-        y_res = torch.stack(ys, dim=-1)
+        if mode == "dense":
+            system.integrate(**kw)
+            grid = torch.as_tensor(t_eval, dtype=torch.float64, device=system.device)
+            if system.ensemble:
+                y_res = torch.movedim(system.sol.grid(grid), 0, -1)          # (*dim, N, T)
+            else:
+                y_res = torch.movedim(system.sol(grid), 0, -1)               # (*dim, T)
+            t_res = grid
+        else:
+            ts, ys = [], []
+            for tq in t_eval:
+                system.integrate(t=float(tq), **kw)
+                ts.append(system[-1].t.clone())
+                ys.append(system[-1].y.clone())
+            t_res = torch.stack(ts, dim=-1)
+            y_res = torch.stack(ys, dim=-1)
     # like the reference (:1252-1253) both keys carry `ode_system.events`: the list of StateTuple(t, y, event) for a
     # single system, the EventLog for an ensemble
     t_events = y_events = system.events if events is not None else None

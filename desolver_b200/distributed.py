@@ -1,12 +1,20 @@
-"""Multi-GPU sharding of an ensemble: one process per GPU (`torch.distributed`, NCCL over NVLink).
+"""Multi-GPU sharding of an ensemble: one process per GPU, collectives behind the C ABI (NCCL over NVLink).
 
 The path shards by trajectory and has NO exchange inside a step: trajectory i
 lives on rank `i mod world` (round-robin, so every rank sees the same distribution of step counts when
 parameters are sorted or structured), each rank runs the fused kernel on its shard to completion, and
 collectives carry only
-  * the termination / statistics all-reduce (attempts, accepted, failed trajectories), and
-  * the final state / counter gather.
-Nothing here is specific to CUDA tensors, so the host logic is covered by world_size-2 gloo tests on CPU.
+  * the termination / statistics all-reduce (attempts, accepted, failed, unfinished trajectories), taken
+    straight from the kernel's device counters and enqueued on a side stream behind the kernel -- the host
+    does not look at anything until somebody asks for the statistics, and
+  * the final state / counter gather: either `dsb_comm_gather` (one in-place ncclAllGather + one interleave
+    kernel per tensor), or no collective at all -- `scatter_store=True` lets the fused kernel write every
+    finished trajectory straight into slot `i * W + rank` of the root's buffer over NVLink (CUDA IPC), so
+    the gather overlaps the integration.
+
+`torch.distributed` is the plumbing (rendezvous, broadcasting the ncclUniqueId / IPC handles); CUDA shards use
+`libdesolver_b200.so`'s `dsb_comm_*` entry points, CPU tensors (the world_size-2 gloo tests of the host logic)
+use torch's collectives.
 """
 import torch
 import torch.distributed as dist
@@ -29,31 +37,75 @@ def local_count(n_global, rank, world_size):
     return (n_global - rank + world_size - 1) // world_size
 
 
+_comms = {}
+
+
+def communicator(device, group=None):
+    """The `cuda_backend.Comm` (dsb_comm_handle) of this process for `group`: rank 0 draws a ncclUniqueId, the
+    process group broadcasts it, every rank joins.  Cached per (group, device)."""
+    from .backend import cuda_backend as cb
+    device = torch.device(device)
+    key = (id(group) if group is not None else None, device.index)
+    comm = _comms.get(key)
+    if comm is None:
+        rank, world_size = world(group)
+        box = [cb.Comm.unique_id() if rank == 0 else None]
+        if world_size > 1:
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=group)
+        with torch.cuda.device(device):
+            comm = _comms[key] = cb.Comm(device.index or 0, world_size, rank, box[0])
+    return comm
+
+
+def destroy_communicators():
+    for c in _comms.values():
+        c.close()
+    _comms.clear()
+
+
 def reduce_statistics(accepted, rejected, status, group=None):
     """All-reduce (SUM) of [attempts, accepted, failed, unfinished] over the ranks: the global
     termination test.  Returns a dict of python ints; identical on every rank."""
     stats = torch.stack([
-        (accepted.sum(dtype=torch.float64) + rejected.sum(dtype=torch.float64)),
-        accepted.sum(dtype=torch.float64),
-        (status == 1).sum().to(torch.float64),
-        (status == 2).sum().to(torch.float64),
+        (accepted.sum(dtype=torch.int64) + rejected.sum(dtype=torch.int64)),
+        accepted.sum(dtype=torch.int64),
+        (status == 1).sum(dtype=torch.int64),
+        (status == 2).sum(dtype=torch.int64),
     ])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    _, world_size = world(group)
+    if world_size > 1:
+        if stats.is_cuda:
+            from .backend import cuda_backend as cb
+            comm = communicator(stats.device, group)
+            comm.allreduce_counters(stats.data_ptr(), stats.data_ptr(), 4, cb.current_stream_ptr(stats.device))
+        else:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     s = stats.tolist()
     return dict(attempts=int(s[0]), accepted=int(s[1]), failed=int(s[2]), unfinished=int(s[3]))
 
 
 def gather_ensemble(shard, n_global, group=None):
-    """Inverse of `shard_round_robin`: every rank receives the full (..., n_global) tensor.
-
-    Shards are padded to the common length ceil(n_global / W) for one all_gather_into_tensor, then
-    interleaved back: global[..., r::W] = shard_r."""
+    """Inverse of `shard_round_robin`: every rank receives the full (..., n_global) tensor,
+    global[..., r::W] = shard_r.  CUDA shards of 4- or 8-byte elements go through `dsb_comm_gather` (one in-place
+    ncclAllGather + one interleave kernel); anything else through torch's all_gather."""
     rank, world_size = world(group)
     if world_size == 1:
         return shard
-    n_max = (n_global + world_size - 1) // world_size
     lead = tuple(shard.shape[:-1])
+    if shard.is_cuda and shard.element_size() in (4, 8):
+        from .backend import cuda_backend as cb
+        comm = communicator(shard.device, group)
+        rows = 1
+        for s in lead:
+            rows *= int(s)
+        flat = shard.contiguous().reshape(rows, shard.shape[-1])
+        staging = torch.empty(comm.staging_bytes(rows, flat.element_size(), n_global), dtype=torch.uint8, device=shard.device)
+        full = torch.empty((rows, n_global), dtype=shard.dtype, device=shard.device)
+        comm.gather(flat, staging, full, n_global, cb.current_stream_ptr(shard.device))
+        staging.record_stream(torch.cuda.current_stream(shard.device))
+        return full.reshape(lead + (n_global,))
+    n_max = (n_global + world_size - 1) // world_size
     padded = torch.zeros(lead + (n_max,), dtype=shard.dtype, device=shard.device)
     padded[..., :shard.shape[-1]] = shard
     flat = torch.empty(world_size * padded.numel(), dtype=shard.dtype, device=shard.device)
@@ -65,47 +117,166 @@ def gather_ensemble(shard, n_global, group=None):
     return full
 
 
+class ScatterTarget:
+    """Destination of the fused kernel's scatter-store on the ROOT rank: one CUDA-IPC allocation holding
+    y[dim][N], t[N], dt[N], accepted[N], rejected[N], status[N] of the GLOBAL ensemble.  Every rank maps it and passes
+    the mapped pointers to its launches (dsb_erk_run_args.out_*), which write trajectory i of rank r to slot
+    i * W + r -- over NVLink for r != root, while the integration is still running."""
+
+    def __init__(self, dim, n_global, device, group=None, root=0):
+        from .backend import cuda_backend as cb
+        self.rank, self.world_size = world(group)
+        self.dim, self.n_global, self.root = int(dim), int(n_global), int(root)
+        self.device = torch.device(device)
+        n = self.n_global
+        pad = lambda b: (b + 255) // 256 * 256                      # noqa: E731
+        self.offsets, off = {}, 0
+        for name, size in (("y", 8 * self.dim * n), ("t", 8 * n), ("dt", 8 * n), ("accepted", 4 * n), ("rejected", 4 * n),
+                           ("status", 4 * n)):
+            self.offsets[name] = off
+            off += pad(size)
+        self.nbytes = off
+        box = [None]
+        if self.rank == self.root:
+            self.buffer = cb.PeerBuffer.allocate(self.nbytes, self.device.index or 0)
+            box[0] = self.buffer.handle
+        if self.world_size > 1:
+            src = dist.get_global_rank(group, self.root) if group is not None else self.root
+            dist.broadcast_object_list(box, src=src, group=group)
+        if self.rank != self.root:
+            self.buffer = cb.PeerBuffer.open(box[0], self.nbytes, self.device.index or 0)
+
+    def pointer(self, name):
+        return self.buffer.ptr + self.offsets[name]
+
+    def result(self):
+        """Root only: the gathered tensors (views of the peer buffer)."""
+        if self.rank != self.root:
+            return None
+        n, b = self.n_global, self.buffer
+        return dict(y=b.tensor(torch.float64, (self.dim, n), self.offsets["y"]),
+                    t=b.tensor(torch.float64, (n,), self.offsets["t"]),
+                    dt=b.tensor(torch.float64, (n,), self.offsets["dt"]),
+                    accepted=b.tensor(torch.int32, (n,), self.offsets["accepted"]),
+                    rejected=b.tensor(torch.int32, (n,), self.offsets["rejected"]),
+                    status=b.tensor(torch.int32, (n,), self.offsets["status"]))
+
+
 class ShardedEnsemble:
     """Round-robin shard of a global ensemble integrated by this rank's `OdeSystem`.
 
     `make_system(y0_shard, constants_shard)` builds the rank-local system; per-trajectory constants
     (tensors whose last axis has the global ensemble length) are sharded the same way as `y0`.
+
+    `integrate()` enqueues the local integration and, behind it on a side stream, the all-reduce of the kernel's own
+    counters; with `wait=False` nothing synchronises with the host until `.statistics` is read (a loop of
+    reset()/integrate() then runs rank-asynchronously: the ranks meet in the collective on the device, never on the
+    host).  `scatter_store=True` (fused right-hand sides, fresh runs): the kernel stores every finished trajectory
+    straight into the root's gather buffer (see ScatterTarget); `gather()` on the root is then free.
     """
 
-    def __init__(self, make_system, y0_global, constants=None, group=None):
+    def __init__(self, make_system, y0_global, constants=None, group=None, scatter_store=False, root=0):
         self.group = group
         self.rank, self.world_size = world(group)
         self.n_global = int(y0_global.shape[-1])
+        self.root = int(root)
         consts = {}
         for k, v in (constants or {}).items():
             if isinstance(v, torch.Tensor) and v.ndim >= 1 and v.shape[-1] == self.n_global:
                 v = shard_round_robin(v, self.rank, self.world_size)
             consts[k] = v
         self.system = make_system(shard_round_robin(y0_global, self.rank, self.world_size), consts)
-        self.statistics = None
+        self._global = None                  # device tensor [attempts, accepted, failed, unfinished] after the all-reduce
+        self._stats = None
+        self._err = None
+        self._side = None
+        self.scatter = None
+        if scatter_store:
+            s = self.system
+            self.scatter = ScatterTarget(s.numel, self.n_global, s.device, group, self.root)
+            s._scatter_store = dict(index_mul=self.world_size, index_add=self.rank, stride=self.n_global,
+                                    **{k: self.scatter.pointer(k) for k in ("y", "t", "dt", "accepted", "rejected", "status")})
 
-    def integrate(self, t=None):
-        """Local integration to completion, then the global termination all-reduce.  A tolerance failure
-        anywhere raises on EVERY rank (after all ranks finished), like the single-GPU error policy."""
+    # ------------------------------------------------------------------ integration
+    def integrate(self, t=None, wait=True):
+        """Local integration, then the global statistics all-reduce.  A tolerance failure anywhere raises on EVERY
+        rank (when the statistics are read: here with wait=True, else at `.statistics`), like the single-GPU error
+        policy."""
         from . import exception_types as etypes
-        err = None
+        from .backend import cuda_backend as cb
+        s = self.system
+        self._stats, self._err = None, None
+        counters = None
+        lazy_before = getattr(s, "lazy_status", False)
         try:
-            self.system.integrate(t)
-        except etypes.FailedIntegration as e:      # keep going: the collective below must still be entered
-            err = e
-        s = self.system
-        self.statistics = reduce_statistics(s.accepted, s.rejected, s.status, self.group)
-        if err is not None or self.statistics["failed"]:
-            new = etypes.FailedIntegration("Failed to integrate system on %d trajectories" % self.statistics["failed"])
-            new.__cause__ = err.__cause__ if err is not None else etypes.FailedToMeetTolerances("on another rank")
-            raise new
-        return self.statistics
+            s.lazy_status = True                 # no host read-back inside integrate()
+            s.integrate(t)
+            counters = s._pending_counters()     # device int64[4] of this call, or None (stage-level / symplectic path)
+        except etypes.FailedIntegration as e:    # keep going: the collective below must still be entered
+            self._err = e
+        finally:
+            s.lazy_status = lazy_before
+        if counters is None:
+            st = reduce_statistics(s.accepted, s.rejected, s.status, self.group)
+            self._stats = st
+        else:
+            dev = s.device
+            self._global = torch.empty(4, dtype=torch.int64, device=dev)
+            if self.world_size > 1:
+                # side stream: the next launch on the compute stream does not wait for the slowest rank's collective
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=dev)
+                cur = torch.cuda.current_stream(dev)
+                snap = counters.clone()
+                self._side.wait_stream(cur)
+                comm = communicator(dev, self.group)
+                comm.allreduce_counters(snap.data_ptr(), self._global.data_ptr(), 4, C_void(self._side.cuda_stream))
+                snap.record_stream(self._side)
+                self._global.record_stream(self._side)
+            else:
+                self._global.copy_(counters)
+        if wait:
+            return self.statistics
+        return None
 
+    @property
+    def statistics(self):
+        from . import exception_types as etypes
+        if self._stats is None and self._global is not None:
+            if self._side is not None:
+                self._side.synchronize()
+            g = self._global.tolist()
+            self._stats = dict(attempts=int(g[0]), accepted=int(g[1]), failed=int(g[2]), unfinished=int(g[3]))
+        if self._stats is not None and (self._err is not None or self._stats["failed"]):
+            err, self._err = self._err, None
+            new = etypes.FailedIntegration("Failed to integrate system on %d trajectories" % self._stats["failed"])
+            new.__cause__ = err.__cause__ if err is not None else etypes.FailedToMeetTolerances("on another rank")
+            failed, self._stats["failed"] = self._stats["failed"], 0      # raise once; the numbers stay readable
+            self._stats["failed_trajectories"] = failed
+            raise new
+        return self._stats
+
+    # ------------------------------------------------------------------ results
     def gather(self):
-        """Final state (*dim, N), times, counters of the GLOBAL ensemble on every rank."""
+        """Final state (*dim, N), times, counters of the GLOBAL ensemble: on every rank through `dsb_comm_gather`;
+        with `scatter_store=True` on the root only (views of the buffer the kernels wrote, None elsewhere) after a
+        device barrier (the all-reduce already enqueued behind every rank's kernel)."""
         s = self.system
+        if self.scatter is not None:
+            _ = self.statistics                    # every rank's kernel has finished once the all-reduce has
+            if self.world_size > 1:
+                dist.barrier(group=self.group)
+            out = self.scatter.result()
+            if out is not None:
+                out["y"] = out["y"].reshape(tuple(s.dim) + (self.n_global,))
+            return out
         return dict(y=gather_ensemble(s[-1].y, self.n_global, self.group),
                     t=gather_ensemble(s[-1].t, self.n_global, self.group),
                     accepted=gather_ensemble(s.accepted, self.n_global, self.group),
                     rejected=gather_ensemble(s.rejected, self.n_global, self.group),
                     status=gather_ensemble(s.status, self.n_global, self.group))
+
+
+def C_void(ptr):
+    import ctypes
+    return ctypes.c_void_p(ptr)

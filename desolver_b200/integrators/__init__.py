@@ -50,9 +50,35 @@ def explicit_methods():
 
 
 def implicit_methods():
+    """Implicit Runge-Kutta schemes (Gauss-Legendre, Lobatto, Radau, DIRK, Backward Euler ...) are outside the hot path
+    this engine replaces (batched Newton + dense LU per stage: a different algorithmic class, SURVEY.md section 8f item 4);
+    none is registered and `OdeSystem.set_method` names the reference class to use instead."""
     return []
 
 
+# names of the reference's implicit / wrapper schemes, so that asking for one gets a targeted error instead of
+# "method does not exist"
+REFERENCE_ONLY_METHODS = ("GaussLegendre4", "GaussLegendre6", "BackwardEuler", "ImplicitMidpoint", "LobattoIIIA2",
+                          "LobattoIIIA4", "LobattoIIIB2", "LobattoIIIB4", "LobattoIIIC2", "LobattoIIIC4", "CrankNicolson",
+                          "DIRK3LStable", "RadauIA3", "RadauIA5", "RadauIIA3", "RadauIIA5", "RadauIIA19")
+
+
+def register_with_reference(reference_integrators=None):
+    """Seam 1 of SURVEY.md section 8b on the reference's side: the unmodified reference `OdeSystem.set_method` accepts a
+    class only if `issubclass(cls, desolver.integrators.IntegratorTemplate)` (differential_system.py:858-866).  The
+    reference's template is an `abc.ABC`, so registering this package's template as a virtual subclass makes every class
+    here acceptable without touching either code base:
+
+        import desolver, desolver_b200
+        desolver_b200.integrators.register_with_reference(desolver.integrators)
+        a = desolver.OdeSystem(rhs, y0_cuda, ...); a.set_method(desolver_b200.integrators.RK45CKSolver)
+    """
+    if reference_integrators is None:
+        import desolver.integrators as reference_integrators
+    reference_integrators.IntegratorTemplate.register(IntegratorTemplate)
+    return reference_integrators
+
+
 __all__ = ["IntegratorTemplate", "TableauIntegrator", "RungeKuttaIntegrator", "ExplicitSymplecticIntegrator",
-           "available_methods", "explicit_methods", "implicit_methods"] + \
+           "available_methods", "explicit_methods", "implicit_methods", "register_with_reference"] + \
           [c.__name__ for c in __explicit_integration_methods__]

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSB_ABI_VERSION 2
+#define DSB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DSB_API __attribute__((visibility("default")))
@@ -37,7 +37,8 @@ typedef enum {
     DSB_OK = 0,
     DSB_ERR_BAD_ARGUMENT = 1,
     DSB_ERR_CUDA = 2,
-    DSB_ERR_UNSUPPORTED = 3   /* no fused kernel for this (rhs, method, dim) combination */
+    DSB_ERR_UNSUPPORTED = 3,  /* no fused kernel for this (rhs, method, dim) combination */
+    DSB_ERR_NCCL = 4          /* a collective failed (dsb_comm_*)                                */
 } dsb_status;
 
 /* Built-in fused right-hand sides (desolver_b200/rhs_plugins.py tags the Python callables). */
@@ -88,6 +89,29 @@ DSB_API int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim,
                    int final_rows, double order, unsigned flags);
 DSB_API int dsb_erk_destroy(dsb_erk_handle h);
 
+/* Dense output / per-step history: the paged structure-of-arrays node store (csrc/node_store.cu).  A node is
+ * (trajectory, ordinal k, t, y[dim], f[dim] = rhs(t, y)) -- what the reference keeps per accepted step as one
+ * CubicHermiteInterp object (integrators/integrator_types.py:109-119, differential_system.py:1020-1023) and as one row
+ * of `a.t` / `a.y` (differential_system.py:1015-1018).  The pool is a log of entries in groups of `width`; group g
+ * holds 2 + 2*dim rows of `width` doubles: row 0 = header {int32 trajectory (-1: empty), int32 k}, row 1 = t, rows
+ * 2..1+dim = y, rows 2+dim.. = f; entry e is slot e % width of group e / width.  Everything is caller-owned device
+ * memory; cursor and page_fill must be zeroed when the store is created (or recycled). */
+typedef struct {
+    double *pool;              /* NULL = no node store                                          */
+    int64_t capacity;          /* entries the pool holds, a multiple of width (and of page_entries) */
+    int32_t width;             /* 32: written by the fused kernels (any trajectory in any slot);
+                                  n: written by dsb_node_append_rows (slot = trajectory)        */
+    int32_t page_entries;      /* fused kernels: a warp claims this many consecutive entries per atomic
+                                  (multiple of 32, >= 32)                                       */
+    int32_t dim;
+    uint64_t *cursor;          /* [4]: [0] entries claimed so far, [1] nodes dropped because the pool was
+                                  full (their node_count still advances, so the caller learns the size that
+                                  would have sufficed), [2] scratch of dsb_node_append_rows                 */
+    int32_t *page_fill;        /* [capacity / page_entries]: entries written in each claimed page (fused
+                                  writer; NULL for a row-written store)                         */
+    int32_t *node_count;       /* [n] in/out: nodes recorded per trajectory                     */
+} dsb_node_store;
+
 typedef struct {
     int64_t n;                 /* trajectories in this shard                                   */
     double *y;                 /* [dim][n] in/out                                              */
@@ -101,10 +125,8 @@ typedef struct {
     int32_t *status;           /* [n] dsb_traj_status (TOL_FAIL entries are skipped on entry)  */
     int64_t max_steps;         /* accepted-step budget per trajectory for this call, <0 = none */
     int32_t first_call;        /* 1: apply integrate()'s entry logic (:956-957, :971-974)      */
-    /* dense output (NULL = off): per trajectory `node_capacity` records of (t, y[dim], f[dim]) */
-    double *nodes;             /* [n][node_capacity][1 + 2*dim]                                */
-    int32_t *node_count;       /* [n] in/out                                                   */
-    int32_t node_capacity;
+    dsb_node_store store;      /* dense output / step history (store.pool = NULL: off): one node per accepted
+                                  step, plus node 0 = the initial condition of a trajectory that has none yet  */
     uint64_t *counters;        /* device, >= 8 words, zeroed by the caller: [0] work queue; on return
                                   [2] += step attempts of this call, [3] += accepted steps,
                                   [4] += trajectories left in DSB_TRAJ_TOL_FAIL, [5] += in DSB_TRAJ_RUNNING  */
@@ -143,6 +165,17 @@ typedef struct {
     const double *ev_coef_dy;  /* device [n_events][dim] weights on dState/dt (NULL: none): `requires_dstate` events,
                                   g(t, y, dy) = w.y + w_dy.dy + wt t - c with dy the interpolant's derivative
                                   (differential_system.py:92-96, utilities/interpolation.py:63-78)                */
+    /* ---- ABI 3: scatter-store (out_y = NULL: off) ------------------------------------------------------------
+     * The final gather of a sharded ensemble fused into the kernel's result store: the result of trajectory i goes
+     * to index o = i * out_index_mul + out_index_add of the out_* arrays INSTEAD of index i of y, t, dt, accepted,
+     * rejected, status (which are then not touched).  With out_index_mul = W ranks and out_index_add = rank the
+     * round-robin shards land interleaved in one [dim][out_stride] buffer; the pointers may address another GPU's
+     * memory (dsb_peer_open), the stores then travel over NVLink while the shard is still integrating.
+     * Needs fresh != 0 and y_init, no dense output, no events; fast flavour, <= 7 stages. */
+    double *out_y;             /* [dim][out_stride]                                                               */
+    double *out_t, *out_dt;    /* [>= n * out_index_mul]                                                          */
+    int32_t *out_accepted, *out_rejected, *out_status;
+    int64_t out_stride, out_index_mul, out_index_add;
 } dsb_erk_run_args;
 
 DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);
@@ -315,21 +348,79 @@ DSB_API int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage
  * K % 16 == 0 and 16-byte aligned pointers, else DSB_ERR_UNSUPPORTED (the caller then uses a library GEMM). */
 DSB_API int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, void *stream);
 
-/* ---- dense output ------------------------------------------------------------------------
- * Replaces DenseOutput.__call__ / find_interval (differential_system.py:205-227) and
- * CubicHermiteInterp.__call__ (utilities/interpolation.py:41-61) over the node store written
- * by dsb_erk_run: out[d][i] = Hermite interpolant of trajectory i at tq[i*tq_stride]. */
-/* Writer for the stage-level path: append the node (t[i], y[:, i], f[:, i]) for every trajectory i whose
- * flags[i] has `mask` set (flags == NULL: all).  With the flag word of dsb_erk_stage_args and mask = 4 this
- * records exactly the steps the last dsb_erk_stage_finish accepted; f is rhs(t, y) evaluated by the caller
- * (the reference's final_rhs, integrators/integrator_types.py:308, dense_output :109-119). */
-DSB_API int dsb_dense_append(double *nodes, int32_t *node_count, int32_t node_capacity, int64_t n, int32_t dim,
-                             const double *t, const double *y, const double *f, const int32_t *flags, int32_t mask,
-                             void *stream);
+/* ---- dense output / step history over the node store ---------------------------------------
+ * Replace DenseOutput.__call__ / grad / find_interval (differential_system.py:205-246) and CubicHermiteInterp.__call__ /
+ * grad (utilities/interpolation.py:41-78).  After a run the caller builds the index once:
+ *   dsb_node_offsets   offsets[0..n] = exclusive prefix sum of node_count (offsets[n] = total nodes)
+ *   dsb_node_locate    loc[offsets[i] + k] = entry of node k of trajectory i, for the first `claimed_entries`
+ *                      (= cursor[0]) entries of the pool; *bad counts inconsistent headers (must stay 0)
+ * and then evaluates any number of query times per trajectory in one launch. */
+DSB_API int64_t dsb_node_offsets_scratch(int64_t n);        /* int64 words of scratch dsb_node_offsets needs */
+DSB_API int dsb_node_offsets(const int32_t *node_count, int64_t n, int64_t *offsets /* [n + 1] */, int64_t *scratch, void *stream);
+DSB_API int dsb_node_locate(const dsb_node_store *st, int64_t claimed_entries, int64_t n, const int64_t *offsets,
+                            int64_t *loc /* [offsets[n]] */, uint64_t *bad /* device, zeroed */, void *stream);
+/* Writer for the stage-level path (lock-step attempts; store.width == n): claims the next row-group and appends the node
+ * (t[i], y[:, i], f[:, i]) for every trajectory i whose flags[i] has `mask` set (flags == NULL: all).  With the flag word
+ * of dsb_erk_stage_args and mask = 4 this records exactly the steps the last dsb_erk_stage_finish accepted; f is
+ * rhs(t, y) evaluated by the caller (the reference's final_rhs, integrators/integrator_types.py:308); f == NULL records
+ * (t, y) only (step history without dense output). */
+DSB_API int dsb_node_append_rows(const dsb_node_store *st, int64_t n, const double *t, const double *y, const double *f,
+                                 const int32_t *flags, int32_t mask, void *stream);
+/* out[q][d][i] = cubic Hermite interpolant (derivative = 0) or its time derivative (1) of trajectory i at
+ * tq[i * tq_stride_traj + q * tq_stride_query], q < nq: a scalar time is strides (0, 0), one time per trajectory (1, 0),
+ * a shared time grid (0, 1) -- the T x N evaluation behind `sol(t_eval)` / solve_ivp(t_eval=...). */
+DSB_API int dsb_node_eval(const dsb_node_store *st, const int64_t *offsets, const int64_t *loc, int64_t n, const double *tq,
+                          int64_t tq_stride_traj, int64_t tq_stride_query, int32_t nq, double *out, int32_t derivative,
+                          void *stream);
+/* Nodes k0 .. k0 + count - 1 of one trajectory as dense rows: t_out[j], y_out[j][dim] (f_out[j][dim] if not NULL) -- the
+ * reference's per-step history `a.t`, `a.y` of a single system (differential_system.py:1015-1018, 1163-1196). */
+DSB_API int dsb_node_gather(const dsb_node_store *st, const int64_t *offsets, const int64_t *loc, int64_t trajectory,
+                            int64_t k0, int64_t count, double *t_out, double *y_out, double *f_out, void *stream);
+/* One explicit Hermite step (the integrator protocol's dense_output(), integrators/integrator_types.py:109-119):
+ * out[d][i] from p0, p1, m0, m1 [dim][n], t0 / t1 [n * t_stride] (t_stride = 0: shared), tq [n * tq_stride]. */
+DSB_API int dsb_hermite_eval(const double *t0, const double *t1, int64_t t_stride, const double *p0, const double *p1,
+                             const double *m0, const double *m1, int64_t n, int32_t dim, const double *tq, int64_t tq_stride,
+                             double *out, int32_t derivative, void *stream);
 
-DSB_API int dsb_dense_eval(const double *nodes, const int32_t *node_count, int64_t n, int32_t dim,
-                   int32_t node_capacity, const double *tq, int64_t tq_stride,
-                   double *out, void *stream);
+/* ---- collectives of a sharded ensemble (NCCL over NVLink 5 / NVSwitch) -----------------------
+ * The reference has no multi-device path; the ensemble engine shards trajectories round-robin over the GPUs of
+ * one box (trajectory i -> rank i mod W) with NO exchange inside a step.  The only
+ * collectives are the termination / statistics all-reduce over the kernels' own counters
+ * (dsb_erk_run_args.counters[2..5]) and the final gather of states and per-trajectory counters.  Both are issued
+ * on the caller's stream, behind the kernel, with no host synchronisation in between.
+ * NCCL is bound at run time (dlopen of libnccl.so.2): every call returns DSB_ERR_UNSUPPORTED without it.
+ * A communicator is either created here from a ncclUniqueId that the host side broadcasts
+ * (dsb_comm_get_unique_id on rank 0 -> any out-of-band channel -> dsb_comm_init_rank on every rank) or wraps an
+ * existing ncclComm_t (dsb_comm_from_nccl; not destroyed with the handle). */
+typedef struct dsb_comm *dsb_comm_handle;
+#define DSB_COMM_ID_BYTES 128
+#define DSB_IPC_HANDLE_BYTES 64
+
+DSB_API int dsb_comm_available(void);          /* 1: NCCL could be bound                          */
+DSB_API int dsb_comm_nccl_version(void);       /* ncclGetVersion code, 0 if unavailable           */
+DSB_API int dsb_comm_get_unique_id(void *id_out /* DSB_COMM_ID_BYTES, host */);
+DSB_API int dsb_comm_init_rank(dsb_comm_handle *out, int device, int nranks, int rank,
+                               const void *id /* DSB_COMM_ID_BYTES, host */);
+DSB_API int dsb_comm_from_nccl(dsb_comm_handle *out, void *nccl_comm /* ncclComm_t */, int device);
+DSB_API int dsb_comm_destroy(dsb_comm_handle c);
+DSB_API int dsb_comm_size(dsb_comm_handle c);
+DSB_API int dsb_comm_rank(dsb_comm_handle c);
+/* recv[k] = sum over ranks of send[k] (send == recv allowed): the global termination test / ensemble statistics
+ * straight from the device counters of dsb_erk_run -- no read-back in front of the collective. */
+DSB_API int dsb_comm_allreduce_counters(dsb_comm_handle c, const uint64_t *send, uint64_t *recv, int count, void *stream);
+/* Inverse of the round-robin sharding: full[r][j * W + w] = shard_w[r][j] on EVERY rank, for `rows` rows of
+ * 4- or 8-byte elements (y: rows = dim; t, accepted, ...: rows = 1).  One in-place ncclAllGather into `staging`
+ * (>= W * rows * ceil(n_global / W) * elem_bytes bytes, device) followed by one interleave kernel. */
+DSB_API int dsb_comm_gather(dsb_comm_handle c, const void *shard, void *staging, void *full, int rows, int elem_bytes,
+                            int64_t n_local, int64_t n_global, void *stream);
+
+/* Peer-visible device buffers (CUDA IPC) for the scatter-store of dsb_erk_run (out_* fields): the owner allocates
+ * and exports, every other process of the box opens the handle and passes the mapped pointer to its own launches,
+ * whose result stores then travel over NVLink while the integration is still running. */
+DSB_API int dsb_peer_alloc(void **dev_ptr, int64_t bytes, void *ipc_handle_out /* DSB_IPC_HANDLE_BYTES */, int device);
+DSB_API int dsb_peer_free(void *dev_ptr, int device);
+DSB_API int dsb_peer_open(void **dev_ptr, const void *ipc_handle, int device);
+DSB_API int dsb_peer_close(void *dev_ptr, int device);
 
 #ifdef __cplusplus
 }

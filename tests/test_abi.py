@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in syms:
         assert hasattr(lib, name), "missing export %s" % name
     info = cb.lib().dsb_build_info().decode()
-    assert "sm_100a" in info and cb.lib().dsb_abi_version() == cb.ABI_VERSION == 2
+    assert "sm_100a" in info and cb.lib().dsb_abi_version() == cb.ABI_VERSION == 3
 
 
 def test_ctypes_struct_matches_header_layout():

@@ -1,0 +1,382 @@
+"""GPU tests of the round-2 additions: per-step history of single systems, the paged node store (dense output at
+ensemble scale, array-valued `sol(t)`, `sol.grad`, `sol.grid`), `solve_ivp(t_eval=...)`, the remaining fixed-step
+tableaux, the complete integrator protocol (`dense_output()`, custom `adaptation_fn`), lazy status, and the fixes of
+the round-1 review (event log accumulation, in-place `dt`, device guards, odd host_io chunks).
+
+Fixtures: tests/golden/history_sho.npz, fixed_step.npz, solve_ivp_teval.npz -- produced by the unmodified reference
+(oracle/make_golden_round2.py)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_inf
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _de():
+    import desolver_b200 as de
+    return de
+
+
+def _sho(method, dense=False, rhs=None, **kw):
+    de = _de()
+    a = de.OdeSystem(rhs or de.rhs_plugins.harmonic_oscillator, torch.tensor([1.0, 0.0], dtype=torch.float64), t=(0, 2 * np.pi),
+                     constants=dict(k=1.0, m=1.0), dense_output=dense, **kw)
+    a.method = method
+    return a
+
+
+# ------------------------------------------------------------------ per-step history
+@pytest.mark.parametrize("key,method,kw", [("rk45", "RK45", dict(dt=0.01, rtol=1e-9, atol=1e-9)),
+                                           ("rk87", "RK87", dict(dt=0.01, rtol=1e-9, atol=1e-9)),
+                                           ("babs9o7h", "BABS9O7H", dict(dt=0.05))])
+@pytest.mark.parametrize("path", ["plugin", "callable"])
+def test_single_system_history_is_every_accepted_step(key, method, kw, path):
+    """`a.t`, `a.y`, `len(a)`, `a[i]` of a single system = the reference's rows (differential_system.py:1015-1018)."""
+    g = load_golden("history_sho.npz")
+    rhs = None
+    if path == "callable":                                    # untagged callable: stage-level kernels + row store
+        def rhs(t, y, k, m):
+            return torch.stack([y[1], -k / m * y[0]])
+    a = _sho(method, rhs=rhs, **kw)
+    assert len(a) == 1 and tuple(a.t.shape) == (1,) and tuple(a.y.shape) == (1, 2)
+    a.integrate()
+    t_ref, y_ref = g[key + ".t"], g[key + ".y"]
+    assert len(a) == int(g[key + ".len"]) == t_ref.shape[0]
+    assert tuple(a.t.shape) == t_ref.shape and tuple(a.y.shape) == y_ref.shape
+    assert np.max(np.abs(a.t.cpu().numpy() - t_ref)) <= 1e-12
+    assert np.max(np.abs(a.y.cpu().numpy() - y_ref)) <= 1e-11
+    assert float(a[0].t) == 0.0 and torch.equal(a[0].y.cpu(), torch.tensor([1.0, 0.0], dtype=torch.float64))
+    assert torch.equal(a[-1].y, a.y[-1]) and float(a[-1].t) == float(a.t[-1])
+    assert torch.equal(a[3].y, a.y[3]) and torch.equal(a[-2].y, a.y[-2])
+    with pytest.raises(IndexError):
+        a[len(a)]
+    assert int(a.accepted.sum()) == len(a) - 1
+    if key == "rk45":
+        assert len(a) - 1 == 84                                # KA0
+
+
+def test_history_slices_nearest_lookup_and_continuation():
+    g = load_golden("history_sho.npz")
+    a = _sho("RK45", dt=0.01, rtol=1e-9, atol=1e-9)
+    a.integrate()
+    s = a[0.5:2.0]                                             # slices are by TIME (reference :1170-1183)
+    assert np.max(np.abs(s.t.cpu().numpy() - g["slice.t"])) <= 1e-12 and np.max(np.abs(s.y.cpu().numpy() - g["slice.y"])) <= 1e-11
+    assert np.max(np.abs(a[1.0:].t.cpu().numpy() - g["slice_open.t"])) <= 1e-12
+    assert np.max(np.abs(a[:3.0:2].t.cpu().numpy() - g["slice_step.t"])) <= 1e-12
+    for q, t_near in zip(g["near.q"], g["near.t"]):             # nearest stored step without dense output (:1187-1196)
+        assert abs(float(a[float(q)].t) - t_near) <= 1e-12
+    a.integrate(7.0)                                           # a second call continues the same history
+    assert len(a) == g["cont.t"].shape[0]
+    assert np.max(np.abs(a.t.cpu().numpy() - g["cont.t"])) <= 1e-12 and np.max(np.abs(a.y.cpu().numpy() - g["cont.y"])) <= 1e-10
+    a.reset()
+    assert len(a) == 1
+    a.integrate()
+    assert len(a) == int(g["rk45.len"])
+
+
+def test_history_grows_past_its_first_allocation():
+    """5001 rows are allocated up front like the reference (:734-742); a longer run re-sizes the store and repeats."""
+    de = _de()
+    a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, torch.tensor([1.0, 0.0], dtype=torch.float64), t=(0, 12.0), dt=1e-3,
+                     constants=dict(k=1.0, m=1.0))
+    a.method = "RK4"
+    a.integrate()
+    assert len(a) in (12001, 12002) and abs(float(a.t[-1]) - 12.0) <= 1e-12
+    tt = a.t.cpu().numpy()
+    assert np.all(np.diff(tt) > 0) and np.max(np.abs(a.y[:, 0].cpu().numpy() - np.cos(tt))) < 1e-9
+    b = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, torch.tensor([1.0, 0.0], dtype=torch.float64), t=(0, 12.0), dt=1e-3,
+                     constants=dict(k=1.0, m=1.0), history="calls")
+    b.method = "RK4"
+    b.integrate()
+    assert len(b) == 2 and torch.equal(b[-1].y, a[-1].y)
+
+
+# ------------------------------------------------------------------ dense output over the node store
+def test_array_valued_sol_and_grad_match_the_reference():
+    g = load_golden("history_sho.npz")
+    a = _sho("RK45", dense=True, dt=0.01, rtol=1e-9, atol=1e-9)
+    a.integrate()
+    tq = torch.as_tensor(g["tq"])
+    got = a.sol(tq)                                            # (T, dim): the reference's t.shape + y.shape
+    assert tuple(got.shape) == g["sol"].shape and np.max(np.abs(got.cpu().numpy() - g["sol"])) <= 1e-11
+    got2 = a.sol(tq[:6].reshape(2, 3))
+    assert tuple(got2.shape) == g["sol2d"].shape and np.max(np.abs(got2.cpu().numpy() - g["sol2d"])) <= 1e-11
+    for q, t in enumerate(g["tq"]):                             # scalar queries = rows of the array query, bit for bit
+        assert torch.equal(a.sol(float(t)), got[q])
+        assert np.max(np.abs(a.sol.grad(float(t)).cpu().numpy() - g["grad"][q])) <= 1e-9
+    assert torch.equal(a.sol.grad(tq)[3], a.sol.grad(float(tq[3])))
+    assert torch.equal(a[1.0].y, a.sol(1.0)) and len(a.sol) == len(a)
+
+
+def test_ensemble_grid_evaluation_and_per_trajectory_steps():
+    de = _de()
+    g = load_golden("lorenz_dense.npz")
+    y0 = torch.as_tensor(g["y0"])
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, dense_output=True)
+    a.method = "RK45"
+    a.integrate()
+    times = torch.as_tensor(g["tq"])
+    grid = a.sol.grid(times)                                   # ONE launch: (T, dim, N)
+    assert tuple(grid.shape) == (len(times), 3, y0.shape[1])
+    assert np.max(rel_inf(np.moveaxis(grid.cpu().numpy(), 0, -1).reshape(3, -1), np.moveaxis(g["dense"], 0, -1).reshape(3, -1))) < 1e-10
+    for q in (0, 7, 23):
+        assert torch.equal(grid[q], a.sol(float(times[q])))
+    per = times[:y0.shape[1]].clone()
+    two = a.sol(torch.stack([per, per.flip(0)]))                # (T=2, N) query times -> (2, dim, N)
+    assert torch.equal(two[0], a.sol(per)) and torch.equal(two[1], a.sol(per.flip(0)))
+    dg = a.sol.grid(times, derivative=True)
+    f = de.rhs_plugins.lorenz(0.0, a.sol(0.3), sigma=10.0, rho=28.0, beta=8.0 / 3.0)
+    assert float((a.sol.grad(0.3) - f).abs().max()) < 1e-4 and tuple(dg.shape) == tuple(grid.shape)
+    # the ragged per-trajectory history: every trajectory's rows = that trajectory run alone as a single system
+    for i in (0, 5):
+        s = de.OdeSystem(de.rhs_plugins.lorenz, y0[:, i].clone(), t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9)
+        s.method = "RK45"
+        s.integrate()
+        t_i, y_i = a.steps(i)
+        assert torch.equal(t_i, s.t) and torch.equal(y_i, s.y) and int(a.accepted[i]) == len(s) - 1
+
+
+def test_dense_output_at_scale_fits_and_is_deterministic():
+    """2^17 Lorenz trajectories with dense output: ~3.3e7 nodes in a ragged store of ~2.2 GB (the round-1 layout
+    needed 7.5 GB at its default capacity), results identical to the run without dense output."""
+    de = _de()
+    n = 1 << 17
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(n, seed=1)).cuda()
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, dense_output=True)
+    a.method = "RK45"
+    a.integrate()
+    b = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    b.method = "RK45"
+    b.integrate()
+    assert torch.equal(a[-1].y, b[-1].y) and torch.equal(a.accepted, b.accepted) and torch.equal(a.rejected, b.rejected)
+    st = a._node_store
+    claimed, dropped = st.usage()
+    total = int(a.accepted.sum()) + n
+    assert dropped == 0 and torch.equal(a.sol.node_count, a.accepted + 1)
+    assert total <= claimed <= total + 4736 * st.page_entries           # no waste beyond one page in progress per warp
+    assert torch.equal(a.sol(2.0), a[-1].y) and torch.equal(a.sol(0.0), y0)
+    mid = a.sol(1.0)
+    a.reset()
+    a.integrate()
+    assert torch.equal(a.sol(1.0), mid)                                 # scheduling-independent, run to run
+
+
+# ------------------------------------------------------------------ solve_ivp(t_eval)
+def test_solve_ivp_t_eval_matches_the_reference_and_the_dense_mode():
+    de = _de()
+    g = load_golden("solve_ivp_teval.npz")
+    y0 = torch.as_tensor(g["y0"])
+    r = de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.5), y0, method="RK45", t_eval=g["t_eval"], rtol=1e-9, atol=1e-9,
+                     first_step=1e-2, ensemble=True)
+    assert tuple(r.y.shape) == g["y"].shape                     # (dim, N, T)
+    for q in range(g["t_eval"].shape[0]):
+        assert rel_inf(r.y[..., q].cpu().numpy(), g["y"][..., q]).max() <= 1e-10
+    assert np.max(np.abs(r.t.cpu().numpy() - g["t"])) <= 1e-13
+    d = de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.5), y0, method="RK45", t_eval=g["t_eval"], rtol=1e-9, atol=1e-9,
+                     first_step=1e-2, ensemble=True, t_eval_mode="dense")
+    assert d.ode_system._launches == 1                          # one integration; the evaluation is one more launch
+    assert tuple(d.y.shape) == g["y"].shape and float((d.y - r.y).abs().max() / r.y.abs().max()) < 1e-6
+    s = de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.5), y0[:, 0].clone(), method="RK45", t_eval=g["t_eval"], rtol=1e-9, atol=1e-9,
+                     first_step=1e-2)
+    assert rel_inf(s.y.cpu().numpy(), g["y"][:, 0]).max() <= 1e-10
+
+
+# ------------------------------------------------------------------ the fixed-step tableaux that had no fixture
+@pytest.mark.parametrize("method", ["RK5", "Midpoint", "Heun's", "Ralston's", "Euler", "Euler-Trapezoidal"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_fixed_step_tableaux(method, fused):
+    de = _de()
+    g = load_golden("fixed_step.npz")
+    a = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(g["y0"]), t=(0.0, float(g["tf"])), dt=float(g["dt0"]), ensemble=True)
+    a.method = method
+    a.use_fused = fused
+    a.integrate()
+    assert np.array_equal(a.accepted.cpu().numpy(), g[method + ".steps"]) and int(a.rejected.sum()) == 0
+    assert rel_inf(a[-1].y.cpu().numpy(), g[method + ".y"]).max() <= 1e-12
+    assert np.max(np.abs(a[-1].t.cpu().numpy() - g[method + ".t"])) <= 1e-13
+
+
+def test_symplectic_euler_history():
+    de = _de()
+    g = load_golden("fixed_step.npz")
+    a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, torch.tensor([1.0, 0.0], dtype=torch.float64), t=(0, 1.0), dt=0.01,
+                     constants=dict(k=1.0, m=1.0))
+    a.method = "Symplectic Forward Euler"
+    a.integrate()
+    assert tuple(a.t.shape) == g["symp_euler.t"].shape
+    assert np.max(np.abs(a.t.cpu().numpy() - g["symp_euler.t"])) <= 1e-13 and np.max(np.abs(a.y.cpu().numpy() - g["symp_euler.y"])) <= 1e-13
+
+
+# ------------------------------------------------------------------ integrator protocol (seam 1)
+def test_integrator_protocol_dense_output_and_custom_adaptation():
+    de = _de()
+    integ = de.integrators.RK45CKSolver((3,), torch.float64, rtol=1e-9, atol=1e-9, device="cuda")
+    y0 = torch.tensor([1.0, 1.0, 20.0], dtype=torch.float64, device="cuda")
+    consts = dict(sigma=10.0, rho=28.0, beta=8.0 / 3.0)
+    new_dt, (dT, dY) = integ(de.rhs_plugins.lorenz, 0.0, y0, consts, 1e-2)
+    t1, interp = integ.dense_output()                          # reference integrator_types.py:109-119
+    assert float(t1) == float(dT) and torch.equal(interp(0.0), y0) and torch.equal(interp(float(t1)), y0 + dY)
+    f0 = de.rhs_plugins.lorenz(0.0, y0, **consts)
+    assert torch.equal(interp.grad(0.0), f0) and torch.equal(interp.m0, f0)
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, constants=consts, dense_output=True)
+    a.integrate()
+    assert abs(float(a.t[1]) - float(t1)) <= 1e-15              # first accepted step of KA1 (after one rejection)
+    half = 0.5 * float(t1)
+    assert float((interp(half) - a.sol(half)).abs().max()) <= 1e-10
+    # a custom controller that defers to the built-in one must reproduce the built-in step
+    custom = de.integrators.RK45CKSolver((3,), torch.float64, rtol=1e-9, atol=1e-9, device="cuda")
+    calls = []
+
+    def controller(self):
+        calls.append(float(self.solver_dict["timestep"]))
+        return self.update_timestep(ignore_custom_adaptation=True)
+    custom.adaptation_fn = controller
+    calls.clear()
+    new_dt2, (dT2, dY2) = custom(de.rhs_plugins.lorenz, 0.0, y0, consts, 1e-2)
+    assert len(calls) == 2 and abs(float(dT2) - float(dT)) <= 1e-15 and abs(float(new_dt2) - float(new_dt)) <= 1e-13
+    assert float((dY2 - dY).abs().max()) <= 1e-13
+    # symplectic protocol step
+    symp = de.integrators.BABs9o7HSolver((2,), torch.float64, device="cuda")
+    q0 = torch.tensor([1.0, 0.0], dtype=torch.float64, device="cuda")
+    step, (dTs, dYs) = symp(de.rhs_plugins.harmonic_oscillator, 0.0, q0, dict(k=1.0, m=1.0), 0.05)
+    assert float(step) == 0.05 and abs(float(dTs) - 0.05) <= 1e-17
+    assert abs(float((q0 + dYs)[0]) - np.cos(0.05)) < 1e-12
+    t_end, it2 = symp.dense_output()
+    assert torch.equal(it2(0.05), q0 + dYs)
+
+
+# ------------------------------------------------------------------ lazy status
+def test_lazy_status_defers_the_counter_read_back():
+    de = _de()
+    y0 = de.benchmarks.lorenz_ensemble(4096, seed=3)
+    a = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(y0), t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    a.method = "RK45"
+    a.integrate()
+    eager = a.stats
+    a.reset()
+    a.lazy_status = True
+    a.integrate()
+    assert a._pending and a._stats is None
+    assert a.success and a.stats == eager and not a._pending
+    bad = y0.copy()
+    bad[:, 7] = np.inf
+    b = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(bad), t=(0.0, 0.1), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    b.lazy_status = True
+    b.integrate()                                              # does not raise: nothing has been read yet
+    assert not b.success and "FailedToMeetTolerances" in repr(type(b._OdeSystem__int_status.__cause__))
+    with pytest.raises(de.exception_types.FailedIntegration):
+        b.check()
+    assert b.stats["failed"] == 1
+
+
+# ------------------------------------------------------------------ fixes from the round-1 review
+def test_event_log_accumulates_over_calls_with_a_plain_callable():
+    de = _de()
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(64, seed=6))
+    ev = lambda t, y, **kw: y[0] - 1.0                          # noqa: E731   (converted to a new object on every call)
+
+    def run(stops):
+        a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+        a.method = "RK45"
+        for tf in stops:
+            a.integrate(tf, events=ev)
+        return a
+    one, two = run([2.0]), run([0.7, 1.4, 2.0])
+    assert int(two.events.count.sum()) == int(one.events.count.sum()) > 0
+    assert torch.equal(two.events.count, one.events.count)
+
+
+def test_max_step_reaches_the_stage_level_kernels():
+    de = _de()
+
+    def rhs(t, y):                                             # untagged: stage-level path
+        return torch.stack([y[1], -y[0]])
+    y0 = torch.tensor([[1.0, 0.5], [0.0, 0.2]], dtype=torch.float64)
+    free = de.solve_ivp(rhs, (0.0, 3.0), y0, method="RK45", rtol=1e-6, atol=1e-6, first_step=1e-2, ensemble=True)
+    capped = de.solve_ivp(rhs, (0.0, 3.0), y0, method="RK45", rtol=1e-6, atol=1e-6, first_step=1e-2, ensemble=True, max_step=0.05)
+    assert int(capped.ode_system.accepted.min()) >= 60 > int(free.ode_system.accepted.max())
+    assert float(capped.ode_system.dt.abs().max()) <= 0.05
+    a = capped.ode_system
+    exact = torch.stack([y0[0] * np.cos(3.0) + y0[1] * np.sin(3.0), -y0[0] * np.sin(3.0) + y0[1] * np.cos(3.0)]).cuda()
+    assert float((a[-1].y - exact).abs().max()) < 1e-6
+
+
+def test_current_device_is_restored_and_other_devices_work():
+    de = _de()
+    before = torch.cuda.current_device()
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(256, seed=2))
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 0.5), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, device="cuda:0")
+    a.integrate()
+    assert torch.cuda.current_device() == before
+    if torch.cuda.device_count() < 2:
+        return
+    b = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 0.5), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, device="cuda:1")
+    b.integrate()                                              # created and launched while cuda:0 is current
+    assert torch.cuda.current_device() == before and torch.equal(a[-1].y.cpu(), b[-1].y.cpu())
+
+
+def test_host_io_with_odd_length_and_several_chunks():
+    de = _de()
+    n = 40001                                                  # n % 4 != 0: chunk boundaries fall inside 32-byte sectors
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(n, seed=8)).pin_memory()
+    a = de.OdeSystem(de.rhs_plugins.lorenz, y0.cuda(), t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    a.integrate()
+    for chunks in (7, 16):
+        h = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, host_io=True,
+                         host_chunks=chunks)
+        h.integrate()
+        assert torch.equal(h[-1].y, a[-1].y.cpu()) and torch.equal(h.accepted, a.accepted.cpu())
+
+
+# ------------------------------------------------------------------ collectives behind the C ABI (one rank)
+def test_comm_entry_points_on_one_rank():
+    from desolver_b200.backend import cuda_backend as cb
+    if not cb.Comm.available():
+        pytest.skip("NCCL not loadable")
+    comm = cb.Comm(0, 1, 0, cb.Comm.unique_id())
+    dev = torch.device("cuda:0")
+    c = torch.arange(8, dtype=torch.int64, device=dev)
+    out = torch.zeros(4, dtype=torch.int64, device=dev)
+    st = cb.current_stream_ptr(dev)
+    comm.allreduce_counters(c.data_ptr() + 16, out.data_ptr(), 4, st)
+    shard = torch.randn(3, 1000, dtype=torch.float64, device=dev)
+    full = torch.empty_like(shard)
+    staging = torch.empty(comm.staging_bytes(3, 8, 1000), dtype=torch.uint8, device=dev)
+    comm.gather(shard, staging, full, 1000, st)
+    torch.cuda.synchronize()
+    assert out.tolist() == [2, 3, 4, 5] and torch.equal(full, shard)
+    comm.close()
+
+
+def test_scatter_store_interleaves_round_robin_shards():
+    """The gather fused into the result store (dsb_erk_run_args.out_*): two shard systems (the two 'ranks' of a
+    round-robin split, here on one device) store straight into one buffer; the buffer equals the unsharded run."""
+    de = _de()
+    from desolver_b200.backend import cuda_backend as cb
+    n, W = 10001, 2
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(n, seed=13)).cuda()
+    ref = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    ref.integrate()
+    buf = cb.PeerBuffer.allocate(8 * 5 * n + 4 * 3 * n + 64, 0)
+    y = buf.tensor(torch.float64, (3, n), 0)
+    t = buf.tensor(torch.float64, (n,), 8 * 3 * n)
+    dt = buf.tensor(torch.float64, (n,), 8 * 4 * n)
+    acc = buf.tensor(torch.int32, (n,), 8 * 5 * n)
+    rej = buf.tensor(torch.int32, (n,), 8 * 5 * n + 4 * n)
+    sta = buf.tensor(torch.int32, (n,), 8 * 5 * n + 8 * n)
+    for x in (y, t, dt, acc, rej, sta):
+        x.fill_(-1)
+    total = 0
+    for rank in range(W):
+        s = de.OdeSystem(de.rhs_plugins.lorenz, y0[:, rank::W].contiguous(), t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+        s._scatter_store = dict(index_mul=W, index_add=rank, stride=n, y=y.data_ptr(), t=t.data_ptr(), dt=dt.data_ptr(),
+                                accepted=acc.data_ptr(), rejected=rej.data_ptr(), status=sta.data_ptr())
+        s.lazy_status = True
+        s.integrate()
+        total += s.stats["attempts"]
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref[-1].y) and torch.equal(t, ref[-1].t) and torch.equal(dt, ref.dt)
+    assert torch.equal(acc, ref.accepted) and torch.equal(rej, ref.rejected) and torch.equal(sta, ref.status)
+    assert total == ref.stats["attempts"]

@@ -47,7 +47,7 @@ int main(int argc, char **argv)
     a.n = n; a.y = y; a.t = t; a.dt = dt;
     for (int p = 0; p < 3; ++p) { a.params[p] = prm + p; a.param_stride[p] = 0; }
     a.tf = 2.0; a.rtol = 1e-9; a.atol = 1e-9; a.accepted = acc; a.rejected = rej; a.status = st;
-    a.max_steps = -1; a.first_call = 1; a.nodes = nullptr; a.node_count = nullptr; a.node_capacity = 0; a.counters = (uint64_t *)ctr;
+    a.max_steps = -1; a.first_call = 1; a.counters = (uint64_t *)ctr;
 #ifdef BENCH_FRESH
     a.fresh = 1; a.t_init = 0.0; a.dt_init = 1e-2;
 #endif
