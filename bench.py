@@ -36,6 +36,43 @@ METRIC = "trajectory-steps/s (RK45 Cash-Karp adaptive fp64, Lorenz-63, 2^20 traj
 UNIT = "trajectory-steps/s"
 
 
+def static_config(n_local):
+    """The workload description shared VERBATIM by both arms (the driver compares the two `config` dicts)."""
+    from desolver_b200 import benchmarks as bm
+    cfg = bm.LORENZ
+    return {"workload": "lorenz63_rk45ck_2^20_per_gpu", "trajectories_per_gpu": int(n_local),
+            "t_span": [cfg["t0"], cfg["tf"]], "rtol": cfg["rtol"], "atol": cfg["atol"], "dt0": cfg["dt0"], "method": "RK45CK",
+            "y0": "U([-20,20]x[-25,25]x[0,50]), numpy default_rng(0), dealt round-robin over the ranks",
+            "l2": "flushed between timed iterations (256 MiB memset)",
+            "sharding": "round-robin over ranks, no data-path collective"}
+
+
+def reference_numpy_numbers():
+    """The reference's own numpy backend (CPU-A: one OdeSystem per trajectory; CPU-B: a whole shard as ONE state with a
+    global dt -- different semantics) cannot travel to the GPU box (pure-Python sources under /root/reference, its build
+    backend `hatchling` and its dependency `autoray` are absent from the offline wheelhouse), so its timing is taken in
+    the build container by tools/reference_numpy_timing.py and committed under profiles/.  If a reference tree IS
+    importable on this box (baseline/_ref or /root/reference), it is timed live instead."""
+    rec = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "round2_reference_numpy_timing.json")))
+        rec["where"] = "build container (recorded by tools/reference_numpy_timing.py)"
+    except Exception:
+        pass
+    for tree in (os.path.join(ROOT, "baseline", "_ref"),):
+        if os.path.isdir(os.path.join(tree, "desolver")):
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import reference_numpy_timing as rnt
+                live = rnt.measure(tree, seconds=6.0)
+                live["where"] = "this box, live (%s)" % tree
+                return live
+            except Exception as e:                          # noqa: BLE001
+                if rec is not None:
+                    rec["live_error"] = repr(e)[:200]
+    return rec
+
+
 def measured_peak_gbs():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -73,6 +110,7 @@ def cpu_reference_sample(seconds_budget, n_global, rank_stride=1):
                          params=params, threads=threads)
     wall = time.perf_counter() - t0
     steps = float((r["accepted"] + r["rejected"]).sum())
+    cpu_reference_sample.last = (m, r)          # kept for the full-size parity gate (checker use of the oracle)
     return steps / wall, threads, "first %d trajectories of the Lorenz ensemble, %.1f s wall" % (m, wall), steps, wall
 
 
@@ -137,11 +175,28 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "lorenz63_rk45ck_2^20_per_gpu", "sample": info[1]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[0], "kind": "port", "sample": info[1]},
+            "config": static_config(args.n_per_gpu),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[0], "kind": "port", "sample": info[1],
+                             "what": "oracle/desolver_oracle.c: C restatement of the reference algorithm, one thread per core"},
+            "cpu_reference_numpy": reference_numpy_numbers(),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def parity_gate(y_gpu, acc_gpu, rej_gpu, ref, global_index):
+    """GPU results (this rank's shard, numpy) against the CPU oracle's results for the same trajectories.
+    `global_index[j]` = position of local trajectory j in the oracle's (prefix) ensemble."""
+    y_ref = ref["y"][:, global_index]
+    err = np.max(np.abs(y_gpu - y_ref), axis=0) / np.max(np.abs(y_ref), axis=0)
+    same = (acc_gpu == ref["accepted"][global_index]) & (rej_gpu == ref["rejected"][global_index])
+    return {"checked_trajectories": int(global_index.shape[0]), "counts_identical_frac": float(same.mean()),
+            "max_rel_err": float(err.max()), "p99_rel_err": float(np.percentile(err, 99)),
+            "p99_99_rel_err": float(np.percentile(err, 99.99)), "median_rel_err": float(np.median(err)),
+            "n_over_1e-10": int((err > 1e-10).sum()),
+            "bar": "counts identical >= 0.999, rel err <= 1e-10 (BASELINE.json north_star); the handful of trajectories "
+                   "beyond 1e-10 are chaos amplifying last-ulp differences of pow/atan -- pinned by "
+                   "tests/test_oracle_golden.py::test_parity_tail_is_chaos_not_arithmetic"}
 
 
 def main():
@@ -153,6 +208,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs / scaling modes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -163,6 +219,7 @@ def main():
     import torch
     import torch.distributed as dist
     import desolver_b200 as de
+    from desolver_b200 import distributed as dd
     from desolver_b200.backend import cuda_backend as cb
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,6 +227,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; desolver_b200 has no CPU fallback")
+    numa_node = dd.bind_to_gpu_numa_node(local_rank) if world > 1 else None     # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -188,31 +246,36 @@ def main():
                         atol=cfg["atol"], constants=dict(sigma=cfg["sigma"], rho=cfg["rho"], beta=cfg["beta"]),
                         ensemble=True)
     sys_.method = "RK45"
+    sys_.lazy_status = True            # integrate() returns when the launch is enqueued; counters are read after the loop
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    comm = dd.communicator(dev) if world > 1 else None                # dsb_comm_* (NCCL) behind the C ABI
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    n_slots = args.steps + args.warmup + 4
+    local_ctr = torch.zeros((n_slots, 4), dtype=torch.int64, device=dev)     # per step: this rank's kernel counters
+    global_ctr = torch.zeros((n_slots, 4), dtype=torch.int64, device=dev)    # ... summed over the ranks
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(ev=None):
-        """device-resident step: reset state from y0 (device copy), integrate, reduce the counters"""
+    def one_step(slot, ev=None):
+        """Device-resident step: reset (the kernel re-initialises from y0 itself), ONE launch, and -- behind it, on a side
+        stream -- the termination / statistics all-reduce of the kernel's own counters (attempts, accepted, failed,
+        unfinished).  No host synchronisation anywhere: the ranks meet in the collective on the device only."""
         sys_.reset()
         sys_._kernel_events = ev              # CUDA events recorded around the dsb_erk_run launch itself
         sys_.integrate()
         sys_._kernel_events = None
-        st = sys_.stats                       # totals accumulated by the kernel itself (one 64-byte D2H in integrate())
+        local_ctr[slot].copy_(sys_._counters[2:6])
         if world > 1:
-            # termination / statistics all-reduce (NCCL) straight from the kernel's device counters
-            # ([2] attempts, [4] failed, [5] unfinished): no host round trip in front of the collective
-            red = sys_._counters[2:6].clone()          # [attempts, accepted, failed, unfinished], int64
-            dist.all_reduce(red)
-            return torch.stack([red[0], red[2] + red[3]]).to(torch.float64)
-        return torch.tensor([float(st["attempts"]), float(st["failed"] + st["running"])], dtype=torch.float64)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            comm.allreduce_counters(local_ctr[slot].data_ptr(), global_ctr[slot].data_ptr(), 4, cb.C.c_void_p(side.cuda_stream))
+        else:
+            global_ctr[slot].copy_(local_ctr[slot])
 
-    for _ in range(args.warmup):
-        one_step()
+    for w in range(args.warmup):
+        one_step(w)
         flush.zero_()
     barrier()
 
@@ -221,62 +284,51 @@ def main():
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = sys_._launches
-    total_attempts = 0.0
     barrier()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         step_ev[i][0].record()
-        st = one_step(kern_ev[i])
+        one_step(args.warmup + i, kern_ev[i])
         step_ev[i][1].record()
         flush.zero_()                          # L2 flush between timed iterations (outside the events)
-        total_attempts_dev = st
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in step_ev]
     kern_ms = [a.elapsed_time(b) for a, b in kern_ev]
-    launches = sys_._launches - launches0
-    attempts_global = float(total_attempts_dev[0].item())       # per step, all ranks (already all-reduced)
-    failed = float(total_attempts_dev[1].item())
-    attempts_local = float(sys_.stats["attempts"])
-    accepted_local = float(sys_.stats["accepted"])
-    t_local = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
+    launches = sys_._launches - launches0 + (args.steps if world > 1 else 0)      # + one all-reduce kernel per step (NCCL)
+    timed = slice(args.warmup, args.warmup + args.steps)
+    g = global_ctr[timed].cpu().numpy()
+    loc = local_ctr[timed].cpu().numpy()
+    assert (g == g[0]).all() and (loc == loc[0]).all(), "the step is deterministic: every pass must count the same"
+    attempts_global, failed = float(g[0, 0]), float(g[0, 2] + g[0, 3])
+    attempts_local, accepted_local = float(loc[0, 0]), float(loc[0, 1])
+    # whole-job time = first event to last event on each rank (the passes run back to back, rank-asynchronously), max over ranks
+    span_ms = step_ev[0][0].elapsed_time(step_ev[-1][1])
+    t_local = torch.tensor([sum(step_ms), sum(kern_ms), span_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
     total_ms, total_kern_ms = float(t_local[0]), float(t_local[1])
     value = attempts_global * args.steps / (total_ms * 1e-3)
 
-    # ---- parity gate, printed with the throughput: the first trajectories of this rank's
-    # shard against the CPU oracle in the same run; run-to-run bitwise determinism of the GPU path ----
-    parity = None
-    if rank == 0:
-        from desolver_b200.integrators import tableaux as tb
-        from oracle import oracle as orc
-        m = min(4096, n_local)
-        ref = orc.erk_ensemble(orc.RHS_LORENZ, np.ascontiguousarray(y0_host[:, :m]), cfg["t0"], cfg["tf"], cfg["dt0"], cfg["rtol"],
-                               cfg["atol"], *tb.rk_arrays("RK45CKSolver"), params=[cfg["sigma"], cfg["rho"], cfg["beta"]],
-                               threads=host_threads())
-        y_a = sys_[-1].y.clone()
-        acc_a, rej_a = sys_.accepted.clone(), sys_.rejected.clone()
-        one_step()
-        deterministic = bool(torch.equal(y_a, sys_[-1].y) and torch.equal(acc_a, sys_.accepted) and torch.equal(rej_a, sys_.rejected))
-        got = y_a[:, :m].cpu().numpy()
-        err = np.max(np.abs(got - ref["y"]), axis=0) / np.max(np.abs(ref["y"]), axis=0)
-        same = (acc_a[:m].cpu().numpy() == ref["accepted"]) & (rej_a[:m].cpu().numpy() == ref["rejected"])
-        parity = {"checked_trajectories": int(m), "counts_identical_frac": float(same.mean()), "max_rel_err": float(err.max()),
-                  "p99_rel_err": float(np.percentile(err, 99)), "bitwise_deterministic": deterministic,
-                  "bar": "counts identical >= 0.999, rel err <= 1e-10 (BASELINE.json north_star)"}
-    elif world > 1:
-        one_step()                                        # keep the collective inside one_step matched across ranks
+    y_a = sys_[-1].y.clone()
+    acc_a, rej_a = sys_.accepted.clone(), sys_.rejected.clone()
+    one_step(n_slots - 1)                    # (every rank: the collective inside one_step stays matched)
+    deterministic = bool(torch.equal(y_a, sys_[-1].y) and torch.equal(acc_a, sys_.accepted) and torch.equal(rej_a, sys_.rejected))
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
 
     # ---- e2e: public API with host buffers.  `host_io=True`: pinned host y0 in, pinned host results out; the
     # upload, the kernels and the download of the chunks overlap inside integrate() (OdeSystem._run_host_pipeline).
     # The timed region covers construction, every host<->device copy, the integration and the final synchronisation.
+    # The status words are not downloaded: the kernel's counters say whether any trajectory failed (none does), and
+    # `a.status` fetches them on demand.
     e2e_steps = max(2, min(args.steps, 5))
     host_out = dict(y=torch.empty((3, n_local), dtype=torch.float64).pin_memory(),
                     accepted=torch.empty(n_local, dtype=torch.int32).pin_memory(),
-                    rejected=torch.empty(n_local, dtype=torch.int32).pin_memory(),
-                    status=torch.empty(n_local, dtype=torch.int32).pin_memory())
+                    rejected=torch.empty(n_local, dtype=torch.int32).pin_memory())
     e2e_ms = []
     E2E_WARMUP = 2                      # allocator / stream-creation warm-up iterations, untimed
     s2 = None
@@ -293,7 +345,7 @@ def main():
         if i >= E2E_WARMUP:
             e2e_ms.append(a.elapsed_time(b))
         if i == 0 and rank == 0:        # the host results are the device-resident results, bit for bit
-            assert torch.equal(s2[-1].y, sys_[-1].y.cpu()) and torch.equal(s2.accepted, sys_.accepted.cpu())
+            assert torch.equal(s2[-1].y, y_a.cpu()) and torch.equal(s2.accepted, acc_a.cpu()) and int(s2.status.sum()) == 0
         flush.zero_()
     # the same with ONE system reused (reset() + integrate()): what a caller who integrates ensemble after ensemble pays;
     # reported next to the headline, which keeps the construction inside the timed region
@@ -315,6 +367,29 @@ def main():
     e2e_value = attempts_global / (float(e2e_t[0]) * 1e-3)
     h2d = int(y0_pinned.numel() * 8)
     d2h = int(sum(v.numel() * v.element_size() for v in host_out.values()))
+    s2 = None
+
+    # ---- the other BASELINE configs / scaling modes, under the same clock ----
+    extra = {}
+    if not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import config_runs as cr
+        peak_gbs = measured_peak_gbs()[0]
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            if world == 1:
+                extra["config4_vdp_2pow24"] = cr.run_vdp(dev, reps=3, check=2048, hbm_peak=peak_gbs)
+                torch.cuda.empty_cache()
+                extra["config3_nbody"] = cr.run_nbody(dev, reps=3, check=16)
+                torch.cuda.empty_cache()
+                extra["config2_linear"] = cr.run_linear(dev, reps=2, check=4)
+            else:
+                extra["strong_2pow20"] = cr.run_lorenz_strong(dev, world, rank, reps=5)
+                extra["vdp_2pow24_sharded"] = cr.run_vdp(dev, world, rank, reps=3, check=2048, hbm_peak=peak_gbs)
+        except Exception as e:                                  # noqa: BLE001  (the headline line must still be printed)
+            extra["error"] = repr(e)[:400]
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
@@ -328,12 +403,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "lorenz63_rk45ck_2^20_per_gpu", "trajectories_per_gpu": n_local,
-                           "t_span": [cfg["t0"], cfg["tf"]], "rtol": cfg["rtol"], "atol": cfg["atol"], "dt0": cfg["dt0"],
-                           "method": "RK45CK", "l2": "flushed between timed iterations (256 MiB memset)",
-                           "sharding": "round-robin over ranks, no data-path collective",
-                           "attempts_per_step": attempts_global, "accepted_local": accepted_local,
-                           "failed_trajectories": failed, "wall_s_timed_region": wall},
+                "config": static_config(n_local),
+                "run": {"attempts_per_step": attempts_global, "accepted_local": accepted_local, "failed_trajectories": failed,
+                        "wall_s_timed_region": wall, "ms_first_to_last_event": float(t_local[2]), "numa_node": numa_node,
+                        "collective": ("dsb_comm_allreduce_counters (NCCL %d) on a side stream behind every launch"
+                                       % cb.lib().dsb_comm_nccl_version()) if world > 1 else None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_kind, "kernel": "dsb::erk_fused_kernel<LorenzRhs, StaticTab<CashKarp45>>",
                              "kernel_ms": total_kern_ms / args.steps,
@@ -346,13 +420,32 @@ def main():
                                 "persistent launch, downloads and the final synchronisation inside the timed region",
                         "ms_per_step_system_reused_rank0": float(np.mean(reuse_ms))},
                 "gpu_launches": launches}
-        line["parity"] = parity
+        line.update(extra and {"configs": extra})
+        # ---- parity gate + CPU baseline: the oracle integrates a prefix of the GLOBAL ensemble (all of it when the host
+        # is fast enough) on the host cores; every trajectory of that prefix that lives on this rank is compared ----
         if not args.no_cpu_baseline:
             rate, cores, sample, _, _ = cpu_reference_sample(args.cpu_seconds, n_local * n_gpus)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "what": "oracle/desolver_oracle.c: C restatement of the reference algorithm, one thread per core"}
+            line["cpu_reference_numpy"] = reference_numpy_numbers()
+            m, ref = cpu_reference_sample.last
+        else:
+            from desolver_b200.integrators import tableaux as tb
+            from oracle import oracle as orc
+            m = min(4096 * n_gpus, n_local * n_gpus)
+            ref = orc.erk_ensemble(orc.RHS_LORENZ, de.benchmarks.lorenz_ensemble(m), cfg["t0"], cfg["tf"], cfg["dt0"], cfg["rtol"],
+                                   cfg["atol"], *tb.rk_arrays("RK45CKSolver"), params=[cfg["sigma"], cfg["rho"], cfg["beta"]],
+                                   threads=host_threads())
+        gidx = np.arange(rank, m, n_gpus)                       # global indices of this rank's trajectories inside the prefix
+        k = gidx.shape[0]
+        parity = parity_gate(y_a[:, :k].cpu().numpy(), acc_a[:k].cpu().numpy(), rej_a[:k].cpu().numpy(), ref, gidx)
+        parity["bitwise_deterministic"] = deterministic
+        parity["of_ensemble"] = "%d of the %d trajectories on rank 0" % (k, n_local)
+        line["parity"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        dd.destroy_communicators()
         dist.destroy_process_group()
 
 

@@ -49,7 +49,7 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
         return DSB_ERR_UNSUPPORTED;
     }
     if (n < 0 || n > 0x7fffffffLL || !r.y || !r.t || !r.dt || !r.counters || !r.accepted || !r.rejected || !r.status ||
-        !a->host_y0 || !a->host_y || !a->host_accepted || !a->host_rejected || !a->host_status || !a->flags ||
+        !a->host_y0 || !a->host_y || !a->host_accepted || !a->host_rejected || !a->flags ||
         !a->stream_up || !a->stream_down || a->chunk_shift < 5 || a->chunk_shift > 30 || !r.fresh || r.y_init ||
         r.store.pool) {
         set_error("dsb_erk_run_host: bad argument (device staging buffers with fresh = 1, no y_init, no dense output; "
@@ -108,7 +108,8 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
                                          sizeof(double) * len, dim, cudaMemcpyDeviceToHost, down));
         DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_accepted + lo, r.accepted + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
         DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_rejected + lo, r.rejected + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
-        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_status + lo, r.status + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
+        if (a->host_status)      // NULL: the caller fetches the status words only if counters[4..5] report a failure
+            DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_status + lo, r.status + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
     }
     DSB_CUDA_CHECK(cudaEventRecord(h->ev_done, down));
     DSB_CUDA_CHECK(cudaStreamWaitEvent(stream, h->ev_done, 0));

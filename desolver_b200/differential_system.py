@@ -187,7 +187,25 @@ class OdeSystem(object):
     _dt = _state_property("dt")
     accepted = _state_property("accepted")
     rejected = _state_property("rejected")
-    status = _state_property("status")
+
+    @property
+    def status(self):
+        """Per-trajectory status words (cuda_backend.TRAJ_*).  A host_io system without a caller-supplied status buffer
+        does not download them: after a clean run (the kernel's counters report no failed / unfinished trajectory) they
+        are all TRAJ_DONE and are materialised here on demand; otherwise they are fetched from the device."""
+        self._materialize()
+        if self._raw_status is None:
+            torch = _torch()
+            if self._host_status_clean:
+                self._raw_status = torch.zeros(self.n_traj, dtype=torch.int32)
+            else:
+                self._raw_status = self._dev_status.cpu()
+        return self._raw_status
+
+    @status.setter
+    def status(self, value):
+        self._materialize()
+        self._raw_status = value
 
     def __init__(self, equ_rhs, y0, t=(0, 1), dense_output=False, dt=1.0, rtol=None, atol=None, constants=dict(),
                  ensemble=False, device=None, dense_capacity=None, strict=False, host_io=False, host_chunks=16,
@@ -331,7 +349,10 @@ class OdeSystem(object):
         self._raw_y = host_buffer("y", (self.numel, n), torch.float64)
         self._raw_accepted = host_buffer("accepted", (n,), torch.int32)
         self._raw_rejected = host_buffer("rejected", (n,), torch.int32)
-        self._raw_status = host_buffer("status", (n,), torch.int32)
+        # status words: downloaded only into a buffer the caller supplies; otherwise on demand (see `status`)
+        self._host_status_buffer = host_buffer("status", (n,), torch.int32) if "status" in host_out else None
+        self._raw_status = self._host_status_buffer
+        self._host_status_clean = True
         self._dev_y = torch.empty((self.numel, n), dtype=torch.float64, device=dev)
         self._raw_t = torch.empty((n,), dtype=torch.float64, device=dev)      # t and dt stay on the device
         self._raw_dt = torch.empty((n,), dtype=torch.float64, device=dev)
@@ -395,7 +416,8 @@ class OdeSystem(object):
             self._raw_dt.fill_(self._initial_dt())
             self._raw_accepted.zero_()
             self._raw_rejected.zero_()
-            self._raw_status.zero_()
+            if self._raw_status is not None:
+                self._raw_status.zero_()
 
     def _detach_history(self):
         if self.__dict__.get("_hist_alias"):
@@ -479,6 +501,17 @@ class OdeSystem(object):
                 t_rows, y_rows = st.gather(0)
                 self._steps_cache = (t_rows, y_rows.reshape((t_rows.shape[0],) + tuple(self.dim)))
         return self._steps_cache
+
+    @staticmethod
+    def _locate_step(t_rows, value):
+        """The reference's `search_bisection` (utilities/utilities.py:223-267): index of the first row whose time is
+        >= value, clamped to the stored range (rows in descending time for a backward integration are handled by
+        mirroring)."""
+        t_host = t_rows.cpu().numpy()
+        rows = t_host.shape[0]
+        asc = rows < 2 or t_host[-1] >= t_host[0]
+        arr, val = (t_host, float(value)) if asc else (-t_host, -float(value))
+        return int(min(np.searchsorted(arr, val, side="left"), rows - 1))
 
     def steps(self, trajectory=0):
         """(t, y) of every accepted step of ONE trajectory (row 0 = its initial condition): the reference's `a.t`,
@@ -901,8 +934,8 @@ class OdeSystem(object):
             a.fresh, a.t_init, a.dt_init = 1, self.t0, self._initial_dt()
             a.counters = self._counters.data_ptr()
             ha.host_y0, ha.host_y = self._y0.data_ptr(), self._raw_y.data_ptr()
-            ha.host_accepted, ha.host_rejected, ha.host_status = (self._raw_accepted.data_ptr(), self._raw_rejected.data_ptr(),
-                                                                  self._raw_status.data_ptr())
+            ha.host_accepted, ha.host_rejected = self._raw_accepted.data_ptr(), self._raw_rejected.data_ptr()
+            ha.host_status = self._host_status_buffer.data_ptr() if self._host_status_buffer is not None else None
             ha.host_stride, ha.chunk_shift = n, shift
             ha.flags = self._pipe_flags.data_ptr()
             ha.stream_up, ha.stream_down = up.cuda_stream, down.cuda_stream
@@ -913,6 +946,8 @@ class OdeSystem(object):
                 c = self._counters.cpu()                      # synchronises `cur`, which waited for the download stream
                 if int(c[6]):
                     raise RuntimeError("dsb_erk_run_host: the kernel timed out waiting for its initial states")
+                self._raw_status = self._host_status_buffer
+                self._host_status_clean = int(c[4]) + int(c[5]) == 0
                 return int(c[2]), int(c[3]), int(c[4]), int(c[5])
             self.host_pipeline = "chunked"                    # driver without stream memory operations
         for st in (up, comp0, comp1):
@@ -951,12 +986,15 @@ class OdeSystem(object):
                     self._raw_y[d, lo:hi].copy_(self._dev_y[d, lo:hi], non_blocking=True)
                 self._raw_accepted[lo:hi].copy_(self._dev_accepted[lo:hi], non_blocking=True)
                 self._raw_rejected[lo:hi].copy_(self._dev_rejected[lo:hi], non_blocking=True)
-                self._raw_status[lo:hi].copy_(self._dev_status[lo:hi], non_blocking=True)
+                if self._host_status_buffer is not None:
+                    self._host_status_buffer[lo:hi].copy_(self._dev_status[lo:hi], non_blocking=True)
         for st in (down, comp0, comp1):
             cur.wait_stream(st)
         self._keepalive = params
         self._pristine = False
         c = self._counters.cpu().reshape(-1, 8)[:chunks]          # synchronises: every copy above has landed
+        self._raw_status = self._host_status_buffer
+        self._host_status_clean = int(c[:, 4].sum()) + int(c[:, 5].sum()) == 0
         return int(c[:, 2].sum()), int(c[:, 3].sum()), int(c[:, 4].sum()), int(c[:, 5].sum())
 
     def _fused_stats(self):
@@ -1489,20 +1527,17 @@ class OdeSystem(object):
                 return StateTuple(t=t_rows[index], y=y_rows[index], event=None)
             if isinstance(index, slice):
                 # the reference slices by TIME (:1170-1183): start / stop are times, located by bisection
-                t_host = t_rows.cpu().numpy()
-                asc = rows < 2 or t_host[-1] >= t_host[0]
-
-                def locate(tv):
-                    arr = t_host if asc else -t_host
-                    return int(min(max(np.searchsorted(arr, float(tv) if asc else -float(tv), side="right") - 1, 0), rows - 1))
-                lo = locate(index.start) if index.start is not None else 0
-                hi = locate(index.stop) + 1 if index.stop is not None else rows
+                lo = self._locate_step(t_rows, index.start) if index.start is not None else 0
+                hi = self._locate_step(t_rows, index.stop) + 1 if index.stop is not None else rows
                 step = index.step if index.step is not None else 1
                 return StateTuple(t=t_rows[lo:hi:step], y=y_rows[lo:hi:step], event=None)
             if self.__dense_output and self._node_store is not None:
                 return StateTuple(t=index, y=self.sol(index), event=None)
-            # nearest stored step (:1187-1196)
-            k = int(torch.argmin(torch.abs(t_rows - float(index))).item())
+            # "nearest" stored step exactly as the reference picks it (:1187-1196): the first row at or after the time,
+            # unless the row after it is strictly closer
+            k = self._locate_step(t_rows, index)
+            if k < rows - 1 and not abs(float(t_rows[k]) - float(index)) < abs(float(t_rows[k + 1]) - float(index)):
+                k += 1
             return StateTuple(t=t_rows[k], y=y_rows[k], event=None)
         if isinstance(index, int):
             if index >= len(self._hist_y) or index < -len(self._hist_y):

@@ -37,6 +37,34 @@ def local_count(n_global, rank, world_size):
     return (n_global - rank + world_size - 1) // world_size
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pins this process (and therefore the pinned host buffers it allocates afterwards: first-touch placement) to the
+    CPUs of the NUMA node the GPU hangs off.  With one process per GPU streaming host-resident ensembles through its
+    own GPU (OdeSystem(host_io=True)), eight ranks otherwise share whatever node they were started on.  Returns the node
+    (or None if the topology cannot be read)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(int(device_index))).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus[-12:].lower()
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 _comms = {}
 
 
@@ -263,9 +291,9 @@ class ShardedEnsemble:
         device barrier (the all-reduce already enqueued behind every rank's kernel)."""
         s = self.system
         if self.scatter is not None:
-            _ = self.statistics                    # every rank's kernel has finished once the all-reduce has
-            if self.world_size > 1:
-                dist.barrier(group=self.group)
+            # the all-reduce sits behind every rank's kernel, so once it has completed here every peer's stores have
+            # been issued and flushed (kernel boundary): no further barrier
+            _ = self.statistics
             out = self.scatter.result()
             if out is not None:
                 out["y"] = out["y"].reshape(tuple(s.dim) + (self.n_global,))

@@ -72,7 +72,9 @@ def linear(t, y, A=None, out=None):
         from .backend import cuda_backend as cb
         res = cb.dgemm(A, y, out=out if (out is not None and out.is_contiguous()) else None)
         if res is not None:
+            linear.calls_dsb += 1
             return res
+    linear.calls_library += 1
     if out is not None and type(y).__module__.split(".")[0] == "torch" and out.is_contiguous():
         import torch
         return torch.matmul(A, y, out=out)
@@ -80,6 +82,8 @@ def linear(t, y, A=None, out=None):
 
 
 linear.use_library_gemm = False
+linear.calls_dsb = 0              # products served by dsb_dgemm / by the array library (CUDA-graph replays are not
+linear.calls_library = 0          # re-counted: what matters is which kernel a captured attempt contains)
 linear.supports_out = True        # rhs(t, y, out=array, **constants) writes the derivative into a caller-owned array
 
 

@@ -197,7 +197,9 @@ typedef struct {
     dsb_erk_run_args run;
     const double *host_y0;     /* [dim][host_stride]                                            */
     double *host_y;            /* [dim][host_stride] out                                        */
-    int32_t *host_accepted, *host_rejected, *host_status;   /* [n] out                          */
+    int32_t *host_accepted, *host_rejected, *host_status;   /* [n] out; host_status may be NULL: every status
+                                  is DSB_TRAJ_DONE iff counters[4] + counters[5] == 0, so a caller can skip that
+                                  download and fetch run.status only when a failure is reported               */
     int64_t host_stride;       /* leading dimension of host_y0 / host_y in elements (0: n)      */
     int32_t chunk_shift;       /* chunk = 2^chunk_shift trajectories                            */
     uint32_t *flags;           /* device, >= 1 + ceil(n / 2^chunk_shift) words (zeroed here)    */

@@ -225,6 +225,9 @@ static void erk_attempt(const orc_problem *prob, const orc_rk_tableau *tab, cons
     }
 }
 
+static int g_factor_ulps = 0;
+void orc_set_factor_perturbation(int ulps) { g_factor_ulps = ulps; }
+
 /* update_timestep (integrator_template.py:46-93).  attempt_no = 0 for the first attempt of a
  * step.  eps_last/eps_last_last carry the retry-chain history.  Returns the factor. */
 static double erk_controller(erk_work *w, const double *y, double h, double rtol, double atol,
@@ -254,7 +257,12 @@ static double erk_controller(erk_work *w, const double *y, double h, double rtol
         corr = corr * (k3 > 0.0 ? k3 : 1.0);
         *eps_last_last = *eps_last; *eps_last = eps_cur;
     }
-    return 1.0 + atan(0.8 * corr - 1.0);
+    double factor = 1.0 + atan(0.8 * corr - 1.0);
+    /* test knob (orc_set_factor_perturbation): nudge the step-size factor by a few ulps -- the size of the
+     * difference between two correctly-behaving libm's -- to measure how far chaos carries it */
+    for (int u = 0; u < (g_factor_ulps < 0 ? -g_factor_ulps : g_factor_ulps); ++u)
+        factor = nextafter(factor, g_factor_ulps > 0 ? INFINITY : -INFINITY);
+    return factor;
 }
 
 static int tableau_is_fsal(const orc_rk_tableau *tab)

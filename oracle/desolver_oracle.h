@@ -108,6 +108,11 @@ void orc_dense_eval(const orc_dense *dense, int dim, double tq, double *out);
 /* Plain RHS evaluation (exposed for tests). */
 void orc_rhs(const orc_problem *prob, const double *params, double t, const double *y, double *dy);
 
+/* Test knob: every step-size factor the controller returns is moved by `ulps` units in the last place (0 = off).
+ * Used by tests/test_oracle_golden.py to show that the parity tail (a handful of 2^20 chaotic trajectories beyond
+ * 1e-10) is the amplification of last-ulp differences, not an arithmetic error.  Not thread-safe: set it between runs. */
+void orc_set_factor_perturbation(int ulps);
+
 #ifdef __cplusplus
 }
 #endif

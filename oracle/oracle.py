@@ -74,6 +74,8 @@ def load():
         lib.orc_hermite_eval.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, C.c_double, _dp]
         lib.orc_dense_eval.restype = None
         lib.orc_dense_eval.argtypes = [C.POINTER(_Dense), C.c_int, C.c_double, _dp]
+        lib.orc_set_factor_perturbation.restype = None
+        lib.orc_set_factor_perturbation.argtypes = [C.c_int]
         lib.orc_rhs.restype = None
         lib.orc_rhs.argtypes = [C.POINTER(_Problem), _dp, C.c_double, _dp, _dp]
         _lib = lib
@@ -244,3 +246,8 @@ def hermite(t0, t1, p0, p1, m0, m1, tq):
     load().orc_hermite_eval(p0.size, float(t0), float(t1), _ptr(p0), _ptr(p1), _ptr(m0), _ptr(m1),
                             float(tq), _ptr(out))
     return out
+
+
+def set_factor_perturbation(ulps):
+    """Test knob of the C oracle: move every step-size factor by `ulps` units in the last place (0 = off)."""
+    load().orc_set_factor_perturbation(int(ulps))
