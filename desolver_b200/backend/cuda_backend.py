@@ -16,7 +16,8 @@ ABI_VERSION = 3
 DSB_OK, DSB_ERR_BAD_ARGUMENT, DSB_ERR_CUDA, DSB_ERR_UNSUPPORTED, DSB_ERR_NCCL = 0, 1, 2, 3, 4
 COMM_ID_BYTES, IPC_HANDLE_BYTES = 128, 64
 TRAJ_DONE, TRAJ_TOL_FAIL, TRAJ_RUNNING, TRAJ_EVENT = 0, 1, 2, 3
-MAX_EVENTS = 4
+MAX_EVENTS = 4            # fused kernels
+MAX_STAGE_EVENTS = 16     # stage-level kernels
 FLAG_STRICT = 1
 MAX_PARAMS = 6
 FUSED_STAGES = (1, 2, 4, 6, 7, 13, 17)
@@ -63,6 +64,16 @@ class ErkRunArgs(C.Structure):
         ("out_y", C.c_void_p), ("out_t", C.c_void_p), ("out_dt", C.c_void_p),
         ("out_accepted", C.c_void_p), ("out_rejected", C.c_void_p), ("out_status", C.c_void_p),
         ("out_stride", C.c_int64), ("out_index_mul", C.c_int64), ("out_index_add", C.c_int64),
+    ]
+
+
+class EventSearchStruct(C.Structure):
+    """dsb_event_search (include/desolver_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64), ("n_events", C.c_int32),
+        ("lo", C.c_void_p), ("hi", C.c_void_p), ("flo", C.c_void_p), ("fhi", C.c_void_p),
+        ("x", C.c_void_p), ("tq", C.c_void_p), ("side", C.c_void_p),
+        ("t0", C.c_void_p), ("t1", C.c_void_p), ("counter", C.c_void_p),
     ]
 
 
@@ -214,6 +225,15 @@ def lib():
     L.dsb_erk_stage_finish_events.argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_int, C.c_void_p, C.c_void_p]
     L.dsb_erk_stage_launches.restype = C.c_int
     L.dsb_erk_stage_launches.argtypes = [C.c_void_p]
+    L.dsb_erk_stage_finish_events_located.restype = C.c_int
+    L.dsb_erk_stage_finish_events_located.argtypes = [C.c_void_p, C.POINTER(ErkStageArgs), C.c_void_p, C.c_void_p, C.c_void_p]
+    es = C.POINTER(EventSearchStruct)
+    L.dsb_event_search_begin.restype = C.c_int
+    L.dsb_event_search_begin.argtypes = [es, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.dsb_event_search_step.restype = C.c_int
+    L.dsb_event_search_step.argtypes = [es, C.c_void_p, C.c_void_p]
+    L.dsb_event_search_roots.restype = C.c_int
+    L.dsb_event_search_roots.argtypes = [es, C.c_void_p, C.c_void_p]
     L.dsb_symp_create.restype = C.c_int
     L.dsb_symp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_uint]
     L.dsb_symp_destroy.restype = C.c_int
@@ -226,6 +246,9 @@ def lib():
     L.dsb_symp_stage_accumulate.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p]
     L.dsb_symp_stage_commit_events.restype = C.c_int
     L.dsb_symp_stage_commit_events.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dsb_symp_stage_commit_events_located.restype = C.c_int
+    L.dsb_symp_stage_commit_events_located.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                       C.c_void_p]
     L.dsb_symp_stage_commit.restype = C.c_int
     L.dsb_symp_stage_commit.argtypes = [C.c_void_p, C.POINTER(SympStageArgs), C.c_void_p]
     # collectives and peer buffers (ABI 3)
@@ -338,6 +361,10 @@ class ErkHandle:
         check(lib().dsb_erk_stage_finish_events(self._h, C.byref(args), int(phase), f1_ptr, stream_ptr),
               "dsb_erk_stage_finish_events")
 
+    def stage_finish_events_located(self, args, f1_ptr, roots_ptr, stream_ptr):
+        check(lib().dsb_erk_stage_finish_events_located(self._h, C.byref(args), f1_ptr, roots_ptr, stream_ptr),
+              "dsb_erk_stage_finish_events_located")
+
     @property
     def stage_launches(self):
         return lib().dsb_erk_stage_launches(self._h)
@@ -393,6 +420,10 @@ class SympHandle:
 
     def stage_commit(self, args, stream_ptr):
         check(lib().dsb_symp_stage_commit(self._h, C.byref(args), stream_ptr), "dsb_symp_stage_commit")
+
+    def stage_commit_events_located(self, args, f0_ptr, f1_ptr, roots_ptr, stream_ptr):
+        check(lib().dsb_symp_stage_commit_events_located(self._h, C.byref(args), f0_ptr, f1_ptr, roots_ptr, stream_ptr),
+              "dsb_symp_stage_commit_events_located")
 
     def stage_commit_events(self, args, phase, f0_ptr, f1_ptr, stream_ptr):
         check(lib().dsb_symp_stage_commit_events(self._h, C.byref(args), int(phase), f0_ptr, f1_ptr, stream_ptr),

@@ -24,7 +24,8 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream);
 int stage_begin(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int first_call, cudaStream_t stream);
 int stage_state(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int stage, cudaStream_t stream);
 int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_t stream);
-int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int phase, const double *f1, cudaStream_t stream);
+int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int phase, const double *f1, const double *roots,
+                        cudaStream_t stream);
 
 }  // namespace dsb
 
@@ -216,7 +217,15 @@ int dsb_erk_stage_finish_events(dsb_erk_handle h, const dsb_erk_stage_args *a, i
 {
     if (!h) { set_error("dsb_erk_stage_finish_events: null handle"); return DSB_ERR_BAD_ARGUMENT; }
     DeviceGuard guard(h->device);
-    return stage_finish_events(h, a, phase, f1, (cudaStream_t)stream);
+    return stage_finish_events(h, a, phase, f1, nullptr, (cudaStream_t)stream);
+}
+
+int dsb_erk_stage_finish_events_located(dsb_erk_handle h, const dsb_erk_stage_args *a, const double *f1, const double *roots,
+                                        void *stream)
+{
+    if (!h || !roots) { set_error("dsb_erk_stage_finish_events_located: null handle or roots"); return DSB_ERR_BAD_ARGUMENT; }
+    DeviceGuard guard(h->device);
+    return stage_finish_events(h, a, 1, f1, roots, (cudaStream_t)stream);
 }
 
 int dsb_erk_stage_launches(dsb_erk_handle h) { return h ? 1 + h->stages + 3 : 0; }

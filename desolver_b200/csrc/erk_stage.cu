@@ -18,7 +18,7 @@ namespace dsb {
 
 constexpr int FLAG_ACTIVE = 1, FLAG_FINAL = 2, FLAG_ACCEPTED = 4;
 constexpr int FLAG_FINAL_LEG = 8;      // re-integration to the root of a terminal event in progress (events are off)
-constexpr int EV_NE = DSB_MAX_EVENTS;  // ev_state rows: 0 t_prev, 1 dt_prev, 2.. last occurrence per event, 2+NE.. g per event
+constexpr int EV_NE = DSB_MAX_STAGE_EVENTS;  // ev_state rows: 0 t_prev, 1 dt_prev, 2.. last occurrence per event, 2+NE.. g per event
 
 __device__ __forceinline__ double tf_of(const dsb_erk_stage_args &a, long long i) { return a.tf_per ? a.tf_per[i] : a.tf; }
 
@@ -409,7 +409,10 @@ __global__ void stage_y1_kernel(dsb_erk_stage_args a)
 
 // ---- events, phase 1: locate / record / terminal roll-back, one thread per trajectory.  The same algorithm as the
 // event block of the fused kernel (erk_fused.cuh): differential_system.py:29-57, 60-167, 1020-1066. -------------------
-__global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restrict__ k0, const double *__restrict__ f1)
+// ext_roots != nullptr: the roots were located by the caller (dsb_event_search_*, any event callable): [n_events][n]
+// event times, NaN = no event of that kind in this step; the polynomial solve is skipped.
+__global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restrict__ k0, const double *__restrict__ f1,
+                                    const double *__restrict__ ext_roots)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -426,7 +429,12 @@ __global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restri
     // formed from the step's own data (p0, m0 = K[0]) -- what the reference's root finder evaluates at t_prev.
     double pc[EV_NE][4];                      // G(tau) = pc0 + pc1 tau + pc2 tau^2 + pc3 tau^3
     unsigned mask = 0;
-    for (int e = 0; e < ne; ++e) {
+    if (ext_roots)
+        for (int e = 0; e < ne; ++e) {
+            const double r = ext_roots[(long long)e * n + i];
+            if (r == r) mask |= 1u << e;
+        }
+    for (int e = 0; e < ne && !ext_roots; ++e) {
         const double *w = a.ev_coef + (long long)e * W;
         const double *wd = a.ev_coef_dy ? a.ev_coef_dy + (long long)e * D : nullptr;
         double gy0 = w[D] * t0 - w[D + 1], gy1 = w[D] * t1 - w[D + 1], dg0 = w[D], dg1 = w[D];
@@ -464,6 +472,12 @@ __global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restri
     int which[EV_NE], cnt = 0;
     for (int e = 0; e < ne; ++e) {
         if (!(mask >> e & 1u)) continue;
+        if (ext_roots) {
+            root[cnt] = ext_roots[(long long)e * n + i];
+            which[cnt] = e;
+            cnt++;
+            continue;
+        }
         const double c0 = pc[e][0], c1 = pc[e][1], c2 = pc[e][2], c3 = pc[e][3];
         const double g0 = c0, g1 = ((c3 + c2) + c1) + c0;
         double lo = 0.0, hi = 1.0, tau = g0 / (g0 - g1);
@@ -548,9 +562,10 @@ __global__ void stage_events_kernel(dsb_erk_stage_args a, const double *__restri
 static void build_final(const dsb_erk_plan *p, FinalRows &fr);
 
 // the event kernel over any buffers that follow the dsb_erk_stage_args conventions (used by symplectic.cu as well)
-int launch_stage_events(const dsb_erk_stage_args &view, const double *k0, const double *f1, cudaStream_t stream)
+int launch_stage_events(const dsb_erk_stage_args &view, const double *k0, const double *f1, const double *ext_roots,
+                        cudaStream_t stream)
 {
-    stage_events_kernel<<<(unsigned)((view.n + 127) / 128), 128, 0, stream>>>(view, k0, f1);
+    stage_events_kernel<<<(unsigned)((view.n + 127) / 128), 128, 0, stream>>>(view, k0, f1, ext_roots);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
@@ -728,14 +743,15 @@ int stage_finish(const dsb_erk_plan *h, const dsb_erk_stage_args *a, cudaStream_
     return stage_finish_parts(h, a, 3, stream);
 }
 
-int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int phase, const double *f1, cudaStream_t stream)
+int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int phase, const double *f1, const double *roots,
+                        cudaStream_t stream)
 {
     int rc = check_args(h, a, "dsb_erk_stage_finish_events");
     if (rc != DSB_OK) return rc;
-    if (a->n_events < 1 || a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
+    if (a->n_events < 1 || a->n_events > DSB_MAX_STAGE_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
         !a->ev_state || !a->tf_per || a->ev_capacity < 1 || (phase != 0 && phase != 1) || (phase == 1 && !f1) || !a->K[0]) {
         set_error("dsb_erk_stage_finish_events: needs 1..%d events with ev_coef, ev_flags, ev_records, ev_count, ev_state, "
-                  "tf_per, ev_capacity >= 1, K[0], phase 0 or 1, and f1 in phase 1", DSB_MAX_EVENTS);
+                  "tf_per, ev_capacity >= 1, K[0], phase 0 or 1, and f1 in phase 1", DSB_MAX_STAGE_EVENTS);
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;
@@ -744,7 +760,7 @@ int stage_finish_events(const dsb_erk_plan *h, const dsb_erk_stage_args *a, int 
         if (rc != DSB_OK) return rc;
         stage_y1_kernel<<<grid_for((long long)a->dim * a->n, 256, h->sm_count), 256, 0, stream>>>(*a);
     } else {
-        stage_events_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, stream>>>(*a, a->K[0], f1);
+        stage_events_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, stream>>>(*a, a->K[0], f1, roots);
         DSB_CUDA_CHECK(cudaGetLastError());
         return stage_finish_parts(h, a, 2, stream);
     }

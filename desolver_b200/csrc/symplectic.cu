@@ -158,7 +158,8 @@ constexpr int SFLAG_ACTIVE = 1;
 constexpr int SFLAG_STEPPED = 4;       // took a step in the commit just done (mask of dsb_dense_append); cleared by begin
 constexpr int SFLAG_FINAL_LEG = 8;     // re-integration to the root of a terminal event (same bit as in erk_stage.cu)
 
-int launch_stage_events(const dsb_erk_stage_args &view, const double *k0, const double *f1, cudaStream_t stream);
+int launch_stage_events(const dsb_erk_stage_args &view, const double *k0, const double *f1, const double *ext_roots,
+                        cudaStream_t stream);
 
 __device__ __forceinline__ double symp_tf(const dsb_symp_stage_args &a, long long i) { return a.tf_per ? a.tf_per[i] : a.tf; }
 
@@ -180,7 +181,7 @@ __global__ void symp_begin_kernel(dsb_symp_stage_args a, int first_call)
                 for (int d = 0; d < a.dim; ++d)
                     if (w[d] != 0.0) g = fma(w[d], a.y[(long long)d * a.n + i], g);
                 a.ev_state[(long long)(2 + e) * a.n + i] = CUDART_NAN;
-                a.ev_state[(long long)(2 + DSB_MAX_EVENTS + e) * a.n + i] = g;
+                a.ev_state[(long long)(2 + DSB_MAX_STAGE_EVENTS + e) * a.n + i] = g;
             }
         }
         if (fabs(span) < DSB_EPS4) go = false;
@@ -368,16 +369,32 @@ int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *a, void 
     return DSB_OK;
 }
 
+static int symp_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a, int phase, const double *f0, const double *f1,
+                              const double *roots, void *stream);
+
 int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a, int phase, const double *f0,
                                  const double *f1, void *stream)
 {
+    return symp_commit_events(h, a, phase, f0, f1, nullptr, stream);
+}
+
+int dsb_symp_stage_commit_events_located(dsb_symp_handle h, const dsb_symp_stage_args *a, const double *f0, const double *f1,
+                                         const double *roots, void *stream)
+{
+    if (!roots) { set_error("dsb_symp_stage_commit_events_located: null roots"); return DSB_ERR_BAD_ARGUMENT; }
+    return symp_commit_events(h, a, 1, f0, f1, roots, stream);
+}
+
+static int symp_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a, int phase, const double *f0, const double *f1,
+                              const double *roots, void *stream)
+{
     int rc = symp_check(h, a, "dsb_symp_stage_commit_events");
     if (rc != DSB_OK) return rc;
-    if (a->n_events < 1 || a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
+    if (a->n_events < 1 || a->n_events > DSB_MAX_STAGE_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
         !a->ev_state || !a->tf_per || !a->ev_scratch || a->ev_capacity < 1 || (phase != 0 && phase != 1) ||
         (phase == 1 && (!f0 || !f1))) {
         set_error("dsb_symp_stage_commit_events: needs 1..%d events with all ev_* buffers, tf_per, phase 0 or 1, and f0, f1 in "
-                  "phase 1", DSB_MAX_EVENTS);
+                  "phase 1", DSB_MAX_STAGE_EVENTS);
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (a->n == 0) return DSB_OK;
@@ -398,7 +415,7 @@ int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a
     v.n_events = a->n_events; v.ev_capacity = a->ev_capacity; v.ev_coef = a->ev_coef; v.ev_flags = a->ev_flags;
     v.ev_records = a->ev_records; v.ev_count = a->ev_count; v.ev_state = a->ev_state; v.tf_per = a->tf_per;
     v.ev_coef_dy = a->ev_coef_dy;
-    rc = launch_stage_events(v, f0, f1, st);
+    rc = launch_stage_events(v, f0, f1, roots, st);
     if (rc != DSB_OK) return rc;
     const int grid = grid_for((long long)a->dim * a->n, 256, h->sm_count);
     if (h->flags & DSB_FLAG_STRICT) symp_commit_kernel<true, SFLAG_STEPPED><<<grid, 256, 0, st>>>(*a);

@@ -783,14 +783,15 @@ class OdeSystem(object):
         coef = torch.as_tensor(np.stack([ev.coefficients(self.numel) for ev in events]), dtype=torch.float64).to(self.device)
         flags = torch.as_tensor([ev.flags for ev in events], dtype=torch.int32).to(self.device)
         self._event_coef_dy = None
-        if any(ev.requires_dstate for ev in events):          # weights on dState/dt (stage-level kernels only)
+        if any(ev.requires_dstate and hasattr(ev, "w") for ev in events):          # weights on dState/dt
             self._event_coef_dy = torch.as_tensor(np.stack([ev.dy_coefficients(self.numel) for ev in events]),
                                                   dtype=torch.float64).to(self.device)
         # the log accumulates over integrate() calls like the reference's `self.__events` (:1043-1048); it is only
         # re-created when the SET of events changes -- compared by value (coefficients, flags), because a plain
         # callable is converted to a new HyperplaneEvent object on every call
-        signature = tuple((tuple(ev.coefficients(self.numel).tolist()), tuple(ev.dy_coefficients(self.numel).tolist()),
-                           int(ev.flags)) for ev in events)
+        signature = tuple(ev.signature if hasattr(ev, "signature") else
+                          (tuple(ev.coefficients(self.numel).tolist()), tuple(ev.dy_coefficients(self.numel).tolist()), int(ev.flags))
+                          for ev in events)
         if self._event_log is None or self._event_log.compiled != signature:
             records = torch.zeros((self.n_traj, int(self.event_capacity), self.numel + 2), dtype=torch.float64, device=self.device)
             count = torch.zeros(self.n_traj, dtype=torch.int32, device=self.device)
@@ -1055,11 +1056,12 @@ class OdeSystem(object):
             k_out = cache
         work, buf, m, index, consts = full, alloc(n), n, None, self.__consts
         a, y_view, t_view = bind(work, buf, m)
+        search = None
         if events:
             # device event detection around any right-hand side (dsb_erk_stage_finish_events): per-trajectory final
             # times (a terminal event re-targets its trajectory), scratch state, and the record store of the log
             coef, flags = self._event_tensors(events)
-            ev_state = torch.zeros((2 + 2 * cb.MAX_EVENTS, n), **f64)
+            ev_state = torch.zeros((2 + 2 * cb.MAX_STAGE_EVENTS, n), **f64)
             tf_per = torch.full((n,), float(tf), **f64)
             a.n_events, a.ev_capacity = len(events), self._event_log.capacity
             a.ev_coef, a.ev_flags = coef.data_ptr(), flags.data_ptr()
@@ -1068,6 +1070,14 @@ class OdeSystem(object):
             if self._event_coef_dy is not None:
                 a.ev_coef_dy = self._event_coef_dy.data_ptr()
             self._keepalive = (coef, flags, ev_state, tf_per)      # referenced by raw pointer until the run has finished
+            if any(not hasattr(ev, "w") for ev in events):
+                # arbitrary event callables: their values come from the caller's code between the event-search kernels
+                from .events import EventSearch
+                search = self._event_search = EventSearch(self, events, self.__consts)
+                f_start = None
+                if search.needs_dy:
+                    f_start = self.equ_rhs(self._user_time(self._t), self._user_shape(self._y), **self.__consts).to(torch.float64).reshape(D, n).contiguous()
+                search.start(self._t, self._y, f_start)
         can_compact = self.ensemble and self.compaction and not callbacks and not dense and not events
         K = [None] * S
         y_committed = self._user_shape(self._y)
@@ -1121,7 +1131,12 @@ class OdeSystem(object):
                 f1 = f1 if f1.is_contiguous() else f1.contiguous()
                 K.append(f1)                                           # keep alive until the attempt finishes
                 del K[S:-1]
-                handle.stage_finish_events(a, 1, f1.data_ptr(), st)
+                if search is not None:
+                    roots = search.locate(buf["flags"], 4, 8, ev_state[0], work["t"], work["y"], buf["y_stage"], K[0], f1)
+                    handle.stage_finish_events_located(a, f1.data_ptr(), roots.data_ptr(), st)
+                    search.advance(buf["flags"], 4)
+                else:
+                    handle.stage_finish_events(a, 1, f1.data_ptr(), st)
             else:
                 handle.stage_finish(a, st)
             if dense:
@@ -1131,8 +1146,8 @@ class OdeSystem(object):
             """One attempt as a CUDA graph: replaying it costs one launch instead of ~S*(1 + RHS kernels) + 4, which
             is what bounds small and medium ensembles.  A right-hand side that is not capture-safe (host
             synchronisation, CPU work) keeps the eager loop."""
-            if not self.use_graphs or callbacks:     # callbacks may rebind the system's tensors (e.g. ode_sys.dt = ...)
-                return None
+            if not self.use_graphs or callbacks or search is not None:     # callbacks may rebind the system's tensors
+                return None                                                # (e.g. ode_sys.dt = ...); the event search looks at the device
             try:
                 g = torch.cuda.CUDAGraph()
                 nfev0, rows0 = self.equ_rhs.nfev, self._rows_used
@@ -1262,9 +1277,10 @@ class OdeSystem(object):
         y_view = self._user_shape(buf["y_stage"])
         t_view = self._user_time(buf["t_stage"])
         first, steps = True, 0
+        search = None
         if events:
             coef, flags = self._event_tensors(events)
-            ev_state = torch.zeros((2 + 2 * cb.MAX_EVENTS, n), **f64)
+            ev_state = torch.zeros((2 + 2 * cb.MAX_STAGE_EVENTS, n), **f64)
             tf_per = torch.full((n,), float(tf), **f64)
             scratch = torch.zeros(n, dtype=torch.int32, device=dev)
             a.n_events, a.ev_capacity = len(events), self._event_log.capacity
@@ -1274,6 +1290,13 @@ class OdeSystem(object):
             if self._event_coef_dy is not None:
                 a.ev_coef_dy = self._event_coef_dy.data_ptr()
             self._keepalive = (coef, flags, ev_state, tf_per, scratch)   # referenced by raw pointer until the run has finished
+            if any(not hasattr(ev, "w") for ev in events):
+                from .events import EventSearch
+                search = self._event_search = EventSearch(self, events, self.__consts)
+                f_start = None
+                if search.needs_dy:
+                    f_start = self.equ_rhs(self._user_time(self._t), self._user_shape(self._y), **self.__consts).to(torch.float64).reshape(D, n).contiguous()
+                search.start(self._t, self._y, f_start)
 
         store = self._ensure_node_store("rows", need=2) if self._want_nodes else None
         dense = store is not None
@@ -1310,7 +1333,12 @@ class OdeSystem(object):
                 handle.stage_commit_events(a, 0, None, None, st)
                 f1 = self.equ_rhs(t_view, y_view, **self.__consts).to(torch.float64).reshape(D, n)
                 keep_f[0] = f1 if f1.is_contiguous() else f1.contiguous()
-                handle.stage_commit_events(a, 1, keep[0].data_ptr(), keep_f[0].data_ptr(), st)
+                if search is not None:
+                    roots = search.locate(buf["flags"], 4, 8, ev_state[0], self._t, self._y, buf["y_stage"], keep[0], keep_f[0])
+                    handle.stage_commit_events_located(a, keep[0].data_ptr(), keep_f[0].data_ptr(), roots.data_ptr(), st)
+                    search.advance(buf["flags"], 4)
+                else:
+                    handle.stage_commit_events(a, 1, keep[0].data_ptr(), keep_f[0].data_ptr(), st)
             else:
                 handle.stage_commit(a, st)
             if dense:
@@ -1320,7 +1348,7 @@ class OdeSystem(object):
         graph, regraph = None, False
 
         def capture_step():
-            if not self.use_graphs or callbacks:             # same CUDA-graph replay as the explicit-RK stage path
+            if not self.use_graphs or callbacks or search is not None:     # same CUDA-graph replay as the explicit-RK stage path
                 return None
             try:
                 g = torch.cuda.CUDAGraph()
@@ -1382,13 +1410,18 @@ class OdeSystem(object):
         torch = _torch()
         user_events = None
         if events is not None:
-            from .events import as_hyperplane
+            from .events import as_hyperplane, CallableEvent
             user_events = [events] if callable(events) and not isinstance(events, (list, tuple)) else list(events)
-            if len(user_events) > cb.MAX_EVENTS:
-                raise NotImplementedError("at most %d events per integrate() call" % cb.MAX_EVENTS)
-            # the device detects affine event functions g(t, y) = w.y + wt*t - c; an ordinary Python callable of that
-            # form (t - t_mark, y[0] - level, ...) is recognised by probing it, anything else raises
-            events = [as_hyperplane(ev, self.numel, self.__consts) for ev in user_events]
+            if len(user_events) > cb.MAX_STAGE_EVENTS:
+                raise NotImplementedError("at most %d events per integrate() call" % cb.MAX_STAGE_EVENTS)
+            # Affine event functions g(t, y[, dy]) = w.y + w_dy.dy + wt*t - c -- HyperplaneEvent objects, or ordinary
+            # callables of that form (t - t_mark, y[0] - level, ...: recognised by probing) -- are located in closed form
+            # inside the step kernels.  ANY other callable (a radius, a product, per-trajectory constants) is evaluated by
+            # the caller's own code between the event-search kernels (events.EventSearch), on the stage-level path.
+            try:
+                events = [as_hyperplane(ev, self.numel, self.__consts) for ev in user_events]
+            except NotImplementedError:
+                events = [ev if isinstance(ev, CallableEvent) else CallableEvent(ev) for ev in user_events]
             if not events:
                 events = user_events = None
         tf = float(t) if t is not None else self.__tf
@@ -1405,10 +1438,11 @@ class OdeSystem(object):
         try:
             if self.host_io and (plugin is None or self.integrator.symplectic):
                 raise NotImplementedError("host_io=True needs an explicit Runge-Kutta method with a fused kernel")
-            if events and (self.host_io or callbacks or eta):
-                raise NotImplementedError("device event detection needs device-resident state and no callbacks / progress "
-                                          "bar in the same call")
-            if events and plugin is not None and (self.integrator.stages > 7 or self._want_nodes):
+            if events and self.host_io:
+                raise NotImplementedError("device event detection needs device-resident state (host_io=False)")
+            general_events = bool(events) and any(not hasattr(ev, "w") for ev in events)
+            if events and plugin is not None and (self.integrator.stages > 7 or self._want_nodes or general_events
+                                                  or len(events) > cb.MAX_EVENTS or callbacks or eta):
                 # the event-detecting fused kernels stop at 7 stages and write no nodes: a system that records dense
                 # output or its step history next to events runs on the stage-level kernels
                 plugin = None

@@ -18,7 +18,8 @@ time marks) are all of this form.
 """
 import numpy as np
 
-__all__ = ["HyperplaneEvent", "as_hyperplane", "component_crossing", "component_extremum", "EventLog"]
+__all__ = ["HyperplaneEvent", "CallableEvent", "EventSearch", "as_hyperplane", "component_crossing", "component_extremum",
+           "EventLog"]
 
 
 class HyperplaneEvent(object):
@@ -94,6 +95,135 @@ class HyperplaneEvent(object):
 
     def __repr__(self):
         return "<HyperplaneEvent %s direction=%d terminal=%s>" % (self.name, self.direction, self.is_terminal)
+
+
+class CallableEvent(object):
+    """ANY event callable of the reference's protocol, `event(t, y[, dy], **constants)` with the optional attributes
+    `is_terminal`, `direction`, `requires_dstate` (differential_system.py:29-57).  It is evaluated by the caller's own
+    (torch) code, batched over the ensemble: `t` is 0-d and `y` (*dim) for a single system, `t` (N,) and `y` (*dim, N) for
+    an ensemble -- and per-trajectory constants arrive exactly as the right-hand side receives them.  The root search
+    runs in the event-search kernels (include/desolver_b200.h, dsb_event_search_*) with the callable between them."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.direction = int(np.sign(getattr(fn, "direction", 0)))
+        self.is_terminal = bool(getattr(fn, "is_terminal", False))
+        self.requires_dstate = bool(getattr(fn, "requires_dstate", False))
+        self.name = getattr(fn, "__name__", repr(fn))
+        self.source = fn
+
+    def __call__(self, t, y, *args, **constants):
+        return self.fn(t, y, *args, **constants)
+
+    def coefficients(self, dim):
+        return np.zeros(dim + 2)
+
+    def dy_coefficients(self, dim):
+        return np.zeros(dim)
+
+    @property
+    def flags(self):
+        return (1 if self.direction > 0 else (2 if self.direction < 0 else 0)) | (4 if self.is_terminal else 0)
+
+    @property
+    def signature(self):
+        return ("callable", id(self.fn), self.flags, self.requires_dstate)
+
+    def __repr__(self):
+        return "<CallableEvent %s direction=%d terminal=%s>" % (self.name, self.direction, self.is_terminal)
+
+
+class EventSearch(object):
+    """Per-attempt driver of the event-search kernels for a stage-level run with arbitrary event callables.
+
+    g at the start of a step is carried over from the end of the previous accepted step (`g0`); after an attempt
+    `locate()` evaluates every event at the attempt's end state, brackets sign changes over the accepted steps, runs the
+    Illinois iteration (`dsb_event_search_step`) with the callables evaluated on the step's cubic Hermite interpolant
+    (`dsb_hermite_eval`) in between, and returns the [n_events][n] root times for the event kernel's record / order /
+    terminal logic."""
+
+    MAX_ITERATIONS = 64
+
+    def __init__(self, system, events, consts):
+        import torch
+        from .backend import cuda_backend as cb
+        self.sys, self.events, self.consts = system, list(events), consts
+        n, E, dev = system.n_traj, len(events), system.device
+        self.n, self.E, self.dev = n, E, dev
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.buf = {k: torch.zeros((E, n), **f64) for k in ("lo", "hi", "flo", "fhi", "x", "tq", "fx", "g0", "g1", "roots")}
+        self.side = torch.zeros((E, n), dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ev_flags = torch.as_tensor([ev.flags for ev in events], dtype=torch.int32).to(dev)
+        self.needs_dy = any(ev.requires_dstate for ev in events)
+        self.yq = torch.empty((system.numel, n), **f64)
+        self.dq = torch.empty((system.numel, n), **f64) if self.needs_dy else None
+        self.iterations = 0
+        self.searches = 0
+        self._cb = cb
+
+    def _call(self, ev, t_flat, y_flat, dy_flat):
+        import torch
+        s = self.sys
+        t = s._user_time(t_flat)
+        y = s._user_shape(y_flat)
+        if ev.requires_dstate:
+            g = ev(t, y, s._user_shape(dy_flat), **self.consts)
+        else:
+            g = ev(t, y, **self.consts)
+        g = torch.as_tensor(g, dtype=torch.float64, device=self.dev)
+        return g.reshape(-1).expand(self.n) if g.numel() == 1 else g.reshape(self.n)
+
+    def evaluate(self, out, t_flat, y_flat, dy_flat):
+        for e, ev in enumerate(self.events):
+            out[e].copy_(self._call(ev, t_flat, y_flat, dy_flat))
+
+    def start(self, t_flat, y_flat, rhs_flat):
+        """g of every event at the current state (the start of the first step)."""
+        self.evaluate(self.buf["g0"], t_flat, y_flat, rhs_flat)
+
+    def locate(self, flags, need_mask, skip_mask, t0, t1, p0, p1, m0, m1):
+        """After an attempt: p0 / p1 the states before / after it, m0 / m1 the right-hand sides there, t0 / t1 the times;
+        `flags` the kernels' flag word (need_mask = accepted, skip_mask = final leg).  Returns the roots tensor."""
+        import ctypes as C
+        cb, b = self._cb, self.buf
+        lib, st = cb.lib(), cb.current_stream_ptr(self.dev)
+        self.evaluate(b["g1"], t1, p1, m1)
+        s = cb.EventSearchStruct()
+        s.n, s.n_events = self.n, self.E
+        for k in ("lo", "hi", "flo", "fhi", "x", "tq"):
+            setattr(s, k, b[k].data_ptr())
+        s.side, s.t0, s.t1, s.counter = self.side.data_ptr(), t0.data_ptr(), t1.data_ptr(), self.counter.data_ptr()
+        self.counter.zero_()
+        cb.check(lib.dsb_event_search_begin(C.byref(s), b["g0"].data_ptr(), b["g1"].data_ptr(), flags.data_ptr(), int(need_mask),
+                                            int(skip_mask), self.ev_flags.data_ptr(), st), "dsb_event_search_begin")
+        pending = int(self.counter.item())                    # the one host look per attempt of this mode
+        self.searches += pending
+        it = 0
+        while pending and it < self.MAX_ITERATIONS:
+            for e, ev in enumerate(self.events):
+                tq = b["tq"][e]
+                cb.check(lib.dsb_hermite_eval(t0.data_ptr(), t1.data_ptr(), 1, p0.data_ptr(), p1.data_ptr(), m0.data_ptr(),
+                                              m1.data_ptr(), self.n, self.sys.numel, tq.data_ptr(), 1, self.yq.data_ptr(), 0, st),
+                         "dsb_hermite_eval")
+                if ev.requires_dstate:
+                    cb.check(lib.dsb_hermite_eval(t0.data_ptr(), t1.data_ptr(), 1, p0.data_ptr(), p1.data_ptr(), m0.data_ptr(),
+                                                  m1.data_ptr(), self.n, self.sys.numel, tq.data_ptr(), 1, self.dq.data_ptr(), 1, st),
+                             "dsb_hermite_eval")
+                b["fx"][e].copy_(self._call(ev, tq, self.yq, self.dq))
+            cb.check(lib.dsb_event_search_step(C.byref(s), b["fx"].data_ptr(), st), "dsb_event_search_step")
+            it += 1
+            if it % 4 == 0:
+                pending = int(self.counter.item())
+        self.iterations += it
+        cb.check(lib.dsb_event_search_roots(C.byref(s), b["roots"].data_ptr(), st), "dsb_event_search_roots")
+        return b["roots"]
+
+    def advance(self, flags, accepted_mask):
+        """After the event kernel: g at the end of a step that stays accepted becomes g at the start of the next one."""
+        import torch
+        keep = (flags & accepted_mask) != 0
+        self.buf["g0"].copy_(torch.where(keep.unsqueeze(0), self.buf["g1"], self.buf["g0"]))
 
 
 def as_hyperplane(event, dim, constants=None):

@@ -67,7 +67,8 @@ typedef enum {
 #define DSB_FLAG_STRICT 1u  /* reference operation order, no FMA contraction, libm pow/atan   */
 
 #define DSB_MAX_PARAMS 6
-#define DSB_MAX_EVENTS 4
+#define DSB_MAX_EVENTS 4          /* fused kernels (dsb_erk_run)                                       */
+#define DSB_MAX_STAGE_EVENTS 16   /* stage-level kernels (dsb_erk_stage_*, dsb_symp_stage_*)           */
 #define DSB_MAX_FUSED_STAGES 17
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -257,7 +258,7 @@ typedef struct {
     const int32_t *ev_flags;   /* [n_events]                                                       */
     double *ev_records;        /* [n][ev_capacity][dim + 2]                                        */
     int32_t *ev_count;         /* [n] in/out                                                       */
-    double *ev_state;          /* [2 + 2*DSB_MAX_EVENTS][n] scratch: t and dt before the last accepted step,
+    double *ev_state;          /* [2 + 2*DSB_MAX_STAGE_EVENTS][n] scratch: t and dt before the last accepted step,
                                   last occurrence time per event, g at the step start per event     */
     double *tf_per;            /* [n] per-trajectory final time, initialised to tf by the caller; a terminal
                                   event re-targets it to the event time (NULL: tf for everyone)     */
@@ -273,6 +274,11 @@ DSB_API int dsb_erk_stage_finish(dsb_erk_handle h, const dsb_erk_stage_args *a, 
  * for the caller's f1 = rhs(t_stage, y_stage); phase 1 = locate / record events over the accepted steps (Hermite
  * interpolant from K[0] and f1), roll back and re-target trajectories stopped by a terminal event, masked commit. */
 DSB_API int dsb_erk_stage_finish_events(dsb_erk_handle h, const dsb_erk_stage_args *a, int phase, const double *f1, void *stream);
+/* Phase 1 with the event times located by the CALLER (any event callable, see dsb_event_search_*): roots is
+ * [n_events][n], NaN = no event of that kind in the step just attempted.  Ordering in time, the repeat filter, the event
+ * records, terminal roll-back / re-targeting and the masked commit are those of phase 1 above. */
+DSB_API int dsb_erk_stage_finish_events_located(dsb_erk_handle h, const dsb_erk_stage_args *a, const double *f1,
+                                                const double *roots, void *stream);
 /* kernel launches issued by one begin + S x state + finish sequence (bench accounting) */
 DSB_API int dsb_erk_stage_launches(dsb_erk_handle h);
 
@@ -326,7 +332,7 @@ typedef struct {
     const int32_t *ev_flags;
     double *ev_records;
     int32_t *ev_count;
-    double *ev_state;          /* [2 + 2*DSB_MAX_EVENTS][n] scratch                              */
+    double *ev_state;          /* [2 + 2*DSB_MAX_STAGE_EVENTS][n] scratch                        */
     double *tf_per;            /* [n] per-system final time, initialised to tf by the caller     */
     int32_t *ev_scratch;       /* [n] scratch                                                    */
     const double *ev_coef_dy;  /* [n_events][dim] weights on dState/dt (NULL: none)              */
@@ -341,6 +347,35 @@ DSB_API int dsb_symp_stage_commit(dsb_symp_handle h, const dsb_symp_stage_args *
  * and commits the others. */
 DSB_API int dsb_symp_stage_commit_events(dsb_symp_handle h, const dsb_symp_stage_args *a, int phase, const double *f0,
                                          const double *f1, void *stream);
+
+DSB_API int dsb_symp_stage_commit_events_located(dsb_symp_handle h, const dsb_symp_stage_args *a, const double *f0,
+                                                 const double *f1, const double *roots, void *stream);
+
+/* ---- root search for arbitrary event functions ---------------------------------------------
+ * Replaces the reference's vectorised Brent iteration on t -> event(t, sol(t)[, sol.grad(t)], **constants) over an
+ * accepted step (differential_system.py:60-167, utilities/optimizer.py:178-366) for callables that are not affine
+ * (those are solved in closed form inside the step kernels).  The callable is evaluated by the caller between the
+ * kernels, batched over every (event, trajectory) pair; all arrays are [n_events][n] device memory:
+ *   begin   bracket [0, 1] (step fractions) where g0 * g1 < 0 in an allowed direction for trajectories whose flag word
+ *           has need_mask set and skip_mask clear; first iterate x and its time tq = t0 + x (t1 - t0);
+ *           *counter (zeroed by the caller) = searches in flight
+ *   step    Illinois update with fx = event(tq, y(tq), ...): new bracket, next x / tq; a converged search leaves the
+ *           count.  The caller loops until the count is 0 or an iteration cap is reached.
+ *   roots   event times, NaN where there is none -> dsb_erk_stage_finish_events_located */
+typedef struct {
+    int64_t n;
+    int32_t n_events;
+    double *lo, *hi, *flo, *fhi;   /* bracket in step fractions and the (Illinois-scaled) function values at its ends */
+    double *x, *tq;                /* current iterate as a step fraction / as a time                                  */
+    int32_t *side;                 /* -100 no event, 100 converged, else the end replaced last                        */
+    const double *t0, *t1;         /* [n] step start / end times                                                      */
+    uint64_t *counter;             /* device word                                                                     */
+} dsb_event_search;
+
+DSB_API int dsb_event_search_begin(const dsb_event_search *s, const double *g0, const double *g1, const int32_t *flags,
+                                   int32_t need_mask, int32_t skip_mask, const int32_t *ev_flags, void *stream);
+DSB_API int dsb_event_search_step(const dsb_event_search *s, const double *fx, void *stream);
+DSB_API int dsb_event_search_roots(const dsb_event_search *s, double *roots, void *stream);
 
 /* ---- dense linear right-hand side ---------------------------------------------------------
  * K = A @ Y for the linear benchmark system y' = A y over an ensemble stored as Y[n][columns]
