@@ -407,6 +407,7 @@ class OdeSystem(object):
         self._node_store = None
         self._steps_cache = None
         self._rows_used = 0
+        self._protocol_path = False
 
     def _materialize(self):
         if self.__dict__.get("_pristine"):
@@ -544,6 +545,8 @@ class OdeSystem(object):
         (S per attempt for FSAL schemes); SURVEY.md fact 5."""
         if self.__dict__.get("_pristine"):
             return self.n_traj
+        if self.__dict__.get("_protocol_path"):
+            return int(self.equ_rhs.nfev)                      # the protocol loop calls the wrapped callable itself
         att = int((self.accepted.sum() + self.rejected.sum()).item())
         if att == 0:
             return self.n_traj
@@ -1395,6 +1398,60 @@ class OdeSystem(object):
                 break
         self._steps_cache = None
 
+    def _run_protocol(self, tf, callbacks, bar):
+        """The reference's own loop (differential_system.py:951-1018, 1070-1084) around ANY integrator that implements the
+        integrator protocol -- a Richardson wrapper, a user-written `IntegratorTemplate` subclass, or a tableau
+        integrator with a custom `adaptation_fn`: final-step clamp, one `integrator(rhs, t, y, constants, timestep)` call
+        per accepted step, `y += dState`, `t += dTime`, `dt = new_timestep` unless it was the final step, callbacks.  The
+        stepping itself happens in whatever the integrator calls (for this package's classes: the stage-level kernels);
+        the loop visits the host once per step, so it serves single systems."""
+        torch = _torch()
+        if self.ensemble:
+            raise NotImplementedError("the protocol loop (Richardson wrappers, custom integrators / adaptation functions) "
+                                      "drives one system at a time: ensemble=False")
+        integ = self.integrator
+        y, t, dt = self._y, self._t, self._dt                      # (D, 1), (1,), (1,) device tensors, advanced in place
+        store = self._ensure_node_store("rows", need=2) if self._want_nodes else None
+        if store is not None and int(store.node_count.max().item()) == 0:
+            f0 = self.equ_rhs(t.reshape(()), self._user_shape(y), **self.__consts).reshape(self.numel, 1).contiguous() if store.with_f else None
+            store.append_rows(t, y, f0, None, 4)
+            self._rows_used += 1
+        tc = float(t[0])
+        if abs(tf - tc) < D.epsilon("float64"):
+            return
+        self._fix_dt_dir(tf, tc)
+        if abs(float(dt[0])) > abs(tf - tc):
+            dt.fill_(float(np.copysign(abs(tf - tc) * 0.5, tf - tc)))
+        steps = 0
+        while float(dt[0]) != 0.0 and abs(tf - float(t[0])) >= D.tol_epsilon("float64"):
+            tc, h = float(t[0]), float(dt[0])
+            final = abs(h + tc) > abs(tf)
+            if final:
+                h = tf - tc
+            new_dt, (dT, dY) = integ(self.equ_rhs, t.reshape(()).clone(), self._user_shape(y).clone(), self.__consts,
+                                     timestep=torch.as_tensor(h, dtype=torch.float64, device=self.device))
+            y.add_(torch.as_tensor(dY, dtype=torch.float64, device=self.device).reshape(self.numel, 1))
+            t.add_(torch.as_tensor(dT, dtype=torch.float64, device=self.device).reshape(1))
+            self.accepted.add_(1)
+            steps += 1
+            if store is not None:
+                if (self._rows_used + 2) > store.capacity:
+                    store.grow(2 * store.capacity)
+                f1 = self.equ_rhs(t.reshape(()), self._user_shape(y), **self.__consts).reshape(self.numel, 1).contiguous() if store.with_f else None
+                store.append_rows(t, y, f1, None, 4)
+                self._rows_used += 1
+            if not final:
+                dt.copy_(torch.as_tensor(new_dt, dtype=torch.float64, device=self.device).reshape(1))
+            for cbk in callbacks:
+                cbk(self)
+            if bar is not None:
+                bar.update()
+            if steps > self._step_cap:
+                break
+        self.status.zero_()
+        self._steps_cache = None
+        self._protocol_path = True
+
     def integrate(self, t=None, callback=None, eta=False, events=None):
         """Integrates every trajectory to time `t` (default: `self.tf`), reference `:912-1101`.
 
@@ -1446,9 +1503,24 @@ class OdeSystem(object):
                 # the event-detecting fused kernels stop at 7 stages and write no nodes: a system that records dense
                 # output or its step history next to events runs on the stage-level kernels
                 plugin = None
+            protocol = (not isinstance(self.integrator, (integrators.RungeKuttaIntegrator, integrators.ExplicitSymplecticIntegrator))
+                        or getattr(self.integrator, "has_custom_adaptation", False))
+            if protocol:
+                if events or self.host_io:
+                    raise NotImplementedError("integrators driven through the protocol loop (Richardson wrappers, custom "
+                                              "integrators / adaptation functions) do not combine with events or host_io")
+                plugin = None
             if self.integrator.symplectic or plugin is None:
                 self._stats = None
-            if self.integrator.symplectic:
+            if protocol:
+                bar = None
+                if eta:
+                    from tqdm.auto import tqdm
+                    bar = tqdm(total=None)
+                self._run_protocol(tf, callbacks, bar)
+                if bar is not None:
+                    bar.close()
+            elif self.integrator.symplectic:
                 bar = None
                 if eta:
                     from tqdm.auto import tqdm

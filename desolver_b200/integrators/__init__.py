@@ -8,6 +8,7 @@ from . import tableaux as _tb
 from ._tableau_data import EXPLICIT_RK as _RK, SYMPLECTIC as _SY
 from .integrator_types import (ExplicitSymplecticIntegrator, IntegratorTemplate, RungeKuttaIntegrator,
                                TableauIntegrator)
+from .richardson import RichardsonIntegratorTemplate, generate_richardson_integrator
 
 __explicit_integration_methods__ = []
 __available_methods = {}
@@ -80,5 +81,6 @@ def register_with_reference(reference_integrators=None):
 
 
 __all__ = ["IntegratorTemplate", "TableauIntegrator", "RungeKuttaIntegrator", "ExplicitSymplecticIntegrator",
-           "available_methods", "explicit_methods", "implicit_methods", "register_with_reference"] + \
+           "available_methods", "explicit_methods", "implicit_methods", "register_with_reference", "RichardsonIntegratorTemplate",
+           "generate_richardson_integrator"] + \
           [c.__name__ for c in __explicit_integration_methods__]

