@@ -1058,6 +1058,7 @@ class OdeSystem(object):
                 cache = self._stage_k_cache = [torch.empty((D, n), **f64) for _ in range(S)]
             k_out = cache
         work, buf, m, index, consts = full, alloc(n), n, None, self.__consts
+        m_live = n
         a, y_view, t_view = bind(work, buf, m)
         search = None
         if events:
@@ -1101,8 +1102,8 @@ class OdeSystem(object):
         keep_node_f = [None]
 
         def scatter_back():
-            for k, v in work.items():
-                full[k].index_copy_(full[k].ndim - 1, index, v)
+            for k, v in work.items():                   # (padding columns beyond m_live are copies: not written back)
+                full[k].index_copy_(full[k].ndim - 1, index[:m_live], v[..., :m_live])
 
         if dense and int(store.node_count.max().item()) == 0:
             record_nodes(None)                                   # node 0 = initial condition
@@ -1205,10 +1206,21 @@ class OdeSystem(object):
                     if index is not None:
                         scatter_back()
                     index = sel if index is None else index[sel]
+                    m_live = int(sel.numel())
+                    # a right-hand side with a tiled kernel (rhs.column_multiple: the linear plugin's dsb_dgemm works on
+                    # 128-column tiles) gets a working set padded with INACTIVE copies of its first column, so that the
+                    # compacted rounds stay on that kernel instead of falling back to a library GEMM
+                    pad = (-m_live) % int(getattr(self.equ_rhs, "column_multiple", 1) or 1)
+                    if pad:
+                        sel = torch.cat([sel, sel[:1].expand(pad)])
+                        index = torch.cat([index, index[:1].expand(pad)])
                     work = {k: v.index_select(v.ndim - 1, index).contiguous() for k, v in full.items()}
                     new_buf = alloc(int(sel.numel()))
                     for k in persistent:
                         new_buf[k] = buf[k].index_select(buf[k].ndim - 1, sel).contiguous()
+                    if pad:
+                        new_buf["flags"][m_live:] = 0
+                        work["status"][m_live:] = cb.TRAJ_DONE
                     buf, m = new_buf, int(sel.numel())
                     consts = {k: (v.index_select(v.ndim - 1, index) if isinstance(v, torch.Tensor) and v.ndim >= 1
                                   and v.shape[-1] == n else v) for k, v in self.__consts.items()}

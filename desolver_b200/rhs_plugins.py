@@ -85,6 +85,7 @@ linear.use_library_gemm = False
 linear.calls_dsb = 0              # products served by dsb_dgemm / by the array library (CUDA-graph replays are not
 linear.calls_library = 0          # re-counted: what matters is which kernel a captured attempt contains)
 linear.supports_out = True        # rhs(t, y, out=array, **constants) writes the derivative into a caller-owned array
+linear.column_multiple = 128      # dsb_dgemm tiles 128 ensemble columns: compacted working sets are padded to that
 
 
 linear.device_plugin = "linear"
