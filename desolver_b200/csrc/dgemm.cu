@@ -41,7 +41,13 @@ namespace gemm {
 #ifndef DSB_GEMM_WTN
 #define DSB_GEMM_WTN 64        // warp tile width (columns): 64 -> 2 warps along N, 32 -> 4 warps along N
 #endif
-constexpr int WM = DSB_GEMM_WM, CTAS = DSB_GEMM_CTAS, WTN = DSB_GEMM_WTN, NT = WTN / 8;
+#ifndef DSB_GEMM_GROUP_M
+#define DSB_GEMM_GROUP_M 0     // > 0: tiles are walked in groups of GROUP_M row blocks (squarer set of concurrent tiles)
+#endif
+#ifndef DSB_GEMM_FRAG_DB
+#define DSB_GEMM_FRAG_DB 0     // 1: fragments of k-substep kk+1 are loaded from shared memory before the DMMAs of kk issue
+#endif
+constexpr int WM = DSB_GEMM_WM, CTAS = DSB_GEMM_CTAS, WTN = DSB_GEMM_WTN, NT = WTN / 8, GROUP_M = DSB_GEMM_GROUP_M;
 constexpr int BM = 32 * WM, BN = 128, BK = DSB_GEMM_BK, STAGES = DSB_GEMM_STAGES, THREADS = 32 * WM * (BN / WTN);
 constexpr int LDA = BK + 4;        // doubles: 2 * LDA words == 8 (mod 32) -> rows g = 0..3 fill one wavefront
 constexpr int LDB = BN + 8;        // doubles: 272 words == 16 (mod 32) -> k rows t = 0, 1 fill one wavefront
@@ -76,6 +82,18 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
     const int g = lane >> 2, t = lane & 3;
     const int mb = M / BM, nb = N / BN, kt = K / BK;
 
+    // tile index -> (row block, column block)
+    auto tile_mn = [&](int tile, int &tm, int &tn) {
+        if (GROUP_M > 0) {
+            const int per_group = GROUP_M * nb, grp = tile / per_group, first = grp * GROUP_M;
+            const int rows = (mb - first) < GROUP_M ? (mb - first) : GROUP_M, r = tile - grp * per_group;
+            tm = first + r % rows;
+            tn = r / rows;
+        } else {
+            tm = tile % mb;
+            tn = tile / mb;
+        }
+    };
     const double *Ag = nullptr, *Bg = nullptr;
     auto load_stage = [&](int stage, int k0) {
         double *a = sA + stage * A_STAGE, *b = sB + stage * B_STAGE;
@@ -92,8 +110,10 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
     };
     // prologue of a tile: the first STAGES-1 k-steps in flight
     auto prologue = [&](int tile) {
-        Ag = A + (size_t)((tile % mb) * BM) * K;
-        Bg = B + (tile / mb) * BN;
+        int tm, tn;
+        tile_mn(tile, tm, tn);
+        Ag = A + (size_t)(tm * BM) * K;
+        Bg = B + tn * BN;
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s) {
             if (s < kt) load_stage(s, s * BK);
@@ -104,7 +124,9 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
     int tile = blockIdx.x;
     if (tile < mb * nb) prologue(tile);
     for (; tile < mb * nb; tile += gridDim.x) {
-        const int m0 = (tile % mb) * BM, n0 = (tile / mb) * BN;
+        int tm0, tn0;
+        tile_mn(tile, tm0, tn0);
+        const int m0 = tm0 * BM, n0 = tn0 * BN;
         double acc[4][NT][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -118,6 +140,26 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
             cp_async_commit();
             const double *a = sA + (k % STAGES) * A_STAGE + (wm * 32 + g) * LDA + t;
             const double *b = sB + (k % STAGES) * B_STAGE + t * LDB + wn * WTN + g;
+#if DSB_GEMM_FRAG_DB
+            double af[2][4], bf[2][NT];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[0][i] = a[i * 8 * LDA];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[0][j] = b[j * 8];
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                if (kk + 1 < BK / 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) af[(kk + 1) & 1][i] = a[i * 8 * LDA + (kk + 1) * 4];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) bf[(kk + 1) & 1][j] = b[(kk + 1) * 4 * LDB + j * 8];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma(acc[i][j], af[kk & 1][i], bf[kk & 1][j]);
+            }
+#else
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
                 double af[4], bf[NT];
@@ -130,6 +172,7 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
 #pragma unroll
                     for (int j = 0; j < NT; ++j) dmma(acc[i][j], af[i], bf[j]);
             }
+#endif
         }
         cp_async_wait<0>();
         __syncthreads();                                                 // every warp is done with the last stages

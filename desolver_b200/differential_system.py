@@ -1164,9 +1164,13 @@ class OdeSystem(object):
                 torch.cuda.synchronize(dev)
                 return None
 
-        graph, rewarm = None, False
+        graph, rewarm, capture_pending = None, False, False
         rhs_calls_per_attempt = S + (1 if dense and store.with_f else 0) + (1 if events else 0)
+        trace = self.__dict__.get("_attempt_trace")          # optional list: (event, event, working columns) per attempt
         while True:
+            if trace is not None:
+                ev_pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev_pair[0].record()
             if dense and (self._rows_used + 2) * n > store.capacity:
                 # the host knows an upper bound of the row-groups in use (one per attempt) without asking the device;
                 # a grown pool has a new address, so the captured attempt is rebuilt
@@ -1178,11 +1182,23 @@ class OdeSystem(object):
                 first = False
                 graph = capture()
             elif rewarm:
-                # after a compaction the right-hand side sees new shapes (e.g. the linear plugin leaves its tiled GEMM
-                # for the library one, whose first call creates handles and workspaces): never inside a capture
+                # after a compaction (or a grown node pool) the attempt runs on new buffers: one eager attempt first --
+                # a right-hand side may meet new shapes, never inside a capture -- and the graph is rebuilt only if a
+                # FURTHER attempt turns out to be needed (the compacted tail of an ensemble often finishes in one round:
+                # capturing for it costs more than it saves)
                 one_attempt(False)
-                rewarm = False
+                rewarm, capture_pending = False, True
+            elif capture_pending:
+                capture_pending = False
                 graph = capture()
+                if graph is not None:
+                    graph.replay()
+                    self.equ_rhs.nfev += rhs_calls_per_attempt
+                    if dense:
+                        self._rows_used += 1
+                        store.invalidate()
+                else:
+                    one_attempt(False)
             elif graph is not None:
                 graph.replay()
                 self.equ_rhs.nfev += rhs_calls_per_attempt
@@ -1193,6 +1209,9 @@ class OdeSystem(object):
                 one_attempt(False)
             self._launches += handle.stage_launches if graph is None else 1
             attempts += 1
+            if trace is not None:
+                ev_pair[1].record()
+                trace.append((ev_pair[0], ev_pair[1], m, graph is not None))
             for cbk in callbacks:
                 cbk(self)
             if bar is not None:
