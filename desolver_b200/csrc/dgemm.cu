@@ -50,7 +50,10 @@ namespace gemm {
 constexpr int WM = DSB_GEMM_WM, CTAS = DSB_GEMM_CTAS, WTN = DSB_GEMM_WTN, NT = WTN / 8, GROUP_M = DSB_GEMM_GROUP_M;
 constexpr int BM = 32 * WM, BN = 128, BK = DSB_GEMM_BK, STAGES = DSB_GEMM_STAGES, THREADS = 32 * WM * (BN / WTN);
 constexpr int LDA = BK + 4;        // doubles: 2 * LDA words == 8 (mod 32) -> rows g = 0..3 fill one wavefront
-constexpr int LDB = BN + 8;        // doubles: 272 words == 16 (mod 32) -> k rows t = 0, 1 fill one wavefront
+#ifndef DSB_GEMM_LDB_PAD
+#define DSB_GEMM_LDB_PAD 8
+#endif
+constexpr int LDB = BN + DSB_GEMM_LDB_PAD;   // doubles; the k rows t = 0..3 of a half-warp must land in different bank groups
 constexpr int A_STAGE = BM * LDA, B_STAGE = BK * LDB;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
 

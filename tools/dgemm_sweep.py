@@ -12,16 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "dgemm_variants")
 VARIANTS = {
     "bk16_s3_c2": "",
-    "bk16_s3_c2_g8": "-DDSB_GEMM_GROUP_M=8",
+    "bk16_s3_c2_ldb4": "-DDSB_GEMM_LDB_PAD=4",
+    "bk16_s3_c2_ldb12": "-DDSB_GEMM_LDB_PAD=12",
+    "bk16_s4_c2_ldb4": "-DDSB_GEMM_LDB_PAD=4 -DDSB_GEMM_STAGES=4",
+    "bk16_s3_c2_ldb4_fdb": "-DDSB_GEMM_LDB_PAD=4 -DDSB_GEMM_FRAG_DB=1",
     "bk16_s3_c2_g16": "-DDSB_GEMM_GROUP_M=16",
-    "bk16_s3_c2_g32": "-DDSB_GEMM_GROUP_M=32",
     "bk16_s3_c2_fdb": "-DDSB_GEMM_FRAG_DB=1",
-    "bk16_s3_c2_g16_fdb": "-DDSB_GEMM_GROUP_M=16 -DDSB_GEMM_FRAG_DB=1",
     "bk16_s4_c2": "-DDSB_GEMM_STAGES=4",
-    "bk32_s2_c2": "-DDSB_GEMM_BK=32 -DDSB_GEMM_STAGES=2",
-    "bk8_s4_c2": "-DDSB_GEMM_BK=8 -DDSB_GEMM_STAGES=4",
-    "bk16_s3_c2_wtn32": "-DDSB_GEMM_WTN=32 -DDSB_GEMM_WM=1",
-    "bk16_s5_c1_wm4": "-DDSB_GEMM_WM=4 -DDSB_GEMM_CTAS=1 -DDSB_GEMM_STAGES=5",
 }
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     os.makedirs(OUT, exist_ok=True)
