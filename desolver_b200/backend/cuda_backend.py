@@ -87,6 +87,7 @@ class ErkHostArgs(C.Structure):
         ("chunk_shift", C.c_int32),
         ("flags", C.c_void_p),
         ("stream_up", C.c_void_p), ("stream_down", C.c_void_p),
+        ("host_t", C.c_void_p),
     ]
 
 
@@ -271,6 +272,8 @@ def lib():
     L.dsb_comm_gather.restype = C.c_int
     L.dsb_comm_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                   C.c_void_p]
+    L.dsb_interleave_shards.restype = C.c_int
+    L.dsb_interleave_shards.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
     L.dsb_peer_alloc.restype = C.c_int
     L.dsb_peer_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_int]
     L.dsb_peer_free.restype = C.c_int

@@ -249,6 +249,27 @@ int dsb_comm_gather(dsb_comm_handle c, const void *shard, void *staging, void *f
     return gather_typed<unsigned int>(c, shard, staging, full, rows, n_local, n_global, sms, (cudaStream_t)stream);
 }
 
+int dsb_interleave_shards(const void *staged, void *full, int rows, int elem_bytes, int64_t n_global, int world, void *stream)
+{
+    if (!staged || !full || rows < 1 || (elem_bytes != 4 && elem_bytes != 8) || n_global < 1 || world < 1) {
+        set_error("dsb_interleave_shards: bad argument");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    int dev = 0, sms = 0;
+    DSB_CUDA_CHECK(cudaGetDevice(&dev));
+    DSB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long n_max = (n_global + world - 1) / world;
+    const int grid = grid_1d((long long)rows * n_global, 256, sms);
+    if (elem_bytes == 8)
+        interleave_kernel<unsigned long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)staged,
+                                                                                     (unsigned long long *)full, rows, n_max, n_global, world);
+    else
+        interleave_kernel<unsigned int><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned int *)staged, (unsigned int *)full, rows,
+                                                                             n_max, n_global, world);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
 // ---- CUDA-IPC peer buffers -----------------------------------------------------------------------------------
 int dsb_peer_alloc(void **dev_ptr, int64_t bytes, void *ipc_handle_out, int device)
 {

@@ -48,12 +48,17 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
                   "flavour, <= 7 stages); use chunked dsb_erk_run launches", h->rhs_id, h->dim, h->stages, h->flags);
         return DSB_ERR_UNSUPPORTED;
     }
+    // host_y0 == NULL: the initial state is already resident (run.y_init, or run.y in place) -- nothing is uploaded and only
+    // the result side of the pipeline runs.  The destinations may then be ANY unified-address pointers, e.g. another
+    // GPU's buffer mapped through dsb_peer_open: the gather of a sharded ensemble as chunked peer copies that overlap
+    // the integration (desolver_b200/distributed.py, PushTarget).
+    const bool upload = a->host_y0 != nullptr;
     if (n < 0 || n > 0x7fffffffLL || !r.y || !r.t || !r.dt || !r.counters || !r.accepted || !r.rejected || !r.status ||
-        !a->host_y0 || !a->host_y || !a->host_accepted || !a->host_rejected || !a->flags ||
-        !a->stream_up || !a->stream_down || a->chunk_shift < 5 || a->chunk_shift > 30 || !r.fresh || r.y_init ||
-        r.store.pool) {
-        set_error("dsb_erk_run_host: bad argument (device staging buffers with fresh = 1, no y_init, no dense output; "
-                  "host buffers, flags and two extra streams are required; 5 <= chunk_shift <= 30)");
+        !a->host_y || !a->host_accepted || !a->host_rejected || !a->flags ||
+        (upload && !a->stream_up) || !a->stream_down || a->chunk_shift < 5 || a->chunk_shift > 30 || !r.fresh ||
+        (upload && r.y_init) || r.store.pool) {
+        set_error("dsb_erk_run_host: bad argument (device buffers with fresh = 1, no dense output; with host_y0 no y_init; "
+                  "result buffers, flags and the extra stream(s) are required; 5 <= chunk_shift <= 30)");
         return DSB_ERR_BAD_ARGUMENT;
     }
     if (n == 0) return DSB_OK;
@@ -72,13 +77,21 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
     }
     DSB_CUDA_CHECK(cudaMemsetAsync(a->flags, 0, sizeof(uint32_t) * (size_t)(1 + nchunks), stream));
     DSB_CUDA_CHECK(cudaEventRecord(h->ev_start, stream));
-    DSB_CUDA_CHECK(cudaStreamWaitEvent(up, h->ev_start, 0));
+    if (upload) DSB_CUDA_CHECK(cudaStreamWaitEvent(up, h->ev_start, 0));
     DSB_CUDA_CHECK(cudaStreamWaitEvent(down, h->ev_start, 0));
 
     // uploads: chunk c of every state row in one 2-D copy, then publish the resident count.  The kernel goes in
     // right after the first chunk has been queued, so that its start is not delayed by the remaining enqueues.
     int status = DSB_OK;
-    for (int64_t c = 0; c < nchunks; ++c) {
+    if (!upload) {
+        dsb_erk_run_args run = r;
+        run.avail = nullptr;                       // everything is resident: the kernel never waits
+        run.done = a->flags + 1;
+        run.done_shift = a->chunk_shift;
+        status = h->fused_launch_flow(h, &run, stream);
+        if (status != DSB_OK) return status;
+    }
+    for (int64_t c = 0; upload && c < nchunks; ++c) {
         const int64_t lo = c << a->chunk_shift, len = (lo + chunk <= n ? chunk : n - lo);
         DSB_CUDA_CHECK(cudaMemcpy2DAsync(r.y + lo, sizeof(double) * ld, a->host_y0 + lo, sizeof(double) * hld,
                                          sizeof(double) * len, dim, cudaMemcpyHostToDevice, up));
@@ -105,11 +118,13 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
             return DSB_ERR_CUDA;
         }
         DSB_CUDA_CHECK(cudaMemcpy2DAsync(a->host_y + lo, sizeof(double) * hld, r.y + lo, sizeof(double) * ld,
-                                         sizeof(double) * len, dim, cudaMemcpyDeviceToHost, down));
-        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_accepted + lo, r.accepted + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
-        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_rejected + lo, r.rejected + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
+                                         sizeof(double) * len, dim, cudaMemcpyDefault, down));
+        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_accepted + lo, r.accepted + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
+        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_rejected + lo, r.rejected + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
         if (a->host_status)      // NULL: the caller fetches the status words only if counters[4..5] report a failure
-            DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_status + lo, r.status + lo, sizeof(int32_t) * len, cudaMemcpyDeviceToHost, down));
+            DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_status + lo, r.status + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
+        if (a->host_t)
+            DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_t + lo, r.t + lo, sizeof(double) * len, cudaMemcpyDefault, down));
     }
     DSB_CUDA_CHECK(cudaEventRecord(h->ev_done, down));
     DSB_CUDA_CHECK(cudaStreamWaitEvent(stream, h->ev_done, 0));

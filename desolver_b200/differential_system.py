@@ -287,6 +287,8 @@ class OdeSystem(object):
         self.lazy_status = False
         self._pending = False
         self._scatter_store = None   # set by distributed.ShardedEnsemble(scatter_store=True)
+        self._push_target = None     # set by distributed.ShardedEnsemble(push=True)
+        self.push_chunks = 16
 
         if self.host_io:
             self._init_host_io(y0, host_out)
@@ -1001,6 +1003,53 @@ class OdeSystem(object):
         self._host_status_clean = int(c[:, 4].sum()) + int(c[:, 5].sum()) == 0
         return int(c[:, 2].sum()), int(c[:, 3].sum()), int(c[:, 4].sum()), int(c[:, 5].sum())
 
+    def _run_push(self, tf, plugin):
+        """Sharded ensemble, gather overlapped with the integration: ONE flow-controlled persistent launch
+        (dsb_erk_run_host without uploads) whose download stream copies chunk c of this shard's results to the ROOT rank's
+        staging buffer (peer memory, CUDA IPC) as soon as the chunk's trajectories are done.  The local state arrays are
+        written as usual.  Nothing is read back: the caller all-reduces the kernel's counters (lazy status)."""
+        torch = _torch()
+        integ = self.integrator
+        pid, names, defaults = plugin
+        n, dev = self.n_traj, self.device
+        handle = cb.erk_handle(dev.index or 0, pid, self.numel, integ.tableau_intermediate, integ.tableau_final, integ.order,
+                               strict=self.strict)
+        params, strides = self._param_tensors(names, defaults)
+        tgt = self._push_target
+        if self.__dict__.get("_push_streams") is None:
+            self._push_streams = torch.cuda.Stream(device=dev)
+        down = self._push_streams
+        cur = torch.cuda.current_stream(dev)
+        shift = max(10, int(np.ceil(np.log2(max(1, -(-n // max(1, self.push_chunks)))))))
+        nflags = 2 + (-(-n // (1 << shift)))
+        if self.__dict__.get("_push_flags") is None or self._push_flags.numel() < nflags:
+            self._push_flags = torch.zeros(nflags, dtype=torch.int32, device=dev)
+        self._counters.zero_()
+        ha = cb.ErkHostArgs()
+        a = ha.run
+        a.n, a.stride = n, n
+        a.y, a.t, a.dt = self._raw_y.data_ptr(), self._raw_t.data_ptr(), self._raw_dt.data_ptr()
+        a.y_init = self._y0.data_ptr()
+        for i, (p, sp) in enumerate(zip(params, strides)):
+            a.params[i], a.param_stride[i] = p.data_ptr(), sp
+        a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+        a.accepted, a.rejected, a.status = self._raw_accepted.data_ptr(), self._raw_rejected.data_ptr(), self._raw_status.data_ptr()
+        a.max_steps, a.first_call = int(self._step_cap), 1
+        a.fresh, a.t_init, a.dt_init = 1, self.t0, self._initial_dt()
+        a.counters = self._counters.data_ptr()
+        ha.host_y0 = None
+        ha.host_y, ha.host_t = tgt["y"], tgt["t"]
+        ha.host_accepted, ha.host_rejected, ha.host_status = tgt["accepted"], tgt["rejected"], tgt["status"]
+        ha.host_stride, ha.chunk_shift = int(tgt["n_max"]), shift
+        ha.flags = self._push_flags.data_ptr()
+        ha.stream_up, ha.stream_down = None, down.cuda_stream
+        if not handle.run_host(ha, C.c_void_p(cur.cuda_stream)):
+            raise RuntimeError("the pushed gather needs the flow-controlled kernel and stream memory operations "
+                               "(dsb_erk_run_host returned DSB_ERR_UNSUPPORTED)")
+        self._launches += 1
+        self._keepalive = params
+        self._pristine = False
+
     def _fused_stats(self):
         """(attempts, accepted, failed, running) of the last dsb_erk_run, from the kernel's own counters: ONE
         64-byte device-to-host copy instead of reductions over the per-trajectory arrays."""
@@ -1576,6 +1625,10 @@ class OdeSystem(object):
                     raise NotImplementedError("host_io=True systems integrate once per reset(), without callbacks, "
                                               "progress bar or dense output")
                 fused_stats = self._run_host_pipeline(tf, plugin)
+            elif (self._push_target is not None and not callbacks and not eta and not events and not self._want_nodes
+                  and self.__dict__.get("_pristine")):
+                self._run_push(tf, plugin)
+                lazy = True
             elif not callbacks and not eta:
                 self._run_fused(tf, plugin, self._step_cap, first_call=True, events=events)
                 if events:

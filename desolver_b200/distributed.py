@@ -190,6 +190,61 @@ class ScatterTarget:
                     status=b.tensor(torch.int32, (n,), self.offsets["status"]))
 
 
+class PushTarget:
+    """Destination of the chunked peer copies of `OdeSystem._run_push` on the ROOT rank: one CUDA-IPC allocation holding,
+    per tensor, the shards in rank-major order -- y[W][dim][n_max], t[W][n_max], accepted / rejected / status[W][n_max] --
+    so that every copy is one contiguous stream over NVLink.  `result()` (root) interleaves them into global order with
+    one kernel per tensor (dsb_interleave_shards)."""
+
+    FIELDS = (("y", 8), ("t", 8), ("accepted", 4), ("rejected", 4), ("status", 4))
+
+    def __init__(self, dim, n_global, device, group=None, root=0):
+        from .backend import cuda_backend as cb
+        self.rank, self.world_size = world(group)
+        self.dim, self.n_global, self.root = int(dim), int(n_global), int(root)
+        self.device = torch.device(device)
+        W = self.world_size
+        self.n_max = (self.n_global + W - 1) // W
+        pad = lambda b: (b + 255) // 256 * 256                      # noqa: E731
+        self.offsets, off = {}, 0
+        for name, size in self.FIELDS:
+            rows = self.dim if name == "y" else 1
+            self.offsets[name] = off
+            off += pad(W * rows * self.n_max * size)
+        self.nbytes = off
+        box = [None]
+        if self.rank == self.root:
+            self.buffer = cb.PeerBuffer.allocate(self.nbytes, self.device.index or 0)
+            box[0] = self.buffer.handle
+        if W > 1:
+            src = dist.get_global_rank(group, self.root) if group is not None else self.root
+            dist.broadcast_object_list(box, src=src, group=group)
+        if self.rank != self.root:
+            self.buffer = cb.PeerBuffer.open(box[0], self.nbytes, self.device.index or 0)
+
+    def slot(self, name):
+        """Address of this rank's slot of tensor `name` in the root's staging buffer."""
+        rows, size = (self.dim, 8) if name == "y" else (1, dict(self.FIELDS)[name])
+        return self.buffer.ptr + self.offsets[name] + self.rank * rows * self.n_max * size
+
+    def result(self):
+        """Root only: the global tensors, interleaved from the staged shards on the current stream."""
+        from .backend import cuda_backend as cb
+        if self.rank != self.root:
+            return None
+        out = {}
+        st = cb.current_stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for name, size in self.FIELDS:
+                rows = self.dim if name == "y" else 1
+                full = torch.empty((rows, self.n_global) if name == "y" else (self.n_global,),
+                                   dtype=torch.float64 if size == 8 else torch.int32, device=self.device)
+                cb.check(cb.lib().dsb_interleave_shards(self.buffer.ptr + self.offsets[name], full.data_ptr(), rows, size,
+                                                        self.n_global, self.world_size, st), "dsb_interleave_shards")
+                out[name] = full
+        return out
+
+
 class ShardedEnsemble:
     """Round-robin shard of a global ensemble integrated by this rank's `OdeSystem`.
 
@@ -203,7 +258,7 @@ class ShardedEnsemble:
     straight into the root's gather buffer (see ScatterTarget); `gather()` on the root is then free.
     """
 
-    def __init__(self, make_system, y0_global, constants=None, group=None, scatter_store=False, root=0):
+    def __init__(self, make_system, y0_global, constants=None, group=None, scatter_store=False, root=0, push=False):
         self.group = group
         self.rank, self.world_size = world(group)
         self.n_global = int(y0_global.shape[-1])
@@ -219,6 +274,12 @@ class ShardedEnsemble:
         self._err = None
         self._side = None
         self.scatter = None
+        self.push = None
+        if push:
+            # the gather as chunked peer copies that overlap the integration (see PushTarget / OdeSystem._run_push)
+            s = self.system
+            self.push = PushTarget(s.numel, self.n_global, s.device, group, self.root)
+            s._push_target = dict(n_max=self.push.n_max, **{k: self.push.slot(k) for k, _ in PushTarget.FIELDS})
         if scatter_store:
             s = self.system
             self.scatter = ScatterTarget(s.numel, self.n_global, s.device, group, self.root)
@@ -290,6 +351,14 @@ class ShardedEnsemble:
         with `scatter_store=True` on the root only (views of the buffer the kernels wrote, None elsewhere) after a
         device barrier (the all-reduce already enqueued behind every rank's kernel)."""
         s = self.system
+        if self.push is not None:
+            # every rank's all-reduce sits behind its kernel AND its last peer copy: once it has completed here, the staged
+            # shards are complete
+            _ = self.statistics
+            out = self.push.result()
+            if out is not None:
+                out["y"] = out["y"].reshape(tuple(s.dim) + (self.n_global,))
+            return out
         if self.scatter is not None:
             # the all-reduce sits behind every rank's kernel, so once it has completed here every peer's stores have
             # been issued and flushed (kernel boundary): no further barrier

@@ -205,6 +205,12 @@ typedef struct {
     int32_t chunk_shift;       /* chunk = 2^chunk_shift trajectories                            */
     uint32_t *flags;           /* device, >= 1 + ceil(n / 2^chunk_shift) words (zeroed here)    */
     void *stream_up, *stream_down;
+    /* ---- ABI 3 ---- */
+    double *host_t;            /* [n] out, optional: final times                                */
+    /* host_y0 == NULL: nothing is uploaded -- the initial state is resident (run.y_init, or run.y in place) and only the
+     * result side of the pipeline runs; stream_up is unused.  The result pointers may then be any unified-address
+     * destinations, e.g. another GPU's buffer mapped with dsb_peer_open: chunk c of the shard's results is copied to
+     * the peer as soon as its trajectories are done, while the rest of the shard is still integrating. */
 } dsb_erk_host_args;
 
 DSB_API int dsb_erk_run_host(dsb_erk_handle h, const dsb_erk_host_args *args, void *stream);
@@ -450,6 +456,10 @@ DSB_API int dsb_comm_allreduce_counters(dsb_comm_handle c, const uint64_t *send,
  * (>= W * rows * ceil(n_global / W) * elem_bytes bytes, device) followed by one interleave kernel. */
 DSB_API int dsb_comm_gather(dsb_comm_handle c, const void *shard, void *staging, void *full, int rows, int elem_bytes,
                             int64_t n_local, int64_t n_global, void *stream);
+/* The interleave step alone, for shards that reached `staged` by other means (peer copies, dsb_erk_run_host with peer
+ * destinations): full[r][j * W + w] = staged[w][r][j], staged = [W][rows][n_max] with n_max = ceil(n_global / W). */
+DSB_API int dsb_interleave_shards(const void *staged, void *full, int rows, int elem_bytes, int64_t n_global, int world,
+                                  void *stream);
 
 /* Peer-visible device buffers (CUDA IPC) for the scatter-store of dsb_erk_run (out_* fields): the owner allocates
  * and exports, every other process of the box opens the handle and passes the mapped pointer to its own launches,

@@ -126,9 +126,10 @@ def _vdp_parity(full, y0, mu, cfg, check):
 
 def run_vdp(dev, world=1, rank=0, reps=3, check=2048, n=1 << 24, hbm_peak=6538.3, scatter=True):
     """Config 4.  world == 1: the whole ensemble on this GPU.  world > 1: round-robin shards, the statistics
-    all-reduce enqueued behind each rank's kernel, and the results gathered on rank 0 -- with `scatter` by the kernels
-    themselves (stores to rank 0's buffer over NVLink while the integration runs), else by dsb_comm_gather afterwards.
-    Times are max over ranks; `ms` INCLUDES the gather."""
+    all-reduce enqueued behind each rank's kernel, and the results gathered -- three ways, all timed: "push" (chunks of
+    finished trajectories copied to rank 0's staging buffer over NVLink while the shard is still integrating, one
+    interleave kernel on rank 0), "scatter" (the kernel's own stores go to rank 0's buffer), "gather" (dsb_comm_gather
+    afterwards: ncclAllGather + interleave on every rank).  Times are max over ranks; `ms` INCLUDES the gather."""
     import torch
     import torch.distributed as dist
     import desolver_b200 as de
@@ -144,16 +145,19 @@ def run_vdp(dev, world=1, rank=0, reps=3, check=2048, n=1 << 24, hbm_peak=6538.3
     y0_shard = torch.as_tensor(np.ascontiguousarray(y0[:, rank::world])).to(dev)
     mu_shard = torch.as_tensor(np.ascontiguousarray(mu[rank::world])).to(dev)
 
-    def build(use_scatter):
+    def build(mode):
         sh = dd.ShardedEnsemble.__new__(dd.ShardedEnsemble)     # shards were cut on the host: build the object directly
         sh.group, sh.rank, sh.world_size, sh.n_global, sh.root = None, rank, world, n, 0
         sh.system = make(y0_shard, dict(mu=mu_shard))
-        sh._global = sh._stats = sh._err = sh._side = sh.scatter = None
-        if use_scatter and world > 1:
-            s = sh.system
+        sh._global = sh._stats = sh._err = sh._side = sh.scatter = sh.push = None
+        s = sh.system
+        if mode == "scatter" and world > 1:
             sh.scatter = dd.ScatterTarget(s.numel, n, s.device, None, 0)
             s._scatter_store = dict(index_mul=world, index_add=rank, stride=n,
                                     **{k: sh.scatter.pointer(k) for k in ("y", "t", "dt", "accepted", "rejected", "status")})
+        if mode == "push" and world > 1:
+            sh.push = dd.PushTarget(s.numel, n, s.device, None, 0)
+            s._push_target = dict(n_max=sh.push.n_max, **{k: sh.push.slot(k) for k, _ in dd.PushTarget.FIELDS})
         return sh
 
     def barrier():
@@ -161,15 +165,15 @@ def run_vdp(dev, world=1, rank=0, reps=3, check=2048, n=1 << 24, hbm_peak=6538.3
             dist.barrier()
 
     results = {}
-    for mode in (["scatter", "gather"] if (world > 1 and scatter) else ["gather"]):
-        sh = build(mode == "scatter")
+    for mode in (["push", "scatter", "gather"] if (world > 1 and scatter) else ["gather"]):
+        sh = build(mode)
         full = [None]
         stats = [None]
 
         def one():
             sh.system.reset()
             sh.integrate(wait=False)                            # kernel + all-reduce enqueued, nothing read back
-            full[0] = sh.gather() if (world > 1 or mode == "scatter") else None
+            full[0] = sh.gather() if world > 1 else None
             stats[0] = sh.statistics
 
         one()                                                   # warm-up (communicator, IPC mapping, allocator)

@@ -39,8 +39,8 @@ for n in (100003, 1 << 18):                                   # a length that do
     if rank == 0:
         ref = make(y0_t, dict(mu=mu_t))
         ref.integrate()
-    for scatter in (False, True):
-        sh = dd.ShardedEnsemble(make, y0_t, dict(mu=mu_t), scatter_store=scatter)
+    for scatter in (False, True, "push"):
+        sh = dd.ShardedEnsemble(make, y0_t, dict(mu=mu_t), scatter_store=scatter is True, push=scatter == "push")
         stats = sh.integrate()
         full = sh.gather()
         torch.cuda.synchronize()
@@ -50,7 +50,7 @@ for n in (100003, 1 << 18):                                   # a length that do
                     and stats["attempts"] == ref.stats["attempts"] and stats["accepted"] == ref.stats["accepted"])
             out["n=%d scatter=%s" % (n, scatter)] = bool(same)
             ok = ok and same
-        elif not scatter:
+        elif scatter is False:
             # dsb_comm_gather delivers the full ensemble on every rank
             chk = torch.tensor([float(full["y"].sum()), float(full["accepted"].sum())], dtype=torch.float64, device=dev)
         dist.barrier()
