@@ -86,17 +86,41 @@ struct dsb_comm {
 namespace dsb {
 
 // Interleave of the gathered shards: full[r][j * W + w] = staged[w][r][j]  (trajectory i lives on rank i mod W).
-// One thread per 8 destination bytes of a row; reads stride over the W rank blocks, writes are contiguous.
-template <class T>
+// grid.y = row; a thread owns one destination element: the writes of a warp are one contiguous segment, its reads are
+// W streams of 32 / W consecutive elements each (whole sectors for W <= 8 doubles).  WSHIFT >= 0: W = 2^WSHIFT, the
+// index split is a shift and a mask (an integer division per element costs more than the memory traffic).
+template <class T, int WSHIFT>
 __global__ void interleave_kernel(const T *__restrict__ staged, T *__restrict__ full, int rows, long long n_max,
                                   long long n_global, int W)
 {
-    const long long total = (long long)rows * n_global;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long r = e / n_global, i = e - r * n_global;
-        const long long j = i / W;
-        const int w = (int)(i - j * W);
-        full[e] = staged[((long long)w * rows + r) * n_max + j];
+    const int r = blockIdx.y;
+    const T *src = staged + (long long)r * n_max;
+    T *dst = full + (long long)r * n_global;
+    const long long slot = (long long)rows * n_max;              // elements per rank block
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_global; i += (long long)gridDim.x * blockDim.x) {
+        long long j;
+        int w;
+        if constexpr (WSHIFT >= 0) { j = i >> WSHIFT; w = (int)(i & ((1 << WSHIFT) - 1)); }
+        else { j = i / W; w = (int)(i - j * W); }
+        dst[i] = src[w * slot + j];
+    }
+}
+
+template <class T>
+static void launch_interleave(const T *staged, T *full, int rows, long long n_max, long long n_global, int W, int sms, cudaStream_t st)
+{
+    long long bx = (n_global + 255) / 256;
+    const long long cap = ((long long)sms * 16 + rows - 1) / rows;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)bx, (unsigned)rows);
+    int shift = -1;
+    for (int k = 0; k < 16; ++k) if ((1 << k) == W) shift = k;
+    switch (shift) {
+    case 0: interleave_kernel<T, 0><<<grid, 256, 0, st>>>(staged, full, rows, n_max, n_global, W); break;
+    case 1: interleave_kernel<T, 1><<<grid, 256, 0, st>>>(staged, full, rows, n_max, n_global, W); break;
+    case 2: interleave_kernel<T, 2><<<grid, 256, 0, st>>>(staged, full, rows, n_max, n_global, W); break;
+    case 3: interleave_kernel<T, 3><<<grid, 256, 0, st>>>(staged, full, rows, n_max, n_global, W); break;
+    default: interleave_kernel<T, -1><<<grid, 256, 0, st>>>(staged, full, rows, n_max, n_global, W); break;
     }
 }
 
@@ -133,8 +157,7 @@ static int gather_typed(dsb_comm *c, const void *shard, void *staging, void *ful
         DSB_CUDA_CHECK(cudaGetLastError());
     }
     if (W > 1) DSB_NCCL_CHECK(g_nccl.AllGather(mine, staging, slot, NCCL_INT8, c->comm, st));   // in place
-    interleave_kernel<T><<<grid_1d((long long)rows * n_global, 256, sms), 256, 0, st>>>((const T *)staging, (T *)full, rows, n_max,
-                                                                                       n_global, W);
+    launch_interleave<T>((const T *)staging, (T *)full, rows, n_max, n_global, W, sms, st);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
@@ -259,13 +282,12 @@ int dsb_interleave_shards(const void *staged, void *full, int rows, int elem_byt
     DSB_CUDA_CHECK(cudaGetDevice(&dev));
     DSB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long n_max = (n_global + world - 1) / world;
-    const int grid = grid_1d((long long)rows * n_global, 256, sms);
     if (elem_bytes == 8)
-        interleave_kernel<unsigned long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)staged,
-                                                                                     (unsigned long long *)full, rows, n_max, n_global, world);
+        launch_interleave<unsigned long long>((const unsigned long long *)staged, (unsigned long long *)full, rows, n_max, n_global,
+                                              world, sms, (cudaStream_t)stream);
     else
-        interleave_kernel<unsigned int><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned int *)staged, (unsigned int *)full, rows,
-                                                                             n_max, n_global, world);
+        launch_interleave<unsigned int>((const unsigned int *)staged, (unsigned int *)full, rows, n_max, n_global, world, sms,
+                                        (cudaStream_t)stream);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
