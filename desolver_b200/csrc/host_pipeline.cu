@@ -54,7 +54,7 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
     // the integration (desolver_b200/distributed.py, PushTarget).
     const bool upload = a->host_y0 != nullptr;
     if (n < 0 || n > 0x7fffffffLL || !r.y || !r.t || !r.dt || !r.counters || !r.accepted || !r.rejected || !r.status ||
-        !a->host_y || !a->host_accepted || !a->host_rejected || !a->flags ||
+        !a->host_y || !a->flags ||
         (upload && !a->stream_up) || !a->stream_down || a->chunk_shift < 5 || a->chunk_shift > 30 || !r.fresh ||
         (upload && r.y_init) || r.store.pool) {
         set_error("dsb_erk_run_host: bad argument (device buffers with fresh = 1, no dense output; with host_y0 no y_init; "
@@ -119,8 +119,10 @@ int run_host(dsb_erk_plan *h, const dsb_erk_host_args *a, cudaStream_t stream)
         }
         DSB_CUDA_CHECK(cudaMemcpy2DAsync(a->host_y + lo, sizeof(double) * hld, r.y + lo, sizeof(double) * ld,
                                          sizeof(double) * len, dim, cudaMemcpyDefault, down));
-        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_accepted + lo, r.accepted + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
-        DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_rejected + lo, r.rejected + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
+        if (a->host_accepted)    // NULL (any of the three counter arrays): not downloaded, the caller reads run.* on demand
+            DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_accepted + lo, r.accepted + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
+        if (a->host_rejected)
+            DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_rejected + lo, r.rejected + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
         if (a->host_status)      // NULL: the caller fetches the status words only if counters[4..5] report a failure
             DSB_CUDA_CHECK(cudaMemcpyAsync(a->host_status + lo, r.status + lo, sizeof(int32_t) * len, cudaMemcpyDefault, down));
         if (a->host_t)

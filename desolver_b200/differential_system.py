@@ -185,8 +185,25 @@ class OdeSystem(object):
     _y = _state_property("y")
     _t = _state_property("t")
     _dt = _state_property("dt")
-    accepted = _state_property("accepted")
-    rejected = _state_property("rejected")
+    def _host_counter(name):                                  # noqa: N805  (class-body helper, like _state_property)
+        """accepted / rejected: as _state_property, except that a host_io system whose caller supplied `host_out` WITHOUT
+        this array does not download it with every pass -- it is fetched from the device arrays on first use."""
+        raw, dev = "_raw_" + name, "_dev_" + name
+
+        def getter(self):
+            self._materialize()
+            if getattr(self, raw) is None:
+                setattr(self, raw, getattr(self, dev).cpu())
+            return getattr(self, raw)
+
+        def setter(self, value):
+            self._materialize()
+            setattr(self, raw, value)
+        return property(getter, setter)
+
+    accepted = _host_counter("accepted")
+    rejected = _host_counter("rejected")
+    del _host_counter
 
     @property
     def status(self):
@@ -349,8 +366,12 @@ class OdeSystem(object):
             return buf
 
         self._raw_y = host_buffer("y", (self.numel, n), torch.float64)
-        self._raw_accepted = host_buffer("accepted", (n,), torch.int32)
-        self._raw_rejected = host_buffer("rejected", (n,), torch.int32)
+        # counters: with a caller-supplied host_out only the arrays it contains are downloaded with every pass; the others
+        # stay on the device and are fetched on first use (`a.accepted`, `a.rejected`, `a.status`)
+        explicit = bool(host_out)
+        self._host_acc_buffer = host_buffer("accepted", (n,), torch.int32) if (not explicit or "accepted" in host_out) else None
+        self._host_rej_buffer = host_buffer("rejected", (n,), torch.int32) if (not explicit or "rejected" in host_out) else None
+        self._raw_accepted, self._raw_rejected = self._host_acc_buffer, self._host_rej_buffer
         # status words: downloaded only into a buffer the caller supplies; otherwise on demand (see `status`)
         self._host_status_buffer = host_buffer("status", (n,), torch.int32) if "status" in host_out else None
         self._raw_status = self._host_status_buffer
@@ -417,8 +438,10 @@ class OdeSystem(object):
             self._raw_y.copy_(self._y0)
             self._raw_t.fill_(self.__t0)
             self._raw_dt.fill_(self._initial_dt())
-            self._raw_accepted.zero_()
-            self._raw_rejected.zero_()
+            if self._raw_accepted is not None:
+                self._raw_accepted.zero_()
+            if self._raw_rejected is not None:
+                self._raw_rejected.zero_()
             if self._raw_status is not None:
                 self._raw_status.zero_()
 
@@ -940,7 +963,8 @@ class OdeSystem(object):
             a.fresh, a.t_init, a.dt_init = 1, self.t0, self._initial_dt()
             a.counters = self._counters.data_ptr()
             ha.host_y0, ha.host_y = self._y0.data_ptr(), self._raw_y.data_ptr()
-            ha.host_accepted, ha.host_rejected = self._raw_accepted.data_ptr(), self._raw_rejected.data_ptr()
+            ha.host_accepted = self._host_acc_buffer.data_ptr() if self._host_acc_buffer is not None else None
+            ha.host_rejected = self._host_rej_buffer.data_ptr() if self._host_rej_buffer is not None else None
             ha.host_status = self._host_status_buffer.data_ptr() if self._host_status_buffer is not None else None
             ha.host_stride, ha.chunk_shift = n, shift
             ha.flags = self._pipe_flags.data_ptr()
@@ -953,6 +977,7 @@ class OdeSystem(object):
                 if int(c[6]):
                     raise RuntimeError("dsb_erk_run_host: the kernel timed out waiting for its initial states")
                 self._raw_status = self._host_status_buffer
+                self._raw_accepted, self._raw_rejected = self._host_acc_buffer, self._host_rej_buffer
                 self._host_status_clean = int(c[4]) + int(c[5]) == 0
                 return int(c[2]), int(c[3]), int(c[4]), int(c[5])
             self.host_pipeline = "chunked"                    # driver without stream memory operations
@@ -990,8 +1015,10 @@ class OdeSystem(object):
             with torch.cuda.stream(down):
                 for d in range(self.numel):
                     self._raw_y[d, lo:hi].copy_(self._dev_y[d, lo:hi], non_blocking=True)
-                self._raw_accepted[lo:hi].copy_(self._dev_accepted[lo:hi], non_blocking=True)
-                self._raw_rejected[lo:hi].copy_(self._dev_rejected[lo:hi], non_blocking=True)
+                if self._host_acc_buffer is not None:
+                    self._host_acc_buffer[lo:hi].copy_(self._dev_accepted[lo:hi], non_blocking=True)
+                if self._host_rej_buffer is not None:
+                    self._host_rej_buffer[lo:hi].copy_(self._dev_rejected[lo:hi], non_blocking=True)
                 if self._host_status_buffer is not None:
                     self._host_status_buffer[lo:hi].copy_(self._dev_status[lo:hi], non_blocking=True)
         for st in (down, comp0, comp1):
@@ -1000,6 +1027,7 @@ class OdeSystem(object):
         self._pristine = False
         c = self._counters.cpu().reshape(-1, 8)[:chunks]          # synchronises: every copy above has landed
         self._raw_status = self._host_status_buffer
+        self._raw_accepted, self._raw_rejected = self._host_acc_buffer, self._host_rej_buffer
         self._host_status_clean = int(c[:, 4].sum()) + int(c[:, 5].sum()) == 0
         return int(c[:, 2].sum()), int(c[:, 3].sum()), int(c[:, 4].sum()), int(c[:, 5].sum())
 

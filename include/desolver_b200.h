@@ -198,7 +198,9 @@ typedef struct {
     dsb_erk_run_args run;
     const double *host_y0;     /* [dim][host_stride]                                            */
     double *host_y;            /* [dim][host_stride] out                                        */
-    int32_t *host_accepted, *host_rejected, *host_status;   /* [n] out; host_status may be NULL: every status
+    int32_t *host_accepted, *host_rejected, *host_status;   /* [n] out; each may be NULL (not downloaded: the
+                                  ensemble totals are in run.counters, the per-trajectory words stay readable in
+                                  run.accepted / rejected / status).  In particular every status
                                   is DSB_TRAJ_DONE iff counters[4] + counters[5] == 0, so a caller can skip that
                                   download and fetch run.status only when a failure is reported               */
     int64_t host_stride;       /* leading dimension of host_y0 / host_y in elements (0: n)      */
