@@ -313,14 +313,24 @@ class OdeSystem(object):
             self.initialise_integrator()
             return
         self._y0 = y0.reshape(self.numel, self.n_traj).contiguous().clone()
-        # one RHS evaluation as a shape check, like the reference (:536-539)
-        probe = self.equ_rhs(self._user_time(torch.full((self.n_traj,), self.__t0, dtype=torch.float64,
-                                                        device=self.device)),
-                             self._user_shape(self._y0), **self.__consts)
-        if tuple(probe.shape) != tuple(self._user_shape(self._y0).shape):
-            raise ValueError("Expected rhs to return a shape that is compatible with y0, got shapes "
-                             "Shape[y0]={} and Shape[dy]={}".format(tuple(self._user_shape(self._y0).shape),
-                                                                    tuple(probe.shape)))
+        # one RHS evaluation as a shape check, like the reference (:536-539) -- except for a built-in right-hand side of
+        # known state shape, where comparing shapes needs no evaluation (for an ensemble the probe would run the Python
+        # callable over all N trajectories: aten kernels and a full-size temporary per construction)
+        known = getattr(self.equ_rhs, "plugin_dim", None) if self._fused_plugin_tag() is not None else None
+        if known is not None:
+            if tuple(known) != tuple(self.dim):
+                raise ValueError("Expected rhs to return a shape that is compatible with y0, got shapes "
+                                 "Shape[y0]={} and Shape[dy]={}".format(tuple(self._user_shape(self._y0).shape),
+                                                                        tuple(known) + ((self.n_traj,) if self.ensemble else ())))
+            self.equ_rhs.nfev += 1                          # the reference's constructor evaluates the rhs once
+        else:
+            probe = self.equ_rhs(self._user_time(torch.full((self.n_traj,), self.__t0, dtype=torch.float64,
+                                                            device=self.device)),
+                                 self._user_shape(self._y0), **self.__consts)
+            if tuple(probe.shape) != tuple(self._user_shape(self._y0).shape):
+                raise ValueError("Expected rhs to return a shape that is compatible with y0, got shapes "
+                                 "Shape[y0]={} and Shape[dy]={}".format(tuple(self._user_shape(self._y0).shape),
+                                                                        tuple(probe.shape)))
         self._reset_state()
         self.initialise_integrator()
 

@@ -29,6 +29,7 @@ def lorenz(t, y, sigma=10.0, rho=28.0, beta=8.0 / 3.0):
 
 
 lorenz.device_plugin = "lorenz"
+lorenz.plugin_dim = (3,)          # state shape of ONE trajectory: lets OdeSystem check shapes without a probe call
 lorenz.plugin_id = RHS_LORENZ
 lorenz.plugin_params = ("sigma", "rho", "beta")
 lorenz.plugin_defaults = dict(sigma=10.0, rho=28.0, beta=8.0 / 3.0)
@@ -41,6 +42,7 @@ def van_der_pol(t, y, mu=1.0):
 
 
 van_der_pol.device_plugin = "van_der_pol"
+van_der_pol.plugin_dim = (2,)          # state shape of ONE trajectory: lets OdeSystem check shapes without a probe call
 van_der_pol.plugin_id = RHS_VDP
 van_der_pol.plugin_params = ("mu",)
 van_der_pol.plugin_defaults = dict(mu=1.0)
@@ -56,6 +58,7 @@ def harmonic_oscillator(t, y, k=1.0, m=1.0):
 
 
 harmonic_oscillator.device_plugin = "harmonic_oscillator"
+harmonic_oscillator.plugin_dim = (2,)          # state shape of ONE trajectory: lets OdeSystem check shapes without a probe call
 harmonic_oscillator.plugin_id = RHS_SHO
 harmonic_oscillator.plugin_params = ("k", "m")
 harmonic_oscillator.plugin_defaults = dict(k=1.0, m=1.0)
@@ -137,6 +140,7 @@ def forced(t, y):
 
 
 forced.device_plugin = "forced"
+forced.plugin_dim = (2,)          # state shape of ONE trajectory: lets OdeSystem check shapes without a probe call
 forced.plugin_id = RHS_FORCED
 forced.plugin_params = ()
 forced.plugin_defaults = dict()
@@ -158,6 +162,7 @@ def duffing(t, y, delta=0.2, alpha=-1.0, beta=1.0, gamma=0.3, omega=1.2):
 
 
 duffing.device_plugin = "duffing"
+duffing.plugin_dim = (2,)          # state shape of ONE trajectory: lets OdeSystem check shapes without a probe call
 duffing.plugin_id = RHS_DUFFING
 duffing.plugin_params = ("delta", "alpha", "beta", "gamma", "omega")
 duffing.plugin_defaults = dict(delta=0.2, alpha=-1.0, beta=1.0, gamma=0.3, omega=1.2)
