@@ -17,5 +17,5 @@ $NCU -k regex:"node_eval|node_locate" -c 2 -o $O/r2_dense_readers python tools/p
 ncu -i $O/r2_dense_readers.ncu-rep --page raw --csv > $O/r2_dense_readers.raw.csv; rm -f $O/r2_dense_readers.ncu-rep
 python tools/dgemm_timing.py 4096 8192 4096 > $O/p_dgemm.log 2>&1 && $NCU -k regex:"dgemm_dmma|d884gemm" -s 2 -c 2 -o $O/r2_dgemm python tools/dgemm_timing.py 4096 8192 4096 > $O/p_dgemm_ncu.log 2>&1
 ncu -i $O/r2_dgemm.ncu-rep --page raw --csv > $O/r2_dgemm.raw.csv
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $O/p_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs > $O/p_bench_ncu.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --no-e2e > $O/p_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --no-e2e > $O/p_bench_ncu.log 2>&1
 du -sh $O; ls -la $O | tail -30
