@@ -118,6 +118,21 @@ def test_config2_linear_4096_by_8192():
     # the flow e^{A t} of the damped near-skew matrix contracts: |y(1)| <= e^{-0.1} |y(0)| up to the integration error
     ratio = a[-1].y.norm(dim=0) / Yd.norm(dim=0)
     assert float((ratio - np.exp(-0.1)).abs().max()) < 1e-8
+    # sampled columns against the CPU oracle (each column = one trajectory of the reference semantics), at full size
+    from desolver_b200.integrators import tableaux as tb
+    from oracle import oracle as orc
+    idx = np.linspace(0, cols - 1, 6).astype(int)
+    ref = orc.erk_ensemble(orc.RHS_LINEAR, Y0[:, idx], 0.0, 1.0, 1e-2, 1e-9, 1e-9, *tb.rk_arrays("RK8713MSolver"), shared=A,
+                           threads=os.cpu_count())
+    got = a[-1].y[:, idx].cpu().numpy()
+    assert rel_inf(got, ref["y"]).max() <= 1e-10
+    assert np.array_equal(a.accepted[idx].cpu().numpy(), ref["accepted"]) and np.array_equal(a.rejected[idx].cpu().numpy(), ref["rejected"])
+    # no product of the configuration left the library's own tensor-core kernel (compacted tail included)
+    assert de.rhs_plugins.linear.calls_dsb > 0
+    lib_before = de.rhs_plugins.linear.calls_library
+    a.reset()
+    a.integrate()
+    assert de.rhs_plugins.linear.calls_library == lib_before
 
 
 def test_config1_events_are_pure_observers_at_full_size():

@@ -412,3 +412,47 @@ def test_richardson_extrapolation_matches_the_reference(key, base, it):
     assert np.max(np.abs(a.t.cpu().numpy() - t_ref)) <= 5e-6 and np.max(np.abs(a.y.cpu().numpy() - y_ref)) <= 5e-6
     assert abs(a.nfev - int(g[key + ".nfev"])) <= 0.02 * int(g[key + ".nfev"])
     assert abs(float(a[-1].y[0]) - 1.0) < 1e-6
+
+
+# ------------------------------------------------------------------ combinations of the node store with other features
+def test_dense_output_with_callbacks_equals_the_one_shot_run():
+    """Chunked launches (callback every k accepted steps) append to the same paged store: same nodes, same interpolants."""
+    de = _de()
+    y0 = torch.as_tensor(de.benchmarks.lorenz_ensemble(300, seed=4))
+
+    def run(callback):
+        a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, dense_output=True)
+        a.method = "RK45"
+        a.callback_every = 7
+        a.integrate(callback=callback)
+        return a
+    calls = []
+    one, chunked = run(None), run(lambda s: calls.append(1))
+    assert len(calls) > 10 and torch.equal(one[-1].y, chunked[-1].y) and torch.equal(one.sol.node_count, chunked.sol.node_count)
+    grid = torch.linspace(0.0, 1.0, 9, dtype=torch.float64)
+    assert torch.equal(one.sol.grid(grid), chunked.sol.grid(grid))
+    t0, y0_rows = one.steps(17)
+    t1, y1_rows = chunked.steps(17)
+    assert torch.equal(t0, t1) and torch.equal(y0_rows, y1_rows)
+
+
+def test_single_system_history_with_events_and_with_the_protocol_loop():
+    de = _de()
+    ev = de.events.component_crossing(0, 0.0, dim=2, direction=-1)
+    a = _sho("RK45", dt=0.01, rtol=1e-9, atol=1e-9)
+    a.integrate(events=ev)                                     # history + events: stage-level kernels, row store
+    b = _sho("RK45", dt=0.01, rtol=1e-9, atol=1e-9)
+    b.integrate()
+    assert len(a) == len(b) and float((a.t - b.t).abs().max()) <= 1e-9 and len(a.events) == 1
+    assert abs(float(a.events[0].t) - np.pi / 2) <= 1e-8
+    term = de.events.component_crossing(0, 0.0, dim=2, direction=-1, is_terminal=True)
+    c = _sho("RK45", dense=True, dt=0.01, rtol=1e-9, atol=1e-9)
+    c.integrate(events=term)                                   # stops at the event: the history ends there
+    assert abs(float(c.t[-1]) - np.pi / 2) <= 1e-8 and len(c) < len(b) and float(c.t[-1]) == float(c[-1].t)
+    assert float((c.sol(1.0) - b[1.0].y).abs().max()) < 1.0     # dense output next to events is available
+    # a Richardson-wrapped integrator with dense output: nodes come from the protocol loop
+    R = de.integrators.generate_richardson_integrator(de.integrators.RK4Solver, richardson_iter=2)
+    d = _sho("RK45", dense=True, dt=0.1, rtol=1e-9, atol=1e-9)
+    d.set_method(R)
+    d.integrate()
+    assert len(d.sol) == len(d) and abs(float(d.sol(1.0)[0]) - np.cos(1.0)) < 1e-7

@@ -186,6 +186,28 @@ def test_integrator_protocol_drives_the_reference_loop():
     assert bool((t == tf).all())
     assert np.array_equal(steps.cpu().numpy(), g["accepted"][:n])
     assert rel_inf(y.cpu().numpy(), g["y_final"][:, :n]).max() <= 1e-10
+    # the same loop as shipped: OdeSystem drives an integrator it does not know (here: a subclass, which takes the
+    # system off the fused and stage-level fast paths) through `_run_protocol`
+    class Wrapped(de.integrators.IntegratorTemplate):
+        symplectic, order = False, 5.0
+
+        def __init__(self, sys_dim, **kw):
+            super().__init__()
+            self.inner = de.integrators.RK45CKSolver(sys_dim, kw.get("dtype"), rtol=kw.get("rtol"), atol=kw.get("atol"),
+                                                     device=kw.get("device"))
+            self.rtol, self.atol, self.dim, self.dtype, self.device = self.inner.rtol, self.inner.atol, self.inner.dim, None, None
+            self.is_implicit = False
+
+        def __call__(self, rhs_, t_, y_, consts, timestep):
+            return self.inner(rhs_, t_, y_, consts, timestep)
+
+        def dense_output(self):
+            return self.inner.dense_output()
+    s = de.OdeSystem(rhs, torch.as_tensor(g["y0"][:, 3].copy()), t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9)
+    s.set_method(Wrapped)
+    s.integrate()
+    assert len(s) - 1 == int(g["accepted"][3]) and rel_inf(s[-1].y.cpu().numpy()[:, None], g["y_final"][:, 3:4]).max() <= 1e-10
+    assert s.success and float(s[-1].t) == 2.0
     # single system: 0-d time and step, reference return convention
     one = de.integrators.RK45CKSolver((3,), torch.float64, rtol=1e-9, atol=1e-9)
     nd, (dT, dY) = one(rhs, torch.tensor(0.0), torch.as_tensor(g["y0"][:, 0].copy()).cuda(), {}, timestep=torch.tensor(1e-2))
