@@ -64,6 +64,8 @@ class ErkRunArgs(C.Structure):
         ("out_y", C.c_void_p), ("out_t", C.c_void_p), ("out_dt", C.c_void_p),
         ("out_accepted", C.c_void_p), ("out_rejected", C.c_void_p), ("out_status", C.c_void_p),
         ("out_stride", C.c_int64), ("out_index_mul", C.c_int64), ("out_index_add", C.c_int64),
+        # ABI 3: stop list
+        ("stops", C.c_void_p), ("n_stops", C.c_int32), ("stop_y", C.c_void_p), ("stop_stride", C.c_int64),
     ]
 
 

@@ -83,7 +83,7 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     default: break;
     }
     if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = p->fused_launch_events_dy =
-        p->fused_launch_scatter = p->fused_launch_dense = nullptr;
+        p->fused_launch_scatter = p->fused_launch_dense = p->fused_launch_multi = nullptr;
 
     double2 host_tab[fm::ATAN_TABLE_SIZE];
     fm::build_atan_table(host_tab);
@@ -151,7 +151,7 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
     DeviceGuard guard(h->device);
     if (a->n_events > 0) {
         if (a->n_events > DSB_MAX_EVENTS || !a->ev_coef || !a->ev_flags || !a->ev_records || !a->ev_count ||
-            a->ev_capacity < 1 || a->store.pool) {
+            a->ev_capacity < 1 || a->store.pool || a->stops) {
             set_error("dsb_erk_run: events need ev_coef, ev_flags, ev_records, ev_count, ev_capacity >= 1, at most %d "
                       "events, and no dense-output store in the same call", DSB_MAX_EVENTS);
             return DSB_ERR_BAD_ARGUMENT;
@@ -164,7 +164,7 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
     }
     if (a->out_y) {
         if (!a->out_t || !a->out_dt || !a->out_accepted || !a->out_rejected || !a->out_status || !a->fresh || !a->y_init ||
-            a->out_index_mul < 1 || a->out_index_add < 0 || a->out_stride < 1 || a->store.pool) {
+            a->out_index_mul < 1 || a->out_index_add < 0 || a->out_stride < 1 || a->store.pool || a->stops) {
             set_error("dsb_erk_run: the scatter-store needs every out_* pointer, out_stride >= 1, out_index_mul >= 1, "
                       "out_index_add >= 0, fresh != 0, y_init, and no dense-output store");
             return DSB_ERR_BAD_ARGUMENT;
@@ -175,6 +175,18 @@ int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *a, void *stream)
             return DSB_ERR_UNSUPPORTED;
         }
         return h->fused_launch_scatter(h, a, (cudaStream_t)stream);
+    }
+    if (a->stops) {
+        if (a->n_stops < 1 || !a->stop_y || a->stop_stride < a->n || a->store.pool || a->max_steps >= 0) {
+            set_error("dsb_erk_run: a stop list needs n_stops >= 1, stop_y, stop_stride >= n, max_steps < 0 and neither events, "
+                      "a node store nor a scatter-store in the same call");
+            return DSB_ERR_BAD_ARGUMENT;
+        }
+        if (!h->fused_launch_multi) {
+            set_error("dsb_erk_run: no multi-stop kernel for rhs_id=%d stages=%d (<= 7 stages)", h->rhs_id, h->stages);
+            return DSB_ERR_UNSUPPORTED;
+        }
+        return h->fused_launch_multi(h, a, (cudaStream_t)stream);
     }
     if (a->store.pool) {
         if (!h->fused_launch_dense) { set_error("dsb_erk_run: no dense-output kernel for this handle"); return DSB_ERR_UNSUPPORTED; }

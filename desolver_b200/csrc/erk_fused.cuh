@@ -206,7 +206,11 @@ static __device__ __noinline__ void flow_done(uint32_t *counter)
 // DENSE: one node (t, y, f = rhs(t, y)) per accepted step goes to the paged node store (dsb_node_store, node_store.cu):
 // dense output and the per-step history of single systems.  Its own instantiation: the node's right-hand side and the
 // page cursor would otherwise live in the hot loop of the plain kernel.
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
+// MULTI: a list of stop times (dsb_erk_run_args.stops) instead of one final time: every trajectory integrates to
+// stops[0], its state is recorded, it continues to stops[1] with integrate()'s entry logic re-applied, ... -- the
+// reference's `for t in t_eval: ode_system.integrate(t)` (differential_system.py:1245-1248) inside ONE launch, bit for bit.
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false,
+          bool MULTI = false>
 #ifndef DSB_EV_MAX_BLOCKS
 #define DSB_EV_MAX_BLOCKS 5
 #endif
@@ -218,6 +222,8 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     using A = Ar<STRICT>;
     constexpr bool EV = EVK != 0;
     static_assert(!(DENSE && (FLOW || SCATTER || EVK != 0)), "the dense-output kernel is device-resident and event-free");
+    static_assert(!(MULTI && (FLOW || SCATTER || EVK != 0 || DENSE)), "the multi-stop kernel is a plain device-resident run");
+    constexpr bool LANE_TF = EV || MULTI;          // the final time is a per-lane value
     constexpr int S = Tab::S, D = Rhs::DIM, NP = Rhs::NPARAM;
     constexpr unsigned FULL = 0xffffffffu;
     const Tab tab(P.tab);
@@ -381,10 +387,31 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
     // and after every accepted step, so the loop top has no per-attempt bookkeeping.
     double tf_lane = tf;               // EV: a terminal event re-targets the trajectory to the event time
     bool final_leg = false;            // EV: re-integration to a terminal root in progress (events are off, :1054)
+    int kstop = 0;                     // MULTI: index of the stop this trajectory is heading for
     auto start_step = [&]() {
-        const double tfc = EV ? tf_lane : tf;
+        const double tfc = LANE_TF ? tf_lane : tf;
         final_step = fabs(dt + t) > fabs(tfc);
         h = final_step ? (tfc - t) : dt;
+    };
+    // MULTI: the trajectory stands at stops[kstop] (record = true: write its state there) or starts (kstop = -1): move to
+    // the next stop with integrate()'s entry logic (differential_system.py:956-957, 971-974); false = no stop is left
+    auto advance_stop = [&](bool record) -> bool {
+        for (;;) {
+            if (record) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) P.a.stop_y[((long long)kstop * D + d) * P.a.stop_stride + idx] = y[d];
+            }
+            if (kstop + 1 >= P.a.n_stops) return false;
+            kstop++;
+            tf_lane = P.a.stops[kstop];
+            const double span = tf_lane - t;
+            record = true;
+            if (fabs(span) < DSB_EPS4) continue;                         // integrate() returns at once: same state
+            if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
+            if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+            if (!((dt != 0.0) && (fabs(span) >= DSB_EPS32))) continue;   // the while condition (:996) fails: same state
+            return true;
+        }
     };
     // g_e(t, y) of the hyperplane events
     auto ev_g = [&](int e, double tt, const double (&yy)[D]) -> double {
@@ -429,8 +456,16 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
             }
         }
         if (!live && done) {                                             // finished earlier, result still in registers
-            bool more = (dt != 0.0) && (fabs((EV ? tf_lane : tf) - t) >= DSB_EPS32);
-            store(more ? (int)DSB_TRAJ_RUNNING : ((EV && final_leg) ? (int)DSB_TRAJ_EVENT : (int)DSB_TRAJ_DONE));
+            bool more = (dt != 0.0) && (fabs((LANE_TF ? tf_lane : tf) - t) >= DSB_EPS32);
+            bool on = false;
+            if constexpr (MULTI) on = !more && advance_stop(true);       // reached a stop: record it, head for the next
+            if (on) {
+                start_step();
+                live = true;
+                trial = 0;
+            } else {
+                store(more ? (int)DSB_TRAJ_RUNNING : ((EV && final_leg) ? (int)DSB_TRAJ_EVENT : (int)DSB_TRAJ_DONE));
+            }
             done = false;
         }
         // refill idle lanes from the queue (warp-aggregated atomicAdd); a loaded trajectory that has nothing to
@@ -491,16 +526,21 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     }
                     if (fresh) P.a.ev_count[idx] = 0;
                 }
-                if (go && P.a.first_call) {
-                    // integrate() entry: differential_system.py:956-957, 971-974
-                    double span = tf - t;
-                    if (fabs(span) < DSB_EPS4) go = false;
-                    else {
-                        if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
-                        if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+                if constexpr (MULTI) {
+                    kstop = -1;
+                    if (go) go = advance_stop(false);                          // entry logic towards stops[0] (or further)
+                } else {
+                    if (go && P.a.first_call) {
+                        // integrate() entry: differential_system.py:956-957, 971-974
+                        double span = tf - t;
+                        if (fabs(span) < DSB_EPS4) go = false;
+                        else {
+                            if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
+                            if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+                        }
                     }
+                    go = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);     // :996
                 }
-                go = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);         // :996
                 if (go && P.a.max_steps == 0) go = false;
                 if (go) {
                     live = true;
@@ -513,7 +553,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                     }
                 } else {
                     const bool frozen = st0 == (int)DSB_TRAJ_TOL_FAIL || st0 == (int)DSB_TRAJ_EVENT;
-                    bool more = !frozen && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+                    bool more = !MULTI && !frozen && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
                     store(frozen ? st0 : (more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE));
                 }
             }
@@ -713,7 +753,7 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
                 }
             }
             start_step();
-            done = !((dt != 0.0) && (fabs((EV ? tf_lane : tf) - t) >= DSB_KC(eps32, DSB_EPS32)))   // :996
+            done = !((dt != 0.0) && (fabs((LANE_TF ? tf_lane : tf) - t) >= DSB_KC(eps32, DSB_EPS32)))   // :996
                    || acc >= step_budget;
             live = !done;
         }
@@ -858,19 +898,21 @@ erk_fused_kernel(const __grid_constant__ ErkKernelArgs<Tab::S> P)
 }
 
 // Host-side launcher, one per instantiation.
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false,
+          bool MULTI = false>
 int launch_erk_fused(const ErkKernelArgs<Tab::S> &args, int blocks, cudaStream_t stream)
 {
-    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE><<<blocks, ERK_THREADS, 0, stream>>>(args);
+    erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE, MULTI><<<blocks, ERK_THREADS, 0, stream>>>(args);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false,
+          bool MULTI = false>
 int occupancy_erk_fused(int *blocks_per_sm)
 {
     DSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE>, ERK_THREADS, 0));
+        blocks_per_sm, erk_fused_kernel<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE, MULTI>, ERK_THREADS, 0));
     return DSB_OK;
 }
 

@@ -32,6 +32,9 @@ struct dsb_erk_plan {
     // same kernel writing one node per accepted step to the paged node store (dense output / step history)
     int (*fused_launch_dense)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
     int dense_blocks = 0;
+    // same kernel heading for a list of stop times (solve_ivp's t_eval in one launch); <= 7 stages
+    int (*fused_launch_multi)(const dsb_erk_plan *, const dsb_erk_run_args *, cudaStream_t) = nullptr;
+    int multi_blocks = 0;
 };
 
 namespace dsb {
@@ -63,7 +66,8 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
-template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false>
+template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false,
+          bool MULTI = false>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
 {
     ErkKernelArgs<Tab::S> args;
@@ -71,8 +75,8 @@ int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStrea
     fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
     args.factor_table = p->d_factor;
-    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE>(
-        args, DENSE ? p->dense_blocks : (EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks)), stream);
+    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE, MULTI>(
+        args, MULTI ? p->multi_blocks : DENSE ? p->dense_blocks : (EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks)), stream);
 }
 
 // true iff the caller's tableau equals the compile-time one bit for bit
@@ -111,6 +115,12 @@ void bind_fused(dsb_erk_plan *p, int *per_sm)
         int d_per_sm = 0;
         occupancy_erk_fused<Rhs, Tab, STRICT, false, 0, false, true>(&d_per_sm);
         p->dense_blocks = p->sm_count * (d_per_sm < 1 ? 1 : d_per_sm);
+    }
+    if constexpr (Tab::S <= 7) {
+        p->fused_launch_multi = fused_trampoline<Rhs, Tab, STRICT, false, 0, false, false, true>;
+        int m_per_sm = 0;
+        occupancy_erk_fused<Rhs, Tab, STRICT, false, 0, false, false, true>(&m_per_sm);
+        p->multi_blocks = p->sm_count * (m_per_sm < 1 ? 1 : m_per_sm);
     }
     occupancy_erk_fused<Rhs, Tab, STRICT>(per_sm);
 }

@@ -322,6 +322,7 @@ class OdeSystem(object):
                 raise ValueError("Expected rhs to return a shape that is compatible with y0, got shapes "
                                  "Shape[y0]={} and Shape[dy]={}".format(tuple(self._user_shape(self._y0).shape),
                                                                         tuple(known) + ((self.n_traj,) if self.ensemble else ())))
+            self._param_tensors(tuple(self.equ_rhs.plugin_params), dict(self.equ_rhs.plugin_defaults))   # shapes of the constants
             self.equ_rhs.nfev += 1                          # the reference's constructor evaluates the rhs once
         else:
             probe = self.equ_rhs(self._user_time(torch.full((self.n_traj,), self.__t0, dtype=torch.float64,
@@ -879,7 +880,7 @@ class OdeSystem(object):
             raise MemoryError("dense-output node store could not be sized")
         self._steps_cache = None
 
-    def _launch_fused(self, tf, plugin, max_steps, first_call, events, store):
+    def _launch_fused(self, tf, plugin, max_steps, first_call, events, store, stops=None):
         integ = self.integrator
         pid, names, defaults = plugin
         handle = cb.erk_handle(self.device.index or 0, pid, self.numel, integ.tableau_intermediate,
@@ -916,6 +917,9 @@ class OdeSystem(object):
         if store is not None:
             a.store = store.struct()
             store.invalidate()
+        if stops is not None:
+            a.stops, a.n_stops = stops[0].data_ptr(), int(stops[0].numel())
+            a.stop_y, a.stop_stride = stops[1].data_ptr(), self.n_traj
         a.counters = self._counters.data_ptr()
         if events:
             coef, flags = self._event_tensors(events)
@@ -1040,6 +1044,50 @@ class OdeSystem(object):
         self._raw_accepted, self._raw_rejected = self._host_acc_buffer, self._host_rej_buffer
         self._host_status_clean = int(c[:, 4].sum()) + int(c[:, 5].sum()) == 0
         return int(c[:, 2].sum()), int(c[:, 3].sum()), int(c[:, 4].sum()), int(c[:, 5].sum())
+
+    def integrate_stops(self, times):
+        """Integrates every trajectory through the stop times `times` (monotone in the direction of integration) exactly
+        as successive `integrate(t)` calls would -- the reference's `t_eval` loop (`differential_system.py:1245-1248`) --
+        and returns the states at the stops, shape (T, *dim[, N]).  For a fused right-hand side with an explicit method
+        of at most 7 stages this is ONE launch of the multi-stop kernel (dsb_erk_run_args.stops), bit-identical to the
+        sequence of calls; otherwise it is that sequence."""
+        torch = _torch()
+        times = [float(x) for x in np.asarray(times, dtype=np.float64).reshape(-1)]
+        if not times:
+            raise ValueError("integrate_stops needs at least one time")
+        plugin = self._fused_plugin() if self.use_fused else None
+        fast = (plugin is not None and not self.host_io and not self._want_nodes and not self.integrator.symplectic
+                and self.integrator.stages <= 7 and not getattr(self.integrator, "has_custom_adaptation", False))
+        if not fast:
+            rows = []
+            for tq in times:
+                self.integrate(tq)
+                rows.append(self[-1].y.clone())
+            return torch.stack(rows)
+        with torch.cuda.device(self.device):
+            self._detach_history()
+            stops = torch.as_tensor(times, dtype=torch.float64).to(self.device)
+            out = torch.empty((len(times), self.numel, self.n_traj), dtype=torch.float64, device=self.device)
+            self._launch_fused(times[-1], plugin, -1, True, None, None, stops=(stops, out))
+            st = self._fused_stats()
+            prev = self._stats or dict(attempts=0, accepted=0)
+            self._stats = dict(attempts=prev["attempts"] + st[0], accepted=prev["accepted"] + st[1], failed=st[2], running=st[3])
+            for k in range(len(times) - 1):                        # one history row per stop, like one per integrate() call
+                self._hist_y.append(out[k])
+                self._hist_t.append(times[k])
+            self._hist_y.append(self._raw_y)
+            self._hist_t.append(self._raw_t)
+            self._hist_alias = True
+            self._keepalive = (self._keepalive, stops, out)
+            if st[2]:
+                new_e = etypes.FailedIntegration("Failed to integrate system")
+                new_e.__cause__ = etypes.FailedToMeetTolerances(
+                    "Failed to integrate {} of {} trajectories to the tolerances required: rtol={}, atol={}".format(
+                        st[2], self.n_traj, self.integrator.rtol, self.integrator.atol))
+                self.__int_status = new_e
+                raise new_e
+            self.__int_status = 1
+        return out.reshape((len(times),) + tuple(self.dim) + ((self.n_traj,) if self.ensemble else ()))
 
     def _run_push(self, tf, plugin):
         """Sharded ensemble, gather overlapped with the integration: ONE flow-controlled persistent launch
@@ -1841,6 +1889,12 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
             else:
                 y_res = torch.movedim(system.sol(grid), 0, -1)               # (*dim, T)
             t_res = grid
+        elif not callbacks and events is None and not options.get("show_prog_bar", False) and not system._want_nodes:
+            # exact stops like the reference's loop of integrate(t) calls; ONE launch where the multi-stop kernel applies
+            rows = system.integrate_stops(t_eval)                                 # (T, *dim[, N])
+            y_res = torch.movedim(rows, 0, -1)
+            grid = torch.as_tensor(t_eval, dtype=torch.float64, device=system.device)
+            t_res = grid.expand(system.n_traj, -1) if system.ensemble else grid
         else:
             ts, ys = [], []
             for tq in t_eval:

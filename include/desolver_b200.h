@@ -177,6 +177,17 @@ typedef struct {
     double *out_t, *out_dt;    /* [>= n * out_index_mul]                                                          */
     int32_t *out_accepted, *out_rejected, *out_status;
     int64_t out_stride, out_index_mul, out_index_add;
+    /* ---- ABI 3: stop list (stops = NULL: off) -------------------------------------------------------------------
+     * The reference serves `solve_ivp(..., t_eval=...)` by calling integrate(t) once per time (differential_system.py:
+     * 1245-1248): every t_eval[k] is an exact stop of the integration.  With a stop list ONE launch does the same per
+     * trajectory: integrate to stops[0] (entry logic :956-957, 971-974, final-step clamp :997-1002), record the state
+     * in stop_y[0], continue to stops[1] with the entry logic re-applied and dt carried over (a final clamped step does
+     * not update it, :1070-1071), ...  `tf` is ignored (the last stop is the final time); y, t, dt, accepted, rejected,
+     * status receive the state at the last stop.  max_steps must be < 0; no events, node store or scatter-store. */
+    const double *stops;       /* device [n_stops], monotone in the direction of integration                     */
+    int32_t n_stops;
+    double *stop_y;            /* device [n_stops][dim][stop_stride] out                                          */
+    int64_t stop_stride;       /* >= n                                                                             */
 } dsb_erk_run_args;
 
 DSB_API int dsb_erk_run(dsb_erk_handle h, const dsb_erk_run_args *args, void *stream);

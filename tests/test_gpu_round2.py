@@ -182,6 +182,15 @@ def test_solve_ivp_t_eval_matches_the_reference_and_the_dense_mode():
     for q in range(g["t_eval"].shape[0]):
         assert rel_inf(r.y[..., q].cpu().numpy(), g["y"][..., q]).max() <= 1e-10
     assert np.max(np.abs(r.t.cpu().numpy() - g["t"])) <= 1e-13
+    # ... served by ONE launch of the multi-stop kernel, bit-identical to the sequence of integrate(t) calls it replaces
+    assert r.ode_system._launches == 1 and len(r.ode_system) == 1 + len(g["t_eval"])
+    seq = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 1.5), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    seq.method = "RK45"
+    for q, tq in enumerate(g["t_eval"]):
+        seq.integrate(float(tq))
+        assert torch.equal(seq[-1].y, r.y[..., q])
+    assert torch.equal(seq.accepted, r.ode_system.accepted) and torch.equal(seq.rejected, r.ode_system.rejected)
+    assert torch.equal(seq.dt, r.ode_system.dt) and torch.equal(seq[-1].t, r.ode_system[-1].t)
     d = de.solve_ivp(de.rhs_plugins.lorenz, (0.0, 1.5), y0, method="RK45", t_eval=g["t_eval"], rtol=1e-9, atol=1e-9,
                      first_step=1e-2, ensemble=True, t_eval_mode="dense")
     assert d.ode_system._launches == 1                          # one integration; the evaluation is one more launch
