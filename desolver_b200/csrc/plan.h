@@ -1,11 +1,16 @@
 // plan.h -- host-side handle behind dsb_erk_handle, shared by abi.cu and the kernel translation units.
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
 
 #include "common.cuh"
 #include "erk_fused.cuh"
+
+#ifndef DSB_ERK_LATENCY_WARPS
+#define DSB_ERK_LATENCY_WARPS 3.0      // resident warps per scheduler at which the FP64 pipe, not latency, bounds an iteration
+#endif
 
 struct dsb_erk_plan {
     int device = 0, rhs_id = 0, dim = 0, stages = 0, final_rows = 0;
@@ -66,6 +71,33 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
     t.order_p = (p2 == (double)(int)p2 && p2 >= 1.0 && p2 <= 64.0) ? (int)p2 : 0;
 }
 
+// Persistent grid for an ensemble of n trajectories: `full` = SMs x resident blocks is right when the ensemble is many
+// waves deep.  A small ensemble (a few waves: the strong-scaling shards of the 2^20 benchmark ensemble, 131072
+// trajectories per GPU at 8 GPUs) finishes sooner on FEWER resident blocks: with w warps per scheduler an iteration costs
+// max(w * c_pipe, c_latency) cycles, so below the point where the FP64 pipe saturates extra residency only stretches
+// every trajectory's latency, and the run is a whole number of such latencies long.  The choice minimises
+// (waves + 1/2) * iteration cost over the block counts per SM; DSB_ERK_BLOCKS_PER_SM overrides it (measurements).
+inline int grid_for_ensemble(const dsb_erk_plan *p, int full, long long n)
+{
+    const int max_per_sm = full / (p->sm_count > 0 ? p->sm_count : 1);
+    if (max_per_sm <= 1) return full;
+    if (const char *env = getenv("DSB_ERK_BLOCKS_PER_SM")) {
+        int w = atoi(env);
+        if (w >= 1 && w <= max_per_sm) return p->sm_count * w;
+    }
+    const double c_pipe = 1.0, c_latency = DSB_ERK_LATENCY_WARPS;     // in units of one warp's pipe-bound iteration
+    double best = 1e300;
+    int best_w = max_per_sm;
+    for (int w = 1; w <= max_per_sm; ++w) {
+        const double lanes = (double)p->sm_count * w * ERK_THREADS;
+        const double waves = (double)n / lanes;
+        const double iter = (w * c_pipe > c_latency ? w * c_pipe : c_latency);
+        const double cost = (waves < 1.0 ? 1.0 : waves + 0.5) * iter;
+        if (cost < best * 0.999) { best = cost; best_w = w; }
+    }
+    return p->sm_count * best_w;
+}
+
 template <class Rhs, class Tab, bool STRICT, bool FLOW = false, int EVK = 0, bool SCATTER = false, bool DENSE = false,
           bool MULTI = false>
 int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStream_t stream)
@@ -75,8 +107,9 @@ int fused_trampoline(const dsb_erk_plan *p, const dsb_erk_run_args *a, cudaStrea
     fill_tableau<Tab::S>(p, args.tab);
     args.atan_table = p->d_atan;
     args.factor_table = p->d_factor;
-    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE, MULTI>(
-        args, MULTI ? p->multi_blocks : DENSE ? p->dense_blocks : (EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks)), stream);
+    int blocks = MULTI ? p->multi_blocks : DENSE ? p->dense_blocks : (EVK == 2 ? p->events_dy_blocks : (EVK == 1 ? p->events_blocks : p->fused_blocks));
+    blocks = grid_for_ensemble(p, blocks, a->n);
+    return launch_erk_fused<Rhs, Tab, STRICT, FLOW, EVK, SCATTER, DENSE, MULTI>(args, blocks, stream);
 }
 
 // true iff the caller's tableau equals the compile-time one bit for bit
