@@ -8,10 +8,6 @@
 #include "common.cuh"
 #include "erk_fused.cuh"
 
-#ifndef DSB_ERK_LATENCY_WARPS
-#define DSB_ERK_LATENCY_WARPS 3.0      // resident warps per scheduler at which the FP64 pipe, not latency, bounds an iteration
-#endif
-
 struct dsb_erk_plan {
     int device = 0, rhs_id = 0, dim = 0, stages = 0, final_rows = 0;
     double order = 0.0;
@@ -72,11 +68,12 @@ void fill_tableau(const dsb_erk_plan *p, TableauData<S> &t)
 }
 
 // Persistent grid for an ensemble of n trajectories: `full` = SMs x resident blocks is right when the ensemble is many
-// waves deep.  A small ensemble (a few waves: the strong-scaling shards of the 2^20 benchmark ensemble, 131072
-// trajectories per GPU at 8 GPUs) finishes sooner on FEWER resident blocks: with w warps per scheduler an iteration costs
-// max(w * c_pipe, c_latency) cycles, so below the point where the FP64 pipe saturates extra residency only stretches
-// every trajectory's latency, and the run is a whole number of such latencies long.  The choice minimises
-// (waves + 1/2) * iteration cost over the block counts per SM; DSB_ERK_BLOCKS_PER_SM overrides it (measurements).
+// waves deep (the 2^20-trajectory benchmark: 9.2 waves).  A SMALL ensemble finishes sooner on fewer resident blocks:
+// the run is (waves + ~1/2) trajectory latencies long -- never less than ~1.25 -- and a trajectory's latency grows with the
+// warps that share a scheduler.  Measured for Cash-Karp x Lorenz (tools/grid_sweep.py, latency of one trajectory relative
+// to one block per SM): 1.00, 1.24, 1.54, 1.89, 2.28, 2.71 for 1..6 blocks, i.e. about 1 + 0.34 (w - 1).  Ensembles of at
+// least 3 waves keep the full grid; below that the block count per SM minimises the model
+// (2^15 trajectories: 0.34 -> 0.23 ms, 2^16: 0.46 -> 0.34 ms, 2^17: 0.58 -> 0.57 ms).  DSB_ERK_BLOCKS_PER_SM overrides.
 inline int grid_for_ensemble(const dsb_erk_plan *p, int full, long long n)
 {
     const int max_per_sm = full / (p->sm_count > 0 ? p->sm_count : 1);
@@ -85,15 +82,16 @@ inline int grid_for_ensemble(const dsb_erk_plan *p, int full, long long n)
         int w = atoi(env);
         if (w >= 1 && w <= max_per_sm) return p->sm_count * w;
     }
-    const double c_pipe = 1.0, c_latency = DSB_ERK_LATENCY_WARPS;     // in units of one warp's pipe-bound iteration
+    const double lanes_per_block_row = (double)p->sm_count * ERK_THREADS;
+    if ((double)n >= 3.0 * lanes_per_block_row * max_per_sm) return full;
     double best = 1e300;
     int best_w = max_per_sm;
-    for (int w = 1; w <= max_per_sm; ++w) {
-        const double lanes = (double)p->sm_count * w * ERK_THREADS;
-        const double waves = (double)n / lanes;
-        const double iter = (w * c_pipe > c_latency ? w * c_pipe : c_latency);
-        const double cost = (waves < 1.0 ? 1.0 : waves + 0.5) * iter;
-        if (cost < best * 0.999) { best = cost; best_w = w; }
+    for (int w = max_per_sm; w >= 1; --w) {
+        const double waves = (double)n / (lanes_per_block_row * w);
+        const double latency = 1.0 + 0.34 * (w - 1);
+        const double rounds = waves + 0.55 > 1.25 ? waves + 0.55 : 1.25;
+        const double cost = rounds * latency;
+        if (cost < best * 0.995) { best = cost; best_w = w; }          // ties go to the larger grid
     }
     return p->sm_count * best_w;
 }
