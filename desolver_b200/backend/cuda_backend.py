@@ -116,6 +116,7 @@ class ErkStageArgs(C.Structure):
         ("ev_records", C.c_void_p), ("ev_count", C.c_void_p),
         ("ev_state", C.c_void_p), ("tf_per", C.c_void_p),
         ("ev_coef_dy", C.c_void_p),
+        ("rtol_vec", C.c_void_p), ("atol_vec", C.c_void_p),
     ]
 
 

@@ -243,7 +243,8 @@ __global__ void stage_increment_kernel(dsb_erk_stage_args a, KPtrs K, FinalRows 
             double sc = np_maximum(fabs(a.y[e]), fabs(slope));
             if (trial > 0) sc = A::add(A::mul(0.8, a.scale[e]), A::mul(0.2, sc));
             a.scale[e] = sc;
-            double tol = A::mad(a.rtol, sc, a.atol);
+            // array-valued tolerances (reference integrator_types.py:37-38 accepts them): one (rtol, atol) per component
+            double tol = A::mad(a.rtol_vec ? a.rtol_vec[d] : a.rtol, sc, a.atol_vec ? a.atol_vec[d] : a.atol);
             double qv = STRICT ? err / tol : fm::fast_div(err, tol);
             x = first ? __dmul_rn(qv, qv) : fma(qv, qv, x);
             first = false;
@@ -282,7 +283,7 @@ __global__ void stage_increment_wide_kernel(dsb_erk_stage_args a, KPtrs K, Final
             double sc = np_maximum(fabs(a.y[e]), fabs(dY / h));
             if (trial > 0) sc = A::add(A::mul(0.8, a.scale[e]), A::mul(0.2, sc));
             a.scale[e] = sc;
-            const double qv = err / A::mad(a.rtol, sc, a.atol);
+            const double qv = err / A::mad(a.rtol_vec ? a.rtol_vec[d] : a.rtol, sc, a.atol_vec ? a.atol_vec[d] : a.atol);
             x = fma(qv, qv, x);
         }
     }

@@ -627,7 +627,7 @@ class OdeSystem(object):
 
     @rtol.setter
     def rtol(self, new_rtol):
-        self.__rtol = float(new_rtol)
+        self.__rtol = new_rtol if np.size(new_rtol) > 1 else float(new_rtol)
         self.initialise_integrator()
 
     @property
@@ -636,7 +636,7 @@ class OdeSystem(object):
 
     @atol.setter
     def atol(self, new_atol):
-        self.__atol = float(new_atol)
+        self.__atol = new_atol if np.size(new_atol) > 1 else float(new_atol)
         self.initialise_integrator()
 
     @property
@@ -746,6 +746,8 @@ class OdeSystem(object):
         if not isinstance(self.integrator, integrators.RungeKuttaIntegrator):
             return None
         if self.integrator.stages not in cb.FUSED_STAGES or len(self.dim) != 1:
+            return None
+        if self.integrator.has_vector_tolerances:          # one tolerance per component: stage-level kernels
             return None
         return pid, tuple(rhs.plugin_params), dict(rhs.plugin_defaults)
 
@@ -1164,6 +1166,7 @@ class OdeSystem(object):
         dense = store is not None
         full = dict(y=self._y, t=self._t, dt=self._dt, accepted=self.accepted, rejected=self.rejected, status=self.status)
         persistent = ("h", "h0", "trial", "flags", "scale", "hist")     # per-trajectory state that outlives an attempt
+        tol_vec = integ.tolerance_arrays(dev) if integ.has_vector_tolerances else None
 
         def alloc(m):
             return dict(h=torch.zeros(m, **f64), h0=torch.zeros(m, **f64), y_stage=torch.empty((D, m), **f64),
@@ -1177,7 +1180,11 @@ class OdeSystem(object):
             a.y, a.t, a.dt = work["y"].data_ptr(), work["t"].data_ptr(), work["dt"].data_ptr()
             for k, v in buf.items():
                 setattr(a, k, v.data_ptr())
-            a.tf, a.rtol, a.atol = float(tf), float(integ.rtol), float(integ.atol)
+            a.tf = float(tf)
+            if tol_vec is not None:
+                a.rtol_vec, a.atol_vec = tol_vec[0].data_ptr(), tol_vec[1].data_ptr()
+            else:
+                a.rtol, a.atol = float(integ.rtol), float(integ.atol)
             a.accepted, a.rejected, a.status = work["accepted"].data_ptr(), work["rejected"].data_ptr(), work["status"].data_ptr()
             a.counters = self._counters.data_ptr()
             shape = tuple(self.dim) + ((m,) if self.ensemble else ())

@@ -137,9 +137,10 @@ class TableauIntegrator(IntegratorTemplate, abc.ABC):
         self.numel = int(np.prod(self.dim)) if len(self.dim) else 1
         self.dtype = dtype
         self.device = device
-        # defaults: 32 * D.epsilon(dtype) = 128 eps (reference integrator_types.py:37-38)
-        self.rtol = float(rtol) if rtol is not None else 32 * D.epsilon(dtype if dtype is not None else "float64")
-        self.atol = float(atol) if atol is not None else 32 * D.epsilon(dtype if dtype is not None else "float64")
+        # defaults: 32 * D.epsilon(dtype) = 128 eps (reference integrator_types.py:37-38).  Like the reference, a
+        # tolerance may be an array of the state's shape (one value per component); those are kept as float64 arrays.
+        self.rtol = self._tolerance(rtol, dtype)
+        self.atol = self._tolerance(atol, dtype)
         self.dState = None
         self.dTime = None
         self.initial_state = None
@@ -150,6 +151,30 @@ class TableauIntegrator(IntegratorTemplate, abc.ABC):
         self._adaptive = False
         self._fsal = False
         self._last_call = None            # (rhs, constants) of the last protocol step: dense_output() may need rhs(t1, y1)
+
+    def _tolerance(self, value, dtype):
+        if value is None:
+            return 32 * D.epsilon(dtype if dtype is not None else "float64")
+        if hasattr(value, "detach"):
+            value = value.detach().cpu().numpy()
+        arr = np.asarray(value, dtype=np.float64)
+        if arr.size == 1:
+            return float(arr.reshape(-1)[0])
+        return np.ascontiguousarray(np.broadcast_to(arr, self.dim))
+
+    @property
+    def has_vector_tolerances(self):
+        return isinstance(self.rtol, np.ndarray) or isinstance(self.atol, np.ndarray)
+
+    def tolerance_arrays(self, device):
+        """(rtol, atol) as flat float64 device tensors of `numel` entries, for the kernels' per-component tolerance
+        arguments (dsb_erk_stage_args.rtol_vec / atol_vec)."""
+        torch = _torch()
+        out = []
+        for v in (self.rtol, self.atol):
+            arr = np.broadcast_to(np.asarray(v, dtype=np.float64), self.dim).reshape(-1) if len(self.dim) else np.asarray([v])
+            out.append(torch.as_tensor(np.ascontiguousarray(arr), dtype=torch.float64).to(device))
+        return out
 
     @classmethod
     def integrator_order(cls):
@@ -258,7 +283,12 @@ class RungeKuttaIntegrator(TableauIntegrator, abc.ABC):
                 setattr(a, k, v.data_ptr())
             # tf = +/-inf in the direction of the step: the final-step clamp belongs to the caller's loop (:997-1002)
             direction = float(torch.sign(dt[0]).item()) or 1.0
-            a.tf, a.rtol, a.atol = direction * float("inf"), float(self.rtol), float(self.atol)
+            a.tf = direction * float("inf")
+            if self.has_vector_tolerances:
+                tol_keep = self.tolerance_arrays(dev)
+                a.rtol_vec, a.atol_vec = tol_keep[0].data_ptr(), tol_keep[1].data_ptr()
+            else:
+                a.rtol, a.atol = float(self.rtol), float(self.atol)
             a.status, a.counters, a.one_step = status.data_ptr(), counters.data_ptr(), 1
             stream = cb.current_stream_ptr(dev)
             y_view = buf["y_stage"].reshape(shape)

@@ -284,6 +284,9 @@ typedef struct {
     const double *ev_coef_dy;  /* [n_events][dim] weights on dState/dt (NULL: none): events of the reference's
                                   `requires_dstate` kind, g(t, y, dy) with dy = the interpolant's derivative
                                   (differential_system.py:92-96, utilities/interpolation.py:63-78)  */
+    /* ABI 3: array-valued tolerances (integrators/integrator_types.py:37-38 takes `rtol` / `atol` of the state's
+     * shape): one value per state component, shared by the trajectories; NULL = the scalar above                  */
+    const double *rtol_vec, *atol_vec;   /* device [dim]                                          */
 } dsb_erk_stage_args;
 
 DSB_API int dsb_erk_stage_begin(dsb_erk_handle h, const dsb_erk_stage_args *a, int first_call, void *stream);

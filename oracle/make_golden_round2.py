@@ -118,6 +118,31 @@ def main():
             print("richardson %s: %d steps, nfev %d" % (key, len(a) - 1, a.nfev))
         np.savez_compressed(os.path.join(GOLD, "richardson_sho.npz"), **blob)
 
+    if want("vector_tol"):
+        # array-valued tolerances (integrator_types.py:37-38): one (rtol, atol) per state component
+        L = bm.LORENZ
+        lconst = dict(sigma=L["sigma"], rho=L["rho"], beta=L["beta"])
+        y0 = bm.lorenz_ensemble(12, seed=14)
+        rtol, atol = np.array([1e-9, 1e-7, 1e-8]), np.array([1e-9, 1e-10, 1e-6])
+        ys, acc, att = [], [], []
+        for i in range(y0.shape[1]):
+            a = de.OdeSystem(rhs_plugins.lorenz, y0=y0[:, i].copy(), t=(0.0, 2.0), dt=1e-2, rtol=rtol, atol=atol, constants=lconst)
+            a.method = "RK45"
+            calls = [0]
+            inner = a.integrator.step
+
+            def counted(*p, _inner=inner, **k):
+                calls[0] += 1
+                return _inner(*p, **k)
+            a.integrator.step = counted
+            a.integrate()
+            ys.append(np.asarray(a.y[-1]))
+            acc.append(len(a) - 1)
+            att.append(calls[0])
+        np.savez_compressed(os.path.join(GOLD, "lorenz_vector_tol.npz"), y0=y0, rtol=rtol, atol=atol, y_final=np.stack(ys, axis=-1),
+                            accepted=np.array(acc, dtype=np.int32), attempts=np.array(att, dtype=np.int32))
+        print("vector_tol: accepted", acc)
+
     if want("teval"):
         L = bm.LORENZ
         y0 = bm.lorenz_ensemble(6, seed=12)

@@ -465,3 +465,26 @@ def test_single_system_history_with_events_and_with_the_protocol_loop():
     d.set_method(R)
     d.integrate()
     assert len(d.sol) == len(d) and abs(float(d.sol(1.0)[0]) - np.cos(1.0)) < 1e-7
+
+
+def test_array_valued_tolerances():
+    """`rtol` / `atol` of the state's shape, one value per component (reference integrator_types.py:37-38): the stage-level
+    kernels take them as vectors; a fused plugin with such tolerances runs there."""
+    de = _de()
+    g = load_golden("lorenz_vector_tol.npz")
+    for ensemble in (True, False):
+        y0 = torch.as_tensor(g["y0"] if ensemble else g["y0"][:, 0].copy())
+        a = de.OdeSystem(de.rhs_plugins.lorenz, y0, t=(0.0, 2.0), dt=1e-2, rtol=g["rtol"], atol=torch.as_tensor(g["atol"]),
+                         ensemble=ensemble)
+        a.method = "RK45"
+        assert a.integrator.has_vector_tolerances and a._fused_plugin() is None
+        a.integrate()
+        k = slice(None) if ensemble else slice(0, 1)
+        assert np.array_equal(a.accepted.cpu().numpy(), g["accepted"][k])
+        assert np.array_equal((a.accepted + a.rejected).cpu().numpy(), g["attempts"][k])
+        y = a[-1].y.cpu().numpy().reshape(3, -1)
+        assert rel_inf(y, g["y_final"][:, k]).max() <= 1e-9
+    # scalar tolerances given as 0-d arrays stay on the fused path
+    b = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(g["y0"]), t=(0.0, 2.0), dt=1e-2, rtol=np.float64(1e-9), atol=np.array(1e-9),
+                     ensemble=True)
+    assert not b.integrator.has_vector_tolerances and b._fused_plugin() is not None
