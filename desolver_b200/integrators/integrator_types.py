@@ -173,7 +173,7 @@ class TableauIntegrator(IntegratorTemplate, abc.ABC):
         out = []
         for v in (self.rtol, self.atol):
             arr = np.broadcast_to(np.asarray(v, dtype=np.float64), self.dim).reshape(-1) if len(self.dim) else np.asarray([v])
-            out.append(torch.as_tensor(np.ascontiguousarray(arr), dtype=torch.float64).to(device))
+            out.append(torch.as_tensor(np.array(arr, dtype=np.float64), dtype=torch.float64).to(device))
         return out
 
     @classmethod
