@@ -69,3 +69,36 @@ def test_affine_callables_are_recognised_and_others_refused():
     bad.requires_dstate = True
     with pytest.raises(NotImplementedError):
         as_hyperplane(bad, 2)
+
+
+def test_callable_event_wrapper_and_the_affine_probe():
+    """Events that are not affine fall through to CallableEvent (evaluated between the event-search kernels); affine
+    callables are recognised by probing and keep the closed-form device path."""
+    import pytest
+    import torch
+    from desolver_b200.events import CallableEvent, HyperplaneEvent, as_hyperplane
+    from oracle import event_cases as ec
+    hp = as_hyperplane(lambda t, y: 2.0 * y[1] - t + 0.5, 3)
+    assert isinstance(hp, HyperplaneEvent) and np.allclose(hp.coefficients(3), [0.0, 2.0, 0.0, -1.0, -0.5])
+    for fn in (ec.lorenz_sphere, ec.lorenz_product, ec.time_cubic):
+        with pytest.raises(NotImplementedError):
+            as_hyperplane(fn, 3)
+    with pytest.raises(NotImplementedError):                     # depends on a per-trajectory constant
+        as_hyperplane(ec.vdp_energy_mu, 2, dict(mu=torch.linspace(0.1, 1.0, 5)))
+    ev = CallableEvent(ec.lorenz_sphere_terminal)
+    assert ev.is_terminal and ev.direction == 1 and ev.flags == (1 | 4) and not ev.requires_dstate
+    assert np.array_equal(ev.coefficients(3), np.zeros(5)) and ev.signature[0] == "callable"
+    y = torch.tensor([[3.0, 30.0], [4.0, 0.0], [25.0, 25.0]], dtype=torch.float64)
+    assert torch.equal(ev(0.0, y), torch.tensor([25.0 - 484.0, 900.0 - 484.0], dtype=torch.float64))
+    dy = CallableEvent(ec.radius_maximum)
+    assert dy.requires_dstate and dy.flags == (2 | 4)
+
+
+def test_nonaffine_event_fixtures_are_well_formed():
+    from oracle import event_cases as ec
+    for name, (rhs_name, evs, tf, tol, method) in ec.CASES.items():
+        g = load_golden("events2_%s.npz" % name)
+        n = g["y0"].shape[1]
+        assert g["records"].shape[0] == n and g["crossings"].shape == (n, len(evs))
+        # the reference reports a SUBSET of the sign changes it steps over (absolute root tolerance, see the test module)
+        assert np.all(g["count"] <= g["crossings"].sum(1) + 1)
