@@ -1,0 +1,462 @@
+// ozaki_gemm.cu -- K3b: the dense linear right-hand side  K = A @ Y_stage  as an FP64-accurate product on the INT8 tensor
+// cores of sm_100a (tcgen05.mma kind::i8, accumulators in TMEM, operands moved by TMA).
+//
+// Same job as dgemm.cu (the `A @ y` of the reference's linear benchmark system, evaluated by numpy/OpenBLAS inside
+// compute_step, integrators/components/runge_kutta_methods.py:49-54), different arithmetic unit.  Blackwell has no FP64
+// tcgen05 kind; its FP64 tensor path is the warp-level DMMA of dgemm.cu (37 TFLOP/s).  The INT8 path is 120 times wider,
+// and integer products are exact, so the FP64 product is assembled from exact pieces (error-free splitting, the scheme
+// of Ozaki, Ogita, Oishi & Rump):
+//
+//   * every row of A (every column of B) is scaled by a power of two so that |x| < 1 and cut into S = 8 signed digits:
+//     x = q0 2^-6 + q1 2^-13 + ... + q7 2^-55 (+ a remainder below 2^-56), |q| <= 64, by round-to-nearest of the running
+//     remainder -- every step exact in FP64.  55 bits relative to the largest element of the row (column);
+//   * the products of digit planes A_i B_j are INT8 GEMMs with INT32 accumulation: |sum_k q q'| <= 4096 * 2^12 = 2^24, and
+//     all planes of one weight i + j = d are summed in the same accumulator (at most 8 of them: < 2^27) -- exact;
+//   * the 36 plane products with d = i + j <= 7 are kept (the dropped ones weigh < 2^-56 relative to |row| |column| K);
+//     the 8 accumulators are combined in FP64 by Horner from the lightest weight: one rounding per accumulator.
+//   The result is not the sequence of roundings of a left-to-right FP64 dot product (nor of cuBLAS' DMMA order); its
+//   error is bounded by ~2^-52 |row max| |column max| K^0.5-ish, measured in tools/ozaki_check.py against an exact product.
+//
+// Kernel (one CTA per SM, persistent over 128 x 64 output tiles, 256 threads):
+//   warp 0   TMA producer: per k-block of 64 it loads 8 units {A_i tile 128 x 64, B_(7-i) tile 64 x 64} (12 KB, 64-byte
+//            swizzle) into a ring of 16 units (two k-blocks), one mbarrier pair per unit;
+//   warp 1   MMA issuer (one lane): step i of a k-block multiplies A_i with B_0..B_(7-i) (two K = 32 instructions each)
+//            into accumulator d = i + j (TMEM columns 64 d .. 64 d + 63: all 512 columns), then commits the unit's
+//            `empty` barrier -- A_i and B_(7-i) are both dead after step i, so the ring drains progressively;
+//   warp 2   owns the TMEM allocation;
+//   warps 4-7 epilogue: tcgen05.ld of the 8 accumulators of 16 columns, Horner in FP64, scale, 128-byte stores per lane.
+// Operand traffic from L2: 96 KB per k-block per tile for 72 MMAs (128 x 64 x 32).
+//
+// The digit planes of A are produced once per matrix (dsb_ozaki_split_a), those of Y per product (dsb_ozaki_split_b,
+// which also transposes to K-major: [plane][column][k]).
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace dsb {
+#ifdef DSB_STANDALONE
+void set_error(const char *, ...) {}
+#endif
+
+namespace oz {
+#ifndef DSB_OZAKI_SLICES
+#define DSB_OZAKI_SLICES 8
+#endif
+constexpr int S = DSB_OZAKI_SLICES;
+constexpr int BM = 128, BN = 64, BK = 64, UMMA_K = 32;
+constexpr int A_TILE = BM * BK, B_TILE = BN * BK, UNIT = A_TILE + B_TILE;
+constexpr int RING = 2 * S;
+constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = RING * UNIT + 1024 /* alignment slack */ + 512 /* barriers */;
+constexpr int TMEM_COLS = 512;
+static_assert(S * BN <= TMEM_COLS, "accumulators must fit TMEM");
+constexpr long long WAIT_LIMIT = 4000000000LL;   // cycles (~2 s): a protocol error traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t sptr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int what)
+{
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > WAIT_LIMIT) {
+            printf("ozaki_gemm: barrier wait %d timed out (block %d thread %d)\n", what, (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, signed 8-bit operands, 32-bit integer accumulators
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile whose rows are 64 bytes, 64-byte swizzle (TMA CU_TENSOR_MAP_SWIZZLE_64B): groups of 8 rows are
+// 512 bytes apart (stride byte offset); the leading byte offset is not used by swizzled K-major layouts
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr)
+{
+    const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (512u >> 4) | (1u << 14) /* descriptor version of sm_100 */ | (4u << 29) /* SWIZZLE_64B */;
+    return ((uint64_t)hi << 32) | lo;
+}
+// c_format S32 (2) | a, b INT8 (1) | K-major both | N >> 3 | M >> 4
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+}  // namespace oz
+
+__global__ void __launch_bounds__(oz::THREADS, 1)
+ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const double *__restrict__ scale_a, const double *__restrict__ scale_b, double *__restrict__ C, int M, int N,
+                  int K, int *__restrict__ dbg_acc)
+{
+    using namespace oz;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (sptr(smem_raw) + 1023u) & ~1023u;             // swizzled tiles: 1024-byte aligned
+    const uint32_t bars = smem_base + RING * UNIT;                            // full[RING], empty[RING], tmem_full, tmem_empty
+    auto full_bar = [&](int u) { return bars + 8u * u; };
+    auto empty_bar = [&](int u) { return bars + 8u * (RING + u); };
+    const uint32_t tmem_full = bars + 8u * (2 * RING), tmem_empty = tmem_full + 8u, tmem_slot = tmem_empty + 8u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = M / BM, tiles = mb * (N / BN), kblocks = K / BK;
+
+    if (warp == 1 && lane == 0) {
+        for (int u = 0; u < RING; ++u) { mbar_init(full_bar(u), 1); mbar_init(empty_bar(u), 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        uint32_t n_unit = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m0 = (tile % mb) * BM, n0 = (tile / mb) * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll 1
+                for (int i = 0; i < S; ++i, ++n_unit) {
+                    const int slot = n_unit % RING;
+                    const uint32_t use = n_unit / RING;
+                    if (use > 0) mbar_wait(empty_bar(slot), (use - 1) & 1, 100 + slot);
+                    mbar_expect_tx(full_bar(slot), UNIT);
+                    const uint32_t dst = smem_base + slot * UNIT;
+                    tma_load_2d(dst, &map_a, kb * BK, i * M + m0, full_bar(slot));
+                    tma_load_2d(dst + A_TILE, &map_b, kb * BK, (S - 1 - i) * N + n0, full_bar(slot));
+                }
+            }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===== MMA issuer =====
+        uint32_t n_kb = 0, n_tile = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+            if (n_tile > 0) {
+                mbar_wait(tmem_empty, (n_tile - 1) & 1, 300);                 // the epilogue has drained the accumulators
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < kblocks; ++kb, ++n_kb) {
+                const int base = (n_kb & 1) * S;
+                const uint32_t parity = (n_kb >> 1) & 1;
+                for (int i = 0; i < S; ++i) mbar_wait(full_bar(base + i), parity, 200 + base + i);
+                tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < S; ++i) {
+                    const uint64_t adesc = smem_desc_sw64(smem_base + (base + i) * UNIT);
+                    for (int j = 0; j < S - i; ++j) {
+                        const uint64_t bdesc = smem_desc_sw64(smem_base + (base + S - 1 - j) * UNIT + A_TILE);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((i + j) * BN);
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                            mma_i8(d_tmem, adesc + (uint64_t)(kk * UMMA_K / 16), bdesc + (uint64_t)(kk * UMMA_K / 16), IDESC,
+                                   (kb > 0 || kk > 0 || i > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(base + i));                           // A_i and B_(S-1-i) are dead once these complete
+                }
+            }
+            tc_commit(tmem_full);
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 =====
+        const int q = warp - 4;
+        uint32_t n_tile = 0;
+        constexpr double W = 1.0 / 128.0;                                     // 2^-7 between neighbouring weights
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+            const int m0 = (tile % mb) * BM, n0 = (tile / mb) * BN;
+            mbar_wait(tmem_full, n_tile & 1, 400);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const double sa = scale_a[row] * (1.0 / 4096.0);                  // 2^-6 * 2^-6 of the two leading digits
+            double *crow = C + (size_t)row * N + n0;
+#pragma unroll 1
+            for (int c = 0; c < BN / 16; ++c) {
+                int acc[S][16];
+#pragma unroll
+                for (int d = 0; d < S; ++d) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 16), acc[d]);
+                tmem_ld_wait();
+                if (dbg_acc != nullptr) {
+#pragma unroll
+                    for (int d = 0; d < S; ++d)
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) dbg_acc[((size_t)d * M + row) * N + n0 + c * 16 + e] = acc[d][e];
+                }
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    double v[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double s = (double)acc[S - 1][e + h];
+#pragma unroll
+                        for (int d = S - 2; d >= 0; --d) s = fma(s, W, (double)acc[d][e + h]);
+                        v[h] = s * sa * __ldg(scale_b + n0 + c * 16 + e + h);
+                    }
+                    *reinterpret_cast<double2 *>(crow + c * 16 + e) = make_double2(v[0], v[1]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ---- digit planes ------------------------------------------------------------------------------------------------------
+namespace oz {
+// power of two p with max < p (max = f 2^e, 0.5 <= f < 1  ->  p = 2^e); 1 for an all-zero (or non-finite) vector
+__device__ __forceinline__ double pow2_above(double mx)
+{
+    if (!(mx > 0.0) || !(mx < 1.7e308)) return 1.0;
+    int e;
+    frexp(mx, &e);
+    return ldexp(1.0, e);
+}
+// the S signed digits of x (|x| < 1): q0 = rint(x 2^6), then 7 bits at a time of the exact remainder
+__device__ __forceinline__ void digits(double x, signed char (&q)[S])
+{
+    double r = x * 64.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double n = rint(r);
+        q[s] = (signed char)(int)n;
+        r = (r - n) * 128.0;
+    }
+}
+}  // namespace oz
+
+// A[M][K] row-major -> planes[S][M][K] int8, scale[M]: one CTA per row, 16 consecutive elements per thread and pass
+__global__ void __launch_bounds__(256) ozaki_split_rows_kernel(const double *__restrict__ A, int K, size_t plane_stride,
+                                                               signed char *__restrict__ planes, double *__restrict__ scale)
+{
+    using namespace oz;
+    const int row = blockIdx.x;
+    const double *a = A + (size_t)row * K;
+    __shared__ double red[8];
+    double mx = 0.0;
+    for (int k = threadIdx.x * 2; k < K; k += 512) {
+        const double2 v = *reinterpret_cast<const double2 *>(a + k);
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+    const double p = pow2_above(mx), inv = 1.0 / p;
+    if (threadIdx.x == 0) scale[row] = p;
+    for (int k0 = threadIdx.x * 16; k0 < K; k0 += 256 * 16) {
+        signed char out[S][16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(a + k0 + e);
+            signed char q[S];
+            digits(v.x * inv, q);
+#pragma unroll
+            for (int s = 0; s < S; ++s) out[s][e] = q[s];
+            digits(v.y * inv, q);
+#pragma unroll
+            for (int s = 0; s < S; ++s) out[s][e + 1] = q[s];
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            *reinterpret_cast<uint4 *>(planes + s * plane_stride + (size_t)row * K + k0) = *reinterpret_cast<const uint4 *>(out[s]);
+    }
+}
+
+// column maxima of B[K][N] (N contiguous): bit pattern of |b| ordered like an unsigned integer, atomicMax per column
+__global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double *__restrict__ B, int K, int N, int rows_per_block,
+                                                           unsigned long long *__restrict__ colmax_bits)
+{
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int k0 = blockIdx.y * rows_per_block, k1 = min(K, k0 + rows_per_block);
+    double mx = 0.0;
+    for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(B[(size_t)k * N + n]));
+    atomicMax(colmax_bits + n, (unsigned long long)__double_as_longlong(mx));
+}
+
+// B[K][N] -> planes[S][N][K] int8 (transposed: k contiguous), scale[N]: one thread per column and 32 rows
+__global__ void __launch_bounds__(128) ozaki_split_cols_kernel(const double *__restrict__ B, int K, int N, size_t plane_stride,
+                                                               const unsigned long long *__restrict__ colmax_bits,
+                                                               signed char *__restrict__ planes, double *__restrict__ scale)
+{
+    using namespace oz;
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const int k0 = blockIdx.y * 32;
+    const double p = pow2_above(__longlong_as_double((long long)colmax_bits[n])), inv = 1.0 / p;
+    if (blockIdx.y == 0) scale[n] = p;
+    signed char out[S][32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        signed char q[S];
+        digits(B[(size_t)(k0 + e) * N + n] * inv, q);
+#pragma unroll
+        for (int s = 0; s < S; ++s) out[s][e] = q[s];
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        uint4 *dst = reinterpret_cast<uint4 *>(planes + s * plane_stride + (size_t)n * K + k0);
+        dst[0] = *reinterpret_cast<const uint4 *>(out[s]);
+        dst[1] = *reinterpret_cast<const uint4 *>(out[s] + 16);
+    }
+}
+
+namespace oz {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// planes[S * rows][K] int8, box of `box_rows` rows x 64 bytes, 64-byte swizzle
+static int make_map(CUtensorMap *map, const void *planes, long long rows, long long K, int box_rows)
+{
+    EncodeTiledFn fn = encode_tiled();
+    if (fn == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DSB_ERR_CUDA; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)K};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(planes), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DSB_ERR_CUDA; }
+    return DSB_OK;
+}
+}  // namespace oz
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" {
+
+DSB_API int dsb_ozaki_slices(void) { return oz::S; }
+
+DSB_API int dsb_ozaki_split_a(const double *A, long long M, long long K, signed char *planes, double *scale, void *stream)
+{
+    if (A == nullptr || planes == nullptr || scale == nullptr || M <= 0 || K <= 0 || K % 16 != 0) {
+        set_error("dsb_ozaki_split_a: bad arguments (K must be a multiple of 16)");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    ozaki_split_rows_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(A, (int)K, (size_t)M * K, planes, scale);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+// workspace: N * 8 bytes (column maxima)
+DSB_API int dsb_ozaki_split_b(const double *B, long long K, long long N, signed char *planes, double *scale, void *workspace,
+                              void *stream)
+{
+    if (B == nullptr || planes == nullptr || scale == nullptr || workspace == nullptr || N <= 0 || K <= 0 || K % 32 != 0) {
+        set_error("dsb_ozaki_split_b: bad arguments (K must be a multiple of 32)");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DSB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, (size_t)N * 8, st));
+    const int rows_per_block = 128;
+    dim3 g1((unsigned)((N + 255) / 256), (unsigned)((K + rows_per_block - 1) / rows_per_block));
+    ozaki_colmax_kernel<<<g1, 256, 0, st>>>(B, (int)K, (int)N, rows_per_block, (unsigned long long *)workspace);
+    dim3 g2((unsigned)((N + 127) / 128), (unsigned)(K / 32));
+    ozaki_split_cols_kernel<<<g2, 128, 0, st>>>(B, (int)K, (int)N, (size_t)N * K, (const unsigned long long *)workspace, planes, scale);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+
+// C[M][N] = A[M][K] B[K][N] from the digit planes of A ([S][M][K]) and of B ([S][N][K]); dbg_acc (optional, [S][M][N] int32)
+// receives the raw accumulators
+DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, const signed char *b_planes, const double *b_scale,
+                           double *C, long long M, long long N, long long K, int sms, int *dbg_acc, void *stream)
+{
+    using namespace oz;
+    if (M <= 0 || N <= 0 || K <= 0 || M % BM != 0 || N % BN != 0 || K % BK != 0 || K > 4096 * 8) {
+        set_error("dsb_ozaki_gemm: needs M %% 128 == 0, N %% 64 == 0, K %% 64 == 0 and K <= 32768 (INT32 accumulators)");
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, a_planes, (long long)S * M, K, BM);
+    if (rc != DSB_OK) return rc;
+    rc = make_map(&map_b, b_planes, (long long)S * N, K, BN);
+    if (rc != DSB_OK) return rc;
+    DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const long long tiles = (M / BM) * (N / BN);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, a_scale, b_scale, C, (int)M, (int)N, (int)K,
+                                                                           dbg_acc);
+    DSB_CUDA_CHECK(cudaGetLastError());
+    return DSB_OK;
+}
+}
