@@ -388,6 +388,8 @@ def main():
                 extra["config3_nbody"] = cr.run_nbody(dev, reps=3, check=16)
                 torch.cuda.empty_cache()
                 extra["config2_linear"] = cr.run_linear(dev, reps=2, check=4)
+                torch.cuda.empty_cache()
+                extra["config2_linear_int8"] = cr.run_linear(dev, reps=2, check=4, gemm="int8")
             else:
                 extra["strong_2pow20"] = cr.run_lorenz_strong(dev, world, rank, reps=5)
                 extra["vdp_2pow24_sharded"] = cr.run_vdp(dev, world, rank, reps=3, check=2048, hbm_peak=peak_gbs)

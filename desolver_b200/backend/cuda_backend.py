@@ -200,6 +200,15 @@ def lib():
     L.dsb_erk_run_host.argtypes = [C.c_void_p, C.POINTER(ErkHostArgs), C.c_void_p]
     L.dsb_dgemm.restype = C.c_int
     L.dsb_dgemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    L.dsb_ozaki_slices.restype = C.c_int
+    L.dsb_ozaki_slices.argtypes = []
+    L.dsb_ozaki_split_a.restype = C.c_int
+    L.dsb_ozaki_split_a.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dsb_ozaki_split_b.restype = C.c_int
+    L.dsb_ozaki_split_b.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dsb_ozaki_gemm.restype = C.c_int
+    L.dsb_ozaki_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_int, C.c_void_p, C.c_void_p]
     L.dsb_erk_run_launches.restype = C.c_int
     L.dsb_erk_run_launches.argtypes = [C.c_void_p]
     ns = C.POINTER(NodeStoreStruct)
@@ -314,6 +323,63 @@ def dgemm(A, B, out=None):
         return None
     check(status, "dsb_dgemm")
     return out
+
+
+class Int8Product:
+    """C = A @ B for one fixed float64 CUDA matrix A through the INT8 tensor-core path (dsb_ozaki_*, csrc/ozaki_gemm.cu):
+    the digit planes of A are cut once (again whenever A is modified in place), those of B per product.  `supports(B)`
+    says whether a right-hand side fits the kernel's tiling; buffers grow to the widest B seen."""
+
+    def __init__(self, A):
+        import torch
+        if not (A.is_cuda and A.dtype == torch.float64 and A.ndim == 2 and A.is_contiguous()):
+            raise ValueError("Int8Product needs a contiguous float64 CUDA matrix")
+        self.A = A
+        self.M, self.K = A.shape
+        self.S = lib().dsb_ozaki_slices()
+        self.sms = torch.cuda.get_device_properties(A.device).multi_processor_count
+        self.a_planes = torch.empty((self.S, self.M, self.K), dtype=torch.int8, device=A.device)
+        self.a_scale = torch.empty(self.M, dtype=torch.float64, device=A.device)
+        self._a_version = None
+        self.b_planes = self.b_scale = self.workspace = None
+        self.columns = 0
+
+    def shape_ok(self):
+        return self.M % 128 == 0 and self.K % 64 == 0 and self.K <= 32768 and self.A.data_ptr() % 16 == 0
+
+    def supports(self, B):
+        import torch
+        return (self.shape_ok() and B.ndim == 2 and B.shape[0] == self.K and B.shape[1] % 64 == 0 and B.shape[1] > 0
+                and B.is_cuda and B.dtype == torch.float64 and B.is_contiguous() and B.device == self.A.device)
+
+    def _prepare(self, n):
+        import torch
+        stream = current_stream_ptr(self.A.device)
+        if self._a_version != self.A._version:
+            check(lib().dsb_ozaki_split_a(self.A.data_ptr(), self.M, self.K, self.a_planes.data_ptr(), self.a_scale.data_ptr(),
+                                          stream), "dsb_ozaki_split_a")
+            self._a_version = self.A._version
+        if n > self.columns:
+            dev = self.A.device
+            self.b_planes = torch.empty((self.S * n * self.K,), dtype=torch.int8, device=dev)
+            self.b_scale = torch.empty(n, dtype=torch.float64, device=dev)
+            self.workspace = torch.empty(n, dtype=torch.int64, device=dev)
+            self.columns = n
+
+    def __call__(self, B, out=None, dbg_acc=None):
+        import torch
+        n = B.shape[1]
+        self._prepare(n)
+        if out is None:
+            out = torch.empty((self.M, n), dtype=torch.float64, device=B.device)
+        stream = current_stream_ptr(B.device)
+        L = lib()
+        check(L.dsb_ozaki_split_b(B.data_ptr(), self.K, n, self.b_planes.data_ptr(), self.b_scale.data_ptr(),
+                                  self.workspace.data_ptr(), stream), "dsb_ozaki_split_b")
+        check(L.dsb_ozaki_gemm(self.a_planes.data_ptr(), self.a_scale.data_ptr(), self.b_planes.data_ptr(), self.b_scale.data_ptr(),
+                               out.data_ptr(), self.M, n, self.K, self.sms, None if dbg_acc is None else dbg_acc.data_ptr(),
+                               stream), "dsb_ozaki_gemm")
+        return out
 
 
 def current_stream_ptr(device):

@@ -31,6 +31,7 @@
 // which also transposes to K-major: [plane][column][k]).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -94,6 +95,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const CUtensorMap *ma
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -134,7 +147,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __global__ void __launch_bounds__(oz::THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const double *__restrict__ scale_a, const double *__restrict__ scale_b, double *__restrict__ C, int M, int N,
-                  int K, int *__restrict__ dbg_acc)
+                  int K, int *__restrict__ dbg_acc, int mode)
 {
     using namespace oz;
     extern __shared__ uint8_t smem_raw[];
@@ -162,7 +175,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-      if (lane == 0) {
+      if (lane == 0 && !(mode & 1)) {
         // ===== TMA producer =====
         uint32_t n_unit = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -183,8 +196,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: the whole warp walks the loop (warp-uniform descriptors), lane 0 issues =====
+        const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+        const uint32_t lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
+        auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
         uint32_t n_kb = 0, n_tile = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
             if (n_tile > 0) {
@@ -194,26 +209,34 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int kb = 0; kb < kblocks; ++kb, ++n_kb) {
                 const int base = (n_kb & 1) * S;
                 const uint32_t parity = (n_kb >> 1) & 1;
-                for (int i = 0; i < S; ++i) mbar_wait(full_bar(base + i), parity, 200 + base + i);
-                tc_fence_after();
+                const uint32_t lo = lo0 + (uint32_t)base * (UNIT / 16);
+                const uint32_t ebar = empty_bar(base);
+                if (!(mode & 1))
 #pragma unroll 1
-                for (int i = 0; i < S; ++i) {
-                    const uint64_t adesc = smem_desc_sw64(smem_base + (base + i) * UNIT);
-                    for (int j = 0; j < S - i; ++j) {
-                        const uint64_t bdesc = smem_desc_sw64(smem_base + (base + S - 1 - j) * UNIT + A_TILE);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((i + j) * BN);
+                    for (int i = 0; i < S; ++i) mbar_wait(full_bar(base + i), parity, 200 + base + i);
+                tc_fence_after();
+                if (mode & 2) {
+                    if (elect_one())
+                        for (int i = 0; i < S; ++i) tc_commit(ebar + 8u * i);
+                } else if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; ++kk)
-                            mma_i8(d_tmem, adesc + (uint64_t)(kk * UMMA_K / 16), bdesc + (uint64_t)(kk * UMMA_K / 16), IDESC,
-                                   (kb > 0 || kk > 0 || i > 0) ? 1u : 0u);
+                    for (int i = 0; i < S; ++i) {
+#pragma unroll
+                        for (int j = 0; j < S - i; ++j) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                                mma_i8(tmem_base + (uint32_t)((i + j) * BN), desc(lo + i * (UNIT / 16) + kk * (UMMA_K / 16)),
+                                       desc(lo + (S - 1 - j) * (UNIT / 16) + A_TILE / 16 + kk * (UMMA_K / 16)), IDESC,
+                                       (i > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0));
+                        }
+                        tc_commit(ebar + 8u * i);                              // A_i and B_(S-1-i) are dead once these complete
                     }
-                    tc_commit(empty_bar(base + i));                           // A_i and B_(S-1-i) are dead once these complete
                 }
+                __syncwarp();
             }
-            tc_commit(tmem_full);
+            if (lane == 0) tc_commit(tmem_full);
+            __syncwarp();
         }
-      }
-      __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 =====
         const int q = warp - 4;
@@ -389,11 +412,14 @@ static int make_map(CUtensorMap *map, const void *planes, long long rows, long l
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DSB_ERR_CUDA; }
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)K};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (getenv("DSB_OZAKI_BOX128")) { box[0] = 128; box[1] = box_rows / 2; sw = CU_TENSOR_MAP_SWIZZLE_128B; }   // timing experiment only
+    if (getenv("DSB_OZAKI_PROMO")) promo = (CUtensorMapL2promotion)atoi(getenv("DSB_OZAKI_PROMO"));
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(planes), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DSB_ERR_CUDA; }
     return DSB_OK;
 }
@@ -406,7 +432,7 @@ extern "C" {
 
 DSB_API int dsb_ozaki_slices(void) { return oz::S; }
 
-DSB_API int dsb_ozaki_split_a(const double *A, long long M, long long K, signed char *planes, double *scale, void *stream)
+DSB_API int dsb_ozaki_split_a(const double *A, int64_t M, int64_t K, signed char *planes, double *scale, void *stream)
 {
     if (A == nullptr || planes == nullptr || scale == nullptr || M <= 0 || K <= 0 || K % 16 != 0) {
         set_error("dsb_ozaki_split_a: bad arguments (K must be a multiple of 16)");
@@ -418,7 +444,7 @@ DSB_API int dsb_ozaki_split_a(const double *A, long long M, long long K, signed 
 }
 
 // workspace: N * 8 bytes (column maxima)
-DSB_API int dsb_ozaki_split_b(const double *B, long long K, long long N, signed char *planes, double *scale, void *workspace,
+DSB_API int dsb_ozaki_split_b(const double *B, int64_t K, int64_t N, signed char *planes, double *scale, void *workspace,
                               void *stream)
 {
     if (B == nullptr || planes == nullptr || scale == nullptr || workspace == nullptr || N <= 0 || K <= 0 || K % 32 != 0) {
@@ -439,7 +465,7 @@ DSB_API int dsb_ozaki_split_b(const double *B, long long K, long long N, signed 
 // C[M][N] = A[M][K] B[K][N] from the digit planes of A ([S][M][K]) and of B ([S][N][K]); dbg_acc (optional, [S][M][N] int32)
 // receives the raw accumulators
 DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, const signed char *b_planes, const double *b_scale,
-                           double *C, long long M, long long N, long long K, int sms, int *dbg_acc, void *stream)
+                           double *C, int64_t M, int64_t N, int64_t K, int sms, int32_t *dbg_acc, void *stream)
 {
     using namespace oz;
     if (M <= 0 || N <= 0 || K <= 0 || M % BM != 0 || N % BN != 0 || K % BK != 0 || K > 4096 * 8) {
@@ -455,7 +481,7 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
     const long long tiles = (M / BM) * (N / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
     ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, a_scale, b_scale, C, (int)M, (int)N, (int)K,
-                                                                           dbg_acc);
+                                                                           dbg_acc, getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }

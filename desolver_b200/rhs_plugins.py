@@ -67,12 +67,24 @@ harmonic_oscillator.plugin_defaults = dict(k=1.0, m=1.0)
 def linear(t, y, A=None, out=None):
     """Dense linear system y' = A @ y (A shared by the whole ensemble; y is (n,) or (n, N)).
 
-    For an ensemble of CUDA float64 columns whose shape fits its tiling, the product is the library's own FP64
-    tensor-core kernel (dsb_dgemm, csrc/dgemm.cu); otherwise -- numpy arrays, the reference, odd shapes -- the
-    array library's matmul.  `linear.use_library_gemm = True` forces the latter."""
+    For an ensemble of CUDA float64 columns whose shape fits its tiling, the product is one of the library's own
+    tensor-core kernels: `linear.gemm = "dmma"` (default) the FP64 DMMA kernel (dsb_dgemm, csrc/dgemm.cu; the rounding
+    sequence of an FP64 GEMM), `linear.gemm = "int8"` the error-free digit-plane product on the INT8 tensor cores
+    (dsb_ozaki_*, csrc/ozaki_gemm.cu; closer to the exact product, 1.7x faster, needs n % 128 == 0 and >= 1024 columns
+    to pay off).  Otherwise -- numpy arrays, the reference, odd shapes -- the array library's matmul;
+    `linear.use_library_gemm = True` forces the latter."""
     if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2
             and getattr(A, "is_cuda", False)):
         from .backend import cuda_backend as cb
+        if linear.gemm == "int8":
+            prod = linear._int8.get(id(A))
+            if prod is None or prod.A is not A:
+                linear._int8.clear()                        # one matrix at a time: the planes of A are as large as A
+                prod = linear._int8[id(A)] = cb.Int8Product(A)
+            if prod.supports(y):
+                res = prod(y, out=out if (out is not None and out.is_contiguous()) else None)
+                linear.calls_int8 += 1
+                return res
         res = cb.dgemm(A, y, out=out if (out is not None and out.is_contiguous()) else None)
         if res is not None:
             linear.calls_dsb += 1
@@ -85,6 +97,9 @@ def linear(t, y, A=None, out=None):
 
 
 linear.use_library_gemm = False
+linear.gemm = "dmma"              # "dmma" | "int8": which tensor-core kernel serves the product (see the docstring)
+linear._int8 = {}
+linear.calls_int8 = 0
 linear.calls_dsb = 0              # products served by dsb_dgemm / by the array library (CUDA-graph replays are not
 linear.calls_library = 0          # re-counted: what matters is which kernel a captured attempt contains)
 linear.supports_out = True        # rhs(t, y, out=array, **constants) writes the derivative into a caller-owned array

@@ -407,6 +407,26 @@ DSB_API int dsb_event_search_roots(const dsb_event_search *s, double *roots, voi
  * K % 16 == 0 and 16-byte aligned pointers, else DSB_ERR_UNSUPPORTED (the caller then uses a library GEMM). */
 DSB_API int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, void *stream);
 
+/* The same product on the INT8 tensor cores (tcgen05.mma kind::i8, TMA, TMEM; csrc/ozaki_gemm.cu): every row of A and
+ * every column of B is scaled by a power of two and cut into dsb_ozaki_slices() = 8 signed digit planes of 7 bits
+ * (error-free: 55 bits below the largest element of the row / column); the 36 plane products of weight <= 7 are exact
+ * INT8 x INT8 -> INT32 GEMMs, combined in FP64.  The result carries an error of about 2^-56 |row max| |column max| per
+ * term plus one rounding -- tighter than a left-to-right FP64 dot product -- but it is NOT the rounding sequence of
+ * dsb_dgemm / cuBLAS / numpy (tests compare it with an exactly rounded reference).
+ *   dsb_ozaki_split_a   A[M][K] row-major -> planes[S][M][K] int8, scale[M]     (once per matrix; K % 16 == 0)
+ *   dsb_ozaki_split_b   B[K][N] row-major -> planes[S][N][K] int8 (transposed), scale[N]; workspace: N * 8 bytes;
+ *                       K % 32 == 0
+ *   dsb_ozaki_gemm      C[M][N] = A B from the planes; M % 128 == 0, N % 64 == 0, K % 64 == 0, K <= 32768 (INT32
+ *                       accumulators), else DSB_ERR_BAD_ARGUMENT; `sms` = CTAs to launch (one per SM); dbg_acc: NULL, or
+ *                       [S][M][N] int32 receiving the raw accumulators (tests).  No hidden synchronisation. */
+DSB_API int dsb_ozaki_slices(void);
+DSB_API int dsb_ozaki_split_a(const double *A, int64_t M, int64_t K, signed char *planes, double *scale, void *stream);
+DSB_API int dsb_ozaki_split_b(const double *B, int64_t K, int64_t N, signed char *planes, double *scale, void *workspace,
+                              void *stream);
+DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, const signed char *b_planes,
+                           const double *b_scale, double *C, int64_t M, int64_t N, int64_t K, int sms, int32_t *dbg_acc,
+                           void *stream);
+
 /* ---- dense output / step history over the node store ---------------------------------------
  * Replace DenseOutput.__call__ / grad / find_interval (differential_system.py:205-246) and CubicHermiteInterp.__call__ /
  * grad (utilities/interpolation.py:41-78).  After a run the caller builds the index once:

@@ -45,11 +45,25 @@ def _threads():
         return os.cpu_count() or 1
 
 
-def run_linear(dev, reps=2, check=8, n=4096, columns=8192):
+def run_linear(dev, reps=2, check=8, n=4096, columns=8192, gemm="dmma"):
+    """Config 2.  gemm = "dmma": every product is dsb_dgemm (FP64 DMMA); "int8": the digit-plane product on the INT8
+    tensor cores (dsb_ozaki_*), the tail of compacted columns still on dsb_dgemm."""
     import torch
     import desolver_b200 as de
     from desolver_b200.integrators import tableaux as tb
     from oracle import oracle as orc
+    lin = de.rhs_plugins.linear
+    previous, lin.gemm = lin.gemm, gemm
+    try:
+        return _run_linear(torch, de, tb, orc, dev, reps, check, n, columns, gemm)
+    finally:
+        lin.gemm = previous
+        lin._int8.clear()
+
+
+def _run_linear(torch, de, tb, orc, dev, reps, check, n, columns, gemm):
+    lin = de.rhs_plugins.linear
+    calls0 = (lin.calls_dsb, lin.calls_library, lin.calls_int8)
     cfg = de.benchmarks.LINEAR
     A, Y0 = de.benchmarks.linear_system(n, columns)
     Ad = torch.as_tensor(A).to(dev)
@@ -61,11 +75,15 @@ def run_linear(dev, reps=2, check=8, n=4096, columns=8192):
     ms = min(ms_all)
     att = a.accepted + a.rejected
     flops_alg = float(att.sum()) * 14 * 2.0 * n ** 2           # (S + 1) * 2 n^2 per column-step attempt
-    out = dict(workload="linear_4096x8192_rk8713m", ms=ms, ms_all=ms_all, column_step_attempts=int(att.sum()),
-               attempts_per_column_max=int(att.max()), gemm_launches_dsb=int(getattr(de.rhs_plugins.linear, "calls_dsb", -1)),
-               gemm_launches_library=int(getattr(de.rhs_plugins.linear, "calls_library", -1)),
+    out = dict(workload="linear_4096x8192_rk8713m", gemm=gemm, ms=ms, ms_all=ms_all, column_step_attempts=int(att.sum()),
+               attempts_per_column_max=int(att.max()), gemm_launches_dsb=int(lin.calls_dsb - calls0[0]),
+               gemm_launches_library=int(lin.calls_library - calls0[1]), gemm_launches_int8=int(lin.calls_int8 - calls0[2]),
                tflops_algorithmic=flops_alg / ms / 1e9, bound="tensor (FP64 DMMA)", peak_tflops=DMMA_PEAK_TFLOPS,
                frac=flops_alg / ms / 1e9 / DMMA_PEAK_TFLOPS)
+    if gemm == "int8":
+        # 36 INT8 plane products per FP64 product; 4.5 POP/s is the dense INT8 tensor peak of the part (not measured here)
+        out.update(bound="tensor (INT8 tcgen05, 36 plane products per FP64 product)", peak_tflops=None, frac=None,
+                   int8_tops=36 * flops_alg / ms / 1e9, fp64_equivalent_tflops=flops_alg / ms / 1e9)
     if check:
         idx = np.linspace(0, columns - 1, check).astype(int)
         t0 = time.time()
