@@ -41,6 +41,9 @@ void set_error(const char *, ...) {}
 #endif
 
 namespace oz {
+#ifndef DSB_OZAKI_COLLECTOR
+#define DSB_OZAKI_COLLECTOR 1
+#endif
 #ifndef DSB_OZAKI_SLICES
 #define DSB_OZAKI_SLICES 8
 #endif
@@ -95,6 +98,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const CUtensorMap *ma
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t smem, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -113,15 +132,30 @@ __device__ __forceinline__ void tc_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, signed 8-bit operands, 32-bit integer accumulators
+// the same arrival on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, signed 8-bit operands, 32-bit integer accumulators.  COLL: what happens to the A operand
+// in the tensor core's collector buffer -- 0 discard (default), 1 fill (read from shared memory and keep), 2 use (A is the
+// operand already in the buffer: no shared-memory read), 3 last use.
+template <int COLL>
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+#define DSB_OZ_MMA(MOD)                                                                                   \
+    asm volatile(                                                                                         \
+        "{\n"                                                                                             \
+        ".reg .pred p;\n"                                                                                 \
+        "setp.ne.b32 p, %4, 0;\n"                                                                         \
+        "tcgen05.mma.cta_group::1.kind::i8" MOD " [%0], %1, %2, %3, p;\n"                                 \
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory")
+    if constexpr (COLL == 1) DSB_OZ_MMA(".collector::a::fill");
+    else if constexpr (COLL == 2) DSB_OZ_MMA(".collector::a::use");
+    else if constexpr (COLL == 3) DSB_OZ_MMA(".collector::a::lastuse");
+    else DSB_OZ_MMA("");
+#undef DSB_OZ_MMA
 }
 // K-major operand tile whose rows are 64 bytes, 64-byte swizzle (TMA CU_TENSOR_MAP_SWIZZLE_64B): groups of 8 rows are
 // 512 bytes apart (stride byte offset); the leading byte offset is not used by swizzled K-major layouts
@@ -144,10 +178,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace oz
 
+// CL = 1: every CTA on its own.  CL = 2: clusters of two CTAs work on neighbouring column blocks of the same row block and
+// share the A tiles -- each CTA loads half of the rows and multicasts them into both shared memories (L2 -> SM traffic of
+// A halves); a ring slot is refilled only after the MMA warps of BOTH CTAs have released it.
+template <int CL>
 __global__ void __launch_bounds__(oz::THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const double *__restrict__ scale_a, const double *__restrict__ scale_b, double *__restrict__ C, int M, int N,
-                  int K, int *__restrict__ dbg_acc, int mode)
+                  int K, int *__restrict__ dbg_acc, int mode, int band)
 {
     using namespace oz;
     extern __shared__ uint8_t smem_raw[];
@@ -157,10 +195,24 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto empty_bar = [&](int u) { return bars + 8u * (RING + u); };
     const uint32_t tmem_full = bars + 8u * (2 * RING), tmem_empty = tmem_full + 8u, tmem_slot = tmem_empty + 8u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = M / BM, tiles = mb * (N / BN), kblocks = K / BK;
+    const int mb = M / BM, groups = mb * (N / BN / CL), kblocks = K / BK;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0, cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    constexpr uint16_t ALL = (uint16_t)((1u << CL) - 1u);
+    // work item `it` of this CTA: row block m0, column block n0 (the CTAs of a cluster take neighbouring column blocks)
+    auto tile_at = [&](int it, int &m0, int &n0) {
+        const int g = cluster_id + it * n_clusters;
+        if (g >= groups) return false;
+        // row blocks are walked in bands of `band` (m fastest inside a band): the CTAs running at the same time share
+        // band * 4 MB of A planes and ~(SMs / band) * 2 MB of B planes, which stay in L2 from one wave to the next
+        const int nbc = N / BN / CL, per_band = band * nbc, b0 = (g / per_band) * band;
+        const int rows = (mb - b0) < band ? (mb - b0) : band, r = g - (g / per_band) * per_band;
+        m0 = (b0 + r % rows) * BM;
+        n0 = ((r / rows) * CL + crank) * BN;
+        return true;
+    };
 
     if (warp == 1 && lane == 0) {
-        for (int u = 0; u < RING; ++u) { mbar_init(full_bar(u), 1); mbar_init(empty_bar(u), 1); }
+        for (int u = 0; u < RING; ++u) { mbar_init(full_bar(u), 1); mbar_init(empty_bar(u), CL); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -169,7 +221,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync(); else __syncthreads();              // barriers of the peer are initialised too
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -178,8 +230,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (lane == 0 && !(mode & 1)) {
         // ===== TMA producer =====
         uint32_t n_unit = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int m0 = (tile % mb) * BM, n0 = (tile / mb) * BN;
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it) {
             for (int kb = 0; kb < kblocks; ++kb) {
 #pragma unroll 1
                 for (int i = 0; i < S; ++i, ++n_unit) {
@@ -188,7 +240,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (use > 0) mbar_wait(empty_bar(slot), (use - 1) & 1, 100 + slot);
                     mbar_expect_tx(full_bar(slot), UNIT);
                     const uint32_t dst = smem_base + slot * UNIT;
-                    tma_load_2d(dst, &map_a, kb * BK, i * M + m0, full_bar(slot));
+                    if constexpr (CL > 1)                                     // my share of the rows, into every CTA of the cluster
+                        tma_load_2d_multicast(dst + crank * (A_TILE / CL), &map_a, kb * BK, i * M + m0 + crank * (BM / CL),
+                                              full_bar(slot), ALL);
+                    else
+                        tma_load_2d(dst, &map_a, kb * BK, i * M + m0, full_bar(slot));
                     tma_load_2d(dst + A_TILE, &map_b, kb * BK, (S - 1 - i) * N + n0, full_bar(slot));
                 }
             }
@@ -201,7 +257,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
         auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
         uint32_t n_kb = 0, n_tile = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
             if (n_tile > 0) {
                 mbar_wait(tmem_empty, (n_tile - 1) & 1, 300);                 // the epilogue has drained the accumulators
                 tc_fence_after();
@@ -217,19 +274,29 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_after();
                 if (mode & 2) {
                     if (elect_one())
-                        for (int i = 0; i < S; ++i) tc_commit(ebar + 8u * i);
+                        for (int i = 0; i < S; ++i) {
+                            if constexpr (CL > 1) tc_commit_multicast(ebar + 8u * i, ALL); else tc_commit(ebar + 8u * i);
+                        }
                 } else if (elect_one()) {
 #pragma unroll
                     for (int i = 0; i < S; ++i) {
 #pragma unroll
-                        for (int j = 0; j < S - i; ++j) {
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            // A_i[kk] stays in the collector while it meets B_0 .. B_(S-1-i)
 #pragma unroll
-                            for (int kk = 0; kk < BK / UMMA_K; ++kk)
-                                mma_i8(tmem_base + (uint32_t)((i + j) * BN), desc(lo + i * (UNIT / 16) + kk * (UMMA_K / 16)),
-                                       desc(lo + (S - 1 - j) * (UNIT / 16) + A_TILE / 16 + kk * (UMMA_K / 16)), IDESC,
-                                       (i > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0));
+                            for (int j = 0; j < S - i; ++j) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)((i + j) * BN);
+                                const uint64_t ad = desc(lo + i * (UNIT / 16) + kk * (UMMA_K / 16));
+                                const uint64_t bd = desc(lo + (S - 1 - j) * (UNIT / 16) + A_TILE / 16 + kk * (UMMA_K / 16));
+                                const uint32_t accumulate = (i > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0);
+                                if (!DSB_OZAKI_COLLECTOR || S - i == 1) mma_i8<0>(d_tmem, ad, bd, IDESC, accumulate);
+                                else if (j == 0) mma_i8<1>(d_tmem, ad, bd, IDESC, accumulate);
+                                else if (j == S - i - 1) mma_i8<3>(d_tmem, ad, bd, IDESC, accumulate);
+                                else mma_i8<2>(d_tmem, ad, bd, IDESC, accumulate);
+                            }
                         }
-                        tc_commit(ebar + 8u * i);                              // A_i and B_(S-1-i) are dead once these complete
+                        // A_i and B_(S-1-i) are dead once these complete (in a cluster: tell the peer, whose loads land here too)
+                        if constexpr (CL > 1) tc_commit_multicast(ebar + 8u * i, ALL); else tc_commit(ebar + 8u * i);
                     }
                 }
                 __syncwarp();
@@ -242,8 +309,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int q = warp - 4;
         uint32_t n_tile = 0;
         constexpr double W = 1.0 / 128.0;                                     // 2^-7 between neighbouring weights
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-            const int m0 = (tile % mb) * BM, n0 = (tile / mb) * BN;
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
             mbar_wait(tmem_full, n_tile & 1, 400);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
@@ -279,7 +346,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync(); else __syncthreads();              // no CTA leaves while its peer can still signal it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -472,16 +539,39 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
         set_error("dsb_ozaki_gemm: needs M %% 128 == 0, N %% 64 == 0, K %% 64 == 0 and K <= 32768 (INT32 accumulators)");
         return DSB_ERR_BAD_ARGUMENT;
     }
+    // clusters of two CTAs that multicast the A tiles were measured: exact, and no faster (3.62 against 3.60 ms on
+    // 4096 x 8192 x 4096 -- the limit is what one SM can take in, not what L2 reads); kept behind DSB_OZAKI_CLUSTER=1
+    const bool pair = (N % (2 * BN) == 0) && sms >= 2 && getenv("DSB_OZAKI_CLUSTER") != nullptr;
     CUtensorMap map_a, map_b;
-    int rc = make_map(&map_a, a_planes, (long long)S * M, K, BM);
+    int rc = make_map(&map_a, a_planes, (long long)S * M, K, pair ? BM / 2 : BM);
     if (rc != DSB_OK) return rc;
     rc = make_map(&map_b, b_planes, (long long)S * N, K, BN);
     if (rc != DSB_OK) return rc;
-    DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const long long tiles = (M / BM) * (N / BN);
-    const int grid = (int)(tiles < sms ? tiles : sms);
-    ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, a_scale, b_scale, C, (int)M, (int)N, (int)K,
-                                                                           dbg_acc, getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0);
+    const int mode = getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0;
+    const int m = (int)M, n = (int)N, k = (int)K;
+    const int band = getenv("DSB_OZAKI_BAND") ? atoi(getenv("DSB_OZAKI_BAND")) : 16;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    if (pair) {
+        DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        const long long groups = (M / BM) * (N / BN / 2);
+        cfg.gridDim = dim3((unsigned)(2 * (groups < sms / 2 ? groups : sms / 2)));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<2>, map_a, map_b, a_scale, b_scale, C, m, n, k, dbg_acc, mode, band));
+    } else {
+        DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        const long long tiles = (M / BM) * (N / BN);
+        cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms));
+        DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<1>, map_a, map_b, a_scale, b_scale, C, m, n, k, dbg_acc, mode, band));
+    }
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
