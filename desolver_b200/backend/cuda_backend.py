@@ -345,7 +345,7 @@ class Int8Product:
         self.columns = 0
 
     def shape_ok(self):
-        return self.M % 128 == 0 and self.K % 64 == 0 and self.K <= 32768 and self.A.data_ptr() % 16 == 0
+        return self.M % 128 == 0 and self.K % 128 == 0 and self.K <= 32768 and self.A.data_ptr() % 16 == 0
 
     def supports(self, B):
         import torch

@@ -17,15 +17,22 @@
 //   The result is not the sequence of roundings of a left-to-right FP64 dot product (nor of cuBLAS' DMMA order); its
 //   error is bounded by ~2^-52 |row max| |column max| K^0.5-ish, measured in tools/ozaki_check.py against an exact product.
 //
-// Kernel (one CTA per SM, persistent over 128 x 64 output tiles, 256 threads):
-//   warp 0   TMA producer: per k-block of 64 it loads 8 units {A_i tile 128 x 64, B_(7-i) tile 64 x 64} (12 KB, 64-byte
-//            swizzle) into a ring of 16 units (two k-blocks), one mbarrier pair per unit;
-//   warp 1   MMA issuer (one lane): step i of a k-block multiplies A_i with B_0..B_(7-i) (two K = 32 instructions each)
-//            into accumulator d = i + j (TMEM columns 64 d .. 64 d + 63: all 512 columns), then commits the unit's
-//            `empty` barrier -- A_i and B_(7-i) are both dead after step i, so the ring drains progressively;
+// Kernel (one CTA per SM, persistent over 128 x 64 output tiles walked in bands of 16 row blocks, 256 threads):
+//   warp 0   TMA producer of the A tiles (128 x 64 bytes, 64-byte swizzle), ring of 16 slots with one mbarrier pair each;
+//   warp 3   TMA producer of the B tiles (64 x 64 bytes), two groups of 8 slots (one group per k-block parity);
+//            position p of a k-block brings A_(7-p) and B_p;
+//   warp 1   MMA issuer (one elected lane): step p multiplies A_(7-p) with B_0 .. B_p (two K = 32 instructions each) into
+//            accumulator d = 7 - p + j (TMEM columns 64 d .. 64 d + 63: all 512 columns).  A_(7-p)[kk] is read from shared
+//            memory once and kept in the tensor core's collector buffer while it meets the p + 1 B tiles (.collector::a::fill /
+//            use / lastuse: 3.53 -> 2.62 ms of MMA time).  The A slot is committed back to its producer after its step, the
+//            B group at the end of the k-block;
 //   warp 2   owns the TMEM allocation;
 //   warps 4-7 epilogue: tcgen05.ld of the 8 accumulators of 16 columns, Horner in FP64, scale, 128-byte stores per lane.
-// Operand traffic from L2: 96 KB per k-block per tile for 72 MMAs (128 x 64 x 32).
+// Operand traffic from L2: 96 KB per k-block per tile for 72 MMAs (128 x 64 x 32).  Measured (4096 x 8192 x 4096, B200):
+// 3.66 ms against 7.78 ms for cuBLAS DGEMM and 8.02 ms for dgemm.cu; the MMA lane never waits for operands (0.03 % of its
+// cycles, DSB_OZAKI_MODE=4), the tensor pipe runs at 52 cycles per instruction against a floor of 32: what is left is the
+// shared-memory port (B tile re-read per instruction + A fills + TMA writes ~ one port-load per MMA cycle).
+// Tried and dropped: clusters of two CTAs multicasting the A tiles (exact, 3.62 ms: no gain -- L2 is not the limit).
 //
 // The digit planes of A are produced once per matrix (dsb_ozaki_split_a), those of Y per product (dsb_ozaki_split_b,
 // which also transposes to K-major: [plane][column][k]).
@@ -50,7 +57,7 @@ namespace oz {
 constexpr int S = DSB_OZAKI_SLICES;
 constexpr int BM = 128, BN = 64, BK = 64, UMMA_K = 32;
 constexpr int A_TILE = BM * BK, B_TILE = BN * BK, UNIT = A_TILE + B_TILE;
-constexpr int RING = 2 * S;
+constexpr int RING = 2 * S;                      // slots per operand: two k-blocks
 constexpr int THREADS = 256;
 constexpr int SMEM_BYTES = RING * UNIT + 1024 /* alignment slack */ + 512 /* barriers */;
 constexpr int TMEM_COLS = 512;
@@ -93,26 +100,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int wha
         }
     }
 }
+// the same, adding the cycles spent waiting to `acc` (mode & 4: where does the pipeline stall)
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int what, long long &acc)
+{
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, what);
+    acc += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem, const CUtensorMap *map, int c0, int c1, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_multicast(uint32_t smem, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint16_t mask)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-                 ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ bool elect_one()
 {
@@ -131,12 +130,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// the same arrival on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, signed 8-bit operands, 32-bit integer accumulators.  COLL: what happens to the A operand
 // in the tensor core's collector buffer -- 0 discard (default), 1 fill (read from shared memory and keep), 2 use (A is the
@@ -178,10 +171,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace oz
 
-// CL = 1: every CTA on its own.  CL = 2: clusters of two CTAs work on neighbouring column blocks of the same row block and
-// share the A tiles -- each CTA loads half of the rows and multicasts them into both shared memories (L2 -> SM traffic of
-// A halves); a ring slot is refilled only after the MMA warps of BOTH CTAs have released it.
-template <int CL>
 __global__ void __launch_bounds__(oz::THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const double *__restrict__ scale_a, const double *__restrict__ scale_b, double *__restrict__ C, int M, int N,
@@ -190,29 +179,32 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     using namespace oz;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (sptr(smem_raw) + 1023u) & ~1023u;             // swizzled tiles: 1024-byte aligned
-    const uint32_t bars = smem_base + RING * UNIT;                            // full[RING], empty[RING], tmem_full, tmem_empty
-    auto full_bar = [&](int u) { return bars + 8u * u; };
-    auto empty_bar = [&](int u) { return bars + 8u * (RING + u); };
-    const uint32_t tmem_full = bars + 8u * (2 * RING), tmem_empty = tmem_full + 8u, tmem_slot = tmem_empty + 8u;
+    const uint32_t smem_b = smem_base + RING * A_TILE;                        // A slots, then B slots
+    const uint32_t bars = smem_b + RING * B_TILE;
+    auto full_a = [&](int u) { return bars + 8u * u; };
+    auto full_b = [&](int u) { return bars + 8u * (RING + u); };
+    auto empty_a = [&](int u) { return bars + 8u * (2 * RING + u); };
+    auto empty_b = [&](int g) { return bars + 8u * (3 * RING + g); };          // one per k-block parity: B tiles retire together
+    const uint32_t tmem_full = bars + 8u * (3 * RING + 2), tmem_empty = tmem_full + 8u, tmem_slot = tmem_empty + 8u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = M / BM, groups = mb * (N / BN / CL), kblocks = K / BK;
-    const int crank = CL > 1 ? (int)cluster_ctarank() : 0, cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-    constexpr uint16_t ALL = (uint16_t)((1u << CL) - 1u);
-    // work item `it` of this CTA: row block m0, column block n0 (the CTAs of a cluster take neighbouring column blocks)
+    const int mb = M / BM, tiles = mb * (N / BN), kblocks = K / BK;
+    // work item `it` of this CTA: row block m0, column block n0
     auto tile_at = [&](int it, int &m0, int &n0) {
-        const int g = cluster_id + it * n_clusters;
-        if (g >= groups) return false;
+        const int g = blockIdx.x + it * gridDim.x;
+        if (g >= tiles) return false;
         // row blocks are walked in bands of `band` (m fastest inside a band): the CTAs running at the same time share
         // band * 4 MB of A planes and ~(SMs / band) * 2 MB of B planes, which stay in L2 from one wave to the next
-        const int nbc = N / BN / CL, per_band = band * nbc, b0 = (g / per_band) * band;
+        const int nbc = N / BN, per_band = band * nbc, b0 = (g / per_band) * band;
         const int rows = (mb - b0) < band ? (mb - b0) : band, r = g - (g / per_band) * per_band;
         m0 = (b0 + r % rows) * BM;
-        n0 = ((r / rows) * CL + crank) * BN;
+        n0 = (r / rows) * BN;
         return true;
     };
 
     if (warp == 1 && lane == 0) {
-        for (int u = 0; u < RING; ++u) { mbar_init(full_bar(u), 1); mbar_init(empty_bar(u), CL); }
+        for (int u = 0; u < RING; ++u) { mbar_init(full_a(u), 1); mbar_init(full_b(u), 1); mbar_init(empty_a(u), 1); }
+        mbar_init(empty_b(0), 1);
+        mbar_init(empty_b(1), 1);
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -221,89 +213,117 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
-    if constexpr (CL > 1) cluster_sync(); else __syncthreads();              // barriers of the peer are initialised too
+    __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    // Order inside a k-block: position p = 0 .. S-1 brings A_(S-1-p) and B_p; step p multiplies A_(S-1-p) with B_0 .. B_p.
+    // The MMA warp can start on the first tiles that land, an A tile is dead after its own step (its slot goes back to the
+    // producer at once), the B tiles of a k-block retire together at its end.
     if (warp == 0) {
       if (lane == 0 && !(mode & 1)) {
-        // ===== TMA producer =====
+        // ===== TMA producer of the A tiles =====
         uint32_t n_unit = 0;
         int m0, n0;
+        long long waited = 0;
         for (int it = 0; tile_at(it, m0, n0); ++it) {
             for (int kb = 0; kb < kblocks; ++kb) {
 #pragma unroll 1
-                for (int i = 0; i < S; ++i, ++n_unit) {
+                for (int p = 0; p < S; ++p, ++n_unit) {
                     const int slot = n_unit % RING;
                     const uint32_t use = n_unit / RING;
-                    if (use > 0) mbar_wait(empty_bar(slot), (use - 1) & 1, 100 + slot);
-                    mbar_expect_tx(full_bar(slot), UNIT);
-                    const uint32_t dst = smem_base + slot * UNIT;
-                    if constexpr (CL > 1)                                     // my share of the rows, into every CTA of the cluster
-                        tma_load_2d_multicast(dst + crank * (A_TILE / CL), &map_a, kb * BK, i * M + m0 + crank * (BM / CL),
-                                              full_bar(slot), ALL);
-                    else
-                        tma_load_2d(dst, &map_a, kb * BK, i * M + m0, full_bar(slot));
-                    tma_load_2d(dst + A_TILE, &map_b, kb * BK, (S - 1 - i) * N + n0, full_bar(slot));
+                    if (use > 0) mbar_wait_timed(empty_a(slot), (use - 1) & 1, 100 + slot, waited);
+                    mbar_expect_tx(full_a(slot), A_TILE);
+                    tma_load_2d(smem_base + slot * A_TILE, &map_a, kb * BK, (S - 1 - p) * M + m0, full_a(slot));
                 }
             }
         }
+        if (mode & 4) reinterpret_cast<long long *>(dbg_acc)[blockIdx.x * 4 + 1] = waited;
+      }
+      __syncwarp();
+    } else if (warp == 3) {
+      if (lane == 0 && !(mode & 1)) {
+        // ===== TMA producer of the B tiles =====
+        uint32_t n_kb = 0;
+        int m0, n0;
+        long long waited = 0;
+        for (int it = 0; tile_at(it, m0, n0); ++it) {
+            for (int kb = 0; kb < kblocks; ++kb, ++n_kb) {
+                const int grp = n_kb & 1;
+                const uint32_t use = n_kb >> 1;
+                if (use > 0) mbar_wait_timed(empty_b(grp), (use - 1) & 1, 150 + grp, waited);
+#pragma unroll 1
+                for (int p = 0; p < S; ++p) {
+                    const int slot = grp * S + p;
+                    mbar_expect_tx(full_b(slot), B_TILE);
+                    tma_load_2d(smem_b + slot * B_TILE, &map_b, kb * BK, p * N + n0, full_b(slot));
+                }
+            }
+        }
+        if (mode & 4) reinterpret_cast<long long *>(dbg_acc)[blockIdx.x * 4 + 2] = waited;
       }
       __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the loop (warp-uniform descriptors), lane 0 issues =====
+        // ===== MMA issuer: the whole warp walks the loop (warp-uniform descriptors), one elected lane issues =====
         const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);
-        const uint32_t lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t lo_a0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16), lo_b0 = ((smem_b >> 4) & 0x3FFFu) | (1u << 16);
         auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
         uint32_t n_kb = 0, n_tile = 0;
         int m0, n0;
+        long long waited = 0, waited_epi = 0;
+        const long long t_start = clock64();
         for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
             if (n_tile > 0) {
-                mbar_wait(tmem_empty, (n_tile - 1) & 1, 300);                 // the epilogue has drained the accumulators
+                mbar_wait_timed(tmem_empty, (n_tile - 1) & 1, 300, waited_epi);   // the epilogue has drained the accumulators
                 tc_fence_after();
             }
             for (int kb = 0; kb < kblocks; ++kb, ++n_kb) {
                 const int base = (n_kb & 1) * S;
                 const uint32_t parity = (n_kb >> 1) & 1;
-                const uint32_t lo = lo0 + (uint32_t)base * (UNIT / 16);
-                const uint32_t ebar = empty_bar(base);
-                if (!(mode & 1))
-#pragma unroll 1
-                    for (int i = 0; i < S; ++i) mbar_wait(full_bar(base + i), parity, 200 + base + i);
-                tc_fence_after();
-                if (mode & 2) {
-                    if (elect_one())
-                        for (int i = 0; i < S; ++i) {
-                            if constexpr (CL > 1) tc_commit_multicast(ebar + 8u * i, ALL); else tc_commit(ebar + 8u * i);
+                const uint32_t lo_a = lo_a0 + (uint32_t)base * (A_TILE / 16), lo_b = lo_b0 + (uint32_t)base * (B_TILE / 16);
+                if (elect_one()) {
+#pragma unroll
+                    for (int p = 0; p < S; ++p) {
+                        if (!(mode & 1)) {
+                            mbar_wait_timed(full_a(base + p), parity, 200 + base + p, waited);
+                            mbar_wait_timed(full_b(base + p), parity, 250 + base + p, waited);
+                            tc_fence_after();
                         }
-                } else if (elect_one()) {
+                        if (!(mode & 2)) {
 #pragma unroll
-                    for (int i = 0; i < S; ++i) {
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                                // A_(S-1-p)[kk] stays in the collector while it meets B_0 .. B_p
 #pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                            // A_i[kk] stays in the collector while it meets B_0 .. B_(S-1-i)
-#pragma unroll
-                            for (int j = 0; j < S - i; ++j) {
-                                const uint32_t d_tmem = tmem_base + (uint32_t)((i + j) * BN);
-                                const uint64_t ad = desc(lo + i * (UNIT / 16) + kk * (UMMA_K / 16));
-                                const uint64_t bd = desc(lo + (S - 1 - j) * (UNIT / 16) + A_TILE / 16 + kk * (UMMA_K / 16));
-                                const uint32_t accumulate = (i > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0);
-                                if (!DSB_OZAKI_COLLECTOR || S - i == 1) mma_i8<0>(d_tmem, ad, bd, IDESC, accumulate);
-                                else if (j == 0) mma_i8<1>(d_tmem, ad, bd, IDESC, accumulate);
-                                else if (j == S - i - 1) mma_i8<3>(d_tmem, ad, bd, IDESC, accumulate);
-                                else mma_i8<2>(d_tmem, ad, bd, IDESC, accumulate);
+                                for (int j = 0; j <= p; ++j) {
+                                    const uint32_t d_tmem = tmem_base + (uint32_t)((S - 1 - p + j) * BN);
+                                    const uint64_t ad = desc(lo_a + p * (A_TILE / 16) + kk * (UMMA_K / 16));
+                                    const uint64_t bd = desc(lo_b + j * (B_TILE / 16) + kk * (UMMA_K / 16));
+                                    // the first product into accumulator d = S-1-p+j of a tile is (kb 0, kk 0, j 0)
+                                    const uint32_t accumulate = (j > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0);
+                                    if (!DSB_OZAKI_COLLECTOR || p == 0) mma_i8<0>(d_tmem, ad, bd, IDESC, accumulate);
+                                    else if (j == 0) mma_i8<1>(d_tmem, ad, bd, IDESC, accumulate);
+                                    else if (j == p) mma_i8<3>(d_tmem, ad, bd, IDESC, accumulate);
+                                    else mma_i8<2>(d_tmem, ad, bd, IDESC, accumulate);
+                                }
                             }
                         }
-                        // A_i and B_(S-1-i) are dead once these complete (in a cluster: tell the peer, whose loads land here too)
-                        if constexpr (CL > 1) tc_commit_multicast(ebar + 8u * i, ALL); else tc_commit(ebar + 8u * i);
+                        tc_commit(empty_a(base + p));                          // this A tile is dead once these complete
                     }
+                    tc_commit(empty_b(n_kb & 1));                              // ... and so are all B tiles of the k-block
                 }
                 __syncwarp();
             }
-            if (lane == 0) tc_commit(tmem_full);
+            if (elect_one()) tc_commit(tmem_full);
             __syncwarp();
         }
+        if ((mode & 4) && lane == 0) {
+            long long *st = reinterpret_cast<long long *>(dbg_acc) + blockIdx.x * 4;
+            st[0] = clock64() - t_start;
+            st[3] = waited_epi;
+        }
+        // the elected lane need not be lane 0: every lane adds what it waited (the others waited nothing)
+        if (mode & 4) atomicAdd(reinterpret_cast<unsigned long long *>(dbg_acc) + gridDim.x * 4 + blockIdx.x, (unsigned long long)waited);
     } else if (warp >= 4) {
         // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 =====
         const int q = warp - 4;
@@ -322,7 +342,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int d = 0; d < S; ++d) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 16), acc[d]);
                 tmem_ld_wait();
-                if (dbg_acc != nullptr) {
+                if (dbg_acc != nullptr && !(mode & 4)) {
 #pragma unroll
                     for (int d = 0; d < S; ++d)
 #pragma unroll
@@ -346,7 +366,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     }
     tc_fence_before();
-    if constexpr (CL > 1) cluster_sync(); else __syncthreads();              // no CTA leaves while its peer can still signal it
+    __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -429,30 +449,51 @@ __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double *__restr
     atomicMax(colmax_bits + n, (unsigned long long)__double_as_longlong(mx));
 }
 
-// B[K][N] -> planes[S][N][K] int8 (transposed: k contiguous), scale[N]: one thread per column and 32 rows
-__global__ void __launch_bounds__(128) ozaki_split_cols_kernel(const double *__restrict__ B, int K, int N, size_t plane_stride,
+// B[K][N] -> planes[S][N][K] int8 (transposed: k contiguous), scale[N].  A CTA takes 32 columns x 128 rows: lane = column
+// (256-byte coalesced row segments), each thread packs the digits of 4 consecutive rows into one 32-bit word per plane,
+// the words go through shared memory (rows padded to 132 bytes: conflict-free both ways) and leave as 128-byte runs
+// along k, one (plane, column) per warp store.
+__global__ void __launch_bounds__(256) ozaki_split_cols_kernel(const double *__restrict__ B, int K, int N, size_t plane_stride,
                                                                const unsigned long long *__restrict__ colmax_bits,
                                                                signed char *__restrict__ planes, double *__restrict__ scale)
 {
     using namespace oz;
-    const int n = blockIdx.x * 128 + threadIdx.x;
-    if (n >= N) return;
-    const int k0 = blockIdx.y * 32;
-    const double p = pow2_above(__longlong_as_double((long long)colmax_bits[n])), inv = 1.0 / p;
-    if (blockIdx.y == 0) scale[n] = p;
-    signed char out[S][32];
+    constexpr int COLS = 32, ROWS = 128, LD = ROWS + 4;
+    __shared__ __align__(16) unsigned char tile[S][COLS][LD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * COLS, k0 = blockIdx.y * ROWS, n = n0 + lane;
+    if (n < N) {
+        const double p = pow2_above(__longlong_as_double((long long)colmax_bits[n])), inv = 1.0 / p;
+        if (blockIdx.y == 0 && warp == 0) scale[n] = p;
+        double v[4][4];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        signed char q[S];
-        digits(B[(size_t)(k0 + e) * N + n] * inv, q);
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int s = 0; s < S; ++s) out[s][e] = q[s];
+            for (int e = 0; e < 4; ++e) v[r][e] = B[(size_t)(k0 + 4 * (warp + 8 * r) + e) * N + n];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t word[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) word[s] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                signed char q[S];
+                digits(v[r][e] * inv, q);
+#pragma unroll
+                for (int s = 0; s < S; ++s) word[s] |= (uint32_t)(unsigned char)q[s] << (8 * e);
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t *>(&tile[s][lane][4 * (warp + 8 * r)]) = word[s];
+        }
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        uint4 *dst = reinterpret_cast<uint4 *>(planes + s * plane_stride + (size_t)n * K + k0);
-        dst[0] = *reinterpret_cast<const uint4 *>(out[s]);
-        dst[1] = *reinterpret_cast<const uint4 *>(out[s] + 16);
+    __syncthreads();
+    // warp w writes (plane, column) pairs w, w + 8, ...: 128 contiguous bytes each
+#pragma unroll 4
+    for (int pair = warp; pair < S * COLS; pair += 8) {
+        const int s = pair / COLS, c = pair % COLS;
+        if (n0 + c < N)
+            *reinterpret_cast<uint32_t *>(planes + s * plane_stride + (size_t)(n0 + c) * K + k0 + 4 * lane) =
+                *reinterpret_cast<const uint32_t *>(&tile[s][c][4 * lane]);
     }
 }
 
@@ -514,8 +555,8 @@ DSB_API int dsb_ozaki_split_a(const double *A, int64_t M, int64_t K, signed char
 DSB_API int dsb_ozaki_split_b(const double *B, int64_t K, int64_t N, signed char *planes, double *scale, void *workspace,
                               void *stream)
 {
-    if (B == nullptr || planes == nullptr || scale == nullptr || workspace == nullptr || N <= 0 || K <= 0 || K % 32 != 0) {
-        set_error("dsb_ozaki_split_b: bad arguments (K must be a multiple of 32)");
+    if (B == nullptr || planes == nullptr || scale == nullptr || workspace == nullptr || N <= 0 || K <= 0 || K % 128 != 0) {
+        set_error("dsb_ozaki_split_b: bad arguments (K must be a multiple of 128)");
         return DSB_ERR_BAD_ARGUMENT;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -523,8 +564,8 @@ DSB_API int dsb_ozaki_split_b(const double *B, int64_t K, int64_t N, signed char
     const int rows_per_block = 128;
     dim3 g1((unsigned)((N + 255) / 256), (unsigned)((K + rows_per_block - 1) / rows_per_block));
     ozaki_colmax_kernel<<<g1, 256, 0, st>>>(B, (int)K, (int)N, rows_per_block, (unsigned long long *)workspace);
-    dim3 g2((unsigned)((N + 127) / 128), (unsigned)(K / 32));
-    ozaki_split_cols_kernel<<<g2, 128, 0, st>>>(B, (int)K, (int)N, (size_t)N * K, (const unsigned long long *)workspace, planes, scale);
+    dim3 g2((unsigned)((N + 31) / 32), (unsigned)(K / 128));
+    ozaki_split_cols_kernel<<<g2, 256, 0, st>>>(B, (int)K, (int)N, (size_t)N * K, (const unsigned long long *)workspace, planes, scale);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }
@@ -539,39 +580,18 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
         set_error("dsb_ozaki_gemm: needs M %% 128 == 0, N %% 64 == 0, K %% 64 == 0 and K <= 32768 (INT32 accumulators)");
         return DSB_ERR_BAD_ARGUMENT;
     }
-    // clusters of two CTAs that multicast the A tiles were measured: exact, and no faster (3.62 against 3.60 ms on
-    // 4096 x 8192 x 4096 -- the limit is what one SM can take in, not what L2 reads); kept behind DSB_OZAKI_CLUSTER=1
-    const bool pair = (N % (2 * BN) == 0) && sms >= 2 && getenv("DSB_OZAKI_CLUSTER") != nullptr;
     CUtensorMap map_a, map_b;
-    int rc = make_map(&map_a, a_planes, (long long)S * M, K, pair ? BM / 2 : BM);
+    int rc = make_map(&map_a, a_planes, (long long)S * M, K, BM);
     if (rc != DSB_OK) return rc;
     rc = make_map(&map_b, b_planes, (long long)S * N, K, BN);
     if (rc != DSB_OK) return rc;
-    const int mode = getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0;
-    const int m = (int)M, n = (int)N, k = (int)K;
+    const int mode = getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0;       // timing experiments (tools/ozaki_check.py)
     const int band = getenv("DSB_OZAKI_BAND") ? atoi(getenv("DSB_OZAKI_BAND")) : 16;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    if (pair) {
-        DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        const long long groups = (M / BM) * (N / BN / 2);
-        cfg.gridDim = dim3((unsigned)(2 * (groups < sms / 2 ? groups : sms / 2)));
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<2>, map_a, map_b, a_scale, b_scale, C, m, n, k, dbg_acc, mode, band));
-    } else {
-        DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        const long long tiles = (M / BM) * (N / BN);
-        cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms));
-        DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<1>, map_a, map_b, a_scale, b_scale, C, m, n, k, dbg_acc, mode, band));
-    }
+    DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const long long tiles = (M / BM) * (N / BN);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, a_scale, b_scale, C, (int)M, (int)N, (int)K,
+                                                                           dbg_acc, mode, band);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }

@@ -415,7 +415,7 @@ DSB_API int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, in
  * dsb_dgemm / cuBLAS / numpy (tests compare it with an exactly rounded reference).
  *   dsb_ozaki_split_a   A[M][K] row-major -> planes[S][M][K] int8, scale[M]     (once per matrix; K % 16 == 0)
  *   dsb_ozaki_split_b   B[K][N] row-major -> planes[S][N][K] int8 (transposed), scale[N]; workspace: N * 8 bytes;
- *                       K % 32 == 0
+ *                       K % 128 == 0
  *   dsb_ozaki_gemm      C[M][N] = A B from the planes; M % 128 == 0, N % 64 == 0, K % 64 == 0, K <= 32768 (INT32
  *                       accumulators), else DSB_ERR_BAD_ARGUMENT; `sms` = CTAs to launch (one per SM); dbg_acc: NULL, or
  *                       [S][M][N] int32 receiving the raw accumulators (tests).  No hidden synchronisation. */
