@@ -17,7 +17,7 @@
 //   The result is not the sequence of roundings of a left-to-right FP64 dot product (nor of cuBLAS' DMMA order); its
 //   error is bounded by ~2^-52 |row max| |column max| K^0.5-ish, measured in tools/ozaki_check.py against an exact product.
 //
-// Kernel (one CTA per SM, persistent over 128 x 64 output tiles walked in bands of 16 row blocks, 256 threads):
+// Kernel (one CTA per SM, persistent over 128 x 64 output tiles walked in bands of row blocks, 256 threads):
 //   warp 0   TMA producer of the A tiles (128 x 64 bytes, 64-byte swizzle), ring of 16 slots with one mbarrier pair each;
 //   warp 3   TMA producer of the B tiles (64 x 64 bytes), two groups of 8 slots (one group per k-block parity);
 //            position p of a k-block brings A_(7-p) and B_p;
@@ -28,11 +28,15 @@
 //            B group at the end of the k-block;
 //   warp 2   owns the TMEM allocation;
 //   warps 4-7 epilogue: tcgen05.ld of the 8 accumulators of 16 columns, Horner in FP64, scale, 128-byte stores per lane.
-// Operand traffic from L2: 96 KB per k-block per tile for 72 MMAs (128 x 64 x 32).  Measured (4096 x 8192 x 4096, B200):
-// 3.66 ms against 7.78 ms for cuBLAS DGEMM and 8.02 ms for dgemm.cu; the MMA lane never waits for operands (0.03 % of its
-// cycles, DSB_OZAKI_MODE=4), the tensor pipe runs at 52 cycles per instruction against a floor of 32: what is left is the
-// shared-memory port (B tile re-read per instruction + A fills + TMA writes ~ one port-load per MMA cycle).
-// Tried and dropped: clusters of two CTAs multicasting the A tiles (exact, 3.62 ms: no gain -- L2 is not the limit).
+// Two flavours: ozaki_gemm_kernel (every CTA on its own, any M % 128 == 0) and ozaki_gemm_pair_kernel (M % 256 == 0: CTA
+// pairs, tcgen05 cta_group::2 -- 256 x 64 tiles, each CTA loads its 128 rows of A and HALF of the B rows, the leader
+// issues UTCIMMA.2CTA for both).  Measured (4096 x 8192 x 4096, B200): pairs **2.93 ms**, single CTAs 3.65 ms, against
+// 7.78 ms for cuBLAS DGEMM and 8.02 ms for dgemm.cu; MMA alone 2.55 ms, TMA alone 2.33 ms, the floor of the pipe 2.2 ms.
+// In the single-CTA kernel the MMA lane never waits for operands (0.03 % of its cycles, DSB_OZAKI_MODE=4) but the tensor
+// pipe runs at 52 cycles per instruction against a floor of 32: the shared-memory port carries the B tile of every
+// instruction, the A fills and the TMA writes; pairs halve the B reads and cut the TMA bytes by a sixth.
+// Tried and dropped: clusters of two CTAs multicasting the A tiles (exact, no gain -- L2 is not the limit); in the pair
+// kernel a remote mbarrier arrive per load (11.5 ms) and cluster-scope acquire waits (4.9 ms).
 //
 // The digit planes of A are produced once per matrix (dsb_ozaki_split_a), those of Y per product (dsb_ozaki_split_b,
 // which also transposes to K-major: [plane][column][k]).
@@ -113,6 +117,64 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const CUtensorMap *ma
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA pairs (cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what)
+{
+    const long long t0 = clock64();
+    while (!mbar_try_cluster(bar, parity)) {
+        if (clock64() - t0 > WAIT_LIMIT) {
+            printf("ozaki_gemm: cluster barrier wait %d timed out (block %d thread %d)\n", what, (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+// TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the barrier `bar_cluster`
+// (a shared::cluster address: the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+// completion of all MMAs issued so far, signalled on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -150,6 +212,23 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
     else DSB_OZ_MMA("");
 #undef DSB_OZ_MMA
 }
+// the same for a CTA pair: D is 256 x N (128 rows in each CTA's TMEM), A = this CTA's 128 rows, B = N / 2 rows from each CTA
+template <int COLL>
+__device__ __forceinline__ void mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+#define DSB_OZ_MMA2(MOD)                                                                                  \
+    asm volatile(                                                                                         \
+        "{\n"                                                                                             \
+        ".reg .pred p;\n"                                                                                 \
+        "setp.ne.b32 p, %4, 0;\n"                                                                         \
+        "tcgen05.mma.cta_group::2.kind::i8" MOD " [%0], %1, %2, %3, p;\n"                                 \
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory")
+    if constexpr (COLL == 1) DSB_OZ_MMA2(".collector::a::fill");
+    else if constexpr (COLL == 2) DSB_OZ_MMA2(".collector::a::use");
+    else if constexpr (COLL == 3) DSB_OZ_MMA2(".collector::a::lastuse");
+    else DSB_OZ_MMA2("");
+#undef DSB_OZ_MMA2
+}
 // K-major operand tile whose rows are 64 bytes, 64-byte swizzle (TMA CU_TENSOR_MAP_SWIZZLE_64B): groups of 8 rows are
 // 512 bytes apart (stride byte offset); the leading byte offset is not used by swizzled K-major layouts
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr)
@@ -160,6 +239,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr)
 }
 // c_format S32 (2) | a, b INT8 (1) | K-major both | N >> 3 | M >> 4
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr int B_HALF = B_TILE / 2;               // a CTA of a pair holds half of the B rows
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16])
 {
@@ -170,6 +251,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace oz
+
+// One output row of a tile (this lane's TMEM lane): the 8 accumulators of 16 columns at a time, Horner in FP64 from the
+// lightest weight, the two power-of-two scales, 128-byte stores.
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int row, int n0, const double *__restrict__ scale_a,
+                                              const double *__restrict__ scale_b, double *__restrict__ C, int M, int N,
+                                              int *__restrict__ dbg_acc)
+{
+    using namespace oz;
+    constexpr double W = 1.0 / 128.0;                                         // 2^-7 between neighbouring weights
+    const double sa = scale_a[row] * (1.0 / 4096.0);                          // 2^-6 * 2^-6 of the two leading digits
+    double *crow = C + (size_t)row * N + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 16; ++c) {
+        int acc[S][16];
+#pragma unroll
+        for (int d = 0; d < S; ++d) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 16), acc[d]);
+        tmem_ld_wait();
+        if (dbg_acc != nullptr) {
+#pragma unroll
+            for (int d = 0; d < S; ++d)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dbg_acc[((size_t)d * M + row) * N + n0 + c * 16 + e] = acc[d][e];
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            double v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double s = (double)acc[S - 1][e + h];
+#pragma unroll
+                for (int d = S - 2; d >= 0; --d) s = fma(s, W, (double)acc[d][e + h]);
+                v[h] = s * sa * __ldg(scale_b + n0 + c * 16 + e + h);
+            }
+            *reinterpret_cast<double2 *>(crow + c * 16 + e) = make_double2(v[0], v[1]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(oz::THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -328,39 +446,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 =====
         const int q = warp - 4;
         uint32_t n_tile = 0;
-        constexpr double W = 1.0 / 128.0;                                     // 2^-7 between neighbouring weights
         int m0, n0;
         for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
             mbar_wait(tmem_full, n_tile & 1, 400);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const double sa = scale_a[row] * (1.0 / 4096.0);                  // 2^-6 * 2^-6 of the two leading digits
-            double *crow = C + (size_t)row * N + n0;
-#pragma unroll 1
-            for (int c = 0; c < BN / 16; ++c) {
-                int acc[S][16];
-#pragma unroll
-                for (int d = 0; d < S; ++d) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * BN + c * 16), acc[d]);
-                tmem_ld_wait();
-                if (dbg_acc != nullptr && !(mode & 4)) {
-#pragma unroll
-                    for (int d = 0; d < S; ++d)
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) dbg_acc[((size_t)d * M + row) * N + n0 + c * 16 + e] = acc[d][e];
-                }
-#pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    double v[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        double s = (double)acc[S - 1][e + h];
-#pragma unroll
-                        for (int d = S - 2; d >= 0; --d) s = fma(s, W, (double)acc[d][e + h]);
-                        v[h] = s * sa * __ldg(scale_b + n0 + c * 16 + e + h);
-                    }
-                    *reinterpret_cast<double2 *>(crow + c * 16 + e) = make_double2(v[0], v[1]);
-                }
-            }
+            epilogue_tile(tmem_base, q, m0 + q * 32 + lane, n0, scale_a, scale_b, C, M, N, (mode & 4) ? nullptr : dbg_acc);
             tc_fence_before();
             mbar_arrive(tmem_empty);
         }
@@ -370,6 +460,179 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ---- the same product on CTA pairs (tcgen05 cta_group::2) ---------------------------------------------------------------
+// Two CTAs on the SMs of one TPC share a 256 x 64 output tile: each holds 128 rows of every accumulator in its own TMEM,
+// loads its own 128 rows of the A planes and HALF of the B planes' rows (32 of 64) -- the tensor cores of the pair read the
+// B operand from both shared memories, so a CTA moves 10 KB instead of 12 KB per unit and re-reads half as much B.  Only
+// the leader (cluster rank 0) issues MMAs; TMA loads of both CTAs count on the leader's `full` barriers, the leader's
+// commits release the slots and publish the accumulators in both CTAs.
+__global__ void __launch_bounds__(oz::THREADS, 1)
+ozaki_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const double *__restrict__ scale_a, const double *__restrict__ scale_b, double *__restrict__ C, int M,
+                       int N, int K, int *__restrict__ dbg_acc, int mode, int band)
+{
+    using namespace oz;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (sptr(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = smem_base + RING * A_TILE;
+    const uint32_t bars = smem_b + RING * B_HALF;
+    auto full_a = [&](int u) { return bars + 8u * u; };
+    auto full_b = [&](int u) { return bars + 8u * (RING + u); };
+    auto empty_a = [&](int u) { return bars + 8u * (2 * RING + u); };
+    auto empty_b = [&](int g) { return bars + 8u * (3 * RING + g); };
+    const uint32_t tmem_full = bars + 8u * (3 * RING + 2), tmem_empty = tmem_full + 8u, tmem_slot = tmem_empty + 8u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int mb = M / (2 * BM), items = mb * (N / BN), kblocks = K / BK;
+    // work item `it` of this pair: 256-row block (this CTA: its 128 rows m0), column block n0
+    auto tile_at = [&](int it, int &m0, int &n0) {
+        const int g = pair_id + it * n_pairs;
+        if (g >= items) return false;
+        const int nbc = N / BN, per_band = band * nbc, b0 = (g / per_band) * band;
+        const int rows = (mb - b0) < band ? (mb - b0) : band, r = g - (g / per_band) * per_band;
+        m0 = (b0 + r % rows) * (2 * BM) + (int)rank * BM;
+        n0 = (r / rows) * BN;
+        return true;
+    };
+
+    if (warp == 1 && lane == 0) {
+        // `full` (used in the leader only): one arrival, the leader's, carrying the byte count of BOTH CTAs' loads -- the
+        // peer's loads just complete their bytes there (a remote arrive per unit costs ~0.5 us: 11.5 ms instead of 3.6)
+        for (int u = 0; u < RING; ++u) { mbar_init(full_a(u), 1); mbar_init(full_b(u), 1); mbar_init(empty_a(u), 1); }
+        mbar_init(empty_b(0), 1);
+        mbar_init(empty_b(1), 1);
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 256);                                            // the epilogue threads of both CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    cluster_sync();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+      if (lane == 0 && !(mode & 1)) {
+        // ===== TMA producer of this CTA's A tiles =====
+        uint32_t n_unit = 0;
+        const uint32_t lbar0 = map_to_cta(full_a(0), 0);
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll 1
+                for (int p = 0; p < S; ++p, ++n_unit) {
+                    const int slot = n_unit % RING;
+                    const uint32_t use = n_unit / RING;
+                    if (use > 0) mbar_wait(empty_a(slot), (use - 1) & 1, 100 + slot);
+                    const uint32_t lbar = lbar0 + 8u * slot;
+                    if (leader) mbar_expect_tx(full_a(slot), 2 * A_TILE);
+                    tma_load_2d_pair(smem_base + slot * A_TILE, &map_a, kb * BK, (S - 1 - p) * M + m0, lbar);
+                }
+            }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 3) {
+      if (lane == 0 && !(mode & 1)) {
+        // ===== TMA producer of this CTA's half of the B tiles =====
+        uint32_t n_kb = 0;
+        const uint32_t lbar0 = map_to_cta(full_b(0), 0);
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it) {
+            for (int kb = 0; kb < kblocks; ++kb, ++n_kb) {
+                const int grp = n_kb & 1;
+                const uint32_t use = n_kb >> 1;
+                if (use > 0) mbar_wait(empty_b(grp), (use - 1) & 1, 150 + grp);
+#pragma unroll 1
+                for (int p = 0; p < S; ++p) {
+                    const int slot = grp * S + p;
+                    const uint32_t lbar = lbar0 + 8u * slot;
+                    if (leader) mbar_expect_tx(full_b(slot), 2 * B_HALF);
+                    tma_load_2d_pair(smem_b + slot * B_HALF, &map_b, kb * BK, p * N + n0 + (int)rank * (BN / 2), lbar);
+                }
+            }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (leader) {
+        // ===== MMA issuer of the pair =====
+        const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+        const uint32_t lo_a0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16), lo_b0 = ((smem_b >> 4) & 0x3FFFu) | (1u << 16);
+        auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
+        uint32_t n_kb = 0, n_tile = 0;
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
+            if (n_tile > 0) {
+                mbar_wait(tmem_empty, (n_tile - 1) & 1, 300);          // both epilogues have drained the accumulators
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < kblocks; ++kb, ++n_kb) {
+                const int base = (n_kb & 1) * S;
+                const uint32_t parity = (n_kb >> 1) & 1;
+                const uint32_t lo_a = lo_a0 + (uint32_t)base * (A_TILE / 16), lo_b = lo_b0 + (uint32_t)base * (B_HALF / 16);
+                if (elect_one()) {
+#pragma unroll
+                    for (int p = 0; p < S; ++p) {
+                        if (!(mode & 1)) {
+                            mbar_wait(full_a(base + p), parity, 200 + base + p);
+                            mbar_wait(full_b(base + p), parity, 250 + base + p);
+                            tc_fence_after();
+                        }
+                        if (!(mode & 2)) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+#pragma unroll
+                                for (int j = 0; j <= p; ++j) {
+                                    const uint32_t d_tmem = tmem_base + (uint32_t)((S - 1 - p + j) * BN);
+                                    const uint64_t ad = desc(lo_a + p * (A_TILE / 16) + kk * (UMMA_K / 16));
+                                    const uint64_t bd = desc(lo_b + j * (B_HALF / 16) + kk * (UMMA_K / 16));
+                                    const uint32_t accumulate = (j > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0);
+                                    if (!DSB_OZAKI_COLLECTOR || p == 0) mma_i8_pair<0>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
+                                    else if (j == 0) mma_i8_pair<1>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
+                                    else if (j == p) mma_i8_pair<3>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
+                                    else mma_i8_pair<2>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
+                                }
+                            }
+                        }
+                        tc_commit_pair(empty_a(base + p));
+                    }
+                    tc_commit_pair(empty_b(n_kb & 1));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit_pair(tmem_full);
+            __syncwarp();
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue of this CTA's 128 rows =====
+        const int q = warp - 4;
+        uint32_t n_tile = 0;
+        const uint32_t lempty = map_to_cta(tmem_empty, 0);
+        int m0, n0;
+        for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
+            mbar_wait(tmem_full, n_tile & 1, 400);
+            tc_fence_after();
+            epilogue_tile(tmem_base, q, m0 + q * 32 + lane, n0, scale_a, scale_b, C, M, N, dbg_acc);
+            tc_fence_before();
+            mbar_arrive_cluster(lempty);
+        }
+    }
+    tc_fence_before();
+    cluster_sync();                                                            // nobody leaves while its peer can still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
@@ -587,6 +850,30 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
     if (rc != DSB_OK) return rc;
     const int mode = getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0;       // timing experiments (tools/ozaki_check.py)
     const int band = getenv("DSB_OZAKI_BAND") ? atoi(getenv("DSB_OZAKI_BAND")) : 16;
+    const bool pair = (M % (2 * BM) == 0) && sms >= 2 && getenv("DSB_OZAKI_NO_PAIR") == nullptr;
+    if (pair) {
+        CUtensorMap map_bh;
+        rc = make_map(&map_bh, b_planes, (long long)S * N, K, BN / 2);
+        if (rc != DSB_OK) return rc;
+        DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        const long long items = (M / (2 * BM)) * (N / BN);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * (items < sms / 2 ? items : sms / 2)));
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int pband = getenv("DSB_OZAKI_BAND") ? band : 4;                 // in 256-row blocks
+        DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_pair_kernel, map_a, map_bh, a_scale, b_scale, C, (int)M, (int)N, (int)K,
+                                          dbg_acc, mode, pband));
+        return DSB_OK;
+    }
     DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const long long tiles = (M / BM) * (N / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
