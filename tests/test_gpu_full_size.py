@@ -135,6 +135,46 @@ def test_config2_linear_4096_by_8192():
     assert de.rhs_plugins.linear.calls_library == lib_before
 
 
+def test_config2_linear_on_the_int8_tensor_cores():
+    """Config 2 with `linear.gemm = "int8"` (csrc/ozaki_gemm.cu, CTA pairs): the digit planes of a column depend on that
+    column alone and the accumulators are exact, so a block of columns integrated on its own gives the same BITS as inside
+    the full ensemble; sampled columns against the CPU oracle (counts identical, states within the parity bar); every
+    product of the run on the INT8 kernel or (compacted tail) on dsb_dgemm, none on the library."""
+    de = _de()
+    lin = de.rhs_plugins.linear
+    n, cols = 4096, 8192
+    A, Y0 = de.benchmarks.linear_system(n, cols)
+    Ad, Yd = torch.as_tensor(A).cuda(), torch.as_tensor(Y0).cuda()
+
+    def run(y):
+        a = de.OdeSystem(lin, y, t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, constants=dict(A=Ad), ensemble=True)
+        a.method = "RK87"
+        a.integrate()
+        return a
+    lin.gemm = "int8"
+    try:
+        int8_before, lib_before = lin.calls_int8, lin.calls_library
+        a = run(Yd)
+        assert lin.calls_int8 > int8_before and lin.calls_library == lib_before
+        assert a.success and bool((a[-1].t == 1.0).all())
+        sub = slice(2048, 2048 + 256)
+        b = run(Yd[:, sub].contiguous())
+    finally:
+        lin.gemm = "dmma"
+        lin._int8.clear()
+    assert torch.equal(b.accepted, a.accepted[sub]) and torch.equal(b.rejected, a.rejected[sub])
+    assert torch.equal(b[-1].y, a[-1].y[:, sub])
+    ratio = a[-1].y.norm(dim=0) / Yd.norm(dim=0)
+    assert float((ratio - np.exp(-0.1)).abs().max()) < 1e-8
+    from desolver_b200.integrators import tableaux as tb
+    from oracle import oracle as orc
+    idx = np.linspace(0, cols - 1, 6).astype(int)
+    ref = orc.erk_ensemble(orc.RHS_LINEAR, Y0[:, idx], 0.0, 1.0, 1e-2, 1e-9, 1e-9, *tb.rk_arrays("RK8713MSolver"), shared=A,
+                           threads=os.cpu_count())
+    assert rel_inf(a[-1].y[:, idx].cpu().numpy(), ref["y"]).max() <= 1e-10
+    assert np.array_equal(a.accepted[idx].cpu().numpy(), ref["accepted"]) and np.array_equal(a.rejected[idx].cpu().numpy(), ref["rejected"])
+
+
 def test_config1_events_are_pure_observers_at_full_size():
     """2^20 Lorenz trajectories with two recorded sections: integration bit-identical to the run without events, every
     recorded state on its hyperplane, event times increasing per trajectory."""

@@ -1,42 +1,64 @@
 #!/usr/bin/env python
-"""Where the end-to-end (host buffers) time of one Lorenz 2^20 pass goes, for the host_io pipelines of OdeSystem:
-"streamed" (one persistent launch + stream memory operations, dsb_erk_run_host) and "chunked" (one launch per chunk)."""
-import os
+"""Where the end-to-end pass (pinned host y0 -> pinned host result through OdeSystem(host_io=True)) spends its time:
+device-resident pass, host pipeline with a reused system, with construction, for several chunk counts; host-side clock of
+the constructor and of integrate()."""
+import json
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
-import torch  # noqa: E402
+import numpy as np
+import torch
+
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import desolver_b200 as de  # noqa: E402
 
-n = 1 << 20
-cfg = de.benchmarks.LORENZ
-y0_pinned = torch.from_numpy(de.benchmarks.lorenz_ensemble(n)).pin_memory()
 dev = torch.device("cuda:0")
-host_out = dict(y=torch.empty((3, n), dtype=torch.float64).pin_memory(), accepted=torch.empty(n, dtype=torch.int32).pin_memory(),
-                rejected=torch.empty(n, dtype=torch.int32).pin_memory(), status=torch.empty(n, dtype=torch.int32).pin_memory())
+cfg = de.benchmarks.LORENZ
+n = 1 << 20
+y0 = de.benchmarks.lorenz_ensemble(n, seed=0)
+y0_pinned = torch.as_tensor(y0).pin_memory()
+host_out = dict(y=torch.empty((3, n), dtype=torch.float64).pin_memory())
+kw = dict(t=(cfg["t0"], cfg["tf"]), dt=cfg["dt0"], rtol=cfg["rtol"], atol=cfg["atol"], ensemble=True, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-for mode, chunks in (("streamed", 4), ("streamed", 8), ("streamed", 16), ("streamed", 32), ("chunked", 4), ("chunked", 8)):
-    res = []
-    for rep in range(6):
+
+def timed(fn, reps=6, warm=2):
+    out = []
+    for i in range(warm + reps):
         flush.zero_()
         torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        s = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned, t=(cfg["t0"], cfg["tf"]), dt=cfg["dt0"], rtol=cfg["rtol"], atol=cfg["atol"],
-                         ensemble=True, device=dev, host_io=True, host_out=host_out, host_chunks=chunks)
-        s.host_pipeline = mode
+        fn()
         b.record()
-        w1 = time.perf_counter()
-        s.integrate()
-        c.record()
         torch.cuda.synchronize()
-        w2 = time.perf_counter()
-        if rep >= 2:
-            res.append((a.elapsed_time(b), b.elapsed_time(c), (w1 - w0) * 1e3, (w2 - w1) * 1e3))
-    r = np.mean(res, axis=0)
-    print("%-8s chunks %2d: events construct %.3f integrate %.3f total %.3f ms | host construct %.3f integrate %.3f ms" %
-          (mode, chunks, r[0], r[1], r[0] + r[1], r[2], r[3]))
+        if i >= warm:
+            out.append(a.elapsed_time(b))
+    return float(np.median(out)), out
+
+
+res = {}
+s = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(y0).to(dev), **kw)
+s.method = "RK45CK"
+res["device_resident_ms"] = timed(lambda: (s.reset(), s.integrate()))[0]
+for chunks in (8, 16, 32, 64):
+    holder = {}
+
+    def build():
+        holder["s"] = None
+        holder["s"] = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned, host_io=True, host_out=host_out, host_chunks=chunks, **kw)
+        holder["s"].integrate()
+    res["e2e_construct_chunks%d_ms" % chunks] = timed(build)[0]
+    s2 = holder["s"]
+    res["e2e_reuse_chunks%d_ms" % chunks] = timed(lambda: (s2.reset(), s2.integrate()))[0]
+# host-side clock of one pass (16 chunks)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+s3 = de.OdeSystem(de.rhs_plugins.lorenz, y0_pinned, host_io=True, host_out=host_out, host_chunks=16, **kw)
+t1 = time.perf_counter()
+s3.integrate()
+t2 = time.perf_counter()
+torch.cuda.synchronize()
+t3 = time.perf_counter()
+res["host_clock_ms"] = dict(constructor=(t1 - t0) * 1e3, integrate_call=(t2 - t1) * 1e3, sync_after=(t3 - t2) * 1e3)
+print(json.dumps(res, indent=1))
