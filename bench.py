@@ -387,9 +387,9 @@ def main():
                 torch.cuda.empty_cache()
                 extra["config3_nbody"] = cr.run_nbody(dev, reps=3, check=16)
                 torch.cuda.empty_cache()
-                extra["config2_linear"] = cr.run_linear(dev, reps=2, check=4)
+                extra["config2_linear"] = cr.run_linear(dev, reps=2, check=4)                    # plugin default: INT8 tensor cores
                 torch.cuda.empty_cache()
-                extra["config2_linear_int8"] = cr.run_linear(dev, reps=2, check=4, gemm="int8")
+                extra["config2_linear_dmma"] = cr.run_linear(dev, reps=2, check=4, gemm="dmma")     # every product on the FP64 DMMA kernel
             else:
                 extra["strong_2pow20"] = cr.run_lorenz_strong(dev, world, rank, reps=5)
                 extra["vdp_2pow24_sharded"] = cr.run_vdp(dev, world, rank, reps=3, check=2048, hbm_peak=peak_gbs)

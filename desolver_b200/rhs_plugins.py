@@ -68,15 +68,16 @@ def linear(t, y, A=None, out=None):
     """Dense linear system y' = A @ y (A shared by the whole ensemble; y is (n,) or (n, N)).
 
     For an ensemble of CUDA float64 columns whose shape fits its tiling, the product is one of the library's own
-    tensor-core kernels: `linear.gemm = "dmma"` (default) the FP64 DMMA kernel (dsb_dgemm, csrc/dgemm.cu; the rounding
-    sequence of an FP64 GEMM), `linear.gemm = "int8"` the error-free digit-plane product on the INT8 tensor cores
-    (dsb_ozaki_*, csrc/ozaki_gemm.cu; closer to the exact product, 1.7x faster, needs n % 128 == 0 and >= 1024 columns
-    to pay off).  Otherwise -- numpy arrays, the reference, odd shapes -- the array library's matmul;
+    tensor-core kernels: `linear.gemm = "dmma"` the FP64 DMMA kernel (dsb_dgemm, csrc/dgemm.cu; the rounding sequence of
+    an FP64 GEMM, bit-identical to cuBLAS), `linear.gemm = "int8"` the error-free digit-plane product on the INT8 tensor
+    cores (dsb_ozaki_*, csrc/ozaki_gemm.cu; closer to the exact product than an FP64 GEMM and 2.4x faster than cuBLAS at
+    4096 x 8192 x 4096; needs n % 128 == 0), `"auto"` (default) the INT8 kernel for large products (n >= 1024 and >= 512
+    columns), the DMMA kernel otherwise.  Numpy arrays, the reference, odd shapes: the array library's matmul;
     `linear.use_library_gemm = True` forces the latter."""
     if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2
             and getattr(A, "is_cuda", False)):
         from .backend import cuda_backend as cb
-        if linear.gemm == "int8":
+        if linear.gemm == "int8" or (linear.gemm == "auto" and min(A.shape) >= 1024 and y.shape[1] >= 512):
             prod = linear._int8.get(id(A))
             if prod is None or prod.A is not A:
                 linear._int8.clear()                        # one matrix at a time: the planes of A are as large as A
@@ -97,7 +98,7 @@ def linear(t, y, A=None, out=None):
 
 
 linear.use_library_gemm = False
-linear.gemm = "dmma"              # "dmma" | "int8": which tensor-core kernel serves the product (see the docstring)
+linear.gemm = "auto"              # "auto" | "dmma" | "int8": which tensor-core kernel serves the product (see the docstring)
 linear._int8 = {}
 linear.calls_int8 = 0
 linear.calls_dsb = 0              # products served by dsb_dgemm / by the array library (CUDA-graph replays are not

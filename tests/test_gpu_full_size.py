@@ -107,12 +107,16 @@ def test_config2_linear_4096_by_8192():
         a.method = "RK87"
         a.integrate()
         return a
-    a = run(Yd)
-    assert a.success and bool((a[-1].t == 1.0).all())
-    att = (a.accepted + a.rejected)
-    assert int(att.min()) >= 8 and int(att.max()) <= 12
-    sub = slice(1024, 1024 + 256)
-    b = run(Yd[:, sub].contiguous())
+    de.rhs_plugins.linear.gemm = "dmma"                 # this test is about the FP64 DMMA kernel (the default "auto" picks INT8 here)
+    try:
+        a = run(Yd)
+        assert a.success and bool((a[-1].t == 1.0).all())
+        att = (a.accepted + a.rejected)
+        assert int(att.min()) >= 8 and int(att.max()) <= 12
+        sub = slice(1024, 1024 + 256)
+        b = run(Yd[:, sub].contiguous())
+    finally:
+        de.rhs_plugins.linear.gemm = "auto"
     assert torch.equal(b.accepted, a.accepted[sub]) and torch.equal(b.rejected, a.rejected[sub])
     assert float((b[-1].y - a[-1].y[:, sub]).abs().max()) <= 1e-13 * float(a[-1].y.abs().max())
     # the flow e^{A t} of the damped near-skew matrix contracts: |y(1)| <= e^{-0.1} |y(0)| up to the integration error
@@ -130,8 +134,12 @@ def test_config2_linear_4096_by_8192():
     # no product of the configuration left the library's own tensor-core kernel (compacted tail included)
     assert de.rhs_plugins.linear.calls_dsb > 0
     lib_before = de.rhs_plugins.linear.calls_library
-    a.reset()
-    a.integrate()
+    de.rhs_plugins.linear.gemm = "dmma"
+    try:
+        a.reset()
+        a.integrate()
+    finally:
+        de.rhs_plugins.linear.gemm = "auto"
     assert de.rhs_plugins.linear.calls_library == lib_before
 
 
@@ -160,7 +168,7 @@ def test_config2_linear_on_the_int8_tensor_cores():
         sub = slice(2048, 2048 + 256)
         b = run(Yd[:, sub].contiguous())
     finally:
-        lin.gemm = "dmma"
+        lin.gemm = "auto"
         lin._int8.clear()
     assert torch.equal(b.accepted, a.accepted[sub]) and torch.equal(b.rejected, a.rejected[sub])
     assert torch.equal(b[-1].y, a[-1].y[:, sub])

@@ -170,7 +170,7 @@ def test_linear_plugin_on_the_int8_kernel_matches_the_oracle():
             a.method = "RK87"
             a.integrate()
         finally:
-            lin.gemm = "dmma"
+            lin.gemm = "auto"
         return a
     before = lin.calls_int8
     a = run("int8")

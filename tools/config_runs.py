@@ -45,9 +45,10 @@ def _threads():
         return os.cpu_count() or 1
 
 
-def run_linear(dev, reps=2, check=8, n=4096, columns=8192, gemm="dmma"):
+def run_linear(dev, reps=2, check=8, n=4096, columns=8192, gemm="auto"):
     """Config 2.  gemm = "dmma": every product is dsb_dgemm (FP64 DMMA); "int8": the digit-plane product on the INT8
-    tensor cores (dsb_ozaki_*), the tail of compacted columns still on dsb_dgemm."""
+    tensor cores (dsb_ozaki_*); "auto" (the plugin's default): INT8 for the full-width products, dsb_dgemm for the
+    compacted tail."""
     import torch
     import desolver_b200 as de
     from desolver_b200.integrators import tableaux as tb
@@ -80,7 +81,7 @@ def _run_linear(torch, de, tb, orc, dev, reps, check, n, columns, gemm):
                gemm_launches_library=int(lin.calls_library - calls0[1]), gemm_launches_int8=int(lin.calls_int8 - calls0[2]),
                tflops_algorithmic=flops_alg / ms / 1e9, bound="tensor (FP64 DMMA)", peak_tflops=DMMA_PEAK_TFLOPS,
                frac=flops_alg / ms / 1e9 / DMMA_PEAK_TFLOPS)
-    if gemm == "int8":
+    if lin.calls_int8 - calls0[2] > 0:
         # 36 INT8 plane products per FP64 product; 4.5 POP/s is the dense INT8 tensor peak of the part (not measured here)
         out.update(bound="tensor (INT8 tcgen05, 36 plane products per FP64 product)", peak_tflops=None, frac=None,
                    int8_tops=36 * flops_alg / ms / 1e9, fp64_equivalent_tflops=flops_alg / ms / 1e9)
