@@ -140,28 +140,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what)
-{
-    const long long t0 = clock64();
-    while (!mbar_try_cluster(bar, parity)) {
-        if (clock64() - t0 > WAIT_LIMIT) {
-            printf("ozaki_gemm: cluster barrier wait %d timed out (block %d thread %d)\n", what, (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
 // TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the barrier `bar_cluster`
 // (a shared::cluster address: the leader's barrier)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster)
