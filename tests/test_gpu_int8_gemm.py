@@ -82,6 +82,26 @@ def test_planes_and_accumulators_are_exact(shape):
     assert float(((C - ref).abs() / (A.abs() @ B.abs())).max()) <= 8 * EPS
 
 
+@pytest.mark.parametrize("shape", [(128, 64, 128), (256, 128, 512), (384, 192, 256)])
+def test_kernel_equals_the_numpy_model_bit_for_bit(shape):
+    """oracle/ozaki_model.py restates the scheme in numpy (rint digits, exact int64 plane products, Horner in float64): digit
+    planes, scales, accumulators and the final doubles of the kernel are the model's, bit for bit -- on single CTAs
+    (M = 128, 384) and on CTA pairs (M = 256)."""
+    from oracle import ozaki_model as om
+    cb = _cb()
+    M, N, K = shape
+    A, B = _operands(M, N, K, seed=5 * M + N, spread=2.0)
+    prod = cb.Int8Product(A)
+    dbg = torch.zeros(prod.S, M, N, dtype=torch.int32, device="cuda")
+    C = prod(B, dbg_acc=dbg)
+    Cm, parts = om.product(A.cpu().numpy(), B.cpu().numpy())
+    assert np.array_equal(prod.a_planes.cpu().numpy(), parts["a_planes"]) and np.array_equal(prod.a_scale.cpu().numpy(), parts["a_scale"])
+    assert np.array_equal(prod.b_planes.view(prod.S, N, K).cpu().numpy(), parts["b_planes"])
+    assert np.array_equal(prod.b_scale.cpu().numpy(), parts["b_scale"])
+    assert np.array_equal(dbg.cpu().numpy().astype(np.int64), parts["acc"])
+    assert np.array_equal(C.cpu().numpy(), Cm)
+
+
 def test_closer_to_the_exact_product_than_an_fp64_gemm():
     """K = 4096 (the benchmark's contraction length): the error against the exactly rounded product stays below half an
     ulp of sum |a b| -- the left-to-right FP64 GEMM is allowed K times that."""
