@@ -32,7 +32,10 @@ namespace ft {
 constexpr int M_BITS = 5;                      // 32 intervals per octave
 constexpr int DEG = 7;
 constexpr int E_LO = -100, E_HI = 28;          // the table covers 2^E_LO <= x < 2^E_HI
-constexpr int HOT_LO = -8, HOT_HI = 2;         // octaves kept in shared memory
+#ifndef DSB_FT_HOT_LO
+#define DSB_FT_HOT_LO -8
+#endif
+constexpr int HOT_LO = DSB_FT_HOT_LO, HOT_HI = 2;   // octaves kept in shared memory
 constexpr int ENTRIES = (E_HI - E_LO) << M_BITS;
 constexpr int HOT_ENTRIES = (HOT_HI - HOT_LO) << M_BITS;
 constexpr int HOT_OFFSET = (HOT_LO - E_LO) << M_BITS;
