@@ -601,7 +601,7 @@ ozaki_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int it = 0; tile_at(it, m0, n0); ++it, ++n_tile) {
             mbar_wait(tmem_full, n_tile & 1, 400);
             tc_fence_after();
-            epilogue_tile(tmem_base, q, m0 + q * 32 + lane, n0, scale_a, scale_b, C, M, N, dbg_acc);
+            epilogue_tile(tmem_base, q, m0 + q * 32 + lane, n0, scale_a, scale_b, C, M, N, (mode & 4) ? nullptr : dbg_acc);
             tc_fence_before();
             mbar_arrive_cluster(lempty);
         }
@@ -754,6 +754,23 @@ static EncodeTiledFn encode_tiled()
     }
     return fn;
 }
+// Tuning / diagnosis knobs, read once: DSB_OZAKI_MODE (bit 0: no loads, bit 1: no MMAs, bit 2: wait-cycle statistics into
+// dbg_acc -- tools/ozaki_check.py, tools/ozaki_stalls.py), DSB_OZAKI_BAND (row blocks per band), DSB_OZAKI_NO_PAIR.
+struct Knobs {
+    int mode = 0, band = 0;
+    bool no_pair = false;
+    Knobs()
+    {
+        if (const char *e = getenv("DSB_OZAKI_MODE")) mode = atoi(e);
+        if (const char *e = getenv("DSB_OZAKI_BAND")) band = atoi(e);
+        no_pair = getenv("DSB_OZAKI_NO_PAIR") != nullptr;
+    }
+};
+static const Knobs &knobs()
+{
+    static const Knobs k;
+    return k;
+}
 // planes[S * rows][K] int8, box of `box_rows` rows x 64 bytes, 64-byte swizzle
 static int make_map(CUtensorMap *map, const void *planes, long long rows, long long K, int box_rows)
 {
@@ -761,14 +778,11 @@ static int make_map(CUtensorMap *map, const void *planes, long long rows, long l
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DSB_ERR_CUDA; }
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)K};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_64B;
-    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    if (getenv("DSB_OZAKI_BOX128")) { box[0] = 128; box[1] = box_rows / 2; sw = CU_TENSOR_MAP_SWIZZLE_128B; }   // timing experiment only
-    if (getenv("DSB_OZAKI_PROMO")) promo = (CUtensorMapL2promotion)atoi(getenv("DSB_OZAKI_PROMO"));
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(planes), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DSB_ERR_CUDA; }
     return DSB_OK;
 }
@@ -826,9 +840,9 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
     if (rc != DSB_OK) return rc;
     rc = make_map(&map_b, b_planes, (long long)S * N, K, BN);
     if (rc != DSB_OK) return rc;
-    const int mode = getenv("DSB_OZAKI_MODE") ? atoi(getenv("DSB_OZAKI_MODE")) : 0;       // timing experiments (tools/ozaki_check.py)
-    const int band = getenv("DSB_OZAKI_BAND") ? atoi(getenv("DSB_OZAKI_BAND")) : 16;
-    const bool pair = (M % (2 * BM) == 0) && sms >= 2 && getenv("DSB_OZAKI_NO_PAIR") == nullptr;
+    const int mode = knobs().mode;
+    const int band = knobs().band > 0 ? knobs().band : 16;                    // single CTAs: bands of 16 x 128 rows
+    const bool pair = (M % (2 * BM) == 0) && sms >= 2 && !knobs().no_pair;
     if (pair) {
         CUtensorMap map_bh;
         rc = make_map(&map_bh, b_planes, (long long)S * N, K, BN / 2);
@@ -847,7 +861,7 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const int pband = getenv("DSB_OZAKI_BAND") ? band : 4;                 // in 256-row blocks
+        const int pband = knobs().band > 0 ? knobs().band : 4;                 // pairs: bands of 4 x 256 rows
         DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_pair_kernel, map_a, map_bh, a_scale, b_scale, C, (int)M, (int)N, (int)K,
                                           dbg_acc, mode, pband));
         return DSB_OK;

@@ -9,6 +9,7 @@ import sys
 import torch
 
 os.environ["DSB_OZAKI_MODE"] = "4"
+os.environ["DSB_OZAKI_NO_PAIR"] = "1"          # the statistics are implemented in the single-CTA kernel
 lib = C.CDLL(os.path.abspath(sys.argv[1]))
 M, N, K = 4096, 8192, 4096
 vp, ll = C.c_void_p, C.c_longlong
