@@ -55,6 +55,9 @@ namespace oz {
 #ifndef DSB_OZAKI_COLLECTOR
 #define DSB_OZAKI_COLLECTOR 1
 #endif
+#ifndef DSB_OZAKI_COLL_MIN_P
+#define DSB_OZAKI_COLL_MIN_P 1   // steps with fewer than this many + 1 products do not use the collector
+#endif
 #ifndef DSB_OZAKI_SLICES
 #define DSB_OZAKI_SLICES 8
 #endif
@@ -574,7 +577,7 @@ ozaki_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                                     const uint64_t ad = desc(lo_a + p * (A_TILE / 16) + kk * (UMMA_K / 16));
                                     const uint64_t bd = desc(lo_b + j * (B_HALF / 16) + kk * (UMMA_K / 16));
                                     const uint32_t accumulate = (j > 0 || kk > 0) ? 1u : (uint32_t)(kb > 0);
-                                    if (!DSB_OZAKI_COLLECTOR || p == 0) mma_i8_pair<0>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
+                                    if (!DSB_OZAKI_COLLECTOR || p < DSB_OZAKI_COLL_MIN_P) mma_i8_pair<0>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
                                     else if (j == 0) mma_i8_pair<1>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
                                     else if (j == p) mma_i8_pair<3>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
                                     else mma_i8_pair<2>(d_tmem, ad, bd, IDESC_PAIR, accumulate);
