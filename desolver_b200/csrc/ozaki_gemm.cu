@@ -845,15 +845,13 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
     if (rc != DSB_OK) return rc;
     const int mode = knobs().mode;
     const int band = knobs().band > 0 ? knobs().band : 16;                    // single CTAs: bands of 16 x 128 rows
-    const bool pair = (M % (2 * BM) == 0) && sms >= 2 && !knobs().no_pair;
-    if (pair) {
-        CUtensorMap map_bh;
-        rc = make_map(&map_bh, b_planes, (long long)S * N, K, BN / 2);
-        if (rc != DSB_OK) return rc;
+    if ((M % (2 * BM) == 0) && sms >= 2 && !knobs().no_pair) {
+        // CTA pairs, as many as the device can hold at once (a pair needs both SMs of a TPC: on a part with odd TPCs fewer
+        // than sms / 2 fit, and a persistent grid larger than that would run in two waves); with too few pairs, or if the
+        // cluster launch is refused, the single-CTA kernel below takes over
         DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        const long long items = (M / (2 * BM)) * (N / BN);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(2 * (items < sms / 2 ? items : sms / 2)));
+        cfg.gridDim = dim3(2);
         cfg.blockDim = dim3(THREADS);
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = (cudaStream_t)stream;
@@ -864,10 +862,24 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const int pband = knobs().band > 0 ? knobs().band : 4;                 // pairs: bands of 4 x 256 rows
-        DSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_pair_kernel, map_a, map_bh, a_scale, b_scale, C, (int)M, (int)N, (int)K,
-                                          dbg_acc, mode, pband));
-        return DSB_OK;
+        int resident = 0;
+        if (cudaOccupancyMaxActiveClusters(&resident, ozaki_gemm_pair_kernel, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            resident = 0;
+        }
+        const int want = sms / 2 < resident ? sms / 2 : resident;
+        if (want * 10 >= (sms / 2) * 8) {
+            CUtensorMap map_bh;
+            rc = make_map(&map_bh, b_planes, (long long)S * N, K, BN / 2);
+            if (rc != DSB_OK) return rc;
+            const long long items = (M / (2 * BM)) * (N / BN);
+            cfg.gridDim = dim3((unsigned)(2 * (items < want ? items : want)));
+            const int pband = knobs().band > 0 ? knobs().band : 4;             // pairs: bands of 4 x 256 rows
+            if (cudaLaunchKernelEx(&cfg, ozaki_gemm_pair_kernel, map_a, map_bh, a_scale, b_scale, C, (int)M, (int)N, (int)K, dbg_acc,
+                                   mode, pband) == cudaSuccess)
+                return DSB_OK;
+            cudaGetLastError();
+        }
     }
     DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const long long tiles = (M / BM) * (N / BN);
