@@ -6,6 +6,7 @@ device memory (`tensor.data_ptr()`), streams (`torch.cuda.current_stream().cuda_
 `torch.distributed`; all arithmetic of the hot path happens in the library's kernels.
 """
 import ctypes as C
+import weakref
 import os
 import subprocess
 
@@ -334,7 +335,7 @@ class Int8Product:
         import torch
         if not (A.is_cuda and A.dtype == torch.float64 and A.ndim == 2 and A.is_contiguous()):
             raise ValueError("Int8Product needs a contiguous float64 CUDA matrix")
-        self.A = A
+        self._A = weakref.ref(A)                 # the planes must not keep the matrix alive (rhs_plugins.linear caches us)
         self.M, self.K = A.shape
         self.S = lib().dsb_ozaki_slices()
         self.sms = torch.cuda.get_device_properties(A.device).multi_processor_count
@@ -344,23 +345,29 @@ class Int8Product:
         self.b_planes = self.b_scale = self.workspace = None
         self.columns = 0
 
+    @property
+    def A(self):
+        return self._A()
+
     def shape_ok(self):
-        return self.M % 128 == 0 and self.K % 128 == 0 and self.K <= 32768 and self.A.data_ptr() % 16 == 0
+        A = self.A
+        return A is not None and self.M % 128 == 0 and self.K % 128 == 0 and self.K <= 32768 and A.data_ptr() % 16 == 0
 
     def supports(self, B):
         import torch
         return (self.shape_ok() and B.ndim == 2 and B.shape[0] == self.K and B.shape[1] % 64 == 0 and B.shape[1] > 0
-                and B.is_cuda and B.dtype == torch.float64 and B.is_contiguous() and B.device == self.A.device)
+                and B.is_cuda and B.dtype == torch.float64 and B.is_contiguous() and B.device == self.a_planes.device)
 
     def _prepare(self, n):
         import torch
-        stream = current_stream_ptr(self.A.device)
-        if self._a_version != self.A._version:
-            check(lib().dsb_ozaki_split_a(self.A.data_ptr(), self.M, self.K, self.a_planes.data_ptr(), self.a_scale.data_ptr(),
+        A = self.A
+        stream = current_stream_ptr(A.device)
+        if self._a_version != A._version:
+            check(lib().dsb_ozaki_split_a(A.data_ptr(), self.M, self.K, self.a_planes.data_ptr(), self.a_scale.data_ptr(),
                                           stream), "dsb_ozaki_split_a")
-            self._a_version = self.A._version
+            self._a_version = A._version
         if n > self.columns:
-            dev = self.A.device
+            dev = A.device
             self.b_planes = torch.empty((self.S * n * self.K,), dtype=torch.int8, device=dev)
             self.b_scale = torch.empty(n, dtype=torch.float64, device=dev)
             self.workspace = torch.empty(n, dtype=torch.int64, device=dev)

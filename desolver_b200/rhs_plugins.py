@@ -9,6 +9,8 @@ implementation in desolver_b200/csrc/ that `OdeSystem(..., ensemble=True)` dispa
 `DiffRHS` forwards unknown attribute reads to the wrapped callable (reference :438-439), so the
 tag survives wrapping.
 """
+import weakref
+
 
 # ids shared with include/desolver_b200.h (DSB_RHS_*) and oracle/desolver_oracle.h (ORC_RHS_*)
 RHS_LINEAR, RHS_LORENZ, RHS_VDP, RHS_NBODY, RHS_SHO, RHS_FORCED, RHS_DUFFING = 0, 1, 2, 3, 4, 5, 6
@@ -77,11 +79,14 @@ def linear(t, y, A=None, out=None):
     if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2
             and getattr(A, "is_cuda", False)):
         from .backend import cuda_backend as cb
-        if linear.gemm == "int8" or (linear.gemm == "auto" and min(A.shape) >= 1024 and y.shape[1] >= 512):
+        import torch
+        int8_ok = A.ndim == 2 and A.dtype == torch.float64 and A.is_contiguous() and y.dtype == torch.float64
+        if int8_ok and (linear.gemm == "int8" or (linear.gemm == "auto" and min(A.shape) >= 1024 and y.shape[1] >= 512)):
             prod = linear._int8.get(id(A))
             if prod is None or prod.A is not A:
                 linear._int8.clear()                        # one matrix at a time: the planes of A are as large as A
                 prod = linear._int8[id(A)] = cb.Int8Product(A)
+                weakref.finalize(A, linear._int8.pop, id(A), None)    # the planes go when the matrix goes
             if prod.supports(y):
                 res = prod(y, out=out if (out is not None and out.is_contiguous()) else None)
                 linear.calls_int8 += 1
