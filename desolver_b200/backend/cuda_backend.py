@@ -358,6 +358,10 @@ class Int8Product:
         return (self.shape_ok() and B.ndim == 2 and B.shape[0] == self.K and B.shape[1] % 64 == 0 and B.shape[1] > 0
                 and B.is_cuda and B.dtype == torch.float64 and B.is_contiguous() and B.device == self.a_planes.device)
 
+    def refresh(self):
+        """Cut the planes of A again if it was modified in place since the last split (torch's version counter)."""
+        self._prepare(0)
+
     def _prepare(self, n):
         import torch
         A = self.A

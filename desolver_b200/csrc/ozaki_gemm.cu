@@ -849,7 +849,6 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
         // CTA pairs, as many as the device can hold at once (a pair needs both SMs of a TPC: on a part with odd TPCs fewer
         // than sms / 2 fit, and a persistent grid larger than that would run in two waves); with too few pairs, or if the
         // cluster launch is refused, the single-CTA kernel below takes over
-        DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2);
         cfg.blockDim = dim3(THREADS);
@@ -862,11 +861,25 @@ DSB_API int dsb_ozaki_gemm(const signed char *a_planes, const double *a_scale, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        int resident = 0;
-        if (cudaOccupancyMaxActiveClusters(&resident, ozaki_gemm_pair_kernel, &cfg) != cudaSuccess) {
-            cudaGetLastError();
-            resident = 0;
+        // per device, once: the shared-memory opt-in and how many pairs fit (both are host-side driver queries that must not
+        // sit in front of every product)
+        static int resident_of[64];
+        static bool known[64];
+        int device = 0;
+        DSB_CUDA_CHECK(cudaGetDevice(&device));
+        const int slot = device & 63;
+        if (!known[slot]) {
+            DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            DSB_CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            int r = 0;
+            if (cudaOccupancyMaxActiveClusters(&r, ozaki_gemm_pair_kernel, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                r = 0;
+            }
+            resident_of[slot] = r;
+            known[slot] = true;
         }
+        const int resident = resident_of[slot];
         const int want = sms / 2 < resident ? sms / 2 : resident;
         if (want * 10 >= (sms / 2) * 8) {
             CUtensorMap map_bh;

@@ -162,6 +162,38 @@ class DenseOutput(object):
         return self._eval(times, derivative, grid=True)
 
 
+def _capture_graph(device, body):
+    """Record `body()` (kernel launches on the current stream) into a torch.cuda.CUDAGraph and return it.
+
+    The steps of `torch.cuda.graph(g)` without its `torch.cuda.empty_cache()`: that call returns every cached block to the
+    driver in front of EACH capture, and with the multi-gigabyte temporaries of a compacted working set in the cache it
+    stalled one integrate() in four for 0.1-0.9 s (cudaFree, then cudaMalloc again); a capture on a side stream needs
+    neither an empty cache nor a collected heap."""
+    torch = _torch()
+    g = torch.cuda.CUDAGraph()
+    side = _capture_streams.get(device)
+    if side is None:
+        side = _capture_streams[device] = torch.cuda.Stream(device)
+    current = torch.cuda.current_stream(device)
+    side.wait_stream(current)
+    with torch.cuda.stream(side):
+        g.capture_begin()
+        try:
+            body()
+        except BaseException:
+            try:
+                g.capture_end()
+            except Exception:
+                pass
+            raise
+        g.capture_end()
+    current.wait_stream(side)
+    return g
+
+
+_capture_streams = {}
+
+
 def _state_property(name):
     """Per-trajectory state tensor that is filled on first use: `reset()` only marks the state as pristine, and a
     fused run from a pristine state lets the kernel initialise everything itself (dsb_erk_run_args.fresh), so
@@ -1156,6 +1188,11 @@ class OdeSystem(object):
         if not isinstance(integ, integrators.RungeKuttaIntegrator):
             raise NotImplementedError("stage-level path supports explicit Runge-Kutta methods")
         n, D, S, dev = self.n_traj, self.numel, integ.stages, self.device
+        # a right-hand side may keep derived device data (rhs_plugins.linear: the INT8 digit planes of A); it refreshes them
+        # here, eagerly, because the attempts below are replayed as CUDA graphs that only see buffers, not Python
+        prepare = getattr(self.equ_rhs, "prepare", None)
+        if prepare is not None:
+            prepare(**self.__consts)
         handle = cb.erk_handle(dev.index or 0, 100, D, integ.tableau_intermediate, integ.tableau_final, integ.order,
                                strict=self.strict)
         chunks = max(1, min(4096, (D + 127) // 128))
@@ -1295,10 +1332,8 @@ class OdeSystem(object):
             if not self.use_graphs or callbacks or search is not None:     # callbacks may rebind the system's tensors
                 return None                                                # (e.g. ode_sys.dt = ...); the event search looks at the device
             try:
-                g = torch.cuda.CUDAGraph()
                 nfev0, rows0 = self.equ_rhs.nfev, self._rows_used
-                with torch.cuda.graph(g):
-                    one_attempt(False)
+                g = _capture_graph(dev, lambda: one_attempt(False))
                 self.equ_rhs.nfev = nfev0            # the capture pass recorded the calls, it did not execute them
                 self._rows_used = rows0
                 return g
@@ -1402,6 +1437,9 @@ class OdeSystem(object):
         n, D, dev = self.n_traj, self.numel, self.device
         stream = cb.current_stream_ptr(dev)
         rhs = self.equ_rhs
+        prepare = getattr(rhs, "prepare", None)           # derived device data of the right-hand side (see _run_stagewise)
+        if prepare is not None:
+            prepare(**self.__consts)
         # drift (position) variables = rows [0, dim0 // 2) of axis 0, kick = the rest (reference integrator_types.py:359-362)
         drift_count = (self.dim[0] // 2) * (D // self.dim[0]) if len(self.dim) else 0
         fused = (self.use_fused and getattr(rhs, "device_plugin", None) == "nbody" and len(self.dim) == 3
@@ -1527,10 +1565,8 @@ class OdeSystem(object):
             if not self.use_graphs or callbacks or search is not None:     # same CUDA-graph replay as the explicit-RK stage path
                 return None
             try:
-                g = torch.cuda.CUDAGraph()
                 nfev0, rows0 = self.equ_rhs.nfev, self._rows_used
-                with torch.cuda.graph(g):
-                    one_step(False)
+                g = _capture_graph(dev, lambda: one_step(False))
                 self.equ_rhs.nfev, self._rows_used = nfev0, rows0
                 return g
             except Exception:

@@ -79,14 +79,8 @@ def linear(t, y, A=None, out=None):
     if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2
             and getattr(A, "is_cuda", False)):
         from .backend import cuda_backend as cb
-        import torch
-        int8_ok = A.ndim == 2 and A.dtype == torch.float64 and A.is_contiguous() and y.dtype == torch.float64
-        if int8_ok and (linear.gemm == "int8" or (linear.gemm == "auto" and min(A.shape) >= 1024 and y.shape[1] >= 512)):
-            prod = linear._int8.get(id(A))
-            if prod is None or prod.A is not A:
-                linear._int8.clear()                        # one matrix at a time: the planes of A are as large as A
-                prod = linear._int8[id(A)] = cb.Int8Product(A)
-                weakref.finalize(A, linear._int8.pop, id(A), None)    # the planes go when the matrix goes
+        if y.dtype == A.dtype and _linear_wants_int8(A, y.shape[1]):
+            prod = _linear_int8_product(A)
             if prod.supports(y):
                 res = prod(y, out=out if (out is not None and out.is_contiguous()) else None)
                 linear.calls_int8 += 1
@@ -102,6 +96,33 @@ def linear(t, y, A=None, out=None):
     return A @ y
 
 
+def _linear_wants_int8(A, columns):
+    import torch
+    if not (getattr(A, "is_cuda", False) and A.ndim == 2 and A.dtype == torch.float64 and A.is_contiguous()):
+        return False
+    return linear.gemm == "int8" or (linear.gemm == "auto" and min(A.shape) >= 1024 and columns >= 512)
+
+
+def _linear_int8_product(A):
+    from .backend import cuda_backend as cb
+    prod = linear._int8.get(id(A))
+    if prod is None or prod.A is not A:
+        linear._int8.clear()                                # one matrix at a time: the planes of A are as large as A
+        prod = linear._int8[id(A)] = cb.Int8Product(A)
+        weakref.finalize(A, linear._int8.pop, id(A), None)  # the planes go when the matrix goes
+    return prod
+
+
+def _linear_prepare(A=None, **unused):
+    """Called by OdeSystem at the start of every stage-level integrate(): the digit planes of an A that was modified in
+    place are cut again BEFORE captured attempts are replayed (a CUDA graph replays kernels, not this Python)."""
+    if not linear.use_library_gemm and linear.gemm in ("auto", "int8") and _linear_wants_int8(A, 1 << 30):
+        prod = _linear_int8_product(A)
+        if prod.shape_ok():
+            prod.refresh()
+
+
+linear.prepare = _linear_prepare
 linear.use_library_gemm = False
 linear.gemm = "auto"              # "auto" | "dmma" | "int8": which tensor-core kernel serves the product (see the docstring)
 linear._int8 = {}

@@ -159,6 +159,39 @@ def test_planes_follow_in_place_updates_of_the_matrix():
     assert float(((C2 - 3.0 * C1).abs() / (A.abs() @ B.abs())).max()) <= 4 * EPS
 
 
+def test_matrix_modified_between_integrations_is_seen_by_replayed_graphs():
+    """The stage-level path replays its attempts as CUDA graphs; the digit planes of A are cut inside the capture, so an
+    in-place update of A between two integrate() calls reaches the replays (as it does with the FP64 kernels)."""
+    import desolver_b200 as de
+    lin = de.rhs_plugins.linear
+    A, Y0 = de.benchmarks.linear_system(256, 256)
+    Ad = torch.as_tensor(A).cuda()
+
+    def run(a=None):
+        if a is None:
+            a = de.OdeSystem(lin, torch.as_tensor(Y0).cuda(), t=(0.0, 1.0), dt=1e-2, rtol=1e-9, atol=1e-9, constants=dict(A=Ad),
+                             ensemble=True)
+            a.method = "RK87"
+        else:
+            a.reset()
+        a.integrate()
+        return a
+    lin.gemm = "int8"
+    try:
+        a = run()
+        run(a)                                           # replays
+        y1 = a[-1].y.clone()
+        Ad.mul_(0.5)                                     # y' = (A / 2) y: y(1) of the new system = y(1/2) of the old one
+        run(a)
+        y2 = a[-1].y.clone()
+        fresh = run()
+    finally:
+        lin.gemm = "auto"
+        Ad.mul_(2.0)
+    assert float((y2 - y1).abs().max()) > 1e-3           # the update was seen
+    assert float((y2 - fresh[-1].y).abs().max()) <= 1e-10 * float(y2.abs().max())
+
+
 def test_shapes_outside_the_tiling_are_refused():
     cb = _cb()
     A, B = _operands(128, 96, 128)
