@@ -308,12 +308,13 @@ def check(status, what=""):
 
 
 def dgemm(A, B, out=None):
-    """C = A @ B for contiguous float64 CUDA matrices through the library's FP64 tensor-core kernel (dsb_dgemm).
-    Returns None when the shape is outside the kernel's tiling (the caller then uses a library GEMM)."""
+    """C = A @ B for contiguous float64 CUDA matrices through the library's FP64 tensor-core kernel (dsb_dgemm): any M,
+    even N and K (shapes that are not multiples of its 64 x 128 x 16 tile run the predicated edge instantiation).
+    Returns None otherwise (the caller then uses a library GEMM)."""
     import torch
     M, K = A.shape
     K2, N = B.shape
-    if (K != K2 or M % 64 or N % 128 or K % 16 or A.dtype != torch.float64 or B.dtype != torch.float64
+    if (K != K2 or N % 2 or K % 2 or min(M, N, K) < 1 or A.dtype != torch.float64 or B.dtype != torch.float64
             or not (A.is_cuda and B.is_cuda and A.is_contiguous() and B.is_contiguous())
             or A.data_ptr() % 16 or B.data_ptr() % 16):
         return None

@@ -18,8 +18,9 @@
 //     warp (A[g][t], B[t][g], g = lane/4, t = lane%4) hit every bank group exactly once per wavefront;
 //   * warp tile 32 x 64: 4 + 8 fragment loads feed 32 DMMAs per k-step of 4; 64 accumulator doubles per lane
 //     (246 registers, which is what limits the SM to two CTAs).
-// Requires M % 64 == 0, N % 128 == 0, K % 16 == 0 and 16-byte aligned pointers (the benchmark configuration
-// 4096 x 4096 x 8192 and every power-of-two problem); the host side uses the library GEMM for other shapes.
+// Shapes with M % 64 == 0, N % 128 == 0, K % 16 == 0 (the benchmark configuration 4096 x 4096 x 8192 and every
+// power-of-two problem) run the unpredicated instantiation; any other shape with even N and K runs the EDGE instantiation
+// (zero-filled cp.async for chunks outside the matrices, guarded stores).  Odd N or K: DSB_ERR_UNSUPPORTED (library GEMM).
 // Results are bit-identical to cuBLAS DGEMM on the shapes tested (same k order per accumulator).
 #include "common.cuh"
 
@@ -62,6 +63,12 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
 }
+// the same with `bytes` (0 or 16) taken from global memory and the rest of the 16 bytes zero-filled: edge tiles
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, unsigned bytes)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
@@ -74,6 +81,10 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 }
 }  // namespace gemm
 
+// EDGE: M, N, K need not be multiples of the tile (N and K even, so that every 16-byte chunk is inside or outside as a
+// whole): chunks outside the matrices are zero-filled by cp.async, stores outside C are skipped.  A separate
+// instantiation, so that the aligned shapes of the benchmark keep their unpredicated loads.
+template <bool EDGE>
 __global__ void __launch_bounds__(gemm::THREADS, gemm::CTAS)
 dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C, int M, int N, int K)
 {
@@ -83,7 +94,8 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;                // WM x 2 warps -> warp tile 32 x 64
     const int g = lane >> 2, t = lane & 3;
-    const int mb = M / BM, nb = N / BN, kt = K / BK;
+    const int mb = EDGE ? (M + BM - 1) / BM : M / BM, nb = EDGE ? (N + BN - 1) / BN : N / BN;
+    const int kt = EDGE ? (K + BK - 1) / BK : K / BK;
 
     // tile index -> (row block, column block)
     auto tile_mn = [&](int tile, int &tm, int &tn) {
@@ -98,23 +110,36 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
         }
     };
     const double *Ag = nullptr, *Bg = nullptr;
+    int m_load = 0, n_load = 0;                                          // first row / column of the tile being loaded
     auto load_stage = [&](int stage, int k0) {
         double *a = sA + stage * A_STAGE, *b = sB + stage * B_STAGE;
 #pragma unroll
         for (int i = 0; i < (BM * BK / 2) / THREADS; ++i) {              // A tile: 128 rows x BK/2 chunks of 2 doubles
             const int c = tid + i * THREADS, row = c / (BK / 2), col = (c % (BK / 2)) * 2;
-            cp_async16(a + row * LDA + col, Ag + (size_t)row * K + k0 + col);
+            if (EDGE) {
+                const bool in = m_load + row < M && k0 + col < K;
+                cp_async16_zfill(a + row * LDA + col, in ? Ag + (size_t)row * K + k0 + col : A, in ? 16u : 0u);
+            } else {
+                cp_async16(a + row * LDA + col, Ag + (size_t)row * K + k0 + col);
+            }
         }
 #pragma unroll
         for (int i = 0; i < (BK * BN / 2) / THREADS; ++i) {              // B tile: BK rows x 64 chunks
             const int c = tid + i * THREADS, row = c >> 6, col = (c & 63) * 2;
-            cp_async16(b + row * LDB + col, Bg + (size_t)(k0 + row) * N + col);
+            if (EDGE) {
+                const bool in = k0 + row < K && n_load + col < N;
+                cp_async16_zfill(b + row * LDB + col, in ? Bg + (size_t)(k0 + row) * N + col : B, in ? 16u : 0u);
+            } else {
+                cp_async16(b + row * LDB + col, Bg + (size_t)(k0 + row) * N + col);
+            }
         }
     };
     // prologue of a tile: the first STAGES-1 k-steps in flight
     auto prologue = [&](int tile) {
         int tm, tn;
         tile_mn(tile, tm, tn);
+        m_load = tm * BM;
+        n_load = tn * BN;
         Ag = A + (size_t)(tm * BM) * K;
         Bg = B + tn * BN;
 #pragma unroll
@@ -185,32 +210,41 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
         if (tile + (int)gridDim.x < mb * nb) prologue(tile + gridDim.x);
 
         // epilogue: lane (g, t) owns C[8 i + g][8 j + 2 t .. + 1] of each 8 x 8 tile: 16-byte stores
-        double *Cg = C + (size_t)(m0 + wm * 32 + g) * N + n0 + wn * WTN + 2 * t;
+        const int r0 = m0 + wm * 32 + g, c0 = n0 + wn * WTN + 2 * t;
+        double *Cg = C + (size_t)r0 * N + c0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j)
-                *reinterpret_cast<double2 *>(Cg + (size_t)i * 8 * N + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+                if (!EDGE || (r0 + i * 8 < M && c0 + j * 8 < N))
+                    *reinterpret_cast<double2 *>(Cg + (size_t)i * 8 * N + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
 }
 
 int launch_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, int sm_count, cudaStream_t stream)
 {
     using namespace gemm;
-    if (M <= 0 || N <= 0 || K <= 0 || M % BM || N % BN || K % BK || M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff ||
+    if (M <= 0 || N <= 0 || K <= 0 || N % 2 || K % 2 || M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff ||
         ((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) % 16) {
-        set_error("dsb_dgemm: needs M %% %d == 0, N %% %d == 0, K %% %d == 0 and 16-byte aligned pointers (got %lld x %lld x %lld)",
-                  BM, BN, BK, (long long)M, (long long)N, (long long)K);
+        set_error("dsb_dgemm: needs even N and K (16-byte rows) and 16-byte aligned pointers (got %lld x %lld x %lld)",
+                  (long long)M, (long long)N, (long long)K);
         return DSB_ERR_UNSUPPORTED;
     }
-    static bool configured = false;
-    if (!configured) {
-        DSB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
+    const bool edge = M % BM || N % BN || K % BK;
+    static bool configured[64];
+    int device = 0;
+    DSB_CUDA_CHECK(cudaGetDevice(&device));
+    if (!configured[device & 63]) {
+        DSB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        DSB_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured[device & 63] = true;
     }
-    const int64_t tiles = (M / BM) * (N / BN);
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = (int)(tiles < (int64_t)sm_count * CTAS ? tiles : (int64_t)sm_count * CTAS);
-    dgemm_dmma_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, C, (int)M, (int)N, (int)K);
+    if (edge)
+        dgemm_dmma_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, C, (int)M, (int)N, (int)K);
+    else
+        dgemm_dmma_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(A, B, C, (int)M, (int)N, (int)K);
     DSB_CUDA_CHECK(cudaGetLastError());
     return DSB_OK;
 }

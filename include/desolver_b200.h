@@ -403,8 +403,9 @@ DSB_API int dsb_event_search_roots(const dsb_event_search *s, double *roots, voi
  * K = A @ Y for the linear benchmark system y' = A y over an ensemble stored as Y[n][columns]
  * (rhs_plugins.linear; the reference evaluates the user's `A @ y` inside compute_step,
  * integrators/components/runge_kutta_methods.py:49-54): C[M][N] = A[M][K] * B[K][N], row-major fp64, as a
- * hand-written FP64 tensor-core kernel (mma.sync.m8n8k4.f64, csrc/dgemm.cu).  Needs M % 64 == 0, N % 128 == 0,
- * K % 16 == 0 and 16-byte aligned pointers, else DSB_ERR_UNSUPPORTED (the caller then uses a library GEMM). */
+ * hand-written FP64 tensor-core kernel (mma.sync.m8n8k4.f64, csrc/dgemm.cu).  Any M; N and K even and 16-byte aligned
+ * pointers (rows are moved in 16-byte pieces), else DSB_ERR_UNSUPPORTED (the caller then uses a library GEMM).  Shapes
+ * with M % 64 == 0, N % 128 == 0, K % 16 == 0 run the unpredicated instantiation. */
 DSB_API int dsb_dgemm(const double *A, const double *B, double *C, int64_t M, int64_t N, int64_t K, void *stream);
 
 /* The same product on the INT8 tensor cores (tcgen05.mma kind::i8, TMA, TMEM; csrc/ozaki_gemm.cu): every row of A and

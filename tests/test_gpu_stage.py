@@ -340,9 +340,26 @@ def test_dgemm_kernel_matches_library_gemm():
     Ai = torch.randint(-8, 9, (128, 64), device="cuda").double()
     Bi = torch.randint(-8, 9, (64, 128), device="cuda").double()
     assert torch.equal(cb.dgemm(Ai, Bi).cpu(), (Ai.cpu().long() @ Bi.cpu().long()).double())
-    # shapes outside the tiling are declined (the caller then uses the library GEMM)
-    assert cb.dgemm(torch.zeros(100, 64, dtype=torch.float64, device="cuda"), torch.zeros(64, 128, dtype=torch.float64, device="cuda")) is None
-    assert cb.dgemm(torch.zeros(64, 64, dtype=torch.float64, device="cuda"), torch.zeros(64, 100, dtype=torch.float64, device="cuda")) is None
+    # shapes that are not multiples of the 64 x 128 x 16 tile run the edge instantiation (zero-filled loads, guarded stores):
+    # any M, even N and K -- ragged in every dimension, smaller than one tile, one row, K below one k-step
+    for M, N, K in ((100, 128, 64), (64, 100, 64), (65, 130, 18), (1, 2, 2), (333, 1002, 250), (1000, 516, 1000), (37, 8190, 4094)):
+        A = torch.randn(M, K, dtype=torch.float64, device="cuda")
+        B = torch.randn(K, N, dtype=torch.float64, device="cuda")
+        C = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+        out = cb.dgemm(A, B, out=C)
+        assert out is C and not bool(torch.isnan(C).any())
+        assert float(((C - A @ B).abs() / (A.abs() @ B.abs())).max()) <= 4e-16 * max(1.0, K ** 0.5)
+    # ... and write nothing outside C: a guard band around the result stays untouched
+    M, N, K = 70, 140, 34
+    A = torch.randn(M, K, dtype=torch.float64, device="cuda")
+    B = torch.randn(K, N, dtype=torch.float64, device="cuda")
+    big = torch.full((M + 2, N), 7.0, dtype=torch.float64, device="cuda")
+    cb.dgemm(A, B, out=big[1:M + 1])
+    assert bool((big[0] == 7.0).all()) and bool((big[M + 1] == 7.0).all())
+    assert float((big[1:M + 1] - A @ B).abs().max()) <= 1e-13
+    # odd N or K (rows that are not 16-byte aligned) are declined: the caller then uses the library GEMM
+    assert cb.dgemm(torch.zeros(64, 64, dtype=torch.float64, device="cuda"), torch.zeros(64, 101, dtype=torch.float64, device="cuda")) is None
+    assert cb.dgemm(torch.zeros(64, 15, dtype=torch.float64, device="cuda"), torch.zeros(15, 128, dtype=torch.float64, device="cuda")) is None
     assert cb.lib().dsb_dgemm(None, None, None, 64, 128, 16, None) == cb.DSB_ERR_BAD_ARGUMENT
 
 
