@@ -64,3 +64,18 @@ a.method = "ABAS5O6H"
 a.integrate()
 torch.cuda.synchronize()
 print("sanitize smoke done")
+# the GEMM kernels of the linear right-hand side: DMMA (aligned and edge instantiation) and the INT8 digit-plane product
+# (single CTAs for M = 128 / 384, CTA pairs for M = 256)
+from desolver_b200.backend import cuda_backend as cb  # noqa: E402
+for M, N, K in ((64, 128, 16), (70, 140, 34), (1, 2, 2), (130, 258, 50)):
+    Ag = torch.randn(M, K, dtype=torch.float64, device="cuda")
+    Bg = torch.randn(K, N, dtype=torch.float64, device="cuda")
+    Cg = cb.dgemm(Ag, Bg)
+    assert float((Cg - Ag @ Bg).abs().max()) < 1e-12
+for M, N, K in ((128, 64, 128), (256, 128, 256), (384, 192, 128)):
+    Ag = torch.randn(M, K, dtype=torch.float64, device="cuda")
+    Bg = torch.randn(K, N, dtype=torch.float64, device="cuda")
+    Cg = cb.Int8Product(Ag)(Bg)
+    assert float((Cg - Ag @ Bg).abs().max()) < 1e-12
+torch.cuda.synchronize()
+print("sanitize_smoke: GEMM kernels done")
