@@ -49,10 +49,11 @@ def static_config(n_local):
 
 def reference_numpy_numbers():
     """The reference's own numpy backend (CPU-A: one OdeSystem per trajectory; CPU-B: a whole shard as ONE state with a
-    global dt -- different semantics) cannot travel to the GPU box (pure-Python sources under /root/reference, its build
-    backend `hatchling` and its dependency `autoray` are absent from the offline wheelhouse), so its timing is taken in
-    the build container by tools/reference_numpy_timing.py and committed under profiles/.  If a reference tree IS
-    importable on this box (baseline/_ref or /root/reference), it is timed live instead."""
+    global dt -- different semantics), timed LIVE on this box's host cores from baseline/_ref -- the unmodified reference,
+    installed in the build container by baseline/install_reference.py (git-ignored, travels with the snapshot; `autoray`,
+    absent from the offline image, is the dispatch-only stand-in oracle/refshim).  CPU-A's per-trajectory results are kept
+    for `parity.reference_live`.  Without baseline/_ref the record taken in the build container
+    (profiles/round2_reference_numpy_timing.json) is quoted instead, and says so in `where`."""
     rec = None
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "round2_reference_numpy_timing.json")))
@@ -64,13 +65,38 @@ def reference_numpy_numbers():
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import reference_numpy_timing as rnt
-                live = rnt.measure(tree, seconds=6.0)
-                live["where"] = "this box, live (%s)" % tree
+                details = []
+                live = rnt.measure(tree, seconds=6.0, details=details)
+                live["where"] = "this box, live (%s: the unmodified reference, installed by baseline/install_reference.py)" % tree
+                reference_numpy_numbers.details = details
                 return live
             except Exception as e:                          # noqa: BLE001
                 if rec is not None:
                     rec["live_error"] = repr(e)[:200]
     return rec
+
+
+reference_numpy_numbers.details = None
+
+
+def reference_live_parity(y_gpu, acc_gpu, rej_gpu, n_gpus, rank):
+    """The GPU results against what the REFERENCE ITSELF (numpy backend, one OdeSystem per trajectory: CPU-A of
+    reference_numpy_numbers) computed on this box in this run, for the trajectories it got through."""
+    det = reference_numpy_numbers.details
+    if not det:
+        return None
+    mine = [d for d in det if d[0] % n_gpus == rank and d[0] // n_gpus < y_gpu.shape[1]]
+    if not mine:
+        return None
+    loc = np.array([d[0] // n_gpus for d in mine])
+    acc = np.array([d[1] for d in mine])
+    att = np.array([d[2] for d in mine])
+    y_ref = np.stack([d[3] for d in mine], axis=1)
+    err = np.max(np.abs(y_gpu[:, loc] - y_ref), axis=0) / np.max(np.abs(y_ref), axis=0)
+    same = (acc_gpu[loc] == acc) & (acc_gpu[loc] + rej_gpu[loc] == att)
+    return {"what": "GPU vs the unmodified reference's numpy backend run on this box (baseline/_ref), same trajectories",
+            "checked_trajectories": int(loc.shape[0]), "counts_identical_frac": float(same.mean()),
+            "max_rel_err": float(err.max()), "median_rel_err": float(np.median(err))}
 
 
 def measured_peak_gbs():
@@ -447,6 +473,9 @@ def main():
         parity = parity_gate(y_a[:, :k].cpu().numpy(), acc_a[:k].cpu().numpy(), rej_a[:k].cpu().numpy(), ref, gidx)
         parity["bitwise_deterministic"] = deterministic
         parity["of_ensemble"] = "%d of the %d trajectories on rank 0" % (k, n_local)
+        live = reference_live_parity(y_a.cpu().numpy(), acc_a.cpu().numpy(), rej_a.cpu().numpy(), n_gpus, rank)
+        if live is not None:
+            parity["reference_live"] = live
         line["parity"] = parity
         print(json.dumps(line))
     if world > 1:

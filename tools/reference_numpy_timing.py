@@ -23,6 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _paths(tree):
+    # worker processes only: the reference prints a banner on import; stdout belongs to the caller's JSON line
+    sys.stdout.flush()
+    os.dup2(2, 1)
     try:
         import autoray  # noqa: F401
         extra = []
@@ -47,6 +50,7 @@ def _cpu_a(job):
     cfg = bm.LORENZ
     y0 = bm.lorenz_ensemble(hi)[:, lo:hi]
     attempts, done, t0 = 0, 0, time.perf_counter()
+    detail = []                                 # (global index, accepted, attempts, final state): bench.py's live parity check
     for i in range(y0.shape[1]):
         a = de.OdeSystem(_lorenz, y0=y0[:, i].copy(), t=(cfg["t0"], cfg["tf"]), dt=cfg["dt0"], rtol=cfg["rtol"], atol=cfg["atol"],
                          constants=dict(sigma=cfg["sigma"], rho=cfg["rho"], beta=cfg["beta"]))
@@ -61,9 +65,10 @@ def _cpu_a(job):
         a.integrate()
         attempts += calls[0]
         done += 1
+        detail.append((lo + i, len(a) - 1, calls[0], np.asarray(a.y[-1], dtype=np.float64).copy()))
         if time.perf_counter() - t0 > budget:
             break
-    return attempts, done, time.perf_counter() - t0
+    return attempts, done, time.perf_counter() - t0, detail
 
 
 def _cpu_b(job):
@@ -89,7 +94,9 @@ def _cpu_b(job):
     return calls[0] * (hi - lo), hi - lo, time.perf_counter() - t0
 
 
-def measure(tree, seconds=20.0, procs=None):
+def measure(tree, seconds=20.0, procs=None, details=None):
+    """`details`: a list that receives CPU-A's per-trajectory results (global index, accepted steps, step attempts, final
+    state) -- what the REFERENCE ITSELF computes on this box, for a live parity check of the GPU run."""
     procs = procs or max(1, len(os.sched_getaffinity(0)))
     out = dict(tree=tree, cores=procs, workload="lorenz63_rk45ck, trajectories of the benchmark ensemble (prefix), t in [0,2], tol 1e-9",
                unit="trajectory-steps/s")
@@ -99,6 +106,9 @@ def measure(tree, seconds=20.0, procs=None):
         t0 = time.perf_counter()
         res = list(pool.map(_cpu_a, jobs))
         wall = time.perf_counter() - t0
+        if details is not None:
+            for r in res:
+                details.extend(r[3])
         out["cpu_a"] = dict(what="one reference OdeSystem per trajectory (same semantics as the engine)", value=sum(r[0] for r in res) / wall,
                             per_core=sum(r[0] for r in res) / wall / procs, trajectories=sum(r[1] for r in res), wall_s=wall)
         shard = 16384
