@@ -63,12 +63,20 @@ def reference_numpy_numbers():
     for tree in (os.path.join(ROOT, "baseline", "_ref"),):
         if os.path.isdir(os.path.join(tree, "desolver")):
             try:
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                import reference_numpy_timing as rnt
-                details = []
-                live = rnt.measure(tree, seconds=6.0, details=details)
+                # its own process: the measurement forks a pool of workers, which must not inherit this process's CUDA /
+                # NCCL state and threads
+                import subprocess
+                import tempfile
+                with tempfile.TemporaryDirectory() as tmp:
+                    npz = os.path.join(tmp, "cpu_a.npz")
+                    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reference_numpy_timing.py"), "--tree", tree,
+                                          "--seconds", "6", "--details-out", npz], check=True, timeout=240,
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+                    live = json.loads(out.stdout.decode())
+                    d = np.load(npz)
+                    reference_numpy_numbers.details = [(int(i), int(a), int(t), d["y"][:, j].copy()) for j, (i, a, t) in
+                                                       enumerate(zip(d["index"], d["accepted"], d["attempts"]))]
                 live["where"] = "this box, live (%s: the unmodified reference, installed by baseline/install_reference.py)" % tree
-                reference_numpy_numbers.details = details
                 return live
             except Exception as e:                          # noqa: BLE001
                 if rec is not None:
