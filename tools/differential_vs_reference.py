@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""Differential run: the UNMODIFIED reference (numpy backend, from baseline/_ref) and desolver_b200 (cuda:0) solve the same
+randomly drawn problems side by side on the GPU box; accepted-step counts, step times, final states, nfev, dense-output
+queries, events and solve_ivp(t_eval) are compared case by case.
+
+    python tools/differential_vs_reference.py [--seed 0] [--cases 200] > profiles/round2_differential_vs_reference.json
+
+TEST / MEASUREMENT INFRASTRUCTURE: needs baseline/_ref (baseline/install_reference.py) and a GPU.  `autoray`, which the
+offline image lacks, is the dispatch-only stand-in oracle/refshim."""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _import_reference():
+    try:
+        import autoray  # noqa: F401
+    except Exception:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        import desolver
+    return desolver
+
+
+# ---- problems: the same callable body serves numpy (reference) and torch (engine) through `xp.stack` ----
+def _rhs_factory(name, xp):
+    if name == "sho":
+        return lambda t, y, k, m: xp.stack([y[1], -k / m * y[0]])
+    if name == "lorenz":
+        return lambda t, y, sigma, rho, beta: xp.stack([sigma * (y[1] - y[0]), y[0] * (rho - y[2]) - y[1], y[0] * y[1] - beta * y[2]])
+    if name == "vdp":
+        return lambda t, y, mu: xp.stack([y[1], mu * (1.0 - y[0] * y[0]) * y[1] - y[0]])
+    if name == "forced":
+        return lambda t, y: xp.stack([y[1], t - y[0]])
+    raise KeyError(name)
+
+
+def _draw(rng, name):
+    if name == "sho":
+        return rng.uniform(-1, 1, 2), dict(k=float(rng.uniform(0.5, 4.0)), m=float(rng.uniform(0.5, 2.0))), (0.0, float(rng.uniform(2.0, 6.5)))
+    if name == "lorenz":
+        return rng.uniform([-15, -20, 5], [15, 20, 40]), dict(sigma=10.0, rho=28.0, beta=8.0 / 3.0), (0.0, float(rng.uniform(0.3, 1.5)))
+    if name == "vdp":
+        return rng.uniform(-2, 2, 2), dict(mu=float(10.0 ** rng.uniform(-1, 0.7))), (0.0, float(rng.uniform(1.0, 6.0)))
+    if name == "forced":
+        return rng.uniform(-1, 1, 2), dict(), (0.0, float(rng.uniform(1.0, 4.0)))
+    raise KeyError(name)
+
+
+ADAPTIVE = ["RK45", "RK87", "DOPRI45", "AHE", "RK108", "RK1412"]
+FIXED = ["RK4", "RK5", "Midpoint", "Heun's", "Ralston's", "Euler", "Euler-Trap"]
+SYMPLECTIC = ["BABS9O7H", "ABAS5O6H", "Symplectic Forward Euler"]
+PLUGIN = {"sho": "harmonic_oscillator", "lorenz": "lorenz", "vdp": "van_der_pol", "forced": "forced"}
+
+
+def run_case(ref, de, torch, rng, kind):
+    prob = str(rng.choice(["sho", "lorenz", "vdp", "forced"]))
+    y0, consts, span = _draw(rng, prob)
+    method = str(rng.choice(ADAPTIVE if kind != "fixed" else FIXED))
+    if kind == "symplectic":
+        prob, method = "sho", str(rng.choice(SYMPLECTIC))
+        y0, consts, span = _draw(rng, prob)
+    backward = kind == "backward"
+    if backward:
+        span = (span[1], span[0])
+    tol = float(10.0 ** rng.choice([-6, -8, -9, -11])) if method in ADAPTIVE else None
+    if method == "AHE":                                          # order 2: keep the step count bounded
+        tol = float(10.0 ** rng.choice([-4, -5, -6]))
+    dt0 = float(rng.choice([1e-3, 1e-2, 0.05, 0.5])) if method in ADAPTIVE else float(rng.choice([0.01, 0.02, 0.05]))
+    if backward:
+        dt0 = -min(abs(dt0), 1e-3)       # the reference's retry chain is broken for dt < 0: avoid rejections
+    path = str(rng.choice(["plugin", "callable"]))
+    dense = kind == "dense"
+    desc = dict(kind=kind, problem=prob, method=method, tol=tol, dt0=dt0, span=span, path=path)
+    kw = dict(t=span, dt=dt0, constants=consts, dense_output=dense)
+    if tol is not None:
+        kw.update(rtol=tol, atol=tol)
+    # --- reference ---
+    r = ref.OdeSystem(_rhs_factory(prob, np), y0=y0.copy(), **kw)
+    r.method = method
+    t0 = time.perf_counter()
+    try:
+        r.integrate()
+    except Exception as e:                                       # noqa: BLE001
+        if backward:                                             # fact 10: min(new, h0) with negative steps
+            return dict(desc, skipped="reference failed on a backward retry: " + repr(e)[:80], steps_equal=True, final_rel_err=0.0)
+        raise
+    desc["ref_s"] = time.perf_counter() - t0
+    # --- engine ---
+    rhs = getattr(de.rhs_plugins, PLUGIN[prob]) if path == "plugin" else _rhs_factory(prob, torch)
+    a = de.OdeSystem(rhs, torch.as_tensor(y0.copy()), device="cuda:0", strict=bool(rng.integers(0, 2)), **kw)
+    a.method = method
+    t0 = time.perf_counter()
+    a.integrate()
+    torch.cuda.synchronize()
+    desc["gpu_s"] = time.perf_counter() - t0
+    t_ref, y_ref = np.asarray(r.t, dtype=np.float64), np.asarray(r.y, dtype=np.float64)
+    t_gpu, y_gpu = a.t.cpu().numpy(), a.y.cpu().numpy()
+    out = dict(desc, steps_ref=len(r) - 1, steps_gpu=len(a) - 1, nfev_ref=int(r.nfev), nfev_gpu=int(a.nfev))
+    out["steps_equal"] = out["steps_ref"] == out["steps_gpu"]
+    scale = max(1.0, float(np.max(np.abs(y_ref))))
+    out["final_rel_err"] = float(np.max(np.abs(y_gpu[-1] - y_ref[-1])) / scale)
+    out["final_t_err"] = float(abs(t_gpu[-1] - t_ref[-1]))
+    if out["steps_equal"]:
+        out["max_t_err"] = float(np.max(np.abs(t_gpu - t_ref)))
+        out["max_y_rel_err"] = float(np.max(np.abs(y_gpu - y_ref)) / scale)
+    if dense:
+        q = np.sort(rng.uniform(min(span), max(span), 9))
+        s_ref = np.stack([np.asarray(r.sol(float(x))) for x in q])
+        s_gpu = np.stack([a.sol(float(x)).cpu().numpy().reshape(-1) for x in q])
+        out["dense_rel_err"] = float(np.max(np.abs(s_gpu - s_ref)) / scale)
+    return out
+
+
+def run_ensemble_case(ref, de, torch, rng):
+    """A small ensemble through the fused kernel against one reference OdeSystem per trajectory."""
+    prob = str(rng.choice(["lorenz", "vdp"]))
+    method = str(rng.choice(["RK45", "RK87", "DOPRI45"]))
+    n, tol = 24, float(10.0 ** rng.choice([-7, -9]))
+    draws = [_draw(rng, prob) for _ in range(n)]
+    span = draws[0][2]
+    y0 = np.stack([d[0] for d in draws], axis=1)
+    consts = dict(draws[0][1])
+    per = None
+    if prob == "vdp":
+        per = np.array([d[1]["mu"] for d in draws])
+        consts = dict(mu=torch.as_tensor(per, device="cuda:0"))
+    a = de.OdeSystem(getattr(de.rhs_plugins, PLUGIN[prob]), torch.as_tensor(y0), t=span, dt=1e-2, rtol=tol, atol=tol, constants=consts,
+                     ensemble=True, device="cuda:0")
+    a.method = method
+    a.integrate()
+    acc, rej, y = a.accepted.cpu().numpy(), a.rejected.cpu().numpy(), a[-1].y.cpu().numpy()
+    same, err = 0, 0.0
+    for i in range(n):
+        c = dict(draws[0][1]) if per is None else dict(mu=float(per[i]))
+        r = ref.OdeSystem(_rhs_factory(prob, np), y0=y0[:, i].copy(), t=span, dt=1e-2, rtol=tol, atol=tol, constants=c)
+        r.method = method
+        calls = [0]
+        inner = r.integrator.step
+
+        def counted(*p, _inner=inner, **k):
+            calls[0] += 1
+            return _inner(*p, **k)
+        r.integrator.step = counted
+        r.integrate()
+        same += int(len(r) - 1 == acc[i] and calls[0] == acc[i] + rej[i])
+        yr = np.asarray(r.y[-1], dtype=np.float64)
+        err = max(err, float(np.max(np.abs(y[:, i] - yr)) / max(1.0, np.max(np.abs(yr)))))
+    return dict(kind="ensemble", problem=prob, method=method, tol=tol, trajectories=n, counts_identical=same, final_rel_err=err,
+                steps_equal=same == n)
+
+
+def run_event_case(ref, de, torch, rng):
+    """A terminal and a recorded event on the Lorenz system: event times, states and where the integration stops."""
+    y0, consts, _ = _draw(rng, "lorenz")
+    level = float(rng.uniform(18.0, 30.0))
+    radius = float(rng.uniform(20.0, 35.0))
+    terminal = bool(rng.integers(0, 2))
+
+    def make(xp):
+        def plane(t, y, **k):
+            return y[2] - level
+
+        def sphere(t, y, **k):
+            return xp.sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]) - radius
+        sphere.is_terminal = terminal
+        plane.direction = 1
+        return [plane, sphere]
+    kw = dict(t=(0.0, 2.0), dt=1e-2, rtol=1e-9, atol=1e-9, constants=consts, dense_output=True)
+    r = ref.OdeSystem(_rhs_factory("lorenz", np), y0=y0.copy(), **kw)
+    r.method = "RK45"
+    r.integrate(events=make(np))
+    a = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(y0.copy()), device="cuda:0", **kw)
+    a.method = "RK45"
+    a.integrate(events=make(torch))
+    ev_r = sorted(float(e.t) for e in r.events)
+    ev_g = sorted(float(e.t) for e in a.events)
+    # the reference accepts a located root only if |g(root)| <= 4 eps ABSOLUTE (utilities/optimizer.py:194-197), so it
+    # reports a SUBSET of the crossings: every event it reports must be among the engine's
+    miss = [t for t in ev_r if not any(abs(t - u) <= 1e-9 for u in ev_g)]
+    out = dict(kind="events", terminal=terminal, events_ref=len(ev_r), events_gpu=len(ev_g), steps_ref=len(r) - 1, steps_gpu=len(a) - 1)
+    stopped_gpu = "terminated" in str(a.integration_status).lower() or float(a.t[-1]) < 2.0
+    stopped_ref = float(r.t[-1]) < 2.0
+    if terminal and stopped_gpu and (not stopped_ref or float(a.t[-1]) < float(r.t[-1]) - 1e-9):
+        # the engine stopped at a terminal crossing that the reference's root finder did not accept (it went on, or stopped
+        # at a later crossing): a documented difference, not compared further
+        out.update(reference_missed_terminal_root=True, t_stop_gpu=float(a.t[-1]), t_stop_ref=float(r.t[-1]), steps_equal=True,
+                   final_rel_err=0.0)
+        return out
+    out.update(ref_events_missing_on_gpu=len(miss), final_t_err=float(abs(float(a.t[-1]) - float(r.t[-1]))),
+               final_rel_err=float(np.max(np.abs(a.y[-1].cpu().numpy() - np.asarray(r.y[-1]))) / max(1.0, float(np.max(np.abs(r.y[-1]))))),
+               steps_equal=len(r) == len(a) and not miss)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cases", type=int, default=200)
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import desolver_b200 as de
+    ref = _import_reference()
+    rng = np.random.default_rng(args.seed)
+    kinds = ["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1
+    rows, failures = [], []
+    for c in range(args.cases):
+        kind = kinds[c % len(kinds)]
+        state = rng.bit_generator.state
+        try:
+            if kind == "ensemble":
+                row = run_ensemble_case(ref, de, torch, rng)
+            elif kind == "events":
+                row = run_event_case(ref, de, torch, rng)
+            else:
+                row = run_case(ref, de, torch, rng, kind)
+        except Exception as e:                                   # noqa: BLE001 -- a crash IS a finding
+            row = dict(kind=kind, error=repr(e)[:300], steps_equal=False, final_rel_err=float("inf"))
+        row["case"] = c
+        rows.append(row)
+        if args.verbose:
+            print(json.dumps(row), file=sys.stderr)
+        if "error" in row or not row.get("steps_equal", True) or not (row.get("final_rel_err", 0.0) <= 1e-9):
+            failures.append(row)
+    ok = [r for r in rows if "error" not in r]
+    summary = dict(cases=len(rows), crashed=len(rows) - len(ok), steps_equal=sum(bool(r.get("steps_equal")) for r in ok),
+                   final_rel_err_max=max((r["final_rel_err"] for r in ok), default=None),
+                   final_rel_err_median=float(np.median([r["final_rel_err"] for r in ok])) if ok else None,
+                   max_t_err=max((r.get("max_t_err", 0.0) for r in ok), default=None),
+                   dense_rel_err_max=max((r["dense_rel_err"] for r in ok if "dense_rel_err" in r), default=None),
+                   reference_missed_terminal_root=sum(bool(r.get("reference_missed_terminal_root")) for r in ok),
+                   skipped=sum("skipped" in r for r in ok),
+                   by_kind={k: dict(cases=sum(r["kind"] == k for r in rows),
+                                    steps_equal=sum(bool(r.get("steps_equal")) for r in rows if r["kind"] == k),
+                                    final_rel_err_max=max((r["final_rel_err"] for r in ok if r["kind"] == k), default=None))
+                            for k in sorted(set(kinds))},
+                   seed=args.seed, failures=failures[:40])
+    print(json.dumps(summary, indent=1))
+
+
+if __name__ == "__main__":
+    main()
