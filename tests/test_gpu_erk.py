@@ -277,3 +277,4 @@ def test_time_dependent_plugins_run_in_the_fused_kernel(strict):
     b.use_fused = False
     b.integrate()
     _compare(b, g["y_final"], g["accepted"], g["attempts"])
+

@@ -99,3 +99,13 @@ def test_reference_only_methods_raise_a_targeted_error():
     import desolver_b200 as b2
     assert b2.integrators.implicit_methods() == []
     assert "RadauIIA5" in b2.integrators.REFERENCE_ONLY_METHODS
+
+
+def test_installed_reference_is_the_unmodified_tree():
+    """baseline/_ref (the copy that travels to the GPU box for bench.py's live CPU-A / CPU-B timing and
+    `parity.reference_live`) is byte for byte /root/reference/desolver."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import install_reference
+    tree = install_reference.install()
+    assert tree is not None and os.path.isdir(os.path.join(tree, "desolver"))
+    assert install_reference._same_tree(os.path.join(REF, "desolver"), os.path.join(tree, "desolver"))

@@ -3,6 +3,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lineinfo \
 //        -DDSB_ERK_MIN_BLOCKS=5 -o erk_bench tools/erk_bench.cu
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <cstdarg>
 #include <vector>
@@ -75,6 +76,18 @@ int main(int argc, char **argv)
     std::vector<int> ha(n), hr(n);
     cudaMemcpy(ha.data(), acc, 4 * n, cudaMemcpyDeviceToHost); cudaMemcpy(hr.data(), rej, 4 * n, cudaMemcpyDeviceToHost);
     for (long long i = 0; i < n; ++i) attempts += ha[i] + hr[i];
+    {   // checksums of the result (two builds of the kernel must agree bit for bit) and the kernel's own statistics
+        std::vector<double> hy(3 * n), ht(n);
+        std::vector<int> hs(n);
+        unsigned long long hc[8];
+        cudaMemcpy(hy.data(), y, 24 * n, cudaMemcpyDeviceToHost); cudaMemcpy(ht.data(), t, 8 * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hs.data(), st, 4 * n, cudaMemcpyDeviceToHost); cudaMemcpy(hc, ctr, 64, cudaMemcpyDeviceToHost);
+        unsigned long long x = 0, sa = 0, sr = 0, ss = 0;
+        for (long long i = 0; i < 3 * n; ++i) { unsigned long long b; memcpy(&b, &hy[i], 8); x = x * 1099511628211ull + b; }
+        for (long long i = 0; i < n; ++i) { unsigned long long b; memcpy(&b, &ht[i], 8); x = x * 1099511628211ull + b; sa += ha[i]; sr += hr[i]; ss += hs[i]; }
+        printf("checksum %016llx accepted %llu rejected %llu status-sum %llu | counters: attempts %llu accepted %llu failed %llu running %llu\n",
+               x, sa, sr, ss, hc[2], hc[3], hc[4], hc[5]);
+    }
     printf("threads %d min_blocks %d regs %d blocks/SM %d : best %.3f ms  %.3e traj-steps/s  (%.1f%% of 8.17e10)  err=%s\n",
            ERK_THREADS, erk_min_blocks<Rhs, 6>(), fa.numRegs, per_sm, best, attempts / (best * 1e-3), 100.0 * attempts / (best * 1e-3) / 8.17e10,
            cudaGetErrorString(cudaGetLastError()));
