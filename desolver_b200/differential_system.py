@@ -1896,9 +1896,9 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
             fn = fn.rhs
         names = inspect.getfullargspec(fn)[0][2:]
         constants = {k: v for k, v in zip(names, args)}
-    max_step = options.get("max_step", np.inf)
-    min_step = options.get("min_step", 0.0)
-    first = min(max(options.get("first_step", 1.0), min_step), max_step)
+    max_step = float(options.get("max_step", np.inf))
+    min_step = float(options.get("min_step", 0.0))
+    first = min(max(float(options.get("first_step", 1.0)), min_step), max_step)
     # t_eval_mode="steps" (default): repeated integrate(t) like the reference -- every t_eval[k] is an exact stop of the
     # integration; "dense": ONE integration over t_span with the node store, then ONE launch of the T x N Hermite
     # evaluation kernel (scipy's semantics: values at t_eval are interpolated, the steps are those of the free run)
@@ -1921,7 +1921,10 @@ def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, e
         t_res = system.t
         y_res = torch.movedim(system.y, 0, -1)
     else:
-        t_eval = np.sort(np.asarray(t_eval, dtype=np.float64))
+        if torch.is_tensor(t_eval):                   # a torch user passes device tensors; the stop list is host data
+            t_eval = t_eval.detach().cpu().numpy()
+        t_eval = np.sort(np.asarray(t_eval, dtype=np.float64).reshape(-1))
+        t_span = tuple(float(v) for v in t_span)
         if t_eval[0] < min(t_span) or t_eval[-1] > max(t_span):
             raise ValueError(f"Expected `t_eval` to be in the range [{t_span[0]}, {t_span[1]}]")
         if mode == "dense":

@@ -129,7 +129,104 @@ def run_case(ref, de, torch, rng, kind):
         s_ref = np.stack([np.asarray(r.sol(float(x))) for x in q])
         s_gpu = np.stack([a.sol(float(x)).cpu().numpy().reshape(-1) for x in q])
         out["dense_rel_err"] = float(np.max(np.abs(s_gpu - s_ref)) / scale)
+        g_ref = np.stack([np.asarray(r.sol.grad(float(x))) for x in q])
+        g_gpu = np.stack([a.sol.grad(float(x)).cpu().numpy().reshape(-1) for x in q])
+        out["dense_grad_rel_err"] = float(np.max(np.abs(g_gpu - g_ref)) / max(1.0, float(np.max(np.abs(g_ref)))))
+        if out["steps_equal"]:
+            lo, hi = sorted((float(q[2]), float(q[6])))
+            out["slice_len_equal"] = len(r[lo:hi].t) == len(a[lo:hi].t)
+            out["nearest_t_err"] = float(abs(float(r[float(q[4])].t) - float(a[float(q[4])].t)))
     return out
+
+
+def run_continue_case(ref, de, torch, rng):
+    """integrate(t1); integrate(t2); reset(); integrate(): history and state of a continued, then repeated, run."""
+    prob = str(rng.choice(["sho", "lorenz", "vdp"]))
+    y0, consts, span = _draw(rng, prob)
+    method = str(rng.choice(["RK45", "RK87", "DOPRI45", "RK4"]))
+    tol = float(10.0 ** rng.choice([-7, -9]))
+    path = str(rng.choice(["plugin", "callable"]))
+    kw = dict(t=span, dt=0.01, constants=consts)
+    if method != "RK4":
+        kw.update(rtol=tol, atol=tol)
+    t1 = span[0] + 0.37 * (span[1] - span[0])
+    r = ref.OdeSystem(_rhs_factory(prob, np), y0=y0.copy(), **kw)
+    r.method = method
+    rhs = getattr(de.rhs_plugins, PLUGIN[prob]) if path == "plugin" else _rhs_factory(prob, torch)
+    a = de.OdeSystem(rhs, torch.as_tensor(y0.copy()), device="cuda:0", **kw)
+    a.method = method
+    out = dict(kind="continue", problem=prob, method=method, tol=tol, path=path)
+    lens, err = [], 0.0
+    for step in ("t1", "tf", "reset"):
+        for o in (r, a):
+            if step == "t1":
+                o.integrate(t1)
+            elif step == "tf":
+                o.integrate()
+            else:
+                o.reset()
+                o.integrate()
+        lens.append((len(r), len(a)))
+        yr = np.asarray(r.y[-1], dtype=np.float64)
+        err = max(err, float(np.max(np.abs(a.y[-1].cpu().numpy() - yr)) / max(1.0, float(np.max(np.abs(yr))))))
+        err = max(err, abs(float(a.t[-1]) - float(r.t[-1])))
+    out.update(lens=lens, steps_equal=all(x == y for x, y in lens), final_rel_err=err, nfev_ref=int(r.nfev), nfev_gpu=int(a.nfev))
+    return out
+
+
+def run_solve_ivp_case(ref, de, torch, rng):
+    """The scipy-style front end: t_eval stops, first_step / max_step options, args tuple."""
+    prob = str(rng.choice(["lorenz", "vdp", "sho"]))
+    y0, consts, span = _draw(rng, prob)
+    method = str(rng.choice(["RK45", "RK87", "DOPRI45"]))
+    tol = float(10.0 ** rng.choice([-6, -8, -10]))
+    opts = dict(rtol=tol, atol=tol, first_step=float(rng.choice([1e-3, 1e-2, 0.1])))
+    if rng.integers(0, 2):
+        opts["max_step"] = float(rng.choice([0.05, 0.2]))
+    t_eval = None
+    if rng.integers(0, 3) > 0:
+        t_eval = np.sort(rng.uniform(span[0], span[1], 6))
+        t_eval[-1] = span[1]
+    args = tuple(consts.values())
+    path = str(rng.choice(["plugin", "callable"]))
+    rr = ref.solve_ivp(_rhs_factory(prob, np), span, y0.copy(), method=method, t_eval=t_eval, args=args or None, **opts)
+    rhs = getattr(de.rhs_plugins, PLUGIN[prob]) if path == "plugin" else _rhs_factory(prob, torch)
+    kw = dict(opts)
+    ga = de.solve_ivp(rhs, span, torch.as_tensor(y0.copy()).cuda(), method=method,
+                      t_eval=None if t_eval is None else torch.as_tensor(t_eval).cuda(), args=args or None, **kw)
+    t_r, y_r = np.asarray(rr.t, dtype=np.float64), np.asarray(rr.y, dtype=np.float64)
+    t_g, y_g = ga.t.cpu().numpy(), ga.y.cpu().numpy()
+    out = dict(kind="solve_ivp", problem=prob, method=method, tol=tol, path=path, t_eval=t_eval is not None, max_step=opts.get("max_step"),
+               shape_ref=list(y_r.shape), shape_gpu=list(y_g.shape), nfev_ref=int(rr.nfev), nfev_gpu=int(ga.nfev))
+    out["steps_equal"] = t_r.shape == t_g.shape and y_r.shape == y_g.shape
+    if out["steps_equal"]:
+        out["max_t_err"] = float(np.max(np.abs(t_r - t_g)))
+        out["path_rel_err"] = float(np.max(np.abs(y_r - y_g)) / max(1.0, float(np.max(np.abs(y_r)))))
+        out["final_rel_err"] = float(np.max(np.abs(y_r[..., -1] - y_g[..., -1])) / max(1.0, float(np.max(np.abs(y_r)))))
+    else:
+        out["final_rel_err"] = float("inf")
+    return out
+
+
+def run_richardson_case(ref, de, torch, rng):
+    """Local Richardson extrapolation over a basis scheme (integrator_types.py:420-613)."""
+    base = str(rng.choice(["RK4Solver", "MidpointSolver", "RK45CKSolver"]))
+    it = int(rng.choice([2, 3]))
+    y0, consts, span = _draw(rng, "sho")
+    tol = float(10.0 ** rng.choice([-6, -8]))
+    kw = dict(t=span, dt=0.05, rtol=tol, atol=tol, constants=consts)
+    r = ref.OdeSystem(_rhs_factory("sho", np), y0=y0.copy(), **kw)
+    r.method = ref.integrators.generate_richardson_integrator(getattr(ref.integrators, base), richardson_iter=it)
+    r.integrate()
+    path = str(rng.choice(["plugin", "callable"]))
+    rhs = de.rhs_plugins.harmonic_oscillator if path == "plugin" else _rhs_factory("sho", torch)
+    a = de.OdeSystem(rhs, torch.as_tensor(y0.copy()), device="cuda:0", **kw)
+    a.method = de.integrators.generate_richardson_integrator(getattr(de.integrators, base), richardson_iter=it)
+    a.integrate()
+    yr = np.asarray(r.y[-1], dtype=np.float64)
+    return dict(kind="richardson", basis=base, richardson_iter=it, tol=tol, path=path, steps_ref=len(r) - 1, steps_gpu=len(a) - 1,
+                steps_equal=len(r) == len(a), nfev_ref=int(r.nfev), nfev_gpu=int(a.nfev),
+                final_rel_err=float(np.max(np.abs(a.y[-1].cpu().numpy() - yr)) / max(1.0, float(np.max(np.abs(yr))))))
 
 
 def run_ensemble_case(ref, de, torch, rng):
@@ -218,12 +315,16 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cases", type=int, default=200)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--only", default=None, help="comma-separated case kinds")
     args = ap.parse_args()
     import torch
     import desolver_b200 as de
     ref = _import_reference()
     rng = np.random.default_rng(args.seed)
-    kinds = ["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1
+    kinds = (["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1 +
+             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1)
+    if args.only:
+        kinds = [k for k in kinds if k in args.only.split(",")]
     rows, failures = [], []
     for c in range(args.cases):
         kind = kinds[c % len(kinds)]
@@ -233,10 +334,17 @@ def main():
                 row = run_ensemble_case(ref, de, torch, rng)
             elif kind == "events":
                 row = run_event_case(ref, de, torch, rng)
+            elif kind == "continue":
+                row = run_continue_case(ref, de, torch, rng)
+            elif kind == "solve_ivp":
+                row = run_solve_ivp_case(ref, de, torch, rng)
+            elif kind == "richardson":
+                row = run_richardson_case(ref, de, torch, rng)
             else:
                 row = run_case(ref, de, torch, rng, kind)
         except Exception as e:                                   # noqa: BLE001 -- a crash IS a finding
-            row = dict(kind=kind, error=repr(e)[:300], steps_equal=False, final_rel_err=float("inf"))
+            import traceback
+            row = dict(kind=kind, error=repr(e)[:300], where=traceback.format_exc()[-700:], steps_equal=False, final_rel_err=float("inf"))
         row["case"] = c
         rows.append(row)
         if args.verbose:
