@@ -611,16 +611,19 @@ class OdeSystem(object):
         """Right-hand-side evaluations in the reference's accounting, summed over the ensemble:
         per trajectory 1 (constructor) + 1 (first initial_rhs) + (S+1) per attempt
         (S per attempt for FSAL schemes); SURVEY.md fact 5."""
+        # the constructor's evaluation is counted until reset() zeroes the counter (reference :906): a reset system
+        # starts again from 0, not from 1
+        ctor = 0 if self.__dict__.get("_nfev_reset") else 1
         if self.__dict__.get("_pristine"):
-            return self.n_traj
+            return self.n_traj * ctor
         if self.__dict__.get("_protocol_path"):
             return int(self.equ_rhs.nfev)                      # the protocol loop calls the wrapped callable itself
         att = int((self.accepted.sum() + self.rejected.sum()).item())
         if att == 0:
-            return self.n_traj
+            return self.n_traj * ctor
         integ = self.integrator
         per_attempt = integ.stages + (0 if getattr(integ, "is_fsal", False) or integ.symplectic else 1)
-        return self.n_traj * 2 + per_attempt * att
+        return self.n_traj * (ctor + 1) + per_attempt * att
 
     @property
     def njev(self):
@@ -764,6 +767,7 @@ class OdeSystem(object):
         self.__int_status = 0
         self.__events = []
         self.equ_rhs.nfev = 0                              # reference :906
+        self.__dict__["_nfev_reset"] = True
         self._reset_state()
         self.initialise_integrator()
 
