@@ -619,10 +619,14 @@ class OdeSystem(object):
         if self.__dict__.get("_protocol_path"):
             return int(self.equ_rhs.nfev)                      # the protocol loop calls the wrapped callable itself
         att = int((self.accepted.sum() + self.rejected.sum()).item())
-        if att == 0:
-            return self.n_traj * ctor
         integ = self.integrator
         per_attempt = integ.stages + (0 if getattr(integ, "is_fsal", False) or integ.symplectic else 1)
+        frozen = self.__dict__.get("_nfev_frozen")
+        if frozen is not None:                                 # evaluations of earlier integrator objects + this one's
+            done, att0 = frozen
+            return done if att == att0 else done + self.n_traj + per_attempt * (att - att0)
+        if att == 0:
+            return self.n_traj * ctor
         return self.n_traj * (ctor + 1) + per_attempt * att
 
     @property
@@ -718,6 +722,12 @@ class OdeSystem(object):
     # ------------------------------------------------------------------ method handling
     def initialise_integrator(self, preserve_states=False):
         kwargs = dict(dtype=self.dtype, device=self.device, atol=self.atol, rtol=self.rtol)
+        if self.__dict__.get("integrator") is not None and not self.__dict__.get("_pristine", True) \
+                and not self.__dict__.get("_protocol_path"):
+            # a NEW integrator object in the middle of a run (method switch, new tolerances; reference :646, :660, :869):
+            # what the old one evaluated is final, and the new one evaluates initial_rhs again on its first step
+            # (integrator_types.py:169-175: final_rhs is None)
+            self.__dict__["_nfev_frozen"] = (self.nfev, int((self.accepted.sum() + self.rejected.sum()).item()))
         self.integrator = self.__method(self.dim, **kwargs)
 
     @property
@@ -768,6 +778,7 @@ class OdeSystem(object):
         self.__events = []
         self.equ_rhs.nfev = 0                              # reference :906
         self.__dict__["_nfev_reset"] = True
+        self.__dict__["_nfev_frozen"] = None
         self._reset_state()
         self.initialise_integrator()
 
@@ -829,8 +840,14 @@ class OdeSystem(object):
             return None
         n, st = self.n_traj, self._node_store
         if st is not None and st.kind != kind:
-            raise NotImplementedError("this system's node store was started by the %s kernels; reset() before switching "
-                                      "between the fused and the stage-level path" % ("fused" if kind == "rows" else "stage-level"))
+            if kind != "rows":
+                # (not reached through integrate(): a system whose store is row-written stays on the stage-level path)
+                raise NotImplementedError("this system's node store was started by the stage-level kernels; reset() before "
+                                          "running it through the fused kernel")
+            # the run began in the fused kernel and continues on the stage-level kernels (another method, per-component
+            # tolerances, events): the same nodes, re-laid out for the row writer
+            st = self._node_store = st.to_rows(with_f=bool(self.__dense_output))
+            self._rows_used = int(st.cursor[0].item()) // n
         if st is None:
             if kind == "fused":
                 page = 32 if (chunked or n <= 4096) else 256
@@ -1703,6 +1720,8 @@ class OdeSystem(object):
         else:
             callbacks = [callback]
         plugin = self._fused_plugin() if self.use_fused else None
+        if plugin is not None and self._node_store is not None and self._node_store.kind == "rows":
+            plugin = None                  # nodes of this run are row-written: it stays on the stage-level kernels until reset()
         fused_stats = None
         lazy = False
         try:

@@ -160,6 +160,34 @@ class NodeStore(object):
                                                   cb.current_stream_ptr(self.device)), "dsb_node_gather")
         return (t_out, y_out, f_out) if with_f else (t_out, y_out)
 
+    def to_rows(self, with_f=True):
+        """The same nodes re-laid out as the row-group log of the stage-level writer (width = n, slot = trajectory, group g
+        = node g of every trajectory that has one, header -1 elsewhere): a run that began in the fused kernel continues
+        on the stage-level kernels (method switch to a scheme without a fused instantiation, per-component tolerances,
+        events next to dense output).  Index arithmetic only -- the node values are copied bit for bit."""
+        torch = _torch()
+        if self.kind != "fused":
+            return self
+        n, F, dim, dev = self.n_traj, self.fields, self.dim, self.device
+        offsets, loc, total = self.index()
+        counts = self.node_count.to(torch.int64)
+        groups = int(counts.max().item()) if n else 0
+        new = NodeStore(dev, dim, n, "rows", capacity=(groups + 2) * n, with_f=with_f)
+        if groups:
+            g = torch.arange(groups, device=dev, dtype=torch.int64).unsqueeze(1)                  # (G, 1)
+            valid = g < counts.unsqueeze(0)                                                        # (G, n)
+            pos = (offsets[:n].unsqueeze(0) + g).clamp_(max=max(total - 1, 0))
+            e = loc[pos]                                                                           # entry of node g of trajectory i
+            src = (e >> 5) * (F * 32) + (e & 31)
+            dst = new.pool[:groups * F * n].view(groups, F, n)
+            empty = torch.tensor([-1, 0], dtype=torch.int32, device=dev).view(torch.float64)       # header {trajectory -1, k 0}
+            for r in range(F if with_f else 2 + dim):
+                vals = self.pool[src + r * 32]
+                dst[:, r, :] = torch.where(valid, vals, empty if r == 0 else torch.zeros_like(vals))
+        new.cursor[0] = groups * n
+        new.node_count.copy_(self.node_count)
+        return new
+
     def append_rows(self, t, y, f, flags_ptr, mask):
         """Stage-level writer: one row-group for the trajectories whose flag word has `mask` set (all if flags_ptr is None)."""
         s = self.struct()

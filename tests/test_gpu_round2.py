@@ -488,3 +488,72 @@ def test_array_valued_tolerances():
     b = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(g["y0"]), t=(0.0, 2.0), dt=1e-2, rtol=np.float64(1e-9), atol=np.array(1e-9),
                      ensemble=True)
     assert not b.integrator.has_vector_tolerances and b._fused_plugin() is not None
+
+
+# ------------------------------------------------------------------ a run that changes kernels half-way (differential run finding)
+@pytest.mark.parametrize("dense", [False, True])
+def test_history_survives_a_switch_from_the_fused_to_the_stage_level_kernels(dense):
+    """integrate(t1) in the fused kernel, then a method without a fused instantiation (RK14(12), 35 stages): the nodes
+    recorded so far are re-laid out for the row writer (NodeStore.to_rows) and the run continues -- history, dense
+    output and counters equal those of the same sequence run on the stage-level kernels throughout (STRICT arithmetic:
+    both paths round like the reference)."""
+    de = _de()
+
+    def run(use_fused):
+        a = de.OdeSystem(de.rhs_plugins.lorenz, torch.tensor([1.0, 1.0, 20.0], dtype=torch.float64), t=(0.0, 1.0), dt=1e-2, rtol=1e-9,
+                         atol=1e-9, dense_output=dense, strict=True)
+        a.use_fused = use_fused
+        a.method = "RK45"
+        a.integrate(0.4)
+        a.method = "RK1412"
+        a.integrate()
+        return a
+    a, b = run(True), run(False)
+    assert a._node_store.kind == "rows" and len(a) == len(b) > 20
+    assert torch.equal(a.t, b.t) and torch.equal(a.y, b.y)
+    assert a.nfev == b.nfev and int(a.accepted.sum()) == len(a) - 1
+    if dense:
+        q = torch.tensor([0.05, 0.39, 0.41, 0.97], dtype=torch.float64, device="cuda")
+        assert torch.equal(a.sol(q), b.sol(q)) and torch.equal(a.sol.grad(q), b.sol.grad(q))
+
+
+def test_a_row_written_run_stays_on_the_stage_level_kernels():
+    """Per-component tolerances start the run on the stage-level kernels; scalar tolerances afterwards would make the
+    system eligible for the fused kernel, whose node layout differs: it stays where its history lives (the reference
+    just carries on, differential_system.py:646-660), and equals the all-stage-level run bit for bit."""
+    de = _de()
+
+    def run(use_fused):
+        a = de.OdeSystem(de.rhs_plugins.van_der_pol, torch.tensor([2.0, 0.0], dtype=torch.float64), t=(0.0, 3.0), dt=1e-2,
+                         rtol=torch.tensor([1e-6, 2e-6], dtype=torch.float64), atol=1e-6, constants=dict(mu=1.5), strict=True)
+        a.use_fused = use_fused
+        a.method = "RK45"
+        a.integrate(1.2)
+        a.rtol = 1e-9
+        a.atol = 1e-9
+        a.integrate()
+        return a
+    a, b = run(True), run(False)
+    assert len(a) == len(b) and torch.equal(a.t, b.t) and torch.equal(a.y, b.y) and a.nfev == b.nfev
+    assert float(a.t[-1]) == 3.0
+
+
+def test_nfev_across_method_switches_and_reset_follows_the_reference():
+    """reference: every new integrator object evaluates initial_rhs once more on its first step (integrator_types.py:
+    169-175); reset() zeroes the counter (differential_system.py:906).  SHO: RK4 (231 steps of 5) then RK45CK (7 per attempt)."""
+    de = _de()
+    a = de.OdeSystem(de.rhs_plugins.harmonic_oscillator, torch.tensor([1.0, 0.0], dtype=torch.float64), t=(0.0, 4.0), dt=0.01,
+                     rtol=1e-8, atol=1e-8, constants=dict(k=1.0, m=1.0))
+    a.method = "RK4"
+    a.integrate(2.0)
+    n1 = len(a) - 1
+    assert a.nfev == 2 + 5 * n1
+    a.method = "RK45"
+    assert a.nfev == 2 + 5 * n1                                # nothing evaluated yet
+    a.integrate()
+    att2 = int((a.accepted + a.rejected).sum()) - n1
+    assert a.nfev == 2 + 5 * n1 + 1 + 7 * att2
+    a.reset()
+    assert a.nfev == 0
+    a.integrate()
+    assert a.nfev == 1 + 7 * int((a.accepted + a.rejected).sum())

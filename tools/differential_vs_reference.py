@@ -174,6 +174,51 @@ def run_continue_case(ref, de, torch, rng):
     return out
 
 
+def run_switch_case(ref, de, torch, rng):
+    """Attribute setters between calls: method switch, new tolerances, new step size, new final time; array tolerances."""
+    prob = str(rng.choice(["lorenz", "vdp", "sho"]))
+    y0, consts, span = _draw(rng, prob)
+    path = str(rng.choice(["plugin", "callable"]))
+    m1, m2 = (str(v) for v in rng.choice(["RK45", "RK87", "DOPRI45", "RK4", "RK108"], 2, replace=False))
+    tol1, tol2 = float(10.0 ** rng.choice([-6, -8])), float(10.0 ** rng.choice([-9, -10]))
+    vec_tol = bool(rng.integers(0, 2))
+    kw = dict(t=span, dt=0.01, constants=consts)
+    dim = y0.shape[0]
+    rt1 = tol1 * (1.0 + np.arange(dim)) if vec_tol else tol1
+    t1 = span[0] + 0.4 * (span[1] - span[0])
+    new_tf = span[1] + 0.3
+    rhs = getattr(de.rhs_plugins, PLUGIN[prob]) if path == "plugin" else _rhs_factory(prob, torch)
+    r = ref.OdeSystem(_rhs_factory(prob, np), y0=y0.copy(), rtol=rt1, atol=tol1, **kw)
+    a = de.OdeSystem(rhs, torch.as_tensor(y0.copy()), device="cuda:0", rtol=torch.as_tensor(rt1) if vec_tol else rt1, atol=tol1, **kw)
+    lens = []
+    desc = dict(kind="switch", problem=prob, path=path, methods=[m1, m2], tols=[tol1, tol2], vector_rtol=vec_tol, tol=tol1,
+                y0=[float(v) for v in y0], constants=consts, span=span)
+    for o in (r, a):
+        o.method = m1
+        o.integrate(t1)
+    lens.append((len(r), len(a)))
+    for name, o in (("ref", r), ("gpu", a)):
+        try:
+            o.method = m2
+            o.rtol = tol2
+            o.atol = tol2
+            o.dt = 0.005
+            o.tf = new_tf
+            o.integrate()
+        except Exception as e:                                   # noqa: BLE001
+            desc[name + "_error"] = repr(e)[:100] + " | cause: " + repr(e.__cause__)[:200]
+    if "ref_error" in desc or "gpu_error" in desc:
+        both = "ref_error" in desc and "gpu_error" in desc
+        return dict(desc, lens=lens, both_failed=both, steps_equal=both, final_rel_err=0.0 if both else float("inf"),
+                    t_ref=float(r.t[-1]), t_gpu=float(a.t[-1]), len_ref=len(r), len_gpu=len(a))
+    lens.append((len(r), len(a)))
+    yr = np.asarray(r.y[-1], dtype=np.float64)
+    return dict(kind="switch", problem=prob, path=path, methods=[m1, m2], tols=[tol1, tol2], vector_rtol=vec_tol, lens=lens, tol=tol1,
+                steps_equal=all(x == y for x, y in lens), nfev_ref=int(r.nfev), nfev_gpu=int(a.nfev),
+                final_t_err=abs(float(a.t[-1]) - float(r.t[-1])),
+                final_rel_err=float(np.max(np.abs(a.y[-1].cpu().numpy() - yr)) / max(1.0, float(np.max(np.abs(yr))))))
+
+
 def run_solve_ivp_case(ref, de, torch, rng):
     """The scipy-style front end: t_eval stops, first_step / max_step options, args tuple."""
     prob = str(rng.choice(["lorenz", "vdp", "sho"]))
@@ -322,7 +367,7 @@ def main():
     ref = _import_reference()
     rng = np.random.default_rng(args.seed)
     kinds = (["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1 +
-             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1)
+             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2)
     if args.only:
         kinds = [k for k in kinds if k in args.only.split(",")]
     rows, failures = [], []
@@ -340,6 +385,8 @@ def main():
                 row = run_solve_ivp_case(ref, de, torch, rng)
             elif kind == "richardson":
                 row = run_richardson_case(ref, de, torch, rng)
+            elif kind == "switch":
+                row = run_switch_case(ref, de, torch, rng)
             else:
                 row = run_case(ref, de, torch, rng, kind)
         except Exception as e:                                   # noqa: BLE001 -- a crash IS a finding
@@ -350,7 +397,9 @@ def main():
         if args.verbose:
             print(json.dumps(row), file=sys.stderr)
         bar = max(1e-9, 1e-2 * (row.get("tol") or 0.0))          # loose tolerances: step sizes ride on rounding noise
-        if "error" in row or not row.get("steps_equal", True) or not (row.get("final_rel_err", 0.0) <= bar):
+        row["nfev_equal"] = row.get("nfev_ref") == row.get("nfev_gpu")
+        if "error" in row or not row.get("steps_equal", True) or not (row.get("final_rel_err", 0.0) <= bar) or \
+                (row.get("steps_equal") and not row["nfev_equal"]):
             failures.append(row)
     ok = [r for r in rows if "error" not in r]
     summary = dict(cases=len(rows), crashed=len(rows) - len(ok), steps_equal=sum(bool(r.get("steps_equal")) for r in ok),
@@ -360,6 +409,8 @@ def main():
                    dense_rel_err_max=max((r["dense_rel_err"] for r in ok if "dense_rel_err" in r), default=None),
                    reference_missed_terminal_root=sum(bool(r.get("reference_missed_terminal_root")) for r in ok),
                    skipped=sum("skipped" in r for r in ok),
+                   nfev_equal=sum(bool(r.get("nfev_equal")) for r in ok if "nfev_ref" in r),
+                   nfev_compared=sum("nfev_ref" in r for r in ok),
                    by_kind={k: dict(cases=sum(r["kind"] == k for r in rows),
                                     steps_equal=sum(bool(r.get("steps_equal")) for r in rows if r["kind"] == k),
                                     final_rel_err_max=max((r["final_rel_err"] for r in ok if r["kind"] == k), default=None))
