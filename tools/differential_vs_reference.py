@@ -312,6 +312,55 @@ def run_ensemble_case(ref, de, torch, rng):
                 steps_equal=same == n)
 
 
+def run_ensemble2_case(ref, de, torch, rng):
+    """Ensembles beyond the plain fused run: torch-callable right-hand sides (stage-level kernels, t of shape (N,)),
+    two-leg integrations, dense-output queries, a method switch -- against one reference OdeSystem per trajectory."""
+    prob = str(rng.choice(["lorenz", "vdp", "forced"]))
+    m1 = str(rng.choice(["RK45", "RK87", "DOPRI45", "RK4"]))
+    m2 = str(rng.choice(["RK45", "RK87", "RK108"])) if rng.integers(0, 2) else m1
+    path = str(rng.choice(["plugin", "callable"]))
+    dense = bool(rng.integers(0, 2))
+    n, tol = 12, float(10.0 ** rng.choice([-7, -9]))
+    draws = [_draw(rng, prob) for _ in range(n)]
+    span = draws[0][2]
+    t1 = span[0] + 0.45 * (span[1] - span[0])
+    y0 = np.stack([d[0] for d in draws], axis=1)
+    consts, per = dict(draws[0][1]), None
+    if prob == "vdp":
+        per = np.array([d[1]["mu"] for d in draws])
+        consts = dict(mu=torch.as_tensor(per, device="cuda:0"))
+    rhs = getattr(de.rhs_plugins, PLUGIN[prob]) if path == "plugin" else _rhs_factory(prob, torch)
+    kw = dict(t=span, dt=1e-2)
+    tk = dict(rtol=tol, atol=tol)
+    a = de.OdeSystem(rhs, torch.as_tensor(y0), constants=consts, ensemble=True, device="cuda:0", dense_output=dense, **kw, **tk)
+    a.method = m1
+    a.integrate(t1)
+    a.method = m2
+    a.integrate()
+    acc, rej, y = a.accepted.cpu().numpy(), a.rejected.cpu().numpy(), a[-1].y.cpu().numpy()
+    q = float(span[0] + 0.77 * (span[1] - span[0]))
+    sq = a.sol(q).cpu().numpy() if dense else None
+    same, err, derr = 0, 0.0, 0.0
+    for i in range(n):
+        c = dict(draws[0][1]) if per is None else dict(mu=float(per[i]))
+        r = ref.OdeSystem(_rhs_factory(prob, np), y0=y0[:, i].copy(), constants=c, dense_output=dense, **kw, **tk)
+        r.method = m1
+        r.integrate(t1)
+        r.method = m2
+        r.integrate()
+        same += int(len(r) - 1 == acc[i])
+        yr = np.asarray(r.y[-1], dtype=np.float64)
+        sc = max(1.0, float(np.max(np.abs(yr))))
+        err = max(err, float(np.max(np.abs(y[:, i] - yr)) / sc))
+        if dense:
+            derr = max(derr, float(np.max(np.abs(sq[:, i] - np.asarray(r.sol(q)))) / sc))
+    out = dict(kind="ensemble2", problem=prob, methods=[m1, m2], path=path, dense=dense, tol=tol, trajectories=n, counts_identical=same,
+               final_rel_err=err, steps_equal=same == n)
+    if dense:
+        out["dense_rel_err"] = derr
+    return out
+
+
 def run_event_case(ref, de, torch, rng):
     """A terminal and a recorded event on the Lorenz system: event times, states and where the integration stops."""
     y0, consts, _ = _draw(rng, "lorenz")
@@ -367,7 +416,7 @@ def main():
     ref = _import_reference()
     rng = np.random.default_rng(args.seed)
     kinds = (["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1 +
-             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2)
+             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2 + ["ensemble2"] * 2)
     if args.only:
         kinds = [k for k in kinds if k in args.only.split(",")]
     rows, failures = [], []
@@ -387,6 +436,8 @@ def main():
                 row = run_richardson_case(ref, de, torch, rng)
             elif kind == "switch":
                 row = run_switch_case(ref, de, torch, rng)
+            elif kind == "ensemble2":
+                row = run_ensemble2_case(ref, de, torch, rng)
             else:
                 row = run_case(ref, de, torch, rng, kind)
         except Exception as e:                                   # noqa: BLE001 -- a crash IS a finding
@@ -399,7 +450,9 @@ def main():
         bar = max(1e-9, 1e-2 * (row.get("tol") or 0.0))          # loose tolerances: step sizes ride on rounding noise
         row["nfev_equal"] = row.get("nfev_ref") == row.get("nfev_gpu")
         if "error" in row or not row.get("steps_equal", True) or not (row.get("final_rel_err", 0.0) <= bar) or \
-                (row.get("steps_equal") and not row["nfev_equal"]):
+                (row.get("steps_equal") and not row["nfev_equal"] and row["kind"] != "richardson"):
+            # (Richardson wrappers: the reference's basis integrators each evaluate initial_rhs on their first sub-step; the
+            # engine's wrapper shares one evaluation -- 2 to 5 evaluations per RUN, states equal to 1e-13)
             failures.append(row)
     ok = [r for r in rows if "error" not in r]
     summary = dict(cases=len(rows), crashed=len(rows) - len(ok), steps_equal=sum(bool(r.get("steps_equal")) for r in ok),
