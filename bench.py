@@ -47,7 +47,7 @@ def static_config(n_local):
             "sharding": "round-robin over ranks, no data-path collective"}
 
 
-def reference_numpy_numbers():
+def reference_numpy_numbers(live=True):
     """The reference's own numpy backend (CPU-A: one OdeSystem per trajectory; CPU-B: a whole shard as ONE state with a
     global dt -- different semantics), timed LIVE on this box's host cores from baseline/_ref -- the unmodified reference,
     installed in the build container by baseline/install_reference.py (git-ignored, travels with the snapshot; `autoray`,
@@ -61,7 +61,7 @@ def reference_numpy_numbers():
     except Exception:
         pass
     for tree in (os.path.join(ROOT, "baseline", "_ref"),):
-        if os.path.isdir(os.path.join(tree, "desolver")):
+        if live and os.path.isdir(os.path.join(tree, "desolver")):
             try:
                 # its own process: the measurement forks a pool of workers, which must not inherit this process's CUDA /
                 # NCCL state and threads
@@ -467,7 +467,8 @@ def main():
             rate, cores, sample, _, _ = cpu_reference_sample(args.cpu_seconds, n_local * n_gpus)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "what": "oracle/desolver_oracle.c: C restatement of the reference algorithm, one thread per core"}
-            line["cpu_reference_numpy"] = reference_numpy_numbers()
+            # the reference itself is timed live at N = 1 only (at N > 1 the other ranks wait in a barrier on the same cores)
+            line["cpu_reference_numpy"] = reference_numpy_numbers(live=(world == 1))
             m, ref = cpu_reference_sample.last
         else:
             from desolver_b200.integrators import tableaux as tb
