@@ -557,6 +557,15 @@ class OdeSystem(object):
             return self.__events
         return self._event_log if self.ensemble else self._event_log.for_trajectory(0)
 
+    def _fire_callbacks(self, callbacks):
+        """User callbacks see the system as it stands NOW: whatever was cached from the node store is dropped first
+        (`a.t[-1]`, `a.y[-1]`, `a.sol` inside a callback; reference differential_system.py:1073-1084)."""
+        self._steps_cache = None
+        if self._node_store is not None:
+            self._node_store.invalidate()
+        for cbk in callbacks:
+            cbk(self)
+
     def _step_history(self):
         """(t[steps + 1], y[steps + 1, *dim]) of a single system: every accepted step, row 0 = the initial condition --
         gathered from the node store by one kernel (dsb_node_gather) and cached until the next integrate() call."""
@@ -1308,6 +1317,7 @@ class OdeSystem(object):
         if dense and int(store.node_count.max().item()) == 0:
             record_nodes(None)                                   # node 0 = initial condition
         first, attempts = True, 0
+        acc_seen = int(work["accepted"].sum().item()) if (callbacks and not self.ensemble) else 0
         # heavy attempts (large state x ensemble): one host look per attempt costs nothing next to the
         # attempt itself and saves up to sync_every-1 wasted lock-step rounds at the end
         sync_every = 1 if D * n * S >= (1 << 24) else self.sync_every
@@ -1410,8 +1420,15 @@ class OdeSystem(object):
             if trace is not None:
                 ev_pair[1].record()
                 trace.append((ev_pair[0], ev_pair[1], m, graph is not None))
-            for cbk in callbacks:
-                cbk(self)
+            if callbacks:
+                # a single system calls back once per ACCEPTED step like the reference's loop (differential_system.py:
+                # 1073-1084); an ensemble once per lock-step round
+                fire = True
+                if not self.ensemble:
+                    acc_now = int(work["accepted"].sum().item())
+                    fire, acc_seen = acc_now > acc_seen, acc_now
+                if fire:
+                    self._fire_callbacks(callbacks)
             if bar is not None:
                 bar.update()
             if callbacks or attempts % sync_every == 0:
@@ -1488,8 +1505,7 @@ class OdeSystem(object):
                     first = False
                     handle.run(a, stream)
                     self._launches += 1
-                    for cbk in callbacks:
-                        cbk(self)
+                    self._fire_callbacks(callbacks)
                     if bar is not None:
                         bar.update()
                     if not bool((self.status == cb.TRAJ_RUNNING).any().item()):
@@ -1617,8 +1633,7 @@ class OdeSystem(object):
                 one_step(False)
             self._launches += (4 + S) if graph is None else 1
             steps += 1
-            for cbk in callbacks:
-                cbk(self)
+            self._fire_callbacks(callbacks)
             if bar is not None:
                 bar.update()
             if callbacks or steps % self.sync_every == 0:
@@ -1672,8 +1687,7 @@ class OdeSystem(object):
                 self._rows_used += 1
             if not final:
                 dt.copy_(torch.as_tensor(new_dt, dtype=torch.float64, device=self.device).reshape(1))
-            for cbk in callbacks:
-                cbk(self)
+            self._fire_callbacks(callbacks)
             if bar is not None:
                 bar.update()
             if steps > self._step_cap:
@@ -1800,8 +1814,7 @@ class OdeSystem(object):
                     first = False
                     st = self._fused_stats()
                     fused_stats = (fused_stats[0] + st[0], fused_stats[1] + st[1], st[2], st[3])
-                    for cbk in callbacks:
-                        cbk(self)
+                    self._fire_callbacks(callbacks)
                     if bar is not None:
                         bar.update()
                     if st[3] == 0:

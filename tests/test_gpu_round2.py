@@ -557,3 +557,23 @@ def test_nfev_across_method_switches_and_reset_follows_the_reference():
     assert a.nfev == 0
     a.integrate()
     assert a.nfev == 1 + 7 * int((a.accepted + a.rejected).sum())
+
+
+@pytest.mark.parametrize("path", ["plugin", "callable"])
+def test_single_system_callbacks_fire_once_per_accepted_step(path):
+    """The reference calls back after every ACCEPTED step (differential_system.py:1073-1084); rejected attempts are
+    invisible to the caller.  (The stage-level loop used to call back once per attempt -- found by the differential run.)"""
+    de = _de()
+    rhs = de.rhs_plugins.forced if path == "plugin" else (lambda t, y: torch.stack([y[1], t - y[0]]))
+    a = de.OdeSystem(rhs, torch.tensor([0.3, -0.2], dtype=torch.float64), t=(0.0, 3.0), dt=0.5, rtol=1e-9, atol=1e-9)
+    a.method = "RK45"
+    seen = []
+
+    def cbk(s):
+        seen.append(float(s.t[-1]))
+        if abs(float(s.dt)) > 0.05:              # a step clamp, as solve_ivp(max_step=...) installs it
+            s.dt = 0.05
+    a.integrate(callback=cbk)
+    assert int(a.rejected.sum()) > 0                                   # dt0 = 0.5 is far too large for the tolerance
+    assert len(seen) == len(a) - 1 == int(a.accepted.sum())
+    assert np.allclose(seen, a.t[1:].cpu().numpy(), rtol=0, atol=0)    # called with the state at each accepted step

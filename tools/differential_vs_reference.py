@@ -370,6 +370,105 @@ def run_ensemble2_case(ref, de, torch, rng):
     return out
 
 
+def run_shape_case(ref, de, torch, rng):
+    """State shapes beyond a short vector: matrix-valued states (Y' = A Y + Y B), a long single system with the reference's
+    global error norm (a ring of coupled oscillators), non-zero start times, callbacks that count and clamp the step."""
+    variant = str(rng.choice(["matrix", "ring", "callback"]))
+    method = str(rng.choice(["RK45", "RK87", "DOPRI45", "RK4", "AHE"]))
+    tol = float(10.0 ** rng.choice([-5, -7, -9])) if method != "AHE" else 1e-5
+    t0 = float(rng.choice([0.0, -1.5, 3.0]))
+    span = (t0, t0 + float(rng.uniform(0.5, 2.0)))
+    kw = dict(t=span, dt=0.01)
+    if method != "RK4":
+        kw.update(rtol=tol, atol=tol)
+    if variant == "matrix":
+        A = rng.normal(size=(3, 3)) * 0.7 - 0.5 * np.eye(3)
+        B = rng.normal(size=(4, 4)) * 0.5
+        y0 = rng.normal(size=(3, 4))
+        At, Bt = torch.as_tensor(A).cuda(), torch.as_tensor(B).cuda()
+        f_np = lambda t, y: A @ y + y @ B                          # noqa: E731
+        f_t = lambda t, y: At @ y + y @ Bt                         # noqa: E731
+    elif variant == "ring":
+        m = int(rng.choice([64, 257, 1000]))
+        y0 = rng.normal(size=(2 * m,))
+        kk = float(rng.uniform(0.5, 3.0))
+        f_np = lambda t, y: np.concatenate([y[m:], kk * (np.roll(y[:m], 1) - 2 * y[:m] + np.roll(y[:m], -1)) - np.sin(t) * y[:m]])      # noqa: E731
+        f_t = lambda t, y: torch.cat([y[m:], kk * (torch.roll(y[:m], 1) - 2 * y[:m] + torch.roll(y[:m], -1)) - torch.sin(t) * y[:m]])  # noqa: E731
+    else:
+        y0 = rng.uniform(-1, 1, 2)
+        f_np = _rhs_factory("forced", np)
+        f_t = _rhs_factory("forced", torch)
+    r = ref.OdeSystem(f_np, y0=y0.copy(), **kw)
+    a = de.OdeSystem(f_t, torch.as_tensor(y0.copy()), device="cuda:0", **kw)
+    calls = {"ref": 0, "gpu": 0}
+    cap = float(rng.choice([0.03, 0.1]))
+    for name, o in (("ref", r), ("gpu", a)):
+        o.method = method
+        if variant == "callback":
+            def cb(sys_, _name=name):
+                calls[_name] += 1
+                if abs(float(sys_.dt)) > cap:
+                    sys_.dt = cap
+            o.integrate(callback=cb)
+        else:
+            o.integrate()
+    yr = np.asarray(r.y[-1], dtype=np.float64)
+    out = dict(kind="shapes", variant=variant, method=method, tol=tol if method != "RK4" else None, span=span, shape=list(y0.shape),
+               steps_ref=len(r) - 1, steps_gpu=len(a) - 1, steps_equal=len(r) == len(a), nfev_ref=int(r.nfev), nfev_gpu=int(a.nfev),
+               final_t_err=abs(float(a.t[-1]) - float(r.t[-1])), shape_equal=tuple(a.y.shape) == tuple(np.asarray(r.y).shape),
+               final_rel_err=float(np.max(np.abs(a.y[-1].cpu().numpy() - yr)) / max(1.0, float(np.max(np.abs(yr))))))
+    if variant == "callback":
+        out["callback_calls"] = [calls["ref"], calls["gpu"]]
+        out["steps_equal"] = out["steps_equal"] and calls["ref"] == calls["gpu"]
+    if not out["shape_equal"]:
+        out["steps_equal"] = False
+    return out
+
+
+def run_event2_case(ref, de, torch, rng):
+    """Event records in detail: times AND states of every recorded event, direction filters, a `requires_dstate` event
+    (a maximum of a component), on a single Van der Pol system."""
+    y0, consts, _ = _draw(rng, "vdp")
+    level = float(rng.uniform(-1.0, 1.0))
+    direction = int(rng.choice([-1, 0, 1]))
+
+    def make(xp):
+        def cross(t, y, **k):
+            return y[0] - level
+        cross.direction = direction
+
+        def vmax(t, y, dy, **k):                 # dy = the interpolant's derivative: zero of the acceleration-free velocity
+            return dy[0]
+        vmax.requires_dstate = True
+        vmax.direction = -1
+
+        def product(t, y, **k):
+            return y[0] * y[1] - 0.3
+        return [cross, vmax, product]
+    kw = dict(t=(0.0, 8.0), dt=1e-2, rtol=1e-9, atol=1e-9, constants=consts, dense_output=True)
+    r = ref.OdeSystem(_rhs_factory("vdp", np), y0=y0.copy(), **kw)
+    r.method = "RK45"
+    r.integrate(events=make(np))
+    a = de.OdeSystem(_rhs_factory("vdp", torch) if rng.integers(0, 2) else de.rhs_plugins.van_der_pol, torch.as_tensor(y0.copy()),
+                     device="cuda:0", **kw)
+    a.method = "RK45"
+    a.integrate(events=make(torch))
+    ev_r = sorted((float(e.t), np.asarray(e.y, dtype=np.float64)) for e in r.events)
+    ev_g = sorted((float(e.t), e.y.cpu().numpy().reshape(-1)) for e in a.events)
+    miss, yerr, terr = 0, 0.0, 0.0
+    for t, y in ev_r:                                    # the reference reports a subset of the crossings (DESIGN.md K7)
+        j = int(np.argmin([abs(t - u) for u, _ in ev_g])) if ev_g else -1
+        if j < 0 or abs(ev_g[j][0] - t) > 1e-8:
+            miss += 1
+            continue
+        terr = max(terr, abs(ev_g[j][0] - t))
+        yerr = max(yerr, float(np.max(np.abs(ev_g[j][1] - y))))
+    return dict(kind="events2", direction=direction, events_ref=len(ev_r), events_gpu=len(ev_g), ref_events_missing_on_gpu=miss,
+                event_t_err=terr, event_y_err=yerr, steps_ref=len(r) - 1, steps_gpu=len(a) - 1,
+                steps_equal=len(r) == len(a) and miss == 0 and len(ev_g) >= len(ev_r),
+                final_rel_err=max(yerr, float(np.max(np.abs(a.y[-1].cpu().numpy() - np.asarray(r.y[-1]))))))
+
+
 def run_event_case(ref, de, torch, rng):
     """A terminal and a recorded event on the Lorenz system: event times, states and where the integration stops."""
     y0, consts, _ = _draw(rng, "lorenz")
@@ -425,7 +524,7 @@ def main():
     ref = _import_reference()
     rng = np.random.default_rng(args.seed)
     kinds = (["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1 +
-             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2 + ["ensemble2"] * 2)
+             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2 + ["ensemble2"] * 2 + ["shapes"] * 3 + ["events2"] * 1)
     if args.only:
         kinds = [k for k in kinds if k in args.only.split(",")]
     rows, failures = [], []
@@ -447,6 +546,10 @@ def main():
                 row = run_switch_case(ref, de, torch, rng)
             elif kind == "ensemble2":
                 row = run_ensemble2_case(ref, de, torch, rng)
+            elif kind == "shapes":
+                row = run_shape_case(ref, de, torch, rng)
+            elif kind == "events2":
+                row = run_event2_case(ref, de, torch, rng)
             else:
                 row = run_case(ref, de, torch, rng, kind)
         except Exception as e:                                   # noqa: BLE001 -- a crash IS a finding
