@@ -728,6 +728,53 @@ class OdeSystem(object):
     def get_current_time(self):
         return self._user_time(self._t)
 
+    @property
+    def counter(self):
+        """Index of the last stored row: `a.t[a.counter]` is the current time (reference `:523, :792`)."""
+        return len(self) - 1
+
+    @property
+    def events_dict(self):
+        """{event function: StateTuple(t = its times, y = its states, event)} of a single system (reference `:573-593`)."""
+        torch = _torch()
+        found = list(self.events) if not self.ensemble else None
+        if found is None:
+            raise NotImplementedError("events_dict is the single-system view; an ensemble's events are in `a.events` (EventLog)")
+        out = {}
+        for ev in {id(e.event): e.event for e in found}.values():
+            mine = [e for e in found if e.event is ev]
+            out[ev] = StateTuple(t=torch.stack([torch.as_tensor(e.t) for e in mine]), y=torch.stack([e.y for e in mine]), event=ev)
+        return out
+
+    def get_step_interpolant(self):
+        """(t_end, interpolant) of the last step (reference `:871-872` = `integrator.dense_output()`): from the integrator
+        when the protocol loop drove it, else from the last two nodes of the store (dense_output=True)."""
+        if self.__dict__.get("_protocol_path") or self._node_store is None or not self._node_store.with_f:
+            return self.integrator.dense_output()
+        from .utilities.interpolation import CubicHermiteInterp
+        if self.ensemble:
+            raise NotImplementedError("per-step interpolants of an ensemble are served by `a.sol` (one launch for all trajectories)")
+        count = int(self._node_store.node_count[0].item())
+        if count < 2:
+            return self.integrator.dense_output()
+        t_rows, y_rows, f_rows = self._node_store.gather(0, k0=count - 2, count=2, with_f=True)
+        shape = tuple(self.dim)
+        interp = CubicHermiteInterp(t_rows[0], t_rows[1], y_rows[0].reshape(shape), y_rows[1].reshape(shape),
+                                    f_rows[0].reshape(shape), f_rows[1].reshape(shape))
+        return t_rows[1], interp
+
+    @property
+    def staggered_mask(self):
+        """The kick mask of the splitting schemes (reference `:531, :820-823`): the default -- second half of axis 0 --
+        is the only one (a custom mask is dead code in the reference)."""
+        return getattr(self.integrator, "staggered_mask", None)
+
+    def set_kick_vars(self, staggered_mask):
+        """reference `:769-788`.  Only the default mask is supported."""
+        if staggered_mask is not None:
+            raise NotImplementedError("custom staggered_mask is not supported (dead code in the reference)")
+        self.initialise_integrator()
+
     # ------------------------------------------------------------------ method handling
     def initialise_integrator(self, preserve_states=False):
         kwargs = dict(dtype=self.dtype, device=self.device, atol=self.atol, rtol=self.rtol)

@@ -110,3 +110,33 @@ def test_constants_spellings_and_float32_state_is_refused_clearly():
         assert b.y.dtype == torch.float64
     except (TypeError, ValueError, NotImplementedError) as e:
         assert "float64" in str(e) or "dtype" in str(e)
+
+
+def test_reference_attributes_exist_and_mean_the_same():
+    """`counter`, `get_step_interpolant()`, `events_dict`, `staggered_mask`, `set_kick_vars` of the reference's OdeSystem
+    (differential_system.py:523, 573-593, 769-792, 871-872)."""
+    de = _de()
+    a = _canonical(dense=True)
+    assert a.counter == 0 and len(a) == 1
+    a.integrate()
+    assert a.counter == len(a) - 1 > 50 and float(a.t[a.counter]) == 1.0 == float(a.get_current_time())
+    t_end, interp = a.get_step_interpolant()
+    assert float(t_end) == 1.0
+    mid = 0.5 * (float(a.t[-2]) + float(a.t[-1]))
+    assert torch.equal(interp(mid).reshape(-1), a.sol(mid).reshape(-1))          # the last step's Hermite piece
+    assert a.staggered_mask is None
+    a.set_kick_vars(None)
+    with pytest.raises(NotImplementedError):
+        a.set_kick_vars(np.array([True, False, True]))
+
+    def plane(t, y, **kw):
+        return y[2] - 25.0
+
+    def late(t, y, **kw):
+        return t - 0.75
+    b = _canonical(dense=True)
+    b.integrate(events=[plane, late])
+    d = b.events_dict
+    assert set(d) == {e.event for e in b.events} and late in d
+    assert float(d[late].t[0]) == pytest.approx(0.75, abs=1e-12) and tuple(d[late].y.shape) == (1, 3)
+    assert sum(int(v.t.shape[0]) for v in d.values()) == len(b.events)

@@ -124,6 +124,27 @@ def run_case(ref, de, torch, rng, kind):
     if out["steps_equal"]:
         out["max_t_err"] = float(np.max(np.abs(t_gpu - t_ref)))
         out["max_y_rel_err"] = float(np.max(np.abs(y_gpu - y_ref)) / scale)
+    # the attributes a caller reads afterwards
+    api = {}
+    for name in ("dt", "t0", "tf", "success", "integration_status", "counter", "njev", "dim", "rtol", "atol", "staggered_mask"):
+        try:
+            u, v = getattr(r, name), getattr(a, name)
+            if name == "staggered_mask":
+                api[name] = (u is None) == (v is None) or method in SYMPLECTIC
+            elif u is None or v is None:
+                api[name] = (u is None and v is None) or "ref %r gpu %r" % (u, v)
+            elif name == "dt":
+                ok = abs(float(u) - float(v)) <= 1e-6 * abs(float(u)) + 1e-300 if out["steps_equal"] else True
+                api[name] = ok or "ref %r gpu %r" % (float(u), float(v))
+            elif name in ("t0", "tf", "rtol", "atol"):
+                api[name] = float(u) == float(v)
+            elif name == "dim":
+                api[name] = tuple(u) == tuple(v)
+            else:
+                api[name] = u == v
+        except Exception as e:                                   # noqa: BLE001
+            api[name] = "error: " + repr(e)[:80]
+    out["api_mismatch"] = {k: v for k, v in api.items() if v is not True}
     if not strict and (not out["steps_equal"] or out["final_rel_err"] > max(1e-9, 1e-2 * (tol or 0.0))):
         # is it the arithmetic flavour?  the same case in STRICT arithmetic (the reference's rounding sequence)
         b = de.OdeSystem(rhs, torch.as_tensor(y0.copy()), device="cuda:0", strict=True, **kw)
@@ -561,6 +582,9 @@ def main():
             print(json.dumps(row), file=sys.stderr)
         bar = max(1e-9, 1e-2 * (row.get("tol") or 0.0))          # loose tolerances: step sizes ride on rounding noise
         row["nfev_equal"] = row.get("nfev_ref") == row.get("nfev_gpu")
+        if row.get("api_mismatch"):
+            row["steps_equal_before_api"] = row.get("steps_equal")
+            row["steps_equal"] = False
         if "error" in row or not row.get("steps_equal", True) or not (row.get("final_rel_err", 0.0) <= bar) or \
                 (row.get("steps_equal") and not row["nfev_equal"] and row["kind"] != "richardson"):
             # (Richardson wrappers: the reference's basis integrators each evaluate initial_rhs on their first sub-step; the
