@@ -490,6 +490,87 @@ def run_event2_case(ref, de, torch, rng):
                 final_rel_err=max(yerr, float(np.max(np.abs(a.y[-1].cpu().numpy() - np.asarray(r.y[-1]))))))
 
 
+def run_nbody_case(ref, de, torch, rng):
+    """Softened gravitational N-body, state (2, nb, 3): the engine's `nbody` plugin (a dual numpy / torch callable) through
+    the reference, against the engine's fused symplectic kernel / stage-level kernels."""
+    nb = int(rng.choice([3, 8, 16]))
+    method = str(rng.choice(SYMPLECTIC + ["RK45", "RK87"]))
+    state = np.stack([rng.normal(size=(nb, 3)), 0.3 * rng.normal(size=(nb, 3))])
+    m = rng.uniform(0.5, 1.5, nb) / nb
+    eps2 = float(rng.choice([1e-2, 1e-4]))
+    dt = float(rng.choice([0.01, 0.02]))
+    tf = float(rng.uniform(0.2, 0.6))
+    kw = dict(t=(0.0, tf), dt=dt)
+    tol = None
+    if method in ("RK45", "RK87"):
+        tol = float(10.0 ** rng.choice([-7, -9]))
+        kw.update(rtol=tol, atol=tol)
+    r = ref.OdeSystem(de.rhs_plugins.nbody, y0=state.copy(), constants=dict(m=m, eps2=eps2, G=1.0), **kw)
+    r.method = method
+    r.integrate()
+    fused = bool(rng.integers(0, 2))
+    a = de.OdeSystem(de.rhs_plugins.nbody, torch.as_tensor(state.copy()), device="cuda:0",
+                     constants=dict(m=torch.as_tensor(m), eps2=eps2, G=1.0), strict=bool(rng.integers(0, 2)), **kw)
+    a.use_fused = fused
+    a.method = method
+    a.integrate()
+    yr = np.asarray(r.y[-1], dtype=np.float64)
+    return dict(kind="nbody", bodies=nb, method=method, tol=tol, use_fused=fused, steps_ref=len(r) - 1, steps_gpu=len(a) - 1,
+                steps_equal=len(r) == len(a), nfev_ref=int(r.nfev), nfev_gpu=int(a.nfev), shape_gpu=list(a.y.shape),
+                final_t_err=abs(float(a.t[-1]) - float(r.t[-1])),
+                final_rel_err=float(np.max(np.abs(a.y[-1].cpu().numpy() - yr)) / max(1.0, float(np.max(np.abs(yr))))))
+
+
+def run_event_ensemble_case(ref, de, torch, rng):
+    """Events over an ensemble (EventLog) against one reference run per trajectory: an affine plane (located inside the
+    fused / stage kernels) or a sphere (search kernels with the callable in between), recorded or terminal."""
+    n = 10
+    affine = bool(rng.integers(0, 2))
+    terminal = bool(rng.integers(0, 2))
+    level = float(rng.uniform(20.0, 28.0)) if affine else float(rng.uniform(22.0, 34.0))
+    draws = [_draw(rng, "lorenz") for _ in range(n)]
+    y0 = np.stack([d[0] for d in draws], axis=1)
+    consts = draws[0][1]
+
+    def make(xp):
+        if affine:
+            def g(t, y, **k):
+                return y[2] - level
+        else:
+            def g(t, y, **k):
+                return xp.sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]) - level
+        g.is_terminal = terminal
+        g.direction = 1
+        return [g]
+    kw = dict(t=(0.0, 1.5), dt=1e-2, rtol=1e-9, atol=1e-9, constants=consts)
+    a = de.OdeSystem(de.rhs_plugins.lorenz, torch.as_tensor(y0), ensemble=True, device="cuda:0", **kw)
+    a.method = "RK45"
+    a.integrate(events=make(torch))
+    log = a.events
+    t_end = a[-1].t.cpu().numpy()
+    y_end = a[-1].y.cpu().numpy()
+    missing = extra = missed_terminal = 0
+    err = terr = 0.0
+    for i in range(n):
+        r = ref.OdeSystem(_rhs_factory("lorenz", np), y0=y0[:, i].copy(), dense_output=True, **kw)
+        r.method = "RK45"
+        r.integrate(events=make(np))
+        ev_r = sorted(float(e.t) for e in r.events)
+        ev_g = sorted(float(e.t) for e in log.for_trajectory(i))
+        # (events the reference found AFTER the time the engine stopped at a terminal crossing are not comparable)
+        missing += sum(1 for t in ev_r if t <= float(t_end[i]) + 1e-9 and not any(abs(t - u) <= 1e-9 for u in ev_g))
+        extra += max(0, len(ev_g) - len(ev_r))
+        if terminal and t_end[i] < float(r.t[-1]) - 1e-9:
+            missed_terminal += 1                                 # the reference's root finder passed over a crossing (DESIGN K7)
+            continue
+        terr = max(terr, abs(float(t_end[i]) - float(r.t[-1])))
+        yr = np.asarray(r.y[-1], dtype=np.float64)
+        err = max(err, float(np.max(np.abs(y_end[:, i] - yr)) / max(1.0, float(np.max(np.abs(yr))))))
+    return dict(kind="events_ens", affine=affine, terminal=terminal, trajectories=n, ref_events_missing_on_gpu=missing,
+                gpu_events_beyond_ref=extra, reference_missed_terminal=missed_terminal, final_t_err=terr, final_rel_err=err,
+                steps_equal=missing == 0 and terr <= 1e-9)
+
+
 def run_event_case(ref, de, torch, rng):
     """A terminal and a recorded event on the Lorenz system: event times, states and where the integration stops."""
     y0, consts, _ = _draw(rng, "lorenz")
@@ -545,7 +626,7 @@ def main():
     ref = _import_reference()
     rng = np.random.default_rng(args.seed)
     kinds = (["adaptive"] * 8 + ["fixed"] * 3 + ["symplectic"] * 2 + ["backward"] * 2 + ["dense"] * 3 + ["ensemble"] * 1 + ["events"] * 1 +
-             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2 + ["ensemble2"] * 2 + ["shapes"] * 3 + ["events2"] * 1)
+             ["continue"] * 2 + ["solve_ivp"] * 3 + ["richardson"] * 1 + ["switch"] * 2 + ["ensemble2"] * 2 + ["shapes"] * 3 + ["events2"] * 1 + ["nbody"] * 2 + ["events_ens"] * 1)
     if args.only:
         kinds = [k for k in kinds if k in args.only.split(",")]
     rows, failures = [], []
@@ -571,6 +652,10 @@ def main():
                 row = run_shape_case(ref, de, torch, rng)
             elif kind == "events2":
                 row = run_event2_case(ref, de, torch, rng)
+            elif kind == "nbody":
+                row = run_nbody_case(ref, de, torch, rng)
+            elif kind == "events_ens":
+                row = run_event_ensemble_case(ref, de, torch, rng)
             else:
                 row = run_case(ref, de, torch, rng, kind)
         except Exception as e:                                   # noqa: BLE001 -- a crash IS a finding
