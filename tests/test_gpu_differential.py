@@ -1,6 +1,7 @@
 """The engine against the UNMODIFIED reference, live: tools/differential_vs_reference.py draws random problems (systems,
 methods, tolerances, right-hand-side spellings, arithmetic flavours, dense output, continued runs, method switches,
-solve_ivp, Richardson wrappers, ensembles, events) and runs each through the reference's numpy backend (baseline/_ref,
+solve_ivp, Richardson wrappers, ensembles, matrix-valued and long states, callbacks, N-body, events with their records)
+and runs each through the reference's numpy backend (baseline/_ref,
 installed by baseline/install_reference.py; CPU) and through desolver_b200 (cuda:0).
 
 Skipped where baseline/_ref did not travel.  Bars: no crash; EVERY case takes exactly the reference's steps and ends within
@@ -30,7 +31,7 @@ def dv():
 
 
 KINDS = ["adaptive", "adaptive", "fixed", "symplectic", "backward", "dense", "ensemble", "events", "continue", "solve_ivp",
-         "richardson", "switch", "ensemble2"]
+         "richardson", "switch", "ensemble2", "shapes", "events2", "nbody", "events_ens"]
 
 
 def test_random_cases_follow_the_live_reference(dv):
@@ -39,9 +40,10 @@ def test_random_cases_follow_the_live_reference(dv):
     rng = np.random.default_rng(20261020)
     runners = dict(ensemble=mod.run_ensemble_case, events=mod.run_event_case, **{"continue": mod.run_continue_case},
                    solve_ivp=mod.run_solve_ivp_case, richardson=mod.run_richardson_case, switch=mod.run_switch_case,
-                   ensemble2=mod.run_ensemble2_case)
+                   ensemble2=mod.run_ensemble2_case, shapes=mod.run_shape_case, events2=mod.run_event2_case,
+                   nbody=mod.run_nbody_case, events_ens=mod.run_event_ensemble_case)
     rows = []
-    for c in range(6 * len(KINDS)):
+    for c in range(5 * len(KINDS)):
         kind = KINDS[c % len(KINDS)]
         if kind in runners:
             row = runners[kind](ref, de, torch, rng)

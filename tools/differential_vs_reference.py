@@ -667,11 +667,9 @@ def main():
             print(json.dumps(row), file=sys.stderr)
         bar = max(1e-9, 1e-2 * (row.get("tol") or 0.0))          # loose tolerances: step sizes ride on rounding noise
         row["nfev_equal"] = row.get("nfev_ref") == row.get("nfev_gpu")
-        if row.get("api_mismatch"):
-            row["steps_equal_before_api"] = row.get("steps_equal")
-            row["steps_equal"] = False
+        row["api_equal"] = not row.get("api_mismatch")
         if "error" in row or not row.get("steps_equal", True) or not (row.get("final_rel_err", 0.0) <= bar) or \
-                (row.get("steps_equal") and not row["nfev_equal"] and row["kind"] != "richardson"):
+                not row["api_equal"] or (row.get("steps_equal") and not row["nfev_equal"] and row["kind"] != "richardson"):
             # (Richardson wrappers: the reference's basis integrators each evaluate initial_rhs on their first sub-step; the
             # engine's wrapper shares one evaluation -- 2 to 5 evaluations per RUN, states equal to 1e-13)
             failures.append(row)
@@ -685,11 +683,13 @@ def main():
                    skipped=sum("skipped" in r for r in ok),
                    nfev_equal=sum(bool(r.get("nfev_equal")) for r in ok if "nfev_ref" in r),
                    nfev_compared=sum("nfev_ref" in r for r in ok),
+                   api_equal=sum(bool(r.get("api_equal")) for r in ok if "api_mismatch" in r),
+                   api_compared=sum("api_mismatch" in r for r in ok),
                    by_kind={k: dict(cases=sum(r["kind"] == k for r in rows),
                                     steps_equal=sum(bool(r.get("steps_equal")) for r in rows if r["kind"] == k),
                                     final_rel_err_max=max((r["final_rel_err"] for r in ok if r["kind"] == k), default=None))
                             for k in sorted(set(kinds))},
-                   seed=args.seed, failures=failures[:40])
+                   seed=args.seed, failures=failures[:80])
     print(json.dumps(summary, indent=1))
 
 
