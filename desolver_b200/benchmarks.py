@@ -41,3 +41,29 @@ def nbody_ensemble(systems, bodies=64, seed=0):
     qv[:, 1] *= 0.1
     state = np.ascontiguousarray(np.moveaxis(qv, 1, 0))
     return state, np.full(bodies, 1.0 / bodies)
+
+
+# ---- an example of a caller-defined fused device plugin (rhs_plugins.register_device_rhs): the Roessler system ----
+def rossler(t, y, a=0.2, b=0.2, c=5.7):
+    """Roessler attractor, written once for numpy / torch (any trailing ensemble axis) ..."""
+    parts = [-y[1] - y[2], y[0] + a * y[1], b + y[2] * (y[0] - c)]
+    if type(y).__module__.split(".")[0] == "torch":
+        import torch
+        return torch.stack(parts)
+    return np.stack(parts)
+
+
+# ... and once as the CUDA body of the fused kernel's right-hand side (same operations, left to right)
+ROSSLER_BODY = """
+dy[0] = -y[1] - y[2];
+dy[1] = y[0] + p[0] * y[1];
+dy[2] = p[1] + y[2] * (y[0] - p[2]);
+"""
+
+
+def rossler_plugin():
+    """`rossler` tagged with its fused device plugin (built on first use, about a minute; `__graft_entry__.build()`
+    prebuilds it in-tree)."""
+    from . import rhs_plugins
+    return rhs_plugins.register_device_rhs(rossler, ROSSLER_BODY, dim=3, params=("a", "b", "c"),
+                                           defaults=dict(a=0.2, b=0.2, c=5.7), name="rossler")

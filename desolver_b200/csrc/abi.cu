@@ -6,6 +6,8 @@
 #include <new>
 
 #include "plan.h"
+#include <map>
+#include <mutex>
 
 namespace dsb {
 
@@ -46,6 +48,27 @@ const char *dsb_build_info(void)
 
 const char *dsb_last_error(void) { return g_error; }
 
+// ---- right-hand sides compiled OUTSIDE this library (desolver_b200.rhs_plugins.register_device_rhs) ----------------
+// A plug-in shared object instantiates the same kernel templates (erk_fused.cuh, plan.h) for its own Rhs struct and
+// hands over the function that binds them to a plan; dsb_erk_create finds it here by its id.
+namespace {
+struct UserRhs { int dim; bool (*select)(dsb_erk_plan *); };
+std::map<int, UserRhs> g_user_rhs;
+std::mutex g_user_rhs_mutex;
+}
+
+int dsb_rhs_register(int rhs_id, int dim, void *select_fn)
+{
+    if (rhs_id < DSB_RHS_USER_BASE || dim < 1 || !select_fn) {
+        set_error("dsb_rhs_register: rhs_id must be >= %d, dim >= 1, select_fn non-null (rhs_id=%d dim=%d)",
+                  (int)DSB_RHS_USER_BASE, rhs_id, dim);
+        return DSB_ERR_BAD_ARGUMENT;
+    }
+    std::lock_guard<std::mutex> lock(g_user_rhs_mutex);
+    g_user_rhs[rhs_id] = UserRhs{dim, reinterpret_cast<bool (*)(dsb_erk_plan *)>(select_fn)};
+    return DSB_OK;
+}
+
 int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int stages,
                    const double *tableau_intermediate, const double *tableau_final, int final_rows,
                    double order, unsigned flags)
@@ -80,7 +103,12 @@ int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim, int sta
     case DSB_RHS_SHO:    fused = dim == 2 && select_fused_sho(p); break;
     case DSB_RHS_FORCED: fused = dim == 2 && select_fused_forced(p); break;
     case DSB_RHS_DUFFING: fused = dim == 2 && select_fused_duffing(p); break;
-    default: break;
+    default: {
+        std::lock_guard<std::mutex> lock(g_user_rhs_mutex);
+        auto it = g_user_rhs.find(rhs_id);
+        if (it != g_user_rhs.end()) fused = dim == it->second.dim && it->second.select(p);
+        break;
+    }
     }
     if (!fused) p->fused_launch = p->fused_launch_flow = p->fused_launch_events = p->fused_launch_events_dy =
         p->fused_launch_scatter = p->fused_launch_dense = p->fused_launch_multi = nullptr;

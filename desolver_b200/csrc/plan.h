@@ -165,9 +165,16 @@ bool select_fused(dsb_erk_plan *p)
     const bool strict = p->flags & DSB_FLAG_STRICT;
     int per_sm = 0;
     p->fused_static = true;
+#ifdef DSB_SELECT_FAST_ONLY
+    // plug-ins built by rhs_plugins.register_device_rhs: the fast flavour only (half the instantiations; a STRICT system
+    // of such a right-hand side runs on the stage-level kernels)
+    if (strict) return false;
+#define DSB_BIND(TAB) do { bind_fused<RhsT<false>, TAB, false>(p, &per_sm); } while (0)
+#else
 #define DSB_BIND(TAB)                                                                         \
     do { if (strict) bind_fused<RhsT<true>, TAB, true>(p, &per_sm);                           \
          else        bind_fused<RhsT<false>, TAB, false>(p, &per_sm); } while (0)
+#endif
     if (matches_static<CashKarp45>(p)) DSB_BIND(StaticTab<CashKarp45>);
     else if (matches_static<DormandPrince87>(p)) DSB_BIND(StaticTab<DormandPrince87>);
     else if (matches_static<DormandPrince54>(p)) DSB_BIND(StaticTab<DormandPrince54>);

@@ -852,6 +852,8 @@ class OdeSystem(object):
             return None
         if self.integrator.has_vector_tolerances:          # one tolerance per component: stage-level kernels
             return None
+        if self.strict and str(rhs.device_plugin).startswith("user:"):
+            return None                                     # caller-built plug-ins carry the fast flavour only
         return pid, tuple(rhs.plugin_params), dict(rhs.plugin_defaults)
 
     def _param_tensors(self, names, defaults):

@@ -214,3 +214,105 @@ FUSED = ("lorenz", "van_der_pol", "harmonic_oscillator", "forced", "duffing")
 
 BUILTIN = {f.device_plugin: f for f in (lorenz, van_der_pol, harmonic_oscillator, linear, nbody, forced, duffing)}
 BUILTIN["forced_oscillator"] = forced_oscillator
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Right-hand sides of the CALLER as fused device plugins.
+#
+# The reference integrates any Python callable (differential_system.py:338-344); here an untagged callable runs between
+# the stage-level kernels (one CUDA graph per lock-step round: 158 ms for the 2^20-trajectory Lorenz ensemble).  A callable
+# whose arithmetic the caller ALSO writes down as a CUDA expression list gets the persistent thread-per-trajectory kernel
+# instead (3.5 ms for the same ensemble): the body is compiled with the kernel templates of this library
+# (csrc/erk_fused.cuh, csrc/plan.h) into a plug-in shared object of its own, registered with the library under a new
+# right-hand-side id (dsb_rhs_register), and the callable is tagged like the built-in ones.
+_USER_PLUGINS = {}          # source hash -> (rhs id, ctypes handle of the plug-in)
+_USER_BASE = 1000           # DSB_RHS_USER_BASE
+
+_PLUGIN_SOURCE = """// generated by desolver_b200.rhs_plugins.register_device_rhs -- %(name)s
+#include <cstdarg>
+#include <cstdio>
+#define DSB_SELECT_FAST_ONLY 1
+#include "plan.h"
+namespace dsb {
+void set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\\n', stderr); }
+template <bool STRICT>
+struct UserRhs {
+    static constexpr int ID = %(base)d, DIM = %(dim)d, NPARAM = %(nparam)d;
+    static constexpr bool TIME = %(time)s;
+    static __device__ __forceinline__ void prepare(double (&)[NPARAM > 0 ? NPARAM : 1]) {}
+    static __device__ __forceinline__ void eval(%(targ)sconst double (&y)[DIM], const double (&p)[NPARAM > 0 ? NPARAM : 1],
+                                                double (&dy)[DIM])
+    {
+%(body)s
+    }
+};
+}  // namespace dsb
+extern "C" __attribute__((visibility("default"))) bool dsb_user_rhs_select(dsb_erk_plan *p)
+{
+    return dsb::select_fused<dsb::UserRhs>(p);
+}
+"""
+
+
+def register_device_rhs(fn, body, dim, params=(), defaults=None, time_dependent=False, name=None, build_dir=None):
+    """Tags the callable `fn(t, y, **constants)` with a fused device plugin compiled from `body`.
+
+    `body`: CUDA C++ statements that fill `dy[0..dim)` from `y[0..dim)`, the per-trajectory parameters `p[0..len(params))`
+    (the `constants` entries named in `params`, in that order; a (N,) tensor is per trajectory, a scalar is shared) and, if
+    `time_dependent`, the stage time `t` -- the same arithmetic as `fn`, which stays the definition of the system: the
+    stage-level kernels (per-component tolerances, events with dense output, STRICT arithmetic, schemes without a fused
+    instantiation) and the reference itself keep calling it.  The plug-in is built once with nvcc (about a minute: every
+    tableau / event / dense-output / multi-stop instantiation of the kernel) into `build_dir` (default: `_plugins/` next
+    to this file, so a prebuilt one travels with the tree) and reused by its source hash.  Returns `fn`."""
+    import ctypes
+    import hashlib
+    import os
+    import shutil
+    import subprocess
+    from .backend import cuda_backend as cb
+    global FUSED
+    dim, params = int(dim), tuple(params)
+    if dim < 1 or len(params) > 6:
+        raise ValueError("register_device_rhs: dim >= 1 and at most 6 per-trajectory parameters (DSB_MAX_PARAMS)")
+    name = name or getattr(fn, "__name__", "rhs")
+    if not name.isidentifier():
+        raise ValueError("register_device_rhs: name must be an identifier")
+    pkg = os.path.dirname(os.path.abspath(__file__))
+    src = _PLUGIN_SOURCE % dict(name=name, base=_USER_BASE, dim=dim, nparam=len(params), time="true" if time_dependent else "false",
+                                targ="double t, " if time_dependent else "",
+                                body="\n".join("        " + line.strip() for line in body.strip().splitlines()))
+    headers = b"".join(open(os.path.join(pkg, "csrc", h), "rb").read() for h in
+                       ("plan.h", "erk_fused.cuh", "common.cuh", "fastmath.cuh", "factor_table.h", "tableau_static.cuh"))
+    key = hashlib.sha256(src.encode() + headers).hexdigest()[:16]
+    if key not in _USER_PLUGINS:
+        out_dir = build_dir or os.path.join(pkg, "_plugins")
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, "dsb_rhs_%s_%s.so" % (name, key))
+        if not os.path.exists(so):
+            nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+            cu = os.path.join(out_dir, "dsb_rhs_%s_%s.cu" % (name, key))
+            with open(cu, "w") as f:
+                f.write(src)
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+                   "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-diag-suppress", "128",
+                   "-I", os.path.join(pkg, "csrc"), "-I", os.path.join(os.path.dirname(pkg), "include"), "-shared",
+                   "-o", so + ".tmp", cu, "-lcudart"]
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            if res.returncode != 0:
+                raise RuntimeError("register_device_rhs: nvcc failed for %s:\n%s" % (cu, res.stdout.decode()[-4000:]))
+            os.replace(so + ".tmp", so)
+        plug = ctypes.CDLL(so)
+        rhs_id = _USER_BASE + len(_USER_PLUGINS)
+        L = cb.lib()
+        L.dsb_rhs_register.restype = ctypes.c_int
+        L.dsb_rhs_register.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        cb.check(L.dsb_rhs_register(rhs_id, dim, ctypes.cast(plug.dsb_user_rhs_select, ctypes.c_void_p)), "dsb_rhs_register")
+        _USER_PLUGINS[key] = (rhs_id, plug)
+    rhs_id = _USER_PLUGINS[key][0]
+    tag = "user:%s:%s" % (name, key)
+    fn.device_plugin, fn.plugin_id, fn.plugin_params = tag, rhs_id, params
+    fn.plugin_defaults = dict(defaults or {})
+    fn.plugin_dim = (dim,)
+    if tag not in FUSED:
+        FUSED = FUSED + (tag,)
+    return fn

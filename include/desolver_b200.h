@@ -90,6 +90,15 @@ DSB_API int dsb_erk_create(dsb_erk_handle *out, int device, int rhs_id, int dim,
                    int final_rows, double order, unsigned flags);
 DSB_API int dsb_erk_destroy(dsb_erk_handle h);
 
+/* Right-hand sides compiled outside this library.  The reference takes ANY Python callable (differential_system.py:
+ * 338-344); a callable the caller also provides as CUDA source is compiled, with the kernel templates of this library
+ * (csrc/erk_fused.cuh, csrc/plan.h), into a plug-in shared object of its own and registered here under an id
+ * >= DSB_RHS_USER_BASE; dsb_erk_create(rhs_id = that id) then binds the persistent fused kernels of THAT right-hand side
+ * (desolver_b200.rhs_plugins.register_device_rhs builds the plug-in with nvcc and calls this).  `select_fn` is the
+ * plug-in's `bool select(dsb_erk_plan *)`: it must come from a build against the same headers as this library. */
+#define DSB_RHS_USER_BASE 1000
+DSB_API int dsb_rhs_register(int rhs_id, int dim, void *select_fn);
+
 /* Dense output / per-step history: the paged structure-of-arrays node store (csrc/node_store.cu).  A node is
  * (trajectory, ordinal k, t, y[dim], f[dim] = rhs(t, y)) -- what the reference keeps per accepted step as one
  * CubicHermiteInterp object (integrators/integrator_types.py:109-119, differential_system.py:1020-1023) and as one row
