@@ -67,3 +67,23 @@ def rossler_plugin():
     from . import rhs_plugins
     return rhs_plugins.register_device_rhs(rossler, ROSSLER_BODY, dim=3, params=("a", "b", "c"),
                                            defaults=dict(a=0.2, b=0.2, c=5.7), name="rossler")
+
+
+# ---- a second example: time-dependent, two components, transcendental functions (the damped driven pendulum) ----
+def driven_pendulum(t, y, q=0.5, f=1.2, w=2.0 / 3.0):
+    if type(y).__module__.split(".")[0] == "torch":
+        import torch
+        return torch.stack([y[1], -torch.sin(y[0]) - q * y[1] + f * torch.cos(w * t)])
+    return np.stack([y[1], -np.sin(y[0]) - q * y[1] + f * np.cos(w * t)])
+
+
+DRIVEN_PENDULUM_BODY = """
+dy[0] = y[1];
+dy[1] = -sin(y[0]) - p[0] * y[1] + p[1] * cos(p[2] * t);
+"""
+
+
+def driven_pendulum_plugin():
+    from . import rhs_plugins
+    return rhs_plugins.register_device_rhs(driven_pendulum, DRIVEN_PENDULUM_BODY, dim=2, params=("q", "f", "w"),
+                                           defaults=dict(q=0.5, f=1.2, w=2.0 / 3.0), time_dependent=True, name="driven_pendulum")

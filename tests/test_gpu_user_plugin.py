@@ -99,6 +99,33 @@ def test_user_plugin_with_dense_output_events_and_single_systems():
     assert len(s) == len(b)
 
 
+def test_time_dependent_user_plugin_with_transcendental_functions():
+    """TIME = true plug-in (stage time t + c_s h), sin / cos in the body, per-trajectory and shared parameters, two ids
+    registered side by side."""
+    de = _de()
+    pend = de.benchmarks.driven_pendulum_plugin()
+    ross = de.benchmarks.rossler_plugin()
+    assert pend.plugin_id != ross.plugin_id and pend.plugin_id >= 1000
+    n = 4096
+    rng = np.random.default_rng(2)
+    y0 = torch.as_tensor(rng.uniform([-3, -2], [3, 2], (n, 2)).T.copy())
+    f = torch.as_tensor(rng.uniform(0.5, 1.5, n)).cuda()
+    kw = dict(t=(1.0, 9.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, constants=dict(q=0.5, f=f, w=2.0 / 3.0))
+
+    def untagged(t, y, q, f, w):
+        return torch.stack([y[1], -torch.sin(y[0]) - q * y[1] + f * torch.cos(w * t)])
+    a = de.OdeSystem(pend, y0, **kw)
+    b = de.OdeSystem(untagged, y0, **kw)
+    for s in (a, b):
+        s.method = "RK45"
+        s.integrate()
+    assert a._launches <= 2 < b._launches
+    same = float(((a.accepted == b.accepted) & (a.rejected == b.rejected)).double().mean())
+    err = float(((a[-1].y - b[-1].y).abs().amax(0) / b[-1].y.abs().amax(0).clamp_min(1.0)).max())
+    print("driven pendulum plug-in: counts identical %.5f, max rel difference %.3g" % (same, err))
+    assert same >= 0.999 and err <= 1e-9                       # (device sin / cos against torch's: last-ulp differences)
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "desolver")), reason="baseline/_ref not present")
 def test_user_plugin_against_the_live_reference():
     de = _de()
