@@ -146,3 +146,20 @@ def test_user_plugin_against_the_live_reference():
         r.integrate()
         assert len(r) - 1 == acc[i]
         assert np.max(np.abs(y[:, i] - np.asarray(r.y[-1]))) <= 1e-10 * max(1.0, np.max(np.abs(r.y[-1])))
+
+
+def test_user_plugin_streams_a_host_resident_ensemble():
+    """The flow-controlled instantiation (dsb_erk_run_host) exists for a plug-in too: pinned host y0 in, host results out,
+    bit for bit the device-resident run."""
+    de = _de()
+    rossler = de.benchmarks.rossler_plugin()
+    n = 50000 + 3
+    y0 = torch.as_tensor(_ensemble(n, seed=5))
+    kw = dict(t=(0.0, 4.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True)
+    a = de.OdeSystem(rossler, y0.cuda(), **kw)
+    a.method = "RK45"
+    a.integrate()
+    h = de.OdeSystem(rossler, y0.pin_memory(), host_io=True, device="cuda:0", **kw)
+    h.method = "RK45"
+    h.integrate()
+    assert not h[-1].y.is_cuda and torch.equal(h[-1].y, a[-1].y.cpu()) and torch.equal(h.accepted.cpu(), a.accepted.cpu())
