@@ -1955,13 +1955,36 @@ class OdeSystem(object):
         raise KeyError("time indexing needs dense_output=True in the ensemble engine")
 
     def __str__(self):
-        return "y({t0}) = {y0}\ndy = {eq}\ny({t}) = {y}\n".format(t0=self.__t0, y0=self[0].y, eq=str(self.equ_rhs),
+        """Equations, initial conditions, current states, constants and time limits (reference `:1146-1161`)."""
+        out = "y({t0}) = {y0}\ndy = {eq}\ny({t}) = {y}\n".format(t0=self.__t0, y0=self[0].y, eq=str(self.equ_rhs),
                                                                  t=self[-1].t, y=self[-1].y)
+        if self.constants:
+            out += "\nThe constants that have been defined for this system are: \n" + str(self.constants)
+        out += "\nThe time limits for this system are:\n"
+        out += "t0 = {}, tf = {}, t_current = {}, step_size = {}".format(self.__t0, self.__tf, self[-1].t, self.dt)
+        return out
+
+    def _summary_rows(self):
+        rows = [("message", self.integration_status), ("nfev", self.nfev), ("njev", self.njev),
+                ("sol", self.sol if self.__dense_output else None), ("t0", self.__t0), ("tf", self.__tf)]
+        if self.ensemble:
+            rows += [("trajectories", self.n_traj), ("method", self.__method.__name__)]
+        return rows
 
     def __repr__(self):
-        return "\n".join(["{:>10}: {}".format(k, v) for k, v in (
-            ("message", self.integration_status), ("nfev", self.nfev), ("njev", self.njev), ("t0", self.__t0),
-            ("tf", self.__tf), ("trajectories", self.n_traj), ("method", self.__method.__name__))])
+        """The reference's summary (`:1103-1115`); an ensemble prints its size instead of every state."""
+        rows = ["{:>10}: {}".format(k, v) for k, v in self._summary_rows()]
+        if not self.ensemble:
+            rows += ["{:>10}: {}".format("y0", self[0].y), "{:>10}: {}     ".format("Equations", repr(self.equ_rhs)),
+                     "{:>10}: {}".format("t", self.t), "{:>10}: {}".format("y", self.y)]
+        return "\n".join(rows)
+
+    def _repr_markdown_(self):
+        """Notebook rendering (reference `:1117-1144`)."""
+        head = "  \n".join("{:>10}: {}".format(k, v) for k, v in self._summary_rows())
+        eq = self.equ_rhs._repr_markdown_() if hasattr(self.equ_rhs, "_repr_markdown_") else str(self.equ_rhs)
+        tail = "" if self.ensemble else "```  \n{:>10}: {}  \n{:>10}: {}  \n```\n".format("t", self.t, "y", self.y)
+        return "```\n{}  \n{:>10}: \n```  \n{}\n \n{}".format(head, "Equations", eq, tail)
 
 
 def solve_ivp(fun, t_span, y0, method="RK45", t_eval=None, dense_output=False, events=None, vectorized=False, args=None,
