@@ -87,3 +87,19 @@ def driven_pendulum_plugin():
     from . import rhs_plugins
     return rhs_plugins.register_device_rhs(driven_pendulum, DRIVEN_PENDULUM_BODY, dim=2, params=("q", "f", "w"),
                                            defaults=dict(q=0.5, f=1.2, w=2.0 / 3.0), time_dependent=True, name="driven_pendulum")
+
+
+# ---- a third example, WITHOUT a hand-written body: `register_device_rhs(fn, dim=...)` evaluates the callable once on
+# symbolic scalars (rhs_plugins.trace_body) and compiles what it recorded -- the Brusselator ----
+def brusselator(t, y, a=1.0, b=3.0):
+    x, v = y[0], y[1]
+    parts = [a + x ** 2 * v - (b + 1.0) * x, b * x - x ** 2 * v]
+    if type(x).__module__.split(".")[0] == "torch":
+        import torch
+        return torch.stack(parts)
+    return np.stack(parts) if isinstance(x, np.ndarray) or np.isscalar(x) else parts
+
+
+def brusselator_plugin():
+    from . import rhs_plugins
+    return rhs_plugins.register_device_rhs(brusselator, dim=2, params=("a", "b"), defaults=dict(a=1.0, b=3.0), name="brusselator")

@@ -254,12 +254,118 @@ extern "C" __attribute__((visibility("default"))) bool dsb_user_rhs_select(dsb_e
 """
 
 
-def register_device_rhs(fn, body, dim, params=(), defaults=None, time_dependent=False, name=None, build_dir=None):
+class _Sym(object):
+    """One scalar of the right-hand side while `trace_body` evaluates the caller's function: every operator returns the
+    CUDA expression of its result, in the order Python evaluates it (so the statement list repeats the callable's
+    arithmetic operation for operation)."""
+    __slots__ = ("code",)
+    __array_priority__ = 1000
+    _FUNCS = ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh", "atan", "asin", "acos", "abs", "exp2", "log2",
+              "log10", "log1p", "expm1", "atan2", "pow", "fmin", "fmax")
+    _ALIASES = dict(arctan="atan", arcsin="asin", arccos="acos", arctan2="atan2", absolute="abs", fabs="abs", power="pow",
+                    minimum="fmin", maximum="fmax", add="+", subtract="-", multiply="*", divide="/", true_divide="/", mul="*",
+                    sub="-", div="/", neg="neg", negative="neg", square="square", reciprocal="reciprocal")
+
+    def __init__(self, code):
+        self.code = code
+
+    @staticmethod
+    def lit(v):
+        if isinstance(v, _Sym):
+            return v.code
+        if hasattr(v, "item") and getattr(v, "ndim", 1) == 0:
+            v = v.item()
+        if isinstance(v, bool) or not isinstance(v, (int, float)):
+            raise TypeError("trace_body: cannot take %r into a device expression (numbers and state / parameter entries only)"
+                            % (type(v).__name__,))
+        return "(%s)" % repr(float(v)) if v < 0 else repr(float(v))
+
+    def _bin(self, op, other, swap=False):
+        a, b = (self.lit(other), self.code) if swap else (self.code, self.lit(other))
+        return _Sym("(%s %s %s)" % (a, op, b))
+
+    def __add__(self, o): return self._bin("+", o)
+    def __radd__(self, o): return self._bin("+", o, True)
+    def __sub__(self, o): return self._bin("-", o)
+    def __rsub__(self, o): return self._bin("-", o, True)
+    def __mul__(self, o): return self._bin("*", o)
+    def __rmul__(self, o): return self._bin("*", o, True)
+    def __truediv__(self, o): return self._bin("/", o)
+    def __rtruediv__(self, o): return self._bin("/", o, True)
+    def __neg__(self): return _Sym("(-%s)" % self.code)
+    def __pos__(self): return self
+    def __abs__(self): return _Sym("fabs(%s)" % self.code)
+
+    def __pow__(self, o):
+        if isinstance(o, (int, float)) and float(o) == int(o) and 1 <= int(o) <= 4:       # x**2 = x*x like numpy / torch
+            return _Sym("(" + " * ".join([self.code] * int(o)) + ")")
+        return _Sym("pow(%s, %s)" % (self.code, self.lit(o)))
+
+    def __rpow__(self, o):
+        return _Sym("pow(%s, %s)" % (self.lit(o), self.code))
+
+    @classmethod
+    def call(cls, name, args):
+        name = cls._ALIASES.get(name, name)
+        a = [cls.lit(v) for v in args]
+        if name in ("+", "-", "*", "/") and len(a) == 2:
+            return _Sym("(%s %s %s)" % (a[0], name, a[1]))
+        if name == "neg":
+            return _Sym("(-%s)" % a[0])
+        if name == "square":
+            return _Sym("(%s * %s)" % (a[0], a[0]))
+        if name == "reciprocal":
+            return _Sym("(1.0 / %s)" % a[0])
+        if name == "abs":
+            return _Sym("fabs(%s)" % a[0])
+        if name in cls._FUNCS:
+            return _Sym("%s(%s)" % (name, ", ".join(a)))
+        raise NotImplementedError("trace_body: no device counterpart for %r" % name)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        return self.call(ufunc.__name__, inputs)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        name = getattr(func, "__name__", str(func))
+        if name in ("stack", "cat", "concatenate") and not kwargs:
+            return list(args[0])
+        if name in ("as_tensor", "tensor", "asarray"):
+            return args[0]
+        return cls.call(name, args)
+
+
+def trace_body(fn, dim, params=(), time_dependent=None):
+    """The CUDA statement list of `fn(t, y, **constants)`: the callable is evaluated ONCE on symbolic scalars (`y[i]`, `p[k]`,
+    `t`), whose operators record the expression they compute.  Works for callables made of arithmetic operators, `**` with
+    small integer exponents, and elementwise numpy / torch functions with a CUDA namesake (sin, cos, exp, log, sqrt, tanh,
+    ...), finished by `stack([...])` (numpy or torch) or a list -- i.e. no data-dependent control flow, no reductions.
+    Returns (body, time_dependent)."""
+    y = [_Sym("y[%d]" % i) for i in range(int(dim))]
+    consts = {name: _Sym("p[%d]" % k) for k, name in enumerate(params)}
+    out = fn(_Sym("t"), y, **consts)
+    out = list(out.tolist() if hasattr(out, "tolist") else out)
+    if len(out) != int(dim):
+        raise ValueError("trace_body: the callable returned %d components for a state of %d" % (len(out), int(dim)))
+    lines = ["dy[%d] = %s;" % (i, _Sym.lit(v)) for i, v in enumerate(out)]
+    uses_t = any(_uses_time(_Sym.lit(v)) for v in out)
+    return "\n".join(lines), (uses_t if time_dependent is None else bool(time_dependent))
+
+
+def _uses_time(code):
+    import re
+    return re.search(r"(?<![A-Za-z0-9_\]])t(?![A-Za-z0-9_(\[])", code) is not None
+
+
+def register_device_rhs(fn, body=None, dim=None, params=(), defaults=None, time_dependent=None, name=None, build_dir=None):
     """Tags the callable `fn(t, y, **constants)` with a fused device plugin compiled from `body`.
 
     `body`: CUDA C++ statements that fill `dy[0..dim)` from `y[0..dim)`, the per-trajectory parameters `p[0..len(params))`
     (the `constants` entries named in `params`, in that order; a (N,) tensor is per trajectory, a scalar is shared) and, if
-    `time_dependent`, the stage time `t` -- the same arithmetic as `fn`, which stays the definition of the system: the
+    `time_dependent`, the stage time `t`; `body=None` writes them by evaluating `fn` once on symbolic scalars
+    (`trace_body`: arithmetic and elementwise functions only) -- the same arithmetic as `fn`, which stays the definition of the system: the
     stage-level kernels (per-component tolerances, events with dense output, STRICT arithmetic, schemes without a fused
     instantiation) and the reference itself keep calling it.  The plug-in is built once with nvcc (about a minute: every
     tableau / event / dense-output / multi-stop instantiation of the kernel) into `build_dir` (default: `_plugins/` next
@@ -271,7 +377,12 @@ def register_device_rhs(fn, body, dim, params=(), defaults=None, time_dependent=
     import subprocess
     from .backend import cuda_backend as cb
     global FUSED
+    if dim is None:
+        raise ValueError("register_device_rhs: dim (components of ONE trajectory's state) is required")
     dim, params = int(dim), tuple(params)
+    if body is None:
+        body, time_dependent = trace_body(fn, dim, params, time_dependent)
+    time_dependent = bool(time_dependent)
     if dim < 1 or len(params) > 6:
         raise ValueError("register_device_rhs: dim >= 1 and at most 6 per-trajectory parameters (DSB_MAX_PARAMS)")
     name = name or getattr(fn, "__name__", "rhs")

@@ -148,6 +148,37 @@ def test_user_plugin_against_the_live_reference():
         assert np.max(np.abs(y[:, i] - np.asarray(r.y[-1]))) <= 1e-10 * max(1.0, np.max(np.abs(r.y[-1])))
 
 
+def test_traced_plugin_needs_no_cuda_source():
+    """`register_device_rhs(fn, dim=...)` without a body: the callable is evaluated once on symbolic scalars and the
+    recorded expressions become the kernel's right-hand side (rhs_plugins.trace_body)."""
+    de = _de()
+    body, timed = de.rhs_plugins.trace_body(de.benchmarks.brusselator, 2, ("a", "b"))
+    assert body == ("dy[0] = ((p[0] + ((y[0] * y[0]) * y[1])) - ((p[1] + 1.0) * y[0]));\n"
+                    "dy[1] = ((p[1] * y[0]) - ((y[0] * y[0]) * y[1]));") and not timed
+    assert de.rhs_plugins.trace_body(de.benchmarks.driven_pendulum, 2, ("q", "f", "w"))[1]            # uses t
+    bruss = de.benchmarks.brusselator_plugin()
+    n = 8192
+    rng = np.random.default_rng(4)
+    y0 = torch.as_tensor(rng.uniform(0.2, 3.0, (2, n)))
+    b_par = torch.as_tensor(rng.uniform(1.5, 3.5, n)).cuda()
+    kw = dict(t=(0.0, 8.0), dt=1e-2, rtol=1e-9, atol=1e-9, ensemble=True, constants=dict(a=1.0, b=b_par))
+
+    def untagged(t, y, a, b):
+        return torch.stack([a + y[0] ** 2 * y[1] - (b + 1.0) * y[0], b * y[0] - y[0] ** 2 * y[1]])
+    u = de.OdeSystem(bruss, y0, **kw)
+    v = de.OdeSystem(untagged, y0, **kw)
+    for s in (u, v):
+        s.method = "RK45"
+        s.integrate()
+    assert u._launches <= 2 < v._launches
+    same = float(((u.accepted == v.accepted) & (u.rejected == v.rejected)).double().mean())
+    err = float(((u[-1].y - v[-1].y).abs().amax(0) / v[-1].y.abs().amax(0).clamp_min(1.0)).max())
+    print("traced Brusselator plug-in: counts identical %.5f, max rel difference %.3g" % (same, err))
+    assert same >= 0.999 and err <= 1e-9
+    with pytest.raises(NotImplementedError):
+        de.rhs_plugins.trace_body(lambda t, y: torch.stack([torch.cumsum(y[0], 0), y[1]]), 2)
+
+
 def test_user_plugin_streams_a_host_resident_ensemble():
     """The flow-controlled instantiation (dsb_erk_run_host) exists for a plug-in too: pinned host y0 in, host results out,
     bit for bit the device-resident run."""
