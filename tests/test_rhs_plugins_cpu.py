@@ -60,3 +60,40 @@ def test_benchmark_inputs_are_prefix_stable():
     assert np.allclose(A + A.T, -0.2 * np.eye(64))                     # near-skew with -0.1 I damping
     st, m = bm.nbody_ensemble(5, bodies=16)
     assert st.shape == (2, 5, 16, 3) and np.isclose(m.sum(), 1.0)
+
+
+def test_trace_body_records_the_callables_arithmetic(tmp_path):
+    """rhs_plugins.trace_body: the statement list recorded from a callable is plain C -- compiled here with gcc (no FMA
+    contraction) and compared with the callable itself at random points: the same operations in the same order, so the
+    results agree to the last bit for pure arithmetic, and to an ulp of libm vs numpy for sin / cos / exp / tanh."""
+    import ctypes
+    import subprocess
+    from desolver_b200 import benchmarks as bm
+    from desolver_b200 import rhs_plugins as rp
+
+    def mixed(t, y, k, c):
+        return np.stack([y[1] * 2.0 - y[2] / (1.0 + y[0] ** 2), -k * np.sin(y[0]) + np.exp(-0.5 * t) * np.tanh(y[2] / c),
+                         abs(y[0]) ** 0.5 - (y[1] - 3.0) ** 3 + np.sqrt(y[2] * y[2] + 1.0)])
+    cases = [(bm.rossler, 3, ("a", "b", "c"), 0), (bm.driven_pendulum, 2, ("q", "f", "w"), 1), (bm.brusselator, 2, ("a", "b"), 0),
+             (mixed, 3, ("k", "c"), 1)]
+    rng = np.random.default_rng(0)
+    for idx, (fn, dim, params, ulps) in enumerate(cases):
+        body, timed = rp.trace_body(fn, dim, params)
+        assert timed == (fn in (bm.driven_pendulum, mixed))
+        src = tmp_path / ("body%d.c" % idx)
+        src.write_text("#include <math.h>\nvoid f(double t, const double *y, const double *p, double *dy)\n{\n%s\n}\n" % body)
+        so = tmp_path / ("body%d.so" % idx)
+        subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(src), "-lm"], check=True)
+        f = ctypes.CDLL(str(so)).f
+        f.argtypes = [ctypes.c_double] + [np.ctypeslib.ndpointer(dtype=np.float64)] * 3
+        for _ in range(200):
+            t, y, p = float(rng.uniform(0, 3)), rng.uniform(-2, 2, dim), rng.uniform(0.3, 3.0, len(params))
+            want = np.asarray(fn(t, y, **dict(zip(params, p))), dtype=np.float64)
+            got = np.empty(dim)
+            f(t, y, p, got)
+            # pure arithmetic: bit for bit; with libm functions in the terms: a few ulps of the TERMS (values here are O(10))
+            assert np.all(np.abs(got - want) <= ulps * 2e-14), (fn.__name__, got, want)
+    with pytest.raises(NotImplementedError):
+        rp.trace_body(lambda t, y: np.stack([np.cumsum(np.asarray(y))[0], y[1]]), 2)
+    with pytest.raises(ValueError):
+        rp.trace_body(lambda t, y: np.stack([y[0]]), 2)
