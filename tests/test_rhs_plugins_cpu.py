@@ -2,6 +2,7 @@
 fixtures) agree with the oracle's C right-hand sides, DiffRHS forwards the plugin tag, benchmark inputs are
 prefix-stable."""
 import numpy as np
+import pytest
 
 from desolver_b200 import benchmarks as bm
 from desolver_b200 import rhs_plugins as rp
@@ -94,6 +95,6 @@ def test_trace_body_records_the_callables_arithmetic(tmp_path):
             # pure arithmetic: bit for bit; with libm functions in the terms: a few ulps of the TERMS (values here are O(10))
             assert np.all(np.abs(got - want) <= ulps * 2e-14), (fn.__name__, got, want)
     with pytest.raises(NotImplementedError):
-        rp.trace_body(lambda t, y: np.stack([np.cumsum(np.asarray(y))[0], y[1]]), 2)
+        rp.trace_body(lambda t, y: np.stack([np.sign(y[0]), y[1]]), 2)        # no device counterpart registered
     with pytest.raises(ValueError):
         rp.trace_body(lambda t, y: np.stack([y[0]]), 2)
