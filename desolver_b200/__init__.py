@@ -16,6 +16,8 @@ from . import rhs_plugins
 from . import benchmarks
 from . import distributed
 from . import events
+from . import utilities
+from . import differential_system
 from .differential_system import DiffRHS, OdeSystem, DenseOutput, StateTuple, rhs_prettifier, solve_ivp
 from .integrators import available_methods
 

@@ -109,3 +109,17 @@ def test_installed_reference_is_the_unmodified_tree():
     tree = install_reference.install()
     assert tree is not None and os.path.isdir(os.path.join(tree, "desolver"))
     assert install_reference._same_tree(os.path.join(REF, "desolver"), os.path.join(tree, "desolver"))
+
+
+def test_utilities_lookups_equal_the_references(ref):
+    """`desolver_b200.utilities.search_bisection(_vec)` against `desolver.utilities` on sorted arrays, including the edges
+    and exact hits."""
+    import desolver_b200 as b2
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        arr = np.sort(rng.uniform(-3, 3, int(rng.integers(2, 40))))
+        vals = np.concatenate([rng.uniform(-4, 4, 30), arr[:3], [arr[0], arr[-1]]])
+        for v in vals:
+            assert b2.utilities.search_bisection(arr, v) == ref.utilities.search_bisection(arr, v)
+        assert np.array_equal(b2.utilities.search_bisection_vec(arr, vals), ref.utilities.search_bisection_vec(arr, vals))
+    assert hasattr(b2, "utilities") and hasattr(b2, "differential_system") and b2.utilities.CubicHermiteInterp is not None
