@@ -13,6 +13,7 @@
 // (integrator_types.py:359-362).  Time advances by tableau column 1 (:412).
 #include <math_constants.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -144,6 +145,137 @@ __global__ void nbody_symplectic_kernel(dsb_symp_run_args a, SympTableau T)
             a.y[(long long)(nb * 3 + i * 3 + k) * n + sys] = v0[k];
         }
         if (i == 0) {
+            a.t[sys] = t;
+            a.dt[sys] = dt;
+            if (a.steps) a.steps[sys] += steps;
+            bool more = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32);
+            if (a.status) a.status[sys] = more ? (int)DSB_TRAJ_RUNNING : (int)DSB_TRAJ_DONE;
+        }
+    }
+}
+
+#ifndef DSB_NBODY_X2_MINB
+#define DSB_NBODY_X2_MINB 3
+#endif
+// ------------------------------------------------------------------------------------------ (A2) two bodies per thread
+// The same loop with bodies i and i + nb/2 in ONE thread (nb even): every partner (x, y, z, m) read from shared memory
+// serves two interactions, which halves the LDS.128 / address / loop instructions per pair (7 -> ~4 non-FP64 issue slots
+// next to the 16 FP64 ones).  Each body's arithmetic -- operations and the left-to-right order over j -- is that of the
+// kernel above, so the results are identical bit for bit.
+template <bool STRICT>
+__global__ void __launch_bounds__(128, DSB_NBODY_X2_MINB) nbody_symplectic_kernel_x2(dsb_symp_run_args a, SympTableau T)
+{
+    using A = Ar<STRICT>;
+    extern __shared__ double4 smem4[];
+    const int nb = a.bodies, half = nb >> 1;
+    const int spb = blockDim.y;
+    double4 *sq = smem4 + (size_t)threadIdx.y * nb;
+    const long long sys = (long long)blockIdx.x * spb + threadIdx.y;
+    const int i0 = threadIdx.x, i1 = threadIdx.x + half;
+    const bool valid = sys < a.n;
+    const long long n = a.n;
+    const long long s_ = valid ? sys : 0;
+    const double m0 = a.masses[i0], m1 = a.masses[i1];
+
+    double q0[2][3], v0[2][3];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int i = b ? i1 : i0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            q0[b][k] = a.y[(long long)(i * 3 + k) * n + s_];
+            v0[b][k] = a.y[(long long)(nb * 3 + i * 3 + k) * n + s_];
+        }
+    }
+    double t = a.t[s_], dt = a.dt[s_];
+    const double tf = a.tf;
+    int steps = 0;
+    bool go = valid;
+    if (a.first_call) {
+        double span = tf - t;
+        if (fabs(span) < DSB_EPS4) go = false;
+        else {
+            if (dt != 0.0 && ((dt > 0.0) != (span > 0.0))) dt = -dt;
+            if (fabs(dt) > fabs(span)) dt = copysign(fabs(span) * 0.5, span);
+        }
+    }
+    for (;;) {
+        bool more = go && (dt != 0.0) && (fabs(tf - t) >= DSB_EPS32) && (a.max_steps < 0 || steps < a.max_steps);
+        if (!__syncthreads_or(more)) break;
+        const bool final_step = fabs(dt + t) > fabs(tf);
+        const double h = final_step ? (tf - t) : dt;
+        double dq[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, dv[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+        for (int s = 0; s < T.stages; ++s) {
+            const double c1 = T.drift[s], c2 = T.kick[s];
+            double vcur[2][3];
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) vcur[b][k] = A::add(v0[b][k], dv[b][k]);
+            if (c2 != 0.0) {
+                const double ax0 = A::add(q0[0][0], dq[0][0]), ay0 = A::add(q0[0][1], dq[0][1]), az0 = A::add(q0[0][2], dq[0][2]);
+                const double ax1 = A::add(q0[1][0], dq[1][0]), ay1 = A::add(q0[1][1], dq[1][1]), az1 = A::add(q0[1][2], dq[1][2]);
+                sq[i0] = make_double4(ax0, ay0, az0, m0);
+                sq[i1] = make_double4(ax1, ay1, az1, m1);
+                __syncthreads();
+                double fx0 = 0.0, fy0 = 0.0, fz0 = 0.0, fx1 = 0.0, fy1 = 0.0, fz1 = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < nb; ++j) {
+                    const double4 pj = sq[j];
+                    const double dx0 = A::sub(pj.x, ax0), dy0 = A::sub(pj.y, ay0), dz0 = A::sub(pj.z, az0);
+                    const double dx1 = A::sub(pj.x, ax1), dy1 = A::sub(pj.y, ay1), dz1 = A::sub(pj.z, az1);
+                    double w0, w1;
+                    if (STRICT) {
+                        double r0 = A::add(A::add(A::add(A::mul(dx0, dx0), A::mul(dy0, dy0)), A::mul(dz0, dz0)), a.eps2);
+                        double r1 = A::add(A::add(A::add(A::mul(dx1, dx1), A::mul(dy1, dy1)), A::mul(dz1, dz1)), a.eps2);
+                        w0 = A::mul(pj.w, pow(r0, -1.5));
+                        w1 = A::mul(pj.w, pow(r1, -1.5));
+                        if (j == i0) w0 = A::mul(w0, 0.0);
+                        if (j == i1) w1 = A::mul(w1, 0.0);
+                    } else {
+                        double r0 = fma(dz0, dz0, fma(dy0, dy0, fma(dx0, dx0, a.eps2)));
+                        double r1 = fma(dz1, dz1, fma(dy1, dy1, fma(dx1, dx1, a.eps2)));
+                        w0 = pj.w * inv_r3_pos(r0);
+                        w1 = pj.w * inv_r3_pos(r1);
+                    }
+                    fx0 = A::mad(dx0, w0, fx0); fy0 = A::mad(dy0, w0, fy0); fz0 = A::mad(dz0, w0, fz0);
+                    fx1 = A::mad(dx1, w1, fx1); fy1 = A::mad(dy1, w1, fy1); fz1 = A::mad(dz1, w1, fz1);
+                }
+                __syncthreads();
+                dv[0][0] = A::add(dv[0][0], A::mul(A::mul(h, A::mul(a.G, fx0)), c2));
+                dv[0][1] = A::add(dv[0][1], A::mul(A::mul(h, A::mul(a.G, fy0)), c2));
+                dv[0][2] = A::add(dv[0][2], A::mul(A::mul(h, A::mul(a.G, fz0)), c2));
+                dv[1][0] = A::add(dv[1][0], A::mul(A::mul(h, A::mul(a.G, fx1)), c2));
+                dv[1][1] = A::add(dv[1][1], A::mul(A::mul(h, A::mul(a.G, fy1)), c2));
+                dv[1][2] = A::add(dv[1][2], A::mul(A::mul(h, A::mul(a.G, fz1)), c2));
+            }
+            if (c1 != 0.0) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) dq[b][k] = A::add(dq[b][k], A::mul(A::mul(h, vcur[b][k]), c1));
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { q0[b][k] = A::add(q0[b][k], dq[b][k]); v0[b][k] = A::add(v0[b][k], dv[b][k]); }
+            t = A::add(t, h);
+            steps++;
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int i = b ? i1 : i0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                a.y[(long long)(i * 3 + k) * n + sys] = q0[b][k];
+                a.y[(long long)(nb * 3 + i * 3 + k) * n + sys] = v0[b][k];
+            }
+        }
+        if (i0 == 0) {
             a.t[sys] = t;
             a.dt[sys] = dt;
             if (a.steps) a.steps[sys] += steps;
@@ -309,6 +441,20 @@ int dsb_symp_run(dsb_symp_handle h, const dsb_symp_run_args *a, void *stream)
     }
     if (a->n == 0) return DSB_OK;
     DeviceGuard guard(h->device);
+    // two bodies per thread where the body count allows it (DSB_NBODY_X2=0 keeps one body per thread)
+    static const bool x2_on = [] { const char *e = getenv("DSB_NBODY_X2"); return !e || atoi(e) != 0; }();
+    if (x2_on && a->bodies % 2 == 0 && a->bodies >= 8 && a->bodies <= 256) {
+        const int tpb = a->bodies / 2;
+        int spb2 = 128 / tpb;
+        if (spb2 < 1) spb2 = 1;
+        dim3 block2((unsigned)tpb, (unsigned)spb2);
+        unsigned grid2 = (unsigned)((a->n + spb2 - 1) / spb2);
+        size_t smem2 = sizeof(double4) * (size_t)spb2 * a->bodies;
+        if (h->flags & DSB_FLAG_STRICT) nbody_symplectic_kernel_x2<true><<<grid2, block2, smem2, (cudaStream_t)stream>>>(*a, h->tab);
+        else nbody_symplectic_kernel_x2<false><<<grid2, block2, smem2, (cudaStream_t)stream>>>(*a, h->tab);
+        DSB_CUDA_CHECK(cudaGetLastError());
+        return DSB_OK;
+    }
     int spb = 128 / a->bodies;
     if (spb < 1) spb = 1;
     dim3 block((unsigned)a->bodies, (unsigned)spb);

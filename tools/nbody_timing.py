@@ -29,3 +29,6 @@ for method in ("BABS9O7H", "ABAS5O6H"):
     pair_evals = steps * kicks * 64 * 64
     print("%s: %d systems, %.2f ms, %.3e system-steps/s, %.3e pair interactions/s, steps/system %d" %
           (method, systems, ms, steps / ms * 1e3, pair_evals / ms * 1e3, steps // systems))
+    yf = a[-1].y
+    print("   checksum %016x" % (int(yf.view(torch.int64).to(torch.float64).sum().item()) & 0xffffffffffffffff),
+          "sum|y| %.17g" % float(yf.abs().sum()))
