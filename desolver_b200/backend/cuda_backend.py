@@ -329,8 +329,11 @@ def dgemm(A, B, out=None):
 
 class Int8Product:
     """C = A @ B for one fixed float64 CUDA matrix A through the INT8 tensor-core path (dsb_ozaki_*, csrc/ozaki_gemm.cu):
-    the digit planes of A are cut once (again whenever A is modified in place), those of B per product.  `supports(B)`
-    says whether a right-hand side fits the kernel's tiling; buffers grow to the widest B seen."""
+    the digit planes of A are cut once (again whenever A is modified in place), those of B per product.  The kernel tiles
+    M by 128, K by 128 and N by 64; other shapes are ZERO-PADDED to the tiling in buffers of this object (exact: a zero
+    contributes nothing to a row / column maximum nor to a plane product, so the unpadded block of the result is what an
+    unpadded kernel would give) at the price of three extra passes over B and C.  `supports(B)` says whether a right-hand
+    side can be served at all (K <= 32768: INT32 accumulators); buffers grow to the widest B seen."""
 
     def __init__(self, A):
         import torch
@@ -338,12 +341,15 @@ class Int8Product:
             raise ValueError("Int8Product needs a contiguous float64 CUDA matrix")
         self._A = weakref.ref(A)                 # the planes must not keep the matrix alive (rhs_plugins.linear caches us)
         self.M, self.K = A.shape
+        self.Mp, self.Kp = -(-self.M // 128) * 128, -(-self.K // 128) * 128
+        self.padded = (self.Mp, self.Kp) != (self.M, self.K)
         self.S = lib().dsb_ozaki_slices()
         self.sms = torch.cuda.get_device_properties(A.device).multi_processor_count
-        self.a_planes = torch.empty((self.S, self.M, self.K), dtype=torch.int8, device=A.device)
-        self.a_scale = torch.empty(self.M, dtype=torch.float64, device=A.device)
+        self.a_planes = torch.empty((self.S, self.Mp, self.Kp), dtype=torch.int8, device=A.device)
+        self.a_scale = torch.empty(self.Mp, dtype=torch.float64, device=A.device)
+        self._a_pad = torch.zeros((self.Mp, self.Kp), dtype=torch.float64, device=A.device) if self.padded else None
         self._a_version = None
-        self.b_planes = self.b_scale = self.workspace = None
+        self.b_planes = self.b_scale = self.workspace = self._b_pad = self._c_pad = None
         self.columns = 0
 
     @property
@@ -352,11 +358,11 @@ class Int8Product:
 
     def shape_ok(self):
         A = self.A
-        return A is not None and self.M % 128 == 0 and self.K % 128 == 0 and self.K <= 32768 and A.data_ptr() % 16 == 0
+        return A is not None and self.M > 0 and self.K > 0 and self.Kp <= 32768 and A.data_ptr() % 16 == 0
 
     def supports(self, B):
         import torch
-        return (self.shape_ok() and B.ndim == 2 and B.shape[0] == self.K and B.shape[1] % 64 == 0 and B.shape[1] > 0
+        return (self.shape_ok() and B.ndim == 2 and B.shape[0] == self.K and B.shape[1] > 0
                 and B.is_cuda and B.dtype == torch.float64 and B.is_contiguous() and B.device == self.a_planes.device)
 
     def refresh(self):
@@ -368,29 +374,49 @@ class Int8Product:
         A = self.A
         stream = current_stream_ptr(A.device)
         if self._a_version != A._version:
-            check(lib().dsb_ozaki_split_a(A.data_ptr(), self.M, self.K, self.a_planes.data_ptr(), self.a_scale.data_ptr(),
+            src = A
+            if self.padded:
+                self._a_pad[:self.M, :self.K].copy_(A)
+                src = self._a_pad
+            check(lib().dsb_ozaki_split_a(src.data_ptr(), self.Mp, self.Kp, self.a_planes.data_ptr(), self.a_scale.data_ptr(),
                                           stream), "dsb_ozaki_split_a")
             self._a_version = A._version
-        if n > self.columns:
+        np_ = -(-n // 64) * 64
+        if np_ > self.columns:
             dev = A.device
-            self.b_planes = torch.empty((self.S * n * self.K,), dtype=torch.int8, device=dev)
-            self.b_scale = torch.empty(n, dtype=torch.float64, device=dev)
-            self.workspace = torch.empty(n, dtype=torch.int64, device=dev)
-            self.columns = n
+            self.b_planes = torch.empty((self.S * np_ * self.Kp,), dtype=torch.int8, device=dev)
+            self.b_scale = torch.empty(np_, dtype=torch.float64, device=dev)
+            self.workspace = torch.empty(np_, dtype=torch.int64, device=dev)
+            self.columns = np_
+        if n and (self.padded or np_ != n):
+            # staging for a right-hand side / result outside the tiling (allocated here, i.e. before any graph capture)
+            if self._b_pad is None or self._b_pad.numel() < self.Kp * np_:
+                self._b_pad = torch.zeros(self.Kp * self.columns, dtype=torch.float64, device=A.device)
+                self._c_pad = torch.empty(self.Mp * self.columns, dtype=torch.float64, device=A.device)
 
     def __call__(self, B, out=None, dbg_acc=None):
         import torch
         n = B.shape[1]
+        np_ = -(-n // 64) * 64
         self._prepare(n)
+        staged = self.padded or np_ != n
         if out is None:
             out = torch.empty((self.M, n), dtype=torch.float64, device=B.device)
         stream = current_stream_ptr(B.device)
         L = lib()
-        check(L.dsb_ozaki_split_b(B.data_ptr(), self.K, n, self.b_planes.data_ptr(), self.b_scale.data_ptr(),
+        b_src, c_dst = B, out
+        if staged:
+            b_src = self._b_pad[:self.Kp * np_].view(self.Kp, np_)
+            b_src.zero_()
+            b_src[:self.K, :n].copy_(B)
+            c_dst = self._c_pad[:self.Mp * np_].view(self.Mp, np_)
+        check(L.dsb_ozaki_split_b(b_src.data_ptr(), self.Kp, np_, self.b_planes.data_ptr(), self.b_scale.data_ptr(),
                                   self.workspace.data_ptr(), stream), "dsb_ozaki_split_b")
         check(L.dsb_ozaki_gemm(self.a_planes.data_ptr(), self.a_scale.data_ptr(), self.b_planes.data_ptr(), self.b_scale.data_ptr(),
-                               out.data_ptr(), self.M, n, self.K, self.sms, None if dbg_acc is None else dbg_acc.data_ptr(),
+                               c_dst.data_ptr(), self.Mp, np_, self.Kp, self.sms, None if dbg_acc is None else dbg_acc.data_ptr(),
                                stream), "dsb_ozaki_gemm")
+        if staged:
+            out.copy_(c_dst[:self.M, :n])
         return out
 
 

@@ -73,7 +73,7 @@ def linear(t, y, A=None, out=None):
     tensor-core kernels: `linear.gemm = "dmma"` the FP64 DMMA kernel (dsb_dgemm, csrc/dgemm.cu; the rounding sequence of
     an FP64 GEMM, bit-identical to cuBLAS), `linear.gemm = "int8"` the error-free digit-plane product on the INT8 tensor
     cores (dsb_ozaki_*, csrc/ozaki_gemm.cu; closer to the exact product than an FP64 GEMM and 2.4x faster than cuBLAS at
-    4096 x 8192 x 4096; needs n % 128 == 0), `"auto"` (default) the INT8 kernel for large products (n >= 1024 and >= 512
+    4096 x 8192 x 4096; shapes outside its 128 x 64 x 128 tiling are zero-padded in staging buffers), `"auto"` (default) the INT8 kernel for large products (n >= 1024 and >= 512
     columns), the DMMA kernel otherwise.  Numpy arrays, the reference, odd shapes: the array library's matmul;
     `linear.use_library_gemm = True` forces the latter."""
     if (not linear.use_library_gemm and type(y).__module__.split(".")[0] == "torch" and y.is_cuda and y.ndim == 2

@@ -192,12 +192,32 @@ def test_matrix_modified_between_integrations_is_seen_by_replayed_graphs():
     assert float((y2 - fresh[-1].y).abs().max()) <= 1e-10 * float(y2.abs().max())
 
 
-def test_shapes_outside_the_tiling_are_refused():
+@pytest.mark.parametrize("shape", [(128, 96, 128), (130, 70, 200), (1, 1, 1), (257, 64, 129), (1000, 777, 1500)])
+def test_shapes_outside_the_tiling_are_zero_padded_exactly(shape):
+    """M, K not multiples of 128 / N not a multiple of 64: operands are zero-padded to the tiling in staging buffers.  A zero
+    changes no row / column maximum and no plane product, so the result is STILL the numpy model's, bit for bit, on the
+    unpadded shapes."""
+    from oracle import ozaki_model as om
     cb = _cb()
-    A, B = _operands(128, 96, 128)
+    M, N, K = shape
+    A, B = _operands(M, N, K, seed=M + 3 * N + K, spread=1.0)
     prod = cb.Int8Product(A)
-    assert not prod.supports(B)                                                    # N % 64 != 0
-    assert not cb.Int8Product(torch.zeros(64, 64, dtype=torch.float64, device="cuda")).shape_ok()   # M % 128 != 0
+    assert prod.supports(B) and prod.shape_ok()
+    C = prod(B)
+    assert tuple(C.shape) == (M, N)
+    Cm, _ = om.product(A.cpu().numpy(), B.cpu().numpy())
+    assert np.array_equal(C.cpu().numpy(), Cm)
+    ref = A @ B
+    assert float((C - ref).abs().max()) <= 1e-12 * max(1.0, float(ref.abs().max()))
+    out = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+    assert prod(B, out=out) is out and torch.equal(out, C)                        # caller-owned result, second call
+    narrower = B[:, : max(1, N // 2)].contiguous()
+    assert np.array_equal(prod(narrower).cpu().numpy(), om.product(A.cpu().numpy(), narrower.cpu().numpy())[0])
+
+
+def test_kernel_arguments_outside_the_tiling_are_refused():
+    cb = _cb()
+    assert not cb.Int8Product(torch.zeros(64, 40000, dtype=torch.float64, device="cuda")).shape_ok()   # K > 32768
     L = cb.lib()
     assert L.dsb_ozaki_gemm(None, None, None, None, None, 128, 96, 64, 1, None, None) == cb.DSB_ERR_BAD_ARGUMENT
     assert L.dsb_ozaki_gemm(None, None, None, None, None, 128, 64, 65536, 1, None, None) == cb.DSB_ERR_BAD_ARGUMENT
