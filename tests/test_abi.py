@@ -92,3 +92,34 @@ def test_package_has_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         de.OdeSystem(de.rhs_plugins.lorenz, [1.0, 1.0, 20.0])
+
+
+def test_caller_defined_rhs_plugins_build_load_and_register_without_a_gpu():
+    """rhs_plugins.register_device_rhs: nvcc cross-compiles the plug-in for sm_100a (prebuilt by __graft_entry__.build(),
+    found again by its source hash), the plug-in exports the selector, dsb_rhs_register takes it under a user id and
+    refuses the built-in id range."""
+    import ctypes
+    import glob
+    import os
+    import desolver_b200 as de
+    from desolver_b200.backend import cuda_backend as cb
+    fn = de.benchmarks.rossler_plugin()
+    assert fn is de.benchmarks.rossler and fn.plugin_id >= 1000 and fn.device_plugin in de.rhs_plugins.FUSED
+    assert fn.plugin_params == ("a", "b", "c") and fn.plugin_dim == (3,)
+    key = fn.device_plugin.split(":")[-1]
+    so = glob.glob(os.path.join(os.path.dirname(de.__file__), "_plugins", "dsb_rhs_rossler_%s.so" % key))
+    assert len(so) == 1
+    plug = ctypes.CDLL(so[0])
+    assert hasattr(plug, "dsb_user_rhs_select")
+    L = cb.lib()
+    L.dsb_rhs_register.restype = ctypes.c_int
+    L.dsb_rhs_register.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    sel = ctypes.cast(plug.dsb_user_rhs_select, ctypes.c_void_p)
+    assert L.dsb_rhs_register(5, 3, sel) == cb.DSB_ERR_BAD_ARGUMENT and b"dsb_rhs_register" in L.dsb_last_error()
+    assert L.dsb_rhs_register(1999, 0, sel) == cb.DSB_ERR_BAD_ARGUMENT
+    assert L.dsb_rhs_register(1999, 3, None) == cb.DSB_ERR_BAD_ARGUMENT
+    assert L.dsb_rhs_register(1999, 3, sel) == 0
+    assert de.benchmarks.rossler_plugin().plugin_id == fn.plugin_id            # registered once, reused
+    # the generated source is what the docstring promises: the caller's statements inside an Rhs struct of the library
+    cu = open(so[0][:-3] + ".cu").read()
+    assert "struct UserRhs" in cu and "dy[2] = p[1] + y[2] * (y[0] - p[2]);" in cu and "select_fused<dsb::UserRhs>" in cu
