@@ -1,9 +1,25 @@
 #!/usr/bin/env python
 """Differential run: the UNMODIFIED reference (numpy backend, from baseline/_ref) and desolver_b200 (cuda:0) solve the same
-randomly drawn problems side by side on the GPU box; accepted-step counts, step times, final states, nfev, dense-output
-queries, events and solve_ivp(t_eval) are compared case by case.
+randomly drawn problems side by side on the GPU box, case by case:
 
-    python tools/differential_vs_reference.py [--seed 0] [--cases 200] > profiles/round2_differential_vs_reference.json
+  adaptive / fixed / symplectic / backward   one system, every explicit method family, plugin or torch-callable right-hand
+                                             side, both arithmetic flavours: steps, step times, states, nfev, and the
+                                             attributes a caller reads afterwards (dt, success, integration_status, ...)
+  dense                                      + dense-output values, derivatives, time slices, nearest-step lookups
+  continue / switch                          integrate(t1); integrate(); reset(); method / tolerance / dt / tf changes
+                                             between calls; per-component tolerances
+  solve_ivp / richardson                     the scipy-style front end (t_eval, first_step, max_step, args); Richardson
+                                             wrappers over fixed-step and adaptive basis schemes
+  shapes                                     matrix-valued states, 2000-component systems with the reference's global
+                                             norm, non-zero start times, step-clamping callbacks
+  ensemble / ensemble2 / events_ens          ensembles (fused and stage-level kernels, two legs, dense queries, events)
+                                             against ONE reference OdeSystem per trajectory
+  events / events2                           recorded and terminal events of arbitrary callables, with their states
+  nbody                                      softened N-body through the fused symplectic kernel / the stage-level kernels
+
+A case that deviates in the fast arithmetic flavour is re-run in STRICT arithmetic (strict_rerun_*).
+
+    python tools/differential_vs_reference.py [--seed 0] [--cases 840] [--only kind,kind] > profiles/round2_differential_vs_reference.json
 
 TEST / MEASUREMENT INFRASTRUCTURE: needs baseline/_ref (baseline/install_reference.py) and a GPU.  `autoray`, which the
 offline image lacks, is the dispatch-only stand-in oracle/refshim."""
