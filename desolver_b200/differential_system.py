@@ -737,9 +737,12 @@ class OdeSystem(object):
     def events_dict(self):
         """{event function: StateTuple(t = its times, y = its states, event)} of a single system (reference `:573-593`)."""
         torch = _torch()
-        found = list(self.events) if not self.ensemble else None
-        if found is None:
-            raise NotImplementedError("events_dict is the single-system view; an ensemble's events are in `a.events` (EventLog)")
+        if self.ensemble:
+            # an ensemble's records live in ONE EventLog (per-trajectory counts, times, states, event indices on the
+            # device): every event function maps to it; `log.for_trajectory(i)` is the reference's list for trajectory i
+            log = self.events
+            return {ev: log for ev in getattr(log, "events", [])}
+        found = list(self.events)
         out = {}
         for ev in {id(e.event): e.event for e in found}.values():
             mine = [e for e in found if e.event is ev]
